@@ -1,0 +1,467 @@
+// orbx_extract.cu — host side of the ORB extractor behind the C ABI (include/orbx.h).
+//
+// Mirrors the reference's ORBextractor object (include/ORBextractor.h:43-109): the constructor
+// tables (src/ORBextractor.cc:408-468) are computed here on the host with the same float/double
+// expressions; everything per-image runs on the device (orbx_extract_kernels.cu).
+#include "orbx_extract.cuh"
+#include <vector>
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+int orbx_extract_configure(int nodeCap, int fastTileBytes);
+size_t orbx_octree_smem_bytes(int nodeCap);
+size_t orbx_fast_smem_bytes(int fastTileBytes);
+int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, orbx_keypoint* d_kps, uint8_t* d_desc,
+                        int cap, int* d_n, int* d_mono);
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+static inline int cv_floor_d(double v) { int i = (int)v; return i - (i > v); }
+
+struct orbx_ext {
+  orbx_ctx* ctx = nullptr;
+  cudaStream_t stream = nullptr;
+  int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
+  double scaleFactor = 0;
+  int maxW = 0, maxH = 0, maxB = 0;
+  std::vector<float> scale, invScale, sigma2, invSigma2;
+  std::vector<int> nFeat;
+  int maxKeypoints = 0;
+
+  // geometry currently configured
+  int curW = -1, curH = -1, curStride = -1;
+  ExtractParams P{};
+  // device allocations (sized for maxW x maxH x maxB at creation)
+  uint8_t* d_pyr = nullptr;      // levels 0..L-1 + blurred levels
+  size_t pyrBytes = 0;
+  int16_t* d_tab = nullptr;
+  size_t tabElems = 0;
+  uint32_t* d_cand = nullptr;
+  uint16_t* d_keyNode = nullptr;
+  size_t candElems = 0;
+  uint2* d_sel = nullptr;
+  size_t selElems = 0;
+  int* d_counts = nullptr;       // candN | selN | selLap | err
+  orbx_keypoint* d_kps = nullptr;
+  uint8_t* d_desc = nullptr;
+  int* d_nOut = nullptr;         // nOut[maxB] | mono[maxB]
+  // pinned staging for the host-pointer API
+  uint8_t* h_img = nullptr;
+  size_t hImgBytes = 0;
+  orbx_keypoint* h_kps = nullptr;
+  uint8_t* h_desc = nullptr;
+  int* h_nOut = nullptr;
+  int lastB = 0;
+  bool level0External = false;
+};
+
+static void level_dims(const orbx_ext* e, int w, int h, int l, int* lw, int* lh) {
+  const float s = e->invScale[l];  // src/ORBextractor.cc:1162-1163
+  *lw = cv_round_f((float)w * s);
+  *lh = cv_round_f((float)h * s);
+}
+
+// Validity of an image size: the reference divides by nCols/nRows/nIni, which must be >= 1 on
+// every level (src/ORBextractor.cc:779-782, :541).
+static bool size_supported(const orbx_ext* e, int w, int h) {
+  for (int l = 0; l < e->nlevels; ++l) {
+    int lw, lh;
+    level_dims(e, w, h, l, &lw, &lh);
+    if (lw - 32 < 30 || lh - 32 < 30) return false;
+    if ((int)std::round((float)(lw - 32) / (float)(lh - 32)) < 1) return false;
+    if (lw > 4095 + 16 || lh > 4095 + 16) return false;  // 12-bit packed candidate coordinates
+  }
+  return true;
+}
+
+static size_t pitch_for(int w) { return align_up((size_t)w + 4, 64); }
+
+// Fill P.lv[] geometry for (w,h); level-0 pointer/pitch are set by the caller.
+static int configure_geometry(orbx_ext* e, int w, int h, int B) {
+  ExtractParams& P = e->P;
+  P.nlevels = e->nlevels;
+  P.iniTh = e->iniTh;
+  P.minTh = e->minTh;
+  P.nodeCap = 0;
+  size_t off = 0;
+  int tile = 0, btile = 0, cand = 0, sel = 0, fastBytes = 0;
+  size_t tab = 0;
+  std::vector<int16_t> htab;
+  for (int l = 0; l < e->nlevels; ++l) {
+    LevelParams& L = P.lv[l];
+    level_dims(e, w, h, l, &L.w, &L.h);
+    L.pitch = (int)pitch_for(L.w);
+    L.imgStride = (size_t)L.pitch * L.h;
+    L.pyr = e->d_pyr + off;
+    off += align_up(L.imgStride * e->maxB, 256);
+    L.maxBX = L.w - ORBX_EDGE + 3;
+    L.maxBY = L.h - ORBX_EDGE + 3;
+    const float width = (float)(L.maxBX - ORBX_MINB), height = (float)(L.maxBY - ORBX_MINB);
+    L.nCols = (int)(width / 30.f);
+    L.nRows = (int)(height / 30.f);
+    L.wCell = (int)std::ceil(width / (float)L.nCols);
+    L.hCell = (int)std::ceil(height / (float)L.nRows);
+    L.tilesPerRow = div_up(L.nCols, ORBX_FAST_CELLS);
+    L.tileStart = tile;
+    tile += L.tilesPerRow * L.nRows;
+    const int tw = std::min(ORBX_FAST_CELLS, L.nCols) * L.wCell + 6;
+    fastBytes = std::max(fastBytes, (int)align_up((size_t)((tw + 3) & ~3) * (L.hCell + 6), 16));
+    L.blurTilesX = div_up(L.w, ORBX_BLUR_TW);
+    L.blurTilesY = div_up(L.h, ORBX_BLUR_TH);
+    L.blurTileStart = btile;
+    btile += L.blurTilesX * L.blurTilesY;
+    L.nFeat = e->nFeat[l];
+    L.nIni = (int)std::round(width / height);
+    L.hX = width / (float)L.nIni;
+    L.candOfs = cand;
+    L.candCap = (int)((size_t)L.w * L.h * 3 / 10) + 64;
+    cand += L.candCap;
+    L.selOfs = sel;
+    L.selCap = L.nFeat + 4 * L.nIni + 8;
+    sel += L.selCap;
+    P.nodeCap = std::max(P.nodeCap, L.selCap);
+    L.scale = e->scale[l];
+    L.kpSize = (float)(int)(31 * e->scale[l]);  // src/ORBextractor.cc:862
+  }
+  for (int l = 0; l < e->nlevels; ++l) {
+    LevelParams& L = P.lv[l];
+    L.blur = e->d_pyr + off;
+    off += align_up(L.imgStride * e->maxB, 256);
+  }
+  if (off > e->pyrBytes || (size_t)cand > e->candElems / e->maxB || (size_t)sel > e->selElems / e->maxB) {
+    orbx_set_error("orbx: internal sizing error (pyr %zu/%zu cand %d sel %d)", off, e->pyrBytes, cand, sel);
+    return ORBX_ECAP;
+  }
+  // resize tables (cv::resize INTER_LINEAR 8U; see oracle/ork_primitives.cpp for the derivation)
+  for (int l = 1; l < e->nlevels; ++l) {
+    LevelParams& L = P.lv[l];
+    const LevelParams& S = P.lv[l - 1];
+    const double sx = 1.0 / ((double)L.w / S.w), sy = 1.0 / ((double)L.h / S.h);
+    L.tabX = (int)htab.size();
+    htab.resize(htab.size() + 3 * (size_t)L.w);
+    int16_t* tx = htab.data() + L.tabX;
+    for (int dx = 0; dx < L.w; ++dx) {
+      float fx = (float)((dx + 0.5) * sx - 0.5);
+      int s = cv_floor_d(fx);
+      fx -= s;
+      if (s < 0) { fx = 0; s = 0; }
+      if (s >= S.w - 1) { fx = 0; s = S.w - 1; }
+      tx[dx] = (int16_t)s;
+      tx[L.w + dx] = (int16_t)cv_round_f((1.f - fx) * 2048.f);
+      tx[2 * L.w + dx] = (int16_t)cv_round_f(fx * 2048.f);
+    }
+    L.tabY = (int)htab.size();
+    htab.resize(htab.size() + 4 * (size_t)L.h);
+    int16_t* ty = htab.data() + L.tabY;
+    for (int dy = 0; dy < L.h; ++dy) {
+      float fy = (float)((dy + 0.5) * sy - 0.5);
+      int s = cv_floor_d(fy);
+      fy -= s;
+      ty[dy] = (int16_t)std::min(std::max(s, 0), S.h - 1);
+      ty[L.h + dy] = (int16_t)std::min(std::max(s + 1, 0), S.h - 1);
+      ty[2 * L.h + dy] = (int16_t)cv_round_f((1.f - fy) * 2048.f);
+      ty[3 * L.h + dy] = (int16_t)cv_round_f(fy * 2048.f);
+    }
+  }
+  if (htab.size() > e->tabElems) {
+    orbx_set_error("orbx: resize table overflow");
+    return ORBX_ECAP;
+  }
+  if (!htab.empty())
+    ORBX_CUDA(cudaMemcpyAsync(e->d_tab, htab.data(), htab.size() * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
+  ORBX_CUDA(cudaStreamSynchronize(e->stream));  // htab is a local
+  P.tab = e->d_tab;
+  P.candPerImage = cand;
+  P.selPerImage = sel;
+  P.totalFastTiles = tile;
+  P.totalBlurTiles = btile;
+  P.fastTileBytes = fastBytes;
+  P.cand = e->d_cand;
+  P.keyNode = e->d_keyNode;
+  P.sel = e->d_sel;
+  P.candN = e->d_counts;
+  P.selN = e->d_counts + e->maxB * e->nlevels;
+  P.selLap = e->d_counts + 2 * e->maxB * e->nlevels;
+  P.err = e->d_counts + 3 * e->maxB * e->nlevels;
+  if (orbx_fast_smem_bytes(fastBytes) > 200 * 1024 || orbx_octree_smem_bytes(P.nodeCap) > 200 * 1024) {
+    orbx_set_error("orbx: shared-memory budget exceeded (fast %zu, octree %zu)", orbx_fast_smem_bytes(fastBytes),
+                   orbx_octree_smem_bytes(P.nodeCap));
+    return ORBX_ECAP;
+  }
+  int rc = orbx_extract_configure(P.nodeCap, fastBytes);
+  if (rc != ORBX_OK) return rc;
+  e->curW = w;
+  e->curH = h;
+  (void)B;
+  return ORBX_OK;
+}
+
+extern "C" {
+
+orbx_ext* orbx_extractor_create(orbx_ctx* ctx, int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh,
+                                int max_w, int max_h, int max_batch) {
+  if (!ctx || nfeatures < 1 || nlevels < 1 || nlevels > ORBX_MAX_LEVELS || !(scaleFactor > 1.f) || iniTh < 1 ||
+      minTh < 1 || iniTh > 254 || minTh > iniTh || max_w < 1 || max_h < 1 || max_batch < 1) {
+    orbx_set_error("orbx_extractor_create: invalid argument");
+    return nullptr;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+  orbx_ext* e = new orbx_ext();
+  e->ctx = ctx;
+  e->nfeatures = nfeatures;
+  e->nlevels = nlevels;
+  e->iniTh = iniTh;
+  e->minTh = minTh;
+  e->scaleFactor = scaleFactor;  // float ctor argument stored in a double member (ORBextractor.h:97)
+  e->maxW = max_w;
+  e->maxH = max_h;
+  e->maxB = max_batch;
+  // --- src/ORBextractor.cc:413-444 ---
+  e->scale.assign(nlevels, 1.f);
+  e->sigma2.assign(nlevels, 1.f);
+  for (int i = 1; i < nlevels; ++i) {
+    e->scale[i] = (float)(e->scale[i - 1] * e->scaleFactor);
+    e->sigma2[i] = e->scale[i] * e->scale[i];
+  }
+  e->invScale.resize(nlevels);
+  e->invSigma2.resize(nlevels);
+  for (int i = 0; i < nlevels; ++i) {
+    e->invScale[i] = 1.0f / e->scale[i];
+    e->invSigma2[i] = 1.0f / e->sigma2[i];
+  }
+  e->nFeat.resize(nlevels);
+  {
+    float factor = (float)(1.0f / e->scaleFactor);
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; ++l) {
+      e->nFeat[l] = cv_round_f(nDesired);
+      sum += e->nFeat[l];
+      nDesired *= factor;
+    }
+    e->nFeat[nlevels - 1] = std::max(nfeatures - sum, 0);
+  }
+  if (!size_supported(e, max_w, max_h)) {
+    orbx_set_error("orbx_extractor_create: %dx%d too small/elongated for %d levels at scale %.3f", max_w, max_h,
+                   nlevels, scaleFactor);
+    delete e;
+    return nullptr;
+  }
+  // --- device memory, sized for the maximum geometry ---
+  size_t pyr = 0, cand = 0, sel = 0, tab = 0;
+  for (int l = 0; l < nlevels; ++l) {
+    int lw, lh;
+    level_dims(e, max_w, max_h, l, &lw, &lh);
+    pyr += 2 * align_up(pitch_for(lw) * (size_t)lh * max_batch, 256);
+    cand += (size_t)lw * lh * 3 / 10 + 64;
+    const int nIni = std::max(1, (int)std::round((float)(lw - 32) / (float)(lh - 32)));
+    sel += e->nFeat[l] + 4 * nIni + 8;
+    tab += 3 * (size_t)lw + 4 * (size_t)lh;
+  }
+  // smaller images than max may have a larger aspect-driven nIni; keep some slack
+  sel += 16 * nlevels;
+  e->maxKeypoints = (int)sel;
+  e->pyrBytes = pyr + 4096;
+  e->candElems = cand * max_batch;
+  e->selElems = sel * max_batch;
+  e->tabElems = tab + 64;
+  bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_pyr, e->pyrBytes) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_tab, e->tabElems * sizeof(int16_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_cand, e->candElems * sizeof(uint32_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_keyNode, e->candElems * sizeof(uint16_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_sel, e->selElems * sizeof(uint2)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_counts, (3 * (size_t)max_batch * nlevels + 16) * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_kps, (size_t)max_batch * sel * sizeof(orbx_keypoint)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_desc, (size_t)max_batch * sel * 32) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_nOut, 2 * (size_t)max_batch * sizeof(int)) == cudaSuccess;
+  e->hImgBytes = pitch_for(max_w) * (size_t)max_h * max_batch;
+  ok = ok && cudaMallocHost(&e->h_img, e->hImgBytes) == cudaSuccess;
+  ok = ok && cudaMallocHost(&e->h_kps, (size_t)max_batch * sel * sizeof(orbx_keypoint)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&e->h_desc, (size_t)max_batch * sel * 32) == cudaSuccess;
+  ok = ok && cudaMallocHost(&e->h_nOut, (2 * (size_t)max_batch + 4) * sizeof(int)) == cudaSuccess;
+  if (ok) ok = cudaMemset(e->d_counts, 0, (3 * (size_t)max_batch * nlevels + 16) * sizeof(int)) == cudaSuccess;
+  if (!ok) {
+    orbx_set_error("orbx_extractor_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    orbx_extractor_destroy(e);
+    return nullptr;
+  }
+  return e;
+}
+
+void orbx_extractor_destroy(orbx_ext* e) {
+  if (!e) return;
+  cudaSetDevice(e->ctx->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaFree(e->d_pyr);
+  cudaFree(e->d_tab);
+  cudaFree(e->d_cand);
+  cudaFree(e->d_keyNode);
+  cudaFree(e->d_sel);
+  cudaFree(e->d_counts);
+  cudaFree(e->d_kps);
+  cudaFree(e->d_desc);
+  cudaFree(e->d_nOut);
+  cudaFreeHost(e->h_img);
+  cudaFreeHost(e->h_kps);
+  cudaFreeHost(e->h_desc);
+  cudaFreeHost(e->h_nOut);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int orbx_extractor_levels(const orbx_ext* e) { return e ? e->nlevels : ORBX_EINVAL; }
+
+int orbx_extractor_scale_tables(const orbx_ext* e, float* scale, float* inv, float* s2, float* is2) {
+  if (!e) return ORBX_EINVAL;
+  for (int l = 0; l < e->nlevels; ++l) {
+    if (scale) scale[l] = e->scale[l];
+    if (inv) inv[l] = e->invScale[l];
+    if (s2) s2[l] = e->sigma2[l];
+    if (is2) is2[l] = e->invSigma2[l];
+  }
+  return e->nlevels;
+}
+
+int orbx_extractor_features_per_level(const orbx_ext* e, int* n) {
+  if (!e || !n) return ORBX_EINVAL;
+  for (int l = 0; l < e->nlevels; ++l) n[l] = e->nFeat[l];
+  return e->nlevels;
+}
+
+int orbx_extractor_max_keypoints(const orbx_ext* e) { return e ? e->maxKeypoints : ORBX_EINVAL; }
+void* orbx_extractor_stream(orbx_ext* e) { return e ? (void*)e->stream : nullptr; }
+
+// shared tail of the three extract entry points: geometry, level-0 binding, launch
+static int run_device(orbx_ext* e, int B, const uint8_t* d_level0, int w, int h, int stride, int lap0, int lap1,
+                      orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int* d_n, int* d_mono) {
+  if (w > e->maxW || h > e->maxH || B > e->maxB || B < 1) {
+    orbx_set_error("orbx_extract: %dx%d x%d exceeds the extractor's capacity %dx%d x%d", w, h, B, e->maxW, e->maxH,
+                   e->maxB);
+    return ORBX_EINVAL;
+  }
+  if (!size_supported(e, w, h)) {
+    orbx_set_error("orbx_extract: image %dx%d unsupported (a pyramid level is narrower than one FAST cell)", w, h);
+    return ORBX_EINVAL;
+  }
+  if (w != e->curW || h != e->curH) {
+    int rc = configure_geometry(e, w, h, B);
+    if (rc != ORBX_OK) return rc;
+  }
+  ExtractParams& P = e->P;
+  P.B = B;
+  P.lap0 = lap0;
+  P.lap1 = lap1;
+  P.lv[0].pyr = const_cast<uint8_t*>(d_level0);
+  P.lv[0].pitch = stride;
+  P.lv[0].imgStride = (size_t)stride * h;
+  e->lastB = B;
+  return orbx_extract_launch(e->ctx, e->stream, P, d_kps, d_desc, cap, d_n, d_mono);
+}
+
+int orbx_extract_batch_device(orbx_ext* e, int B, const uint8_t* d_imgs, int w, int h, int stride, int lap0, int lap1,
+                              orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int* d_n_out, int* d_mono_out) {
+  if (!e || !d_imgs || !d_kps || !d_desc || !d_n_out || !d_mono_out || cap < 1) return ORBX_EINVAL;
+  if (w <= 0 || h <= 0) return ORBX_EMPTY;
+  if (stride < w) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(e->ctx->device));
+  e->level0External = true;
+  return run_device(e, B, d_imgs, w, h, stride, lap0, lap1, d_kps, d_desc, cap, d_n_out, d_mono_out);
+}
+
+int orbx_extract_batch(orbx_ext* e, int B, const uint8_t* const* imgs, int w, int h, int stride, int lap0, int lap1,
+                       orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
+  if (!e || !imgs || B < 1) return ORBX_EINVAL;
+  if (w <= 0 || h <= 0) return ORBX_EMPTY;
+  for (int b = 0; b < B; ++b)
+    if (!imgs[b]) return ORBX_EMPTY;
+  if (stride < w || !kps || !desc || !n_out || cap < 1) return ORBX_EINVAL;
+  if (B > e->maxB || w > e->maxW || h > e->maxH) {
+    orbx_set_error("orbx_extract_batch: request exceeds extractor capacity");
+    return ORBX_EINVAL;
+  }
+  ORBX_CUDA(cudaSetDevice(e->ctx->device));
+  // stage into pinned memory with the device pitch, one H2D copy for the whole batch
+  const int pitch = (int)pitch_for(w);
+  for (int b = 0; b < B; ++b)
+    for (int y = 0; y < h; ++y)
+      std::memcpy(e->h_img + ((size_t)b * h + y) * pitch, imgs[b] + (size_t)y * stride, w);
+  // level-0 lives at the start of d_pyr (configure_geometry lays levels out in order)
+  uint8_t* d_l0 = e->d_pyr;
+  ORBX_CUDA(cudaMemcpyAsync(d_l0, e->h_img, (size_t)B * h * pitch, cudaMemcpyHostToDevice, e->stream));
+  e->level0External = false;
+  const int dcap = e->maxKeypoints;
+  int rc = run_device(e, B, d_l0, w, h, pitch, lap0, lap1, e->d_kps, e->d_desc, dcap, e->d_nOut, e->d_nOut + e->maxB);
+  if (rc != ORBX_OK) return rc;
+  ORBX_CUDA(cudaMemcpyAsync(e->h_nOut, e->d_nOut, sizeof(int) * 2 * e->maxB, cudaMemcpyDeviceToHost, e->stream));
+  ORBX_CUDA(cudaMemcpyAsync(e->h_nOut + 2 * e->maxB, e->P.err, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  ORBX_CUDA(cudaMemcpyAsync(e->h_kps, e->d_kps, sizeof(orbx_keypoint) * (size_t)B * dcap, cudaMemcpyDeviceToHost,
+                            e->stream));
+  ORBX_CUDA(cudaMemcpyAsync(e->h_desc, e->d_desc, (size_t)32 * B * dcap, cudaMemcpyDeviceToHost, e->stream));
+  ORBX_CUDA(cudaStreamSynchronize(e->stream));
+  if (e->h_nOut[2 * e->maxB] != 0) {
+    orbx_set_error("orbx_extract: device capacity overflow (code %d)", e->h_nOut[2 * e->maxB]);
+    ORBX_CUDA(cudaMemsetAsync(e->P.err, 0, sizeof(int), e->stream));
+    return ORBX_ECAP;
+  }
+  for (int b = 0; b < B; ++b) {
+    const int n = e->h_nOut[b];
+    if (n > cap) {
+      orbx_set_error("orbx_extract: %d keypoints exceed caller capacity %d", n, cap);
+      return ORBX_ECAP;
+    }
+    std::memcpy(kps + (size_t)b * cap, e->h_kps + (size_t)b * dcap, sizeof(orbx_keypoint) * n);
+    std::memcpy(desc + (size_t)b * cap * 32, e->h_desc + (size_t)b * dcap * 32, (size_t)32 * n);
+    n_out[b] = n;
+    if (mono_out) mono_out[b] = e->h_nOut[e->maxB + b];
+  }
+  return ORBX_OK;
+}
+
+int orbx_extract(orbx_ext* e, const uint8_t* img, int w, int h, int stride, int lap0, int lap1, orbx_keypoint* kps,
+                 uint8_t* desc, int cap, int* n_out, int* mono_out) {
+  if (!e) return ORBX_EINVAL;
+  if (!img || w <= 0 || h <= 0) return ORBX_EMPTY;
+  int n = 0, mono = 0;
+  int rc = orbx_extract_batch(e, 1, &img, w, h, stride, lap0, lap1, kps, desc, cap, &n, &mono);
+  if (n_out) *n_out = n;
+  if (mono_out) *mono_out = mono;
+  return rc;
+}
+
+int orbx_pyramid_level(orbx_ext* e, int b, int level, uint8_t* dst, int dst_stride, int* w_out, int* h_out) {
+  if (!e || e->curW < 0 || level < 0 || level >= e->nlevels || b < 0 || b >= e->lastB) return ORBX_EINVAL;
+  const LevelParams& L = e->P.lv[level];
+  if (w_out) *w_out = L.w;
+  if (h_out) *h_out = L.h;
+  if (!dst) return ORBX_OK;
+  if (dst_stride < L.w) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(e->ctx->device));
+  ORBX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, L.pyr + (size_t)b * L.imgStride, L.pitch, L.w, L.h,
+                              cudaMemcpyDeviceToHost, e->stream));
+  ORBX_CUDA(cudaStreamSynchronize(e->stream));
+  return ORBX_OK;
+}
+
+int orbx_debug_candidates(orbx_ext* e, int b, int level, int16_t* xy, uint8_t* score, int cap, int* n_out) {
+  if (!e || e->curW < 0 || level < 0 || level >= e->nlevels || b < 0 || b >= e->lastB) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(e->ctx->device));
+  const LevelParams& L = e->P.lv[level];
+  int n = 0;
+  ORBX_CUDA(cudaMemcpy(&n, e->P.candN + b * e->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  n = std::min(n, L.candCap);
+  if (n_out) *n_out = n;
+  if (n > cap) return ORBX_ECAP;
+  std::vector<uint32_t> tmp(n);
+  if (n)
+    ORBX_CUDA(cudaMemcpy(tmp.data(), e->P.cand + (size_t)b * e->P.candPerImage + L.candOfs, sizeof(uint32_t) * n,
+                         cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) {
+    xy[2 * i] = (int16_t)(tmp[i] & 0xfff);
+    xy[2 * i + 1] = (int16_t)((tmp[i] >> 12) & 0xfff);
+    score[i] = (uint8_t)(tmp[i] >> 24);
+  }
+  return ORBX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// orbx_extract.cuh — device-visible parameter blocks of the batched ORB extractor.
+#pragma once
+#include "orbx_common.cuh"
+
+#define ORBX_EDGE 19          // EDGE_THRESHOLD, src/ORBextractor.cc:72
+#define ORBX_MINB 16          // minBorderX = EDGE_THRESHOLD-3, src/ORBextractor.cc:771
+#define ORBX_FAST_CELLS 8     // cells per FAST tile (one cell row x up to 8 cells)
+#define ORBX_BLUR_TW 128
+#define ORBX_BLUR_TH 16
+
+// One pyramid level of a batch of B equally sized images.
+struct LevelParams {
+  int w, h, pitch;                 // level size in pixels, row pitch in bytes
+  size_t imgStride;                // bytes between consecutive images of the batch
+  uint8_t* pyr;                    // un-blurred level (level 0 may alias the caller's input)
+  uint8_t* blur;                   // 7x7 sigma-2 blurred level
+  // FAST cell tiling (src/ORBextractor.cc:771-804)
+  int nCols, nRows, wCell, hCell, maxBX, maxBY;
+  int tileStart, tilesPerRow;      // flattened FAST tile ids of this level
+  int blurTileStart, blurTilesX, blurTilesY;
+  // resize tables (level l from l-1): offsets into ExtractParams::tab (int16 units)
+  int tabX, tabY;
+  // quadtree
+  int nFeat, nIni;
+  float hX;
+  int candOfs, candCap;            // slice of the per-image candidate buffer
+  int selOfs, selCap;              // slice of the per-image selected-keypoint buffer
+  float scale, kpSize;
+};
+
+struct ExtractParams {
+  int nlevels, B;
+  int iniTh, minTh;
+  int lap0, lap1;
+  int candPerImage, selPerImage;   // per-image strides of cand / sel buffers
+  int totalFastTiles, totalBlurTiles;
+  int nodeCap;
+  int fastTileBytes;               // bytes of one FAST shared-memory plane (max over levels, 16-aligned)
+  const int16_t* tab;              // resize coefficient tables
+  uint32_t* cand;                  // [B][candPerImage] packed x | y<<12 | score<<24 (coords rel. to minBorder)
+  int* candN;                      // [B][nlevels]
+  uint16_t* keyNode;               // [B][candPerImage] quadtree scratch
+  uint2* sel;                      // [B][selPerImage] packed selected keypoints
+  int* selN;                       // [B][nlevels]
+  int* selLap;                     // [B][nlevels] number of "lapping" keypoints per level
+  int* err;                        // device error flag (capacity overflow)
+  LevelParams lv[ORBX_MAX_LEVELS];
+};

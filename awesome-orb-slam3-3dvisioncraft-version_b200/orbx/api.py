@@ -1,0 +1,223 @@
+"""ctypes binding of the C ABI in include/orbx.h."""
+import ctypes as C
+import os
+import re
+import subprocess
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(_PKG)
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4")])
+
+
+class OrbxError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_PKG, "liborbx.so")
+
+
+def build_library(force=False):
+    """nvcc-compile every kernel for sm_100a into liborbx.so (in-tree)."""
+    args = ["make", "-C", _PKG, "-s"]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args + ["liborbx.so"])
+    return lib_path()
+
+
+def declared_symbols():
+    """Every function include/orbx.h declares (used by the CPU-side ABI test)."""
+    txt = open(os.path.join(_ROOT, "include", "orbx.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(orbx_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load_library():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise OrbxError("liborbx.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(p)
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    L.orbx_abi_version.restype = i
+    L.orbx_last_error.restype = C.c_char_p
+    L.orbx_create.restype = vp
+    L.orbx_create.argtypes = [i]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_stream.restype = vp
+    L.orbx_stream.argtypes = [vp]
+    L.orbx_synchronize.argtypes = [vp]
+    L.orbx_launch_count.restype = C.c_uint64
+    L.orbx_launch_count.argtypes = [vp]
+    L.orbx_extractor_create.restype = vp
+    L.orbx_extractor_create.argtypes = [vp, i, f, i, i, i, i, i, i]
+    L.orbx_extractor_destroy.argtypes = [vp]
+    L.orbx_extractor_levels.argtypes = [vp]
+    L.orbx_extractor_scale_tables.argtypes = [vp, vp, vp, vp, vp]
+    L.orbx_extractor_features_per_level.argtypes = [vp, vp]
+    L.orbx_extractor_max_keypoints.argtypes = [vp]
+    L.orbx_extractor_stream.restype = vp
+    L.orbx_extractor_stream.argtypes = [vp]
+    L.orbx_extract.argtypes = [vp, vp, i, i, i, i, i, vp, vp, i, vp, vp]
+    L.orbx_extract_batch.argtypes = [vp, i, vp, i, i, i, i, i, vp, vp, i, vp, vp]
+    L.orbx_extract_batch_device.argtypes = [vp, i, vp, i, i, i, i, i, vp, vp, i, vp, vp]
+    L.orbx_pyramid_level.argtypes = [vp, i, i, vp, i, vp, vp]
+    L.orbx_debug_candidates.argtypes = [vp, i, i, vp, vp, i, vp]
+    _LIB = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load_library().orbx_last_error().decode(errors="replace")
+        raise OrbxError("%s failed with status %d: %s" % (what, rc, msg))
+
+
+class Context:
+    """orbx_ctx: one per (process, device)."""
+
+    def __init__(self, device=0):
+        L = load_library()
+        self.h = L.orbx_create(device)
+        if not self.h:
+            raise OrbxError("orbx_create(%d): %s" % (device, L.orbx_last_error().decode(errors="replace")))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            load_library().orbx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(load_library().orbx_synchronize(self.h), "orbx_synchronize")
+
+    @property
+    def launches(self):
+        return int(load_library().orbx_launch_count(self.h))
+
+
+class ORBextractor:
+    """Mirror of ORB_SLAM3::ORBextractor (include/ORBextractor.h:43-109).
+
+    __call__(image, lapping) -> (monoIndex_or_-1, keypoints, descriptors) follows operator()
+    (src/ORBextractor.cc:1074-1156): an empty image returns -1 and empty outputs.
+    """
+
+    def __init__(self, ctx, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7,
+                 max_w=752, max_h=480, max_batch=1):
+        L = load_library()
+        self.ctx = ctx
+        self.h = L.orbx_extractor_create(ctx.h, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_w,
+                                         max_h, max_batch)
+        if not self.h:
+            raise OrbxError("orbx_extractor_create: " + L.orbx_last_error().decode(errors="replace"))
+        self.nfeatures, self.nlevels, self.max_batch = nfeatures, nlevels, max_batch
+        t = [np.empty(nlevels, np.float32) for _ in range(4)]
+        L.orbx_extractor_scale_tables(self.h, *[_p(a) for a in t])
+        self.mvScaleFactor, self.mvInvScaleFactor, self.mvLevelSigma2, self.mvInvLevelSigma2 = t
+        nf = np.empty(nlevels, np.int32)
+        L.orbx_extractor_features_per_level(self.h, _p(nf))
+        self.mnFeaturesPerLevel = nf
+        self.cap = L.orbx_extractor_max_keypoints(self.h)
+        self.stream = L.orbx_extractor_stream(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            load_library().orbx_extractor_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # reference getters (include/ORBextractor.h:59-81)
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactors(self):
+        return self.mvScaleFactor
+
+    def GetInverseScaleFactors(self):
+        return self.mvInvScaleFactor
+
+    def GetScaleSigmaSquares(self):
+        return self.mvLevelSigma2
+
+    def GetInverseScaleSigmaSquares(self):
+        return self.mvInvLevelSigma2
+
+    def __call__(self, image, vLappingArea=(0, 0)):
+        if image is None or image.size == 0:
+            return -1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        image = np.ascontiguousarray(image, np.uint8)
+        kps = np.empty(self.cap, KP_DTYPE)
+        desc = np.empty((self.cap, 32), np.uint8)
+        n, mono = C.c_int(0), C.c_int(0)
+        rc = load_library().orbx_extract(self.h, _p(image), image.shape[1], image.shape[0], image.strides[0],
+                                         int(vLappingArea[0]), int(vLappingArea[1]), _p(kps), _p(desc), self.cap,
+                                         C.byref(n), C.byref(mono))
+        if rc == -1:
+            return -1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        _check(rc, "orbx_extract")
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images, vLappingArea=(0, 0)):
+        """images: sequence of equally sized uint8 arrays -> list of (monoIndex, kps, desc)."""
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        B = len(imgs)
+        h, w = imgs[0].shape
+        assert all(im.shape == (h, w) for im in imgs)
+        ptrs = (C.c_void_p * B)(*[im.ctypes.data for im in imgs])
+        kps = np.empty((B, self.cap), KP_DTYPE)
+        desc = np.empty((B, self.cap, 32), np.uint8)
+        n = np.zeros(B, np.int32)
+        mono = np.zeros(B, np.int32)
+        rc = load_library().orbx_extract_batch(self.h, B, ptrs, w, h, w, int(vLappingArea[0]), int(vLappingArea[1]),
+                                               _p(kps), _p(desc), self.cap, _p(n), _p(mono))
+        _check(rc, "orbx_extract_batch")
+        return [(int(mono[b]), kps[b, :n[b]].copy(), desc[b, :n[b]].copy()) for b in range(B)]
+
+    def extract_batch_device(self, d_imgs_ptr, B, w, h, stride, d_kps_ptr, d_desc_ptr, cap, d_n_ptr, d_mono_ptr,
+                             vLappingArea=(0, 0)):
+        rc = load_library().orbx_extract_batch_device(self.h, B, d_imgs_ptr, w, h, stride, int(vLappingArea[0]),
+                                                      int(vLappingArea[1]), d_kps_ptr, d_desc_ptr, cap, d_n_ptr,
+                                                      d_mono_ptr)
+        _check(rc, "orbx_extract_batch_device")
+
+    def pyramid_level(self, level, b=0):
+        """mvImagePyramid[level] of image b of the last call."""
+        w, h = C.c_int(0), C.c_int(0)
+        _check(load_library().orbx_pyramid_level(self.h, b, level, None, 0, C.byref(w), C.byref(h)),
+               "orbx_pyramid_level")
+        out = np.empty((h.value, w.value), np.uint8)
+        _check(load_library().orbx_pyramid_level(self.h, b, level, _p(out), w.value, C.byref(w), C.byref(h)),
+               "orbx_pyramid_level")
+        return out
+
+    def debug_candidates(self, level, b=0):
+        cap = 1 << 20
+        xy = np.empty((cap, 2), np.int16)
+        sc = np.empty(cap, np.uint8)
+        n = C.c_int(0)
+        _check(load_library().orbx_debug_candidates(self.h, b, level, _p(xy), _p(sc), cap, C.byref(n)),
+               "orbx_debug_candidates")
+        return xy[:n.value].copy(), sc[:n.value].copy()

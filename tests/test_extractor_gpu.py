@@ -1,0 +1,108 @@
+"""GPU parity: liborbx's extractor (through the C ABI) vs the CPU oracle — bit-exact keypoints,
+descriptors, pyramid levels and FAST candidate sets."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _images():
+    from orbx import synth
+    return {
+        "scene0": synth.scene_image(0),
+        "scene1": synth.scene_image(1),
+        "scene2": synth.scene_image(2),
+        "noise": synth.noise_image(5),
+        "const": synth.constant_image(90),
+        "stereoR": synth.stereo_pair(3)[1],
+    }
+
+
+def _assert_same(ref, got, tag):
+    rc, rk, rd, rm = ref
+    gm, gk, gd = got
+    assert rc == 0
+    assert len(gk) == len(rk), "%s: keypoint count %d vs oracle %d" % (tag, len(gk), len(rk))
+    assert gm == rm, "%s: monoIndex" % tag
+    for f in rk.dtype.names:
+        bad = np.flatnonzero(rk[f] != gk[f])
+        assert bad.size == 0, "%s: field %s differs at %s" % (tag, f, bad[:8])
+    assert np.array_equal(rd, gd), "%s: descriptors differ in %d rows" % (tag, (rd != gd).any(axis=1).sum())
+
+
+def test_pyramid_and_candidates(ctx, ork):
+    import orbx
+    from orbx import synth
+    img = synth.scene_image(0)
+    ex = orbx.ORBextractor(ctx)
+    orc = ork.Extractor()
+    ex(img)
+    orc(img)
+    for l in range(8):
+        assert np.array_equal(ex.pyramid_level(l), orc.pyramid_level(l)), "pyramid level %d" % l
+        gxy, gsc = ex.debug_candidates(l)
+        oxy, osc = orc.candidates(l)
+        g = sorted(zip(gxy[:, 1].tolist(), gxy[:, 0].tolist(), gsc.tolist()))
+        o = sorted(zip(oxy[:, 1].tolist(), oxy[:, 0].tolist(), osc.tolist()))
+        assert g == o, "FAST candidates differ on level %d (%d vs %d)" % (l, len(g), len(o))
+
+
+@pytest.mark.parametrize("lap", [(0, 0), (0, 1000), (200, 400)])
+def test_extract_matches_oracle(ctx, ork, lap):
+    import orbx
+    ex = orbx.ORBextractor(ctx)
+    orc = ork.Extractor()
+    for name, img in _images().items():
+        _assert_same(orc(img, lap), ex(img, lap), "%s lap=%s" % (name, lap))
+
+
+def test_empty_image_returns_minus_one(ctx):
+    import orbx
+    ex = orbx.ORBextractor(ctx)
+    rc, k, d = ex(np.empty((0, 0), np.uint8))
+    assert rc == -1 and len(k) == 0 and d.shape == (0, 32)
+
+
+def test_other_sizes_and_parameters(ctx, ork):
+    import orbx
+    from orbx import synth
+    cases = [
+        (synth.scene_image(11, 360, 270), dict(nfeatures=500)),
+        (synth.scene_image(12, 640, 480), dict(nfeatures=1500, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7)),
+        (synth.scene_image(13, 752, 480), dict(nfeatures=5000)),           # mono initialisation extractor
+        (synth.scene_image(14, 1920, 1080), dict(nfeatures=2000)),          # BASELINE config 4
+        (synth.scene_image(15, 800, 600), dict(nfeatures=800, scaleFactor=1.5, nlevels=4, iniThFAST=30, minThFAST=10)),
+    ]
+    for img, kw in cases:
+        h, w = img.shape
+        ex = orbx.ORBextractor(ctx, max_w=w, max_h=h, **kw)
+        orc = ork.Extractor(kw.get("nfeatures", 1000), kw.get("scaleFactor", 1.2), kw.get("nlevels", 8),
+                            kw.get("iniThFAST", 20), kw.get("minThFAST", 7))
+        _assert_same(orc(img), ex(img), "%dx%d %s" % (w, h, kw))
+        ex.close()
+
+
+def test_batch_equals_single(ctx, ork):
+    import orbx
+    imgs = list(_images().values())
+    ex = orbx.ORBextractor(ctx, max_batch=len(imgs))
+    orc = ork.Extractor()
+    out = ex.extract_batch(imgs)
+    for i, img in enumerate(imgs):
+        _assert_same(orc(img), out[i], "batch[%d]" % i)
+
+
+def test_strided_input_and_reuse(ctx, ork):
+    """Non-contiguous rows (stride > width) and repeated calls on one extractor instance."""
+    import orbx
+    from orbx import synth
+    big = synth.scene_image(21, 800, 500)
+    view = big[10:490, 20:772]
+    assert not view.flags["C_CONTIGUOUS"]
+    ex = orbx.ORBextractor(ctx)
+    orc = ork.Extractor()
+    for _ in range(2):
+        _assert_same(orc(np.ascontiguousarray(view)), ex(np.ascontiguousarray(view)), "reuse")
+    # smaller image on the same instance (geometry reconfiguration)
+    small = synth.scene_image(22, 640, 400)
+    _assert_same(orc(small), ex(small), "smaller image, same instance")
