@@ -132,7 +132,7 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
     orbx_set_error("orbx: internal sizing error (pyr %zu/%zu cand %d sel %d)", off, e->pyrBytes, cand, sel);
     return ORBX_ECAP;
   }
-  // resize tables (cv::resize INTER_LINEAR 8U; see oracle/ork_primitives.cpp for the derivation)
+  // resize tables: cv::resize INTER_LINEAR 8U, 11-bit fixed-point coefficients (kernel K1)
   for (int l = 1; l < e->nlevels; ++l) {
     LevelParams& L = P.lv[l];
     const LevelParams& S = P.lv[l - 1];

@@ -1,0 +1,46 @@
+"""CPU: the C-ABI library loads and exports every symbol include/orbx.h declares; the product
+refuses to run without a CUDA device (no CPU fallback); the product never references oracle/."""
+import os
+import re
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "awesome-orb-slam3-3dvisioncraft-version_b200")
+
+
+def test_library_exports_every_declared_symbol():
+    import orbx
+    if not os.path.exists(orbx.lib_path()):
+        orbx.build_library()
+    L = orbx.load_library()
+    syms = orbx.declared_symbols()
+    assert len(syms) >= 19
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert L.orbx_abi_version() >= 1
+
+
+def test_no_cpu_fallback_without_device():
+    import orbx
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(orbx.OrbxError):
+        orbx.Context(0)
+
+
+def test_product_never_touches_the_oracle():
+    bad = []
+    for dp, _, files in os.walk(PKG):
+        if os.path.basename(dp) == "build":
+            continue
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py", ".hpp")) or f == "Makefile":
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"(^|[^a-z_])(libork|ork_[a-z]+\(|import oracle|from oracle|oracle/ork)", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, "product sources reference the oracle: %s" % bad

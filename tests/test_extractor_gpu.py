@@ -106,3 +106,15 @@ def test_strided_input_and_reuse(ctx, ork):
     # smaller image on the same instance (geometry reconfiguration)
     small = synth.scene_image(22, 640, 400)
     _assert_same(orc(small), ex(small), "smaller image, same instance")
+
+
+def test_gpu_reproduces_golden_vectors(ctx):
+    """The committed known-answer vectors (minted from real cv2 primitives, tools/make_golden.py)."""
+    import orbx
+    from golden_util import extractor_cases, assert_kp_equal
+    for name, img, lap, nf, gk, gd, gm in extractor_cases():
+        h, w = img.shape
+        ex = orbx.ORBextractor(ctx, nfeatures=nf, max_w=w, max_h=h)
+        m, k, d = ex(img, lap)
+        assert_kp_equal(k, d, m, gk, gd, gm, name)
+        ex.close()
