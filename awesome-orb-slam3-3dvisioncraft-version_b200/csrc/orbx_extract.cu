@@ -13,7 +13,7 @@ int orbx_extract_configure(int nodeCap, int fastTileBytes);
 size_t orbx_octree_smem_bytes(int nodeCap);
 size_t orbx_fast_smem_bytes(int fastTileBytes);
 int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, orbx_keypoint* d_kps, uint8_t* d_desc,
-                        int cap, int* d_n, int* d_mono);
+                        int cap, int* d_n, int* d_mono, cudaEvent_t* ev);
 
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
 static inline int cv_floor_d(double v) { int i = (int)v; return i - (i > v); }
@@ -53,6 +53,9 @@ struct orbx_ext {
   int* h_nOut = nullptr;
   int lastB = 0;
   bool level0External = false;
+  bool profiling = false;
+  bool profiled = false;
+  cudaEvent_t ev[ORBX_EXT_STAGES + 1] = {};
 };
 
 static void level_dims(const orbx_ext* e, int w, int h, int l, int* lw, int* lh) {
@@ -85,7 +88,6 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   P.nodeCap = 0;
   size_t off = 0;
   int tile = 0, btile = 0, cand = 0, sel = 0, fastBytes = 0;
-  size_t tab = 0;
   std::vector<int16_t> htab;
   for (int l = 0; l < e->nlevels; ++l) {
     LevelParams& L = P.lv[l];
@@ -306,6 +308,8 @@ void orbx_extractor_destroy(orbx_ext* e) {
   cudaFreeHost(e->h_kps);
   cudaFreeHost(e->h_desc);
   cudaFreeHost(e->h_nOut);
+  for (int i = 0; i <= ORBX_EXT_STAGES; ++i)
+    if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -327,6 +331,28 @@ int orbx_extractor_features_per_level(const orbx_ext* e, int* n) {
   if (!e || !n) return ORBX_EINVAL;
   for (int l = 0; l < e->nlevels; ++l) n[l] = e->nFeat[l];
   return e->nlevels;
+}
+
+int orbx_extractor_set_profiling(orbx_ext* e, int enable) {
+  if (!e) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(e->ctx->device));
+  if (enable && !e->ev[0])
+    for (int i = 0; i <= ORBX_EXT_STAGES; ++i) ORBX_CUDA(cudaEventCreate(&e->ev[i]));
+  e->profiling = enable != 0;
+  e->profiled = false;
+  return ORBX_OK;
+}
+
+int orbx_extractor_stage_ms(orbx_ext* e, float* ms, int* launches) {
+  if (!e || !ms || !e->profiled) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(e->ctx->device));
+  ORBX_CUDA(cudaEventSynchronize(e->ev[ORBX_EXT_STAGES]));
+  for (int i = 0; i < ORBX_EXT_STAGES; ++i) ORBX_CUDA(cudaEventElapsedTime(&ms[i], e->ev[i], e->ev[i + 1]));
+  if (launches) {
+    launches[0] = e->nlevels - 1;
+    for (int i = 1; i < ORBX_EXT_STAGES; ++i) launches[i] = 1;
+  }
+  return ORBX_OK;
 }
 
 int orbx_extractor_max_keypoints(const orbx_ext* e) { return e ? e->maxKeypoints : ORBX_EINVAL; }
@@ -356,7 +382,8 @@ static int run_device(orbx_ext* e, int B, const uint8_t* d_level0, int w, int h,
   P.lv[0].pitch = stride;
   P.lv[0].imgStride = (size_t)stride * h;
   e->lastB = B;
-  return orbx_extract_launch(e->ctx, e->stream, P, d_kps, d_desc, cap, d_n, d_mono);
+  e->profiled = e->profiling;
+  return orbx_extract_launch(e->ctx, e->stream, P, d_kps, d_desc, cap, d_n, d_mono, e->profiling ? e->ev : nullptr);
 }
 
 int orbx_extract_batch_device(orbx_ext* e, int B, const uint8_t* d_imgs, int w, int h, int stride, int lap0, int lap1,

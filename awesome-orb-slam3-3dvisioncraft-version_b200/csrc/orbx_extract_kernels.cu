@@ -9,7 +9,7 @@
 // __fmul_rn/__fadd_rn so nvcc cannot contract them into FMAs (parity hazard).
 #include "orbx_extract.cuh"
 
-__constant__ int8_t c_pattern[1024] = {
+__constant__ __align__(16) int8_t c_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 // umax[v]: half-width of the r=15 disc at row v (src/ORBextractor.cc:452-467); same for every extractor.
@@ -589,6 +589,12 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 
 __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ ExtractParams p, orbx_keypoint* kps,
                                                        uint8_t* desc, int cap, int* nOut, int* monoOut) {
+  // lanes of a warp read 32 different pattern rows: stage the table in shared memory (constant
+  // memory would serialise the divergent addresses)
+  __shared__ int s_pat[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)   // transposed: word (byte row r, pair k) at [k*32 + r]
+    s_pat[(i & 7) * 32 + (i >> 3)] = reinterpret_cast<const int*>(c_pattern)[i];
+  __syncthreads();
   const int b = blockIdx.y;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   // locate (level, i) of this warp's keypoint and the counts it needs for its output slot
@@ -647,12 +653,12 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ E
   const float ang = __fmul_rn(angle, factorPI);
   const float a = (float)cos((double)ang), bsn = (float)sin((double)ang);
   const uint8_t* bl = L.blur + (size_t)b * L.imgStride + (size_t)py * L.pitch + px;
-  const int8_t* pat = c_pattern + lane * 32;
   int val = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const float x0 = (float)pat[k * 4 + 0], y0 = (float)pat[k * 4 + 1];
-    const float x1 = (float)pat[k * 4 + 2], y1 = (float)pat[k * 4 + 3];
+    const int pw = s_pat[k * 32 + lane];   // (x0,y0,x1,y1) packed int8
+    const float x0 = (float)(int8_t)(pw & 0xff), y0 = (float)(int8_t)((pw >> 8) & 0xff);
+    const float x1 = (float)(int8_t)((pw >> 16) & 0xff), y1 = (float)(int8_t)((pw >> 24) & 0xff);
     const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, bsn), __fmul_rn(y0, a)));
     const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bsn)));
     const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bsn), __fmul_rn(y1, a)));
@@ -697,23 +703,30 @@ int orbx_extract_configure(int nodeCap, int fastTileBytes) {
 }
 
 int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, orbx_keypoint* d_kps, uint8_t* d_desc,
-                        int cap, int* d_n, int* d_mono) {
+                        int cap, int* d_n, int* d_mono, cudaEvent_t* ev /* [ORBX_EXT_STAGES+1] or null */) {
   const int B = p.B;
   ORBX_CUDA(cudaMemsetAsync(p.candN, 0, sizeof(int) * B * p.nlevels, st));
+#define ORBX_EV(i) do { if (ev) ORBX_CUDA(cudaEventRecord(ev[i], st)); } while (0)
+  ORBX_EV(0);
   for (int l = 1; l < p.nlevels; ++l) {
     dim3 grid(div_up(div_up(p.lv[l].w, 4), 128), p.lv[l].h, B);
     pyr_resize_kernel<<<grid, 128, 0, st>>>(p, l);
     ORBX_LAUNCH(ctx);
   }
+  ORBX_EV(1);
   fast_cells_kernel<<<dim3(p.totalFastTiles, B), 256, orbx_fast_smem_bytes(p.fastTileBytes), st>>>(p);
   ORBX_LAUNCH(ctx);
+  ORBX_EV(2);
   gauss7_kernel<<<dim3(p.totalBlurTiles, B), 256, 0, st>>>(p);
   ORBX_LAUNCH(ctx);
+  ORBX_EV(3);
   octree_kernel<<<dim3(p.nlevels, B), OCT_NT, orbx_octree_smem_bytes(p.nodeCap), st>>>(p);
   ORBX_LAUNCH(ctx);
+  ORBX_EV(4);
   const int warpsPerImage = p.selPerImage;
   describe_kernel<<<dim3(div_up(warpsPerImage * 32, 128), B), 128, 0, st>>>(p, d_kps, d_desc, cap, d_n, d_mono);
   ORBX_LAUNCH(ctx);
+  ORBX_EV(5);
   ORBX_CUDA(cudaGetLastError());
   return ORBX_OK;
 }

@@ -68,6 +68,8 @@ def load_library():
     L.orbx_extract.argtypes = [vp, vp, i, i, i, i, i, vp, vp, i, vp, vp]
     L.orbx_extract_batch.argtypes = [vp, i, vp, i, i, i, i, i, vp, vp, i, vp, vp]
     L.orbx_extract_batch_device.argtypes = [vp, i, vp, i, i, i, i, i, vp, vp, i, vp, vp]
+    L.orbx_extractor_set_profiling.argtypes = [vp, i]
+    L.orbx_extractor_stage_ms.argtypes = [vp, vp, vp]
     L.orbx_pyramid_level.argtypes = [vp, i, i, vp, i, vp, vp]
     L.orbx_debug_candidates.argtypes = [vp, i, i, vp, vp, i, vp]
     _LIB = L
@@ -202,6 +204,17 @@ class ORBextractor:
                                                       int(vLappingArea[1]), d_kps_ptr, d_desc_ptr, cap, d_n_ptr,
                                                       d_mono_ptr)
         _check(rc, "orbx_extract_batch_device")
+
+    STAGES = ("pyramid", "fast", "blur", "quadtree", "describe")
+
+    def set_profiling(self, on=True):
+        _check(load_library().orbx_extractor_set_profiling(self.h, int(on)), "orbx_extractor_set_profiling")
+
+    def stage_ms(self):
+        ms = np.zeros(len(self.STAGES), np.float32)
+        ln = np.zeros(len(self.STAGES), np.int32)
+        _check(load_library().orbx_extractor_stage_ms(self.h, _p(ms), _p(ln)), "orbx_extractor_stage_ms")
+        return ms, ln
 
     def pyramid_level(self, level, b=0):
         """mvImagePyramid[level] of image b of the last call."""

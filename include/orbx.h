@@ -116,6 +116,14 @@ int orbx_extract_batch_device(orbx_ext *ext, int B, const uint8_t *d_imgs, int w
 int orbx_pyramid_level(orbx_ext *ext, int b, int level, uint8_t *dst, int dst_stride,
                        int *w_out, int *h_out);
 
+/* Per-stage device time of the LAST extract call, measured with CUDA events recorded on the
+ * extractor's stream between its kernels (enable first; costs ~6 event records per call).
+ * Stages: 0 pyramid (nlevels-1 resize launches), 1 FAST cells, 2 Gaussian blur, 3 quadtree,
+ * 4 orientation+descriptor.  ms[] and launches[] hold ORBX_EXT_STAGES entries. */
+#define ORBX_EXT_STAGES 5
+int orbx_extractor_set_profiling(orbx_ext *ext, int enable);
+int orbx_extractor_stage_ms(orbx_ext *ext, float *ms, int *launches);
+
 /* Test/diagnostic view: FAST candidates of (image b, level) of the last call, i.e. the
  * contents of `vToDistributeKeys` (src/ORBextractor.cc:775,845-851) in an unspecified
  * order.  xy = [n][2] int16 (coordinates relative to minBorder), score = [n] uint8. */
