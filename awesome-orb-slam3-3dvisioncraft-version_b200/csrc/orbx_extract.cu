@@ -492,3 +492,24 @@ int orbx_debug_candidates(orbx_ext* e, int b, int level, int16_t* xy, uint8_t* s
 }
 
 }  // extern "C"
+
+// Internal: device view of image b's pyramid of the last extract call (used by the stereo matcher).
+int orbx_ext_pyramid_view(orbx_ext* e, int b, int* nlevels, const uint8_t** ptr, int* w, int* h, int* pitch, float* scale,
+                          float* invScale, cudaStream_t* st) {
+  if (!e || e->curW < 0 || b < 0 || b >= e->lastB) {
+    orbx_set_error("orbx: extractor has no pyramid for image %d (run an extraction first)", b);
+    return ORBX_EINVAL;
+  }
+  *nlevels = e->nlevels;
+  for (int l = 0; l < e->nlevels; ++l) {
+    const LevelParams& L = e->P.lv[l];
+    ptr[l] = L.pyr + (size_t)b * L.imgStride;
+    w[l] = L.w;
+    h[l] = L.h;
+    pitch[l] = L.pitch;
+    scale[l] = e->scale[l];
+    invScale[l] = e->invScale[l];
+  }
+  *st = e->stream;
+  return ORBX_OK;
+}

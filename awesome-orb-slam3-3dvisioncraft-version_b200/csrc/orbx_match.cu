@@ -1,0 +1,1070 @@
+// orbx_match.cu — sm_100a descriptor matchers behind include/orbx.h.
+//
+// Replaces (reference paths): Frame::AssignFeaturesToGrid/GetFeaturesInArea src/Frame.cc:444-478,755-850;
+// Frame::ComputeStereoMatches src/Frame.cc:955-1133; ORBmatcher::SearchByProjection x2
+// src/ORBmatcher.cc:59-255,2244-2509; SearchForTriangulation :1138-1428; ComputeThreeMaxima :2654-2695;
+// DescriptorDistance :2700-2716; Pinhole::epipolarConstrain src/CameraModels/Pinhole.cpp:155-177.
+//
+// Structure shared by both projection searches: the expensive part (grid walk + 256-bit Hamming via
+// __popc over 8 words) runs one warp per query, fully parallel, and records each query's candidates in
+// the reference's visiting order; the reference's *ordered greedy* semantics (a keypoint taken by an
+// earlier MapPoint with observations is skipped by later ones) is then replayed exactly by a single warp
+// per frame walking the queries in order with warp-wide (dist,position) min-reductions.
+#include <algorithm>
+#include "orbx_match.cuh"
+
+#define TH_HIGH 100
+#define TH_LOW 50
+#define HISTO_LENGTH 30
+
+// ------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ int hamming256(const uint4* __restrict__ a, const uint4* __restrict__ b) {
+  const uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// C round(): half away from zero
+__device__ __forceinline__ int round_haz(float v) { return (int)roundf(v); }
+
+struct CellRange { int x0, x1, y0, y1; bool empty; };
+
+// GetFeaturesInArea cell window (src/Frame.cc:779-802)
+__device__ __forceinline__ CellRange cell_range(const FrameDev& F, float x, float y, float r) {
+  CellRange c;
+  c.empty = true;
+  c.x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, F.minX), r), F.wInv)));
+  if (c.x0 >= ORBX_GRID_COLS) return c;
+  c.x1 = min(ORBX_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, F.minX), r), F.wInv)));
+  if (c.x1 < 0) return c;
+  c.y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, F.minY), r), F.hInv)));
+  if (c.y0 >= ORBX_GRID_ROWS) return c;
+  c.y1 = min(ORBX_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, F.minY), r), F.hInv)));
+  if (c.y1 < 0) return c;
+  c.empty = false;
+  return c;
+}
+
+__device__ __forceinline__ bool in_window(const orbx_keypoint& kp, float x, float y, float r, int minLevel, int maxLevel) {
+  const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+  if (checkLevels) {
+    if (kp.octave < minLevel) return false;
+    if (maxLevel >= 0 && kp.octave > maxLevel) return false;
+  }
+  return fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r;
+}
+
+// Warp-cooperative walk of the candidates of one query in the reference's order.  Calls
+// f(position, keypointIndex) for every keypoint GetFeaturesInArea would return; `position` is the
+// index in the returned vector.  All 32 lanes must call; f runs on the lane that owns the candidate.
+// Returns the total number of candidates.
+template <typename Fn>
+__device__ __forceinline__ int walk_candidates(const FrameDev& F, float x, float y, float r, int minLevel, int maxLevel,
+                                               Fn f) {
+  const int lane = threadIdx.x & 31;
+  const CellRange c = cell_range(F, x, y, r);
+  if (c.empty) return 0;
+  int pos = 0;
+  for (int ix = c.x0; ix <= c.x1; ++ix) {
+    // cells (ix, y0..y1) are contiguous in the CSR (cell id = ix*48 + iy): one linear span per column
+    const int beg = F.cellStart[ix * ORBX_GRID_ROWS + c.y0], end = F.cellStart[ix * ORBX_GRID_ROWS + c.y1 + 1];
+    for (int base = beg; base < end; base += 32) {
+      const int i = base + lane;
+      int idx = -1;
+      bool ok = false;
+      if (i < end) {
+        idx = F.cellIdx[i];
+        ok = in_window(F.kps[idx], x, y, r, minLevel, maxLevel);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) f(pos + __popc(m & ((1u << lane) - 1)), idx);
+      pos += __popc(m);
+    }
+  }
+  return pos;
+}
+
+// ------------------------------------------------------------------------------------
+// K7 grid build: one CTA per frame.  Counting sort by cell, ascending keypoint index in a cell.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grid_build_kernel(const FrameDev* __restrict__ frames) {
+  const FrameDev F = frames[blockIdx.x];
+  __shared__ int s_cnt[ORBX_NCELLS];
+  __shared__ int s_warp[9];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < ORBX_NCELLS; i += 256) s_cnt[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < F.n; i += 256) {
+    const orbx_keypoint kp = F.kps[i];
+    const int px = round_haz(__fmul_rn(__fsub_rn(kp.x, F.minX), F.wInv));   // PosInGrid, src/Frame.cc:852-862
+    const int py = round_haz(__fmul_rn(__fsub_rn(kp.y, F.minY), F.hInv));
+    if (px < 0 || px >= ORBX_GRID_COLS || py < 0 || py >= ORBX_GRID_ROWS) continue;
+    atomicAdd(&s_cnt[px * ORBX_GRID_ROWS + py], 1);
+  }
+  __syncthreads();
+  // exclusive scan of 3072 counts: 12 per thread
+  const int per = ORBX_NCELLS / 256;
+  int local[ORBX_NCELLS / 256];
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < per; ++k) { local[k] = s_cnt[tid * per + k]; sum += local[k]; }
+  int incl = sum;
+  const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (tid == 0) { int run = 0; for (int w = 0; w < 8; ++w) { int v = s_warp[w]; s_warp[w] = run; run += v; } s_warp[8] = run; }
+  __syncthreads();
+  int run = s_warp[wid] + incl - sum;
+#pragma unroll
+  for (int k = 0; k < per; ++k) { F.cellStart[tid * per + k] = run; s_cnt[tid * per + k] = run; run += local[k]; }
+  if (tid == 255) F.cellStart[ORBX_NCELLS] = s_warp[8];
+  __syncthreads();
+  // unordered fill, then sort each cell's few entries ascending (= insertion order of the reference)
+  for (int i = tid; i < F.n; i += 256) {
+    const orbx_keypoint kp = F.kps[i];
+    const int px = round_haz(__fmul_rn(__fsub_rn(kp.x, F.minX), F.wInv));
+    const int py = round_haz(__fmul_rn(__fsub_rn(kp.y, F.minY), F.hInv));
+    if (px < 0 || px >= ORBX_GRID_COLS || py < 0 || py >= ORBX_GRID_ROWS) continue;
+    F.cellIdx[atomicAdd(&s_cnt[px * ORBX_GRID_ROWS + py], 1)] = i;
+  }
+  __syncthreads();
+  for (int c = tid; c < ORBX_NCELLS; c += 256) {
+    const int b = F.cellStart[c], e = s_cnt[c];
+    for (int i = b + 1; i < e; ++i) {
+      const int v = F.cellIdx[i];
+      int j = i - 1;
+      while (j >= b && F.cellIdx[j] > v) { F.cellIdx[j + 1] = F.cellIdx[j]; --j; }
+      F.cellIdx[j + 1] = v;
+    }
+  }
+}
+
+int orbx_launch_grid_build(orbx_ctx* ctx, cudaStream_t st, const FrameDev* d_frames, int nFrames) {
+  grid_build_kernel<<<nFrames, 256, 0, st>>>(d_frames);
+  ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+int orbx_upload_frame(DevScope& S, const orbx_frame_desc* f, FrameDev* out) {
+  if (!f || f->n < 0 || (f->n > 0 && (!f->kps || !f->desc)) || !(f->max_x > f->min_x) || !(f->max_y > f->min_y)) {
+    orbx_set_error("orbx: invalid frame descriptor");
+    return ORBX_EINVAL;
+  }
+  out->n = f->n;
+  out->kps = S.upload(f->kps, f->n);
+  out->desc = S.upload(f->desc, (size_t)f->n * 32);
+  out->uright = f->uright ? S.upload(f->uright, f->n) : nullptr;
+  out->minX = f->min_x;
+  out->minY = f->min_y;
+  out->maxX = f->max_x;
+  out->maxY = f->max_y;
+  out->wInv = (float)ORBX_GRID_COLS / (f->max_x - f->min_x);
+  out->hInv = (float)ORBX_GRID_ROWS / (f->max_y - f->min_y);
+  out->cellStart = S.alloc<int>(ORBX_NCELLS + 1);
+  out->cellIdx = S.alloc<int>(f->n);
+  return S.failed ? ORBX_ECUDA : ORBX_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// features_in_area (test primitive): warp per query
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) features_in_area_kernel(const FrameDev* frames, int nq, const float* x, const float* y,
+                                                               const float* r, const int* minL, const int* maxL,
+                                                               int* outIdx, int cap, int* outN) {
+  const FrameDev F = frames[0];
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  int* dst = outIdx + (size_t)q * cap;
+  const int n = walk_candidates(F, x[q], y[q], r[q], minL[q], maxL[q], [&](int pos, int idx) {
+    if (pos < cap) dst[pos] = idx;
+  });
+  if ((threadIdx.x & 31) == 0) outN[q] = n;
+}
+
+// ------------------------------------------------------------------------------------
+// K8a  SearchByProjection(Frame, MapPoints): phase A (parallel candidate scoring)
+//   candidate record: idx | dist<<16 | (level & 0xf) << 25
+// ------------------------------------------------------------------------------------
+struct SbpMapArgs {
+  int nq;
+  const float *projX, *projY, *projXR, *viewCos;
+  const int* level;
+  const uint8_t* mpDesc;
+  const uint8_t* flags;
+  float th, nnratio;
+  const float* scaleFactors;
+  // phase A -> B
+  int* candOfs;      // [nq]
+  int* candCnt;      // [nq]
+  uint32_t* cand;    // [candCap]
+  int candCap;
+  int* total;        // running allocation counter
+  int* err;
+  // outputs
+  const uint8_t* kpBlocked;
+  int* bestIdx;
+  int* nmatches;
+};
+
+__global__ void __launch_bounds__(128) sbp_map_score_kernel(const FrameDev* frames, SbpMapArgs A) {
+  const FrameDev F = frames[0];
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (q >= A.nq) return;
+  if (lane == 0) { A.candCnt[q] = 0; A.candOfs[q] = 0; }
+  if (!(A.flags[q] & 1)) return;
+  const int lvl = A.level[q];
+  float r = ((double)A.viewCos[q] > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos, src/ORBmatcher.cc:260-266
+  if (A.th != 1.0f) r = __fmul_rn(r, A.th);
+  const float rs = __fmul_rn(r, A.scaleFactors[lvl]);
+  const float x = A.projX[q], y = A.projY[q];
+  // pass 1: count (static gates only; the "already assigned" gate is dynamic and applied in phase B)
+  const float xr = A.projXR ? A.projXR[q] : 0.f;
+  auto gate = [&](int idx) {
+    if (F.uright) {
+      const float ur = F.uright[idx];
+      if (ur > 0 && fabsf(__fsub_rn(xr, ur)) > rs) return false;
+    }
+    return true;
+  };
+  int cnt = 0;
+  walk_candidates(F, x, y, rs, lvl - 1, lvl, [&](int, int idx) { if (gate(idx)) ++cnt; });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (cnt == 0) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(A.total, cnt);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (base + cnt > A.candCap) {
+    if (lane == 0) atomicExch(A.err, 1);
+    return;
+  }
+  // pass 2: fill in visiting order.  Position among *gated* candidates = rank of its walk position.
+  const uint4* dq = reinterpret_cast<const uint4*>(A.mpDesc + 32 * (size_t)q);
+  const CellRange c = cell_range(F, x, y, rs);
+  int pos = 0;
+  for (int ix = c.x0; ix <= c.x1; ++ix) {
+    const int beg = F.cellStart[ix * ORBX_GRID_ROWS + c.y0], end = F.cellStart[ix * ORBX_GRID_ROWS + c.y1 + 1];
+    for (int b0 = beg; b0 < end; b0 += 32) {
+      const int i = b0 + lane;
+      int idx = -1;
+      bool ok = false;
+      if (i < end) {
+        idx = F.cellIdx[i];
+        ok = in_window(F.kps[idx], x, y, rs, lvl - 1, lvl) && gate(idx);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int d = hamming256(dq, reinterpret_cast<const uint4*>(F.desc + 32 * (size_t)idx));
+        A.cand[base + pos + __popc(m & ((1u << lane) - 1))] =
+            (uint32_t)idx | ((uint32_t)d << 16) | ((uint32_t)(F.kps[idx].octave & 0xf) << 25);
+      }
+      pos += __popc(m);
+    }
+  }
+  if (lane == 0) { A.candCnt[q] = cnt; A.candOfs[q] = base; }
+}
+
+// phase B: one warp per frame replays the queries in order
+__global__ void __launch_bounds__(32) sbp_map_resolve_kernel(const FrameDev* frames, SbpMapArgs A) {
+  extern __shared__ uint8_t s_blocked[];
+  const FrameDev F = frames[0];
+  const int lane = threadIdx.x;
+  for (int i = lane; i < F.n; i += 32) s_blocked[i] = A.kpBlocked ? A.kpBlocked[i] : 0;
+  __syncwarp();
+  int n = 0;
+  for (int q = 0; q < A.nq; ++q) {
+    const int cnt = A.candCnt[q];
+    int best = -1;
+    if (cnt > 0) {
+      const int ofs = A.candOfs[q];
+      // two smallest (dist, position) keys among non-blocked candidates
+      unsigned k1 = 0xffffffffu, k2 = 0xffffffffu;   // key = dist<<20 | position
+      for (int b0 = 0; b0 < cnt; b0 += 32) {
+        const int i = b0 + lane;
+        unsigned key = 0xffffffffu;
+        if (i < cnt) {
+          const uint32_t c = A.cand[ofs + i];
+          if (!s_blocked[c & 0xffff]) key = (((c >> 16) & 0x1ff) << 20) | (unsigned)i;
+        }
+        const unsigned m1 = __reduce_min_sync(0xffffffffu, key);
+        const unsigned m2 = __reduce_min_sync(0xffffffffu, key == m1 ? 0xffffffffu : key);
+        // merge (m1,m2) into (k1,k2)
+        if (m1 < k1) { k2 = min(k1, m2); k1 = m1; }
+        else { k2 = min(k2, m1); }
+      }
+      if (k1 != 0xffffffffu) {
+        const int bestDist = k1 >> 20;
+        const uint32_t c1 = A.cand[ofs + (k1 & 0xfffff)];
+        const int bestLevel = (c1 >> 25) & 0xf;
+        int bestDist2 = 256, bestLevel2 = -1;
+        if (k2 != 0xffffffffu) {
+          bestDist2 = k2 >> 20;
+          bestLevel2 = (A.cand[ofs + (k2 & 0xfffff)] >> 25) & 0xf;
+        }
+        if (bestDist <= TH_HIGH) {
+          const bool reject = bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2);
+          if (!reject) {
+            best = c1 & 0xffff;
+            if (lane == 0) s_blocked[best] = (A.flags[q] & 2) ? 1 : 0;
+            ++n;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) A.bestIdx[q] = best;
+  }
+  if (lane == 0) *A.nmatches = n;
+}
+
+// ------------------------------------------------------------------------------------
+// K8b  SearchByProjection(Cur, Last)
+// ------------------------------------------------------------------------------------
+struct SbpFrameArgs {
+  int nq;
+  const uint8_t* flags;
+  const float* xw;
+  const int* octave;
+  const float* angle;
+  const uint8_t* mpDesc;
+  float Tc[12];
+  float fx, fy, cx, cy, bf;
+  float th;
+  int mode;          // 0 = +-1 octave, 1 = forward, 2 = backward
+  int checkOri;
+  const float* scaleFactors;
+  int* candOfs;
+  int* candCnt;
+  uint32_t* cand;    // idx | dist<<16
+  int candCap;
+  int* total;
+  int* err;
+  const uint8_t* curBlocked;
+  int* matchIdx;
+  uint8_t* kept;
+  int* curMatch;
+  int* nmatches;
+};
+
+__global__ void __launch_bounds__(128) sbp_frame_score_kernel(const FrameDev* frames, SbpFrameArgs A) {
+  const FrameDev F = frames[0];
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (q >= A.nq) return;
+  if (lane == 0) { A.candCnt[q] = 0; A.candOfs[q] = 0; }
+  if (!(A.flags[q] & 1)) return;
+  const float X = A.xw[3 * q], Y = A.xw[3 * q + 1], Z = A.xw[3 * q + 2];
+  // x3Dc = Rcw*x3Dw + tcw in fp32, fixed left-to-right order
+  const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A.Tc[0], X), __fmul_rn(A.Tc[1], Y)), __fmul_rn(A.Tc[2], Z)), A.Tc[3]);
+  const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A.Tc[4], X), __fmul_rn(A.Tc[5], Y)), __fmul_rn(A.Tc[6], Z)), A.Tc[7]);
+  const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A.Tc[8], X), __fmul_rn(A.Tc[9], Y)), __fmul_rn(A.Tc[10], Z)), A.Tc[11]);
+  const float invzc = (float)(1.0 / (double)zc);
+  if (invzc < 0) return;
+  const float u = __fadd_rn(__fdiv_rn(__fmul_rn(A.fx, xc), zc), A.cx);
+  const float v = __fadd_rn(__fdiv_rn(__fmul_rn(A.fy, yc), zc), A.cy);
+  if (u < F.minX || u > F.maxX) return;
+  if (v < F.minY || v > F.maxY) return;
+  const int oct = A.octave[q];
+  const float radius = __fmul_rn(A.th, A.scaleFactors[oct]);
+  int minL, maxL;
+  if (A.mode == 1) { minL = oct; maxL = -1; }
+  else if (A.mode == 2) { minL = 0; maxL = oct; }
+  else { minL = oct - 1; maxL = oct + 1; }
+  const float ur = __fsub_rn(u, __fmul_rn(A.bf, invzc));
+  auto gate = [&](int idx) {
+    if (F.uright) {
+      const float k = F.uright[idx];
+      if (k > 0 && fabsf(__fsub_rn(ur, k)) > radius) return false;
+    }
+    return true;
+  };
+  int cnt = 0;
+  walk_candidates(F, u, v, radius, minL, maxL, [&](int, int idx) { if (gate(idx)) ++cnt; });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (cnt == 0) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(A.total, cnt);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (base + cnt > A.candCap) {
+    if (lane == 0) atomicExch(A.err, 1);
+    return;
+  }
+  const uint4* dq = reinterpret_cast<const uint4*>(A.mpDesc + 32 * (size_t)q);
+  const CellRange c = cell_range(F, u, v, radius);
+  int pos = 0;
+  for (int ix = c.x0; ix <= c.x1; ++ix) {
+    const int beg = F.cellStart[ix * ORBX_GRID_ROWS + c.y0], end = F.cellStart[ix * ORBX_GRID_ROWS + c.y1 + 1];
+    for (int b0 = beg; b0 < end; b0 += 32) {
+      const int i = b0 + lane;
+      int idx = -1;
+      bool ok = false;
+      if (i < end) {
+        idx = F.cellIdx[i];
+        ok = in_window(F.kps[idx], u, v, radius, minL, maxL) && gate(idx);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int d = hamming256(dq, reinterpret_cast<const uint4*>(F.desc + 32 * (size_t)idx));
+        A.cand[base + pos + __popc(m & ((1u << lane) - 1))] = (uint32_t)idx | ((uint32_t)d << 16);
+      }
+      pos += __popc(m);
+    }
+  }
+  if (lane == 0) { A.candCnt[q] = cnt; A.candOfs[q] = base; }
+}
+
+__device__ __forceinline__ int rot_bin(float a, float b) {
+  const float factor = 1.0f / HISTO_LENGTH;
+  float rot = __fsub_rn(a, b);
+  if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+  int bin = round_haz(__fmul_rn(rot, factor));
+  if (bin == HISTO_LENGTH) bin = 0;
+  return bin;
+}
+
+// ComputeThreeMaxima (src/ORBmatcher.cc:2654-2695) on bin counts; serial, 30 bins
+__device__ void three_maxima(const int* h, int& i1, int& i2, int& i3) {
+  int m1 = 0, m2 = 0, m3 = 0;
+  i1 = i2 = i3 = -1;
+  for (int i = 0; i < HISTO_LENGTH; ++i) {
+    const int s = h[i];
+    if (s > m1) { m3 = m2; m2 = m1; m1 = s; i3 = i2; i2 = i1; i1 = i; }
+    else if (s > m2) { m3 = m2; m2 = s; i3 = i2; i2 = i; }
+    else if (s > m3) { m3 = s; i3 = i; }
+  }
+  if ((float)m2 < __fmul_rn(0.1f, (float)m1)) { i2 = -1; i3 = -1; }
+  else if ((float)m3 < __fmul_rn(0.1f, (float)m1)) { i3 = -1; }
+}
+
+__global__ void __launch_bounds__(32) sbp_frame_resolve_kernel(const FrameDev* frames, SbpFrameArgs A) {
+  extern __shared__ uint8_t s_blocked[];
+  __shared__ int s_hist[HISTO_LENGTH];
+  __shared__ int s_keep[3];
+  const FrameDev F = frames[0];
+  const int lane = threadIdx.x;
+  for (int i = lane; i < F.n; i += 32) { s_blocked[i] = A.curBlocked ? A.curBlocked[i] : 0; A.curMatch[i] = -1; }
+  if (lane < HISTO_LENGTH) s_hist[lane] = 0;
+  __syncwarp();
+  int n = 0;
+  for (int q = 0; q < A.nq; ++q) {
+    const int cnt = A.candCnt[q];
+    int best = -1;
+    if (cnt > 0) {
+      const int ofs = A.candOfs[q];
+      unsigned k1 = 0xffffffffu;
+      for (int b0 = 0; b0 < cnt; b0 += 32) {
+        const int i = b0 + lane;
+        unsigned key = 0xffffffffu;
+        if (i < cnt) {
+          const uint32_t c = A.cand[ofs + i];
+          if (!s_blocked[c & 0xffff]) key = (((c >> 16) & 0x1ff) << 20) | (unsigned)i;
+        }
+        k1 = min(k1, __reduce_min_sync(0xffffffffu, key));
+      }
+      if (k1 != 0xffffffffu && (int)(k1 >> 20) <= TH_HIGH) {
+        best = A.cand[ofs + (k1 & 0xfffff)] & 0xffff;
+        if (lane == 0) {
+          s_blocked[best] = (A.flags[q] & 2) ? 1 : 0;
+          A.curMatch[best] = q;
+          if (A.checkOri) s_hist[rot_bin(A.angle[q], F.kps[best].angle)]++;
+        }
+        ++n;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) { A.matchIdx[q] = best; A.kept[q] = best >= 0; }
+  }
+  __syncwarp();
+  if (A.checkOri) {
+    if (lane == 0) { int i1, i2, i3; three_maxima(s_hist, i1, i2, i3); s_keep[0] = i1; s_keep[1] = i2; s_keep[2] = i3; }
+    __syncwarp();
+    const int i1 = s_keep[0], i2 = s_keep[1], i3 = s_keep[2];
+    int removed = 0;
+    for (int q = lane; q < A.nq; q += 32) {
+      const int idx = A.matchIdx[q];
+      if (idx < 0) continue;
+      const int bin = rot_bin(A.angle[q], F.kps[idx].angle);
+      if (bin != i1 && bin != i2 && bin != i3) {
+        A.curMatch[idx] = -1;   // mvpMapPoints[idx] = NULL (even if a later query re-assigned it)
+        A.kept[q] = 0;
+        ++removed;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+    n -= removed;
+  }
+  if (lane == 0) *A.nmatches = n;
+}
+
+// ------------------------------------------------------------------------------------
+// K9  ComputeStereoMatches: warp per left keypoint (row-band Hamming + 11x11 SAD + parabola),
+//     then one CTA per frame for the median SAD rejection.
+// ------------------------------------------------------------------------------------
+struct StereoArgs {
+  int nL, nR;
+  const orbx_keypoint *kpL, *kpR;
+  const uint8_t *descL, *descR;
+  float bf, b;
+  int nlevels;
+  float scale[ORBX_MAX_LEVELS], invScale[ORBX_MAX_LEVELS];
+  const uint8_t* pyrL[ORBX_MAX_LEVELS];
+  const uint8_t* pyrR[ORBX_MAX_LEVELS];
+  int lw[ORBX_MAX_LEVELS], lh[ORBX_MAX_LEVELS], pitchL[ORBX_MAX_LEVELS], pitchR[ORBX_MAX_LEVELS];
+  float* uright;
+  float* depth;
+  int* sad;      // [nL] best SAD of accepted matches, -1 otherwise
+};
+
+__global__ void __launch_bounds__(128) stereo_match_kernel(const __grid_constant__ StereoArgs A) {
+  const int iL = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (iL >= A.nL) return;
+  if (lane == 0) { A.uright[iL] = -1.0f; A.depth[iL] = -1.0f; A.sad[iL] = -1; }
+  const orbx_keypoint kl = A.kpL[iL];
+  const int nRows = A.lh[0];
+  const int row = (int)kl.y;
+  if (row < 0 || row >= nRows) return;
+  const float minZ = A.b, minD = 0.f, maxD = __fdiv_rn(A.bf, minZ);
+  const float minU = __fsub_rn(kl.x, maxD), maxU = __fsub_rn(kl.x, minD);
+  if (maxU < 0) return;
+  const uint4* dl = reinterpret_cast<const uint4*>(A.descL + 32 * (size_t)iL);
+  unsigned key = 0xffffffffu;   // dist<<16 | iR : first minimum in ascending iR
+  for (int iR = lane; iR < A.nR; iR += 32) {
+    const orbx_keypoint kr = A.kpR[iR];
+    const float r = __fmul_rn(2.0f, A.scale[kr.octave]);
+    const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));
+    if (row < minr || row > maxr) continue;
+    if (kr.octave < kl.octave - 1 || kr.octave > kl.octave + 1) continue;
+    if (kr.x >= minU && kr.x <= maxU) {
+      const int d = hamming256(dl, reinterpret_cast<const uint4*>(A.descR + 32 * (size_t)iR));
+      key = min(key, ((unsigned)d << 16) | (unsigned)iR);
+    }
+  }
+  key = __reduce_min_sync(0xffffffffu, key);
+  if (key == 0xffffffffu) return;
+  const int bestDist = key >> 16, bestIdxR = key & 0xffff;
+  if (!(bestDist < TH_HIGH)) return;                 // bestDist starts at TH_HIGH: strict <
+  if (!(bestDist < (TH_HIGH + TH_LOW) / 2)) return;
+  const float uR0 = A.kpR[bestIdxR].x;
+  const int oct = kl.octave;
+  const float sf = A.invScale[oct];
+  const float scaleduL = roundf(__fmul_rn(kl.x, sf)), scaledvL = roundf(__fmul_rn(kl.y, sf)), scaleduR0 = roundf(__fmul_rn(uR0, sf));
+  const int w = 5, L = 5;
+  const int W = A.lw[oct], H = A.lh[oct];
+  const int cxL = (int)scaleduL, cy = (int)scaledvL, cxR = (int)scaleduR0;
+  if (cy - w < 0 || cy + w >= H || cxL - w < 0 || cxL + w >= W) return;
+  const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+  if (iniu < 0 || endu >= W) return;
+  if (cxR - L - w < 0) return;
+  const uint8_t* IL = A.pyrL[oct];
+  const uint8_t* IR = A.pyrR[oct];
+  const int pL = A.pitchL[oct], pR = A.pitchR[oct];
+  const int cL = __ldg(IL + (size_t)cy * pL + cxL);
+  // each lane owns up to 4 of the 121 patch pixels
+  int la[4], ldy[4], ldx[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = lane + 32 * k;
+    ldy[k] = p / 11 - w;
+    ldx[k] = p % 11 - w;
+    la[k] = p < 121 ? (int)__ldg(IL + (size_t)(cy + ldy[k]) * pL + cxL + ldx[k]) - cL : 0;
+  }
+  int sads[11];
+#pragma unroll
+  for (int inc = -L; inc <= L; ++inc) {
+    const int cR = __ldg(IR + (size_t)cy * pR + cxR + inc);
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = lane + 32 * k;
+      if (p < 121) s += abs(la[k] - ((int)__ldg(IR + (size_t)(cy + ldy[k]) * pR + cxR + inc + ldx[k]) - cR));
+    }
+    sads[inc + L] = __reduce_add_sync(0xffffffffu, s);
+  }
+  if (lane != 0) return;
+  int bestSad = 0x7fffffff, bestinc = 0;
+#pragma unroll
+  for (int i = 0; i < 11; ++i)
+    if (sads[i] < bestSad) { bestSad = sads[i]; bestinc = i - L; }
+  if (bestinc == -L || bestinc == L) return;
+  float d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+  for (int i = 1; i < 10; ++i)
+    if (i == bestinc + L) { d1 = (float)sads[i - 1]; d2 = (float)sads[i]; d3 = (float)sads[i + 1]; }
+  const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+  if (deltaR < -1 || deltaR > 1) return;
+  float bestuR = __fmul_rn(A.scale[oct], __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+  float disparity = __fsub_rn(kl.x, bestuR);
+  if (disparity >= minD && disparity < maxD) {
+    if (disparity <= 0) {
+      disparity = (float)0.01;
+      bestuR = (float)((double)kl.x - 0.01);
+    }
+    A.depth[iL] = __fdiv_rn(A.bf, disparity);
+    A.uright[iL] = bestuR;
+    A.sad[iL] = bestSad;
+  }
+}
+
+// median of the accepted SADs (element size/2 of the sorted list) -> reject sad >= 1.5*1.4*median
+__global__ void __launch_bounds__(256) stereo_median_kernel(int nL, const int* sad, float* uright, float* depth) {
+  __shared__ int s_m, s_med;
+  if (threadIdx.x == 0) { s_m = 0; s_med = -1; }
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < nL; i += 256) local += sad[i] >= 0;
+  if (local) atomicAdd(&s_m, local);
+  __syncthreads();
+  const int M = s_m;
+  if (M == 0) return;
+  const int target = M / 2;
+  for (int i = threadIdx.x; i < nL; i += 256) {
+    const int d = sad[i];
+    if (d < 0) continue;
+    int rank = 0;
+    for (int j = 0; j < nL; ++j) {
+      const int e = sad[j];
+      rank += (e >= 0) && (e < d || (e == d && j < i));
+    }
+    if (rank == target) s_med = d;
+  }
+  __syncthreads();
+  const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), (float)s_med);
+  for (int i = threadIdx.x; i < nL; i += 256) {
+    const int d = sad[i];
+    if (d >= 0 && !((float)d < thDist)) { uright[i] = -1.0f; depth[i] = -1.0f; }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K10  SearchForTriangulation: warp per KF1 feature (in FeatureVector order)
+// ------------------------------------------------------------------------------------
+struct TriArgs {
+  int n1, n2;
+  const uint8_t *has1, *has2;
+  int nn1, nn2;
+  const int *n1id, *n1off, *n1idx, *n2id, *n2off, *n2idx;
+  float F12[9];
+  float epx, epy;
+  const float* sigma2;
+  const float* scaleFactors;
+  int onlyStereo, coarse, checkOri;
+  int* match12;
+  int* nmatches;
+};
+
+__global__ void __launch_bounds__(128) tri_match_kernel(const FrameDev* frames, TriArgs A) {
+  const FrameDev K1 = frames[0], K2 = frames[1];
+  const int p1 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (p1 >= A.n1off[A.nn1]) return;
+  // node of position p1 (upper_bound on offsets), then the same node id in KF2
+  int lo = 0, hi = A.nn1;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.n1off[mid] <= p1) lo = mid; else hi = mid; }
+  const int node = A.n1id[lo];
+  int l2 = 0, h2 = A.nn2;
+  while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (A.n2id[mid] < node) l2 = mid + 1; else h2 = mid; }
+  if (l2 >= A.nn2 || A.n2id[l2] != node) return;
+  const int idx1 = A.n1idx[p1];
+  if (A.has1[idx1]) return;
+  const bool bStereo1 = K1.uright && K1.uright[idx1] >= 0;
+  if (A.onlyStereo && !bStereo1) return;
+  const orbx_keypoint kp1 = K1.kps[idx1];
+  const uint4* d1 = reinterpret_cast<const uint4*>(K1.desc + 32 * (size_t)idx1);
+  // epipolar line of kp1 in image 2: l = x1^T F12
+  const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, A.F12[0]), __fmul_rn(kp1.y, A.F12[3])), A.F12[6]);
+  const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, A.F12[1]), __fmul_rn(kp1.y, A.F12[4])), A.F12[7]);
+  const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, A.F12[2]), __fmul_rn(kp1.y, A.F12[5])), A.F12[8]);
+  const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+  // running-best semantics (dist <= best so far, gates before acceptance) == min dist, LAST on ties
+  unsigned key = 0xffffffffu;   // dist<<20 | (0xfffff - position)
+  const int b2 = A.n2off[l2], e2 = A.n2off[l2 + 1];
+  for (int i2 = b2 + lane; i2 < e2; i2 += 32) {
+    const int idx2 = A.n2idx[i2];
+    if (A.has2[idx2]) continue;
+    const bool bStereo2 = K2.uright && K2.uright[idx2] >= 0;
+    if (A.onlyStereo && !bStereo2) continue;
+    const int dist = hamming256(d1, reinterpret_cast<const uint4*>(K2.desc + 32 * (size_t)idx2));
+    if (dist > TH_LOW) continue;
+    const orbx_keypoint kp2 = K2.kps[idx2];
+    if (!bStereo1 && !bStereo2) {
+      const float dex = __fsub_rn(A.epx, kp2.x), dey = __fsub_rn(A.epy, kp2.y);
+      if (__fadd_rn(__fmul_rn(dex, dex), __fmul_rn(dey, dey)) < __fmul_rn(100.f, A.scaleFactors[kp2.octave])) continue;
+    }
+    bool ok = A.coarse != 0;
+    if (!ok && den != 0) {
+      const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+      const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+      ok = (double)dsqr < 3.84 * (double)A.sigma2[kp2.octave];
+    }
+    if (ok) key = min(key, ((unsigned)dist << 20) | (unsigned)(0xfffff - (i2 - b2)));
+  }
+  key = __reduce_min_sync(0xffffffffu, key);
+  if (lane == 0 && key != 0xffffffffu) A.match12[idx1] = A.n2idx[b2 + (0xfffff - (key & 0xfffff))];
+}
+
+__global__ void __launch_bounds__(256) tri_rot_filter_kernel(const FrameDev* frames, TriArgs A) {
+  const FrameDev K1 = frames[0], K2 = frames[1];
+  __shared__ int s_hist[HISTO_LENGTH];
+  __shared__ int s_keep[3];
+  __shared__ int s_n;
+  if (threadIdx.x < HISTO_LENGTH) s_hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < A.n1; i += 256) {
+    const int m = A.match12[i];
+    if (m < 0) continue;
+    ++local;
+    if (A.checkOri) atomicAdd(&s_hist[rot_bin(K1.kps[i].angle, K2.kps[m].angle)], 1);
+  }
+  if (local) atomicAdd(&s_n, local);
+  __syncthreads();
+  if (A.checkOri) {
+    if (threadIdx.x == 0) { int i1, i2, i3; three_maxima(s_hist, i1, i2, i3); s_keep[0] = i1; s_keep[1] = i2; s_keep[2] = i3; }
+    __syncthreads();
+    int removed = 0;
+    for (int i = threadIdx.x; i < A.n1; i += 256) {
+      const int m = A.match12[i];
+      if (m < 0) continue;
+      const int bin = rot_bin(K1.kps[i].angle, K2.kps[m].angle);
+      if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { A.match12[i] = -1; ++removed; }
+    }
+    if (removed) atomicSub(&s_n, removed);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *A.nmatches = s_n;
+}
+
+// =====================================================================================
+// host entry points
+// =====================================================================================
+struct orbx_ext;
+int orbx_ext_pyramid_view(orbx_ext* e, int b, int* nlevels, const uint8_t** ptr, int* w, int* h, int* pitch, float* scale,
+                          float* invScale, cudaStream_t* st);
+
+static int candidate_capacity(int nq, int n) { return std::max(1 << 16, std::min(nq, 1 << 16) * 128 + n); }
+
+extern "C" {
+
+int orbx_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+  int d = 0;
+  for (int i = 0; i < 32; ++i) d += __builtin_popcount((unsigned)(a[i] ^ b[i]));
+  return d;
+}
+
+int orbx_features_in_area(orbx_ctx* ctx, const orbx_frame_desc* frame, int nq, const float* x, const float* y,
+                          const float* r, const int32_t* minL, const int32_t* maxL, int32_t* out_idx, int cap,
+                          int32_t* out_n) {
+  if (!ctx || !frame || nq < 0 || cap < 1 || !x || !y || !r || !minL || !maxL || !out_idx || !out_n) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevScope S(st);
+  FrameDev F;
+  int rc = orbx_upload_frame(S, frame, &F);
+  if (rc != ORBX_OK) return rc;
+  FrameDev* dF = S.upload(&F, 1);
+  float *dx = S.upload(x, nq), *dy = S.upload(y, nq), *dr = S.upload(r, nq);
+  int *dmin = S.upload(minL, nq), *dmax = S.upload(maxL, nq);
+  int* dout = S.alloc<int>((size_t)nq * cap);
+  int* dn = S.alloc<int>(nq);
+  if (S.failed) return ORBX_ECUDA;
+  rc = orbx_launch_grid_build(ctx, st, dF, 1);
+  if (rc != ORBX_OK) return rc;
+  if (nq > 0) {
+    features_in_area_kernel<<<div_up(nq * 32, 128), 128, 0, st>>>(dF, nq, dx, dy, dr, dmin, dmax, dout, cap, dn);
+    ORBX_LAUNCH(ctx);
+    ORBX_CUDA(cudaMemcpyAsync(out_idx, dout, sizeof(int) * (size_t)nq * cap, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(out_n, dn, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+  }
+  ORBX_CUDA(cudaStreamSynchronize(st));
+  return ORBX_OK;
+}
+
+int orbx_search_by_projection_map(orbx_ctx* ctx, const orbx_frame_desc* frame, const uint8_t* kp_blocked, int nq,
+                                  const float* proj_x, const float* proj_y, const float* proj_xr, const int32_t* level,
+                                  const float* view_cos, const uint8_t* mp_desc, const uint8_t* flags, float th,
+                                  float nnratio, const float* scale_factors, int nlevels, int32_t* best_idx,
+                                  int32_t* nmatches) {
+  if (!ctx || !frame || nq < 0 || !proj_x || !proj_y || !level || !view_cos || !mp_desc || !flags || !scale_factors ||
+      nlevels < 1 || nlevels > ORBX_MAX_LEVELS || !best_idx || !nmatches || frame->n > 65535)
+    return ORBX_EINVAL;
+  if (frame->uright && !proj_xr) return ORBX_EINVAL;
+  for (int q = 0; q < nq; ++q)
+    if ((flags[q] & 1) && (level[q] < 0 || level[q] >= nlevels)) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevScope S(st);
+  FrameDev F;
+  int rc = orbx_upload_frame(S, frame, &F);
+  if (rc != ORBX_OK) return rc;
+  FrameDev* dF = S.upload(&F, 1);
+  SbpMapArgs A;
+  A.nq = nq;
+  A.projX = S.upload(proj_x, nq);
+  A.projY = S.upload(proj_y, nq);
+  A.projXR = proj_xr ? S.upload(proj_xr, nq) : nullptr;
+  A.viewCos = S.upload(view_cos, nq);
+  A.level = S.upload(level, nq);
+  A.mpDesc = S.upload(mp_desc, (size_t)nq * 32);
+  A.flags = S.upload(flags, nq);
+  A.th = th;
+  A.nnratio = nnratio;
+  A.scaleFactors = S.upload(scale_factors, nlevels);
+  A.candCap = candidate_capacity(nq, frame->n);
+  A.candOfs = S.alloc<int>(nq);
+  A.candCnt = S.alloc<int>(nq);
+  A.cand = S.alloc<uint32_t>(A.candCap);
+  int* misc = S.alloc<int>(4);
+  A.total = misc;
+  A.err = misc + 1;
+  A.nmatches = misc + 2;
+  A.kpBlocked = kp_blocked ? S.upload(kp_blocked, frame->n) : nullptr;
+  A.bestIdx = S.alloc<int>(nq);
+  if (S.failed) return ORBX_ECUDA;
+  ORBX_CUDA(cudaMemsetAsync(misc, 0, 4 * sizeof(int), st));
+  rc = orbx_launch_grid_build(ctx, st, dF, 1);
+  if (rc != ORBX_OK) return rc;
+  if (nq > 0) {
+    sbp_map_score_kernel<<<div_up(nq * 32, 128), 128, 0, st>>>(dF, A);
+    ORBX_LAUNCH(ctx);
+  }
+  sbp_map_resolve_kernel<<<1, 32, align_up((size_t)frame->n + 16, 16), st>>>(dF, A);
+  ORBX_LAUNCH(ctx);
+  int h[4];
+  ORBX_CUDA(cudaMemcpyAsync(h, misc, sizeof h, cudaMemcpyDeviceToHost, st));
+  if (nq > 0) ORBX_CUDA(cudaMemcpyAsync(best_idx, A.bestIdx, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaStreamSynchronize(st));
+  if (h[1]) {
+    orbx_set_error("orbx_search_by_projection_map: candidate buffer overflow (%d > %d)", h[0], A.candCap);
+    return ORBX_ECAP;
+  }
+  *nmatches = h[2];
+  return ORBX_OK;
+}
+
+int orbx_search_by_projection_frame(orbx_ctx* ctx, const orbx_frame_desc* cur, const uint8_t* cur_blocked,
+                                    const orbx_camera* cam, const float* Tcw_cur, const float* Tcw_last, int nq,
+                                    const uint8_t* flags, const float* xw, const int32_t* octave, const float* angle,
+                                    const uint8_t* mp_desc, float th, int bMono, int check_orientation,
+                                    const float* scale_factors, int nlevels, int32_t* match_idx, uint8_t* kept,
+                                    int32_t* cur_match, int32_t* nmatches) {
+  if (!ctx || !cur || !cam || !Tcw_cur || !Tcw_last || nq < 0 || !flags || !xw || !octave || !angle || !mp_desc ||
+      !scale_factors || nlevels < 1 || nlevels > ORBX_MAX_LEVELS || !match_idx || !kept || !cur_match || !nmatches ||
+      cur->n > 65535)
+    return ORBX_EINVAL;
+  for (int q = 0; q < nq; ++q)
+    if ((flags[q] & 1) && (octave[q] < 0 || octave[q] >= nlevels)) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevScope S(st);
+  FrameDev F;
+  int rc = orbx_upload_frame(S, cur, &F);
+  if (rc != ORBX_OK) return rc;
+  FrameDev* dF = S.upload(&F, 1);
+  SbpFrameArgs A;
+  A.nq = nq;
+  A.flags = S.upload(flags, nq);
+  A.xw = S.upload(xw, (size_t)nq * 3);
+  A.octave = S.upload(octave, nq);
+  A.angle = S.upload(angle, nq);
+  A.mpDesc = S.upload(mp_desc, (size_t)nq * 32);
+  for (int i = 0; i < 12; ++i) A.Tc[i] = Tcw_cur[i];
+  A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
+  A.th = th;
+  {
+    // bForward / bBackward (src/ORBmatcher.cc:2258-2266): z of the current camera centre in the last frame
+    const float* Tc = Tcw_cur;
+    const float* Tl = Tcw_last;
+    float twc[3];
+    for (int i = 0; i < 3; ++i) twc[i] = -(Tc[0 * 4 + i] * Tc[3] + Tc[1 * 4 + i] * Tc[7] + Tc[2 * 4 + i] * Tc[11]);
+    const float tlcz = Tl[8] * twc[0] + Tl[9] * twc[1] + Tl[10] * twc[2] + Tl[11];
+    const bool fwd = tlcz > cam->b && !bMono, bwd = -tlcz > cam->b && !bMono;
+    A.mode = fwd ? 1 : (bwd ? 2 : 0);
+  }
+  A.checkOri = check_orientation;
+  A.scaleFactors = S.upload(scale_factors, nlevels);
+  A.candCap = candidate_capacity(nq, cur->n);
+  A.candOfs = S.alloc<int>(nq);
+  A.candCnt = S.alloc<int>(nq);
+  A.cand = S.alloc<uint32_t>(A.candCap);
+  int* misc = S.alloc<int>(4);
+  A.total = misc;
+  A.err = misc + 1;
+  A.nmatches = misc + 2;
+  A.curBlocked = cur_blocked ? S.upload(cur_blocked, cur->n) : nullptr;
+  A.matchIdx = S.alloc<int>(nq);
+  A.kept = S.alloc<uint8_t>(nq);
+  A.curMatch = S.alloc<int>(cur->n);
+  if (S.failed) return ORBX_ECUDA;
+  ORBX_CUDA(cudaMemsetAsync(misc, 0, 4 * sizeof(int), st));
+  rc = orbx_launch_grid_build(ctx, st, dF, 1);
+  if (rc != ORBX_OK) return rc;
+  if (nq > 0) {
+    sbp_frame_score_kernel<<<div_up(nq * 32, 128), 128, 0, st>>>(dF, A);
+    ORBX_LAUNCH(ctx);
+  }
+  sbp_frame_resolve_kernel<<<1, 32, align_up((size_t)cur->n + 16, 16), st>>>(dF, A);
+  ORBX_LAUNCH(ctx);
+  int h[4];
+  ORBX_CUDA(cudaMemcpyAsync(h, misc, sizeof h, cudaMemcpyDeviceToHost, st));
+  if (nq > 0) {
+    ORBX_CUDA(cudaMemcpyAsync(match_idx, A.matchIdx, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(kept, A.kept, nq, cudaMemcpyDeviceToHost, st));
+  }
+  if (cur->n > 0) ORBX_CUDA(cudaMemcpyAsync(cur_match, A.curMatch, sizeof(int) * cur->n, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaStreamSynchronize(st));
+  if (h[1]) {
+    orbx_set_error("orbx_search_by_projection_frame: candidate buffer overflow (%d > %d)", h[0], A.candCap);
+    return ORBX_ECAP;
+  }
+  *nmatches = h[2];
+  return ORBX_OK;
+}
+
+int orbx_stereo_match(orbx_ctx* ctx, orbx_ext* extL, int bL, orbx_ext* extR, int bR, const orbx_keypoint* kpL,
+                      const uint8_t* descL, int nL, const orbx_keypoint* kpR, const uint8_t* descR, int nR, float bf,
+                      float b, float* uright, float* depth) {
+  if (!ctx || !extL || !extR || nL < 0 || nR < 0 || nR > 65535 || !uright || !depth || !(b > 0)) return ORBX_EINVAL;
+  if ((nL && (!kpL || !descL)) || (nR && (!kpR || !descR))) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  StereoArgs A;
+  int nlv = 0, nlv2 = 0, w2[ORBX_MAX_LEVELS], h2[ORBX_MAX_LEVELS];
+  float sc2[ORBX_MAX_LEVELS], isc2[ORBX_MAX_LEVELS];
+  cudaStream_t stL, stR;
+  int rc = orbx_ext_pyramid_view(extL, bL, &nlv, A.pyrL, A.lw, A.lh, A.pitchL, A.scale, A.invScale, &stL);
+  if (rc != ORBX_OK) return rc;
+  rc = orbx_ext_pyramid_view(extR, bR, &nlv2, A.pyrR, w2, h2, A.pitchR, sc2, isc2, &stR);
+  if (rc != ORBX_OK) return rc;
+  if (nlv != nlv2) return ORBX_EINVAL;
+  for (int l = 0; l < nlv; ++l)
+    if (w2[l] != A.lw[l] || h2[l] != A.lh[l]) {
+      orbx_set_error("orbx_stereo_match: left/right pyramids differ in size");
+      return ORBX_EINVAL;
+    }
+  for (int i = 0; i < nL; ++i)
+    if (kpL[i].octave < 0 || kpL[i].octave >= nlv) return ORBX_EINVAL;
+  for (int i = 0; i < nR; ++i)
+    if (kpR[i].octave < 0 || kpR[i].octave >= nlv) return ORBX_EINVAL;
+  // the pyramids were written on the extractors' streams
+  ORBX_CUDA(cudaStreamSynchronize(stL));
+  if (stR != stL) ORBX_CUDA(cudaStreamSynchronize(stR));
+  cudaStream_t st = ctx->stream;
+  DevScope S(st);
+  A.nL = nL;
+  A.nR = nR;
+  A.nlevels = nlv;
+  A.kpL = S.upload(kpL, nL);
+  A.kpR = S.upload(kpR, nR);
+  A.descL = S.upload(descL, (size_t)nL * 32);
+  A.descR = S.upload(descR, (size_t)nR * 32);
+  A.bf = bf;
+  A.b = b;
+  A.uright = S.alloc<float>(nL);
+  A.depth = S.alloc<float>(nL);
+  A.sad = S.alloc<int>(nL);
+  if (S.failed) return ORBX_ECUDA;
+  if (nL > 0) {
+    stereo_match_kernel<<<div_up(nL * 32, 128), 128, 0, st>>>(A);
+    ORBX_LAUNCH(ctx);
+    stereo_median_kernel<<<1, 256, 0, st>>>(nL, A.sad, A.uright, A.depth);
+    ORBX_LAUNCH(ctx);
+    ORBX_CUDA(cudaMemcpyAsync(uright, A.uright, sizeof(float) * nL, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(depth, A.depth, sizeof(float) * nL, cudaMemcpyDeviceToHost, st));
+  }
+  ORBX_CUDA(cudaStreamSynchronize(st));
+  return ORBX_OK;
+}
+
+int orbx_search_for_triangulation(orbx_ctx* ctx, const orbx_frame_desc* kf1, const orbx_frame_desc* kf2,
+                                  const uint8_t* has_mp1, const uint8_t* has_mp2, int nn1, const int32_t* fv1_node,
+                                  const int32_t* fv1_off, const int32_t* fv1_idx, int nn2, const int32_t* fv2_node,
+                                  const int32_t* fv2_off, const int32_t* fv2_idx, const orbx_camera* cam1,
+                                  const orbx_camera* cam2, const float* R1w, const float* t1w, const float* R2w,
+                                  const float* t2w, const float* level_sigma2, const float* scale_factors, int nlevels,
+                                  int only_stereo, int coarse, int check_orientation, int32_t* match12,
+                                  int32_t* nmatches) {
+  if (!ctx || !kf1 || !kf2 || !has_mp1 || !has_mp2 || nn1 < 0 || nn2 < 0 || !cam1 || !cam2 || !R1w || !t1w || !R2w ||
+      !t2w || !level_sigma2 || !scale_factors || nlevels < 1 || nlevels > ORBX_MAX_LEVELS || !match12 || !nmatches)
+    return ORBX_EINVAL;
+  if ((nn1 && (!fv1_node || !fv1_off || !fv1_idx)) || (nn2 && (!fv2_node || !fv2_off || !fv2_idx))) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevScope S(st);
+  FrameDev F[2];
+  int rc = orbx_upload_frame(S, kf1, &F[0]);
+  if (rc != ORBX_OK) return rc;
+  rc = orbx_upload_frame(S, kf2, &F[1]);
+  if (rc != ORBX_OK) return rc;
+  FrameDev* dF = S.upload(F, 2);
+  TriArgs A;
+  A.n1 = kf1->n;
+  A.n2 = kf2->n;
+  A.has1 = S.upload(has_mp1, kf1->n);
+  A.has2 = S.upload(has_mp2, kf2->n);
+  A.nn1 = nn1;
+  A.nn2 = nn2;
+  const int tot1 = nn1 ? fv1_off[nn1] : 0, tot2 = nn2 ? fv2_off[nn2] : 0;
+  static const int zero = 0;
+  A.n1id = S.upload(nn1 ? fv1_node : &zero, std::max(nn1, 1));
+  A.n1off = S.upload(nn1 ? fv1_off : &zero, nn1 + 1);
+  A.n1idx = S.upload(tot1 ? fv1_idx : &zero, std::max(tot1, 1));
+  A.n2id = S.upload(nn2 ? fv2_node : &zero, std::max(nn2, 1));
+  A.n2off = S.upload(nn2 ? fv2_off : &zero, nn2 + 1);
+  A.n2idx = S.upload(tot2 ? fv2_idx : &zero, std::max(tot2, 1));
+  {
+    // Epipole and fundamental matrix, fp32 with a fixed evaluation order (no FMA on the host: this TU's
+    // host code is compiled with -ffp-contract=off).  The reference rebuilds F12 for every candidate pair
+    // (src/CameraModels/Pinhole.cpp:155-160); it only depends on the two keyframes.
+    float Cw[3], C2[3], R12[9], t12[3], Am[9], Bm[9];
+    for (int i = 0; i < 3; ++i) Cw[i] = -(R1w[0 * 3 + i] * t1w[0] + R1w[1 * 3 + i] * t1w[1] + R1w[2 * 3 + i] * t1w[2]);
+    for (int i = 0; i < 3; ++i) C2[i] = R2w[i * 3 + 0] * Cw[0] + R2w[i * 3 + 1] * Cw[1] + R2w[i * 3 + 2] * Cw[2] + t2w[i];
+    A.epx = cam2->fx * C2[0] / C2[2] + cam2->cx;
+    A.epy = cam2->fy * C2[1] / C2[2] + cam2->cy;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        R12[i * 3 + j] = R1w[i * 3 + 0] * R2w[j * 3 + 0] + R1w[i * 3 + 1] * R2w[j * 3 + 1] + R1w[i * 3 + 2] * R2w[j * 3 + 2];
+    for (int i = 0; i < 3; ++i) t12[i] = -(R12[i * 3 + 0] * t2w[0] + R12[i * 3 + 1] * t2w[1] + R12[i * 3 + 2] * t2w[2]) + t1w[i];
+    const float tx[9] = {0, -t12[2], t12[1], t12[2], 0, -t12[0], -t12[1], t12[0], 0};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Am[i * 3 + j] = tx[i * 3 + 0] * R12[0 * 3 + j] + tx[i * 3 + 1] * R12[1 * 3 + j] + tx[i * 3 + 2] * R12[2 * 3 + j];
+    const float i1x = 1.0f / cam1->fx, i1y = 1.0f / cam1->fy, c1x = -cam1->cx * i1x, c1y = -cam1->cy * i1y;
+    const float i2x = 1.0f / cam2->fx, i2y = 1.0f / cam2->fy, c2x = -cam2->cx * i2x, c2y = -cam2->cy * i2y;
+    for (int j = 0; j < 3; ++j) {
+      Bm[0 * 3 + j] = i1x * Am[0 * 3 + j];
+      Bm[1 * 3 + j] = i1y * Am[1 * 3 + j];
+      Bm[2 * 3 + j] = c1x * Am[0 * 3 + j] + c1y * Am[1 * 3 + j] + Am[2 * 3 + j];
+    }
+    for (int i = 0; i < 3; ++i) {
+      A.F12[i * 3 + 0] = Bm[i * 3 + 0] * i2x;
+      A.F12[i * 3 + 1] = Bm[i * 3 + 1] * i2y;
+      A.F12[i * 3 + 2] = Bm[i * 3 + 0] * c2x + Bm[i * 3 + 1] * c2y + Bm[i * 3 + 2];
+    }
+  }
+  A.sigma2 = S.upload(level_sigma2, nlevels);
+  A.scaleFactors = S.upload(scale_factors, nlevels);
+  A.onlyStereo = only_stereo;
+  A.coarse = coarse;
+  A.checkOri = check_orientation;
+  A.match12 = S.alloc<int>(kf1->n);
+  A.nmatches = S.alloc<int>(1);
+  if (S.failed) return ORBX_ECUDA;
+  ORBX_CUDA(cudaMemsetAsync(A.match12, 0xff, sizeof(int) * std::max(kf1->n, 1), st));
+  ORBX_CUDA(cudaMemsetAsync(A.nmatches, 0, sizeof(int), st));
+  if (tot1 > 0 && nn2 > 0) {
+    tri_match_kernel<<<div_up(tot1 * 32, 128), 128, 0, st>>>(dF, A);
+    ORBX_LAUNCH(ctx);
+  }
+  tri_rot_filter_kernel<<<1, 256, 0, st>>>(dF, A);
+  ORBX_LAUNCH(ctx);
+  if (kf1->n > 0) ORBX_CUDA(cudaMemcpyAsync(match12, A.match12, sizeof(int) * kf1->n, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaMemcpyAsync(nmatches, A.nmatches, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaStreamSynchronize(st));
+  return ORBX_OK;
+}
+
+}  // extern "C"

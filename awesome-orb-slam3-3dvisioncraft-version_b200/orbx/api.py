@@ -4,6 +4,7 @@ import os
 import re
 import subprocess
 import numpy as np
+from .abi import Frame, Camera, make_camera, ptr as _ptr, c32 as _c32  # noqa: F401
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _ROOT = os.path.dirname(_PKG)
@@ -70,6 +71,14 @@ def load_library():
     L.orbx_extract_batch_device.argtypes = [vp, i, vp, i, i, i, i, i, vp, vp, i, vp, vp]
     L.orbx_extractor_set_profiling.argtypes = [vp, i]
     L.orbx_extractor_stage_ms.argtypes = [vp, vp, vp]
+    L.orbx_descriptor_distance.argtypes = [vp, vp]
+    L.orbx_features_in_area.argtypes = [vp, vp, i, vp, vp, vp, vp, vp, vp, i, vp]
+    L.orbx_stereo_match.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, vp, i, f, f, vp, vp]
+    L.orbx_search_by_projection_map.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, f, f, vp, i, vp, vp]
+    L.orbx_search_by_projection_frame.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, f, i, i, vp, i,
+                                                  vp, vp, vp, vp]
+    L.orbx_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp,
+                                                vp, vp, vp, vp, i, i, i, i, vp, vp]
     L.orbx_pyramid_level.argtypes = [vp, i, i, vp, i, vp, vp]
     L.orbx_debug_candidates.argtypes = [vp, i, i, vp, vp, i, vp]
     _LIB = L
@@ -234,3 +243,93 @@ class ORBextractor:
         _check(load_library().orbx_debug_candidates(self.h, b, level, _p(xy), _p(sc), cap, C.byref(n)),
                "orbx_debug_candidates")
         return xy[:n.value].copy(), sc[:n.value].copy()
+
+
+class ORBmatcher:
+    """Mirror of ORB_SLAM3::ORBmatcher (include/ORBmatcher.h:35-108) for the hot-path overloads, on flat
+    arrays.  Results come back as index arrays; the C++ shim scatters them into Frame::mvpMapPoints."""
+
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
+
+    def __init__(self, ctx, nnratio=0.6, checkOri=True):
+        self.ctx, self.mfNNratio, self.mbCheckOrientation = ctx, float(nnratio), bool(checkOri)
+
+    @staticmethod
+    def DescriptorDistance(a, b):
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        return load_library().orbx_descriptor_distance(_p(a), _p(b))
+
+    def SearchByProjectionMap(self, F, kp_blocked, projX, projY, projXR, level, viewCos, mpDesc, flags, th,
+                              scaleFactors):
+        nq = len(projX)
+        best = np.full(nq, -1, np.int32)
+        nm = C.c_int(0)
+        a = [_c32(kp_blocked, np.uint8), _c32(projX, np.float32), _c32(projY, np.float32), _c32(projXR, np.float32),
+             _c32(level, np.int32), _c32(viewCos, np.float32), _c32(mpDesc, np.uint8), _c32(flags, np.uint8)]
+        sf = _c32(scaleFactors, np.float32)
+        rc = load_library().orbx_search_by_projection_map(self.ctx.h, F.ref(), _ptr(a[0]), nq, _ptr(a[1]), _ptr(a[2]),
+                                                          _ptr(a[3]), _ptr(a[4]), _ptr(a[5]), _ptr(a[6]), _ptr(a[7]),
+                                                          float(th), self.mfNNratio, _ptr(sf), len(sf), _p(best),
+                                                          C.byref(nm))
+        _check(rc, "orbx_search_by_projection_map")
+        return nm.value, best
+
+    def SearchByProjectionFrame(self, Cur, cur_blocked, cam, Tcw_cur, Tcw_last, flags, xw, octave, angle, mpDesc, th,
+                                bMono, scaleFactors):
+        nq = len(flags)
+        match = np.full(nq, -1, np.int32)
+        kept = np.zeros(nq, np.uint8)
+        cur_match = np.full(Cur.n, -1, np.int32)
+        nm = C.c_int(0)
+        a = [_c32(cur_blocked, np.uint8), _c32(Tcw_cur, np.float32), _c32(Tcw_last, np.float32),
+             _c32(flags, np.uint8), _c32(xw, np.float32), _c32(octave, np.int32), _c32(angle, np.float32),
+             _c32(mpDesc, np.uint8)]
+        sf = _c32(scaleFactors, np.float32)
+        rc = load_library().orbx_search_by_projection_frame(self.ctx.h, Cur.ref(), _ptr(a[0]), C.byref(cam), _ptr(a[1]),
+                                                            _ptr(a[2]), nq, _ptr(a[3]), _ptr(a[4]), _ptr(a[5]),
+                                                            _ptr(a[6]), _ptr(a[7]), float(th), int(bMono),
+                                                            int(self.mbCheckOrientation), _ptr(sf), len(sf), _p(match),
+                                                            _p(kept), _p(cur_match), C.byref(nm))
+        _check(rc, "orbx_search_by_projection_frame")
+        return nm.value, match, kept, cur_match
+
+    def SearchForTriangulation(self, KF1, KF2, has1, has2, fv1, fv2, cam1, cam2, R1w, t1w, R2w, t2w, sigma2,
+                               scaleFactors, bOnlyStereo=False, bCoarse=False):
+        """fv = (node_ids, offsets, indices) CSR of a DBoW2::FeatureVector."""
+        m12 = np.full(KF1.n, -1, np.int32)
+        nm = C.c_int(0)
+        f1 = [_c32(v, np.int32) for v in fv1]
+        f2 = [_c32(v, np.int32) for v in fv2]
+        a = [_c32(has1, np.uint8), _c32(has2, np.uint8), _c32(R1w, np.float32), _c32(t1w, np.float32),
+             _c32(R2w, np.float32), _c32(t2w, np.float32), _c32(sigma2, np.float32), _c32(scaleFactors, np.float32)]
+        rc = load_library().orbx_search_for_triangulation(
+            self.ctx.h, KF1.ref(), KF2.ref(), _ptr(a[0]), _ptr(a[1]), len(f1[0]), _ptr(f1[0]), _ptr(f1[1]), _ptr(f1[2]),
+            len(f2[0]), _ptr(f2[0]), _ptr(f2[1]), _ptr(f2[2]), C.byref(cam1), C.byref(cam2), _ptr(a[2]), _ptr(a[3]),
+            _ptr(a[4]), _ptr(a[5]), _ptr(a[6]), _ptr(a[7]), len(a[7]), int(bOnlyStereo), int(bCoarse),
+            int(self.mbCheckOrientation), _p(m12), C.byref(nm))
+        _check(rc, "orbx_search_for_triangulation")
+        return nm.value, m12
+
+
+def features_in_area(ctx, F, x, y, r, minLevel, maxLevel, cap=256):
+    nq = len(x)
+    out = np.full((nq, cap), -1, np.int32)
+    n = np.zeros(nq, np.int32)
+    a = [_c32(x, np.float32), _c32(y, np.float32), _c32(r, np.float32), _c32(minLevel, np.int32),
+         _c32(maxLevel, np.int32)]
+    _check(load_library().orbx_features_in_area(ctx.h, F.ref(), nq, *[_ptr(v) for v in a], _p(out), cap, _p(n)),
+           "orbx_features_in_area")
+    return out, n
+
+
+def stereo_match(ctx, extL, bL, extR, bR, kpL, descL, kpR, descR, bf, b):
+    """Frame::ComputeStereoMatches -> (mvuRight, mvDepth)."""
+    kpL, kpR = np.ascontiguousarray(kpL), np.ascontiguousarray(kpR)
+    descL, descR = np.ascontiguousarray(descL, np.uint8), np.ascontiguousarray(descR, np.uint8)
+    ur = np.empty(len(kpL), np.float32)
+    dp = np.empty(len(kpL), np.float32)
+    _check(load_library().orbx_stereo_match(ctx.h, extL.h, bL, extR.h, bR, _p(kpL), _p(descL), len(kpL), _p(kpR),
+                                            _p(descR), len(kpR), float(bf), float(b), _p(ur), _p(dp)),
+           "orbx_stereo_match")
+    return ur, dp

@@ -130,6 +130,106 @@ int orbx_extractor_stage_ms(orbx_ext *ext, float *ms, int *launches);
 int orbx_debug_candidates(orbx_ext *ext, int b, int level, int16_t *xy, uint8_t *score,
                           int cap, int *n_out);
 
+/* ====================================================================================
+ * Matchers.  A Frame / KeyFrame crosses the boundary as flat arrays (the shim flattens the
+ * reference's pointer graph once per call, under the same mutexes the reference takes).
+ * Only the pinhole, Nleft == -1 configuration (mono / rectified stereo / RGB-D) is covered;
+ * KannalaBrandt8 stereo-fisheye (mpCamera2) is out of scope.
+ * ================================================================================== */
+typedef struct orbx_frame_desc {
+  int32_t n;                 /* Frame::N */
+  const orbx_keypoint *kps;  /* mvKeysUn: x, y, octave, angle are read */
+  const uint8_t *desc;       /* mDescriptors, [n][32] */
+  const float *uright;       /* mvuRight [n]; NULL = monocular (all -1) */
+  float min_x, min_y, max_x, max_y; /* mnMinX, mnMinY, mnMaxX, mnMaxY (src/Frame.cc:147-152) */
+} orbx_frame_desc;
+
+typedef struct orbx_camera {
+  float fx, fy, cx, cy; /* Pinhole::mvParameters (src/CameraModels/Pinhole.cpp:31-50) */
+  float bf, b;          /* Frame::mbf, Frame::mb = mbf/fx (src/Frame.cc:166) */
+} orbx_camera;
+
+/* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2700-2716): Hamming distance of two
+ * 256-bit descriptors.  A static CPU helper in the reference (also called from Frame.cc,
+ * MapPoint.cc, LoopClosing.cc); provided here for the shim, computed on the host. */
+int orbx_descriptor_distance(const uint8_t *a, const uint8_t *b);
+
+/* Frame::AssignFeaturesToGrid + GetFeaturesInArea (src/Frame.cc:444-478,755-850) as a device
+ * primitive, exposed for tests: returns, for each of nq queries (x, y, r, minLevel, maxLevel),
+ * the indices GetFeaturesInArea would return, in the reference's order (cell column outer,
+ * cell row inner, insertion order inside a cell).  out_idx is [nq][cap], out_n is [nq]
+ * (the true count, which may exceed cap). */
+int orbx_features_in_area(orbx_ctx *ctx, const orbx_frame_desc *frame, int nq, const float *x,
+                          const float *y, const float *r, const int32_t *min_level,
+                          const int32_t *max_level, int32_t *out_idx, int cap, int32_t *out_n);
+
+/* Frame::ComputeStereoMatches (src/Frame.cc:955-1133).  extL/extR hold the pyramids
+ * (mvImagePyramid) of the extraction that produced the keypoints: image bL of extL's last call
+ * and image bR of extR's last call (extL may equal extR in batch mode).  Host arrays in,
+ * uright/depth [nL] out (-1 where unmatched). */
+int orbx_stereo_match(orbx_ctx *ctx, orbx_ext *extL, int bL, orbx_ext *extR, int bR,
+                      const orbx_keypoint *kpL, const uint8_t *descL, int nL,
+                      const orbx_keypoint *kpR, const uint8_t *descR, int nR, float bf, float b,
+                      float *uright, float *depth);
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)
+ * (src/ORBmatcher.cc:59-255), track-local-map search.
+ *   kp_blocked[n]   : 1 where F.mvpMapPoints[i] != NULL && Observations() > 0 at entry
+ *   per MapPoint q  : proj_x/proj_y/proj_xr = mTrackProjX/Y/XR, level = mnTrackScaleLevel,
+ *                     view_cos = mTrackViewCos, mp_desc = GetDescriptor(),
+ *                     flags bit0 = mbTrackInView && !isBad() && !(bFarPoints && depth > thFar),
+ *                           bit1 = Observations() > 0 (an assigned keypoint then blocks later queries)
+ *   th, nnratio     : the call's th and the matcher's mfNNratio
+ *   scale_factors   : F.mvScaleFactors [nlevels]
+ * Out: best_idx[nq] = keypoint the MapPoint was assigned to, or -1; *nmatches = return value.
+ * The caller replays  F.mvpMapPoints[best_idx[q]] = pMP_q  in increasing q. */
+int orbx_search_by_projection_map(orbx_ctx *ctx, const orbx_frame_desc *frame,
+                                  const uint8_t *kp_blocked, int nq, const float *proj_x,
+                                  const float *proj_y, const float *proj_xr, const int32_t *level,
+                                  const float *view_cos, const uint8_t *mp_desc,
+                                  const uint8_t *flags, float th, float nnratio,
+                                  const float *scale_factors, int nlevels, int32_t *best_idx,
+                                  int32_t *nmatches);
+
+/* ORBmatcher::SearchByProjection(Frame &Cur, const Frame &Last, th, bMono)
+ * (src/ORBmatcher.cc:2244-2509), motion-model search.
+ *   Tcw_cur / Tcw_last : 4x4 row-major float32 poses (mTcw)
+ *   per last-frame keypoint q (nq = Last.N): flags bit0 = mvpMapPoints[q] && !mvbOutlier[q],
+ *                     bit1 = Observations() > 0; xw[q][3] = GetWorldPos(); octave, angle of the
+ *                     last frame's keypoint; mp_desc = GetDescriptor()
+ * Out: match_idx[nq] = current keypoint chosen for q (before the rotation-histogram filter) or -1;
+ *      kept[nq] = 0 where the rotation filter removed the match; cur_match[n] = final
+ *      CurrentFrame.mvpMapPoints as a last-frame index or -1; *nmatches = return value. */
+int orbx_search_by_projection_frame(orbx_ctx *ctx, const orbx_frame_desc *cur,
+                                    const uint8_t *cur_blocked, const orbx_camera *cam,
+                                    const float *Tcw_cur, const float *Tcw_last, int nq,
+                                    const uint8_t *flags, const float *xw, const int32_t *octave,
+                                    const float *angle, const uint8_t *mp_desc, float th, int bMono,
+                                    int check_orientation, const float *scale_factors, int nlevels,
+                                    int32_t *match_idx, uint8_t *kept, int32_t *cur_match,
+                                    int32_t *nmatches);
+
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo, bCoarse)
+ * (src/ORBmatcher.cc:1138-1428); the F12 argument is unused by the reference overload.
+ *   kf1/kf2        : keypoints (mvKeysUn), descriptors, mvuRight of the two keyframes
+ *   has_mp1/2      : GetMapPoint(i) != NULL
+ *   fv*_node/off/idx : DBoW2::FeatureVector as CSR — node ids ascending [nn], offsets [nn+1],
+ *                     feature indices in the map's vector order
+ *   R1w,t1w,R2w,t2w : GetRotation()/GetTranslation() (row-major 3x3 / 3), float32
+ *   level_sigma2   : mvLevelSigma2 [nlevels]; scale_factors = mvScaleFactors [nlevels]
+ * Out: match12[n1] = vMatches12 after the rotation filter; *nmatches = return value. */
+int orbx_search_for_triangulation(orbx_ctx *ctx, const orbx_frame_desc *kf1,
+                                  const orbx_frame_desc *kf2, const uint8_t *has_mp1,
+                                  const uint8_t *has_mp2, int nn1, const int32_t *fv1_node,
+                                  const int32_t *fv1_off, const int32_t *fv1_idx, int nn2,
+                                  const int32_t *fv2_node, const int32_t *fv2_off,
+                                  const int32_t *fv2_idx, const orbx_camera *cam1,
+                                  const orbx_camera *cam2, const float *R1w, const float *t1w,
+                                  const float *R2w, const float *t2w, const float *level_sigma2,
+                                  const float *scale_factors, int nlevels, int only_stereo,
+                                  int coarse, int check_orientation, int32_t *match12,
+                                  int32_t *nmatches);
+
 #ifdef __cplusplus
 }
 #endif

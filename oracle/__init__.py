@@ -152,3 +152,122 @@ class Extractor:
         rc = lib().ork_candidates(self.h, level, _p(xy), _p(sc), cap, C.byref(n))
         assert rc == 0
         return xy[:n.value].copy(), sc[:n.value].copy()
+
+
+# ------------------------------------------------------------------------------------------------
+# matchers (oracle/ork_matcher.cpp).  `Frame` / `Camera` are the POD mirrors of include/orbx.h.
+# ------------------------------------------------------------------------------------------------
+def _frame_types():
+    import sys
+    pkg = os.path.join(os.path.dirname(_HERE), "awesome-orb-slam3-3dvisioncraft-version_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    from orbx import abi
+    return abi
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dt)
+
+
+def _pp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def descriptor_distance(a, b):
+    a, b = _c(a, np.uint8), _c(b, np.uint8)
+    f = lib().ork_descriptor_distance
+    f.argtypes = [C.c_void_p, C.c_void_p]
+    return f(_pp(a), _pp(b))
+
+
+def features_in_area(F, x, y, r, minLevel, maxLevel, cap=256):
+    nq = len(x)
+    out = np.full((nq, cap), -1, np.int32)
+    n = np.zeros(nq, np.int32)
+    a = [_c(x, np.float32), _c(y, np.float32), _c(r, np.float32), _c(minLevel, np.int32), _c(maxLevel, np.int32)]
+    f = lib().ork_features_in_area
+    f.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+    f(F.ref(), nq, *[_pp(v) for v in a], _pp(out), cap, _pp(n))
+    return out, n
+
+
+def stereo_match(pyrL, pyrR, kpL, descL, kpR, descR, scale, inv_scale, bf, b):
+    """pyrL/pyrR: lists of un-bordered uint8 level images."""
+    L = len(pyrL)
+    pl = [np.ascontiguousarray(p, np.uint8) for p in pyrL]
+    pr = [np.ascontiguousarray(p, np.uint8) for p in pyrR]
+    PL = (C.c_void_p * L)(*[p.ctypes.data for p in pl])
+    PR = (C.c_void_p * L)(*[p.ctypes.data for p in pr])
+    lw = np.array([p.shape[1] for p in pl], np.int32)
+    lh = np.array([p.shape[0] for p in pl], np.int32)
+    kpL, kpR = np.ascontiguousarray(kpL), np.ascontiguousarray(kpR)
+    descL, descR = _c(descL, np.uint8), _c(descR, np.uint8)
+    sc, isc = _c(scale, np.float32), _c(inv_scale, np.float32)
+    ur = np.empty(len(kpL), np.float32)
+    dp = np.empty(len(kpL), np.float32)
+    f = lib().ork_stereo_match
+    f.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
+                                     C.c_float, C.c_void_p, C.c_void_p]
+    f(PL, PR, _pp(lw), _pp(lh), _pp(kpL), _pp(descL), len(kpL), _pp(kpR), _pp(descR), len(kpR), _pp(sc), _pp(isc),
+      float(bf), float(b), _pp(ur), _pp(dp))
+    return ur, dp
+
+
+def search_by_projection_map(F, kp_blocked, projX, projY, projXR, level, viewCos, mpDesc, flags, th, nnratio,
+                             scaleFactors):
+    nq = len(projX)
+    best = np.full(nq, -1, np.int32)
+    nm = C.c_int(0)
+    a = [_c(kp_blocked, np.uint8), _c(projX, np.float32), _c(projY, np.float32), _c(projXR, np.float32),
+         _c(level, np.int32), _c(viewCos, np.float32), _c(mpDesc, np.uint8), _c(flags, np.uint8)]
+    if a[0] is None:
+        a[0] = np.zeros(F.n, np.uint8)
+    if a[3] is None:
+        a[3] = np.zeros(nq, np.float32)
+    sf = _c(scaleFactors, np.float32)
+    f = lib().ork_search_by_projection_map
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_void_p, C.c_int,
+                                                                        C.c_void_p, C.c_void_p]
+    f(F.ref(), _pp(a[0]), nq, *[_pp(v) for v in a[1:]], float(th), float(nnratio), _pp(sf), len(sf), _pp(best),
+      C.byref(nm))
+    return nm.value, best
+
+
+def search_by_projection_frame(Cur, cur_blocked, cam, Tcw_cur, Tcw_last, flags, xw, octave, angle, mpDesc, th, bMono,
+                               checkOri, scaleFactors):
+    nq = len(flags)
+    match = np.full(nq, -1, np.int32)
+    kept = np.zeros(nq, np.uint8)
+    cur_match = np.full(Cur.n, -1, np.int32)
+    nm = C.c_int(0)
+    blk = _c(cur_blocked, np.uint8)
+    if blk is None:
+        blk = np.zeros(Cur.n, np.uint8)
+    a = [_c(Tcw_cur, np.float32), _c(Tcw_last, np.float32)]
+    b = [_c(flags, np.uint8), _c(xw, np.float32), _c(octave, np.int32), _c(angle, np.float32), _c(mpDesc, np.uint8)]
+    sf = _c(scaleFactors, np.float32)
+    f = lib().ork_search_by_projection_frame
+    f.argtypes = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int] + \
+                 [C.c_void_p] * 4
+    f(Cur.ref(), _pp(blk), C.byref(cam), _pp(a[0]), _pp(a[1]), nq, *[_pp(v) for v in b], float(th), int(bMono),
+      int(checkOri), _pp(sf), len(sf), _pp(match), _pp(kept), _pp(cur_match), C.byref(nm))
+    return nm.value, match, kept, cur_match
+
+
+def search_for_triangulation(KF1, KF2, has1, has2, fv1, fv2, cam1, cam2, R1w, t1w, R2w, t2w, sigma2, scaleFactors,
+                             bOnlyStereo=False, bCoarse=False, checkOri=True):
+    m12 = np.full(KF1.n, -1, np.int32)
+    nm = C.c_int(0)
+    f1 = [_c(v, np.int32) for v in fv1]
+    f2 = [_c(v, np.int32) for v in fv2]
+    a = [_c(has1, np.uint8), _c(has2, np.uint8)]
+    g = [_c(R1w, np.float32), _c(t1w, np.float32), _c(R2w, np.float32), _c(t2w, np.float32), _c(sigma2, np.float32),
+         _c(scaleFactors, np.float32)]
+    f = lib().ork_search_for_triangulation
+    f.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_void_p] * 8 + \
+                 [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+    f(KF1.ref(), KF2.ref(), _pp(a[0]), _pp(a[1]), len(f1[0]), _pp(f1[0]), _pp(f1[1]), _pp(f1[2]), len(f2[0]),
+      _pp(f2[0]), _pp(f2[1]), _pp(f2[2]), C.byref(cam1), C.byref(cam2), *[_pp(v) for v in g], len(g[5]),
+      int(bOnlyStereo), int(bCoarse), int(checkOri), _pp(m12), C.byref(nm))
+    return nm.value, m12
