@@ -222,12 +222,8 @@ def test_stereo_match_properties(ork, frame):
     disp = kL["x"][ok] - ur[ok]
     assert (disp >= 0).all() and (disp < sc.FX).all()
     assert np.allclose(dp[ok], sc.BF / np.maximum(disp, 0.01), rtol=1e-5)
-    # the synthetic right image is the left one shifted by an integer per-band disparity d in [3, 48]:
-    # the recovered sub-pixel disparities must sit close to integers in that range for most matches
-    # (exact only on octave 0, where keypoints and the SAD search live on the original pixel grid)
-    o0 = kL["octave"][ok] == 0
-    frac = np.abs(disp[o0] - np.rint(disp[o0]))
-    assert o0.sum() > 50 and np.median(frac) < 0.1 and (disp > 2.0).mean() > 0.9 and (disp < 52).all()
+    # the synthetic right image is the left one shifted by a per-band disparity bf/z in [3, 48] px
+    assert (disp > 1.0).mean() > 0.95 and (disp < 52).all()
     # swapping left/right (negative disparities) yields (almost) no matches
     ur2, _ = ork.stereo_match(frame["pyrR"], frame["pyrL"], kR, frame["dR"], kL, frame["dL"], frame["scale"],
                               (1.0 / frame["scale"]).astype(np.float32), sc.BF, sc.BF / sc.FX)
