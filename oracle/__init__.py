@@ -271,3 +271,40 @@ def search_for_triangulation(KF1, KF2, has1, has2, fv1, fv2, cam1, cam2, R1w, t1
       _pp(f2[0]), _pp(f2[1]), _pp(f2[2]), C.byref(cam1), C.byref(cam2), *[_pp(v) for v in g], len(g[5]),
       int(bOnlyStereo), int(bCoarse), int(checkOri), _pp(m12), C.byref(nm))
     return nm.value, m12
+
+
+# ------------------------------------------------------------------------------------------------
+# optimisers (oracle/ork_optimizer.cpp)
+# ------------------------------------------------------------------------------------------------
+def pose_optimization(xw, obs, inv_sigma2, cam, Tcw):
+    """-> (Tcw_out[4,4] f32, outlier[E] u8, nInliers, iters[4])"""
+    xw, obs, inv_sigma2 = _c(xw, np.float32), _c(obs, np.float32), _c(inv_sigma2, np.float32)
+    T = np.array(Tcw, np.float32).reshape(4, 4).copy()
+    E = len(inv_sigma2)
+    outl = np.zeros(max(E, 1), np.uint8)
+    nin = C.c_int(0)
+    iters = np.zeros(4, np.int32)
+    f = lib().ork_pose_optimization
+    f.argtypes = [C.c_int] + [C.c_void_p] * 8
+    f(E, _pp(xw), _pp(obs), _pp(inv_sigma2), C.byref(cam), _pp(T), _pp(outl), C.byref(nin), _pp(iters))
+    return T, outl[:E].copy(), nin.value, iters
+
+
+def local_ba(kf_T, kf_fixed, mp_xyz, e_kf, e_mp, e_obs, e_inv_sigma2, cam, lambda_init=0.0, stop=None):
+    """-> (kf_T_out, mp_xyz_out, edge_bad, iters[2], status)"""
+    T = np.array(kf_T, np.float32).reshape(-1, 16).copy()
+    X = np.array(mp_xyz, np.float32).reshape(-1, 3).copy()
+    fixed = _c(kf_fixed, np.uint8)
+    ekf, emp = _c(e_kf, np.int32), _c(e_mp, np.int32)
+    obs, isg = _c(e_obs, np.float32), _c(e_inv_sigma2, np.float32)
+    E = len(ekf)
+    bad = np.zeros(max(E, 1), np.uint8)
+    iters = np.zeros(2, np.int32)
+    status = C.c_int(0)
+    st = _c(stop, np.uint8) if stop is not None else None
+    f = lib().ork_local_ba
+    f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + \
+                 [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(len(T), _pp(T), _pp(fixed), len(X), _pp(X), E, _pp(ekf), _pp(emp), _pp(obs), _pp(isg), C.byref(cam),
+      float(lambda_init), _pp(st), _pp(bad), _pp(iters), C.byref(status))
+    return T.reshape(-1, 4, 4), X, bad[:E].copy(), iters, status.value

@@ -1,0 +1,708 @@
+// ork_optimizer.cpp — ORACLE (test infrastructure): CPU restatement of the two non-linear optimisers on
+// the hot path and of the g2o machinery beneath them, on flat arrays, sequential, fp64.
+//
+//   Optimizer::PoseOptimization            src/Optimizer.cc:907-1272
+//   Optimizer::LocalBundleAdjustment       src/Optimizer.cc:1811-2523  (numeric core :1958-2352)
+//   OptimizationAlgorithmLevenberg::solve  Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-185
+//   BlockSolver buildSystem/solve/setLambda Thirdparty/g2o/g2o/core/block_solver.hpp:354-486,502-610
+//   Base{Unary,Binary}Edge::constructQuadraticForm  core/base_unary_edge.hpp:43-74, base_binary_edge.hpp:55-117
+//   RobustKernelHuber                      core/robust_kernel_impl.cpp:66-91 (dsqr is a *float* member, .h:84)
+//   SparseOptimizer::optimize/update       core/sparse_optimizer.cpp:354-434
+//   SE3Quat                                types/se3quat.h ; edges types/types_six_dof_expmap.cpp, src/OptimizableTypes.cpp
+//   Converter::toSE3Quat / toCvMat         src/Converter.cc:34-50
+//
+// Eigen is not vendored in the reference; its Quaterniond<->Matrix3d conversions, quaternion product and
+// LDLT are restated from their published algorithms.  Everything here is tolerance-level w.r.t. the true
+// reference (summation order, pivoting details), which is what the 1e-4 rad / 1e-3 m target allows.
+#include "ork.h"
+#include <algorithm>
+#include <cstring>
+#include <limits>
+
+namespace ork {
+
+struct Quat { double x, y, z, w; };
+struct SE3 { Quat r; double t[3]; };
+
+static Quat quat_from_R(const double R[9]) {   // Eigen quaternionbase_assign_impl<Matrix3d>
+  Quat q;
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    q.w = 0.5 * t;
+    t = 0.5 / t;
+    q.x = (R[7] - R[5]) * t;
+    q.y = (R[2] - R[6]) * t;
+    q.z = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i * 3 + i]) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1.0);
+    double v[3];
+    v[i] = 0.5 * t;
+    t = 0.5 / t;
+    q.w = (R[k * 3 + j] - R[j * 3 + k]) * t;
+    v[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+    v[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+    q.x = v[0]; q.y = v[1]; q.z = v[2];
+  }
+  return q;
+}
+static void quat_normalize(Quat& q) {   // SE3Quat::normalizeRotation
+  if (q.w < 0) { q.x = -q.x; q.y = -q.y; q.z = -q.z; q.w = -q.w; }
+  const double n = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  q.x /= n; q.y /= n; q.z /= n; q.w /= n;
+}
+static Quat quat_mul(const Quat& a, const Quat& b) {
+  Quat r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  return r;
+}
+static void quat_rot(const Quat& q, const double v[3], double out[3]) {   // Eigen _transformVector
+  double uv[3] = {q.y * v[2] - q.z * v[1], q.z * v[0] - q.x * v[2], q.x * v[1] - q.y * v[0]};
+  uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+  out[0] = v[0] + q.w * uv[0] + (q.y * uv[2] - q.z * uv[1]);
+  out[1] = v[1] + q.w * uv[1] + (q.z * uv[0] - q.x * uv[2]);
+  out[2] = v[2] + q.w * uv[2] + (q.x * uv[1] - q.y * uv[0]);
+}
+static void quat_to_R(const Quat& q, double R[9]) {   // Eigen toRotationMatrix
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+static SE3 se3_from_Tcw(const float* T) {   // Converter::toSE3Quat: float 4x4 -> SE3Quat(R,t)
+  double R[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i * 3 + j] = T[i * 4 + j];
+  SE3 s;
+  s.r = quat_from_R(R);
+  quat_normalize(s.r);
+  for (int i = 0; i < 3; ++i) s.t[i] = T[i * 4 + 3];
+  return s;
+}
+static void se3_to_Tcw(const SE3& s, float* T) {   // Converter::toCvMat(SE3Quat)
+  double R[9];
+  quat_to_R(s.r, R);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) T[i * 4 + j] = (float)R[i * 3 + j];
+    T[i * 4 + 3] = (float)s.t[i];
+  }
+  T[12] = T[13] = T[14] = 0.f;
+  T[15] = 1.f;
+}
+static void se3_map(const SE3& s, const double x[3], double out[3]) {
+  quat_rot(s.r, x, out);
+  out[0] += s.t[0]; out[1] += s.t[1]; out[2] += s.t[2];
+}
+static SE3 se3_mul(const SE3& a, const SE3& b) {   // SE3Quat::operator*
+  SE3 r = a;
+  double rt[3];
+  quat_rot(a.r, b.t, rt);
+  r.t[0] += rt[0]; r.t[1] += rt[1]; r.t[2] += rt[2];
+  r.r = quat_mul(a.r, b.r);
+  quat_normalize(r.r);
+  return r;
+}
+static void mat3_mul(const double A[9], const double B[9], double C[9]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+static SE3 se3_exp(const double u[6]) {   // SE3Quat::exp, update = [omega, upsilon]
+  const double* om = u;
+  const double* up = u + 3;
+  const double theta = std::sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+  const double O[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};
+  double O2[9], R[9], V[9];
+  mat3_mul(O, O, O2);
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (theta < 0.00001) {
+    for (int i = 0; i < 9; ++i) R[i] = I[i] + O[i] + O2[i];
+    for (int i = 0; i < 9; ++i) V[i] = R[i];
+  } else {
+    const double a = std::sin(theta) / theta, b = (1 - std::cos(theta)) / (theta * theta);
+    const double c = (theta - std::sin(theta)) / std::pow(theta, 3);
+    for (int i = 0; i < 9; ++i) R[i] = I[i] + a * O[i] + b * O2[i];
+    for (int i = 0; i < 9; ++i) V[i] = I[i] + b * O[i] + c * O2[i];
+  }
+  SE3 s;
+  s.r = quat_from_R(R);
+  quat_normalize(s.r);
+  for (int i = 0; i < 3; ++i) s.t[i] = V[i * 3] * up[0] + V[i * 3 + 1] * up[1] + V[i * 3 + 2] * up[2];
+  return s;
+}
+
+struct Huber {
+  double delta;
+  float dsqr;   // float member in the reference (robust_kernel_impl.h:84)
+  explicit Huber(float d) : delta(d), dsqr((float)((double)d * (double)d)) {}
+  // returns rho[0] and sets w = rho[1]
+  double robustify(double e, double& w) const {
+    if (e <= dsqr) { w = 1.; return e; }
+    const double sqrte = std::sqrt(e);
+    w = delta / sqrte;
+    return 2 * sqrte * delta - dsqr;
+  }
+};
+
+// Eigen::LDLT-style factorisation with diagonal pivoting (largest |diagonal| first); solves A x = b.
+// Returns false when a negative pivot appears (Eigen::LDLT::isPositive() == false).
+static bool ldlt_solve_pivoted(int n, const double* Ain, const double* b, double* x) {
+  std::vector<double> A(Ain, Ain + (size_t)n * n);
+  std::vector<int> perm(n);
+  for (int i = 0; i < n; ++i) perm[i] = i;
+  bool positive = true;
+  for (int k = 0; k < n; ++k) {
+    int p = k;
+    double best = std::fabs(A[(size_t)k * n + k]);
+    for (int i = k + 1; i < n; ++i)
+      if (std::fabs(A[(size_t)i * n + i]) > best) { best = std::fabs(A[(size_t)i * n + i]); p = i; }
+    if (p != k) {
+      for (int j = 0; j < n; ++j) std::swap(A[(size_t)k * n + j], A[(size_t)p * n + j]);
+      for (int i = 0; i < n; ++i) std::swap(A[(size_t)i * n + k], A[(size_t)i * n + p]);
+      std::swap(perm[k], perm[p]);
+    }
+    const double d = A[(size_t)k * n + k];
+    if (d < 0) positive = false;
+    if (d == 0) continue;
+    for (int i = k + 1; i < n; ++i) A[(size_t)i * n + k] /= d;
+    for (int i = k + 1; i < n; ++i)
+      for (int j = k + 1; j <= i; ++j) {
+        A[(size_t)i * n + j] -= A[(size_t)i * n + k] * d * A[(size_t)j * n + k];
+        A[(size_t)j * n + i] = A[(size_t)i * n + j];
+      }
+  }
+  if (!positive) return false;
+  std::vector<double> y(n);
+  for (int i = 0; i < n; ++i) y[i] = b[perm[i]];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) y[i] -= A[(size_t)i * n + j] * y[j];
+  for (int i = 0; i < n; ++i) {
+    const double d = A[(size_t)i * n + i];
+    y[i] = (d != 0) ? y[i] / d : 0.0;
+  }
+  for (int i = n - 1; i >= 0; --i)
+    for (int j = i + 1; j < n; ++j) y[i] -= A[(size_t)j * n + i] * y[j];
+  for (int i = 0; i < n; ++i) x[perm[i]] = y[i];
+  return true;
+}
+
+// SimplicialLDLT stand-in for the reduced camera system: un-pivoted LDL^T; fails on a zero pivot.
+static bool ldlt_solve_plain(int n, const double* Ain, const double* b, double* x) {
+  std::vector<double> A(Ain, Ain + (size_t)n * n);
+  for (int k = 0; k < n; ++k) {
+    const double d = A[(size_t)k * n + k];
+    if (d == 0 || !std::isfinite(d)) return false;
+    for (int i = k + 1; i < n; ++i) A[(size_t)i * n + k] /= d;
+    for (int i = k + 1; i < n; ++i)
+      for (int j = k + 1; j <= i; ++j) A[(size_t)i * n + j] -= A[(size_t)i * n + k] * d * A[(size_t)j * n + k];
+  }
+  std::vector<double> y(b, b + n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) y[i] -= A[(size_t)i * n + j] * y[j];
+  for (int i = 0; i < n; ++i) y[i] /= A[(size_t)i * n + i];
+  for (int i = n - 1; i >= 0; --i)
+    for (int j = n - 1; j > i; --j) y[i] -= A[(size_t)j * n + i] * y[j];
+  for (int i = 0; i < n; ++i) x[i] = y[i];
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Levenberg-Marquardt as modified in the reference's g2o.  `P` supplies the problem.
+// ------------------------------------------------------------------------------------------------
+template <typename P>
+static int lm_optimize(P& prob, int iterations, double userLambdaInit, const volatile uint8_t* stop) {
+  double lambda = -1, ni = 2;
+  int nBad = 0, cj = 0;
+  bool ok = true;
+  auto terminate = [&]() { return stop && *stop; };
+  for (int it = 0; it < iterations && !terminate() && ok; ++it) {
+    prob.computeErrors();
+    double currentChi = prob.robustChi2();
+    double tempChi = currentChi;
+    const double iniChi = currentChi;
+    prob.buildSystem();
+    if (it == 0) {
+      lambda = userLambdaInit > 0 ? userLambdaInit : 1e-50 * prob.maxDiagonal();
+      ni = 2;
+      nBad = 0;
+    }
+    double rho = 0;
+    int qmax = 0;
+    do {
+      prob.push();
+      const bool ok2 = prob.solve(lambda);
+      prob.update();
+      prob.computeErrors();
+      tempChi = prob.robustChi2();
+      if (!ok2) tempChi = std::numeric_limits<double>::max();
+      rho = currentChi - tempChi;
+      double scale = prob.computeScale(lambda);
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - std::pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, 2. / 3.);
+        const double scaleFactor = std::max(1. / 3., alpha);
+        lambda *= scaleFactor;
+        ni = 2;
+        currentChi = tempChi;
+      } else {
+        lambda *= ni;
+        ni *= 2;
+        prob.pop();
+      }
+      ++qmax;
+    } while (rho < 0 && qmax < 100 && !terminate());
+    ++cj;
+    if (qmax == 100 || rho == 0) { ok = false; continue; }   // Terminate
+    if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
+    if (nBad >= 3) ok = false;
+  }
+  return cj;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PoseOptimization
+// ------------------------------------------------------------------------------------------------
+struct PoseProblem {
+  int E;
+  const float* xw;
+  const float* obs;
+  const float* invSigma2;
+  orbx_camera cam;
+  std::vector<uint8_t> active, stereo;
+  std::vector<double> err;   // [E][3] error of the last evaluated state ("stale" semantics)
+  bool robust = true;
+  Huber hMono, hStereo;
+  SE3 est, backup;
+  double H[36], b[6], x[6];
+  PoseProblem() : hMono((float)std::sqrt(5.991)), hStereo((float)std::sqrt(7.815)) {}
+
+  void edge_error(int e, const SE3& T, double* out) const {
+    const double X[3] = {xw[3 * e], xw[3 * e + 1], xw[3 * e + 2]};
+    double p[3];
+    se3_map(T, X, p);
+    if (!stereo[e]) {
+      // obs - Pinhole::project (float parameters widen to double)
+      out[0] = (double)obs[3 * e] - ((double)cam.fx * p[0] / p[2] + (double)cam.cx);
+      out[1] = (double)obs[3 * e + 1] - ((double)cam.fy * p[1] / p[2] + (double)cam.cy);
+      out[2] = 0;
+    } else {
+      const float invz = (float)(1.0f / p[2]);   // types_six_dof_expmap.cpp:340 (float!)
+      const double u = p[0] * invz * (double)cam.fx + (double)cam.cx;
+      const double v = p[1] * invz * (double)cam.fy + (double)cam.cy;
+      out[0] = (double)obs[3 * e] - u;
+      out[1] = (double)obs[3 * e + 1] - v;
+      out[2] = (double)obs[3 * e + 2] - (u - (double)cam.bf * invz);
+    }
+  }
+  double chi2(int e) const {
+    const double w = (double)invSigma2[e];
+    const double* r = &err[3 * e];
+    return r[0] * w * r[0] + r[1] * w * r[1] + (stereo[e] ? r[2] * w * r[2] : 0.0);
+  }
+  void computeErrors() {
+    for (int e = 0; e < E; ++e)
+      if (active[e]) edge_error(e, est, &err[3 * e]);
+  }
+  double robustChi2() const {
+    double chi = 0;
+    for (int e = 0; e < E; ++e) {
+      if (!active[e]) continue;
+      const double c = chi2(e);
+      double w;
+      chi += robust ? (stereo[e] ? hStereo : hMono).robustify(c, w) : c;
+    }
+    return chi;
+  }
+  void buildSystem() {
+    std::memset(H, 0, sizeof H);
+    std::memset(b, 0, sizeof b);
+    for (int e = 0; e < E; ++e) {
+      if (!active[e]) continue;
+      const double X[3] = {xw[3 * e], xw[3 * e + 1], xw[3 * e + 2]};
+      double p[3];
+      se3_map(est, X, p);
+      double J[18];
+      int D;
+      const double fx = cam.fx, fy = cam.fy, bf = cam.bf;
+      if (!stereo[e]) {
+        D = 2;
+        const double x = p[0], y = p[1], z = p[2];
+        // -projectJac * [ -[p]x | I ]   (OptimizableTypes.cpp:50-65)
+        const double j00 = fx / z, j02 = -fx * x / (z * z), j11 = fy / z, j12 = -fy * y / (z * z);
+        const double S[18] = {0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1};
+        for (int c = 0; c < 6; ++c) {
+          J[c] = -(j00 * S[c] + j02 * S[12 + c]);
+          J[6 + c] = -(j11 * S[6 + c] + j12 * S[12 + c]);
+        }
+      } else {
+        D = 3;
+        const double x = p[0], y = p[1], invz = 1.0 / p[2], invz2 = invz * invz;
+        J[0] = x * y * invz2 * fx; J[1] = -(1 + (x * x * invz2)) * fx; J[2] = y * invz * fx;
+        J[3] = -invz * fx; J[4] = 0; J[5] = x * invz2 * fx;
+        J[6] = (1 + y * y * invz2) * fy; J[7] = -x * y * invz2 * fy; J[8] = -x * invz * fy;
+        J[9] = 0; J[10] = -invz * fy; J[11] = y * invz2 * fy;
+        J[12] = J[0] - bf * y * invz2; J[13] = J[1] + bf * x * invz2; J[14] = J[2];
+        J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf * invz2;
+      }
+      const double om = (double)invSigma2[e];
+      double w = 1.0;
+      if (robust) (stereo[e] ? hStereo : hMono).robustify(chi2(e), w);
+      const double* r = &err[3 * e];
+      for (int i = 0; i < 6; ++i) {
+        double s = 0;
+        for (int d = 0; d < D; ++d) s += J[d * 6 + i] * om * r[d];
+        b[i] -= w * s;
+        for (int j = 0; j < 6; ++j) {
+          double a = 0;
+          for (int d = 0; d < D; ++d) a += J[d * 6 + i] * (w * om) * J[d * 6 + j];
+          H[i * 6 + j] += a;
+        }
+      }
+    }
+  }
+  double maxDiagonal() const {
+    double m = 0;
+    for (int i = 0; i < 6; ++i) m = std::max(std::fabs(H[i * 6 + i]), m);
+    return m;
+  }
+  void push() { backup = est; }
+  void pop() { est = backup; }
+  bool solve(double lambda) {
+    double A[36];
+    std::memcpy(A, H, sizeof A);
+    for (int i = 0; i < 6; ++i) A[i * 6 + i] += lambda;
+    for (int i = 0; i < 6; ++i) x[i] = 0;   // (_x keeps its previous content on failure; zero is used on the first)
+    return ldlt_solve_pivoted(6, A, b, x);
+  }
+  void update() { est = se3_mul(se3_exp(x), est); }
+  double computeScale(double lambda) const {
+    double s = 0;
+    for (int j = 0; j < 6; ++j) s += x[j] * (lambda * x[j] + b[j]);
+    return s;
+  }
+};
+
+}  // namespace ork
+
+using namespace ork;
+
+extern "C" {
+
+int ork_pose_optimization(int E, const float* xw, const float* obs, const float* invSigma2, const orbx_camera* cam,
+                          float* Tcw, uint8_t* outlier, int* nInliers, int* iters) {
+  for (int r = 0; r < 4; ++r) iters[r] = 0;
+  *nInliers = 0;
+  if (E < 3) return ORBX_OK;   // nInitialCorrespondences<3 -> return 0, pose untouched
+  PoseProblem P;
+  P.E = E;
+  P.xw = xw;
+  P.obs = obs;
+  P.invSigma2 = invSigma2;
+  P.cam = *cam;
+  P.active.assign(E, 1);
+  P.stereo.resize(E);
+  P.err.assign((size_t)3 * E, 0.0);
+  for (int e = 0; e < E; ++e) { P.stereo[e] = obs[3 * e + 2] >= 0; outlier[e] = 0; }
+  const float chi2Mono = 5.991f, chi2Stereo = 7.815f;
+  const SE3 init = se3_from_Tcw(Tcw);
+  int nBad = 0;
+  for (int it = 0; it < 4; ++it) {
+    P.est = init;                       // vSE3->setEstimate(toSE3Quat(pFrame->mTcw)) every round
+    for (int e = 0; e < E; ++e) P.active[e] = !outlier[e];   // initializeOptimization(0): level-0 edges
+    iters[it] = lm_optimize(P, 10, 0.0, nullptr);
+    nBad = 0;
+    for (int e = 0; e < E; ++e) {
+      if (outlier[e]) P.edge_error(e, P.est, &P.err[3 * e]);   // e->computeError() for excluded edges
+      const float chi2 = (float)P.chi2(e);
+      if (chi2 > (P.stereo[e] ? chi2Stereo : chi2Mono)) { outlier[e] = 1; ++nBad; }
+      else outlier[e] = 0;
+    }
+    if (it == 2) P.robust = false;      // e->setRobustKernel(0)
+    if (E < 10) break;                  // optimizer.edges().size()<10
+  }
+  se3_to_Tcw(P.est, Tcw);
+  *nInliers = E - nBad;
+  return ORBX_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// LocalBundleAdjustment (numeric core): poses (some fixed) + marginalised points, Schur complement.
+// ------------------------------------------------------------------------------------------------
+namespace ork {
+
+struct LbaProblem {
+  int K, M, E;
+  std::vector<SE3> pose, poseBackup;
+  std::vector<double> pt, ptBackup;       // [M][3]
+  const uint8_t* fixed;
+  const int* ekf;
+  const int* emp;
+  const float* obs;
+  const float* invSigma2;
+  orbx_camera cam;
+  std::vector<uint8_t> stereo;
+  std::vector<double> err;                // [E][3]
+  Huber hMono, hStereo;
+  std::vector<int> hidx;                  // pose -> index among free poses or -1
+  int nFree = 0;
+  std::vector<double> Hpp, Hll, Hpl;      // [nFree][36], [M][9], [E][18] (6x3 per edge, row-major)
+  std::vector<double> b, x;               // [6 nFree + 3 M]
+  LbaProblem() : hMono((float)std::sqrt(5.991)), hStereo((float)std::sqrt(7.815)) {}
+
+  void edge_error(int e, double* out) const {
+    double p[3];
+    se3_map(pose[ekf[e]], &pt[3 * emp[e]], p);
+    if (!stereo[e]) {
+      out[0] = (double)obs[3 * e] - ((double)cam.fx * p[0] / p[2] + (double)cam.cx);
+      out[1] = (double)obs[3 * e + 1] - ((double)cam.fy * p[1] / p[2] + (double)cam.cy);
+      out[2] = 0;
+    } else {
+      const float invz = (float)(1.0f / p[2]);   // types_six_dof_expmap.cpp:191
+      const double u = p[0] * invz * (double)cam.fx + (double)cam.cx;
+      const double v = p[1] * invz * (double)cam.fy + (double)cam.cy;
+      out[0] = (double)obs[3 * e] - u;
+      out[1] = (double)obs[3 * e + 1] - v;
+      out[2] = (double)obs[3 * e + 2] - (u - (double)cam.bf * invz);
+    }
+  }
+  double chi2(int e) const {
+    const double w = (double)invSigma2[e];
+    const double* r = &err[3 * e];
+    return r[0] * w * r[0] + r[1] * w * r[1] + (stereo[e] ? r[2] * w * r[2] : 0.0);
+  }
+  bool depthPositive(int e) const {
+    double p[3];
+    se3_map(pose[ekf[e]], &pt[3 * emp[e]], p);
+    return p[2] > 0.0;
+  }
+  void computeErrors() { for (int e = 0; e < E; ++e) edge_error(e, &err[3 * e]); }
+  double robustChi2() const {
+    double chi = 0, w;
+    for (int e = 0; e < E; ++e) chi += (stereo[e] ? hStereo : hMono).robustify(chi2(e), w);
+    return chi;
+  }
+  void buildSystem() {
+    std::fill(Hpp.begin(), Hpp.end(), 0.0);
+    std::fill(Hll.begin(), Hll.end(), 0.0);
+    std::fill(Hpl.begin(), Hpl.end(), 0.0);
+    std::fill(b.begin(), b.end(), 0.0);
+    const double fx = cam.fx, fy = cam.fy, bf = cam.bf;
+    for (int e = 0; e < E; ++e) {
+      const int k = ekf[e], m = emp[e];
+      double p[3], R[9];
+      se3_map(pose[k], &pt[3 * m], p);
+      quat_to_R(pose[k].r, R);
+      const double x = p[0], y = p[1], z = p[2];
+      double Ji[9], Jj[18];   // d err / d point (Dx3), d err / d pose (Dx6)
+      int D;
+      if (!stereo[e]) {
+        D = 2;
+        // projectJac = -pCamera->projectJac ; Ji = projectJac * R ; Jj = projectJac * SE3deriv
+        const double j00 = -(fx / z), j02 = fx * x / (z * z), j11 = -(fy / z), j12 = fy * y / (z * z);
+        for (int c = 0; c < 3; ++c) {
+          Ji[c] = j00 * R[c] + j02 * R[6 + c];
+          Ji[3 + c] = j11 * R[3 + c] + j12 * R[6 + c];
+        }
+        const double S[18] = {0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1};
+        for (int c = 0; c < 6; ++c) {
+          Jj[c] = j00 * S[c] + j02 * S[12 + c];
+          Jj[6 + c] = j11 * S[6 + c] + j12 * S[12 + c];
+        }
+      } else {
+        D = 3;
+        const double z2 = z * z;
+        for (int c = 0; c < 3; ++c) {
+          Ji[c] = -fx * R[c] / z + fx * x * R[6 + c] / z2;
+          Ji[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z2;
+          Ji[6 + c] = Ji[c] - bf * R[6 + c] / z2;
+        }
+        Jj[0] = x * y / z2 * fx; Jj[1] = -(1 + (x * x / z2)) * fx; Jj[2] = y / z * fx;
+        Jj[3] = -1. / z * fx; Jj[4] = 0; Jj[5] = x / z2 * fx;
+        Jj[6] = (1 + y * y / z2) * fy; Jj[7] = -x * y / z2 * fy; Jj[8] = -x / z * fy;
+        Jj[9] = 0; Jj[10] = -1. / z * fy; Jj[11] = y / z2 * fy;
+        Jj[12] = Jj[0] - bf * y / z2; Jj[13] = Jj[1] + bf * x / z2; Jj[14] = Jj[2];
+        Jj[15] = Jj[3]; Jj[16] = 0; Jj[17] = Jj[5] - bf / z2;
+      }
+      const double om = (double)invSigma2[e];
+      double w;
+      (stereo[e] ? hStereo : hMono).robustify(chi2(e), w);
+      const double* r = &err[3 * e];
+      double omr[3];
+      for (int d = 0; d < D; ++d) omr[d] = -om * r[d] * w;   // omega_r *= rho[1]
+      const double wo = w * om;
+      // point (vertex 0, "from"): never fixed
+      double* bl = &b[6 * nFree + 3 * m];
+      double* hl = &Hll[9 * (size_t)m];
+      for (int i = 0; i < 3; ++i) {
+        double s = 0;
+        for (int d = 0; d < D; ++d) s += Ji[d * 3 + i] * omr[d];
+        bl[i] += s;
+        for (int j = 0; j < 3; ++j) {
+          double a = 0;
+          for (int d = 0; d < D; ++d) a += Ji[d * 3 + i] * wo * Ji[d * 3 + j];
+          hl[i * 3 + j] += a;
+        }
+      }
+      const int hk = hidx[k];
+      if (hk >= 0) {
+        double* bp = &b[6 * hk];
+        double* hp = &Hpp[36 * (size_t)hk];
+        double* hpl = &Hpl[18 * (size_t)e];
+        for (int i = 0; i < 6; ++i) {
+          double s = 0;
+          for (int d = 0; d < D; ++d) s += Jj[d * 6 + i] * omr[d];
+          bp[i] += s;
+          for (int j = 0; j < 6; ++j) {
+            double a = 0;
+            for (int d = 0; d < D; ++d) a += Jj[d * 6 + i] * wo * Jj[d * 6 + j];
+            hp[i * 6 + j] += a;
+          }
+          for (int j = 0; j < 3; ++j) {
+            double a = 0;
+            for (int d = 0; d < D; ++d) a += Jj[d * 6 + i] * wo * Ji[d * 3 + j];
+            hpl[i * 3 + j] += a;   // pose-landmark block of this observation
+          }
+        }
+      }
+    }
+  }
+  double maxDiagonal() const {
+    double m = 0;
+    for (int k = 0; k < nFree; ++k)
+      for (int i = 0; i < 6; ++i) m = std::max(std::fabs(Hpp[36 * (size_t)k + i * 6 + i]), m);
+    for (int p = 0; p < M; ++p)
+      for (int i = 0; i < 3; ++i) m = std::max(std::fabs(Hll[9 * (size_t)p + i * 3 + i]), m);
+    return m;
+  }
+  void push() { poseBackup = pose; ptBackup = pt; }
+  void pop() { pose = poseBackup; pt = ptBackup; }
+  std::vector<std::vector<int>> edgesOfPoint;   // observation lists per point (free poses only)
+  bool solve(double lambda) {
+    const int n = 6 * nFree;
+    std::vector<double> S((size_t)n * n, 0.0), bs(b.begin(), b.begin() + n), Dinv((size_t)9 * M);
+    for (int k = 0; k < nFree; ++k)
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) S[(size_t)(6 * k + i) * n + 6 * k + j] = Hpp[36 * (size_t)k + i * 6 + j] + (i == j ? lambda : 0.0);
+    for (int m = 0; m < M; ++m) {
+      double D[9];
+      for (int i = 0; i < 9; ++i) D[i] = Hll[9 * (size_t)m + i];
+      D[0] += lambda; D[4] += lambda; D[8] += lambda;
+      // Matrix3d::inverse(): cofactors / determinant
+      const double c00 = D[4] * D[8] - D[5] * D[7], c01 = D[5] * D[6] - D[3] * D[8], c02 = D[3] * D[7] - D[4] * D[6];
+      const double det = D[0] * c00 + D[1] * c01 + D[2] * c02, id = 1.0 / det;
+      double* Di = &Dinv[9 * (size_t)m];
+      Di[0] = c00 * id; Di[1] = (D[2] * D[7] - D[1] * D[8]) * id; Di[2] = (D[1] * D[5] - D[2] * D[4]) * id;
+      Di[3] = c01 * id; Di[4] = (D[0] * D[8] - D[2] * D[6]) * id; Di[5] = (D[2] * D[3] - D[0] * D[5]) * id;
+      Di[6] = c02 * id; Di[7] = (D[1] * D[6] - D[0] * D[7]) * id; Di[8] = (D[0] * D[4] - D[1] * D[3]) * id;
+      const double* bl = &b[n + 3 * m];
+      double db[3];
+      for (int i = 0; i < 3; ++i) db[i] = Di[i * 3] * bl[0] + Di[i * 3 + 1] * bl[1] + Di[i * 3 + 2] * bl[2];
+      const std::vector<int>& obsE = edgesOfPoint[m];
+      for (size_t a = 0; a < obsE.size(); ++a) {
+        const int e1 = obsE[a], k1 = hidx[ekf[e1]];
+        const double* B1 = &Hpl[18 * (size_t)e1];
+        double BD[18];
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 3; ++j) BD[i * 3 + j] = B1[i * 3] * Di[j] + B1[i * 3 + 1] * Di[3 + j] + B1[i * 3 + 2] * Di[6 + j];
+        for (int i = 0; i < 6; ++i) bs[6 * k1 + i] -= B1[i * 3] * db[0] + B1[i * 3 + 1] * db[1] + B1[i * 3 + 2] * db[2];
+        for (size_t c = 0; c < obsE.size(); ++c) {
+          const int e2 = obsE[c], k2 = hidx[ekf[e2]];
+          const double* B2 = &Hpl[18 * (size_t)e2];
+          for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j)
+              S[(size_t)(6 * k1 + i) * n + 6 * k2 + j] -= BD[i * 3] * B2[j * 3] + BD[i * 3 + 1] * B2[j * 3 + 1] + BD[i * 3 + 2] * B2[j * 3 + 2];
+        }
+      }
+    }
+    std::fill(x.begin(), x.end(), 0.0);
+    if (n > 0 && !ldlt_solve_plain(n, S.data(), bs.data(), x.data())) return false;
+    // landmarks: xl = Dinv (bl - Hpl^T xp)
+    for (int m = 0; m < M; ++m) {
+      double cl[3] = {b[n + 3 * m], b[n + 3 * m + 1], b[n + 3 * m + 2]};
+      for (int e : edgesOfPoint[m]) {
+        const int k = hidx[ekf[e]];
+        const double* B = &Hpl[18 * (size_t)e];
+        for (int j = 0; j < 3; ++j)
+          for (int i = 0; i < 6; ++i) cl[j] -= B[i * 3 + j] * x[6 * k + i];
+      }
+      const double* Di = &Dinv[9 * (size_t)m];
+      for (int i = 0; i < 3; ++i) x[n + 3 * m + i] = Di[i * 3] * cl[0] + Di[i * 3 + 1] * cl[1] + Di[i * 3 + 2] * cl[2];
+    }
+    return true;
+  }
+  void update() {
+    for (int k = 0; k < K; ++k)
+      if (hidx[k] >= 0) pose[k] = se3_mul(se3_exp(&x[6 * hidx[k]]), pose[k]);
+    const int n = 6 * nFree;
+    for (int i = 0; i < 3 * M; ++i) pt[i] += x[n + i];
+  }
+  double computeScale(double lambda) const {
+    double s = 0;
+    for (size_t j = 0; j < x.size(); ++j) s += x[j] * (lambda * x[j] + b[j]);
+    return s;
+  }
+};
+
+}  // namespace ork
+
+extern "C" {
+
+// Numeric core of LocalBundleAdjustment.  Outputs: poses/points written back (float) unless aborted;
+// edge_bad[e] = 1 where the final chi2/depth test fails (vToErase); *status: 0 ok, 1 aborted by the stop
+// flag before optimising, 2 rejected by the >=50 % outlier sanity check (nothing written back).
+int ork_local_ba(int K, float* kfT, const uint8_t* kfFixed, int M, float* mpXyz, int E, const int* ekf, const int* emp,
+                 const float* obs, const float* invSigma2, const orbx_camera* cam, double lambdaInit,
+                 const volatile uint8_t* stop, uint8_t* edgeBad, int* iters, int* status) {
+  iters[0] = iters[1] = 0;
+  *status = 0;
+  for (int e = 0; e < E; ++e) edgeBad[e] = 0;
+  if (stop && *stop) { *status = 1; return ORBX_OK; }
+  LbaProblem P;
+  P.K = K; P.M = M; P.E = E;
+  P.fixed = kfFixed; P.ekf = ekf; P.emp = emp; P.obs = obs; P.invSigma2 = invSigma2; P.cam = *cam;
+  P.pose.resize(K);
+  for (int k = 0; k < K; ++k) P.pose[k] = se3_from_Tcw(kfT + 16 * k);
+  P.pt.resize((size_t)3 * M);
+  for (int i = 0; i < 3 * M; ++i) P.pt[i] = mpXyz[i];
+  P.stereo.resize(E);
+  for (int e = 0; e < E; ++e) P.stereo[e] = obs[3 * e + 2] >= 0;
+  P.err.assign((size_t)3 * E, 0.0);
+  P.hidx.assign(K, -1);
+  for (int k = 0; k < K; ++k)
+    if (!kfFixed[k]) P.hidx[k] = P.nFree++;
+  P.Hpp.assign((size_t)36 * P.nFree, 0.0);
+  P.Hll.assign((size_t)9 * M, 0.0);
+  P.Hpl.assign((size_t)18 * E, 0.0);
+  P.b.assign((size_t)6 * P.nFree + 3 * M, 0.0);
+  P.x.assign(P.b.size(), 0.0);
+  P.edgesOfPoint.assign(M, {});
+  for (int e = 0; e < E; ++e)
+    if (P.hidx[ekf[e]] >= 0) P.edgesOfPoint[emp[e]].push_back(e);
+  iters[0] = lm_optimize(P, 5, lambdaInit, stop);
+  bool doMore = !(stop && *stop);
+  if (doMore) iters[1] = lm_optimize(P, 10, lambdaInit, stop);
+  int nBad = 0;
+  for (int e = 0; e < E; ++e) {
+    const double c = P.chi2(e);
+    if (c > (P.stereo[e] ? 7.815 : 5.991) || !P.depthPositive(e)) { edgeBad[e] = 1; ++nBad; }
+  }
+  if (nBad >= E * 0.5) { *status = 2; return ORBX_OK; }
+  for (int k = 0; k < K; ++k)
+    if (!kfFixed[k]) se3_to_Tcw(P.pose[k], kfT + 16 * k);
+  for (int i = 0; i < 3 * M; ++i) mpXyz[i] = (float)P.pt[i];
+  return ORBX_OK;
+}
+
+}  // extern "C"

@@ -145,3 +145,104 @@ def tri_scenario(seed, kps, desc, uright=None, baseline=0.25, rot_deg=2.0, nword
                 R2w=R2.astype(np.float32).ravel(), t2w=t2.astype(np.float32),
                 sigma2=((np.float32(1.2) ** np.arange(8)) ** 2).astype(np.float32),
                 scaleFactors=(np.float32(1.2) ** np.arange(8)).astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------------
+# optimiser scenes
+# ------------------------------------------------------------------------------------------------
+def se3_matrix(R, t):
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = R, t
+    return T
+
+
+def rot_err_deg(Ra, Rb):
+    c = (np.trace(Ra.T @ Rb) - 1) / 2
+    return np.degrees(np.arccos(np.clip(c, -1, 1)))
+
+
+def pose_opt_scenario(seed, E=300, stereo_frac=0.7, outlier_frac=0.2, rot_deg=2.0, trans=0.05):
+    """E 3-D points seen from a ground-truth pose; pixel noise sigma = scale[octave]; gross outliers;
+    initial pose perturbed by (rot_deg, trans)."""
+    rng = np.random.default_rng(seed)
+    scale = 1.2 ** np.arange(8)
+    R = rot_small(rng, rng.uniform(0, 30))
+    t = rng.uniform(-1, 1, 3)
+    Tgt = se3_matrix(R, t)
+    z = rng.uniform(1.5, 15, E)
+    u = rng.uniform(30, 722, E)
+    v = rng.uniform(30, 450, E)
+    Xc = np.stack([(u - CX) / FX * z, (v - CY) / FY * z, z], 1)
+    Xw = (Xc - t) @ R          # R^T (Xc - t)
+    octv = np.minimum(rng.geometric(0.35, E) - 1, 7)
+    sig = scale[octv]
+    obs = np.stack([u + rng.normal(0, 1, E) * sig, v + rng.normal(0, 1, E) * sig, np.full(E, -1.0)], 1)
+    st = rng.random(E) < stereo_frac
+    obs[st, 2] = obs[st, 0] - BF / z[st] + rng.normal(0, 1, st.sum()) * sig[st]
+    out = rng.random(E) < outlier_frac
+    obs[out, 0] += rng.choice([-1, 1], out.sum()) * rng.uniform(20, 80, out.sum())
+    obs[out, 1] += rng.choice([-1, 1], out.sum()) * rng.uniform(20, 80, out.sum())
+    Rp = rot_small(rng, rot_deg)
+    Tinit = se3_matrix(Rp @ R, Rp @ t + rng.normal(0, trans, 3))
+    return dict(xw=Xw.astype(np.float32), obs=obs.astype(np.float32),
+                inv_sigma2=(1.0 / sig ** 2).astype(np.float32), Tcw=Tinit.astype(np.float32), Tgt=Tgt,
+                is_outlier=out)
+
+
+def lba_scenario(seed, K=20, M=3000, n_fixed=3, obs_range=(3, 10), outlier_frac=0.05, stereo_frac=0.6,
+                 rot_deg=1.0, trans=0.03, pt_sigma=0.02):
+    rng = np.random.default_rng(seed)
+    scale = 1.2 ** np.arange(8)
+    # cameras on a gentle arc looking at a point cloud 4-12 m ahead
+    Tgt = []
+    for k in range(K):
+        R = rot_small(rng, 4.0) @ np.array([[np.cos(0.03 * k), 0, np.sin(0.03 * k)], [0, 1, 0],
+                                             [-np.sin(0.03 * k), 0, np.cos(0.03 * k)]])
+        c = np.array([0.25 * k, rng.normal(0, 0.05), rng.normal(0, 0.1)])
+        Tgt.append(se3_matrix(R, -R @ c))
+    Tgt = np.array(Tgt)
+    P = np.stack([rng.uniform(-4, 9, M), rng.uniform(-2.5, 2.5, M), rng.uniform(4, 12, M)], 1)
+    ekf, emp, obs, isg = [], [], [], []
+    for m in range(M):
+        want = int(rng.integers(obs_range[0], obs_range[1] + 1))
+        ks = rng.permutation(K)
+        got = 0
+        for k in ks:
+            pc = Tgt[k, :3, :3] @ P[m] + Tgt[k, :3, 3]
+            if pc[2] < 0.5:
+                continue
+            u, v = FX * pc[0] / pc[2] + CX, FY * pc[1] / pc[2] + CY
+            if not (0 < u < 752 and 0 < v < 480):
+                continue
+            o = min(int(rng.geometric(0.35)) - 1, 7)
+            s = scale[o]
+            uo, vo = u + rng.normal(0, 1) * s, v + rng.normal(0, 1) * s
+            ur = -1.0
+            if rng.random() < stereo_frac:
+                ur = uo - BF / pc[2] + rng.normal(0, 1) * s
+            if rng.random() < outlier_frac:
+                uo += rng.choice([-1, 1]) * rng.uniform(15, 60)
+            ekf.append(k), emp.append(m), obs.append([uo, vo, ur]), isg.append(1.0 / s ** 2)
+            got += 1
+            if got >= want:
+                break
+    # keep only points with >= 2 observations (a MapPoint in the reference's local map always has them;
+    # an unobserved point would make its 3x3 Hessian block singular) and re-index
+    ekf, emp = np.array(ekf, np.int32), np.array(emp, np.int32)
+    obs, isg = np.array(obs, np.float32), np.array(isg, np.float32)
+    cnt = np.bincount(emp, minlength=M)
+    keep_pt = cnt >= 2
+    remap = np.cumsum(keep_pt) - 1
+    ke = keep_pt[emp]
+    ekf, emp, obs, isg = ekf[ke], remap[emp[ke]].astype(np.int32), obs[ke], isg[ke]
+    P = P[keep_pt]
+    M = len(P)
+    fixed = np.zeros(K, np.uint8)
+    fixed[:n_fixed] = 1
+    Tin = Tgt.copy()
+    for k in range(n_fixed, K):
+        Rp = rot_small(rng, rot_deg)
+        Tin[k] = se3_matrix(Rp @ Tgt[k, :3, :3], Rp @ Tgt[k, :3, 3] + rng.normal(0, trans, 3))
+    Pin = P + rng.normal(0, pt_sigma, P.shape)
+    return dict(kf_T=Tin.astype(np.float32).reshape(K, 16), kf_fixed=fixed, mp_xyz=Pin.astype(np.float32),
+                e_kf=ekf, e_mp=emp, e_obs=obs, e_inv_sigma2=isg, Tgt=Tgt, Pgt=P)
