@@ -1,0 +1,1072 @@
+// orbx_optimize.cu — sm_100a PoseOptimization and LocalBundleAdjustment behind include/orbx.h.
+//
+// Replaces (reference paths): Optimizer::PoseOptimization src/Optimizer.cc:907-1272, the numeric core of
+// Optimizer::LocalBundleAdjustment src/Optimizer.cc:1958-2352, and the g2o code under them
+// (Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-185, core/block_solver.hpp:354-610,
+// core/base_{unary,binary}_edge.hpp, core/robust_kernel_impl.cpp:66-91, types/se3quat.h,
+// types/types_six_dof_expmap.cpp, src/OptimizableTypes.cpp).
+//
+// B200 design: these are tiny, latency-bound fp64 problems (E ~ 150-500 edges for a pose, ~18 k edges /
+// 20 keyframes / 3000 points for a local BA), so a whole optimisation — graph-free: flat edge arrays, the
+// LM controller, the 6x6 solve or the Schur complement + dense LDL^T, the chi2 classification — runs
+// inside ONE thread block with zero host round trips; independent streams batch across blocks/SMs.
+// Reductions use fixed-shape trees, so results are run-to-run deterministic.  Compiled with --fmad=false so
+// every expression rounds exactly as in the CPU path (only summation order differs).
+#include <algorithm>
+#include <vector>
+#include "orbx_match.cuh"
+
+// ------------------------------------------------------------------------------------
+// SE3 (unit quaternion + translation), fp64 — same expressions as g2o::SE3Quat / Eigen
+// ------------------------------------------------------------------------------------
+struct Quat { double x, y, z, w; };
+struct SE3d { Quat r; double t[3]; };
+
+__device__ __forceinline__ Quat quat_from_R(const double* R) {
+  Quat q;
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = sqrt(t + 1.0);
+    q.w = 0.5 * t;
+    t = 0.5 / t;
+    q.x = (R[7] - R[5]) * t;
+    q.y = (R[2] - R[6]) * t;
+    q.z = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i * 3 + i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1.0);
+    double v[3];
+    v[i] = 0.5 * t;
+    t = 0.5 / t;
+    q.w = (R[k * 3 + j] - R[j * 3 + k]) * t;
+    v[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+    v[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+    q.x = v[0]; q.y = v[1]; q.z = v[2];
+  }
+  return q;
+}
+__device__ __forceinline__ void quat_normalize(Quat& q) {
+  if (q.w < 0) { q.x = -q.x; q.y = -q.y; q.z = -q.z; q.w = -q.w; }
+  const double n = sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  q.x /= n; q.y /= n; q.z /= n; q.w /= n;
+}
+__device__ __forceinline__ Quat quat_mul(const Quat& a, const Quat& b) {
+  Quat r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  return r;
+}
+__device__ __forceinline__ void quat_rot(const Quat& q, const double* v, double* out) {
+  double uv0 = q.y * v[2] - q.z * v[1], uv1 = q.z * v[0] - q.x * v[2], uv2 = q.x * v[1] - q.y * v[0];
+  uv0 += uv0; uv1 += uv1; uv2 += uv2;
+  out[0] = v[0] + q.w * uv0 + (q.y * uv2 - q.z * uv1);
+  out[1] = v[1] + q.w * uv1 + (q.z * uv0 - q.x * uv2);
+  out[2] = v[2] + q.w * uv2 + (q.x * uv1 - q.y * uv0);
+}
+__device__ __forceinline__ void quat_to_R(const Quat& q, double* R) {
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+__device__ __forceinline__ SE3d se3_from_Tcw(const float* T) {   // Converter::toSE3Quat
+  double R[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i * 3 + j] = (double)T[i * 4 + j];
+  SE3d s;
+  s.r = quat_from_R(R);
+  quat_normalize(s.r);
+  for (int i = 0; i < 3; ++i) s.t[i] = (double)T[i * 4 + 3];
+  return s;
+}
+__device__ __forceinline__ void se3_to_Tcw(const SE3d& s, float* T) {   // Converter::toCvMat(SE3Quat)
+  double R[9];
+  quat_to_R(s.r, R);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) T[i * 4 + j] = (float)R[i * 3 + j];
+    T[i * 4 + 3] = (float)s.t[i];
+  }
+  T[12] = T[13] = T[14] = 0.f;
+  T[15] = 1.f;
+}
+__device__ __forceinline__ void se3_map(const SE3d& s, const double* x, double* out) {
+  quat_rot(s.r, x, out);
+  out[0] += s.t[0]; out[1] += s.t[1]; out[2] += s.t[2];
+}
+__device__ __forceinline__ SE3d se3_mul(const SE3d& a, const SE3d& b) {
+  SE3d r = a;
+  double rt[3];
+  quat_rot(a.r, b.t, rt);
+  r.t[0] += rt[0]; r.t[1] += rt[1]; r.t[2] += rt[2];
+  r.r = quat_mul(a.r, b.r);
+  quat_normalize(r.r);
+  return r;
+}
+__device__ SE3d se3_exp(const double* u) {   // SE3Quat::exp, u = [omega, upsilon]
+  const double* om = u;
+  const double* up = u + 3;
+  const double theta = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+  const double O[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};
+  double O2[9], R[9], V[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) O2[i * 3 + j] = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
+  if (theta < 0.00001) {
+    for (int i = 0; i < 9; ++i) { R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
+  } else {
+    const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta);
+    const double c = (theta - sin(theta)) / pow(theta, 3.0);
+    for (int i = 0; i < 9; ++i) {
+      const double id = (i % 4 == 0) ? 1.0 : 0.0;
+      R[i] = id + a * O[i] + b * O2[i];
+      V[i] = id + b * O[i] + c * O2[i];
+    }
+  }
+  SE3d s;
+  s.r = quat_from_R(R);
+  quat_normalize(s.r);
+  for (int i = 0; i < 3; ++i) s.t[i] = V[i * 3] * up[0] + V[i * 3 + 1] * up[1] + V[i * 3 + 2] * up[2];
+  return s;
+}
+
+// RobustKernelHuber (delta is the reference's float sqrt(5.991|7.815) widened; dsqr is a float member)
+struct HuberD { double delta; float dsqr; };
+__device__ __forceinline__ HuberD huber_make(float d) {
+  HuberD h;
+  h.delta = (double)d;
+  h.dsqr = (float)((double)d * (double)d);
+  return h;
+}
+__device__ __forceinline__ double huber_rho(const HuberD& h, double e, double& w) {
+  if (e <= (double)h.dsqr) { w = 1.0; return e; }
+  const double sqrte = sqrt(e);
+  w = h.delta / sqrte;
+  return 2 * sqrte * h.delta - (double)h.dsqr;
+}
+
+// projection residual of one observation (mono 2-D or stereo 3-D); p = camera-frame point
+__device__ __forceinline__ void reproj_error(const double* p, const float* ob, bool stereo, float fx, float fy, float cx,
+                                             float cy, float bf, double* out) {
+  if (!stereo) {
+    out[0] = (double)ob[0] - ((double)fx * p[0] / p[2] + (double)cx);
+    out[1] = (double)ob[1] - ((double)fy * p[1] / p[2] + (double)cy);
+    out[2] = 0;
+  } else {
+    const float invz = (float)(1.0 / p[2]);   // float invz: types_six_dof_expmap.cpp:191,340
+    const double u = p[0] * (double)invz * (double)fx + (double)cx;
+    const double v = p[1] * (double)invz * (double)fy + (double)cy;
+    out[0] = (double)ob[0] - u;
+    out[1] = (double)ob[1] - v;
+    out[2] = (double)ob[2] - (u - (double)bf * (double)invz);
+  }
+}
+
+// d err / d pose (Dx6): EdgeSE3ProjectXYZOnlyPose / EdgeSE3ProjectXYZ (mono) and the stereo variants.
+// `binary` selects the z-division form of the LocalBA edges (x*y/z_2 ...) over the only-pose form (x*y*invz_2 ...).
+__device__ __forceinline__ void jac_pose(const double* p, bool stereo, bool binary, double fx, double fy, double bf, double* J) {
+  const double x = p[0], y = p[1], z = p[2];
+  if (!stereo) {
+    // mono: -(projectJac * [ -[p]x | I ])
+    const double j00 = fx / z, j02 = -fx * x / (z * z), j11 = fy / z, j12 = -fy * y / (z * z);
+    const double S0[6] = {0, z, -y, 1, 0, 0}, S1[6] = {-z, 0, x, 0, 1, 0}, S2[6] = {y, -x, 0, 0, 0, 1};
+    if (!binary) {
+      for (int c = 0; c < 6; ++c) {
+        J[c] = -(j00 * S0[c] + j02 * S2[c]);
+        J[6 + c] = -(j11 * S1[c] + j12 * S2[c]);
+      }
+    } else {
+      const double n00 = -(fx / z), n02 = fx * x / (z * z), n11 = -(fy / z), n12 = fy * y / (z * z);
+      for (int c = 0; c < 6; ++c) {
+        J[c] = n00 * S0[c] + n02 * S2[c];
+        J[6 + c] = n11 * S1[c] + n12 * S2[c];
+      }
+    }
+  } else if (!binary) {
+    const double invz = 1.0 / z, invz2 = invz * invz;
+    J[0] = x * y * invz2 * fx; J[1] = -(1 + (x * x * invz2)) * fx; J[2] = y * invz * fx;
+    J[3] = -invz * fx; J[4] = 0; J[5] = x * invz2 * fx;
+    J[6] = (1 + y * y * invz2) * fy; J[7] = -x * y * invz2 * fy; J[8] = -x * invz * fy;
+    J[9] = 0; J[10] = -invz * fy; J[11] = y * invz2 * fy;
+    J[12] = J[0] - bf * y * invz2; J[13] = J[1] + bf * x * invz2; J[14] = J[2];
+    J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf * invz2;
+  } else {
+    const double z2 = z * z;
+    J[0] = x * y / z2 * fx; J[1] = -(1 + (x * x / z2)) * fx; J[2] = y / z * fx;
+    J[3] = -1. / z * fx; J[4] = 0; J[5] = x / z2 * fx;
+    J[6] = (1 + y * y / z2) * fy; J[7] = -x * y / z2 * fy; J[8] = -x / z * fy;
+    J[9] = 0; J[10] = -1. / z * fy; J[11] = y / z2 * fy;
+    J[12] = J[0] - bf * y / z2; J[13] = J[1] + bf * x / z2; J[14] = J[2];
+    J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf / z2;
+  }
+}
+
+// Block-wide sum of NV doubles per thread; every thread returns the same totals (fixed-shape tree:
+// lane butterfly, then warps in index order).  s_red must hold (blockDim/32)*NV doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum(double* v, double* s_red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  __syncthreads();   // protect s_red from the previous use
+  if (lane == 0)
+    for (int k = 0; k < NV; ++k) s_red[wid * NV + k] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = 0;
+    for (int w = 0; w < nw; ++w) s += s_red[w * NV + k];
+    v[k] = s;
+  }
+}
+
+// Eigen::LDLT-like 6x6 solve with diagonal pivoting (largest |diagonal|); false on a negative pivot.
+__device__ bool ldlt6_solve(const double* Ain, const double* b, double* x) {
+  double A[36];
+  int perm[6];
+  for (int i = 0; i < 36; ++i) A[i] = Ain[i];
+  for (int i = 0; i < 6; ++i) perm[i] = i;
+  bool positive = true;
+  for (int k = 0; k < 6; ++k) {
+    int p = k;
+    double best = fabs(A[k * 6 + k]);
+    for (int i = k + 1; i < 6; ++i)
+      if (fabs(A[i * 6 + i]) > best) { best = fabs(A[i * 6 + i]); p = i; }
+    if (p != k) {
+      for (int j = 0; j < 6; ++j) { const double t = A[k * 6 + j]; A[k * 6 + j] = A[p * 6 + j]; A[p * 6 + j] = t; }
+      for (int i = 0; i < 6; ++i) { const double t = A[i * 6 + k]; A[i * 6 + k] = A[i * 6 + p]; A[i * 6 + p] = t; }
+      const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+    }
+    const double d = A[k * 6 + k];
+    if (d < 0) positive = false;
+    if (d == 0) continue;
+    for (int i = k + 1; i < 6; ++i) A[i * 6 + k] /= d;
+    for (int i = k + 1; i < 6; ++i)
+      for (int j = k + 1; j <= i; ++j) {
+        A[i * 6 + j] -= A[i * 6 + k] * d * A[j * 6 + k];
+        A[j * 6 + i] = A[i * 6 + j];
+      }
+  }
+  if (!positive) return false;
+  double y[6];
+  for (int i = 0; i < 6; ++i) y[i] = b[perm[i]];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < i; ++j) y[i] -= A[i * 6 + j] * y[j];
+  for (int i = 0; i < 6; ++i) { const double d = A[i * 6 + i]; y[i] = (d != 0) ? y[i] / d : 0.0; }
+  for (int i = 5; i >= 0; --i)
+    for (int j = i + 1; j < 6; ++j) y[i] -= A[j * 6 + i] * y[j];
+  for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+  return true;
+}
+
+// =====================================================================================
+// K11  PoseOptimization: one CTA per frame
+// =====================================================================================
+#define PO_NT 128
+
+struct PoseOptArgs {
+  const int* edgeOfs;     // [P+1]
+  const float* xw;        // [Etot][3]
+  const float* obs;       // [Etot][3]
+  const float* invSigma2; // [Etot]
+  float fx, fy, cx, cy, bf;
+  float* Tcw;             // [P][16]
+  uint8_t* outlier;       // [Etot]
+  int* nInliers;          // [P]
+  int* iters;             // [P][4]
+  double* err;            // [Etot][3] scratch: residual of the last evaluated state
+};
+
+__global__ void __launch_bounds__(PO_NT) pose_opt_kernel(const PoseOptArgs A) {
+  const int prob = blockIdx.x, tid = threadIdx.x;
+  const int e0 = A.edgeOfs[prob], E = A.edgeOfs[prob + 1] - e0;
+  __shared__ SE3d s_est, s_backup, s_init;
+  __shared__ double s_red[(PO_NT / 32) * 28];
+  __shared__ double s_H[36], s_b[6], s_x[6];
+  __shared__ int s_ok;
+  const float* xw = A.xw + 3 * (size_t)e0;
+  const float* obs = A.obs + 3 * (size_t)e0;
+  const float* isg = A.invSigma2 + e0;
+  uint8_t* outlier = A.outlier + e0;
+  double* err = A.err + 3 * (size_t)e0;
+  int* iters = A.iters + 4 * prob;
+  if (tid < 4) iters[tid] = 0;
+  if (E < 3) {   // nInitialCorrespondences<3: return 0, pose untouched (src/Optimizer.cc:1134-1135)
+    if (tid == 0) A.nInliers[prob] = 0;
+    for (int e = tid; e < E; e += PO_NT) outlier[e] = 0;
+    return;
+  }
+  if (tid == 0) s_init = se3_from_Tcw(A.Tcw + 16 * prob);
+  for (int e = tid; e < E; e += PO_NT) outlier[e] = 0;
+  __syncthreads();
+  const HuberD hMono = huber_make(sqrtf(5.991f)), hStereo = huber_make(sqrtf(7.815f));
+  const double fx = A.fx, fy = A.fy, bf = A.bf;
+  bool robust = true;
+  int nBadFinal = 0;
+
+  for (int round = 0; round < 4; ++round) {
+    if (tid == 0) s_est = s_init;      // vSE3->setEstimate(toSE3Quat(pFrame->mTcw)) every round
+    __syncthreads();
+    // ---------------- optimize(10): modified g2o Levenberg-Marquardt ----------------
+    double lambda = -1, ni = 2;
+    int nBad = 0, cj = 0;
+    bool ok = true;
+    for (int it = 0; it < 10 && ok; ++it) {
+      // computeActiveErrors + activeRobustChi2 + buildSystem in one pass over the active edges
+      double acc[28];
+#pragma unroll
+      for (int k = 0; k < 28; ++k) acc[k] = 0;
+      const SE3d est = s_est;
+      for (int e = tid; e < E; e += PO_NT) {
+        if (outlier[e]) continue;                 // level-1 edges are not active
+        const double X[3] = {(double)xw[3 * e], (double)xw[3 * e + 1], (double)xw[3 * e + 2]};
+        double p[3], r[3], J[18];
+        se3_map(est, X, p);
+        const bool st = obs[3 * e + 2] >= 0;
+        reproj_error(p, obs + 3 * e, st, A.fx, A.fy, A.cx, A.cy, A.bf, r);
+        err[3 * e] = r[0]; err[3 * e + 1] = r[1]; err[3 * e + 2] = r[2];
+        const double om = (double)isg[e];
+        const double chi = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
+        double w = 1.0;
+        if (robust) acc[27] += huber_rho(st ? hStereo : hMono, chi, w);
+        else acc[27] += chi;
+        jac_pose(p, st, false, fx, fy, bf, J);
+        const int D = st ? 3 : 2;
+        int idx = 0;
+        for (int i = 0; i < 6; ++i) {
+          double s = 0;
+          for (int d = 0; d < D; ++d) s += J[d * 6 + i] * om * r[d];
+          acc[21 + i] -= w * s;
+          for (int j = i; j < 6; ++j) {
+            double a = 0;
+            for (int d = 0; d < D; ++d) a += J[d * 6 + i] * (w * om) * J[d * 6 + j];
+            acc[idx++] += a;
+          }
+        }
+      }
+      block_sum<28>(acc, s_red);
+      double currentChi = acc[27];
+      const double iniChi = currentChi;
+      if (tid == 0) {
+        int idx = 0;
+        for (int i = 0; i < 6; ++i)
+          for (int j = i; j < 6; ++j) { s_H[i * 6 + j] = acc[idx]; s_H[j * 6 + i] = acc[idx]; ++idx; }
+        for (int i = 0; i < 6; ++i) s_b[i] = acc[21 + i];
+      }
+      if (it == 0) {
+        double m = 0;
+        { int idx = 0; for (int i = 0; i < 6; ++i) { m = fmax(fabs(acc[idx]), m); idx += 6 - i; } }
+        lambda = 1e-50 * m;   // computeLambdaInit with _tau = 1e-50
+        ni = 2;
+        nBad = 0;
+      }
+      __syncthreads();
+      double rho = 0;
+      int qmax = 0;
+      do {
+        if (tid == 0) {
+          s_backup = s_est;                       // push()
+          double Hl[36], x[6];
+          for (int i = 0; i < 36; ++i) Hl[i] = s_H[i];
+          for (int i = 0; i < 6; ++i) { Hl[i * 6 + i] += lambda; x[i] = 0; }
+          s_ok = ldlt6_solve(Hl, s_b, x) ? 1 : 0;
+          for (int i = 0; i < 6; ++i) s_x[i] = x[i];
+          s_est = se3_mul(se3_exp(x), s_est);     // oplus: exp(update) * estimate
+        }
+        __syncthreads();
+        const SE3d trial = s_est;
+        double chi[1] = {0};
+        for (int e = tid; e < E; e += PO_NT) {
+          if (outlier[e]) continue;
+          const double X[3] = {(double)xw[3 * e], (double)xw[3 * e + 1], (double)xw[3 * e + 2]};
+          double p[3], r[3];
+          se3_map(trial, X, p);
+          const bool st = obs[3 * e + 2] >= 0;
+          reproj_error(p, obs + 3 * e, st, A.fx, A.fy, A.cx, A.cy, A.bf, r);
+          err[3 * e] = r[0]; err[3 * e + 1] = r[1]; err[3 * e + 2] = r[2];
+          const double om = (double)isg[e];
+          const double c = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
+          double w;
+          chi[0] += robust ? huber_rho(st ? hStereo : hMono, c, w) : c;
+        }
+        block_sum<1>(chi, s_red);
+        double tempChi = chi[0];
+        if (!s_ok) tempChi = 1.7976931348623157e308;
+        rho = currentChi - tempChi;
+        double scale = 0;
+        for (int j = 0; j < 6; ++j) scale += s_x[j] * (lambda * s_x[j] + s_b[j]);
+        scale += 1e-3;
+        rho /= scale;
+        if (rho > 0 && isfinite(tempChi)) {
+          double alpha = 1. - pow((2 * rho - 1), 3.0);
+          alpha = fmin(alpha, 2. / 3.);
+          const double scaleFactor = fmax(1. / 3., alpha);
+          lambda *= scaleFactor;
+          ni = 2;
+          currentChi = tempChi;
+        } else {
+          lambda *= ni;
+          ni *= 2;
+          __syncthreads();
+          if (tid == 0) s_est = s_backup;         // pop()
+        }
+        __syncthreads();
+        ++qmax;
+      } while (rho < 0 && qmax < 100);
+      ++cj;
+      if (qmax == 100 || rho == 0) { ok = false; continue; }
+      if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
+      if (nBad >= 3) ok = false;
+    }
+    if (tid == 0) iters[round] = cj;
+    // ---------------- chi2 classification (src/Optimizer.cc:1157-1255) ----------------
+    const SE3d est = s_est;
+    double bad[1] = {0};
+    for (int e = tid; e < E; e += PO_NT) {
+      const bool st = obs[3 * e + 2] >= 0;
+      if (outlier[e]) {                           // e->computeError() for edges that sat out
+        const double X[3] = {(double)xw[3 * e], (double)xw[3 * e + 1], (double)xw[3 * e + 2]};
+        double p[3], r[3];
+        se3_map(est, X, p);
+        reproj_error(p, obs + 3 * e, st, A.fx, A.fy, A.cx, A.cy, A.bf, r);
+        err[3 * e] = r[0]; err[3 * e + 1] = r[1]; err[3 * e + 2] = r[2];
+      }
+      const double om = (double)isg[e];
+      const double* r = err + 3 * e;
+      const float chi2 = (float)(r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0));
+      const bool isBad = chi2 > (st ? 7.815f : 5.991f);
+      outlier[e] = isBad ? 1 : 0;
+      bad[0] += isBad ? 1.0 : 0.0;
+    }
+    block_sum<1>(bad, s_red);
+    nBadFinal = (int)bad[0];
+    if (round == 2) robust = false;               // e->setRobustKernel(0)
+    if (E < 10) break;                            // optimizer.edges().size()<10
+  }
+  if (tid == 0) {
+    se3_to_Tcw(s_est, A.Tcw + 16 * prob);
+    A.nInliers[prob] = E - nBadFinal;
+  }
+}
+
+// =====================================================================================
+// K12  LocalBundleAdjustment: one CTA (1024 threads) per problem; all state in global/L2 scratch
+// =====================================================================================
+#define LBA_NT 1024
+
+struct LbaArgs {
+  int K, M, E, nFree, n;      // n = 6*nFree
+  float* kfT;                 // [K][16] in/out
+  const uint8_t* kfFixed;
+  float* mpXyz;               // [M][3] in/out
+  const int *ekf, *emp;
+  const float *obs, *invSigma2;
+  float fx, fy, cx, cy, bf;
+  double lambdaInit;
+  const volatile uint8_t* stop;   // device-visible (mapped host) or null
+  // graph indices (host-built)
+  const int* hidx;            // [K] index among free poses or -1
+  const int* ptOfs;           // [M+1] edges of a point whose pose is free (for the Schur complement)
+  const int* ptEdges;
+  const int* ptAllOfs;        // [M+1] all edges of a point
+  const int* ptAllEdges;
+  const int* kfOfs;           // [nFree+1] edges of a free pose
+  const int* kfEdges;
+  const int* obsEdge;         // [M][nFree] edge id of (point, free pose) or -1
+  // scratch (doubles unless noted)
+  SE3d *pose, *poseBak;       // [K]
+  double *pt, *ptBak;         // [M][3]
+  double* err;                // [E][3]
+  double *Ji, *Jj;            // [E][9], [E][18]
+  double *wom, *omr;          // [E], [E][3]
+  double *Hpl, *BD;           // [E][18] (6x3), B*Dinv
+  double *Hll, *Dinv;         // [M][9]
+  double* Hpp;                // [nFree][36]
+  double *b, *x;              // [n + 3M]
+  double *S, *bs;             // [n][n], [n]
+  double* db;                 // [M][3]
+  // outputs
+  uint8_t* edgeBad;
+  int* iters;                 // [2]
+  int* status;
+};
+
+__device__ __forceinline__ bool lba_stop(const LbaArgs& A, int* s_flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) *s_flag = (A.stop && *A.stop) ? 1 : 0;
+  __syncthreads();
+  return *s_flag != 0;
+}
+
+// residuals + robust chi2 of every edge at the current estimate
+__device__ double lba_errors_chi(const LbaArgs& A, const HuberD& hM, const HuberD& hS, double* s_red) {
+  double chi[1] = {0};
+  for (int e = threadIdx.x; e < A.E; e += LBA_NT) {
+    double p[3], r[3];
+    se3_map(A.pose[A.ekf[e]], A.pt + 3 * (size_t)A.emp[e], p);
+    const bool st = A.obs[3 * e + 2] >= 0;
+    reproj_error(p, A.obs + 3 * e, st, A.fx, A.fy, A.cx, A.cy, A.bf, r);
+    A.err[3 * e] = r[0]; A.err[3 * e + 1] = r[1]; A.err[3 * e + 2] = r[2];
+    const double om = (double)A.invSigma2[e];
+    const double c = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
+    double w;
+    chi[0] += huber_rho(st ? hS : hM, c, w);
+  }
+  block_sum<1>(chi, s_red);
+  return chi[0];
+}
+
+__global__ void __launch_bounds__(LBA_NT) lba_kernel(const LbaArgs A) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NW = LBA_NT / 32;
+  __shared__ double s_red[(LBA_NT / 32) * 2];
+  __shared__ int s_flag;
+  __shared__ double s_scal[4];
+  const HuberD hM = huber_make(sqrtf(5.991f)), hS = huber_make(sqrtf(7.815f));
+  const double fx = A.fx, fy = A.fy, bf = A.bf;
+  const int n = A.n, NX = A.n + 3 * A.M;
+
+  if (tid == 0) { A.iters[0] = A.iters[1] = 0; *A.status = 0; }
+  for (int e = tid; e < A.E; e += LBA_NT) A.edgeBad[e] = 0;
+  if (lba_stop(A, &s_flag)) {   // if(pbStopFlag) if(*pbStopFlag) return;  (src/Optimizer.cc:2195-2197)
+    if (tid == 0) *A.status = 1;
+    return;
+  }
+  for (int k = tid; k < A.K; k += LBA_NT) A.pose[k] = se3_from_Tcw(A.kfT + 16 * k);
+  for (int i = tid; i < 3 * A.M; i += LBA_NT) A.pt[i] = (double)A.mpXyz[i];
+  __syncthreads();
+
+  for (int call = 0; call < 2; ++call) {
+    const int iterations = call == 0 ? 5 : 10;
+    if (call == 1 && lba_stop(A, &s_flag)) break;   // bDoMore
+    double lambda = -1, ni = 2;
+    int nBad = 0, cj = 0;
+    bool ok = true;
+    for (int it = 0; it < iterations && ok; ++it) {
+      if (lba_stop(A, &s_flag)) break;
+      // ---- computeActiveErrors / activeRobustChi2 ----
+      double currentChi = lba_errors_chi(A, hM, hS, s_red);
+      const double iniChi = currentChi;
+      // ---- buildSystem: per-edge Jacobians, then deterministic gathers per point / per pose ----
+      for (int e = tid; e < A.E; e += LBA_NT) {
+        const int k = A.ekf[e];
+        double p[3], R[9];
+        se3_map(A.pose[k], A.pt + 3 * (size_t)A.emp[e], p);
+        quat_to_R(A.pose[k].r, R);
+        const bool st = A.obs[3 * e + 2] >= 0;
+        const int D = st ? 3 : 2;
+        double* Ji = A.Ji + 9 * (size_t)e;
+        double* Jj = A.Jj + 18 * (size_t)e;
+        const double x = p[0], y = p[1], z = p[2];
+        if (!st) {
+          const double j00 = -(fx / z), j02 = fx * x / (z * z), j11 = -(fy / z), j12 = fy * y / (z * z);
+          for (int c = 0; c < 3; ++c) {
+            Ji[c] = j00 * R[c] + j02 * R[6 + c];
+            Ji[3 + c] = j11 * R[3 + c] + j12 * R[6 + c];
+            Ji[6 + c] = 0;
+          }
+        } else {
+          const double z2 = z * z;
+          for (int c = 0; c < 3; ++c) {
+            Ji[c] = -fx * R[c] / z + fx * x * R[6 + c] / z2;
+            Ji[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z2;
+            Ji[6 + c] = Ji[c] - bf * R[6 + c] / z2;
+          }
+        }
+        jac_pose(p, st, true, fx, fy, bf, Jj);
+        if (!st) for (int c = 12; c < 18; ++c) Jj[c] = 0;
+        const double om = (double)A.invSigma2[e];
+        const double* r = A.err + 3 * e;
+        const double c2 = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
+        double w;
+        huber_rho(st ? hS : hM, c2, w);
+        for (int d = 0; d < 3; ++d) A.omr[3 * e + d] = (d < D) ? -om * r[d] * w : 0.0;
+        const double wo = w * om;
+        A.wom[e] = wo;
+        // pose-landmark block of this observation: Jj^T (w Omega) Ji   (6x3)
+        double* hpl = A.Hpl + 18 * (size_t)e;
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 3; ++j) {
+            double a = 0;
+            for (int d = 0; d < D; ++d) a += Jj[d * 6 + i] * wo * Ji[d * 3 + j];
+            hpl[i * 3 + j] = a;
+          }
+      }
+      __syncthreads();
+      // points: Hll, b_l (every edge of the point, fixed poses included)
+      for (int m = tid; m < A.M; m += LBA_NT) {
+        double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+        for (int q = A.ptAllOfs[m]; q < A.ptAllOfs[m + 1]; ++q) {
+          const int e = A.ptAllEdges[q];
+          const int D = A.obs[3 * e + 2] >= 0 ? 3 : 2;
+          const double* Ji = A.Ji + 9 * (size_t)e;
+          const double wo = A.wom[e];
+          const double* omr = A.omr + 3 * e;
+          for (int i = 0; i < 3; ++i) {
+            double s = 0;
+            for (int d = 0; d < D; ++d) s += Ji[d * 3 + i] * omr[d];
+            bl[i] += s;
+            for (int j = 0; j < 3; ++j) {
+              double a = 0;
+              for (int d = 0; d < D; ++d) a += Ji[d * 3 + i] * wo * Ji[d * 3 + j];
+              H[i * 3 + j] += a;
+            }
+          }
+        }
+        for (int i = 0; i < 9; ++i) A.Hll[9 * (size_t)m + i] = H[i];
+        for (int i = 0; i < 3; ++i) A.b[n + 3 * m + i] = bl[i];
+      }
+      // free poses: Hpp (upper 21) + b_p, one warp per pose
+      for (int hk = wid; hk < A.nFree; hk += NW) {
+        double acc[27];
+#pragma unroll
+        for (int i = 0; i < 27; ++i) acc[i] = 0;
+        for (int q = A.kfOfs[hk] + lane; q < A.kfOfs[hk + 1]; q += 32) {
+          const int e = A.kfEdges[q];
+          const int D = A.obs[3 * e + 2] >= 0 ? 3 : 2;
+          const double* Jj = A.Jj + 18 * (size_t)e;
+          const double wo = A.wom[e];
+          const double* omr = A.omr + 3 * e;
+          int idx = 0;
+          for (int i = 0; i < 6; ++i) {
+            double s = 0;
+            for (int d = 0; d < D; ++d) s += Jj[d * 6 + i] * omr[d];
+            acc[21 + i] += s;
+            for (int j = i; j < 6; ++j) {
+              double a = 0;
+              for (int d = 0; d < D; ++d) a += Jj[d * 6 + i] * wo * Jj[d * 6 + j];
+              acc[idx++] += a;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 27; ++i)
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        if (lane == 0) {
+          int idx = 0;
+          for (int i = 0; i < 6; ++i)
+            for (int j = i; j < 6; ++j) {
+              A.Hpp[36 * (size_t)hk + i * 6 + j] = acc[idx];
+              A.Hpp[36 * (size_t)hk + j * 6 + i] = acc[idx];
+              ++idx;
+            }
+          for (int i = 0; i < 6; ++i) A.b[6 * hk + i] = acc[21 + i];
+        }
+      }
+      __syncthreads();
+      if (it == 0) {
+        if (A.lambdaInit > 0) lambda = A.lambdaInit;
+        else {
+          double m[1] = {0};   // max |diag|: reduce with max (emulated through block_sum-free tree below)
+          for (int i = tid; i < A.nFree * 6; i += LBA_NT) m[0] = fmax(m[0], fabs(A.Hpp[36 * (size_t)(i / 6) + (i % 6) * 7]));
+          for (int i = tid; i < A.M * 3; i += LBA_NT) m[0] = fmax(m[0], fabs(A.Hll[9 * (size_t)(i / 3) + (i % 3) * 4]));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m[0] = fmax(m[0], __shfl_xor_sync(0xffffffffu, m[0], o));
+          __syncthreads();
+          if (lane == 0) s_red[wid] = m[0];
+          __syncthreads();
+          double mm = 0;
+          for (int w = 0; w < NW; ++w) mm = fmax(mm, s_red[w]);
+          __syncthreads();
+          lambda = 1e-50 * mm;
+        }
+        ni = 2;
+        nBad = 0;
+      }
+      double rho = 0;
+      int qmax = 0;
+      bool stopped = false;
+      do {
+        // ---- push ----
+        for (int k = tid; k < A.K; k += LBA_NT) A.poseBak[k] = A.pose[k];
+        for (int i = tid; i < 3 * A.M; i += LBA_NT) A.ptBak[i] = A.pt[i];
+        // ---- solve with Schur complement (block_solver.hpp:354-486) ----
+        // landmarks: Dinv = (Hll + lambda I)^-1 ; db = Dinv b_l
+        for (int m = tid; m < A.M; m += LBA_NT) {
+          double Dm[9];
+          for (int i = 0; i < 9; ++i) Dm[i] = A.Hll[9 * (size_t)m + i];
+          Dm[0] += lambda; Dm[4] += lambda; Dm[8] += lambda;
+          const double c00 = Dm[4] * Dm[8] - Dm[5] * Dm[7], c01 = Dm[5] * Dm[6] - Dm[3] * Dm[8], c02 = Dm[3] * Dm[7] - Dm[4] * Dm[6];
+          const double det = Dm[0] * c00 + Dm[1] * c01 + Dm[2] * c02, id = 1.0 / det;
+          double* Di = A.Dinv + 9 * (size_t)m;
+          Di[0] = c00 * id; Di[1] = (Dm[2] * Dm[7] - Dm[1] * Dm[8]) * id; Di[2] = (Dm[1] * Dm[5] - Dm[2] * Dm[4]) * id;
+          Di[3] = c01 * id; Di[4] = (Dm[0] * Dm[8] - Dm[2] * Dm[6]) * id; Di[5] = (Dm[2] * Dm[3] - Dm[0] * Dm[5]) * id;
+          Di[6] = c02 * id; Di[7] = (Dm[1] * Dm[6] - Dm[0] * Dm[7]) * id; Di[8] = (Dm[0] * Dm[4] - Dm[1] * Dm[3]) * id;
+          const double* bl = A.b + n + 3 * m;
+          for (int i = 0; i < 3; ++i) A.db[3 * m + i] = Di[i * 3] * bl[0] + Di[i * 3 + 1] * bl[1] + Di[i * 3 + 2] * bl[2];
+        }
+        __syncthreads();
+        // BD[e] = B_e Dinv_m for edges of free poses
+        for (int e = tid; e < A.E; e += LBA_NT) {
+          if (A.hidx[A.ekf[e]] < 0) continue;
+          const double* B = A.Hpl + 18 * (size_t)e;
+          const double* Di = A.Dinv + 9 * (size_t)A.emp[e];
+          double* BD = A.BD + 18 * (size_t)e;
+          for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 3; ++j) BD[i * 3 + j] = B[i * 3] * Di[j] + B[i * 3 + 1] * Di[3 + j] + B[i * 3 + 2] * Di[6 + j];
+        }
+        __syncthreads();
+        // reduced system: one warp per (free pose i, free pose j >= i) block, lanes over pose i's edges
+        const int nBlocks = A.nFree * (A.nFree + 1) / 2;
+        for (int blk = wid; blk < nBlocks; blk += NW) {
+          int bi = 0, rem = blk;
+          while (rem >= A.nFree - bi) { rem -= A.nFree - bi; ++bi; }
+          const int bj = bi + rem;
+          double acc[36];
+#pragma unroll
+          for (int i = 0; i < 36; ++i) acc[i] = 0;
+          for (int q = A.kfOfs[bi] + lane; q < A.kfOfs[bi + 1]; q += 32) {
+            const int e1 = A.kfEdges[q];
+            const int e2 = A.obsEdge[(size_t)A.emp[e1] * A.nFree + bj];
+            if (e2 < 0) continue;
+            const double* BD = A.BD + 18 * (size_t)e1;
+            const double* B2 = A.Hpl + 18 * (size_t)e2;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+              for (int j = 0; j < 6; ++j)
+                acc[i * 6 + j] += BD[i * 3] * B2[j * 3] + BD[i * 3 + 1] * B2[j * 3 + 1] + BD[i * 3 + 2] * B2[j * 3 + 2];
+          }
+#pragma unroll
+          for (int i = 0; i < 36; ++i)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+          if (lane == 0) {
+            for (int i = 0; i < 6; ++i)
+              for (int j = 0; j < 6; ++j) {
+                double v = -acc[i * 6 + j];
+                if (bi == bj) v += A.Hpp[36 * (size_t)bi + i * 6 + j] + (i == j ? lambda : 0.0);
+                A.S[(size_t)(6 * bi + i) * n + 6 * bj + j] = v;
+                A.S[(size_t)(6 * bj + j) * n + 6 * bi + i] = v;
+              }
+          }
+        }
+        // b_schur = b_p - sum_e B_e db_m, one warp per free pose
+        for (int hk = wid; hk < A.nFree; hk += NW) {
+          double acc[6] = {0, 0, 0, 0, 0, 0};
+          for (int q = A.kfOfs[hk] + lane; q < A.kfOfs[hk + 1]; q += 32) {
+            const int e = A.kfEdges[q];
+            const double* B = A.Hpl + 18 * (size_t)e;
+            const double* db = A.db + 3 * (size_t)A.emp[e];
+            for (int i = 0; i < 6; ++i) acc[i] += B[i * 3] * db[0] + B[i * 3 + 1] * db[1] + B[i * 3 + 2] * db[2];
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+          if (lane == 0)
+            for (int i = 0; i < 6; ++i) A.bs[6 * hk + i] = A.b[6 * hk + i] - acc[i];
+        }
+        __syncthreads();
+        // dense LDL^T of S in place (lower), un-pivoted (stand-in for SimplicialLDLT); fails on a zero pivot
+        if (tid == 0) s_flag = 1;
+        __syncthreads();
+        for (int k = 0; k < n; ++k) {
+          const double d = A.S[(size_t)k * n + k];
+          if (d == 0 || !isfinite(d)) { if (tid == 0) s_flag = 0; break; }
+          for (int i = k + 1 + tid; i < n; i += LBA_NT) A.S[(size_t)i * n + k] /= d;
+          __syncthreads();
+          const int mrem = n - k - 1;
+          for (int t = tid; t < mrem * mrem; t += LBA_NT) {
+            const int i = k + 1 + t / mrem, j = k + 1 + t % mrem;
+            if (j <= i) A.S[(size_t)i * n + j] -= A.S[(size_t)i * n + k] * d * A.S[(size_t)j * n + k];
+          }
+          __syncthreads();
+        }
+        __syncthreads();
+        const bool solved = s_flag != 0;
+        for (int i = tid; i < NX; i += LBA_NT) A.x[i] = 0;
+        __syncthreads();
+        if (solved && n > 0) {
+          // forward (column sweep keeps the j-ascending subtraction order), diagonal, backward (j descending)
+          for (int i = tid; i < n; i += LBA_NT) A.x[i] = A.bs[i];
+          __syncthreads();
+          for (int j = 0; j < n; ++j) {
+            const double yj = A.x[j];
+            for (int i = j + 1 + tid; i < n; i += LBA_NT) A.x[i] -= A.S[(size_t)i * n + j] * yj;
+            __syncthreads();
+          }
+          for (int i = tid; i < n; i += LBA_NT) A.x[i] /= A.S[(size_t)i * n + i];
+          __syncthreads();
+          for (int j = n - 1; j >= 0; --j) {
+            const double yj = A.x[j];
+            for (int i = tid; i < j; i += LBA_NT) A.x[i] -= A.S[(size_t)j * n + i] * yj;
+            __syncthreads();
+          }
+          // landmarks: x_l = Dinv (b_l - sum_e B_e^T x_p)
+          for (int m = tid; m < A.M; m += LBA_NT) {
+            double cl[3] = {A.b[n + 3 * m], A.b[n + 3 * m + 1], A.b[n + 3 * m + 2]};
+            for (int q = A.ptOfs[m]; q < A.ptOfs[m + 1]; ++q) {
+              const int e = A.ptEdges[q];
+              const int hk = A.hidx[A.ekf[e]];
+              const double* B = A.Hpl + 18 * (size_t)e;
+              for (int j = 0; j < 3; ++j)
+                for (int i = 0; i < 6; ++i) cl[j] -= B[i * 3 + j] * A.x[6 * hk + i];
+            }
+            const double* Di = A.Dinv + 9 * (size_t)m;
+            for (int i = 0; i < 3; ++i) A.x[n + 3 * m + i] = Di[i * 3] * cl[0] + Di[i * 3 + 1] * cl[1] + Di[i * 3 + 2] * cl[2];
+          }
+        }
+        __syncthreads();
+        // ---- update (oplus) ----
+        for (int k = tid; k < A.K; k += LBA_NT)
+          if (A.hidx[k] >= 0) A.pose[k] = se3_mul(se3_exp(A.x + 6 * A.hidx[k]), A.pose[k]);
+        for (int i = tid; i < 3 * A.M; i += LBA_NT) A.pt[i] += A.x[n + i];
+        __syncthreads();
+        double tempChi = lba_errors_chi(A, hM, hS, s_red);
+        if (!solved) tempChi = 1.7976931348623157e308;
+        rho = currentChi - tempChi;
+        double sc[1] = {0};
+        for (int j = tid; j < NX; j += LBA_NT) sc[0] += A.x[j] * (lambda * A.x[j] + A.b[j]);
+        block_sum<1>(sc, s_red);
+        const double scale = sc[0] + 1e-3;
+        rho /= scale;
+        if (rho > 0 && isfinite(tempChi)) {
+          double alpha = 1. - pow((2 * rho - 1), 3.0);
+          alpha = fmin(alpha, 2. / 3.);
+          const double scaleFactor = fmax(1. / 3., alpha);
+          lambda *= scaleFactor;
+          ni = 2;
+          currentChi = tempChi;
+        } else {
+          lambda *= ni;
+          ni *= 2;
+          for (int k = tid; k < A.K; k += LBA_NT) A.pose[k] = A.poseBak[k];   // pop
+          for (int i = tid; i < 3 * A.M; i += LBA_NT) A.pt[i] = A.ptBak[i];
+        }
+        __syncthreads();
+        ++qmax;
+        stopped = lba_stop(A, &s_flag);
+      } while (rho < 0 && qmax < 100 && !stopped);
+      ++cj;
+      if (qmax == 100 || rho == 0) { ok = false; continue; }
+      if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
+      if (nBad >= 3) ok = false;
+    }
+    if (tid == 0) A.iters[call] = cj;
+  }
+  __syncthreads();
+  // ---- final chi2 / depth test on the residuals of the last evaluated state (src/Optimizer.cc:2295-2352) ----
+  double bad[1] = {0};
+  for (int e = tid; e < A.E; e += LBA_NT) {
+    const bool st = A.obs[3 * e + 2] >= 0;
+    const double om = (double)A.invSigma2[e];
+    const double* r = A.err + 3 * e;
+    const double c = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
+    double p[3];
+    se3_map(A.pose[A.ekf[e]], A.pt + 3 * (size_t)A.emp[e], p);
+    const bool isBad = c > (st ? 7.815 : 5.991) || !(p[2] > 0.0);
+    A.edgeBad[e] = isBad ? 1 : 0;
+    bad[0] += isBad ? 1.0 : 0.0;
+  }
+  block_sum<1>(bad, s_red);
+  if (bad[0] >= A.E * 0.5) {
+    if (tid == 0) *A.status = 2;
+    return;
+  }
+  for (int k = tid; k < A.K; k += LBA_NT)
+    if (!A.kfFixed[k]) se3_to_Tcw(A.pose[k], A.kfT + 16 * k);
+  for (int i = tid; i < 3 * A.M; i += LBA_NT) A.mpXyz[i] = (float)A.pt[i];
+  (void)s_scal;
+}
+
+// =====================================================================================
+// host entry points
+// =====================================================================================
+extern "C" {
+
+int orbx_pose_optimization_batch_device(orbx_ctx* ctx, int P, const int32_t* d_edge_ofs, const float* d_xw,
+                                        const float* d_obs, const float* d_inv_sigma2, const orbx_camera* cam,
+                                        float* d_Tcw, uint8_t* d_outlier, int32_t* d_n_inliers, int32_t* d_iters,
+                                        double* d_scratch) {
+  if (!ctx || P < 1 || !d_edge_ofs || !d_xw || !d_obs || !d_inv_sigma2 || !cam || !d_Tcw || !d_outlier || !d_n_inliers ||
+      !d_iters || !d_scratch)
+    return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  PoseOptArgs A;
+  A.edgeOfs = d_edge_ofs;
+  A.xw = d_xw;
+  A.obs = d_obs;
+  A.invSigma2 = d_inv_sigma2;
+  A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
+  A.Tcw = d_Tcw;
+  A.outlier = d_outlier;
+  A.nInliers = d_n_inliers;
+  A.iters = d_iters;
+  A.err = d_scratch;
+  pose_opt_kernel<<<P, PO_NT, 0, ctx->stream>>>(A);
+  ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+int orbx_pose_optimization(orbx_ctx* ctx, int n_edges, const float* xw, const float* obs, const float* inv_sigma2,
+                           const orbx_camera* cam, float* Tcw, uint8_t* outlier, int32_t* n_inliers, int32_t* iters) {
+  if (!ctx || n_edges < 0 || !cam || !Tcw || !n_inliers || !iters) return ORBX_EINVAL;
+  if (n_edges > 0 && (!xw || !obs || !inv_sigma2 || !outlier)) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevScope S(st);
+  const int ofs[2] = {0, n_edges};
+  int* d_ofs = S.upload(ofs, 2);
+  float* d_xw = S.upload(xw, (size_t)3 * n_edges);
+  float* d_obs = S.upload(obs, (size_t)3 * n_edges);
+  float* d_isg = S.upload(inv_sigma2, n_edges);
+  float* d_T = S.upload(Tcw, 16);
+  uint8_t* d_out = S.alloc<uint8_t>(n_edges);
+  int* d_res = S.alloc<int>(5);
+  double* d_scr = S.alloc<double>((size_t)3 * n_edges);
+  if (S.failed) return ORBX_ECUDA;
+  int rc = orbx_pose_optimization_batch_device(ctx, 1, d_ofs, d_xw, d_obs, d_isg, cam, d_T, d_out, d_res, d_res + 1, d_scr);
+  if (rc != ORBX_OK) return rc;
+  int h[5];
+  ORBX_CUDA(cudaMemcpyAsync(h, d_res, sizeof h, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaMemcpyAsync(Tcw, d_T, 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (n_edges > 0) ORBX_CUDA(cudaMemcpyAsync(outlier, d_out, n_edges, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaStreamSynchronize(st));
+  *n_inliers = h[0];
+  for (int i = 0; i < 4; ++i) iters[i] = h[1 + i];
+  return ORBX_OK;
+}
+
+int orbx_local_ba(orbx_ctx* ctx, int n_kf, float* kf_Tcw, const uint8_t* kf_fixed, int n_mp, float* mp_xyz, int n_edges,
+                  const int32_t* e_kf, const int32_t* e_mp, const float* e_obs, const float* e_inv_sigma2,
+                  const orbx_camera* cam, double lambda_init, const volatile uint8_t* stop_flag, uint8_t* edge_bad,
+                  int32_t* iters, int32_t* status) {
+  if (!ctx || n_kf < 1 || !kf_Tcw || !kf_fixed || n_mp < 1 || !mp_xyz || n_edges < 1 || !e_kf || !e_mp || !e_obs ||
+      !e_inv_sigma2 || !cam || !edge_bad || !iters || !status)
+    return ORBX_EINVAL;
+  for (int e = 0; e < n_edges; ++e)
+    if (e_kf[e] < 0 || e_kf[e] >= n_kf || e_mp[e] < 0 || e_mp[e] >= n_mp) {
+      orbx_set_error("orbx_local_ba: edge %d references vertex out of range", e);
+      return ORBX_EINVAL;
+    }
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevScope S(st);
+  LbaArgs A;
+  A.K = n_kf; A.M = n_mp; A.E = n_edges;
+  // --- graph indices (the reference builds the same adjacency inside g2o's buildStructure) ---
+  std::vector<int> hidx(n_kf, -1);
+  int nFree = 0;
+  for (int k = 0; k < n_kf; ++k)
+    if (!kf_fixed[k]) hidx[k] = nFree++;
+  A.nFree = nFree;
+  A.n = 6 * nFree;
+  std::vector<int> ptAllOfs(n_mp + 1, 0), ptOfs(n_mp + 1, 0), kfOfs(nFree + 1, 0);
+  for (int e = 0; e < n_edges; ++e) {
+    ++ptAllOfs[e_mp[e] + 1];
+    if (hidx[e_kf[e]] >= 0) { ++ptOfs[e_mp[e] + 1]; ++kfOfs[hidx[e_kf[e]] + 1]; }
+  }
+  for (int m = 0; m < n_mp; ++m) { ptAllOfs[m + 1] += ptAllOfs[m]; ptOfs[m + 1] += ptOfs[m]; }
+  for (int k = 0; k < nFree; ++k) kfOfs[k + 1] += kfOfs[k];
+  std::vector<int> ptAllEdges(std::max(n_edges, 1)), ptEdges(std::max(ptOfs[n_mp], 1)), kfEdges(std::max(kfOfs[nFree], 1));
+  std::vector<int> obsEdge((size_t)n_mp * std::max(nFree, 1), -1);
+  {
+    std::vector<int> a(ptAllOfs.begin(), ptAllOfs.end() - 1), b(ptOfs.begin(), ptOfs.end() - 1), c(kfOfs.begin(), kfOfs.end() - 1);
+    for (int e = 0; e < n_edges; ++e) {
+      ptAllEdges[a[e_mp[e]]++] = e;
+      const int hk = hidx[e_kf[e]];
+      if (hk >= 0) {
+        ptEdges[b[e_mp[e]]++] = e;
+        kfEdges[c[hk]++] = e;
+        obsEdge[(size_t)e_mp[e] * nFree + hk] = e;   // a (KeyFrame, MapPoint) pair has one observation
+      }
+    }
+  }
+  A.kfT = S.upload(kf_Tcw, (size_t)16 * n_kf);
+  A.kfFixed = S.upload(kf_fixed, n_kf);
+  A.mpXyz = S.upload(mp_xyz, (size_t)3 * n_mp);
+  A.ekf = S.upload(e_kf, n_edges);
+  A.emp = S.upload(e_mp, n_edges);
+  A.obs = S.upload(e_obs, (size_t)3 * n_edges);
+  A.invSigma2 = S.upload(e_inv_sigma2, n_edges);
+  A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
+  A.lambdaInit = lambda_init;
+  A.hidx = S.upload(hidx.data(), n_kf);
+  A.ptOfs = S.upload(ptOfs.data(), n_mp + 1);
+  A.ptEdges = S.upload(ptEdges.data(), ptEdges.size());
+  A.ptAllOfs = S.upload(ptAllOfs.data(), n_mp + 1);
+  A.ptAllEdges = S.upload(ptAllEdges.data(), ptAllEdges.size());
+  A.kfOfs = S.upload(kfOfs.data(), nFree + 1);
+  A.kfEdges = S.upload(kfEdges.data(), kfEdges.size());
+  A.obsEdge = S.upload(obsEdge.data(), obsEdge.size());
+  A.pose = S.alloc<SE3d>(n_kf);
+  A.poseBak = S.alloc<SE3d>(n_kf);
+  A.pt = S.alloc<double>((size_t)3 * n_mp);
+  A.ptBak = S.alloc<double>((size_t)3 * n_mp);
+  A.err = S.alloc<double>((size_t)3 * n_edges);
+  A.Ji = S.alloc<double>((size_t)9 * n_edges);
+  A.Jj = S.alloc<double>((size_t)18 * n_edges);
+  A.wom = S.alloc<double>(n_edges);
+  A.omr = S.alloc<double>((size_t)3 * n_edges);
+  A.Hpl = S.alloc<double>((size_t)18 * n_edges);
+  A.BD = S.alloc<double>((size_t)18 * n_edges);
+  A.Hll = S.alloc<double>((size_t)9 * n_mp);
+  A.Dinv = S.alloc<double>((size_t)9 * n_mp);
+  A.Hpp = S.alloc<double>((size_t)36 * std::max(nFree, 1));
+  A.b = S.alloc<double>((size_t)A.n + 3 * n_mp);
+  A.x = S.alloc<double>((size_t)A.n + 3 * n_mp);
+  A.S = S.alloc<double>((size_t)std::max(A.n, 1) * std::max(A.n, 1));
+  A.bs = S.alloc<double>(std::max(A.n, 1));
+  A.db = S.alloc<double>((size_t)3 * n_mp);
+  A.edgeBad = S.alloc<uint8_t>(n_edges);
+  int* d_res = S.alloc<int>(3);
+  A.iters = d_res;
+  A.status = d_res + 2;
+  // stop flag: a mapped pinned byte the kernel polls; the host forwards *stop_flag into it while waiting
+  uint8_t* h_flag = nullptr;
+  uint8_t* d_flag = nullptr;
+  if (stop_flag) {
+    ORBX_CUDA(cudaHostAlloc(&h_flag, 64, cudaHostAllocMapped));
+    *h_flag = *stop_flag ? 1 : 0;
+    ORBX_CUDA(cudaHostGetDevicePointer(&d_flag, h_flag, 0));
+  }
+  A.stop = d_flag;
+  if (S.failed) { if (h_flag) cudaFreeHost(h_flag); return ORBX_ECUDA; }
+  lba_kernel<<<1, LBA_NT, 0, st>>>(A);
+  ORBX_LAUNCH(ctx);
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    if (h_flag) cudaFreeHost(h_flag);
+    orbx_set_error("orbx_local_ba: launch failed: %s", cudaGetErrorString(le));
+    return ORBX_ECUDA;
+  }
+  int h[3];
+  cudaEvent_t done;
+  ORBX_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  ORBX_CUDA(cudaMemcpyAsync(h, d_res, sizeof h, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaMemcpyAsync(edge_bad, A.edgeBad, n_edges, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaEventRecord(done, st));
+  if (stop_flag) {
+    while (cudaEventQuery(done) == cudaErrorNotReady)
+      if (*stop_flag) *(volatile uint8_t*)h_flag = 1;   // forward Tracking's InterruptBA() to the device
+  }
+  cudaError_t e2 = cudaEventSynchronize(done);
+  cudaEventDestroy(done);
+  if (e2 != cudaSuccess) {
+    if (h_flag) cudaFreeHost(h_flag);
+    orbx_set_error("orbx_local_ba: %s", cudaGetErrorString(e2));
+    return ORBX_ECUDA;
+  }
+  iters[0] = h[0];
+  iters[1] = h[1];
+  *status = h[2];
+  if (h[2] == 0) {
+    ORBX_CUDA(cudaMemcpyAsync(kf_Tcw, A.kfT, sizeof(float) * 16 * n_kf, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaMemcpyAsync(mp_xyz, A.mpXyz, sizeof(float) * 3 * n_mp, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(cudaStreamSynchronize(st));
+  }
+  if (h_flag) cudaFreeHost(h_flag);
+  return ORBX_OK;
+}
+
+}  // extern "C"

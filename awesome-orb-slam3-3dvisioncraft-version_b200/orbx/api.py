@@ -79,6 +79,9 @@ def load_library():
                                                   vp, vp, vp, vp]
     L.orbx_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp,
                                                 vp, vp, vp, vp, i, i, i, i, vp, vp]
+    L.orbx_pose_optimization.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.orbx_pose_optimization_batch_device.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.orbx_local_ba.argtypes = [vp, i, vp, vp, i, vp, i, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
     L.orbx_pyramid_level.argtypes = [vp, i, i, vp, i, vp, vp]
     L.orbx_debug_candidates.argtypes = [vp, i, i, vp, vp, i, vp]
     _LIB = L
@@ -333,3 +336,42 @@ def stereo_match(ctx, extL, bL, extR, bR, kpL, descL, kpR, descR, bf, b):
                                             _p(descR), len(kpR), float(bf), float(b), _p(ur), _p(dp)),
            "orbx_stereo_match")
     return ur, dp
+
+
+class Optimizer:
+    """Mirror of the two static ORB_SLAM3::Optimizer entry points on the hot path (include/Optimizer.h:58,62)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def PoseOptimization(self, xw, obs, inv_sigma2, cam, Tcw):
+        """-> (Tcw_out[4,4], mvbOutlier[E], return value, LM iterations per round[4])"""
+        xw, obs, isg = _c32(xw, np.float32), _c32(obs, np.float32), _c32(inv_sigma2, np.float32)
+        T = np.array(Tcw, np.float32).reshape(4, 4).copy()
+        E = len(isg)
+        outl = np.zeros(max(E, 1), np.uint8)
+        nin = C.c_int(0)
+        iters = np.zeros(4, np.int32)
+        rc = load_library().orbx_pose_optimization(self.ctx.h, E, _ptr(xw), _ptr(obs), _ptr(isg), C.byref(cam), _p(T),
+                                                   _p(outl), C.byref(nin), _p(iters))
+        _check(rc, "orbx_pose_optimization")
+        return T, outl[:E].copy(), nin.value, iters
+
+    def LocalBundleAdjustment(self, kf_T, kf_fixed, mp_xyz, e_kf, e_mp, e_obs, e_inv_sigma2, cam, lambda_init=0.0,
+                              stop=None):
+        """-> (kf_T_out[K,4,4], mp_xyz_out[M,3], edge_bad[E], iters[2], status)"""
+        T = np.array(kf_T, np.float32).reshape(-1, 16).copy()
+        X = np.array(mp_xyz, np.float32).reshape(-1, 3).copy()
+        fixed = _c32(kf_fixed, np.uint8)
+        ekf, emp = _c32(e_kf, np.int32), _c32(e_mp, np.int32)
+        obs, isg = _c32(e_obs, np.float32), _c32(e_inv_sigma2, np.float32)
+        E = len(ekf)
+        bad = np.zeros(max(E, 1), np.uint8)
+        iters = np.zeros(2, np.int32)
+        status = C.c_int(0)
+        st = _c32(stop, np.uint8) if stop is not None else None
+        rc = load_library().orbx_local_ba(self.ctx.h, len(T), _p(T), _ptr(fixed), len(X), _p(X), E, _ptr(ekf), _ptr(emp),
+                                          _ptr(obs), _ptr(isg), C.byref(cam), float(lambda_init), _ptr(st), _p(bad),
+                                          _p(iters), C.byref(status))
+        _check(rc, "orbx_local_ba")
+        return T.reshape(-1, 4, 4), X, bad[:E].copy(), iters, status.value

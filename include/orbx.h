@@ -230,6 +230,50 @@ int orbx_search_for_triangulation(orbx_ctx *ctx, const orbx_frame_desc *kf1,
                                   int coarse, int check_orientation, int32_t *match12,
                                   int32_t *nmatches);
 
+/* ====================================================================================
+ * Optimisers (g2o linearisation + Levenberg-Marquardt as modified by ORB-SLAM3, all fp64 on
+ * the device; one thread block runs a whole optimisation).
+ * ================================================================================== */
+
+/* Optimizer::PoseOptimization(Frame*) (src/Optimizer.cc:907-1272).
+ *   n_edges     : keypoints i with pFrame->mvpMapPoints[i] != NULL, in increasing i
+ *   xw[e][3]    : pMP->GetWorldPos() (float32, as the reference copies it)
+ *   obs[e][3]   : kpUn.pt.x, kpUn.pt.y, mvuRight[i]   (mvuRight < 0 => monocular 2-D edge, else 3-D stereo edge)
+ *   inv_sigma2  : pFrame->mvInvLevelSigma2[kpUn.octave]
+ *   Tcw[16]     : pFrame->mTcw, row-major float32; overwritten with the optimised pose
+ * Out: outlier[e] = pFrame->mvbOutlier; *n_inliers = the reference's return value
+ *      (nInitialCorrespondences - nBad, 0 and pose untouched when n_edges < 3);
+ *      iters[4] = LM iterations g2o ran in each of the four rounds (parity evidence). */
+int orbx_pose_optimization(orbx_ctx *ctx, int n_edges, const float *xw, const float *obs,
+                           const float *inv_sigma2, const orbx_camera *cam, float *Tcw,
+                           uint8_t *outlier, int32_t *n_inliers, int32_t *iters);
+
+/* Many-stream mode: P independent PoseOptimization problems in one launch.  edge_ofs[P+1]
+ * delimits each problem's slice of xw/obs/inv_sigma2/outlier; Tcw is [P][16]; n_inliers [P];
+ * iters [P][4].  All pointers are DEVICE pointers; the call only enqueues on orbx_stream(ctx). */
+int orbx_pose_optimization_batch_device(orbx_ctx *ctx, int P, const int32_t *d_edge_ofs,
+                                        const float *d_xw, const float *d_obs,
+                                        const float *d_inv_sigma2, const orbx_camera *cam,
+                                        float *d_Tcw, uint8_t *d_outlier, int32_t *d_n_inliers,
+                                        int32_t *d_iters, double *d_scratch /* [3 * total_edges] */);
+
+/* Optimizer::LocalBundleAdjustment(KeyFrame*, bool *pbStopFlag, Map*, int &num_fixedKF)
+ * (src/Optimizer.cc:1811-2523) — the numeric core: graph = n_kf SE3 vertices (kf_fixed[k] != 0:
+ * fixed), n_mp marginalised points, one edge per observation (mono 2-D when obs[e][2] < 0, else
+ * stereo 3-D), Huber on every edge, optimize(5) then optimize(10), final chi2/depth test.
+ *   kf_Tcw[n_kf][16], mp_xyz[n_mp][3] : in/out, float32 (written back unless aborted)
+ *   e_kf/e_mp/e_obs/e_inv_sigma2      : per observation
+ *   lambda_init : 0 => g2o's tau*max(diag) rule; the reference passes 100 for inertial maps (:1968)
+ *   stop_flag   : HOST pointer polled like g2o's forceStopFlag (*pbStopFlag), may be NULL
+ * Out: edge_bad[e] = 1 for observations the reference would erase (vToErase, :2295-2344);
+ *      iters[2] = LM iterations of the two optimize() calls;
+ *      *status = 0 done, 1 stopped before optimising, 2 rejected (>= 50 % bad: nothing written). */
+int orbx_local_ba(orbx_ctx *ctx, int n_kf, float *kf_Tcw, const uint8_t *kf_fixed, int n_mp,
+                  float *mp_xyz, int n_edges, const int32_t *e_kf, const int32_t *e_mp,
+                  const float *e_obs, const float *e_inv_sigma2, const orbx_camera *cam,
+                  double lambda_init, const volatile uint8_t *stop_flag, uint8_t *edge_bad,
+                  int32_t *iters, int32_t *status);
+
 #ifdef __cplusplus
 }
 #endif

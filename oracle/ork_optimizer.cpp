@@ -19,7 +19,40 @@
 #include <cstring>
 #include <limits>
 
+#include <array>
+
 namespace ork {
+
+// Summation order.  The reference does not define one: g2o walks `_activeEdges` after a std::sort on
+// edge ids that are all equal (sparse_optimizer.cpp:482-487), and LocalBA inserts a point's edges in
+// KeyFrame-pointer order (Optimizer.cc:2080).  The oracle therefore fixes ONE order, chosen so that a
+// parallel machine can reproduce it bit for bit: items are dealt round-robin to NT accumulators (item i
+// goes to accumulator i % NT, each accumulator adds its items in increasing i), every group of 32
+// accumulators is combined by the 5-stage xor butterfly (offsets 16,8,4,2,1), and the group results are
+// added in group order.  With NT = 1 this is the plain sequential sum.
+template <int NV>
+struct TreeAcc {
+  int NT;
+  std::vector<std::array<double, NV>> part;
+  explicit TreeAcc(int nt) : NT(nt), part(nt) {
+    for (auto& p : part) p.fill(0.0);
+  }
+  std::array<double, NV>& slot(int item) { return part[item % NT]; }
+  void finish(double* out) {
+    for (int g = 0; g < NT / 32; ++g)
+      for (int o = 16; o > 0; o >>= 1) {
+        std::array<double, NV> tmp[32];
+        for (int l = 0; l < 32; ++l)
+          for (int k = 0; k < NV; ++k) tmp[l][k] = part[g * 32 + l][k] + part[g * 32 + (l ^ o)][k];
+        for (int l = 0; l < 32; ++l) part[g * 32 + l] = tmp[l];
+      }
+    for (int k = 0; k < NV; ++k) {
+      double sum = 0;
+      for (int g = 0; g < NT / 32; ++g) sum += part[g * 32][k];
+      out[k] = sum;
+    }
+  }
+};
 
 struct Quat { double x, y, z, w; };
 struct SE3 { Quat r; double t[3]; };
@@ -314,18 +347,19 @@ struct PoseProblem {
       if (active[e]) edge_error(e, est, &err[3 * e]);
   }
   double robustChi2() const {
-    double chi = 0;
+    TreeAcc<1> acc(128);
     for (int e = 0; e < E; ++e) {
       if (!active[e]) continue;
       const double c = chi2(e);
       double w;
-      chi += robust ? (stereo[e] ? hStereo : hMono).robustify(c, w) : c;
+      acc.slot(e)[0] += robust ? (stereo[e] ? hStereo : hMono).robustify(c, w) : c;
     }
+    double chi;
+    acc.finish(&chi);
     return chi;
   }
   void buildSystem() {
-    std::memset(H, 0, sizeof H);
-    std::memset(b, 0, sizeof b);
+    TreeAcc<27> acc(128);   // 21 upper-triangle entries of H, then b
     for (int e = 0; e < E; ++e) {
       if (!active[e]) continue;
       const double X[3] = {xw[3 * e], xw[3 * e + 1], xw[3 * e + 2]};
@@ -358,17 +392,25 @@ struct PoseProblem {
       double w = 1.0;
       if (robust) (stereo[e] ? hStereo : hMono).robustify(chi2(e), w);
       const double* r = &err[3 * e];
+      std::array<double, 27>& a27 = acc.slot(e);
+      int idx = 0;
       for (int i = 0; i < 6; ++i) {
-        double s = 0;
-        for (int d = 0; d < D; ++d) s += J[d * 6 + i] * om * r[d];
-        b[i] -= w * s;
-        for (int j = 0; j < 6; ++j) {
+        double sg = 0;
+        for (int d = 0; d < D; ++d) sg += J[d * 6 + i] * om * r[d];
+        a27[21 + i] -= w * sg;                       // b -= rho' * J^T Omega e
+        for (int j = i; j < 6; ++j) {
           double a = 0;
           for (int d = 0; d < D; ++d) a += J[d * 6 + i] * (w * om) * J[d * 6 + j];
-          H[i * 6 + j] += a;
+          a27[idx++] += a;                           // H += J^T (rho' Omega) J   (upper triangle, mirrored)
         }
       }
     }
+    double out[27];
+    acc.finish(out);
+    int idx = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) { H[i * 6 + j] = out[idx]; H[j * 6 + i] = out[idx]; ++idx; }
+    for (int i = 0; i < 6; ++i) b[i] = out[21 + i];
   }
   double maxDiagonal() const {
     double m = 0;
@@ -489,8 +531,11 @@ struct LbaProblem {
   }
   void computeErrors() { for (int e = 0; e < E; ++e) edge_error(e, &err[3 * e]); }
   double robustChi2() const {
-    double chi = 0, w;
-    for (int e = 0; e < E; ++e) chi += (stereo[e] ? hStereo : hMono).robustify(chi2(e), w);
+    TreeAcc<1> acc(1024);
+    double w;
+    for (int e = 0; e < E; ++e) acc.slot(e)[0] += (stereo[e] ? hStereo : hMono).robustify(chi2(e), w);
+    double chi;
+    acc.finish(&chi);
     return chi;
   }
   void buildSystem() {
@@ -557,25 +602,45 @@ struct LbaProblem {
       }
       const int hk = hidx[k];
       if (hk >= 0) {
-        double* bp = &b[6 * hk];
-        double* hp = &Hpp[36 * (size_t)hk];
         double* hpl = &Hpl[18 * (size_t)e];
-        for (int i = 0; i < 6; ++i) {
-          double s = 0;
-          for (int d = 0; d < D; ++d) s += Jj[d * 6 + i] * omr[d];
-          bp[i] += s;
-          for (int j = 0; j < 6; ++j) {
-            double a = 0;
-            for (int d = 0; d < D; ++d) a += Jj[d * 6 + i] * wo * Jj[d * 6 + j];
-            hp[i * 6 + j] += a;
-          }
+        for (int i = 0; i < 6; ++i)
           for (int j = 0; j < 3; ++j) {
             double a = 0;
             for (int d = 0; d < D; ++d) a += Jj[d * 6 + i] * wo * Ji[d * 3 + j];
-            hpl[i * 3 + j] += a;   // pose-landmark block of this observation
+            hpl[i * 3 + j] = a;   // pose-landmark block of this observation
+          }
+        // contribution to the pose's own block, gathered below in the pose's edge-list order
+        std::array<double, 27>& c = poseContrib[e];
+        int idx = 0;
+        for (int i = 0; i < 6; ++i) {
+          double sg = 0;
+          for (int d = 0; d < D; ++d) sg += Jj[d * 6 + i] * omr[d];
+          c[21 + i] = sg;
+          for (int j = i; j < 6; ++j) {
+            double a = 0;
+            for (int d = 0; d < D; ++d) a += Jj[d * 6 + i] * wo * Jj[d * 6 + j];
+            c[idx++] = a;
           }
         }
       }
+    }
+    for (int hk = 0; hk < nFree; ++hk) {
+      TreeAcc<27> acc(32);
+      const std::vector<int>& L = edgesOfPose[hk];
+      for (size_t q = 0; q < L.size(); ++q) {
+        std::array<double, 27>& sl = acc.slot((int)q);
+        for (int i = 0; i < 27; ++i) sl[i] += poseContrib[L[q]][i];
+      }
+      double out[27];
+      acc.finish(out);
+      int idx = 0;
+      for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) {
+          Hpp[36 * (size_t)hk + i * 6 + j] = out[idx];
+          Hpp[36 * (size_t)hk + j * 6 + i] = out[idx];
+          ++idx;
+        }
+      for (int i = 0; i < 6; ++i) b[6 * hk + i] = out[21 + i];
     }
   }
   double maxDiagonal() const {
@@ -589,12 +654,13 @@ struct LbaProblem {
   void push() { poseBackup = pose; ptBackup = pt; }
   void pop() { pose = poseBackup; pt = ptBackup; }
   std::vector<std::vector<int>> edgesOfPoint;   // observation lists per point (free poses only)
+  std::vector<std::vector<int>> edgesOfPose;    // observation lists per free pose
+  std::vector<std::array<double, 27>> poseContrib;
+  std::vector<int> obsEdge;                     // [M][nFree] edge id of (point, free pose) or -1
   bool solve(double lambda) {
     const int n = 6 * nFree;
-    std::vector<double> S((size_t)n * n, 0.0), bs(b.begin(), b.begin() + n), Dinv((size_t)9 * M);
-    for (int k = 0; k < nFree; ++k)
-      for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) S[(size_t)(6 * k + i) * n + 6 * k + j] = Hpp[36 * (size_t)k + i * 6 + j] + (i == j ? lambda : 0.0);
+    std::vector<double> S((size_t)std::max(n, 1) * std::max(n, 1), 0.0), bs(std::max(n, 1)), Dinv((size_t)9 * M), db((size_t)3 * M);
+    std::vector<double> BD((size_t)18 * E, 0.0);
     for (int m = 0; m < M; ++m) {
       double D[9];
       for (int i = 0; i < 9; ++i) D[i] = Hll[9 * (size_t)m + i];
@@ -607,24 +673,54 @@ struct LbaProblem {
       Di[3] = c01 * id; Di[4] = (D[0] * D[8] - D[2] * D[6]) * id; Di[5] = (D[2] * D[3] - D[0] * D[5]) * id;
       Di[6] = c02 * id; Di[7] = (D[1] * D[6] - D[0] * D[7]) * id; Di[8] = (D[0] * D[4] - D[1] * D[3]) * id;
       const double* bl = &b[n + 3 * m];
-      double db[3];
-      for (int i = 0; i < 3; ++i) db[i] = Di[i * 3] * bl[0] + Di[i * 3 + 1] * bl[1] + Di[i * 3 + 2] * bl[2];
-      const std::vector<int>& obsE = edgesOfPoint[m];
-      for (size_t a = 0; a < obsE.size(); ++a) {
-        const int e1 = obsE[a], k1 = hidx[ekf[e1]];
-        const double* B1 = &Hpl[18 * (size_t)e1];
-        double BD[18];
-        for (int i = 0; i < 6; ++i)
-          for (int j = 0; j < 3; ++j) BD[i * 3 + j] = B1[i * 3] * Di[j] + B1[i * 3 + 1] * Di[3 + j] + B1[i * 3 + 2] * Di[6 + j];
-        for (int i = 0; i < 6; ++i) bs[6 * k1 + i] -= B1[i * 3] * db[0] + B1[i * 3 + 1] * db[1] + B1[i * 3 + 2] * db[2];
-        for (size_t c = 0; c < obsE.size(); ++c) {
-          const int e2 = obsE[c], k2 = hidx[ekf[e2]];
+      for (int i = 0; i < 3; ++i) db[3 * m + i] = Di[i * 3] * bl[0] + Di[i * 3 + 1] * bl[1] + Di[i * 3 + 2] * bl[2];
+    }
+    for (int e = 0; e < E; ++e) {
+      if (hidx[ekf[e]] < 0) continue;
+      const double* B = &Hpl[18 * (size_t)e];
+      const double* Di = &Dinv[9 * (size_t)emp[e]];
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 3; ++j) BD[18 * (size_t)e + i * 3 + j] = B[i * 3] * Di[j] + B[i * 3 + 1] * Di[3 + j] + B[i * 3 + 2] * Di[6 + j];
+    }
+    // reduced camera system, block (bi, bj >= bi): Hpp + lambda I (diagonal) - sum over pose bi's edges e1 whose
+    // point is also seen by pose bj (edge e2) of (B_e1 Dinv) B_e2^T ; the lower block is its transpose
+    for (int bi = 0; bi < nFree; ++bi)
+      for (int bj = bi; bj < nFree; ++bj) {
+        TreeAcc<36> acc(32);
+        const std::vector<int>& L = edgesOfPose[bi];
+        for (size_t q = 0; q < L.size(); ++q) {
+          const int e1 = L[q], e2 = obsEdge[(size_t)emp[e1] * nFree + bj];
+          if (e2 < 0) continue;
+          const double* bd = &BD[18 * (size_t)e1];
           const double* B2 = &Hpl[18 * (size_t)e2];
+          std::array<double, 36>& sl = acc.slot((int)q);
           for (int i = 0; i < 6; ++i)
             for (int j = 0; j < 6; ++j)
-              S[(size_t)(6 * k1 + i) * n + 6 * k2 + j] -= BD[i * 3] * B2[j * 3] + BD[i * 3 + 1] * B2[j * 3 + 1] + BD[i * 3 + 2] * B2[j * 3 + 2];
+              sl[i * 6 + j] += bd[i * 3] * B2[j * 3] + bd[i * 3 + 1] * B2[j * 3 + 1] + bd[i * 3 + 2] * B2[j * 3 + 2];
         }
+        double out[36];
+        acc.finish(out);
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) {
+            double v = -out[i * 6 + j];
+            if (bi == bj) v += Hpp[36 * (size_t)bi + i * 6 + j] + (i == j ? lambda : 0.0);
+            S[(size_t)(6 * bi + i) * n + 6 * bj + j] = v;
+            S[(size_t)(6 * bj + j) * n + 6 * bi + i] = v;
+          }
       }
+    for (int hk = 0; hk < nFree; ++hk) {
+      TreeAcc<6> acc(32);
+      const std::vector<int>& L = edgesOfPose[hk];
+      for (size_t q = 0; q < L.size(); ++q) {
+        const int e = L[q];
+        const double* B = &Hpl[18 * (size_t)e];
+        const double* d3 = &db[3 * (size_t)emp[e]];
+        std::array<double, 6>& sl = acc.slot((int)q);
+        for (int i = 0; i < 6; ++i) sl[i] += B[i * 3] * d3[0] + B[i * 3 + 1] * d3[1] + B[i * 3 + 2] * d3[2];
+      }
+      double out[6];
+      acc.finish(out);
+      for (int i = 0; i < 6; ++i) bs[6 * hk + i] = b[6 * hk + i] - out[i];
     }
     std::fill(x.begin(), x.end(), 0.0);
     if (n > 0 && !ldlt_solve_plain(n, S.data(), bs.data(), x.data())) return false;
@@ -649,9 +745,11 @@ struct LbaProblem {
     for (int i = 0; i < 3 * M; ++i) pt[i] += x[n + i];
   }
   double computeScale(double lambda) const {
-    double s = 0;
-    for (size_t j = 0; j < x.size(); ++j) s += x[j] * (lambda * x[j] + b[j]);
-    return s;
+    TreeAcc<1> acc(1024);
+    for (size_t j = 0; j < x.size(); ++j) acc.slot((int)j)[0] += x[j] * (lambda * x[j] + b[j]);
+    double sc;
+    acc.finish(&sc);
+    return sc;
   }
 };
 
@@ -688,8 +786,15 @@ int ork_local_ba(int K, float* kfT, const uint8_t* kfFixed, int M, float* mpXyz,
   P.b.assign((size_t)6 * P.nFree + 3 * M, 0.0);
   P.x.assign(P.b.size(), 0.0);
   P.edgesOfPoint.assign(M, {});
+  P.edgesOfPose.assign(P.nFree, {});
+  P.poseContrib.resize(E);
+  P.obsEdge.assign((size_t)M * std::max(P.nFree, 1), -1);
   for (int e = 0; e < E; ++e)
-    if (P.hidx[ekf[e]] >= 0) P.edgesOfPoint[emp[e]].push_back(e);
+    if (P.hidx[ekf[e]] >= 0) {
+      P.edgesOfPoint[emp[e]].push_back(e);
+      P.edgesOfPose[P.hidx[ekf[e]]].push_back(e);
+      P.obsEdge[(size_t)emp[e] * P.nFree + P.hidx[ekf[e]]] = e;
+    }
   iters[0] = lm_optimize(P, 5, lambdaInit, stop);
   bool doMore = !(stop && *stop);
   if (doMore) iters[1] = lm_optimize(P, 10, lambdaInit, stop);

@@ -1,0 +1,128 @@
+"""GPU parity: liborbx PoseOptimization / LocalBundleAdjustment (C ABI) vs the CPU oracle.
+
+fp64 on both sides with identical expressions; only the summation order differs (device: fixed-shape
+trees; oracle: edge order), so poses must agree far inside the 1e-4 rad / 1e-3 m target, with the same
+LM iteration counts and the same inlier/outlier classification."""
+import numpy as np
+import pytest
+
+import scenarios as sc
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL_RAD, T_TOL_M = 1e-4, 1e-3          # north_star tolerance
+TIGHT = 2e-6                               # what identical arithmetic actually delivers (float32 outputs)
+
+
+def _pose_delta(Ta, Tb):
+    Ra, Rb = Ta[:3, :3].astype(float), Tb[:3, :3].astype(float)
+    # small-angle rotation distance ||Ra - Rb||_F / sqrt(2) (arccos of the trace is ill-conditioned near 0
+    # on float32 matrices: a 1e-7 rounding of the trace already reads as 4e-4 rad)
+    ang = np.linalg.norm(Ra - Rb) / np.sqrt(2.0)
+    return ang, np.linalg.norm(Ta[:3, 3].astype(float) - Tb[:3, 3].astype(float))
+
+
+@pytest.mark.parametrize("E,stereo_frac", [(150, 0.7), (300, 0.7), (500, 0.7), (300, 0.0), (300, 1.0)])
+def test_pose_optimization_matches_oracle(ctx, ork, E, stereo_frac):
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    flips = 0
+    for seed in range(12):
+        s = sc.pose_opt_scenario(100 * E + seed, E=E, stereo_frac=stereo_frac)
+        rT, rout, rn, rit = ork.pose_optimization(s["xw"], s["obs"], s["inv_sigma2"], cam, s["Tcw"])
+        gT, gout, gn, git = opt.PoseOptimization(s["xw"], s["obs"], s["inv_sigma2"], cam, s["Tcw"])
+        assert np.array_equal(git, rit), (seed, git, rit)            # same iteration count, every round
+        ang, dt = _pose_delta(gT, rT)
+        assert ang < ROT_TOL_RAD and dt < T_TOL_M
+        assert ang < TIGHT and dt < TIGHT, (seed, ang, dt)
+        flips += int((gout != rout).sum())
+        assert abs(gn - rn) <= int((gout != rout).sum())
+        # and the optimiser did its job: close to the ground truth, gross outliers rejected
+        ang_gt, dt_gt = _pose_delta(gT, s["Tgt"].astype(np.float32))
+        assert ang_gt < np.radians(0.3) and dt_gt < 0.03
+        assert not (s["is_outlier"] & (gout == 0)).any()
+    assert flips == 0, "chi2-threshold decisions flipped for %d edges" % flips
+
+
+def test_pose_optimization_edge_cases(ctx, ork):
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    s = sc.pose_opt_scenario(1, E=300)
+    for E in (0, 2, 3, 9, 10):        # <3: untouched pose, returns 0 ; <10 edges: a single round
+        sl = slice(0, E)
+        rT, rout, rn, rit = ork.pose_optimization(s["xw"][sl], s["obs"][sl], s["inv_sigma2"][sl], cam, s["Tcw"])
+        gT, gout, gn, git = opt.PoseOptimization(s["xw"][sl], s["obs"][sl], s["inv_sigma2"][sl], cam, s["Tcw"])
+        assert gn == rn and np.array_equal(git, rit) and np.array_equal(gout, rout), E
+        assert np.allclose(gT, rT, atol=1e-5)
+        if E < 3:
+            assert gn == 0 and np.array_equal(gT, s["Tcw"].reshape(4, 4))
+        if 3 <= E < 10:
+            assert git[1:].sum() == 0
+
+
+@pytest.mark.parametrize("K,M,nfixed", [(6, 300, 2), (20, 3000, 3)])
+def test_local_ba_matches_oracle(ctx, ork, K, M, nfixed):
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    for seed in range(2):
+        s = sc.lba_scenario(seed, K=K, M=M, n_fixed=nfixed)
+        a = (s["kf_T"], s["kf_fixed"], s["mp_xyz"], s["e_kf"], s["e_mp"], s["e_obs"], s["e_inv_sigma2"], cam)
+        rT, rX, rbad, rit, rst = ork.local_ba(*a)
+        gT, gX, gbad, git, gst = opt.LocalBundleAdjustment(*a)
+        assert gst == rst == 0
+        assert np.array_equal(git, rit), (git, rit)
+        for k in range(K):
+            ang, dt = _pose_delta(gT[k], rT[k])
+            assert ang < ROT_TOL_RAD and dt < T_TOL_M
+            assert ang < 1e-5 and dt < 1e-5, (k, ang, dt)
+        # points: compare the well-constrained ones (a monocular point seen under a tiny parallax has a
+        # near-singular 3x3 block; its update is rounding noise on both sides)
+        good = np.linalg.norm(rX - s["Pgt"], axis=1) < 1.0
+        assert good.mean() > 0.9
+        assert np.abs(gX - rX)[good].max() < 1e-3
+        assert np.median(np.abs(gX - rX)) < 1e-5
+        assert (gbad != rbad).mean() < 1e-3
+        # fixed keyframes are untouched, free ones moved towards the ground truth
+        Tin = s["kf_T"].reshape(-1, 4, 4)
+        assert np.array_equal(gT[:nfixed], Tin[:nfixed])
+        before = np.mean([_pose_delta(Tin[k], s["Tgt"][k].astype(np.float32))[0] for k in range(nfixed, K)])
+        after = np.mean([_pose_delta(gT[k], s["Tgt"][k].astype(np.float32))[0] for k in range(nfixed, K)])
+        assert after < 0.25 * before
+
+
+def test_local_ba_stop_flag_and_sanity_abort(ctx, ork):
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    s = sc.lba_scenario(3, K=6, M=300, n_fixed=2)
+    a = (s["kf_T"], s["kf_fixed"], s["mp_xyz"], s["e_kf"], s["e_mp"], s["e_obs"], s["e_inv_sigma2"], cam)
+    stop = np.ones(1, np.uint8)                     # mbAbortBA already set: nothing happens
+    gT, gX, gbad, git, gst = opt.LocalBundleAdjustment(*a, stop=stop)
+    rT, rX, rbad, rit, rst = ork.local_ba(*a, stop=stop)
+    assert gst == rst == 1 and git.sum() == 0
+    assert np.array_equal(gT.reshape(-1, 16), s["kf_T"]) and np.array_equal(gX, s["mp_xyz"])
+    stop[0] = 0                                     # flag present but clear: identical to no flag
+    gT2, gX2, _, git2, gst2 = opt.LocalBundleAdjustment(*a, stop=stop)
+    gT3, gX3, _, git3, gst3 = opt.LocalBundleAdjustment(*a)
+    assert gst2 == gst3 == 0 and np.array_equal(git2, git3) and np.array_equal(gT2, gT3) and np.array_equal(gX2, gX3)
+    # >= 50 % bad observations: the reference returns without writing anything back
+    bad = sc.lba_scenario(4, K=6, M=300, n_fixed=2, outlier_frac=0.9)
+    b = (bad["kf_T"], bad["kf_fixed"], bad["mp_xyz"], bad["e_kf"], bad["e_mp"], bad["e_obs"], bad["e_inv_sigma2"], cam)
+    gT, gX, gbad, git, gst = opt.LocalBundleAdjustment(*b)
+    rT, rX, rbad, rit, rst = ork.local_ba(*b)
+    assert gst == rst == 2
+    assert np.array_equal(gT.reshape(-1, 16), bad["kf_T"]) and np.array_equal(gX, bad["mp_xyz"])
+
+
+def test_lba_is_deterministic(ctx):
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    s = sc.lba_scenario(5, K=8, M=500, n_fixed=2)
+    a = (s["kf_T"], s["kf_fixed"], s["mp_xyz"], s["e_kf"], s["e_mp"], s["e_obs"], s["e_inv_sigma2"], cam)
+    r1 = opt.LocalBundleAdjustment(*a)
+    r2 = opt.LocalBundleAdjustment(*a)
+    assert np.array_equal(r1[0], r2[0]) and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
