@@ -1,0 +1,117 @@
+// ref_iface.h — SYNTAX-CHECK STAND-INS, not product code and not the reference's headers.
+//
+// Declares just enough of OpenCV's and the reference's public interface (names, member types, signatures as
+// used by the shim) for `g++ -fsyntax-only` to type-check the shim sources in a container that has neither
+// OpenCV nor the reference's dependencies.  Interface facts restated from include/ORBextractor.h:43-109,
+// include/ORBmatcher.h:35-108, include/Optimizer.h:46-119, include/Frame.h, include/KeyFrame.h,
+// include/MapPoint.h, include/Map.h of the reference.
+#pragma once
+#include <cassert>
+#include <cstdint>
+#include <cstring>
+#include <list>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#define CV_8U 0
+#define CV_8UC1 0
+#define CV_32F 5
+
+namespace cv {
+struct Point2f { float x, y; };
+struct Rect { int x, y, w, h; Rect(int a, int b, int c, int d) : x(a), y(b), w(c), h(d) {} };
+struct KeyPoint {
+  Point2f pt; float size, angle, response; int octave, class_id;
+  KeyPoint() {}
+  KeyPoint(float x, float y, float s, float a, float r, int o, int c) : pt{x, y}, size(s), angle(a), response(r), octave(o), class_id(c) {}
+};
+struct Mat {
+  int rows, cols; size_t step; unsigned char* data;
+  Mat() {}
+  Mat(int r, int c, int type);
+  Mat operator()(const Rect&) const;
+  int type() const;
+  bool empty() const;
+  template <typename T> T& at(int r, int c = 0);
+  template <typename T> const T& at(int r, int c = 0) const;
+  template <typename T = unsigned char> T* ptr(int r = 0);
+  template <typename T = unsigned char> const T* ptr(int r = 0) const;
+};
+struct InputArray { bool empty() const; Mat getMat() const; };
+struct OutputArray { void release() const; void create(int, int, int) const; Mat getMat() const; };
+enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
+void copyMakeBorder(const Mat&, Mat&, int, int, int, int, int);
+}  // namespace cv
+
+namespace DBoW2 { typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector; }
+
+namespace ORB_SLAM3 {
+class Map; class KeyFrame; class Frame; class GeometricCamera;
+
+class ORBextractor {
+ public:
+  ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+  ~ORBextractor() {}
+  int operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
+                 cv::OutputArray _descriptors, std::vector<int>& vLappingArea);
+  std::vector<cv::Mat> mvImagePyramid;
+ protected:
+  int nfeatures; double scaleFactor; int nlevels; int iniThFAST; int minThFAST;
+  std::vector<int> mnFeaturesPerLevel, umax;
+  std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+};
+
+class MapPoint {
+ public:
+  cv::Mat GetWorldPos(); void SetWorldPos(const cv::Mat&); cv::Mat GetDescriptor();
+  std::map<KeyFrame*, std::tuple<int, int> > GetObservations(); int Observations();
+  void EraseObservation(KeyFrame*); bool isBad(); void UpdateNormalAndDepth(); Map* GetMap();
+  long unsigned int mnId, mnBALocalForKF;
+  float mTrackProjX, mTrackProjY, mTrackDepth, mTrackProjXR, mTrackViewCos; bool mbTrackInView; int mnTrackScaleLevel;
+  static std::mutex mGlobalMutex;
+};
+
+class Frame {
+ public:
+  void SetPose(cv::Mat Tcw); void ComputeStereoMatches();
+  ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
+  static float fx, fy, cx, cy; float mbf, mb; int N;
+  std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn; std::vector<MapPoint*> mvpMapPoints;
+  std::vector<float> mvuRight, mvDepth; cv::Mat mDescriptors, mDescriptorsRight; std::vector<bool> mvbOutlier;
+  cv::Mat mTcw; std::vector<float> mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
+  static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+};
+
+class KeyFrame {
+ public:
+  cv::Mat GetPose(); cv::Mat GetRotation(); cv::Mat GetTranslation(); void SetPose(const cv::Mat&);
+  std::vector<KeyFrame*> GetVectorCovisibleKeyFrames(); std::vector<MapPoint*> GetMapPointMatches();
+  MapPoint* GetMapPoint(const size_t& idx); void EraseMapPointMatch(MapPoint*); bool isBad(); Map* GetMap();
+  long unsigned int mnId, mnBALocalForKF, mnBAFixedForKF;
+  const float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mb = 0;
+  std::vector<cv::KeyPoint> mvKeysUn; std::vector<float> mvuRight; cv::Mat mDescriptors; DBoW2::FeatureVector mFeatVec;
+  std::vector<float> mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
+  const int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+};
+
+class Map { public: long unsigned int GetInitKFid(); bool IsInertial(); std::mutex mMutexMapUpdate; };
+
+class ORBmatcher {
+ public:
+  ORBmatcher(float nnratio = 0.6, bool checkOri = true);
+  static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+  int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false, const float thFarPoints = 50.0f);
+  int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+  int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo, const bool bCoarse = false);
+ protected:
+  float mfNNratio; bool mbCheckOrientation;
+};
+
+class Optimizer {
+ public:
+  static void LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, int& num_fixedKF);
+  static int PoseOptimization(Frame* pFrame);
+};
+}  // namespace ORB_SLAM3

@@ -44,3 +44,11 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"(^|[^a-z_])(libork|ork_[a-z]+\(|import oracle|from oracle|oracle/ork)", txt):
                     bad.append(os.path.join(dp, f))
     assert not bad, "product sources reference the oracle: %s" % bad
+
+
+def test_shim_type_checks_against_interface_stubs():
+    """The drop-in C++ classes (same signatures as the reference) compile against interface stand-ins."""
+    import subprocess
+    out = subprocess.run(["make", "-C", os.path.join(PKG, "shim"), "check"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "syntax check OK" in out.stdout
