@@ -31,6 +31,13 @@ __device__ __forceinline__ int round_haz(float v) { return (int)roundf(v); }
 
 struct CellRange { int x0, x1, y0, y1; bool empty; };
 
+// frame f of a batch, with its keypoint count resolved
+__device__ __forceinline__ FrameDev load_frame(const FrameDev* frames, int f) {
+  FrameDev F = frames[f];
+  if (F.nDev) F.n = *F.nDev;
+  return F;
+}
+
 // GetFeaturesInArea cell window (src/Frame.cc:779-802)
 __device__ __forceinline__ CellRange cell_range(const FrameDev& F, float x, float y, float r) {
   CellRange c;
@@ -90,7 +97,7 @@ __device__ __forceinline__ int walk_candidates(const FrameDev& F, float x, float
 // K7 grid build: one CTA per frame.  Counting sort by cell, ascending keypoint index in a cell.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) grid_build_kernel(const FrameDev* __restrict__ frames) {
-  const FrameDev F = frames[blockIdx.x];
+  const FrameDev F = load_frame(frames, blockIdx.x);
   __shared__ int s_cnt[ORBX_NCELLS];
   __shared__ int s_warp[9];
   const int tid = threadIdx.x;
@@ -156,6 +163,7 @@ int orbx_upload_frame(DevScope& S, const orbx_frame_desc* f, FrameDev* out) {
     return ORBX_EINVAL;
   }
   out->n = f->n;
+  out->nDev = nullptr;
   out->kps = S.upload(f->kps, f->n);
   out->desc = S.upload(f->desc, (size_t)f->n * 32);
   out->uright = f->uright ? S.upload(f->uright, f->n) : nullptr;
@@ -176,7 +184,7 @@ int orbx_upload_frame(DevScope& S, const orbx_frame_desc* f, FrameDev* out) {
 __global__ void __launch_bounds__(128) features_in_area_kernel(const FrameDev* frames, int nq, const float* x, const float* y,
                                                                const float* r, const int* minL, const int* maxL,
                                                                int* outIdx, int cap, int* outN) {
-  const FrameDev F = frames[0];
+  const FrameDev F = load_frame(frames, 0);
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= nq) return;
   int* dst = outIdx + (size_t)q * cap;
@@ -190,31 +198,13 @@ __global__ void __launch_bounds__(128) features_in_area_kernel(const FrameDev* f
 // K8a  SearchByProjection(Frame, MapPoints): phase A (parallel candidate scoring)
 //   candidate record: idx | dist<<16 | (level & 0xf) << 25
 // ------------------------------------------------------------------------------------
-struct SbpMapArgs {
-  int nq;
-  const float *projX, *projY, *projXR, *viewCos;
-  const int* level;
-  const uint8_t* mpDesc;
-  const uint8_t* flags;
-  float th, nnratio;
-  const float* scaleFactors;
-  // phase A -> B
-  int* candOfs;      // [nq]
-  int* candCnt;      // [nq]
-  uint32_t* cand;    // [candCap]
-  int candCap;
-  int* total;        // running allocation counter
-  int* err;
-  // outputs
-  const uint8_t* kpBlocked;
-  int* bestIdx;
-  int* nmatches;
-};
 
-__global__ void __launch_bounds__(128) sbp_map_score_kernel(const FrameDev* frames, SbpMapArgs A) {
-  const FrameDev F = frames[0];
+__global__ void __launch_bounds__(128) sbp_map_score_kernel(const FrameDev* frames, const SbpMapArgs* args) {
+  const SbpMapArgs A = args[blockIdx.y];
+  const FrameDev F = load_frame(frames, blockIdx.y);
+  const int nq = A.nqDev ? *A.nqDev : A.nq;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (q >= A.nq) return;
+  if (q >= nq) return;
   if (lane == 0) { A.candCnt[q] = 0; A.candOfs[q] = 0; }
   if (!(A.flags[q] & 1)) return;
   const int lvl = A.level[q];
@@ -270,14 +260,16 @@ __global__ void __launch_bounds__(128) sbp_map_score_kernel(const FrameDev* fram
 }
 
 // phase B: one warp per frame replays the queries in order
-__global__ void __launch_bounds__(32) sbp_map_resolve_kernel(const FrameDev* frames, SbpMapArgs A) {
+__global__ void __launch_bounds__(32) sbp_map_resolve_kernel(const FrameDev* frames, const SbpMapArgs* args) {
   extern __shared__ uint8_t s_blocked[];
-  const FrameDev F = frames[0];
+  const SbpMapArgs A = args[blockIdx.x];
+  const FrameDev F = load_frame(frames, blockIdx.x);
+  const int nq = A.nqDev ? *A.nqDev : A.nq;
   const int lane = threadIdx.x;
   for (int i = lane; i < F.n; i += 32) s_blocked[i] = A.kpBlocked ? A.kpBlocked[i] : 0;
   __syncwarp();
   int n = 0;
-  for (int q = 0; q < A.nq; ++q) {
+  for (int q = 0; q < nq; ++q) {
     const int cnt = A.candCnt[q];
     int best = -1;
     if (cnt > 0) {
@@ -325,36 +317,15 @@ __global__ void __launch_bounds__(32) sbp_map_resolve_kernel(const FrameDev* fra
 // ------------------------------------------------------------------------------------
 // K8b  SearchByProjection(Cur, Last)
 // ------------------------------------------------------------------------------------
-struct SbpFrameArgs {
-  int nq;
-  const uint8_t* flags;
-  const float* xw;
-  const int* octave;
-  const float* angle;
-  const uint8_t* mpDesc;
-  float Tc[12];
-  float fx, fy, cx, cy, bf;
-  float th;
-  int mode;          // 0 = +-1 octave, 1 = forward, 2 = backward
-  int checkOri;
-  const float* scaleFactors;
-  int* candOfs;
-  int* candCnt;
-  uint32_t* cand;    // idx | dist<<16
-  int candCap;
-  int* total;
-  int* err;
-  const uint8_t* curBlocked;
-  int* matchIdx;
-  uint8_t* kept;
-  int* curMatch;
-  int* nmatches;
-};
 
-__global__ void __launch_bounds__(128) sbp_frame_score_kernel(const FrameDev* frames, SbpFrameArgs A) {
-  const FrameDev F = frames[0];
+__global__ void __launch_bounds__(128) sbp_frame_score_kernel(const FrameDev* frames, const SbpFrameArgs* args) {
+  SbpFrameArgs A = args[blockIdx.y];
+  const FrameDev F = load_frame(frames, blockIdx.y);
+  const int nq = A.nqDev ? *A.nqDev : A.nq;
+  if (A.TcDev)
+    for (int i = 0; i < 12; ++i) A.Tc[i] = A.TcDev[i];
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (q >= A.nq) return;
+  if (q >= nq) return;
   if (lane == 0) { A.candCnt[q] = 0; A.candOfs[q] = 0; }
   if (!(A.flags[q] & 1)) return;
   const float X = A.xw[3 * q], Y = A.xw[3 * q + 1], Z = A.xw[3 * q + 2];
@@ -441,17 +412,19 @@ __device__ void three_maxima(const int* h, int& i1, int& i2, int& i3) {
   else if ((float)m3 < __fmul_rn(0.1f, (float)m1)) { i3 = -1; }
 }
 
-__global__ void __launch_bounds__(32) sbp_frame_resolve_kernel(const FrameDev* frames, SbpFrameArgs A) {
+__global__ void __launch_bounds__(32) sbp_frame_resolve_kernel(const FrameDev* frames, const SbpFrameArgs* args) {
   extern __shared__ uint8_t s_blocked[];
   __shared__ int s_hist[HISTO_LENGTH];
   __shared__ int s_keep[3];
-  const FrameDev F = frames[0];
+  const SbpFrameArgs A = args[blockIdx.x];
+  const FrameDev F = load_frame(frames, blockIdx.x);
+  const int nq = A.nqDev ? *A.nqDev : A.nq;
   const int lane = threadIdx.x;
   for (int i = lane; i < F.n; i += 32) { s_blocked[i] = A.curBlocked ? A.curBlocked[i] : 0; A.curMatch[i] = -1; }
   if (lane < HISTO_LENGTH) s_hist[lane] = 0;
   __syncwarp();
   int n = 0;
-  for (int q = 0; q < A.nq; ++q) {
+  for (int q = 0; q < nq; ++q) {
     const int cnt = A.candCnt[q];
     int best = -1;
     if (cnt > 0) {
@@ -485,7 +458,7 @@ __global__ void __launch_bounds__(32) sbp_frame_resolve_kernel(const FrameDev* f
     __syncwarp();
     const int i1 = s_keep[0], i2 = s_keep[1], i3 = s_keep[2];
     int removed = 0;
-    for (int q = lane; q < A.nq; q += 32) {
+    for (int q = lane; q < nq; q += 32) {
       const int idx = A.matchIdx[q];
       if (idx < 0) continue;
       const int bin = rot_bin(A.angle[q], F.kps[idx].angle);
@@ -506,24 +479,12 @@ __global__ void __launch_bounds__(32) sbp_frame_resolve_kernel(const FrameDev* f
 // K9  ComputeStereoMatches: warp per left keypoint (row-band Hamming + 11x11 SAD + parabola),
 //     then one CTA per frame for the median SAD rejection.
 // ------------------------------------------------------------------------------------
-struct StereoArgs {
-  int nL, nR;
-  const orbx_keypoint *kpL, *kpR;
-  const uint8_t *descL, *descR;
-  float bf, b;
-  int nlevels;
-  float scale[ORBX_MAX_LEVELS], invScale[ORBX_MAX_LEVELS];
-  const uint8_t* pyrL[ORBX_MAX_LEVELS];
-  const uint8_t* pyrR[ORBX_MAX_LEVELS];
-  int lw[ORBX_MAX_LEVELS], lh[ORBX_MAX_LEVELS], pitchL[ORBX_MAX_LEVELS], pitchR[ORBX_MAX_LEVELS];
-  float* uright;
-  float* depth;
-  int* sad;      // [nL] best SAD of accepted matches, -1 otherwise
-};
 
-__global__ void __launch_bounds__(128) stereo_match_kernel(const __grid_constant__ StereoArgs A) {
+__global__ void __launch_bounds__(128) stereo_match_kernel(const StereoArgs* __restrict__ args) {
+  const StereoArgs& A = args[blockIdx.y];
+  const int nL = A.nLDev ? *A.nLDev : A.nL, nR = A.nRDev ? *A.nRDev : A.nR;
   const int iL = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (iL >= A.nL) return;
+  if (iL >= nL) return;
   if (lane == 0) { A.uright[iL] = -1.0f; A.depth[iL] = -1.0f; A.sad[iL] = -1; }
   const orbx_keypoint kl = A.kpL[iL];
   const int nRows = A.lh[0];
@@ -534,7 +495,7 @@ __global__ void __launch_bounds__(128) stereo_match_kernel(const __grid_constant
   if (maxU < 0) return;
   const uint4* dl = reinterpret_cast<const uint4*>(A.descL + 32 * (size_t)iL);
   unsigned key = 0xffffffffu;   // dist<<16 | iR : first minimum in ascending iR
-  for (int iR = lane; iR < A.nR; iR += 32) {
+  for (int iR = lane; iR < nR; iR += 32) {
     const orbx_keypoint kr = A.kpR[iR];
     const float r = __fmul_rn(2.0f, A.scale[kr.octave]);
     const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));
@@ -612,7 +573,12 @@ __global__ void __launch_bounds__(128) stereo_match_kernel(const __grid_constant
 }
 
 // median of the accepted SADs (element size/2 of the sorted list) -> reject sad >= 1.5*1.4*median
-__global__ void __launch_bounds__(256) stereo_median_kernel(int nL, const int* sad, float* uright, float* depth) {
+__global__ void __launch_bounds__(256) stereo_median_kernel(const StereoArgs* __restrict__ args) {
+  const StereoArgs& A = args[blockIdx.x];
+  const int nL = A.nLDev ? *A.nLDev : A.nL;
+  const int* sad = A.sad;
+  float* uright = A.uright;
+  float* depth = A.depth;
   __shared__ int s_m, s_med;
   if (threadIdx.x == 0) { s_m = 0; s_med = -1; }
   __syncthreads();
@@ -741,6 +707,36 @@ __global__ void __launch_bounds__(256) tri_rot_filter_kernel(const FrameDev* fra
 }
 
 // =====================================================================================
+// batched launchers
+// =====================================================================================
+int orbx_launch_stereo_batch(orbx_ctx* ctx, cudaStream_t st, const StereoArgs* dArgs, int S, int maxL) {
+  stereo_match_kernel<<<dim3(div_up(maxL * 32, 128), S), 128, 0, st>>>(dArgs);
+  ORBX_LAUNCH(ctx);
+  stereo_median_kernel<<<S, 256, 0, st>>>(dArgs);
+  ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+int orbx_launch_sbp_frame_batch(orbx_ctx* ctx, cudaStream_t st, const FrameDev* dF, const SbpFrameArgs* dA, int S, int maxQ,
+                                int maxN) {
+  sbp_frame_score_kernel<<<dim3(div_up(maxQ * 32, 128), S), 128, 0, st>>>(dF, dA);
+  ORBX_LAUNCH(ctx);
+  sbp_frame_resolve_kernel<<<S, 32, align_up((size_t)maxN + 16, 16), st>>>(dF, dA);
+  ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+int orbx_launch_sbp_map_batch(orbx_ctx* ctx, cudaStream_t st, const FrameDev* dF, const SbpMapArgs* dA, int S, int maxQ,
+                              int maxN) {
+  sbp_map_score_kernel<<<dim3(div_up(maxQ * 32, 128), S), 128, 0, st>>>(dF, dA);
+  ORBX_LAUNCH(ctx);
+  sbp_map_resolve_kernel<<<S, 32, align_up((size_t)maxN + 16, 16), st>>>(dF, dA);
+  ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+// =====================================================================================
 // host entry points
 // =====================================================================================
 struct orbx_ext;
@@ -829,11 +825,14 @@ int orbx_search_by_projection_map(orbx_ctx* ctx, const orbx_frame_desc* frame, c
   ORBX_CUDA(cudaMemsetAsync(misc, 0, 4 * sizeof(int), st));
   rc = orbx_launch_grid_build(ctx, st, dF, 1);
   if (rc != ORBX_OK) return rc;
+  A.nqDev = nullptr;
+  SbpMapArgs* dA = S.upload(&A, 1);
+  if (S.failed) return ORBX_ECUDA;
   if (nq > 0) {
-    sbp_map_score_kernel<<<div_up(nq * 32, 128), 128, 0, st>>>(dF, A);
+    sbp_map_score_kernel<<<dim3(div_up(nq * 32, 128), 1), 128, 0, st>>>(dF, dA);
     ORBX_LAUNCH(ctx);
   }
-  sbp_map_resolve_kernel<<<1, 32, align_up((size_t)frame->n + 16, 16), st>>>(dF, A);
+  sbp_map_resolve_kernel<<<1, 32, align_up((size_t)frame->n + 16, 16), st>>>(dF, dA);
   ORBX_LAUNCH(ctx);
   int h[4];
   ORBX_CUDA(cudaMemcpyAsync(h, misc, sizeof h, cudaMemcpyDeviceToHost, st));
@@ -904,11 +903,15 @@ int orbx_search_by_projection_frame(orbx_ctx* ctx, const orbx_frame_desc* cur, c
   ORBX_CUDA(cudaMemsetAsync(misc, 0, 4 * sizeof(int), st));
   rc = orbx_launch_grid_build(ctx, st, dF, 1);
   if (rc != ORBX_OK) return rc;
+  A.nqDev = nullptr;
+  A.TcDev = nullptr;
+  SbpFrameArgs* dA = S.upload(&A, 1);
+  if (S.failed) return ORBX_ECUDA;
   if (nq > 0) {
-    sbp_frame_score_kernel<<<div_up(nq * 32, 128), 128, 0, st>>>(dF, A);
+    sbp_frame_score_kernel<<<dim3(div_up(nq * 32, 128), 1), 128, 0, st>>>(dF, dA);
     ORBX_LAUNCH(ctx);
   }
-  sbp_frame_resolve_kernel<<<1, 32, align_up((size_t)cur->n + 16, 16), st>>>(dF, A);
+  sbp_frame_resolve_kernel<<<1, 32, align_up((size_t)cur->n + 16, 16), st>>>(dF, dA);
   ORBX_LAUNCH(ctx);
   int h[4];
   ORBX_CUDA(cudaMemcpyAsync(h, misc, sizeof h, cudaMemcpyDeviceToHost, st));
@@ -968,10 +971,13 @@ int orbx_stereo_match(orbx_ctx* ctx, orbx_ext* extL, int bL, orbx_ext* extR, int
   A.depth = S.alloc<float>(nL);
   A.sad = S.alloc<int>(nL);
   if (S.failed) return ORBX_ECUDA;
+  A.nLDev = A.nRDev = nullptr;
+  StereoArgs* dA = S.upload(&A, 1);
+  if (S.failed) return ORBX_ECUDA;
   if (nL > 0) {
-    stereo_match_kernel<<<div_up(nL * 32, 128), 128, 0, st>>>(A);
+    stereo_match_kernel<<<dim3(div_up(nL * 32, 128), 1), 128, 0, st>>>(dA);
     ORBX_LAUNCH(ctx);
-    stereo_median_kernel<<<1, 256, 0, st>>>(nL, A.sad, A.uright, A.depth);
+    stereo_median_kernel<<<1, 256, 0, st>>>(dA);
     ORBX_LAUNCH(ctx);
     ORBX_CUDA(cudaMemcpyAsync(uright, A.uright, sizeof(float) * nL, cudaMemcpyDeviceToHost, st));
     ORBX_CUDA(cudaMemcpyAsync(depth, A.depth, sizeof(float) * nL, cudaMemcpyDeviceToHost, st));

@@ -273,7 +273,9 @@ __device__ bool ldlt6_solve(const double* Ain, const double* b, double* x) {
 #define PO_NT 128
 
 struct PoseOptArgs {
-  const int* edgeOfs;     // [P+1]
+  const int* edgeOfs;     // [P+1] contiguous slices ...
+  const int* edgeStart;   // ... or, when non-null, [P] slice starts with
+  const int* edgeCount;   //     [P] slice lengths (batched pipelines with fixed per-problem capacity)
   const float* xw;        // [Etot][3]
   const float* obs;       // [Etot][3]
   const float* invSigma2; // [Etot]
@@ -287,7 +289,8 @@ struct PoseOptArgs {
 
 __global__ void __launch_bounds__(PO_NT) pose_opt_kernel(const PoseOptArgs A) {
   const int prob = blockIdx.x, tid = threadIdx.x;
-  const int e0 = A.edgeOfs[prob], E = A.edgeOfs[prob + 1] - e0;
+  const int e0 = A.edgeStart ? A.edgeStart[prob] : A.edgeOfs[prob];
+  const int E = A.edgeStart ? A.edgeCount[prob] : A.edgeOfs[prob + 1] - e0;
   __shared__ SE3d s_est, s_backup, s_init;
   __shared__ double s_red[(PO_NT / 32) * 28];
   __shared__ double s_H[36], s_b[6], s_x[6];
@@ -878,6 +881,29 @@ __global__ void __launch_bounds__(LBA_NT) lba_kernel(const LbaArgs A) {
   (void)s_scal;
 }
 
+// internal (orbx_track.cu): P problems with fixed-capacity slices
+int orbx_launch_pose_opt_slices(orbx_ctx* ctx, cudaStream_t st, int P, const int* d_start, const int* d_count, const float* d_xw,
+                                const float* d_obs, const float* d_isg, const orbx_camera* cam, float* d_Tcw, uint8_t* d_outlier,
+                                int* d_ninl, int* d_iters, double* d_scratch) {
+  PoseOptArgs A;
+  A.edgeOfs = nullptr;
+  A.edgeStart = d_start;
+  A.edgeCount = d_count;
+  A.xw = d_xw;
+  A.obs = d_obs;
+  A.invSigma2 = d_isg;
+  A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
+  A.Tcw = d_Tcw;
+  A.outlier = d_outlier;
+  A.nInliers = d_ninl;
+  A.iters = d_iters;
+  A.err = d_scratch;
+  pose_opt_kernel<<<P, PO_NT, 0, st>>>(A);
+  ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
 // =====================================================================================
 // host entry points
 // =====================================================================================
@@ -893,6 +919,8 @@ int orbx_pose_optimization_batch_device(orbx_ctx* ctx, int P, const int32_t* d_e
   ORBX_CUDA(cudaSetDevice(ctx->device));
   PoseOptArgs A;
   A.edgeOfs = d_edge_ofs;
+  A.edgeStart = nullptr;
+  A.edgeCount = nullptr;
   A.xw = d_xw;
   A.obs = d_obs;
   A.invSigma2 = d_inv_sigma2;

@@ -1,0 +1,538 @@
+// orbx_track.cu — many-stream tracking replay: the per-frame chain of Tracking::Track for S independent
+// stereo streams, device-resident between stages.
+//
+//   Frame::Frame(stereo)            src/Frame.cc:90-170      -> extractor (2*S images), ComputeStereoMatches
+//   Tracking::TrackWithMotionModel  src/Tracking.cc:2331-2433 -> SearchByProjection(Cur, Last, th), PoseOptimization,
+//                                                                 outlier MapPoints dropped (:2402-2419)
+//   Tracking::TrackLocalMap         src/Tracking.cc:2436-2480 -> SearchLocalPoints (:2848-2967: frustum test, points
+//                                                                 already matched are skipped), SearchByProjection(F,
+//                                                                 local points, th), PoseOptimization
+// The map each stream tracks against is synthesised from the frame itself (no dataset offline): stereo points
+// back-projected at the true pose stand in for the last frame's / local map's MapPoints.  The glue kernels
+// here (back-projection, edge gathering, frustum projection) are the device form of that harness and of
+// Frame::isInFrustum's projection (src/Frame.cc:571-660); the heavy kernels are the ones behind the
+// single-frame C ABI.
+#include <algorithm>
+#include <vector>
+#include "orbx_match.cuh"
+
+struct orbx_ext;
+int orbx_ext_pyramid_view(orbx_ext* e, int b, int* nlevels, const uint8_t** ptr, int* w, int* h, int* pitch, float* scale,
+                          float* invScale, cudaStream_t* st);
+int orbx_launch_pose_opt_slices(orbx_ctx* ctx, cudaStream_t st, int P, const int* d_start, const int* d_count, const float* d_xw,
+                                const float* d_obs, const float* d_isg, const orbx_camera* cam, float* d_Tcw, uint8_t* d_outlier,
+                                int* d_ninl, int* d_iters, double* d_scratch);
+
+struct TrackDev {
+  int S, cap;
+  float fx, fy, cx, cy, bf;
+  float invSigma2[ORBX_MAX_LEVELS];
+  const orbx_keypoint* kps;   // [2S][cap]
+  const uint8_t* desc;        // [2S][cap][32]
+  const int* n;               // [2S]
+  float *uright, *depth;      // [S][cap]
+  // "map points" = the frame's own stereo points
+  uint8_t* mpFlags;           // [S][cap] local map: bit0 has MapPoint, bit1 Observations()>0
+  uint8_t* lastFlags;         // [S][cap] subset of the map the *last frame* had tracked (3 of every 5 points)
+  float* xw;                  // [S][cap][3]
+  int* octave;                // [S][cap]
+  float* angle;               // [S][cap]
+  // search 1 outputs
+  int *matchIdx, *curMatch, *nm1;
+  uint8_t* kept;
+  // pose-opt edges (slice s = [s*cap, s*cap + count[s]))
+  float *exw, *eobs, *eisg;
+  int *ekp, *ecount, *estart, *kpEdge;
+  uint8_t* eoutlier;
+  int *ninl, *iters;
+  // local-map search
+  uint8_t *blocked, *mpTaken, *mapFlags;
+  float *projX, *projY, *projXR, *viewCos;
+  int *level, *bestIdx, *nm2, *kpMp;
+  float *Ttrue, *Tprior, *T1, *T2;
+  int* stats;
+};
+
+// K-glue 1: back-project stereo keypoints at the true pose: Xw = Rcw^T (Xc - tcw)
+__global__ void __launch_bounds__(128) backproject_kernel(const TrackDev D) {
+  const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.cap) return;
+  const size_t o = (size_t)s * D.cap + i;
+  const int n = D.n[2 * s];
+  uint8_t fl = 0, lfl = 0;
+  if (i < n) {
+    const orbx_keypoint kp = D.kps[(size_t)(2 * s) * D.cap + i];
+    const float z = D.depth[o];
+    D.octave[o] = kp.octave;
+    D.angle[o] = kp.angle;
+    if (z > 0) {
+      const float* T = D.Ttrue + 16 * s;
+      const float xc = (kp.x - D.cx) * z / D.fx, yc = (kp.y - D.cy) * z / D.fy;
+      const float dx = xc - T[3], dy = yc - T[7], dz = z - T[11];
+      D.xw[3 * o] = T[0] * dx + T[4] * dy + T[8] * dz;
+      D.xw[3 * o + 1] = T[1] * dx + T[5] * dy + T[9] * dz;
+      D.xw[3 * o + 2] = T[2] * dx + T[6] * dy + T[10] * dz;
+      fl = 3;
+      // the last frame had tracked ~60 % of the local map; the rest is only reachable through TrackLocalMap
+      lfl = (((unsigned)i * 2654435761u) >> 16) % 5u < 3u ? 3 : 0;
+    }
+  }
+  D.mpFlags[o] = fl;
+  D.lastFlags[o] = lfl;
+}
+
+// K-glue 2: PoseOptimization's edge list: keypoints i (ascending) that hold a MapPoint (src/Optimizer.cc:961-1130)
+// mode 0: MapPoint of keypoint i = curMatch[i]; mode 1: kpMp[i]
+__global__ void __launch_bounds__(256) gather_edges_kernel(const TrackDev D, int mode) {
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const int n = D.n[2 * s];
+  const size_t base = (size_t)s * D.cap;
+  const int* src = (mode == 0 ? D.curMatch : D.kpMp) + base;
+  __shared__ int s_warp[9];
+  __shared__ int s_run;
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 256) {
+    const int i = i0 + tid;
+    const int q = i < n ? src[i] : -1;
+    const int has = q >= 0;
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    const int lane = tid & 31, wid = tid >> 5;
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    int before = s_run;
+    for (int w = 0; w < wid; ++w) before += s_warp[w];
+    const int slot = before + __popc(m & ((1u << lane) - 1));
+    if (i < n) D.kpEdge[base + i] = has ? slot : -1;
+    if (has) {
+      const orbx_keypoint kp = D.kps[(size_t)(2 * s) * D.cap + i];
+      const size_t e = base + slot;
+      D.exw[3 * e] = D.xw[3 * (base + q)];
+      D.exw[3 * e + 1] = D.xw[3 * (base + q) + 1];
+      D.exw[3 * e + 2] = D.xw[3 * (base + q) + 2];
+      D.eobs[3 * e] = kp.x;
+      D.eobs[3 * e + 1] = kp.y;
+      D.eobs[3 * e + 2] = D.uright[base + i];
+      D.eisg[e] = D.invSigma2[kp.octave];
+      D.ekp[e] = i;
+    }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; s_run += t; }
+    __syncthreads();
+  }
+  if (tid == 0) { D.ecount[s] = s_run; D.estart[s] = s * D.cap; }
+}
+
+// K-glue 3: after the first PoseOptimization: drop outlier MapPoints (src/Tracking.cc:2402-2419), mark the
+// keypoints and MapPoints that stay matched (SearchLocalPoints skips them, :2864-2869)
+__global__ void __launch_bounds__(128) after_pose1_kernel(const TrackDev D) {
+  const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.cap) return;
+  const size_t o = (size_t)s * D.cap + i;
+  if (i >= D.n[2 * s]) { D.blocked[o] = 0; return; }
+  const int q = D.curMatch[o];
+  uint8_t blk = 0;
+  if (q >= 0) {
+    const int e = D.kpEdge[o];
+    if (D.eoutlier[(size_t)s * D.cap + e]) D.curMatch[o] = -1;
+    else { blk = 1; D.mpTaken[(size_t)s * D.cap + q] = 1; }
+  }
+  D.blocked[o] = blk;
+}
+
+// K-glue 4: Frame::isInFrustum's projection (src/Frame.cc:581-657) with the pose of PoseOptimization #1
+__global__ void __launch_bounds__(128) project_map_kernel(const TrackDev D, float minX, float minY, float maxX, float maxY) {
+  const int s = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= D.cap) return;
+  const size_t o = (size_t)s * D.cap + q;
+  uint8_t fl = 0;
+  if (q < D.n[2 * s] && (D.mpFlags[o] & 1) && !D.mpTaken[o]) {
+    const float* T = D.T1 + 16 * s;
+    const float X = D.xw[3 * o], Y = D.xw[3 * o + 1], Z = D.xw[3 * o + 2];
+    const float xc = T[0] * X + T[1] * Y + T[2] * Z + T[3];
+    const float yc = T[4] * X + T[5] * Y + T[6] * Z + T[7];
+    const float zc = T[8] * X + T[9] * Y + T[10] * Z + T[11];
+    if (zc > 0.0f) {
+      const float invz = 1.0f / zc;
+      const float u = D.fx * xc / zc + D.cx, v = D.fy * yc / zc + D.cy;
+      if (u >= minX && u <= maxX && v >= minY && v <= maxY) {
+        D.projX[o] = u;
+        D.projY[o] = v;
+        D.projXR[o] = u - D.bf * invz;
+        D.level[o] = D.octave[o];      // PredictScale: the point is seen at its own distance
+        D.viewCos[o] = 1.0f;
+        fl = 3;
+      }
+    }
+  }
+  D.mapFlags[o] = fl;
+}
+
+// K-glue 5: MapPoint of each keypoint after the local-map search, then per-stream stats
+__global__ void __launch_bounds__(256) merge_matches_kernel(const TrackDev D) {
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const int n = D.n[2 * s];
+  const size_t base = (size_t)s * D.cap;
+  for (int i = tid; i < n; i += 256) D.kpMp[base + i] = D.curMatch[base + i];
+  __syncthreads();
+  // replay  F.mvpMapPoints[bestIdx[q]] = pMP_q.  Every MapPoint of this harness has Observations() > 0, so a
+  // keypoint is claimed by at most one query and the scatter order is immaterial.
+  for (int q = tid; q < n; q += 256) {
+    const int b = D.bestIdx[base + q];
+    if (b >= 0) D.kpMp[base + b] = q;
+  }
+}
+
+__global__ void __launch_bounds__(256) stats_kernel(const TrackDev D) {
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const int n = D.n[2 * s];
+  const size_t base = (size_t)s * D.cap;
+  __shared__ int s_st;
+  if (tid == 0) s_st = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = tid; i < n; i += 256) c += D.uright[base + i] >= 0;
+  if (c) atomicAdd(&s_st, c);
+  __syncthreads();
+  if (tid == 0) {
+    int* st = D.stats + ORBX_TRACK_STATS * s;
+    st[0] = n;
+    st[1] = D.n[2 * s + 1];
+    st[2] = s_st;
+    st[3] = D.nm1[s];
+    st[4] = D.ninl[s];
+    st[5] = D.nm2[s];
+    st[6] = D.ninl[D.S + s];
+    int it = 0;
+    for (int k = 0; k < 4; ++k) it += D.iters[4 * s + k] + D.iters[4 * D.S + 4 * s + k];
+    st[7] = it;
+  }
+}
+
+struct orbx_tracker {
+  orbx_ctx* ctx = nullptr;
+  orbx_ext* ext = nullptr;
+  cudaStream_t st = nullptr;
+  int S = 0, cap = 0, nlevels = 0;
+  orbx_camera cam{};
+  float thFrame = 7.f, thMap = 1.f, nnMap = 0.8f;
+  TrackDev D{};
+  std::vector<void*> allocs;
+  orbx_keypoint* d_kps = nullptr;
+  uint8_t* d_desc = nullptr;
+  int *d_n = nullptr, *d_mono = nullptr;
+  FrameDev* d_frames = nullptr;
+  StereoArgs* d_stereo = nullptr;
+  SbpFrameArgs* d_sbpf = nullptr;
+  SbpMapArgs* d_sbpm = nullptr;
+  float* d_scale = nullptr;
+  double* d_scratch = nullptr;
+  int* d_misc = nullptr;      // per-frame candidate totals / error flags
+  uint8_t* d_imgs = nullptr;  // staging for the host-pointer entry point
+  uint8_t* h_imgs = nullptr;
+  float* h_pose = nullptr;
+  int* h_stats = nullptr;
+  int argW = -1, argH = -1, argStride = -1;
+  const uint8_t* argImgs = nullptr;
+  bool profiling = false, profiled = false;
+  cudaEvent_t ev[ORBX_TRACK_STAGES + 1] = {};
+};
+
+template <typename T>
+static T* talloc(orbx_tracker* t, size_t count) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+  cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T));
+  t->allocs.push_back(p);
+  return (T*)p;
+}
+
+extern "C" {
+
+void orbx_tracker_destroy(orbx_tracker* t) {
+  if (!t) return;
+  cudaSetDevice(t->ctx->device);
+  cudaStreamSynchronize(t->st);
+  for (void* p : t->allocs) cudaFree(p);
+  if (t->h_imgs) cudaFreeHost(t->h_imgs);
+  if (t->h_pose) cudaFreeHost(t->h_pose);
+  if (t->h_stats) cudaFreeHost(t->h_stats);
+  for (int i = 0; i <= ORBX_TRACK_STAGES; ++i)
+    if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+  delete t;
+}
+
+orbx_tracker* orbx_tracker_create(orbx_ctx* ctx, orbx_ext* ext, int S, const orbx_camera* cam, float th_frame, float th_map,
+                                  float nnratio_map) {
+  if (!ctx || !ext || S < 1 || !cam || !(cam->b > 0)) {
+    orbx_set_error("orbx_tracker_create: invalid argument");
+    return nullptr;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+  orbx_tracker* t = new orbx_tracker();
+  t->ctx = ctx;
+  t->ext = ext;
+  t->st = (cudaStream_t)orbx_extractor_stream(ext);
+  t->S = S;
+  t->cap = orbx_extractor_max_keypoints(ext);
+  t->nlevels = orbx_extractor_levels(ext);
+  t->cam = *cam;
+  t->thFrame = th_frame;
+  t->thMap = th_map;
+  t->nnMap = nnratio_map;
+  const size_t SC = (size_t)S * t->cap;
+  TrackDev& D = t->D;
+  D.S = S;
+  D.cap = t->cap;
+  D.fx = cam->fx; D.fy = cam->fy; D.cx = cam->cx; D.cy = cam->cy; D.bf = cam->bf;
+  float sc[ORBX_MAX_LEVELS], isg[ORBX_MAX_LEVELS];
+  orbx_extractor_scale_tables(ext, sc, nullptr, nullptr, isg);
+  for (int l = 0; l < t->nlevels; ++l) D.invSigma2[l] = isg[l];
+  t->d_kps = talloc<orbx_keypoint>(t, 2 * SC);
+  t->d_desc = talloc<uint8_t>(t, 2 * SC * 32);
+  t->d_n = talloc<int>(t, 2 * S);
+  t->d_mono = talloc<int>(t, 2 * S);
+  D.kps = t->d_kps; D.desc = t->d_desc; D.n = t->d_n;
+  D.uright = talloc<float>(t, SC); D.depth = talloc<float>(t, SC);
+  D.mpFlags = talloc<uint8_t>(t, SC); D.lastFlags = talloc<uint8_t>(t, SC); D.xw = talloc<float>(t, 3 * SC);
+  D.octave = talloc<int>(t, SC); D.angle = talloc<float>(t, SC);
+  D.matchIdx = talloc<int>(t, SC); D.curMatch = talloc<int>(t, SC); D.nm1 = talloc<int>(t, S);
+  D.kept = talloc<uint8_t>(t, SC);
+  D.exw = talloc<float>(t, 3 * SC); D.eobs = talloc<float>(t, 3 * SC); D.eisg = talloc<float>(t, SC);
+  D.ekp = talloc<int>(t, SC); D.ecount = talloc<int>(t, S); D.estart = talloc<int>(t, S); D.kpEdge = talloc<int>(t, SC);
+  D.eoutlier = talloc<uint8_t>(t, SC);
+  D.ninl = talloc<int>(t, 2 * S); D.iters = talloc<int>(t, 8 * S);
+  D.blocked = talloc<uint8_t>(t, SC); D.mpTaken = talloc<uint8_t>(t, SC); D.mapFlags = talloc<uint8_t>(t, SC);
+  D.projX = talloc<float>(t, SC); D.projY = talloc<float>(t, SC); D.projXR = talloc<float>(t, SC); D.viewCos = talloc<float>(t, SC);
+  D.level = talloc<int>(t, SC); D.bestIdx = talloc<int>(t, SC); D.nm2 = talloc<int>(t, S); D.kpMp = talloc<int>(t, SC);
+  D.Ttrue = talloc<float>(t, 16 * S); D.Tprior = talloc<float>(t, 16 * S); D.T1 = talloc<float>(t, 16 * S); D.T2 = talloc<float>(t, 16 * S);
+  D.stats = talloc<int>(t, ORBX_TRACK_STATS * S);
+  t->d_frames = talloc<FrameDev>(t, S);
+  t->d_stereo = talloc<StereoArgs>(t, S);
+  t->d_sbpf = talloc<SbpFrameArgs>(t, S);
+  t->d_sbpm = talloc<SbpMapArgs>(t, S);
+  t->d_scale = talloc<float>(t, ORBX_MAX_LEVELS);
+  t->d_scratch = talloc<double>(t, 3 * SC);
+  t->d_misc = talloc<int>(t, 8 * S);
+  int* cellStart = talloc<int>(t, (size_t)S * (ORBX_NCELLS + 1));
+  int* cellIdx = talloc<int>(t, SC);
+  const int candCap = t->cap * 96;
+  uint32_t* cand = talloc<uint32_t>(t, (size_t)S * candCap);
+  int* candOfs = talloc<int>(t, SC);
+  int* candCnt = talloc<int>(t, SC);
+  if (!cand || !candCnt || !D.stats || !t->d_scratch) {
+    orbx_set_error("orbx_tracker_create: device allocation failed");
+    orbx_tracker_destroy(t);
+    return nullptr;
+  }
+  cudaMemcpy(t->d_scale, sc, sizeof(float) * t->nlevels, cudaMemcpyHostToDevice);
+  // static parts of the per-frame argument blocks
+  std::vector<FrameDev> F(S);
+  std::vector<SbpFrameArgs> AF(S);
+  std::vector<SbpMapArgs> AM(S);
+  for (int s = 0; s < S; ++s) {
+    const size_t o = (size_t)s * t->cap;
+    F[s].n = 0;
+    F[s].nDev = t->d_n + 2 * s;
+    F[s].kps = t->d_kps + (size_t)(2 * s) * t->cap;
+    F[s].desc = t->d_desc + (size_t)(2 * s) * t->cap * 32;
+    F[s].uright = D.uright + o;
+    F[s].cellStart = cellStart + (size_t)s * (ORBX_NCELLS + 1);
+    F[s].cellIdx = cellIdx + o;
+    F[s].minX = F[s].minY = 0; F[s].maxX = F[s].maxY = 1; F[s].wInv = F[s].hInv = 1;   // set per step (image size)
+    SbpFrameArgs& a = AF[s];
+    a.nq = 0; a.nqDev = t->d_n + 2 * s; a.TcDev = D.Tprior + 16 * s;
+    a.flags = D.lastFlags + o; a.xw = D.xw + 3 * o; a.octave = D.octave + o; a.angle = D.angle + o;
+    a.mpDesc = F[s].desc;
+    a.fx = cam->fx; a.fy = cam->fy; a.cx = cam->cx; a.cy = cam->cy; a.bf = cam->bf;
+    a.th = th_frame; a.mode = 0; a.checkOri = 1; a.scaleFactors = t->d_scale;
+    a.candOfs = candOfs + o; a.candCnt = candCnt + o; a.cand = cand + (size_t)s * candCap; a.candCap = candCap;
+    a.total = t->d_misc + 8 * s; a.err = t->d_misc + 8 * s + 1;
+    a.curBlocked = nullptr; a.matchIdx = D.matchIdx + o; a.kept = D.kept + o; a.curMatch = D.curMatch + o; a.nmatches = D.nm1 + s;
+    SbpMapArgs& m = AM[s];
+    m.nq = 0; m.nqDev = t->d_n + 2 * s;
+    m.projX = D.projX + o; m.projY = D.projY + o; m.projXR = D.projXR + o; m.viewCos = D.viewCos + o; m.level = D.level + o;
+    m.mpDesc = F[s].desc; m.flags = D.mapFlags + o; m.th = th_map; m.nnratio = nnratio_map; m.scaleFactors = t->d_scale;
+    m.candOfs = candOfs + o; m.candCnt = candCnt + o; m.cand = cand + (size_t)s * candCap; m.candCap = candCap;
+    m.total = t->d_misc + 8 * s + 2; m.err = t->d_misc + 8 * s + 3;
+    m.kpBlocked = D.blocked + o; m.bestIdx = D.bestIdx + o; m.nmatches = D.nm2 + s;
+  }
+  cudaMemcpy(t->d_frames, F.data(), sizeof(FrameDev) * S, cudaMemcpyHostToDevice);
+  cudaMemcpy(t->d_sbpf, AF.data(), sizeof(SbpFrameArgs) * S, cudaMemcpyHostToDevice);
+  cudaMemcpy(t->d_sbpm, AM.data(), sizeof(SbpMapArgs) * S, cudaMemcpyHostToDevice);
+  if (cudaGetLastError() != cudaSuccess) {
+    orbx_set_error("orbx_tracker_create: setup copies failed");
+    orbx_tracker_destroy(t);
+    return nullptr;
+  }
+  return t;
+}
+
+// image-size dependent argument blocks (stereo pyramids, grid bounds): rebuilt when (w,h) changes
+static int tracker_bind_geometry(orbx_tracker* t, int w, int h) {
+  const int S = t->S;
+  std::vector<StereoArgs> A(S);
+  std::vector<FrameDev> F(S);
+  ORBX_CUDA(cudaMemcpy(F.data(), t->d_frames, sizeof(FrameDev) * S, cudaMemcpyDeviceToHost));
+  for (int s = 0; s < S; ++s) {
+    StereoArgs& a = A[s];
+    int nl = 0, nl2 = 0, w2[ORBX_MAX_LEVELS], h2[ORBX_MAX_LEVELS];
+    float sc2[ORBX_MAX_LEVELS], isc2[ORBX_MAX_LEVELS];
+    cudaStream_t st1, st2;
+    int rc = orbx_ext_pyramid_view(t->ext, 2 * s, &nl, a.pyrL, a.lw, a.lh, a.pitchL, a.scale, a.invScale, &st1);
+    if (rc != ORBX_OK) return rc;
+    rc = orbx_ext_pyramid_view(t->ext, 2 * s + 1, &nl2, a.pyrR, w2, h2, a.pitchR, sc2, isc2, &st2);
+    if (rc != ORBX_OK) return rc;
+    a.nlevels = nl;
+    a.nL = a.nR = 0;
+    a.nLDev = t->d_n + 2 * s;
+    a.nRDev = t->d_n + 2 * s + 1;
+    a.kpL = t->d_kps + (size_t)(2 * s) * t->cap;
+    a.kpR = t->d_kps + (size_t)(2 * s + 1) * t->cap;
+    a.descL = t->d_desc + (size_t)(2 * s) * t->cap * 32;
+    a.descR = t->d_desc + (size_t)(2 * s + 1) * t->cap * 32;
+    a.bf = t->cam.bf;
+    a.b = t->cam.b;
+    a.uright = t->D.uright + (size_t)s * t->cap;
+    a.depth = t->D.depth + (size_t)s * t->cap;
+    a.sad = t->D.kpEdge + (size_t)s * t->cap;   // scratch reuse: kpEdge is rewritten later in the step
+    F[s].minX = 0.f; F[s].minY = 0.f; F[s].maxX = (float)w; F[s].maxY = (float)h;   // rectified stereo: image bounds (src/Frame.cc:147-152)
+    F[s].wInv = (float)ORBX_GRID_COLS / (F[s].maxX - F[s].minX);
+    F[s].hInv = (float)ORBX_GRID_ROWS / (F[s].maxY - F[s].minY);
+  }
+  ORBX_CUDA(cudaMemcpy(t->d_stereo, A.data(), sizeof(StereoArgs) * S, cudaMemcpyHostToDevice));
+  ORBX_CUDA(cudaMemcpy(t->d_frames, F.data(), sizeof(FrameDev) * S, cudaMemcpyHostToDevice));
+  t->argW = w;
+  t->argH = h;
+  return ORBX_OK;
+}
+
+int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int h, int stride, const float* d_Tcw_true,
+                             const float* d_Tcw_prior, float* d_Tcw_out, int32_t* d_stats) {
+  if (!t || !d_imgs || !d_Tcw_true || !d_Tcw_prior || !d_Tcw_out) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  cudaStream_t st = t->st;
+  const int S = t->S, cap = t->cap;
+  TrackDev& D = t->D;
+  cudaEvent_t* ev = t->profiling ? t->ev : nullptr;
+#define TRK_EV(i) do { if (ev) ORBX_CUDA(cudaEventRecord(ev[i], st)); } while (0)
+  TRK_EV(0);
+  // 1. Frame::Frame(stereo): ORB extraction of the 2*S images (src/Frame.cc:111-114)
+  int rc = orbx_extract_batch_device(t->ext, 2 * S, d_imgs, w, h, stride, 0, 0, t->d_kps, t->d_desc, cap, t->d_n, t->d_mono);
+  if (rc != ORBX_OK) return rc;
+  if (w != t->argW || h != t->argH || stride != t->argStride || d_imgs != t->argImgs) {   // level 0 aliases the input
+    rc = tracker_bind_geometry(t, w, h);
+    if (rc != ORBX_OK) return rc;
+    t->argStride = stride;
+    t->argImgs = d_imgs;
+  }
+  TRK_EV(1);
+  ORBX_CUDA(cudaMemcpyAsync(D.Ttrue, d_Tcw_true, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, st));
+  ORBX_CUDA(cudaMemcpyAsync(D.Tprior, d_Tcw_prior, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, st));
+  ORBX_CUDA(cudaMemcpyAsync(D.T1, d_Tcw_prior, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, st));
+  ORBX_CUDA(cudaMemsetAsync(t->d_misc, 0, sizeof(int) * 8 * S, st));
+  ORBX_CUDA(cudaMemsetAsync(D.mpTaken, 0, (size_t)S * cap, st));
+  // 2. ComputeStereoMatches (src/Frame.cc:132)
+  rc = orbx_launch_stereo_batch(t->ctx, st, t->d_stereo, S, cap);
+  if (rc != ORBX_OK) return rc;
+  TRK_EV(2);
+  // 3. synthetic map + AssignFeaturesToGrid + SearchByProjection(Cur, Last, th) (src/Tracking.cc:2370)
+  const dim3 gk(div_up(cap, 128), S);
+  backproject_kernel<<<gk, 128, 0, st>>>(D);
+  ORBX_LAUNCH(t->ctx);
+  rc = orbx_launch_grid_build(t->ctx, st, t->d_frames, S);
+  if (rc != ORBX_OK) return rc;
+  rc = orbx_launch_sbp_frame_batch(t->ctx, st, t->d_frames, t->d_sbpf, S, cap, cap);
+  if (rc != ORBX_OK) return rc;
+  TRK_EV(3);
+  // 4. PoseOptimization (src/Tracking.cc:2395)
+  gather_edges_kernel<<<S, 256, 0, st>>>(D, 0);
+  ORBX_LAUNCH(t->ctx);
+  rc = orbx_launch_pose_opt_slices(t->ctx, st, S, D.estart, D.ecount, D.exw, D.eobs, D.eisg, &t->cam, D.T1, D.eoutlier, D.ninl,
+                                   D.iters, t->d_scratch);
+  if (rc != ORBX_OK) return rc;
+  TRK_EV(4);
+  // 5. TrackLocalMap: SearchLocalPoints + SearchByProjection(F, local points, th) (src/Tracking.cc:2449,:2964)
+  after_pose1_kernel<<<gk, 128, 0, st>>>(D);
+  ORBX_LAUNCH(t->ctx);
+  project_map_kernel<<<gk, 128, 0, st>>>(D, 0.f, 0.f, (float)w, (float)h);
+  ORBX_LAUNCH(t->ctx);
+  rc = orbx_launch_sbp_map_batch(t->ctx, st, t->d_frames, t->d_sbpm, S, cap, cap);
+  if (rc != ORBX_OK) return rc;
+  TRK_EV(5);
+  // 6. PoseOptimization (src/Tracking.cc:2468), starting from the pose of step 4
+  merge_matches_kernel<<<S, 256, 0, st>>>(D);
+  ORBX_LAUNCH(t->ctx);
+  gather_edges_kernel<<<S, 256, 0, st>>>(D, 1);
+  ORBX_LAUNCH(t->ctx);
+  ORBX_CUDA(cudaMemcpyAsync(D.T2, D.T1, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, st));
+  // ninl/iters of the second optimisation land in the odd slots
+  rc = orbx_launch_pose_opt_slices(t->ctx, st, S, D.estart, D.ecount, D.exw, D.eobs, D.eisg, &t->cam, D.T2, D.eoutlier,
+                                   D.ninl + S, D.iters + 4 * S, t->d_scratch);
+  if (rc != ORBX_OK) return rc;
+  TRK_EV(6);
+  ORBX_CUDA(cudaMemcpyAsync(d_Tcw_out, D.T2, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, st));
+  if (d_stats) {
+    stats_kernel<<<S, 256, 0, st>>>(D);
+    ORBX_LAUNCH(t->ctx);
+    ORBX_CUDA(cudaMemcpyAsync(d_stats, D.stats, sizeof(int) * ORBX_TRACK_STATS * S, cudaMemcpyDeviceToDevice, st));
+  }
+  t->profiled = t->profiling;
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+int orbx_tracker_step(orbx_tracker* t, const uint8_t* const* imgs, int w, int h, int stride, const float* Tcw_true,
+                      const float* Tcw_prior, float* Tcw_out, int32_t* stats) {
+  if (!t || !imgs || !Tcw_true || !Tcw_prior || !Tcw_out || w <= 0 || h <= 0 || stride < w) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  const int S = t->S;
+  const size_t img = (size_t)w * h;
+  if (!t->h_imgs) {
+    ORBX_CUDA(cudaMallocHost(&t->h_imgs, 2 * S * img));
+    ORBX_CUDA(cudaMallocHost(&t->h_pose, sizeof(float) * 16 * S * 3));
+    ORBX_CUDA(cudaMallocHost(&t->h_stats, sizeof(int) * ORBX_TRACK_STATS * S));
+    t->d_imgs = talloc<uint8_t>(t, 2 * S * img);
+    if (!t->d_imgs) return ORBX_ECUDA;
+  }
+  for (int b = 0; b < 2 * S; ++b)
+    for (int y = 0; y < h; ++y) memcpy(t->h_imgs + b * img + (size_t)y * w, imgs[b] + (size_t)y * stride, w);
+  memcpy(t->h_pose, Tcw_true, sizeof(float) * 16 * S);
+  memcpy(t->h_pose + 16 * S, Tcw_prior, sizeof(float) * 16 * S);
+  cudaStream_t st = t->st;
+  ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, t->h_imgs, 2 * S * img, cudaMemcpyHostToDevice, st));
+  // poses ride in T2 / a scratch region of exw (both overwritten later in the step, after they were consumed)
+  float* d_true = t->D.T2;
+  float* d_prior = reinterpret_cast<float*>(t->D.eobs);
+  ORBX_CUDA(cudaMemcpyAsync(d_true, t->h_pose, sizeof(float) * 16 * S, cudaMemcpyHostToDevice, st));
+  ORBX_CUDA(cudaMemcpyAsync(d_prior, t->h_pose + 16 * S, sizeof(float) * 16 * S, cudaMemcpyHostToDevice, st));
+  float* d_out = t->D.Tprior;   // D.Tprior is consumed before the final copy
+  int rc = orbx_tracker_step_device(t, t->d_imgs, w, h, w, d_true, d_prior, d_out, t->D.stats);
+  if (rc != ORBX_OK) return rc;
+  ORBX_CUDA(cudaMemcpyAsync(t->h_pose + 32 * S, d_out, sizeof(float) * 16 * S, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaMemcpyAsync(t->h_stats, t->D.stats, sizeof(int) * ORBX_TRACK_STATS * S, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(cudaStreamSynchronize(st));
+  memcpy(Tcw_out, t->h_pose + 32 * S, sizeof(float) * 16 * S);
+  if (stats) memcpy(stats, t->h_stats, sizeof(int) * ORBX_TRACK_STATS * S);
+  return ORBX_OK;
+}
+
+int orbx_tracker_set_profiling(orbx_tracker* t, int enable) {
+  if (!t) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  if (enable && !t->ev[0])
+    for (int i = 0; i <= ORBX_TRACK_STAGES; ++i) ORBX_CUDA(cudaEventCreate(&t->ev[i]));
+  t->profiling = enable != 0;
+  t->profiled = false;
+  return ORBX_OK;
+}
+
+int orbx_tracker_stage_ms(orbx_tracker* t, float* ms) {
+  if (!t || !ms || !t->profiled) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  ORBX_CUDA(cudaEventSynchronize(t->ev[ORBX_TRACK_STAGES]));
+  for (int i = 0; i < ORBX_TRACK_STAGES; ++i) ORBX_CUDA(cudaEventElapsedTime(&ms[i], t->ev[i], t->ev[i + 1]));
+  return ORBX_OK;
+}
+
+}  // extern "C"

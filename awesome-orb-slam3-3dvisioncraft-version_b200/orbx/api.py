@@ -82,6 +82,13 @@ def load_library():
     L.orbx_pose_optimization.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_pose_optimization_batch_device.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_local_ba.argtypes = [vp, i, vp, vp, i, vp, i, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
+    L.orbx_tracker_create.restype = vp
+    L.orbx_tracker_create.argtypes = [vp, vp, i, vp, f, f, f]
+    L.orbx_tracker_destroy.argtypes = [vp]
+    L.orbx_tracker_step_device.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
+    L.orbx_tracker_step.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
+    L.orbx_tracker_set_profiling.argtypes = [vp, i]
+    L.orbx_tracker_stage_ms.argtypes = [vp, vp]
     L.orbx_pyramid_level.argtypes = [vp, i, i, vp, i, vp, vp]
     L.orbx_debug_candidates.argtypes = [vp, i, i, vp, vp, i, vp]
     _LIB = L
@@ -375,3 +382,53 @@ class Optimizer:
                                           _p(iters), C.byref(status))
         _check(rc, "orbx_local_ba")
         return T.reshape(-1, 4, 4), X, bad[:E].copy(), iters, status.value
+
+
+class Tracker:
+    """Many-stream tracking replay (orbx_tracker): S stereo streams advance one frame per step()."""
+
+    STAGES = ("extract", "stereo_match", "search_last_frame", "pose_opt_1", "search_local_map", "pose_opt_2")
+    STATS = ("nL", "nR", "nStereo", "matches_frame", "inliers_1", "matches_map", "inliers_2", "lm_iters")
+
+    def __init__(self, ctx, ext, S, cam, th_frame=7.0, th_map=1.0, nnratio_map=0.8):
+        self.ctx, self.ext, self.S, self.cam = ctx, ext, S, cam
+        self.h = load_library().orbx_tracker_create(ctx.h, ext.h, S, C.byref(cam), th_frame, th_map, nnratio_map)
+        if not self.h:
+            raise OrbxError("orbx_tracker_create: " + load_library().orbx_last_error().decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "h", None):
+            load_library().orbx_tracker_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, images, Tcw_true, Tcw_prior):
+        """images: [L0, R0, L1, R1, ...] equally sized uint8 arrays (host) -> (Tcw_out[S,4,4], stats[S,8])"""
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        assert len(imgs) == 2 * self.S
+        h, w = imgs[0].shape
+        ptrs = (C.c_void_p * len(imgs))(*[im.ctypes.data for im in imgs])
+        Tt = np.ascontiguousarray(Tcw_true, np.float32).reshape(self.S, 16)
+        Tp = np.ascontiguousarray(Tcw_prior, np.float32).reshape(self.S, 16)
+        out = np.empty((self.S, 16), np.float32)
+        stats = np.zeros((self.S, 8), np.int32)
+        _check(load_library().orbx_tracker_step(self.h, ptrs, w, h, w, _p(Tt), _p(Tp), _p(out), _p(stats)),
+               "orbx_tracker_step")
+        return out.reshape(self.S, 4, 4), stats
+
+    def step_device(self, d_imgs, w, h, stride, d_true, d_prior, d_out, d_stats):
+        _check(load_library().orbx_tracker_step_device(self.h, d_imgs, w, h, stride, d_true, d_prior, d_out, d_stats),
+               "orbx_tracker_step_device")
+
+    def set_profiling(self, on=True):
+        _check(load_library().orbx_tracker_set_profiling(self.h, int(on)), "orbx_tracker_set_profiling")
+
+    def stage_ms(self):
+        ms = np.zeros(len(self.STAGES), np.float32)
+        _check(load_library().orbx_tracker_stage_ms(self.h, _p(ms)), "orbx_tracker_stage_ms")
+        return ms

@@ -3,7 +3,9 @@
 
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
 line on rank 0.  A *step* is one pass of the hot path over one batch: S independent 752x480 stereo
-streams, one stereo frame each (2*S images per GPU).  Multi-GPU = replicas only (independent streams,
+streams advance one frame each (2*S images per GPU) through the whole per-frame chain — ORB extraction L+R,
+ComputeStereoMatches, SearchByProjection(last frame), PoseOptimization, SearchByProjection(local map),
+PoseOptimization (orbx_tracker_step).  Multi-GPU = replicas only (independent streams,
 no data-path collective; NCCL is used for the barrier and the max-over-ranks reduction).
 
   value  : stereo frames/s, inputs resident in HBM (device API), CUDA-event timed on the launch stream
@@ -26,12 +28,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "awesome-orb-slam3-3dvisioncraft-version_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
 W, H, NFEAT, NLEVELS = 752, 480, 1000, 8
 METRIC = "tracking frames/sec (extract+match+poseopt) EuRoC 752x480"
 UNIT = "stereo frames/s"
+WORKLOAD = ("EuRoC MH01-shaped stereo 752x480, 1000 feat, 8 levels: ORB extraction L+R, ComputeStereoMatches, "
+            "SearchByProjection(last frame), PoseOptimization, SearchByProjection(local map), PoseOptimization")
 
 
 def level_sizes(w=W, h=H, nlevels=NLEVELS, sf=1.2):
@@ -107,19 +112,46 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def make_poses(n_streams, seed=7):
+    """Ground-truth pose per stream and the motion-model guess tracking starts from (0.4 deg, 1 cm off)."""
+    rng = np.random.default_rng(seed)
+
+    def rot(deg):
+        w = rng.normal(0, 1, 3)
+        w = w / np.linalg.norm(w) * np.deg2rad(deg)
+        th = np.linalg.norm(w)
+        K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+        return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+
+    Tt = np.zeros((n_streams, 4, 4), np.float32)
+    Tp = np.zeros((n_streams, 4, 4), np.float32)
+    for s in range(n_streams):
+        R, t = rot(rng.uniform(0.1, 10)), rng.uniform(-0.5, 0.5, 3)
+        Rp = rot(0.4)
+        Tt[s] = np.eye(4)
+        Tt[s][:3, :3], Tt[s][:3, 3] = R, t
+        Tp[s] = np.eye(4)
+        Tp[s][:3, :3], Tp[s][:3, 3] = Rp @ R, Rp @ t + rng.normal(0, 0.01, 3)
+    return Tt, Tp
+
+
 def cpu_oracle_frames_per_s(n_frames, threads=1):
-    """Time the CPU oracle on n_frames stereo frames (2 extractions each)."""
+    """Time the CPU oracle chain (tests/replay_reference.track_frame) on n_frames stereo frames."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
+    from orbx import abi
+    from replay_reference import track_frame
     imgs = make_streams(min(n_frames, 12))
+    npool = len(imgs) // 2
+    Tt, Tp = make_poses(npool)
+    cam = abi.make_camera()
     oracle.lib()
 
     def work(tid, count):
-        ex = oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7)
+        ex = (oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7), oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7))
         for i in range(count):
-            j = (tid * 5 + i) % (len(imgs) // 2)
-            ex(imgs[2 * j])
-            ex(imgs[2 * j + 1])
+            j = (tid * 5 + i) % npool
+            track_frame(oracle, cam, imgs[2 * j], imgs[2 * j + 1], Tt[j], Tp[j], extractors=ex)
         return count
 
     per = [n_frames // threads + (1 if t < n_frames % threads else 0) for t in range(threads)]
@@ -134,28 +166,55 @@ def cpu_oracle_frames_per_s(n_frames, threads=1):
     return n_frames / dt, dt
 
 
+def _ref_worker(job):
+    tid, count = job
+    import oracle
+    from orbx import abi
+    from replay_reference import track_frame
+    g = _ref_worker.__dict__
+    if "imgs" not in g:
+        g["imgs"] = make_streams(12)
+        g["poses"] = make_poses(12)
+        g["cam"] = abi.make_camera()
+        g["ex"] = (oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7), oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7))
+    imgs, (Tt, Tp) = g["imgs"], g["poses"]
+    for i in range(count):
+        j = (tid * 5 + i) % 12
+        track_frame(oracle, g["cam"], imgs[2 * j], imgs[2 * j + 1], Tt[j], Tp[j], extractors=g["ex"])
+    return count
+
+
 def run_reference(args):
+    """The reference arm: the reference's CPU implementation cannot be built here (needs OpenCV 3/Eigen/Boost/
+    Pangolin), so this times the CPU oracle — a line-by-line port of it — on all host cores, one independent
+    stream per process, on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
     cores = os.cpu_count() or 1
-    threads = max(1, min(cores, 64))
-    frames_per_step = max(threads, 16)
-    for _ in range(args.warmup):
-        cpu_oracle_frames_per_s(threads, threads)
-    t_total, n_total = 0.0, 0
-    for _ in range(args.steps):
-        fps, dt = cpu_oracle_frames_per_s(frames_per_step, threads)
-        t_total += dt
-        n_total += frames_per_step
+    procs = max(1, min(cores, 64))
+    per_proc = 2
+    frames_per_step = procs * per_proc
+    import oracle
+    oracle.lib()   # build once before forking
+    with mp.get_context("fork").Pool(procs) as pool:
+        jobs = [(t, per_proc) for t in range(procs)]
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_ref_worker, jobs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_ref_worker, jobs)
+        t_total = time.perf_counter() - t0
+    n_total = frames_per_step * args.steps
     value = n_total / t_total
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "impl": "reference",
-           "config": {"workload": "EuRoC-shaped 752x480 stereo, 1000 feat, 8 levels: ORB extraction L+R "
-                                  "(CPU oracle, %d frames/step)" % frames_per_step},
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                            "sample": "%d stereo frames per step x %d steps, %d threads" % (frames_per_step, args.steps, threads)},
+           "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic", "impl": "reference",
+           "config": {"workload": WORKLOAD + " (CPU oracle, %d frames/step)" % frames_per_step},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                            "sample": "%d stereo frames per step x %d steps on %d processes (host has %d cores)"
+                                      % (frames_per_step, args.steps, procs, cores)},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -187,38 +246,41 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
 
     S = args.streams
     B = 2 * S
+    cam = orbx.make_camera()
     ctx = orbx.Context(local)
     ex = orbx.ORBextractor(ctx, NFEAT, 1.2, NLEVELS, 20, 7, max_w=W, max_h=H, max_batch=B)
+    trk = orbx.Tracker(ctx, ex, S, cam, th_frame=7.0, th_map=1.0, nnratio_map=0.8)
     imgs = make_streams(S, seed0=100 + 1000 * rank)
-    cap = ex.cap
+    Tt, Tp = make_poses(S, seed=7 + rank)
     stream = torch.cuda.ExternalStream(ex.stream, device=local)
 
     # ---------------- resident arm: inputs already in HBM ----------------
-    host = torch.from_numpy(np.stack(imgs)).pin_memory()
-    d_img = host.cuda(non_blocking=False)
-    d_kps = torch.empty((B, cap, 6), dtype=torch.float32, device="cuda")
-    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device="cuda")
-    d_n = torch.zeros(B, dtype=torch.int32, device="cuda")
-    d_mono = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_img = torch.from_numpy(np.stack(imgs)).cuda()
+    d_true = torch.from_numpy(Tt.reshape(S, 16)).cuda()
+    d_prior = torch.from_numpy(Tp.reshape(S, 16)).cuda()
+    d_out = torch.zeros((S, 16), dtype=torch.float32, device="cuda")
+    d_stats = torch.zeros((S, 8), dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     torch.cuda.synchronize()
 
     def step_device():
-        ex.extract_batch_device(d_img.data_ptr(), B, W, H, W, d_kps.data_ptr(), d_desc.data_ptr(), cap,
-                                d_n.data_ptr(), d_mono.data_ptr())
+        trk.step_device(d_img.data_ptr(), W, H, W, d_true.data_ptr(), d_prior.data_ptr(), d_out.data_ptr(),
+                        d_stats.data_ptr())
 
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
     ex.set_profiling(True)
+    trk.set_profiling(True)
     launches0 = ctx.launches
-    stage_sum = np.zeros(len(ex.STAGES))
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    ext_sum = np.zeros(len(ex.STAGES))
+    trk_sum = np.zeros(len(trk.STAGES))
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
@@ -230,31 +292,33 @@ def main():
             step_device()
             ev[k][1].record(stream)
         ev[k][1].synchronize()
-        ms, ln = ex.stage_ms()
-        stage_sum += ms
+        ext_sum += ex.stage_ms()[0]
+        trk_sum += trk.stage_ms()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = ctx.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
     ex.set_profiling(False)
-    kp_mean = float(d_n.float().mean().item())
+    trk.set_profiling(False)
+    stats = d_stats.cpu().numpy()
+    pose_err = float(np.abs(d_out.cpu().numpy().reshape(S, 4, 4)[:, :3, 3] - Tt[:, :3, 3]).max())
 
     # ---------------- e2e arm: host buffers through the C ABI ----------------
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        ex.extract_batch(imgs)
+        trk.step(imgs, Tt, Tp)
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        res = ex.extract_batch(imgs)
+        To, st = trk.step(imgs, Tt, Tp)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    h2d = B * W * H
-    d2h = int(sum(len(r[1]) for r in res) * (24 + 32) + 2 * 4 * B)
+    h2d = B * W * H + 2 * S * 64
+    d2h = S * 64 + S * 8 * 4
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- reduce over ranks (max time) ----------------
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -271,49 +335,58 @@ def main():
         return
 
     # ---------------- roofline of the dominant kernel (live CUDA-event stage times) ----------------
-    stage_ms = stage_sum / args.steps
+    ext_ms = ext_sum / args.steps          # kernels inside stage "extract"
+    trk_ms = trk_sum / args.steps
+    kp_mean = float(stats[:, 0].mean())
     alg = algorithmic_bytes(int(round(kp_mean)))
-    dom = int(np.argmax(stage_ms))
-    dom_name = ex.STAGES[dom]
+    kernel_ms = {("extract." + n): float(v) for n, v in zip(ex.STAGES, ext_ms)}
+    kernel_ms.update({n: float(v) for n, v in zip(trk.STAGES[1:], trk_ms[1:])})
+    dom_name = max(kernel_ms, key=kernel_ms.get)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    dom_bytes = alg[dom_name] * B
-    n_launch = (NLEVELS - 1) if dom_name == "pyramid" else 1
-    achieved = dom_bytes / n_launch / (stage_ms[dom] / n_launch * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    short = dom_name.split(".")[-1]
+    if dom_name.startswith("extract."):
+        n_launch = (NLEVELS - 1) if short == "pyramid" else 1
+        dom_bytes = alg[short] * B
+    else:   # matcher / optimiser stages: bytes of the arrays the stage must touch once
+        n_launch = 2
+        dom_bytes = int(S * kp_mean * (32 + 24 + 16) * 2)
+    achieved = dom_bytes / (kernel_ms[dom_name] * 1e-3) / 1e9 if kernel_ms[dom_name] > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(dom_name)
+            traffic = json.load(open(tp)).get(short)
         except Exception:
             traffic = None
-    roof = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic,
-            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-            "stage_ms": {n: float(v) for n, v in zip(ex.STAGES, stage_ms)},
-            "extractor_total": {"achieved": alg["total"] * B / (stage_ms.sum() * 1e-3) / 1e9,
-                                "frac": alg["total"] * B / (stage_ms.sum() * 1e-3) / 1e9 / peak,
-                                "bytes_per_image": alg["total"]}}
+    ext_total_ms = float(ext_ms.sum())
+    roof = {"bound": "hbm", "kernel": dom_name, "launches_per_step": n_launch, "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+            "algorithmic_bytes_per_launch": dom_bytes // n_launch, "stage_ms": kernel_ms,
+            "extractor_total": {"achieved": alg["total"] * B / (ext_total_ms * 1e-3) / 1e9,
+                                "frac": alg["total"] * B / (ext_total_ms * 1e-3) / 1e9 / peak,
+                                "bytes_per_image": alg["total"], "ms": ext_total_ms}}
 
     cpu = None
-    if not args.no_cpu and world >= 1:
+    if not args.no_cpu:
         fps, dt = cpu_oracle_frames_per_s(args.cpu_frames, 1)
         cpu = {"value": fps, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "%d stereo frames (2 extractions each) of the same workload, %.1f s, 1 thread of %d cores"
+               "sample": "%d stereo frames of the same chain, %.1f s, 1 thread (host has %d cores)"
                          % (args.cpu_frames, dt, os.cpu_count() or 0)}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": "EuRoC MH01-shaped stereo 752x480, 1000 feat, 8 levels, extractor (L+R) only "
-                                  "[matcher/pose-opt stages join as they land]",
-                      "streams_per_gpu": S, "images_per_step_per_gpu": B, "parallelism": "replicas x%d" % world,
+           "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "streams_per_gpu": S, "images_per_step_per_gpu": B,
+                      "parallelism": "replicas x%d" % world,
                       "l2": "256 MiB flush between timed steps + working set > L2",
-                      "mean_keypoints_per_image": kp_mean},
+                      "mean_per_stream": {n: float(v) for n, v in zip(trk.STATS, stats.mean(0))},
+                      "max_translation_error_m": pose_err},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "steps": e2e_steps},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}

@@ -274,6 +274,40 @@ int orbx_local_ba(orbx_ctx *ctx, int n_kf, float *kf_Tcw, const uint8_t *kf_fixe
                   double lambda_init, const volatile uint8_t *stop_flag, uint8_t *edge_bad,
                   int32_t *iters, int32_t *status);
 
+/* ====================================================================================
+ * Many-stream tracking replay: S independent stereo streams
+ * advance one frame per call, everything device-resident between stages:
+ *   extract L+R (2*S images) -> ComputeStereoMatches -> SearchByProjection(Cur, Last) ->
+ *   PoseOptimization -> SearchByProjection(F, local map) -> PoseOptimization.
+ * No dataset is available offline, so the map a stream tracks against is synthesised from the frame
+ * itself: its stereo points back-projected at Tcw_true play the role of the last frame's / local
+ * map's MapPoints (real descriptors, real candidate densities), and tracking starts from
+ * Tcw_prior (the motion-model guess).  The per-stage kernels are exactly the ones behind the
+ * single-frame entry points above.
+ * ================================================================================== */
+typedef struct orbx_tracker orbx_tracker;
+#define ORBX_TRACK_STATS 8 /* nL, nR, nStereo, matches(last frame), inliers, matches(local map), inliers, LM its */
+
+orbx_tracker *orbx_tracker_create(orbx_ctx *ctx, orbx_ext *ext /* max_batch >= 2*S */, int S,
+                                  const orbx_camera *cam, float th_frame, float th_map,
+                                  float nnratio_map);
+void orbx_tracker_destroy(orbx_tracker *trk);
+/* images: [2*S][h][stride] device bytes, image 2s = left, 2s+1 = right of stream s; poses [S][16]
+ * row-major float32 device arrays; stats [S][ORBX_TRACK_STATS] device int32.  Enqueues on the
+ * extractor's stream and returns. */
+int orbx_tracker_step_device(orbx_tracker *trk, const uint8_t *d_imgs, int w, int h, int stride,
+                             const float *d_Tcw_true, const float *d_Tcw_prior, float *d_Tcw_out,
+                             int32_t *d_stats);
+/* Same through HOST buffers: copies the 2*S images in, the S poses and stats out, synchronises. */
+int orbx_tracker_step(orbx_tracker *trk, const uint8_t *const *imgs, int w, int h, int stride,
+                      const float *Tcw_true, const float *Tcw_prior, float *Tcw_out, int32_t *stats);
+/* Per-stage device time of the last step (CUDA events on the stream), ORBX_TRACK_STAGES entries:
+ * 0 extract, 1 stereo match, 2 search-by-projection (last frame), 3 pose optimisation #1,
+ * 4 search-by-projection (local map), 5 pose optimisation #2. */
+#define ORBX_TRACK_STAGES 6
+int orbx_tracker_set_profiling(orbx_tracker *trk, int enable);
+int orbx_tracker_stage_ms(orbx_tracker *trk, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

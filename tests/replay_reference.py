@@ -1,0 +1,82 @@
+"""The tracking-replay chain of orbx_tracker_step, composed on the CPU from the oracle's functions plus numpy
+float32 glue that mirrors the harness kernels' expression order (back-projection, frustum projection).
+Used by the GPU parity test of the whole chain and by bench.py's CPU baseline."""
+import numpy as np
+
+import scenarios as sc
+
+F32 = np.float32
+
+
+def track_frame(ork, cam, L, R, Tcw_true, Tcw_prior, th_frame=7.0, th_map=1.0, nn_map=0.8, nfeatures=1000,
+                extractors=None):
+    from orbx import abi
+    exL, exR = extractors if extractors else (ork.Extractor(nfeatures), ork.Extractor(nfeatures))
+    _, kL, dL, _ = exL(L)
+    _, kR, dR, _ = exR(R)
+    scale, inv_scale = exL.scale, exL.inv_scale
+    isg = exL.inv_sigma2
+    pyrL = [exL.pyramid_level(l) for l in range(exL.nlevels)]
+    pyrR = [exR.pyramid_level(l) for l in range(exR.nlevels)]
+    bf, b = F32(cam.bf), F32(cam.b)
+    ur, dp = ork.stereo_match(pyrL, pyrR, kL, dL, kR, dR, scale, inv_scale, float(bf), float(b))
+    n = len(kL)
+    fx, fy, cx, cy = F32(cam.fx), F32(cam.fy), F32(cam.cx), F32(cam.cy)
+    # --- back-projection at the true pose (backproject_kernel) ---
+    T = np.asarray(Tcw_true, F32).reshape(4, 4)
+    has = dp > 0
+    z = dp.astype(F32)
+    xc = (kL["x"] - cx) * z / fx
+    yc = (kL["y"] - cy) * z / fy
+    dx, dy, dz = xc - T[0, 3], yc - T[1, 3], z - T[2, 3]
+    xw = np.stack([T[0, 0] * dx + T[1, 0] * dy + T[2, 0] * dz, T[0, 1] * dx + T[1, 1] * dy + T[2, 1] * dz,
+                   T[0, 2] * dx + T[1, 2] * dy + T[2, 2] * dz], 1).astype(F32)
+    flags = np.where(has, 3, 0).astype(np.uint8)
+    in_last = (((np.arange(n, dtype=np.uint64) * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)) >> np.uint64(16)) % np.uint64(5) < 3
+    last_flags = np.where(has & in_last, 3, 0).astype(np.uint8)   # the last frame tracked ~60 % of the local map
+    H, W = L.shape
+    Fr = abi.Frame(kL, dL, ur, bounds=(0, 0, W, H))
+    # --- SearchByProjection(Cur, Last) ---
+    Tp = np.asarray(Tcw_prior, F32).reshape(4, 4)
+    nm1, match, kept, cur = ork.search_by_projection_frame(Fr, None, cam, Tp, np.eye(4, dtype=F32), last_flags, xw,
+                                                           kL["octave"].astype(np.int32), kL["angle"], dL, th_frame,
+                                                           False, True, scale)
+    # (the device harness fixes the octave-window mode to "neither forward nor backward"; with Tcw_last = I and a
+    #  prior close to the true pose |tlc.z| < mb holds as long as the test keeps the translation small)
+
+    def edges(assign):
+        idx = np.flatnonzero(assign >= 0)
+        q = assign[idx]
+        obs = np.stack([kL["x"][idx], kL["y"][idx], ur[idx]], 1).astype(F32)
+        return idx, xw[q], obs, isg[kL["octave"][idx]].astype(F32)
+
+    idx1, exw, eobs, eisg = edges(cur)
+    T1, out1, nin1, it1 = ork.pose_optimization(exw, eobs, eisg, cam, Tp)
+    # --- drop outliers, SearchLocalPoints + SearchByProjection(F, local map) ---
+    cur2 = cur.copy()
+    cur2[idx1[out1 == 1]] = -1
+    blocked = (cur2 >= 0).astype(np.uint8)
+    taken = np.zeros(n, bool)
+    taken[cur2[cur2 >= 0]] = True
+    X, Y, Z = xw[:, 0], xw[:, 1], xw[:, 2]
+    xcm = T1[0, 0] * X + T1[0, 1] * Y + T1[0, 2] * Z + T1[0, 3]
+    ycm = T1[1, 0] * X + T1[1, 1] * Y + T1[1, 2] * Z + T1[1, 3]
+    zcm = T1[2, 0] * X + T1[2, 1] * Y + T1[2, 2] * Z + T1[2, 3]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        invz = F32(1.0) / zcm
+        u = fx * xcm / zcm + cx
+        v = fy * ycm / zcm + cy
+    vis = has & ~taken & (zcm > 0) & (u >= 0) & (u <= W) & (v >= 0) & (v <= H)
+    mflags = np.where(vis, 3, 0).astype(np.uint8)
+    projXR = (u - bf * invz).astype(F32)
+    nm2, best = ork.search_by_projection_map(Fr, blocked, np.where(vis, u, 0).astype(F32), np.where(vis, v, 0).astype(F32),
+                                             np.where(vis, projXR, 0).astype(F32), kL["octave"].astype(np.int32),
+                                             np.ones(n, F32), dL, mflags, th_map, nn_map, scale)
+    kpmp = cur2.copy()
+    for q in range(n):
+        if best[q] >= 0:
+            kpmp[best[q]] = q
+    idx2, exw2, eobs2, eisg2 = edges(kpmp)
+    T2, out2, nin2, it2 = ork.pose_optimization(exw2, eobs2, eisg2, cam, T1)
+    stats = np.array([n, len(kR), int((ur >= 0).sum()), nm1, nin1, nm2, nin2, int(it1.sum() + it2.sum())], np.int32)
+    return T2, stats

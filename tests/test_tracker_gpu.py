@@ -1,0 +1,49 @@
+"""GPU parity of the whole per-frame chain (orbx_tracker_step: extract -> stereo match -> SearchByProjection(last)
+-> PoseOptimization -> SearchByProjection(local map) -> PoseOptimization) against the same chain composed from the
+CPU oracle's functions."""
+import numpy as np
+import pytest
+
+import scenarios as sc
+from replay_reference import track_frame
+
+pytestmark = pytest.mark.gpu
+
+
+def _poses(rng, S):
+    Tt, Tp = [], []
+    for _ in range(S):
+        R = sc.rot_small(rng, rng.uniform(0, 10))
+        t = rng.uniform(-0.5, 0.5, 3)
+        T = sc.se3_matrix(R, t)
+        Rp = sc.rot_small(rng, 0.4)
+        P = sc.se3_matrix(Rp @ R, Rp @ t + rng.normal(0, 0.01, 3))
+        Tt.append(T.astype(np.float32))
+        Tp.append(P.astype(np.float32))
+    return np.array(Tt), np.array(Tp)
+
+
+def test_tracker_chain_matches_oracle_chain(ctx, ork):
+    import orbx
+    from orbx import synth
+    S = 3
+    cam = orbx.make_camera()
+    rng = np.random.default_rng(11)
+    imgs = []
+    for s in range(S):
+        L, R = synth.stereo_pair(40 + s)
+        imgs += [L, R]
+    Tt, Tp = _poses(rng, S)
+    ex = orbx.ORBextractor(ctx, max_batch=2 * S)
+    trk = orbx.Tracker(ctx, ex, S, cam)
+    for rep in range(2):   # second call: same buffers, same answer
+        Tout, stats = trk.step(imgs, Tt, Tp)
+        for s in range(S):
+            T2, st = track_frame(ork, cam, imgs[2 * s], imgs[2 * s + 1], Tt[s], Tp[s])
+            assert np.array_equal(stats[s], st), (s, stats[s], st)
+            assert np.abs(Tout[s] - T2).max() < 2e-6, (s, np.abs(Tout[s] - T2).max())
+            # the replay converges back to the pose the map was built at
+            assert np.abs(Tout[s][:3, 3] - Tt[s][:3, 3]).max() < 5e-3
+            assert st[2] > 300 and st[3] > 150 and st[6] > 150
+    trk.close()
+    ex.close()
