@@ -107,9 +107,10 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
     L.tileStart = tile;
     tile += L.tilesPerRow * L.nRows;
     const int tw = std::min(ORBX_FAST_CELLS, L.nCols) * L.wCell + 6;
-    fastBytes = std::max(fastBytes, (int)align_up((size_t)((tw + 3) & ~3) * (L.hCell + 6), 16));
-    L.blurTilesX = div_up(L.w, ORBX_BLUR_TW);
-    L.blurTilesY = div_up(L.h, ORBX_BLUR_TH);
+    // one shared-memory plane: (tw + alignment slack + one spare word) x (hCell + 6 + 2 score border rows)
+    fastBytes = std::max(fastBytes, (int)align_up((size_t)(((tw + 3 + 3) & ~3) + 8) * (L.hCell + 8), 16));
+    L.blurTilesX = div_up(L.w, ORBX_BLUR_TW);        // 128 columns per warp (32 lanes x 4 px)
+    L.blurTilesY = div_up(L.h, ORBX_BLUR_TH);        // 8 warps x 32-row strips per CTA
     L.blurTileStart = btile;
     btile += L.blurTilesX * L.blurTilesY;
     L.nFeat = e->nFeat[l];
@@ -128,6 +129,8 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   for (int l = 0; l < e->nlevels; ++l) {
     LevelParams& L = P.lv[l];
     L.blur = e->d_pyr + off;
+    L.blurPitch = L.pitch;             // internal pitch, also for level 0 (whose `pyr` may be rebound per call)
+    L.blurStride = L.imgStride;
     off += align_up(L.imgStride * e->maxB, 256);
   }
   if (off > e->pyrBytes || (size_t)cand > e->candElems / e->maxB || (size_t)sel > e->selElems / e->maxB) {
@@ -391,6 +394,10 @@ int orbx_extract_batch_device(orbx_ext* e, int B, const uint8_t* d_imgs, int w, 
   if (!e || !d_imgs || !d_kps || !d_desc || !d_n_out || !d_mono_out || cap < 1) return ORBX_EINVAL;
   if (w <= 0 || h <= 0) return ORBX_EMPTY;
   if (stride < w) return ORBX_EINVAL;
+  if ((stride & 3) || (reinterpret_cast<uintptr_t>(d_imgs) & 3)) {
+    orbx_set_error("orbx_extract_batch_device: image base and stride must be multiples of 4 bytes (32-bit tile loads)");
+    return ORBX_EINVAL;
+  }
   ORBX_CUDA(cudaSetDevice(e->ctx->device));
   e->level0External = true;
   return run_device(e, B, d_imgs, w, h, stride, lap0, lap1, d_kps, d_desc, cap, d_n_out, d_mono_out);

@@ -6,14 +6,16 @@
 #define ORBX_MINB 16          // minBorderX = EDGE_THRESHOLD-3, src/ORBextractor.cc:771
 #define ORBX_FAST_CELLS 8     // cells per FAST tile (one cell row x up to 8 cells)
 #define ORBX_BLUR_TW 128
-#define ORBX_BLUR_TH 16
+#define ORBX_BLUR_TH 256
 
 // One pyramid level of a batch of B equally sized images.
 struct LevelParams {
   int w, h, pitch;                 // level size in pixels, row pitch in bytes
   size_t imgStride;                // bytes between consecutive images of the batch
   uint8_t* pyr;                    // un-blurred level (level 0 may alias the caller's input)
-  uint8_t* blur;                   // 7x7 sigma-2 blurred level
+  uint8_t* blur;                   // 7x7 sigma-2 blurred level (own pitch: level 0 of `pyr` may be caller memory)
+  int blurPitch;
+  size_t blurStride;
   // FAST cell tiling (src/ORBextractor.cc:771-804)
   int nCols, nRows, wCell, hCell, maxBX, maxBY;
   int tileStart, tilesPerRow;      // flattened FAST tile ids of this level

@@ -52,27 +52,37 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
 // =====================================================================================
 // K2  per-cell FAST-9-16 + cell-local 3x3 NMS + iniTh->minTh fallback + candidate emission.
 // One CTA = one cell row x up to ORBX_FAST_CELLS cells of one level of one image.
+//
+// Work is staged so that the expensive per-pixel arithmetic only runs on a dense, compacted list:
+//   A. tile -> shared memory with 32-bit loads (tile origin rounded down to a 4-byte boundary)
+//   B. early reject, 4 pixels per instruction stream: VABSDIFF4 of the centre word against the four
+//      compass ring positions (0,4,8,12), SWAR ">t" masks, and the necessary condition "two adjacent
+//      compass points differ by more than t" (every 9-arc of the 16-ring contains two adjacent compass
+//      points).  Survivors are appended to a shared-memory list.
+//   C. exact score of every survivor: the 16 ring differences are packed as (256+d, 256-d) in one
+//      s16x2 register by a single IMAD each, and the max-over-arcs-of-min network runs for both
+//      polarities at once on VIMNMX3.S16x2 (40 instructions).  corner <=> arcmax > minTh.
+//   D. cell-local 3x3 NMS, per-cell "has a corner >= iniTh" flag, emission (one global atomic per tile).
 // =====================================================================================
-__device__ __forceinline__ int arc9_maxmin(const int (&d)[16]) {
-  int t[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) t[k] = min(min(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
-  int best = -256;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) best = max(best, min(min(t[k], t[(k + 3) & 15]), t[(k + 6) & 15]));
-  return best;
+__device__ __forceinline__ unsigned swar_gt_u8(unsigned x, unsigned k) {   // k = (0x7f - t) * 0x01010101, t < 128
+  return (((x & 0x7f7f7f7fu) + k) | x) & 0x80808080u;
 }
 
-// 16-bit cyclic mask has >= 9 consecutive ones?
-__device__ __forceinline__ bool has_arc9(uint32_t m) {
-  m |= m << 16;
-  uint32_t r = m & (m >> 1);
-  r &= r >> 2;
-  r &= r >> 4;   // 8 consecutive
-  r &= m >> 8;   // 9 consecutive
-  return (r & 0xffffu) != 0;
-}
+__device__ __forceinline__ unsigned vmin3(unsigned a, unsigned b, unsigned c) { return __vimin3_s16x2(a, b, c); }
+__device__ __forceinline__ unsigned vmax3(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
 
+// X[k] = (256 + d_k) | (256 - d_k) << 16 ; returns max over the 16 cyclic 9-arcs of the lane-wise minimum
+__device__ __forceinline__ unsigned arc9_maxmin_x2(const unsigned (&X)[16]) {
+  unsigned t[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) t[k] = vmin3(X[k], X[(k + 1) & 15], X[(k + 2) & 15]);
+  unsigned m[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) m[k] = vmin3(t[k], t[(k + 3) & 15], t[(k + 6) & 15]);
+  const unsigned a0 = vmax3(m[0], m[1], m[2]), a1 = vmax3(m[3], m[4], m[5]), a2 = vmax3(m[6], m[7], m[8]);
+  const unsigned a3 = vmax3(m[9], m[10], m[11]), a4 = vmax3(m[12], m[13], m[14]);
+  return vmax3(vmax3(a0, a1, a2), vmax3(a3, a4, m[15]), a0);
+}
 
 __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ ExtractParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -87,6 +97,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const int ci = lt / L.tilesPerRow;
   const int j0 = (lt - ci * L.tilesPerRow) * ORBX_FAST_CELLS;
   const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
   const int iniY = ORBX_MINB + ci * L.hCell;
   if (iniY >= L.maxBY - 3) return;
@@ -102,87 +113,181 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const int wI = tw - 6, hI = th - 6;                 // interior (evaluated) pixels
   if (wI <= 0 || hI <= 0) return;
 
-  // shared: image tile [th][tp] | score [(hI+2)][sp] | flag [hI][sp] | cellHasIni[ORBX_FAST_CELLS]
-  const int tp = (tw + 3) & ~3;
+  // shared layout: [flags 64 B][image tile th x tpw words][score (hI+2) x sp][survivor flag hI x sp]
+  //                [column->cell table][candidate list]
+  const int xa = iniX & ~3;                           // aligned tile origin
+  const int off = iniX - xa;                          // 0..3: byte column of tile column 0
+  const int tpw = (off + tw + 3) / 4 + 1;             // words per tile row (+1: the stage-B window reads word c+1)
+  const int tp = tpw * 4;
   const int sp = wI + 2;
-  int* shas = reinterpret_cast<int*>(smem);
+  int* sflag = reinterpret_cast<int*>(smem);          // [0..7] cellHasIni, [8] nCand, [9] nEmit, [10] emit base
   uint8_t* simg = smem + 64;
   uint8_t* ssc = simg + (size_t)p.fastTileBytes;
-  uint8_t* sfl = ssc + (size_t)p.fastTileBytes;
+  uint8_t* scell = ssc + (size_t)p.fastTileBytes;     // [wI] cell index of interior column x
+  uint16_t* scand = reinterpret_cast<uint16_t*>(scell + 512);
 
+  // ---- A: load ----
   const uint8_t* img = L.pyr + (size_t)b * L.imgStride;
-  for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
-    int y = i / tw, x = i - y * tw;
-    simg[y * tp + x] = __ldg(img + (size_t)(iniY + y) * L.pitch + iniX + x);
+  {
+    const int nwords = th * tpw;
+    uint32_t* simg32 = reinterpret_cast<uint32_t*>(simg);
+    const int rowWords = (L.pitch - xa) / 4;          // words readable in a row without leaving the pitch
+    for (int i = tid; i < nwords; i += 256) {
+      const int r = i / tpw, c = i - r * tpw;
+      uint32_t v = 0;
+      if (c < rowWords) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(iniY + r) * L.pitch + xa) + c);
+      simg32[i] = v;
+    }
+    for (int i = tid; i < (hI + 2) * sp; i += 256) ssc[i] = 0;
+    for (int x = tid; x < wI; x += 256) scell[x] = (uint8_t)(x / L.wCell);
+    if (tid < 16) sflag[tid] = 0;
   }
-  for (int i = threadIdx.x; i < (hI + 2) * sp; i += blockDim.x) ssc[i] = 0;
-  if (threadIdx.x < ORBX_FAST_CELLS) shas[threadIdx.x] = 0;
   __syncthreads();
 
+  // ---- B: compass early reject, one 4-pixel word per thread-iteration ----
   const int t = p.minTh;
-  for (int i = threadIdx.x; i < hI * wI; i += blockDim.x) {
-    const int y = i / wI, x = i - y * wI;
-    const uint8_t* c = simg + (y + 3) * tp + (x + 3);
-    const int v = c[0];
-    int d[16];
-    d[0] = v - c[3 * tp];      d[1] = v - c[3 * tp + 1];   d[2] = v - c[2 * tp + 2];   d[3] = v - c[tp + 3];
-    d[4] = v - c[3];           d[5] = v - c[-tp + 3];      d[6] = v - c[-2 * tp + 2];  d[7] = v - c[-3 * tp + 1];
-    d[8] = v - c[-3 * tp];     d[9] = v - c[-3 * tp - 1];  d[10] = v - c[-2 * tp - 2]; d[11] = v - c[-tp - 3];
-    d[12] = v - c[-3];         d[13] = v - c[tp - 3];      d[14] = v - c[2 * tp - 2];  d[15] = v - c[3 * tp - 1];
-    uint32_t mb = 0, md = 0;
+  const unsigned kGt = (unsigned)(0x7f - t) * 0x01010101u;
+  {
+    const uint32_t* simg32 = reinterpret_cast<const uint32_t*>(simg);
+    const int c0 = (off + 3) / 4, c1 = (off + 3 + wI - 1) / 4;   // words that hold interior pixels
+    const int ncw = c1 - c0 + 1;
+    const int nwordsB = hI * ncw;
+    for (int i0 = 0; i0 < nwordsB; i0 += 256) {
+      const int i = min(i0 + tid, nwordsB - 1);       // out-of-range lanes redo the last word and drop its result
+      const bool live = i0 + tid < nwordsB;
+      const int y = i / ncw, c = c0 + (i - y * ncw);
+      const uint32_t* row = simg32 + (y + 3) * tpw + c;
+      const uint32_t V = row[0];
+      const uint32_t r0 = row[3 * tpw], r8 = row[-3 * tpw];
+      const uint32_t r4 = __funnelshift_r(row[0], row[1], 24);     // bytes +3..+6
+      const uint32_t r12 = __funnelshift_r(row[-1], row[0], 8);    // bytes -3..0
+      const unsigned b0 = swar_gt_u8(__vabsdiffu4(r0, V), kGt), b4 = swar_gt_u8(__vabsdiffu4(r4, V), kGt);
+      const unsigned b8 = swar_gt_u8(__vabsdiffu4(r8, V), kGt), b12 = swar_gt_u8(__vabsdiffu4(r12, V), kGt);
+      unsigned cand = ((b0 | b8) & (b4 | b12));       // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
+      // drop bytes outside the interior columns
+      const int xb = c * 4 - (off + 3);               // interior x of byte 0 (may be negative)
+      if (xb < 0) cand &= 0xffffffffu << (8 * (-xb));
+      if (xb + 3 >= wI) cand &= 0xffffffffu >> (8 * (xb + 4 - wI));
+      if (!live) cand = 0;
+      // warp-aggregated append: one shared-memory atomic per warp instead of one per thread
+      const int cnt = __popc(cand);
+      int incl = cnt;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      mb |= (uint32_t)(d[k] > t) << k;
-      md |= (uint32_t)(d[k] < -t) << k;
-    }
-    int score = 0;
-    if (has_arc9(mb)) {
-      score = arc9_maxmin(d) - 1;
-    } else if (has_arc9(md)) {
-#pragma unroll
-      for (int k = 0; k < 16; ++k) d[k] = -d[k];
-      score = arc9_maxmin(d) - 1;
-    }
-    if (score > 0) ssc[(y + 1) * sp + x + 1] = (uint8_t)score;
-  }
-  __syncthreads();
-
-  // NMS inside the pixel's own cell: horizontal neighbours across a cell seam count as 0
-  for (int i = threadIdx.x; i < hI * wI; i += blockDim.x) {
-    const int y = i / wI, x = i - y * wI;
-    const uint8_t* s = ssc + (y + 1) * sp + x + 1;
-    const int sc = s[0];
-    uint8_t keep = 0;
-    if (sc > 0) {
-      const int cell = x / L.wCell, xin = x - cell * L.wCell;
-      const bool hasL = xin != 0, hasR = (xin != L.wCell - 1) && (x + 1 < wI);
-      bool ok = sc > s[-sp] && sc > s[sp];
-      if (hasL) ok = ok && sc > s[-1] && sc > s[-sp - 1] && sc > s[sp - 1];
-      if (hasR) ok = ok && sc > s[1] && sc > s[-sp + 1] && sc > s[sp + 1];
-      if (ok) {
-        keep = 1;
-        if (sc >= p.iniTh) atomicOr(&shas[cell], 1);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
       }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int wbase = 0;
+      if (lane == 31 && total) wbase = atomicAdd(&sflag[8], total);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      int slot = wbase + incl - cnt;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (cand & (0x80u << (8 * k))) scand[slot++] = (uint16_t)((y << 9) | (xb + k));
     }
-    sfl[y * sp + x] = keep;
   }
   __syncthreads();
 
-  uint32_t* cand = p.cand + (size_t)b * p.candPerImage + L.candOfs;
+  // ---- C: exact score of the survivors ----
+  {
+    const int nCand = sflag[8];
+    const int K0 = 256 * 65537;
+    for (int i = tid; i < nCand; i += 256) {
+      const int code = scand[i];
+      const int y = code >> 9, x = code & 511;
+      const uint8_t* c = simg + (y + 3) * tp + (x + 3 + off);
+      const int Kv = K0 - 65535 * (int)c[0];          // X = 65535*r + Kv = (256 + v - r) | (256 - v + r) << 16
+      unsigned X[16];
+      X[0] = 65535u * c[3 * tp] + Kv;       X[1] = 65535u * c[3 * tp + 1] + Kv;   X[2] = 65535u * c[2 * tp + 2] + Kv;
+      X[3] = 65535u * c[tp + 3] + Kv;       X[4] = 65535u * c[3] + Kv;            X[5] = 65535u * c[-tp + 3] + Kv;
+      X[6] = 65535u * c[-2 * tp + 2] + Kv;  X[7] = 65535u * c[-3 * tp + 1] + Kv;  X[8] = 65535u * c[-3 * tp] + Kv;
+      X[9] = 65535u * c[-3 * tp - 1] + Kv;  X[10] = 65535u * c[-2 * tp - 2] + Kv; X[11] = 65535u * c[-tp - 3] + Kv;
+      X[12] = 65535u * c[-3] + Kv;          X[13] = 65535u * c[tp - 3] + Kv;      X[14] = 65535u * c[2 * tp - 2] + Kv;
+      X[15] = 65535u * c[3 * tp - 1] + Kv;
+      const unsigned am = arc9_maxmin_x2(X);
+      const int arcmax = max((int)(am & 0xffffu), (int)(am >> 16)) - 256;
+      if (arcmax > t && arcmax > 1) ssc[(y + 1) * sp + x + 1] = (uint8_t)(arcmax - 1);
+    }
+  }
+  __syncthreads();
+
+  // ---- D: NMS inside the pixel's own cell (neighbours across a cell seam count as 0), on the candidate list only:
+  //         ~30 % of the pixels are candidates, ~12 % carry a score, ~1 % survive ----
+  uint32_t* ssurv = reinterpret_cast<uint32_t*>(simg);   // survivor list reuses the image plane (dead after stage C)
+  {
+    const int nCand = sflag[8];
+    for (int i0 = 0; i0 < nCand; i0 += 256) {
+      const int i = i0 + tid;
+      bool keep = false;
+      int code = 0, sc = 0;
+      if (i < nCand) {
+        code = scand[i];
+        const int y = code >> 9, x = code & 511;
+        const uint8_t* sp0 = ssc + (y + 1) * sp + x + 1;
+        sc = sp0[0];
+        if (sc > 0) {
+          const int cell = scell[x];
+          const bool hasL = x > 0 && scell[x - 1] == cell, hasR = x + 1 < wI && scell[x + 1] == cell;
+          bool ok = sc > sp0[-sp] && sc > sp0[sp];
+          if (hasL) ok = ok && sc > sp0[-1] && sc > sp0[-sp - 1] && sc > sp0[sp - 1];
+          if (hasR) ok = ok && sc > sp0[1] && sc > sp0[-sp + 1] && sc > sp0[sp + 1];
+          if (ok) {
+            keep = true;
+            if (sc >= p.iniTh) atomicOr(&sflag[cell], 1);
+          }
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      int wbase = 0;
+      if (lane == 0 && m) wbase = atomicAdd(&sflag[9], __popc(m));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (keep) ssurv[wbase + __popc(m & ((1u << lane) - 1))] = (uint32_t)code | ((uint32_t)sc << 16);
+    }
+  }
+  __syncthreads();
+  // cells that own a corner >= iniTh drop their weaker survivors (the 20 -> 7 fallback only applies to empty cells)
+  const int nSurv = sflag[9];
+  {
+    int cnt = 0;
+    for (int i = tid; i < nSurv; i += 256) {
+      const uint32_t v = ssurv[i];
+      const int x = v & 511, sc = v >> 16;
+      const bool out = !(sflag[scell[x]] && sc < p.iniTh);
+      if (!out) ssurv[i] = 0xffffffffu;
+      cnt += out;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0 && cnt) atomicAdd(&sflag[11], cnt);
+  }
+  __syncthreads();
   int* candN = p.candN + b * p.nlevels + level;
-  for (int i = threadIdx.x; i < hI * wI; i += blockDim.x) {
-    const int y = i / wI, x = i - y * wI;
-    if (!sfl[y * sp + x]) continue;
-    const int sc = ssc[(y + 1) * sp + x + 1];
-    const int cell = x / L.wCell;
-    if (shas[cell] && sc < p.iniTh) continue;
-    const int slot = atomicAdd(candN, 1);
-    if (slot < L.candCap) {
-      // coordinates relative to (minBorderX, minBorderY), as the reference stores them (:847-848)
-      const int rx = iniX + 3 + x - ORBX_MINB, ry = iniY + 3 + y - ORBX_MINB;
-      cand[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)sc << 24);
-    } else {
-      atomicExch(p.err, 1);
+  if (tid == 0) {
+    sflag[10] = sflag[11] ? atomicAdd(candN, sflag[11]) : 0;   // ONE global atomic per tile
+    sflag[12] = 0;
+  }
+  __syncthreads();
+  uint32_t* cand = p.cand + (size_t)b * p.candPerImage + L.candOfs;
+  const int base = sflag[10];
+  for (int i0 = 0; i0 < nSurv; i0 += 256) {
+    const int i = i0 + tid;
+    const uint32_t v = i < nSurv ? ssurv[i] : 0xffffffffu;
+    const bool k = v != 0xffffffffu;
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    int wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(&sflag[12], __popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (k) {
+      const int slot = base + wbase + __popc(m & ((1u << lane) - 1));
+      if (slot < L.candCap) {
+        // coordinates relative to (minBorderX, minBorderY), as the reference stores them (:847-848)
+        const int x = v & 511, y = (v >> 9) & 127, sc = v >> 16;
+        const int rx = iniX + 3 + x - ORBX_MINB, ry = iniY + 3 + y - ORBX_MINB;
+        cand[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)sc << 24);
+      } else {
+        atomicExch(p.err, 1);
+      }
     }
   }
 }
@@ -190,16 +295,44 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
 // =====================================================================================
 // K5  7x7 sigma-2 Gaussian, OpenCV 4.x fixed point: [18,34,48,56,48,34,18]/256 per pass,
 //     (sum + 2^15) >> 16, BORDER_REFLECT_101.
+// Register-sliding separable filter, no shared memory: a thread owns 4 adjacent columns (one 32-bit word)
+// and walks down a strip of rows.  Per row it forms the 4 horizontal 7-tap sums with DP4A (u8 pixels x
+// s8 weights, two 4-byte windows per output built by funnel shifts), keeps the last 7 rows of those
+// sums in registers, and emits one packed output word per row from the vertical 7-tap combination.
+// A warp covers 128 columns; global loads are one coalesced 128-byte row segment plus two halo words.
 // =====================================================================================
+#define BLUR_STRIP 32   // output rows per warp (6 extra rows are filtered horizontally per strip)
+
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;
-  return i;
+  return min(max(i, 0), n - 1);
+}
+
+// 32-bit word of pixels [4c, 4c+4) of a row, with BORDER_REFLECT_101 outside [0, w)
+__device__ __forceinline__ uint32_t blur_word(const uint8_t* __restrict__ row, int c, int w) {
+  const int x = 4 * c;
+  if (x >= 0 && x + 4 <= w) return __ldg(reinterpret_cast<const uint32_t*>(row) + c);
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v |= (uint32_t)__ldg(row + reflect101(x + k, w)) << (8 * k);
+  return v;
+}
+
+// horizontal 7-tap sums of the 4 pixels of word `b`, given its left/right neighbours
+__device__ __forceinline__ void blur_hrow(uint32_t a, uint32_t b, uint32_t c, int (&h)[4]) {
+  const unsigned W0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);   // taps -3..0
+  const unsigned W1 = 48u | (34u << 8) | (18u << 16);                 // taps +1..+3
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    // window A = pixels p-3..p, window B = pixels p+1..p+4 (p = 4c+k)
+    const uint32_t wa = k == 3 ? b : __funnelshift_r(a, b, 8 * (k + 1));
+    const uint32_t wb = __funnelshift_rc(b, c, 8 * (k + 1));   // clamp mode: a shift of 32 yields `c`
+    h[k] = (int)__dp4a(wb, W1, __dp4a(wa, W0, 0u));
+  }
 }
 
 __global__ void __launch_bounds__(256) gauss7_kernel(const __grid_constant__ ExtractParams p) {
-  __shared__ uint8_t sin_[(ORBX_BLUR_TH + 6) * (ORBX_BLUR_TW + 8)];
-  __shared__ uint16_t sh[(ORBX_BLUR_TH + 6) * ORBX_BLUR_TW];
   const int tile = blockIdx.x;
   int level = 0;
 #pragma unroll 1
@@ -208,38 +341,38 @@ __global__ void __launch_bounds__(256) gauss7_kernel(const __grid_constant__ Ext
   const LevelParams& L = p.lv[level];
   const int lt = tile - L.blurTileStart;
   const int tyi = lt / L.blurTilesX, txi = lt - tyi * L.blurTilesX;
-  const int x0 = txi * ORBX_BLUR_TW, y0 = tyi * ORBX_BLUR_TH;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = txi * 32 + lane;                       // word column
+  const int y0 = (tyi * 8 + wid) * BLUR_STRIP;         // first output row of this warp's strip
+  if (4 * c >= L.w || y0 >= L.h) return;
   const uint8_t* img = L.pyr + (size_t)blockIdx.y * L.imgStride;
-  const int PW = ORBX_BLUR_TW + 8;
-  for (int i = threadIdx.x; i < (ORBX_BLUR_TH + 6) * (ORBX_BLUR_TW + 6); i += blockDim.x) {
-    int y = i / (ORBX_BLUR_TW + 6), x = i - y * (ORBX_BLUR_TW + 6);
-    int gy = reflect101(y0 + y - 3, L.h), gx = reflect101(x0 + x - 3, L.w);
-    // tiles hanging over the right/bottom edge read reflected garbage that is never written out
-    gy = min(max(gy, 0), L.h - 1);
-    gx = min(max(gx, 0), L.w - 1);
-    sin_[y * PW + x] = __ldg(img + (size_t)gy * L.pitch + gx);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < (ORBX_BLUR_TH + 6) * ORBX_BLUR_TW; i += blockDim.x) {
-    int y = i / ORBX_BLUR_TW, x = i - y * ORBX_BLUR_TW;
-    const uint8_t* s = sin_ + y * PW + x;
-    int acc = 18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3];
-    sh[i] = (uint16_t)acc;
-  }
-  __syncthreads();
-  uint8_t* out = L.blur + (size_t)blockIdx.y * L.imgStride;
-  for (int i = threadIdx.x; i < ORBX_BLUR_TH * (ORBX_BLUR_TW / 4); i += blockDim.x) {
-    int y = i / (ORBX_BLUR_TW / 4), x = (i - y * (ORBX_BLUR_TW / 4)) * 4;
-    if (y0 + y >= L.h || x0 + x >= L.w) continue;
-    uint32_t o = 0;
+  uint8_t* out = L.blur + (size_t)blockIdx.y * L.blurStride;
+  const int y1 = min(y0 + BLUR_STRIP, L.h);
+  int h[7][4];   // horizontal sums of rows y-3..y+3 (statically indexed: the row loop is unrolled by 7)
+  // prologue: rows y0-3 .. y0+2
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint16_t* s = sh + y * ORBX_BLUR_TW + x + k;
-      uint32_t acc = 18u * (s[0] + s[6 * ORBX_BLUR_TW]) + 34u * (s[ORBX_BLUR_TW] + s[5 * ORBX_BLUR_TW]) +
-                     48u * (s[2 * ORBX_BLUR_TW] + s[4 * ORBX_BLUR_TW]) + 56u * s[3 * ORBX_BLUR_TW];
-      o |= ((acc + 32768u) >> 16) << (8 * k);
+  for (int r = 0; r < 6; ++r) {
+    const uint8_t* row = img + (size_t)reflect101(y0 - 3 + r, L.h) * L.pitch;
+    blur_hrow(blur_word(row, c - 1, L.w), blur_word(row, c, L.w), blur_word(row, c + 1, L.w), h[r]);
+  }
+  for (int yb = y0; yb < y1; yb += 7) {
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+      const int y = yb + u;
+      if (y < y1) {
+        // newest row y+3 goes to slot (6+u)%7; rows y-3..y+3 sit in slots (u+j)%7, j = 0..6
+        const uint8_t* row = img + (size_t)reflect101(y + 3, L.h) * L.pitch;
+        blur_hrow(blur_word(row, c - 1, L.w), blur_word(row, c, L.w), blur_word(row, c + 1, L.w), h[(6 + u) % 7]);
+        uint32_t o = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned acc = 18u * (unsigned)(h[u % 7][k] + h[(u + 6) % 7][k]) + 34u * (unsigned)(h[(u + 1) % 7][k] + h[(u + 5) % 7][k]) +
+                               48u * (unsigned)(h[(u + 2) % 7][k] + h[(u + 4) % 7][k]) + 56u * (unsigned)h[(u + 3) % 7][k];
+          o |= ((acc + 32768u) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(out + (size_t)y * L.blurPitch + 4 * c) = o;   // pitch padding absorbs the tail
+      }
     }
-    *reinterpret_cast<uint32_t*>(out + (size_t)(y0 + y) * L.pitch + x0 + x) = o;
   }
 }
 
@@ -652,7 +785,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ E
   const float factorPI = (float)(3.14159265358979323846 / 180.0);
   const float ang = __fmul_rn(angle, factorPI);
   const float a = (float)cos((double)ang), bsn = (float)sin((double)ang);
-  const uint8_t* bl = L.blur + (size_t)b * L.imgStride + (size_t)py * L.pitch + px;
+  const uint8_t* bl = L.blur + (size_t)b * L.blurStride + (size_t)py * L.blurPitch + px;
   int val = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -663,7 +796,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ E
     const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bsn)));
     const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bsn), __fmul_rn(y1, a)));
     const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, bsn)));
-    const int t0 = __ldg(bl + r0 * L.pitch + c0), t1 = __ldg(bl + r1 * L.pitch + c1);
+    const int t0 = __ldg(bl + r0 * L.blurPitch + c0), t1 = __ldg(bl + r1 * L.blurPitch + c1);
     val |= (t0 < t1) << k;
   }
   // --- output slot: non-lapping keypoints fill from the front, lapping ones from the back ---
@@ -689,7 +822,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ E
 // ------------------------------------------------------------------------------------
 // host-side launchers (called from orbx_extract.cu)
 // ------------------------------------------------------------------------------------
-size_t orbx_fast_smem_bytes(int fastTileBytes) { return (size_t)3 * fastTileBytes + 64; }
+size_t orbx_fast_smem_bytes(int fastTileBytes) { return (size_t)4 * fastTileBytes + 64 + 512; }
 size_t orbx_octree_smem_bytes(int nodeCap) {
   return (size_t)nodeCap * (2 * sizeof(short4) + sizeof(unsigned long long) + 4 * 2 + 16 + 4 * 4);
 }

@@ -270,7 +270,7 @@ __device__ bool ldlt6_solve(const double* Ain, const double* b, double* x) {
 // =====================================================================================
 // K11  PoseOptimization: one CTA per frame
 // =====================================================================================
-#define PO_NT 128
+#define PO_NT 256
 
 struct PoseOptArgs {
   const int* edgeOfs;     // [P+1] contiguous slices ...
@@ -287,7 +287,7 @@ struct PoseOptArgs {
   double* err;            // [Etot][3] scratch: residual of the last evaluated state
 };
 
-__global__ void __launch_bounds__(PO_NT) pose_opt_kernel(const PoseOptArgs A) {
+__global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A) {
   const int prob = blockIdx.x, tid = threadIdx.x;
   const int e0 = A.edgeStart ? A.edgeStart[prob] : A.edgeOfs[prob];
   const int E = A.edgeStart ? A.edgeCount[prob] : A.edgeOfs[prob + 1] - e0;

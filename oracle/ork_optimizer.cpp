@@ -347,7 +347,7 @@ struct PoseProblem {
       if (active[e]) edge_error(e, est, &err[3 * e]);
   }
   double robustChi2() const {
-    TreeAcc<1> acc(128);
+    TreeAcc<1> acc(256);
     for (int e = 0; e < E; ++e) {
       if (!active[e]) continue;
       const double c = chi2(e);
@@ -359,7 +359,7 @@ struct PoseProblem {
     return chi;
   }
   void buildSystem() {
-    TreeAcc<27> acc(128);   // 21 upper-triangle entries of H, then b
+    TreeAcc<27> acc(256);   // 21 upper-triangle entries of H, then b
     for (int e = 0; e < E; ++e) {
       if (!active[e]) continue;
       const double X[3] = {xw[3 * e], xw[3 * e + 1], xw[3 * e + 2]};
