@@ -209,15 +209,11 @@ __global__ void __launch_bounds__(256) stats_kernel(const TrackDev D) {
   }
 }
 
-struct orbx_tracker {
-  orbx_ctx* ctx = nullptr;
-  orbx_ext* ext = nullptr;
-  cudaStream_t st = nullptr;
-  int S = 0, cap = 0, nlevels = 0;
-  orbx_camera cam{};
-  float thFrame = 7.f, thMap = 1.f, nnMap = 0.8f;
+// One set of per-step device state.  The tracker owns two: in overlap mode step t runs on slot t%2, its
+// extraction + stereo stage on stream A and its matching + pose stage on stream B, so the latency-bound fp64
+// pose optimisation of step t overlaps the throughput-bound extraction of step t+1.
+struct TrackSlot {
   TrackDev D{};
-  std::vector<void*> allocs;
   orbx_keypoint* d_kps = nullptr;
   uint8_t* d_desc = nullptr;
   int *d_n = nullptr, *d_mono = nullptr;
@@ -225,10 +221,28 @@ struct orbx_tracker {
   StereoArgs* d_stereo = nullptr;
   SbpFrameArgs* d_sbpf = nullptr;
   SbpMapArgs* d_sbpm = nullptr;
-  float* d_scale = nullptr;
   double* d_scratch = nullptr;
   int* d_misc = nullptr;      // per-frame candidate totals / error flags
+  cudaEvent_t evA = nullptr, evB = nullptr;
+  bool usedB = false;
+};
+
+struct orbx_tracker {
+  orbx_ctx* ctx = nullptr;
+  orbx_ext* ext = nullptr;
+  cudaStream_t stA = nullptr, stB = nullptr;   // stB == stA unless overlap mode is on
+  cudaStream_t ownB = nullptr;
+  int S = 0, cap = 0, nlevels = 0;
+  orbx_camera cam{};
+  float thFrame = 7.f, thMap = 1.f, nnMap = 0.8f;
+  TrackSlot slot[2];
+  int nslots = 1;
+  unsigned long long stepCount = 0;
+  std::vector<void*> allocs;
+  float* d_scale = nullptr;
   uint8_t* d_imgs = nullptr;  // staging for the host-pointer entry point
+  float *d_hposeIn = nullptr, *d_hposeOut = nullptr;
+  int* d_hstats = nullptr;
   uint8_t* h_imgs = nullptr;
   float* h_pose = nullptr;
   int* h_stats = nullptr;
@@ -247,52 +261,20 @@ static T* talloc(orbx_tracker* t, size_t count) {
   return (T*)p;
 }
 
-extern "C" {
-
-void orbx_tracker_destroy(orbx_tracker* t) {
-  if (!t) return;
-  cudaSetDevice(t->ctx->device);
-  cudaStreamSynchronize(t->st);
-  for (void* p : t->allocs) cudaFree(p);
-  if (t->h_imgs) cudaFreeHost(t->h_imgs);
-  if (t->h_pose) cudaFreeHost(t->h_pose);
-  if (t->h_stats) cudaFreeHost(t->h_stats);
-  for (int i = 0; i <= ORBX_TRACK_STAGES; ++i)
-    if (t->ev[i]) cudaEventDestroy(t->ev[i]);
-  delete t;
-}
-
-orbx_tracker* orbx_tracker_create(orbx_ctx* ctx, orbx_ext* ext, int S, const orbx_camera* cam, float th_frame, float th_map,
-                                  float nnratio_map) {
-  if (!ctx || !ext || S < 1 || !cam || !(cam->b > 0)) {
-    orbx_set_error("orbx_tracker_create: invalid argument");
-    return nullptr;
-  }
-  if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
-  orbx_tracker* t = new orbx_tracker();
-  t->ctx = ctx;
-  t->ext = ext;
-  t->st = (cudaStream_t)orbx_extractor_stream(ext);
-  t->S = S;
-  t->cap = orbx_extractor_max_keypoints(ext);
-  t->nlevels = orbx_extractor_levels(ext);
-  t->cam = *cam;
-  t->thFrame = th_frame;
-  t->thMap = th_map;
-  t->nnMap = nnratio_map;
-  const size_t SC = (size_t)S * t->cap;
-  TrackDev& D = t->D;
+static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float thFrame, float thMap, float nnMap) {
+  const int S = t->S, cap = t->cap;
+  const size_t SC = (size_t)S * cap;
+  const orbx_camera* cam = &t->cam;
+  TrackDev& D = K.D;
   D.S = S;
-  D.cap = t->cap;
+  D.cap = cap;
   D.fx = cam->fx; D.fy = cam->fy; D.cx = cam->cx; D.cy = cam->cy; D.bf = cam->bf;
-  float sc[ORBX_MAX_LEVELS], isg[ORBX_MAX_LEVELS];
-  orbx_extractor_scale_tables(ext, sc, nullptr, nullptr, isg);
   for (int l = 0; l < t->nlevels; ++l) D.invSigma2[l] = isg[l];
-  t->d_kps = talloc<orbx_keypoint>(t, 2 * SC);
-  t->d_desc = talloc<uint8_t>(t, 2 * SC * 32);
-  t->d_n = talloc<int>(t, 2 * S);
-  t->d_mono = talloc<int>(t, 2 * S);
-  D.kps = t->d_kps; D.desc = t->d_desc; D.n = t->d_n;
+  K.d_kps = talloc<orbx_keypoint>(t, 2 * SC);
+  K.d_desc = talloc<uint8_t>(t, 2 * SC * 32);
+  K.d_n = talloc<int>(t, 2 * S);
+  K.d_mono = talloc<int>(t, 2 * S);
+  D.kps = K.d_kps; D.desc = K.d_desc; D.n = K.d_n;
   D.uright = talloc<float>(t, SC); D.depth = talloc<float>(t, SC);
   D.mpFlags = talloc<uint8_t>(t, SC); D.lastFlags = talloc<uint8_t>(t, SC); D.xw = talloc<float>(t, 3 * SC);
   D.octave = talloc<int>(t, SC); D.angle = talloc<float>(t, SC);
@@ -307,101 +289,189 @@ orbx_tracker* orbx_tracker_create(orbx_ctx* ctx, orbx_ext* ext, int S, const orb
   D.level = talloc<int>(t, SC); D.bestIdx = talloc<int>(t, SC); D.nm2 = talloc<int>(t, S); D.kpMp = talloc<int>(t, SC);
   D.Ttrue = talloc<float>(t, 16 * S); D.Tprior = talloc<float>(t, 16 * S); D.T1 = talloc<float>(t, 16 * S); D.T2 = talloc<float>(t, 16 * S);
   D.stats = talloc<int>(t, ORBX_TRACK_STATS * S);
-  t->d_frames = talloc<FrameDev>(t, S);
-  t->d_stereo = talloc<StereoArgs>(t, S);
-  t->d_sbpf = talloc<SbpFrameArgs>(t, S);
-  t->d_sbpm = talloc<SbpMapArgs>(t, S);
-  t->d_scale = talloc<float>(t, ORBX_MAX_LEVELS);
-  t->d_scratch = talloc<double>(t, 3 * SC);
-  t->d_misc = talloc<int>(t, 8 * S);
+  K.d_frames = talloc<FrameDev>(t, S);
+  K.d_stereo = talloc<StereoArgs>(t, S);
+  K.d_sbpf = talloc<SbpFrameArgs>(t, S);
+  K.d_sbpm = talloc<SbpMapArgs>(t, S);
+  K.d_scratch = talloc<double>(t, 3 * SC);
+  K.d_misc = talloc<int>(t, 8 * S);
   int* cellStart = talloc<int>(t, (size_t)S * (ORBX_NCELLS + 1));
   int* cellIdx = talloc<int>(t, SC);
-  const int candCap = t->cap * 96;
+  const int candCap = cap * 96;
   uint32_t* cand = talloc<uint32_t>(t, (size_t)S * candCap);
   int* candOfs = talloc<int>(t, SC);
   int* candCnt = talloc<int>(t, SC);
-  if (!cand || !candCnt || !D.stats || !t->d_scratch) {
-    orbx_set_error("orbx_tracker_create: device allocation failed");
-    orbx_tracker_destroy(t);
-    return nullptr;
-  }
-  cudaMemcpy(t->d_scale, sc, sizeof(float) * t->nlevels, cudaMemcpyHostToDevice);
+  if (!cand || !candCnt || !D.stats || !K.d_scratch || !K.d_misc) return false;
+  if (cudaEventCreateWithFlags(&K.evA, cudaEventDisableTiming) != cudaSuccess) return false;
+  if (cudaEventCreateWithFlags(&K.evB, cudaEventDisableTiming) != cudaSuccess) return false;
   // static parts of the per-frame argument blocks
   std::vector<FrameDev> F(S);
   std::vector<SbpFrameArgs> AF(S);
   std::vector<SbpMapArgs> AM(S);
   for (int s = 0; s < S; ++s) {
-    const size_t o = (size_t)s * t->cap;
+    const size_t o = (size_t)s * cap;
     F[s].n = 0;
-    F[s].nDev = t->d_n + 2 * s;
-    F[s].kps = t->d_kps + (size_t)(2 * s) * t->cap;
-    F[s].desc = t->d_desc + (size_t)(2 * s) * t->cap * 32;
+    F[s].nDev = K.d_n + 2 * s;
+    F[s].kps = K.d_kps + (size_t)(2 * s) * cap;
+    F[s].desc = K.d_desc + (size_t)(2 * s) * cap * 32;
     F[s].uright = D.uright + o;
     F[s].cellStart = cellStart + (size_t)s * (ORBX_NCELLS + 1);
     F[s].cellIdx = cellIdx + o;
-    F[s].minX = F[s].minY = 0; F[s].maxX = F[s].maxY = 1; F[s].wInv = F[s].hInv = 1;   // set per step (image size)
+    F[s].minX = F[s].minY = 0; F[s].maxX = F[s].maxY = 1; F[s].wInv = F[s].hInv = 1;   // set per image size
     SbpFrameArgs& a = AF[s];
-    a.nq = 0; a.nqDev = t->d_n + 2 * s; a.TcDev = D.Tprior + 16 * s;
+    a.nq = 0; a.nqDev = K.d_n + 2 * s; a.TcDev = D.Tprior + 16 * s;
     a.flags = D.lastFlags + o; a.xw = D.xw + 3 * o; a.octave = D.octave + o; a.angle = D.angle + o;
     a.mpDesc = F[s].desc;
     a.fx = cam->fx; a.fy = cam->fy; a.cx = cam->cx; a.cy = cam->cy; a.bf = cam->bf;
-    a.th = th_frame; a.mode = 0; a.checkOri = 1; a.scaleFactors = t->d_scale;
+    a.th = thFrame; a.mode = 0; a.checkOri = 1; a.scaleFactors = t->d_scale;
     a.candOfs = candOfs + o; a.candCnt = candCnt + o; a.cand = cand + (size_t)s * candCap; a.candCap = candCap;
-    a.total = t->d_misc + 8 * s; a.err = t->d_misc + 8 * s + 1;
+    a.total = K.d_misc + 8 * s; a.err = K.d_misc + 8 * s + 1;
     a.curBlocked = nullptr; a.matchIdx = D.matchIdx + o; a.kept = D.kept + o; a.curMatch = D.curMatch + o; a.nmatches = D.nm1 + s;
     SbpMapArgs& m = AM[s];
-    m.nq = 0; m.nqDev = t->d_n + 2 * s;
+    m.nq = 0; m.nqDev = K.d_n + 2 * s;
     m.projX = D.projX + o; m.projY = D.projY + o; m.projXR = D.projXR + o; m.viewCos = D.viewCos + o; m.level = D.level + o;
-    m.mpDesc = F[s].desc; m.flags = D.mapFlags + o; m.th = th_map; m.nnratio = nnratio_map; m.scaleFactors = t->d_scale;
+    m.mpDesc = F[s].desc; m.flags = D.mapFlags + o; m.th = thMap; m.nnratio = nnMap; m.scaleFactors = t->d_scale;
     m.candOfs = candOfs + o; m.candCnt = candCnt + o; m.cand = cand + (size_t)s * candCap; m.candCap = candCap;
-    m.total = t->d_misc + 8 * s + 2; m.err = t->d_misc + 8 * s + 3;
+    m.total = K.d_misc + 8 * s + 2; m.err = K.d_misc + 8 * s + 3;
     m.kpBlocked = D.blocked + o; m.bestIdx = D.bestIdx + o; m.nmatches = D.nm2 + s;
   }
-  cudaMemcpy(t->d_frames, F.data(), sizeof(FrameDev) * S, cudaMemcpyHostToDevice);
-  cudaMemcpy(t->d_sbpf, AF.data(), sizeof(SbpFrameArgs) * S, cudaMemcpyHostToDevice);
-  cudaMemcpy(t->d_sbpm, AM.data(), sizeof(SbpMapArgs) * S, cudaMemcpyHostToDevice);
-  if (cudaGetLastError() != cudaSuccess) {
-    orbx_set_error("orbx_tracker_create: setup copies failed");
+  cudaMemcpy(K.d_frames, F.data(), sizeof(FrameDev) * S, cudaMemcpyHostToDevice);
+  cudaMemcpy(K.d_sbpf, AF.data(), sizeof(SbpFrameArgs) * S, cudaMemcpyHostToDevice);
+  cudaMemcpy(K.d_sbpm, AM.data(), sizeof(SbpMapArgs) * S, cudaMemcpyHostToDevice);
+  return cudaGetLastError() == cudaSuccess;
+}
+
+extern "C" {
+
+void orbx_tracker_destroy(orbx_tracker* t) {
+  if (!t) return;
+  cudaSetDevice(t->ctx->device);
+  cudaStreamSynchronize(t->stA);
+  if (t->ownB) cudaStreamSynchronize(t->ownB);
+  for (void* p : t->allocs) cudaFree(p);
+  if (t->h_imgs) cudaFreeHost(t->h_imgs);
+  if (t->h_pose) cudaFreeHost(t->h_pose);
+  if (t->h_stats) cudaFreeHost(t->h_stats);
+  for (int i = 0; i <= ORBX_TRACK_STAGES; ++i)
+    if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+  for (int k = 0; k < 2; ++k) {
+    if (t->slot[k].evA) cudaEventDestroy(t->slot[k].evA);
+    if (t->slot[k].evB) cudaEventDestroy(t->slot[k].evB);
+  }
+  if (t->ownB) cudaStreamDestroy(t->ownB);
+  delete t;
+}
+
+orbx_tracker* orbx_tracker_create(orbx_ctx* ctx, orbx_ext* ext, int S, const orbx_camera* cam, float th_frame, float th_map,
+                                  float nnratio_map) {
+  if (!ctx || !ext || S < 1 || !cam || !(cam->b > 0)) {
+    orbx_set_error("orbx_tracker_create: invalid argument");
+    return nullptr;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+  orbx_tracker* t = new orbx_tracker();
+  t->ctx = ctx;
+  t->ext = ext;
+  t->stA = t->stB = (cudaStream_t)orbx_extractor_stream(ext);
+  t->S = S;
+  t->cap = orbx_extractor_max_keypoints(ext);
+  t->nlevels = orbx_extractor_levels(ext);
+  t->cam = *cam;
+  t->thFrame = th_frame;
+  t->thMap = th_map;
+  t->nnMap = nnratio_map;
+  float sc[ORBX_MAX_LEVELS], isg[ORBX_MAX_LEVELS];
+  orbx_extractor_scale_tables(ext, sc, nullptr, nullptr, isg);
+  t->d_scale = talloc<float>(t, ORBX_MAX_LEVELS);
+  if (!t->d_scale || cudaMemcpy(t->d_scale, sc, sizeof(float) * t->nlevels, cudaMemcpyHostToDevice) != cudaSuccess ||
+      !slot_alloc(t, t->slot[0], isg, th_frame, th_map, nnratio_map)) {
+    orbx_set_error("orbx_tracker_create: device allocation failed");
     orbx_tracker_destroy(t);
     return nullptr;
   }
   return t;
 }
 
-// image-size dependent argument blocks (stereo pyramids, grid bounds): rebuilt when (w,h) changes
+int orbx_tracker_set_overlap(orbx_tracker* t, int enable) {
+  if (!t) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  ORBX_CUDA(cudaStreamSynchronize(t->stA));
+  if (t->ownB) ORBX_CUDA(cudaStreamSynchronize(t->ownB));
+  if (enable) {
+    if (!t->ownB) {
+      // stage B is light and latency-bound: give its stream the highest priority so its thread blocks take any
+      // SM slot that frees up while the (throughput-bound) extraction grids of the next step drain
+      int lo = 0, hi = 0;
+      ORBX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      ORBX_CUDA(cudaStreamCreateWithPriority(&t->ownB, cudaStreamNonBlocking, hi));
+    }
+    if (t->nslots < 2) {
+      float sc[ORBX_MAX_LEVELS], isg[ORBX_MAX_LEVELS];
+      orbx_extractor_scale_tables(t->ext, sc, nullptr, nullptr, isg);
+      if (!slot_alloc(t, t->slot[1], isg, t->thFrame, t->thMap, t->nnMap)) {
+        orbx_set_error("orbx_tracker_set_overlap: device allocation failed");
+        return ORBX_ECUDA;
+      }
+      t->nslots = 2;
+      t->argW = -1;   // rebind both slots' geometry
+    }
+    t->stB = t->ownB;
+  } else {
+    t->stB = t->stA;
+  }
+  t->slot[0].usedB = t->slot[1].usedB = false;
+  return ORBX_OK;
+}
+
+void* orbx_tracker_result_stream(orbx_tracker* t) { return t ? (void*)t->stB : nullptr; }
+
+int orbx_tracker_synchronize(orbx_tracker* t) {
+  if (!t) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  ORBX_CUDA(cudaStreamSynchronize(t->stA));
+  if (t->stB != t->stA) ORBX_CUDA(cudaStreamSynchronize(t->stB));
+  return ORBX_OK;
+}
+
+// image-size dependent argument blocks (stereo pyramids, grid bounds): rebuilt when (w,h) or the input binding changes
 static int tracker_bind_geometry(orbx_tracker* t, int w, int h) {
   const int S = t->S;
-  std::vector<StereoArgs> A(S);
-  std::vector<FrameDev> F(S);
-  ORBX_CUDA(cudaMemcpy(F.data(), t->d_frames, sizeof(FrameDev) * S, cudaMemcpyDeviceToHost));
-  for (int s = 0; s < S; ++s) {
-    StereoArgs& a = A[s];
-    int nl = 0, nl2 = 0, w2[ORBX_MAX_LEVELS], h2[ORBX_MAX_LEVELS];
-    float sc2[ORBX_MAX_LEVELS], isc2[ORBX_MAX_LEVELS];
-    cudaStream_t st1, st2;
-    int rc = orbx_ext_pyramid_view(t->ext, 2 * s, &nl, a.pyrL, a.lw, a.lh, a.pitchL, a.scale, a.invScale, &st1);
-    if (rc != ORBX_OK) return rc;
-    rc = orbx_ext_pyramid_view(t->ext, 2 * s + 1, &nl2, a.pyrR, w2, h2, a.pitchR, sc2, isc2, &st2);
-    if (rc != ORBX_OK) return rc;
-    a.nlevels = nl;
-    a.nL = a.nR = 0;
-    a.nLDev = t->d_n + 2 * s;
-    a.nRDev = t->d_n + 2 * s + 1;
-    a.kpL = t->d_kps + (size_t)(2 * s) * t->cap;
-    a.kpR = t->d_kps + (size_t)(2 * s + 1) * t->cap;
-    a.descL = t->d_desc + (size_t)(2 * s) * t->cap * 32;
-    a.descR = t->d_desc + (size_t)(2 * s + 1) * t->cap * 32;
-    a.bf = t->cam.bf;
-    a.b = t->cam.b;
-    a.uright = t->D.uright + (size_t)s * t->cap;
-    a.depth = t->D.depth + (size_t)s * t->cap;
-    a.sad = t->D.kpEdge + (size_t)s * t->cap;   // scratch reuse: kpEdge is rewritten later in the step
-    F[s].minX = 0.f; F[s].minY = 0.f; F[s].maxX = (float)w; F[s].maxY = (float)h;   // rectified stereo: image bounds (src/Frame.cc:147-152)
-    F[s].wInv = (float)ORBX_GRID_COLS / (F[s].maxX - F[s].minX);
-    F[s].hInv = (float)ORBX_GRID_ROWS / (F[s].maxY - F[s].minY);
+  ORBX_CUDA(cudaStreamSynchronize(t->stA));
+  if (t->stB != t->stA) ORBX_CUDA(cudaStreamSynchronize(t->stB));
+  for (int k = 0; k < t->nslots; ++k) {
+    TrackSlot& K = t->slot[k];
+    std::vector<StereoArgs> A(S);
+    std::vector<FrameDev> F(S);
+    ORBX_CUDA(cudaMemcpy(F.data(), K.d_frames, sizeof(FrameDev) * S, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < S; ++s) {
+      StereoArgs& a = A[s];
+      int nl = 0, nl2 = 0, w2[ORBX_MAX_LEVELS], h2[ORBX_MAX_LEVELS];
+      float sc2[ORBX_MAX_LEVELS], isc2[ORBX_MAX_LEVELS];
+      cudaStream_t st1, st2;
+      int rc = orbx_ext_pyramid_view(t->ext, 2 * s, &nl, a.pyrL, a.lw, a.lh, a.pitchL, a.scale, a.invScale, &st1);
+      if (rc != ORBX_OK) return rc;
+      rc = orbx_ext_pyramid_view(t->ext, 2 * s + 1, &nl2, a.pyrR, w2, h2, a.pitchR, sc2, isc2, &st2);
+      if (rc != ORBX_OK) return rc;
+      a.nlevels = nl;
+      a.nL = a.nR = 0;
+      a.nLDev = K.d_n + 2 * s;
+      a.nRDev = K.d_n + 2 * s + 1;
+      a.kpL = K.d_kps + (size_t)(2 * s) * t->cap;
+      a.kpR = K.d_kps + (size_t)(2 * s + 1) * t->cap;
+      a.descL = K.d_desc + (size_t)(2 * s) * t->cap * 32;
+      a.descR = K.d_desc + (size_t)(2 * s + 1) * t->cap * 32;
+      a.bf = t->cam.bf;
+      a.b = t->cam.b;
+      a.uright = K.D.uright + (size_t)s * t->cap;
+      a.depth = K.D.depth + (size_t)s * t->cap;
+      a.sad = K.D.kpEdge + (size_t)s * t->cap;   // scratch reuse: kpEdge is rewritten later in the step
+      F[s].minX = 0.f; F[s].minY = 0.f; F[s].maxX = (float)w; F[s].maxY = (float)h;   // rectified stereo: image bounds (src/Frame.cc:147-152)
+      F[s].wInv = (float)ORBX_GRID_COLS / (F[s].maxX - F[s].minX);
+      F[s].hInv = (float)ORBX_GRID_ROWS / (F[s].maxY - F[s].minY);
+    }
+    ORBX_CUDA(cudaMemcpy(K.d_stereo, A.data(), sizeof(StereoArgs) * S, cudaMemcpyHostToDevice));
+    ORBX_CUDA(cudaMemcpy(K.d_frames, F.data(), sizeof(FrameDev) * S, cudaMemcpyHostToDevice));
   }
-  ORBX_CUDA(cudaMemcpy(t->d_stereo, A.data(), sizeof(StereoArgs) * S, cudaMemcpyHostToDevice));
-  ORBX_CUDA(cudaMemcpy(t->d_frames, F.data(), sizeof(FrameDev) * S, cudaMemcpyHostToDevice));
   t->argW = w;
   t->argH = h;
   return ORBX_OK;
@@ -411,14 +481,18 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
                              const float* d_Tcw_prior, float* d_Tcw_out, int32_t* d_stats) {
   if (!t || !d_imgs || !d_Tcw_true || !d_Tcw_prior || !d_Tcw_out) return ORBX_EINVAL;
   ORBX_CUDA(cudaSetDevice(t->ctx->device));
-  cudaStream_t st = t->st;
+  cudaStream_t sa = t->stA, sb = t->stB;
+  const bool overlap = sb != sa;
   const int S = t->S, cap = t->cap;
-  TrackDev& D = t->D;
+  TrackSlot& K = t->slot[overlap ? (int)(t->stepCount & 1) : 0];
+  TrackDev& D = K.D;
   cudaEvent_t* ev = t->profiling ? t->ev : nullptr;
-#define TRK_EV(i) do { if (ev) ORBX_CUDA(cudaEventRecord(ev[i], st)); } while (0)
-  TRK_EV(0);
+#define TRK_EV(i, st) do { if (ev) ORBX_CUDA(cudaEventRecord(ev[i], st)); } while (0)
+  // the slot's buffers are free once stage B of the step that last used them has finished
+  if (overlap && K.usedB) ORBX_CUDA(cudaStreamWaitEvent(sa, K.evB, 0));
+  TRK_EV(0, sa);
   // 1. Frame::Frame(stereo): ORB extraction of the 2*S images (src/Frame.cc:111-114)
-  int rc = orbx_extract_batch_device(t->ext, 2 * S, d_imgs, w, h, stride, 0, 0, t->d_kps, t->d_desc, cap, t->d_n, t->d_mono);
+  int rc = orbx_extract_batch_device(t->ext, 2 * S, d_imgs, w, h, stride, 0, 0, K.d_kps, K.d_desc, cap, K.d_n, K.d_mono);
   if (rc != ORBX_OK) return rc;
   if (w != t->argW || h != t->argH || stride != t->argStride || d_imgs != t->argImgs) {   // level 0 aliases the input
     rc = tracker_bind_geometry(t, w, h);
@@ -426,57 +500,66 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
     t->argStride = stride;
     t->argImgs = d_imgs;
   }
-  TRK_EV(1);
-  ORBX_CUDA(cudaMemcpyAsync(D.Ttrue, d_Tcw_true, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, st));
-  ORBX_CUDA(cudaMemcpyAsync(D.Tprior, d_Tcw_prior, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, st));
-  ORBX_CUDA(cudaMemcpyAsync(D.T1, d_Tcw_prior, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, st));
-  ORBX_CUDA(cudaMemsetAsync(t->d_misc, 0, sizeof(int) * 8 * S, st));
-  ORBX_CUDA(cudaMemsetAsync(D.mpTaken, 0, (size_t)S * cap, st));
+  TRK_EV(1, sa);
+  ORBX_CUDA(cudaMemcpyAsync(D.Ttrue, d_Tcw_true, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sa));
+  ORBX_CUDA(cudaMemcpyAsync(D.Tprior, d_Tcw_prior, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sa));
+  ORBX_CUDA(cudaMemcpyAsync(D.T1, d_Tcw_prior, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sa));
+  ORBX_CUDA(cudaMemsetAsync(K.d_misc, 0, sizeof(int) * 8 * S, sa));
+  ORBX_CUDA(cudaMemsetAsync(D.mpTaken, 0, (size_t)S * cap, sa));
   // 2. ComputeStereoMatches (src/Frame.cc:132)
-  rc = orbx_launch_stereo_batch(t->ctx, st, t->d_stereo, S, cap);
+  rc = orbx_launch_stereo_batch(t->ctx, sa, K.d_stereo, S, cap);
   if (rc != ORBX_OK) return rc;
-  TRK_EV(2);
+  if (overlap) {
+    ORBX_CUDA(cudaEventRecord(K.evA, sa));
+    ORBX_CUDA(cudaStreamWaitEvent(sb, K.evA, 0));
+  }
+  TRK_EV(2, sb);
   // 3. synthetic map + AssignFeaturesToGrid + SearchByProjection(Cur, Last, th) (src/Tracking.cc:2370)
   const dim3 gk(div_up(cap, 128), S);
-  backproject_kernel<<<gk, 128, 0, st>>>(D);
+  backproject_kernel<<<gk, 128, 0, sb>>>(D);
   ORBX_LAUNCH(t->ctx);
-  rc = orbx_launch_grid_build(t->ctx, st, t->d_frames, S);
+  rc = orbx_launch_grid_build(t->ctx, sb, K.d_frames, S);
   if (rc != ORBX_OK) return rc;
-  rc = orbx_launch_sbp_frame_batch(t->ctx, st, t->d_frames, t->d_sbpf, S, cap, cap);
+  rc = orbx_launch_sbp_frame_batch(t->ctx, sb, K.d_frames, K.d_sbpf, S, cap, cap);
   if (rc != ORBX_OK) return rc;
-  TRK_EV(3);
+  TRK_EV(3, sb);
   // 4. PoseOptimization (src/Tracking.cc:2395)
-  gather_edges_kernel<<<S, 256, 0, st>>>(D, 0);
+  gather_edges_kernel<<<S, 256, 0, sb>>>(D, 0);
   ORBX_LAUNCH(t->ctx);
-  rc = orbx_launch_pose_opt_slices(t->ctx, st, S, D.estart, D.ecount, D.exw, D.eobs, D.eisg, &t->cam, D.T1, D.eoutlier, D.ninl,
-                                   D.iters, t->d_scratch);
+  rc = orbx_launch_pose_opt_slices(t->ctx, sb, S, D.estart, D.ecount, D.exw, D.eobs, D.eisg, &t->cam, D.T1, D.eoutlier, D.ninl,
+                                   D.iters, K.d_scratch);
   if (rc != ORBX_OK) return rc;
-  TRK_EV(4);
+  TRK_EV(4, sb);
   // 5. TrackLocalMap: SearchLocalPoints + SearchByProjection(F, local points, th) (src/Tracking.cc:2449,:2964)
-  after_pose1_kernel<<<gk, 128, 0, st>>>(D);
+  after_pose1_kernel<<<gk, 128, 0, sb>>>(D);
   ORBX_LAUNCH(t->ctx);
-  project_map_kernel<<<gk, 128, 0, st>>>(D, 0.f, 0.f, (float)w, (float)h);
+  project_map_kernel<<<gk, 128, 0, sb>>>(D, 0.f, 0.f, (float)w, (float)h);
   ORBX_LAUNCH(t->ctx);
-  rc = orbx_launch_sbp_map_batch(t->ctx, st, t->d_frames, t->d_sbpm, S, cap, cap);
+  rc = orbx_launch_sbp_map_batch(t->ctx, sb, K.d_frames, K.d_sbpm, S, cap, cap);
   if (rc != ORBX_OK) return rc;
-  TRK_EV(5);
+  TRK_EV(5, sb);
   // 6. PoseOptimization (src/Tracking.cc:2468), starting from the pose of step 4
-  merge_matches_kernel<<<S, 256, 0, st>>>(D);
+  merge_matches_kernel<<<S, 256, 0, sb>>>(D);
   ORBX_LAUNCH(t->ctx);
-  gather_edges_kernel<<<S, 256, 0, st>>>(D, 1);
+  gather_edges_kernel<<<S, 256, 0, sb>>>(D, 1);
   ORBX_LAUNCH(t->ctx);
-  ORBX_CUDA(cudaMemcpyAsync(D.T2, D.T1, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, st));
-  // ninl/iters of the second optimisation land in the odd slots
-  rc = orbx_launch_pose_opt_slices(t->ctx, st, S, D.estart, D.ecount, D.exw, D.eobs, D.eisg, &t->cam, D.T2, D.eoutlier,
-                                   D.ninl + S, D.iters + 4 * S, t->d_scratch);
+  ORBX_CUDA(cudaMemcpyAsync(D.T2, D.T1, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sb));
+  // inliers / iterations of the second optimisation land in the second halves of ninl / iters
+  rc = orbx_launch_pose_opt_slices(t->ctx, sb, S, D.estart, D.ecount, D.exw, D.eobs, D.eisg, &t->cam, D.T2, D.eoutlier,
+                                   D.ninl + S, D.iters + 4 * S, K.d_scratch);
   if (rc != ORBX_OK) return rc;
-  TRK_EV(6);
-  ORBX_CUDA(cudaMemcpyAsync(d_Tcw_out, D.T2, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, st));
+  TRK_EV(6, sb);
+  ORBX_CUDA(cudaMemcpyAsync(d_Tcw_out, D.T2, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sb));
   if (d_stats) {
-    stats_kernel<<<S, 256, 0, st>>>(D);
+    stats_kernel<<<S, 256, 0, sb>>>(D);
     ORBX_LAUNCH(t->ctx);
-    ORBX_CUDA(cudaMemcpyAsync(d_stats, D.stats, sizeof(int) * ORBX_TRACK_STATS * S, cudaMemcpyDeviceToDevice, st));
+    ORBX_CUDA(cudaMemcpyAsync(d_stats, D.stats, sizeof(int) * ORBX_TRACK_STATS * S, cudaMemcpyDeviceToDevice, sb));
   }
+  if (overlap) {
+    ORBX_CUDA(cudaEventRecord(K.evB, sb));
+    K.usedB = true;
+  }
+  t->stepCount++;
   t->profiled = t->profiling;
   ORBX_CUDA(cudaGetLastError());
   return ORBX_OK;
@@ -493,25 +576,24 @@ int orbx_tracker_step(orbx_tracker* t, const uint8_t* const* imgs, int w, int h,
     ORBX_CUDA(cudaMallocHost(&t->h_pose, sizeof(float) * 16 * S * 3));
     ORBX_CUDA(cudaMallocHost(&t->h_stats, sizeof(int) * ORBX_TRACK_STATS * S));
     t->d_imgs = talloc<uint8_t>(t, 2 * S * img);
-    if (!t->d_imgs) return ORBX_ECUDA;
+    t->d_hposeIn = talloc<float>(t, 32 * S);
+    t->d_hposeOut = talloc<float>(t, 16 * S);
+    t->d_hstats = talloc<int>(t, ORBX_TRACK_STATS * S);
+    if (!t->d_imgs || !t->d_hposeIn || !t->d_hposeOut || !t->d_hstats) return ORBX_ECUDA;
   }
   for (int b = 0; b < 2 * S; ++b)
     for (int y = 0; y < h; ++y) memcpy(t->h_imgs + b * img + (size_t)y * w, imgs[b] + (size_t)y * stride, w);
   memcpy(t->h_pose, Tcw_true, sizeof(float) * 16 * S);
   memcpy(t->h_pose + 16 * S, Tcw_prior, sizeof(float) * 16 * S);
-  cudaStream_t st = t->st;
-  ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, t->h_imgs, 2 * S * img, cudaMemcpyHostToDevice, st));
-  // poses ride in T2 / a scratch region of exw (both overwritten later in the step, after they were consumed)
-  float* d_true = t->D.T2;
-  float* d_prior = reinterpret_cast<float*>(t->D.eobs);
-  ORBX_CUDA(cudaMemcpyAsync(d_true, t->h_pose, sizeof(float) * 16 * S, cudaMemcpyHostToDevice, st));
-  ORBX_CUDA(cudaMemcpyAsync(d_prior, t->h_pose + 16 * S, sizeof(float) * 16 * S, cudaMemcpyHostToDevice, st));
-  float* d_out = t->D.Tprior;   // D.Tprior is consumed before the final copy
-  int rc = orbx_tracker_step_device(t, t->d_imgs, w, h, w, d_true, d_prior, d_out, t->D.stats);
+  cudaStream_t sa = t->stA, sb = t->stB;
+  ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, t->h_imgs, 2 * S * img, cudaMemcpyHostToDevice, sa));
+  ORBX_CUDA(cudaMemcpyAsync(t->d_hposeIn, t->h_pose, sizeof(float) * 32 * S, cudaMemcpyHostToDevice, sa));
+  int rc = orbx_tracker_step_device(t, t->d_imgs, w, h, w, t->d_hposeIn, t->d_hposeIn + 16 * S, t->d_hposeOut, t->d_hstats);
   if (rc != ORBX_OK) return rc;
-  ORBX_CUDA(cudaMemcpyAsync(t->h_pose + 32 * S, d_out, sizeof(float) * 16 * S, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(t->h_stats, t->D.stats, sizeof(int) * ORBX_TRACK_STATS * S, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaStreamSynchronize(st));
+  ORBX_CUDA(cudaMemcpyAsync(t->h_pose + 32 * S, t->d_hposeOut, sizeof(float) * 16 * S, cudaMemcpyDeviceToHost, sb));
+  ORBX_CUDA(cudaMemcpyAsync(t->h_stats, t->d_hstats, sizeof(int) * ORBX_TRACK_STATS * S, cudaMemcpyDeviceToHost, sb));
+  ORBX_CUDA(cudaStreamSynchronize(sb));
+  if (sb != sa) ORBX_CUDA(cudaStreamSynchronize(sa));
   memcpy(Tcw_out, t->h_pose + 32 * S, sizeof(float) * 16 * S);
   if (stats) memcpy(stats, t->h_stats, sizeof(int) * ORBX_TRACK_STATS * S);
   return ORBX_OK;

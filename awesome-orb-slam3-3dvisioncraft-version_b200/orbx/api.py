@@ -87,6 +87,10 @@ def load_library():
     L.orbx_tracker_destroy.argtypes = [vp]
     L.orbx_tracker_step_device.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
     L.orbx_tracker_step.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
+    L.orbx_tracker_set_overlap.argtypes = [vp, i]
+    L.orbx_tracker_result_stream.restype = vp
+    L.orbx_tracker_result_stream.argtypes = [vp]
+    L.orbx_tracker_synchronize.argtypes = [vp]
     L.orbx_tracker_set_profiling.argtypes = [vp, i]
     L.orbx_tracker_stage_ms.argtypes = [vp, vp]
     L.orbx_pyramid_level.argtypes = [vp, i, i, vp, i, vp, vp]
@@ -424,6 +428,16 @@ class Tracker:
     def step_device(self, d_imgs, w, h, stride, d_true, d_prior, d_out, d_stats):
         _check(load_library().orbx_tracker_step_device(self.h, d_imgs, w, h, stride, d_true, d_prior, d_out, d_stats),
                "orbx_tracker_step_device")
+
+    def set_overlap(self, on=True):
+        _check(load_library().orbx_tracker_set_overlap(self.h, int(on)), "orbx_tracker_set_overlap")
+
+    @property
+    def result_stream(self):
+        return load_library().orbx_tracker_result_stream(self.h)
+
+    def synchronize(self):
+        _check(load_library().orbx_tracker_synchronize(self.h), "orbx_tracker_synchronize")
 
     def set_profiling(self, on=True):
         _check(load_library().orbx_tracker_set_profiling(self.h, int(on)), "orbx_tracker_set_profiling")

@@ -301,6 +301,14 @@ int orbx_tracker_step_device(orbx_tracker *trk, const uint8_t *d_imgs, int w, in
 /* Same through HOST buffers: copies the 2*S images in, the S poses and stats out, synchronises. */
 int orbx_tracker_step(orbx_tracker *trk, const uint8_t *const *imgs, int w, int h, int stride,
                       const float *Tcw_true, const float *Tcw_prior, float *Tcw_out, int32_t *stats);
+/* Overlap mode: step t's extraction + stereo matching run on the extractor's stream and its matching +
+ * pose stages on a second stream, double-buffered, so the latency-bound fp64 optimisation of step t
+ * overlaps the throughput-bound extraction of step t+1 (frames of different steps are independent
+ * until Track() consumes them, exactly as Frame construction precedes Tracking::Track in the reference).
+ * Results of a step are complete on orbx_tracker_result_stream(); orbx_tracker_synchronize() waits for both. */
+int orbx_tracker_set_overlap(orbx_tracker *trk, int enable);
+void *orbx_tracker_result_stream(orbx_tracker *trk);
+int orbx_tracker_synchronize(orbx_tracker *trk);
 /* Per-stage device time of the last step (CUDA events on the stream), ORBX_TRACK_STAGES entries:
  * 0 extract, 1 stereo match, 2 search-by-projection (last frame), 3 pose optimisation #1,
  * 4 search-by-projection (local map), 5 pose optimisation #2. */

@@ -47,3 +47,29 @@ def test_tracker_chain_matches_oracle_chain(ctx, ork):
             assert st[2] > 300 and st[3] > 150 and st[6] > 150
     trk.close()
     ex.close()
+
+
+def test_tracker_overlap_mode_gives_identical_results(ctx, ork):
+    """Two-stream, double-buffered overlap mode is pure scheduling: same poses and statistics, step after step."""
+    import orbx
+    from orbx import synth
+    S = 2
+    cam = orbx.make_camera()
+    rng = np.random.default_rng(5)
+    imgsA, imgsB = [], []
+    for s in range(S):
+        L, R = synth.stereo_pair(60 + s)
+        imgsA += [L, R]
+        L, R = synth.stereo_pair(70 + s)
+        imgsB += [L, R]
+    Tt, Tp = _poses(rng, S)
+    ex = orbx.ORBextractor(ctx, max_batch=2 * S)
+    trk = orbx.Tracker(ctx, ex, S, cam)
+    ref = [trk.step(im, Tt, Tp) for im in (imgsA, imgsB, imgsA)]
+    trk.set_overlap(True)
+    got = [trk.step(im, Tt, Tp) for im in (imgsA, imgsB, imgsA, imgsB)]
+    for k in range(3):
+        assert np.array_equal(ref[k][0], got[k][0]) and np.array_equal(ref[k][1], got[k][1]), k
+    assert np.array_equal(got[3][0], got[1][0])
+    trk.close()
+    ex.close()
