@@ -142,8 +142,11 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
     LevelParams& L = P.lv[l];
     const LevelParams& S = P.lv[l - 1];
     const double sx = 1.0 / ((double)L.w / S.w), sy = 1.0 / ((double)L.h / S.h);
+    // packed tables: X[dx] = {xofs, a0, a1, 0}, padded to a multiple of 4 columns; Y[dy] = {y0, y1, b0, b1}
+    htab.resize(align_up(htab.size(), 8));            // 16-byte alignment for the vector loads
     L.tabX = (int)htab.size();
-    htab.resize(htab.size() + 3 * (size_t)L.w);
+    const int wpad = (int)align_up((size_t)L.w, 4);
+    htab.resize(htab.size() + 4 * (size_t)wpad, 0);
     int16_t* tx = htab.data() + L.tabX;
     for (int dx = 0; dx < L.w; ++dx) {
       float fx = (float)((dx + 0.5) * sx - 0.5);
@@ -151,9 +154,9 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
       fx -= s;
       if (s < 0) { fx = 0; s = 0; }
       if (s >= S.w - 1) { fx = 0; s = S.w - 1; }
-      tx[dx] = (int16_t)s;
-      tx[L.w + dx] = (int16_t)cv_round_f((1.f - fx) * 2048.f);
-      tx[2 * L.w + dx] = (int16_t)cv_round_f(fx * 2048.f);
+      tx[4 * dx] = (int16_t)s;
+      tx[4 * dx + 1] = (int16_t)cv_round_f((1.f - fx) * 2048.f);
+      tx[4 * dx + 2] = (int16_t)cv_round_f(fx * 2048.f);
     }
     L.tabY = (int)htab.size();
     htab.resize(htab.size() + 4 * (size_t)L.h);
@@ -162,10 +165,10 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
       float fy = (float)((dy + 0.5) * sy - 0.5);
       int s = cv_floor_d(fy);
       fy -= s;
-      ty[dy] = (int16_t)std::min(std::max(s, 0), S.h - 1);
-      ty[L.h + dy] = (int16_t)std::min(std::max(s + 1, 0), S.h - 1);
-      ty[2 * L.h + dy] = (int16_t)cv_round_f((1.f - fy) * 2048.f);
-      ty[3 * L.h + dy] = (int16_t)cv_round_f(fy * 2048.f);
+      ty[4 * dy] = (int16_t)std::min(std::max(s, 0), S.h - 1);
+      ty[4 * dy + 1] = (int16_t)std::min(std::max(s + 1, 0), S.h - 1);
+      ty[4 * dy + 2] = (int16_t)cv_round_f((1.f - fy) * 2048.f);
+      ty[4 * dy + 3] = (int16_t)cv_round_f(fy * 2048.f);
     }
   }
   if (htab.size() > e->tabElems) {
@@ -261,7 +264,7 @@ orbx_ext* orbx_extractor_create(orbx_ctx* ctx, int nfeatures, float scaleFactor,
     cand += (size_t)lw * lh * 3 / 10 + 64;
     const int nIni = std::max(1, (int)std::round((float)(lw - 32) / (float)(lh - 32)));
     sel += e->nFeat[l] + 4 * nIni + 8;
-    tab += 3 * (size_t)lw + 4 * (size_t)lh;
+    tab += 4 * ((size_t)lw + 4) + 4 * (size_t)lh + 16;
   }
   // smaller images than max may have a larger aspect-driven nIni; keep some slack
   sel += 16 * nlevels;

@@ -18,7 +18,8 @@ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9
 // =====================================================================================
 // K1  pyramid level l from level l-1: cv::resize(INTER_LINEAR) 8U fixed point.
 // grid (ceil(w/4/128), h, B), block 128; each thread produces 4 horizontally adjacent pixels.
-// tab layout per level: X: [xofs(w) | a0(w) | a1(w)]  Y: [y0(h) | y1(h) | b0(h) | b1(h)]  (int16)
+// Packed coefficient tables (int16 x 4 per destination column / row, one 8-byte load each):
+//   X[dx] = { xofs, a0, a1, 0 }     Y[dy] = { y0, y1, b0, b1 }
 // =====================================================================================
 __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__ ExtractParams p, int level) {
   const LevelParams& D = p.lv[level];
@@ -26,24 +27,25 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
   const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int dy = blockIdx.y;
   if (dx0 >= D.w) return;
-  const int16_t* tx = p.tab + D.tabX;
-  const int16_t* ty = p.tab + D.tabY;
-  const int y0 = ty[dy], y1 = ty[D.h + dy], b0 = ty[2 * D.h + dy], b1 = ty[3 * D.h + dy];
+  const short4 ty = reinterpret_cast<const short4*>(p.tab + D.tabY)[dy];
+  const int b0 = ty.z, b1 = ty.w;
   const uint8_t* src = S.pyr + (size_t)blockIdx.z * S.imgStride;
-  const uint8_t* S0 = src + (size_t)y0 * S.pitch;
-  const uint8_t* S1 = src + (size_t)y1 * S.pitch;
+  const uint8_t* S0 = src + (size_t)ty.x * S.pitch;
+  const uint8_t* S1 = src + (size_t)ty.y * S.pitch;
+  // the table is padded to a multiple of 4 entries, so the two 16-byte loads never leave it
+  const int4* tx4 = reinterpret_cast<const int4*>(p.tab + D.tabX) + (dx0 >> 1);
+  const int4 e01 = __ldg(tx4), e23 = __ldg(tx4 + 1);
+  const int ent[8] = {e01.x, e01.y, e01.z, e01.w, e23.x, e23.y, e23.z, e23.w};
+  const int xmax = S.w - 1;
   uint32_t out = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    int dx = dx0 + i;
-    if (dx < D.w) {
-      int x0 = tx[dx], a0 = tx[D.w + dx], a1 = tx[2 * D.w + dx];
-      int x1 = min(x0 + 1, S.w - 1);
-      int T0 = __ldg(S0 + x0) * a0 + __ldg(S0 + x1) * a1;
-      int T1 = __ldg(S1 + x0) * a0 + __ldg(S1 + x1) * a1;
-      int v = (((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2;
-      out |= (uint32_t)(v & 0xff) << (8 * i);
-    }
+    const int x0 = ent[2 * i] & 0xffff, a0 = ent[2 * i] >> 16, a1 = (short)(ent[2 * i + 1] & 0xffff);
+    const int x1 = min(x0 + 1, xmax);
+    const int T0 = __ldg(S0 + x0) * a0 + __ldg(S0 + x1) * a1;
+    const int T1 = __ldg(S1 + x0) * a0 + __ldg(S1 + x1) * a1;
+    const int v = (((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2;
+    out |= (uint32_t)(v & 0xff) << (8 * i);
   }
   uint8_t* dst = D.pyr + (size_t)blockIdx.z * D.imgStride + (size_t)dy * D.pitch + dx0;
   *reinterpret_cast<uint32_t*>(dst) = out;  // pitch is a multiple of 16 and padded: safe past w

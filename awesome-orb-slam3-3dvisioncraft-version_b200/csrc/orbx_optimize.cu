@@ -262,8 +262,78 @@ __device__ bool ldlt6_solve(const double* Ain, const double* b, double* x) {
     for (int j = 0; j < i; ++j) y[i] -= A[i * 6 + j] * y[j];
   for (int i = 0; i < 6; ++i) { const double d = A[i * 6 + i]; y[i] = (d != 0) ? y[i] / d : 0.0; }
   for (int i = 5; i >= 0; --i)
-    for (int j = i + 1; j < 6; ++j) y[i] -= A[j * 6 + i] * y[j];
+    for (int j = 5; j > i; --j) y[i] -= A[j * 6 + i] * y[j];
   for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+  return true;
+}
+
+// Warp-cooperative version of ldlt6_solve on shared memory (A: 36 doubles, overwritten; perm/y scratch).  Same
+// arithmetic as the serial routine, element for element: step k picks the largest |diagonal| (first on ties),
+// swaps row/column k<->p, scales column k by the pivot and applies A[i][j] -= A[i][k]*d*A[j][k] to the trailing
+// lower triangle (mirrored); forward substitution subtracts columns in increasing j, backward in decreasing j.
+// All 32 lanes of ONE warp must call; returns the same value on every lane.
+__device__ bool ldlt6_solve_warp(double* A, const double* b, double* x, int* perm, double* y) {
+  const int lane = threadIdx.x & 31;
+  if (lane < 6) perm[lane] = lane;
+  __syncwarp();
+  bool positive = true;
+  for (int k = 0; k < 6; ++k) {
+    // pivot: first index >= k with the largest |A[i][i]|
+    int p = k;
+    double best = fabs(A[k * 6 + k]);
+    for (int i = k + 1; i < 6; ++i) {
+      const double v = fabs(A[i * 6 + i]);
+      if (v > best) { best = v; p = i; }
+    }
+    if (p != k) {   // (uniform: every lane computed the same p)
+      double r0 = 0, r1 = 0;
+      if (lane < 6) { r0 = A[k * 6 + lane]; r1 = A[p * 6 + lane]; }
+      __syncwarp();
+      if (lane < 6) { A[k * 6 + lane] = r1; A[p * 6 + lane] = r0; }
+      __syncwarp();
+      if (lane < 6) { r0 = A[lane * 6 + k]; r1 = A[lane * 6 + p]; }
+      __syncwarp();
+      if (lane < 6) { A[lane * 6 + k] = r1; A[lane * 6 + p] = r0; }
+      if (lane == 0) { const int t = perm[k]; perm[k] = perm[p]; perm[p] = t; }
+      __syncwarp();
+    }
+    const double d = A[k * 6 + k];
+    if (d < 0) positive = false;
+    if (d == 0) continue;
+    if (lane > k && lane < 6) A[lane * 6 + k] /= d;
+    __syncwarp();
+    // trailing lower triangle: lane -> (i, j) with k < j <= i < 6  (at most 15 pairs)
+    {
+      const int m = 5 - k;                       // size of the trailing block
+      int i = -1, j = -1;
+      if (lane < m * (m + 1) / 2) {
+        int r = 0, rem = lane;
+        while (rem > r) { rem -= r + 1; ++r; }   // row r of the packed triangle, column rem
+        i = k + 1 + r;
+        j = k + 1 + rem;
+      }
+      double v = 0;
+      if (i >= 0) v = A[i * 6 + j] - A[i * 6 + k] * d * A[j * 6 + k];
+      __syncwarp();
+      if (i >= 0) { A[i * 6 + j] = v; A[j * 6 + i] = v; }
+      __syncwarp();
+    }
+  }
+  if (!positive) return false;
+  if (lane < 6) y[lane] = b[perm[lane]];
+  __syncwarp();
+  for (int j = 0; j < 6; ++j) {                  // forward: y[i] -= L[i][j] * y[j], j ascending
+    if (lane > j && lane < 6) y[lane] -= A[lane * 6 + j] * y[j];
+    __syncwarp();
+  }
+  if (lane < 6) { const double d = A[lane * 6 + lane]; y[lane] = (d != 0) ? y[lane] / d : 0.0; }
+  __syncwarp();
+  for (int j = 5; j >= 0; --j) {                 // backward: y[i] -= L[j][i] * y[j], j descending
+    if (lane < j) y[lane] -= A[j * 6 + lane] * y[j];
+    __syncwarp();
+  }
+  if (lane < 6) x[perm[lane]] = y[lane];
+  __syncwarp();
   return true;
 }
 
@@ -293,8 +363,8 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
   const int E = A.edgeStart ? A.edgeCount[prob] : A.edgeOfs[prob + 1] - e0;
   __shared__ SE3d s_est, s_backup, s_init;
   __shared__ double s_red[(PO_NT / 32) * 28];
-  __shared__ double s_H[36], s_b[6], s_x[6];
-  __shared__ int s_ok;
+  __shared__ double s_H[36], s_b[6], s_x[6], s_A[36], s_y[6];
+  __shared__ int s_ok, s_perm[6];
   const float* xw = A.xw + 3 * (size_t)e0;
   const float* obs = A.obs + 3 * (size_t)e0;
   const float* isg = A.invSigma2 + e0;
@@ -375,14 +445,18 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
       double rho = 0;
       int qmax = 0;
       do {
-        if (tid == 0) {
-          s_backup = s_est;                       // push()
-          double Hl[36], x[6];
-          for (int i = 0; i < 36; ++i) Hl[i] = s_H[i];
-          for (int i = 0; i < 6; ++i) { Hl[i * 6 + i] += lambda; x[i] = 0; }
-          s_ok = ldlt6_solve(Hl, s_b, x) ? 1 : 0;
-          for (int i = 0; i < 6; ++i) s_x[i] = x[i];
-          s_est = se3_mul(se3_exp(x), s_est);     // oplus: exp(update) * estimate
+        if (tid < 32) {                           // warp 0: 6x6 solve cooperatively, then lane 0 applies the update
+          if (tid == 0) s_backup = s_est;         // push()
+          for (int i = tid; i < 36; i += 32) s_A[i] = s_H[i] + ((i % 7 == 0) ? lambda : 0.0);
+          if (tid < 6) s_x[tid] = 0;
+          __syncwarp();
+          const bool okSolve = ldlt6_solve_warp(s_A, s_b, s_x, s_perm, s_y);
+          if (tid == 0) {
+            s_ok = okSolve ? 1 : 0;
+            double x[6];
+            for (int i = 0; i < 6; ++i) x[i] = s_x[i];
+            s_est = se3_mul(se3_exp(x), s_est);   // oplus: exp(update) * estimate
+          }
         }
         __syncthreads();
         const SE3d trial = s_est;

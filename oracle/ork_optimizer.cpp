@@ -222,7 +222,7 @@ static bool ldlt_solve_pivoted(int n, const double* Ain, const double* b, double
     y[i] = (d != 0) ? y[i] / d : 0.0;
   }
   for (int i = n - 1; i >= 0; --i)
-    for (int j = i + 1; j < n; ++j) y[i] -= A[(size_t)j * n + i] * y[j];
+    for (int j = n - 1; j > i; --j) y[i] -= A[(size_t)j * n + i] * y[j];
   for (int i = 0; i < n; ++i) x[perm[i]] = y[i];
   return true;
 }
