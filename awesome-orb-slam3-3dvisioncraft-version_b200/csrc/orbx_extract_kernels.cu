@@ -131,14 +131,13 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   // ---- A: load ----
   const uint8_t* img = L.pyr + (size_t)b * L.imgStride;
   {
-    const int nwords = th * tpw;
     uint32_t* simg32 = reinterpret_cast<uint32_t*>(simg);
     const int rowWords = (L.pitch - xa) / 4;          // words readable in a row without leaving the pitch
-    for (int i = tid; i < nwords; i += 256) {
-      const int r = i / tpw, c = i - r * tpw;
-      uint32_t v = 0;
-      if (c < rowWords) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(iniY + r) * L.pitch + xa) + c);
-      simg32[i] = v;
+    const int cw = min(tpw, rowWords);
+    for (int r = wid; r < th; r += 8) {               // one warp per tile row: coalesced 128-byte segments, no division
+      const uint32_t* g = reinterpret_cast<const uint32_t*>(img + (size_t)(iniY + r) * L.pitch + xa);
+      uint32_t* d = simg32 + r * tpw;
+      for (int c = lane; c < tpw; c += 32) d[c] = c < cw ? __ldg(g + c) : 0u;
     }
     for (int i = tid; i < (hI + 2) * sp; i += 256) ssc[i] = 0;
     for (int x = tid; x < wI; x += 256) scell[x] = (uint8_t)(x / L.wCell);
@@ -153,40 +152,43 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
     const uint32_t* simg32 = reinterpret_cast<const uint32_t*>(simg);
     const int c0 = (off + 3) / 4, c1 = (off + 3 + wI - 1) / 4;   // words that hold interior pixels
     const int ncw = c1 - c0 + 1;
-    const int nwordsB = hI * ncw;
-    for (int i0 = 0; i0 < nwordsB; i0 += 256) {
-      const int i = min(i0 + tid, nwordsB - 1);       // out-of-range lanes redo the last word and drop its result
-      const bool live = i0 + tid < nwordsB;
-      const int y = i / ncw, c = c0 + (i - y * ncw);
-      const uint32_t* row = simg32 + (y + 3) * tpw + c;
-      const uint32_t V = row[0];
-      const uint32_t r0 = row[3 * tpw], r8 = row[-3 * tpw];
-      const uint32_t r4 = __funnelshift_r(row[0], row[1], 24);     // bytes +3..+6
-      const uint32_t r12 = __funnelshift_r(row[-1], row[0], 8);    // bytes -3..0
-      const unsigned b0 = swar_gt_u8(__vabsdiffu4(r0, V), kGt), b4 = swar_gt_u8(__vabsdiffu4(r4, V), kGt);
-      const unsigned b8 = swar_gt_u8(__vabsdiffu4(r8, V), kGt), b12 = swar_gt_u8(__vabsdiffu4(r12, V), kGt);
-      unsigned cand = ((b0 | b8) & (b4 | b12));       // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
-      // drop bytes outside the interior columns
-      const int xb = c * 4 - (off + 3);               // interior x of byte 0 (may be negative)
-      if (xb < 0) cand &= 0xffffffffu << (8 * (-xb));
-      if (xb + 3 >= wI) cand &= 0xffffffffu >> (8 * (xb + 4 - wI));
-      if (!live) cand = 0;
-      // warp-aggregated append: one shared-memory atomic per warp instead of one per thread
-      const int cnt = __popc(cand);
-      int incl = cnt;
+    for (int y = wid; y < hI; y += 8) {               // one warp per interior row, lanes over its 4-pixel words
+      const uint32_t* rowBase = simg32 + (y + 3) * tpw;
+      for (int cb = 0; cb < ncw; cb += 32) {          // warp-uniform trip count
+        const int c = c0 + min(cb + lane, ncw - 1);   // out-of-range lanes redo the last word and drop its result
+        const bool live = cb + lane < ncw;
+        const uint32_t* row = rowBase + c;
+        const uint32_t V = row[0];
+        const uint32_t r0 = row[3 * tpw], r8 = row[-3 * tpw];
+        const uint32_t r4 = __funnelshift_r(row[0], row[1], 24);     // bytes +3..+6
+        const uint32_t r12 = __funnelshift_r(row[-1], row[0], 8);    // bytes -3..0
+        const unsigned b0 = swar_gt_u8(__vabsdiffu4(r0, V), kGt), b4 = swar_gt_u8(__vabsdiffu4(r4, V), kGt);
+        const unsigned b8 = swar_gt_u8(__vabsdiffu4(r8, V), kGt), b12 = swar_gt_u8(__vabsdiffu4(r12, V), kGt);
+        unsigned cand = ((b0 | b8) & (b4 | b12));     // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
+        // drop bytes outside the interior columns
+        const int xb = c * 4 - (off + 3);             // interior x of byte 0 (may be negative)
+        if (xb < 0) cand &= 0xffffffffu << (8 * (-xb));
+        if (xb + 3 >= wI) cand &= 0xffffffffu >> (8 * (xb + 4 - wI));
+        if (!live) cand = 0;
+        if (__any_sync(0xffffffffu, cand != 0)) {
+          // warp-aggregated append: one shared-memory atomic per warp
+          const int cnt = __popc(cand);
+          int incl = cnt;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+          }
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          int wbase = 0;
+          if (lane == 31) wbase = atomicAdd(&sflag[8], total);
+          wbase = __shfl_sync(0xffffffffu, wbase, 31);
+          int slot = wbase + incl - cnt;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (cand & (0x80u << (8 * k))) scand[slot++] = (uint16_t)((y << 9) | (xb + k));
+        }
       }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      int wbase = 0;
-      if (lane == 31 && total) wbase = atomicAdd(&sflag[8], total);
-      wbase = __shfl_sync(0xffffffffu, wbase, 31);
-      int slot = wbase + incl - cnt;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (cand & (0x80u << (8 * k))) scand[slot++] = (uint16_t)((y << 9) | (xb + k));
     }
   }
   __syncthreads();
@@ -228,17 +230,14 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
         const int y = code >> 9, x = code & 511;
         const uint8_t* sp0 = ssc + (y + 1) * sp + x + 1;
         sc = sp0[0];
-        if (sc > 0) {
-          const int cell = scell[x];
-          const bool hasL = x > 0 && scell[x - 1] == cell, hasR = x + 1 < wI && scell[x + 1] == cell;
-          bool ok = sc > sp0[-sp] && sc > sp0[sp];
-          if (hasL) ok = ok && sc > sp0[-1] && sc > sp0[-sp - 1] && sc > sp0[sp - 1];
-          if (hasR) ok = ok && sc > sp0[1] && sc > sp0[-sp + 1] && sc > sp0[sp + 1];
-          if (ok) {
-            keep = true;
-            if (sc >= p.iniTh) atomicOr(&sflag[cell], 1);
-          }
-        }
+        // branch-free 3x3 maximum of the neighbours inside the pixel's own cell (others count as 0)
+        const int cell = scell[x];
+        const int mL = ((x > 0) & (scell[max(x - 1, 0)] == cell)) ? 0xff : 0, mR = ((x + 1 < wI) & (scell[x + 1] == cell)) ? 0xff : 0;
+        const int nL = max(max((int)sp0[-1], (int)sp0[-sp - 1]), (int)sp0[sp - 1]) & mL;
+        const int nR = max(max((int)sp0[1], (int)sp0[-sp + 1]), (int)sp0[sp + 1]) & mR;
+        const int nmax = max(max((int)sp0[-sp], (int)sp0[sp]), max(nL, nR));
+        keep = sc > nmax;                             // sc == 0 (no corner) can never exceed nmax >= 0
+        if (keep && sc >= p.iniTh) atomicOr(&sflag[cell], 1);
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
       int wbase = 0;
