@@ -71,4 +71,16 @@ int orbx_synchronize(orbx_ctx* c) {
 
 uint64_t orbx_launch_count(const orbx_ctx* c) { return c ? c->launches.load() : 0; }
 
+void* orbx_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    orbx_set_error("orbx_host_alloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+void orbx_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 }  // extern "C"

@@ -581,12 +581,28 @@ int orbx_tracker_step(orbx_tracker* t, const uint8_t* const* imgs, int w, int h,
     t->d_hstats = talloc<int>(t, ORBX_TRACK_STATS * S);
     if (!t->d_imgs || !t->d_hposeIn || !t->d_hposeOut || !t->d_hstats) return ORBX_ECUDA;
   }
-  for (int b = 0; b < 2 * S; ++b)
-    for (int y = 0; y < h; ++y) memcpy(t->h_imgs + b * img + (size_t)y * w, imgs[b] + (size_t)y * stride, w);
+  cudaStream_t sa = t->stA, sb = t->stB;
+  // page-locked caller memory is DMA'd directly (one copy when the images are also contiguous); anything else is
+  // staged through the tracker's own pinned buffer first
+  bool pinned = true, contiguous = stride == w;
+  for (int b = 0; b < 2 * S && pinned; ++b) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, imgs[b]) != cudaSuccess || at.type != cudaMemoryTypeHost) pinned = false;
+    if (b > 0 && imgs[b] != imgs[b - 1] + img) contiguous = false;
+  }
+  cudaGetLastError();   // a failed attribute query on pageable memory leaves a sticky-free error behind
+  if (pinned && contiguous) {
+    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, imgs[0], 2 * S * img, cudaMemcpyHostToDevice, sa));
+  } else if (pinned) {
+    for (int b = 0; b < 2 * S; ++b)
+      ORBX_CUDA(cudaMemcpy2DAsync(t->d_imgs + b * img, w, imgs[b], stride, w, h, cudaMemcpyHostToDevice, sa));
+  } else {
+    for (int b = 0; b < 2 * S; ++b)
+      for (int y = 0; y < h; ++y) memcpy(t->h_imgs + b * img + (size_t)y * w, imgs[b] + (size_t)y * stride, w);
+    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, t->h_imgs, 2 * S * img, cudaMemcpyHostToDevice, sa));
+  }
   memcpy(t->h_pose, Tcw_true, sizeof(float) * 16 * S);
   memcpy(t->h_pose + 16 * S, Tcw_prior, sizeof(float) * 16 * S);
-  cudaStream_t sa = t->stA, sb = t->stB;
-  ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, t->h_imgs, 2 * S * img, cudaMemcpyHostToDevice, sa));
   ORBX_CUDA(cudaMemcpyAsync(t->d_hposeIn, t->h_pose, sizeof(float) * 32 * S, cudaMemcpyHostToDevice, sa));
   int rc = orbx_tracker_step_device(t, t->d_imgs, w, h, w, t->d_hposeIn, t->d_hposeIn + 16 * S, t->d_hposeOut, t->d_hstats);
   if (rc != ORBX_OK) return rc;

@@ -5,6 +5,6 @@ The classes mirror the reference's operator interface for the tracking hot path
 There is no CPU fallback: importing works anywhere, but creating a Context without the built
 library or without a CUDA device raises.
 """
-from .api import (Context, ORBextractor, KP_DTYPE, OrbxError, lib_path, load_library,
+from .api import (Context, host_array, ORBextractor, KP_DTYPE, OrbxError, lib_path, load_library,
                   build_library, declared_symbols, ORBmatcher, Optimizer, Tracker, features_in_area, stereo_match, Frame,
                   Camera, make_camera)  # noqa: F401

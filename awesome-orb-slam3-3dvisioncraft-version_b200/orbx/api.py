@@ -57,6 +57,9 @@ def load_library():
     L.orbx_synchronize.argtypes = [vp]
     L.orbx_launch_count.restype = C.c_uint64
     L.orbx_launch_count.argtypes = [vp]
+    L.orbx_host_alloc.restype = vp
+    L.orbx_host_alloc.argtypes = [C.c_size_t]
+    L.orbx_host_free.argtypes = [vp]
     L.orbx_extractor_create.restype = vp
     L.orbx_extractor_create.argtypes = [vp, i, f, i, i, i, i, i, i]
     L.orbx_extractor_destroy.argtypes = [vp]
@@ -107,6 +110,20 @@ def _check(rc, what):
     if rc != 0:
         msg = load_library().orbx_last_error().decode(errors="replace")
         raise OrbxError("%s failed with status %d: %s" % (what, rc, msg))
+
+
+def host_array(shape, dtype=np.uint8):
+    """numpy array backed by page-locked memory (orbx_host_alloc): host-pointer entry points DMA from it directly.
+    The memory lives until the process exits (the finaliser frees it when the array is collected)."""
+    import weakref
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = load_library().orbx_host_alloc(n)
+    if not p:
+        raise OrbxError("orbx_host_alloc(%d) failed" % n)
+    buf = (C.c_uint8 * n).from_address(p)
+    a = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    weakref.finalize(buf, load_library().orbx_host_free, p)
+    return a
 
 
 class Context:

@@ -322,8 +322,10 @@ def main():
             n = s1 - s0
             ex = orbx.ORBextractor(ctx, NFEAT, 1.2, NLEVELS, 20, 7, max_w=W, max_h=H, max_batch=2 * n)
             trk = orbx.Tracker(ctx, ex, n, cam, th_frame=7.0, th_map=1.0, nnratio_map=0.8)
+            pin = orbx.host_array((2 * n, H, W), np.uint8)     # page-locked inputs for the e2e arm
+            pin[:] = np.stack(imgs[2 * s0:2 * s1])
             out.append(dict(
-                n=n, ex=ex, trk=trk, imgs=imgs[2 * s0:2 * s1], Tt=Tt[s0:s1], Tp=Tp[s0:s1],
+                n=n, ex=ex, trk=trk, imgs=[pin[i] for i in range(2 * n)], Tt=Tt[s0:s1], Tp=Tp[s0:s1],
                 stream=torch.cuda.ExternalStream(ex.stream, device=local),
                 d_img=torch.from_numpy(np.stack(imgs[2 * s0:2 * s1])).cuda(),
                 d_true=torch.from_numpy(Tt[s0:s1].reshape(n, 16)).cuda(),

@@ -61,6 +61,12 @@ int orbx_synchronize(orbx_ctx *ctx);
 /* Number of kernel launches issued through this context since creation. */
 uint64_t orbx_launch_count(const orbx_ctx *ctx);
 
+/* Page-locked host memory.  Host-pointer entry points accept any host memory; when the images they are given
+ * live in page-locked memory (from here, cudaHostAlloc or cudaHostRegister) they are DMA'd to the device
+ * directly instead of being staged through an internal pinned buffer. */
+void *orbx_host_alloc(size_t bytes);
+void orbx_host_free(void *p);
+
 /* ------------------------------------------------------------------------------------
  * ORBextractor — replaces ORBextractor::ORBextractor (src/ORBextractor.cc:408-468,
  * include/ORBextractor.h:49-50).  max_w/max_h/max_batch size the device-resident
