@@ -8,12 +8,13 @@
 #include <cmath>
 #include <cstring>
 #include <algorithm>
+#include <cstdlib>
 
 int orbx_extract_configure(int nodeCap, int fastTileBytes);
 size_t orbx_octree_smem_bytes(int nodeCap);
 size_t orbx_fast_smem_bytes(int fastTileBytes);
-int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, orbx_keypoint* d_kps, uint8_t* d_desc,
-                        int cap, int* d_n, int* d_mono, cudaEvent_t* ev);
+int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, const FastTmaMaps& maps, orbx_keypoint* d_kps,
+                        uint8_t* d_desc, int cap, int* d_n, int* d_mono, cudaEvent_t* ev);
 
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
 static inline int cv_floor_d(double v) { int i = (int)v; return i - (i > v); }
@@ -31,6 +32,10 @@ struct orbx_ext {
   // geometry currently configured
   int curW = -1, curH = -1, curStride = -1;
   ExtractParams P{};
+  FastTmaMaps maps{};
+  bool tmaOk = false;              // the driver exposes cuTensorMapEncodeTiled and ORBX_NO_TMA is unset
+  const uint8_t* tmaL0 = nullptr;  // level-0 binding the level-0 tensor map was encoded for
+  int tmaL0Pitch = -1;
   // device allocations (sized for maxW x maxH x maxB at creation)
   uint8_t* d_pyr = nullptr;      // levels 0..L-1 + blurred levels
   size_t pyrBytes = 0;
@@ -79,6 +84,40 @@ static bool size_supported(const orbx_ext* e, int w, int h) {
 
 static size_t pitch_for(int w) { return align_up((size_t)w + 4, 64); }
 
+// ---- TMA tensor maps for the FAST tiles (cuTensorMapEncodeTiled through the runtime's driver entry point: no
+// link-time dependency on libcuda) ----
+typedef CUresult (*orbx_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static orbx_tmap_encode_fn tmap_encoder() {
+  static orbx_tmap_encode_fn fn = []() -> orbx_tmap_encode_fn {
+    if (std::getenv("ORBX_NO_TMA")) return nullptr;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (orbx_tmap_encode_fn)p;
+  }();
+  return fn;
+}
+
+// Level l of a batch as a 3-D tensor (bytes of a row, rows, images); box = one FAST tile.  Returns false when the
+// layout does not satisfy TMA's 16-byte rules (the kernel then falls back to 32-bit loads for that level).
+static bool encode_fast_map(CUtensorMap* m, const LevelParams& L, const uint8_t* base, int pitch, size_t imgStride, int B) {
+  orbx_tmap_encode_fn enc = tmap_encoder();
+  if (!enc) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (imgStride & 15) || L.fastTP > 256 || L.fastTH > 256)
+    return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)L.h, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)imgStride};
+  const cuuint32_t box[3] = {(cuuint32_t)L.fastTP, (cuuint32_t)L.fastTH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Fill P.lv[] geometry for (w,h); level-0 pointer/pitch are set by the caller.
 static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   ExtractParams& P = e->P;
@@ -103,12 +142,19 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
     L.nRows = (int)(height / 30.f);
     L.wCell = (int)std::ceil(width / (float)L.nCols);
     L.hCell = (int)std::ceil(height / (float)L.nRows);
-    L.tilesPerRow = div_up(L.nCols, ORBX_FAST_CELLS);
+    // cells per tile: as many as fit a TMA box (<= 256 bytes wide).  The box starts at the tile's x origin rounded
+    // down to 16 bytes (the TMA unit faults on an unaligned innermost coordinate -- tools/tma_probe), so up to 15
+    // leading bytes are dead: pitch = align16(15 + n*wCell + 6 + 4)
+    L.fastCells = std::min(ORBX_FAST_CELLS, L.nCols);
+    while (L.fastCells > 1 && align_up((size_t)15 + L.fastCells * L.wCell + 6 + 4, 16) > 256) --L.fastCells;
+    L.fastTP = (int)align_up((size_t)15 + L.fastCells * L.wCell + 6 + 4, 16);
+    L.fastTH = L.hCell + 6;
+    L.useTma = 0;
+    L.tilesPerRow = div_up(L.nCols, L.fastCells);
     L.tileStart = tile;
     tile += L.tilesPerRow * L.nRows;
-    const int tw = std::min(ORBX_FAST_CELLS, L.nCols) * L.wCell + 6;
-    // one shared-memory plane: (tw + alignment slack + one spare word) x (hCell + 6 + 2 score border rows)
-    fastBytes = std::max(fastBytes, (int)align_up((size_t)(((tw + 3 + 3) & ~3) + 8) * (L.hCell + 8), 16));
+    // one shared-memory plane holds the image tile (fastTP x fastTH) or the score plane ((wI+2) x (hI+2))
+    fastBytes = std::max(fastBytes, (int)align_up((size_t)L.fastTP * (L.hCell + 8), 128));
     L.blurTilesX = div_up(L.w, ORBX_BLUR_TW);        // 128 columns per warp (32 lanes x 4 px)
     L.blurTilesY = div_up(L.h, ORBX_BLUR_TH);        // 8 warps x 32-row strips per CTA
     L.blurTileStart = btile;
@@ -198,6 +244,11 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   }
   int rc = orbx_extract_configure(P.nodeCap, fastBytes);
   if (rc != ORBX_OK) return rc;
+  for (int l = 1; l < e->nlevels; ++l) {
+    LevelParams& L = P.lv[l];
+    L.useTma = (l < ORBX_TMA_LEVELS && encode_fast_map(&e->maps.m[l], L, L.pyr, L.pitch, L.imgStride, e->maxB)) ? 1 : 0;
+  }
+  e->tmaL0 = nullptr;   // level 0 is (re)bound per call
   e->curW = w;
   e->curH = h;
   (void)B;
@@ -387,9 +438,14 @@ static int run_device(orbx_ext* e, int B, const uint8_t* d_level0, int w, int h,
   P.lv[0].pyr = const_cast<uint8_t*>(d_level0);
   P.lv[0].pitch = stride;
   P.lv[0].imgStride = (size_t)stride * h;
+  if (e->tmaL0 != d_level0 || e->tmaL0Pitch != stride) {   // level-0 tensor map follows the caller's buffer
+    P.lv[0].useTma = encode_fast_map(&e->maps.m[0], P.lv[0], d_level0, stride, (size_t)stride * h, e->maxB) ? 1 : 0;
+    e->tmaL0 = d_level0;
+    e->tmaL0Pitch = stride;
+  }
   e->lastB = B;
   e->profiled = e->profiling;
-  return orbx_extract_launch(e->ctx, e->stream, P, d_kps, d_desc, cap, d_n, d_mono, e->profiling ? e->ev : nullptr);
+  return orbx_extract_launch(e->ctx, e->stream, P, e->maps, d_kps, d_desc, cap, d_n, d_mono, e->profiling ? e->ev : nullptr);
 }
 
 int orbx_extract_batch_device(orbx_ext* e, int B, const uint8_t* d_imgs, int w, int h, int stride, int lap0, int lap1,

@@ -1,6 +1,7 @@
 // orbx_extract.cuh — device-visible parameter blocks of the batched ORB extractor.
 #pragma once
 #include "orbx_common.cuh"
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #define ORBX_EDGE 19          // EDGE_THRESHOLD, src/ORBextractor.cc:72
 #define ORBX_MINB 16          // minBorderX = EDGE_THRESHOLD-3, src/ORBextractor.cc:771
@@ -19,6 +20,9 @@ struct LevelParams {
   // FAST cell tiling (src/ORBextractor.cc:771-804)
   int nCols, nRows, wCell, hCell, maxBX, maxBY;
   int tileStart, tilesPerRow;      // flattened FAST tile ids of this level
+  int fastCells;                   // cells per FAST tile (<= ORBX_FAST_CELLS, chosen so the TMA box is <= 256 B wide)
+  int fastTP, fastTH;              // FAST shared-memory tile: row pitch in bytes (= TMA box width) and rows
+  int useTma;                      // 1: the tile is fetched by one cp.async.bulk.tensor, 0: by 32-bit loads
   int blurTileStart, blurTilesX, blurTilesY;
   // resize tables (level l from l-1): offsets into ExtractParams::tab (int16 units)
   int tabX, tabY;
@@ -48,3 +52,13 @@ struct ExtractParams {
   int* err;                        // device error flag (capacity overflow)
   LevelParams lv[ORBX_MAX_LEVELS];
 };
+
+// One 3-D tensor map (x = bytes of a row, y = rows, z = image of the batch) per pyramid level, for the FAST tiles.
+// Only the first ORBX_TMA_LEVELS levels get one (deeper levels use the 32-bit-load path): the maps are passed as the
+// FIRST __grid_constant__ kernel parameter and, together with ExtractParams, must stay inside the classic 4 KB
+// parameter window -- a descriptor that sits beyond it makes UTMALDG raise "illegal instruction" on sm_100a.
+#define ORBX_TMA_LEVELS 8
+struct alignas(128) FastTmaMaps {
+  CUtensorMap m[ORBX_TMA_LEVELS];
+};
+static_assert(sizeof(FastTmaMaps) + sizeof(ExtractParams) <= 4096, "kernel parameters must fit the 4 KB window");

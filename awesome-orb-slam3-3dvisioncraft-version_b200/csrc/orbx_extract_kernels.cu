@@ -86,8 +86,9 @@ __device__ __forceinline__ unsigned arc9_maxmin_x2(const unsigned (&X)[16]) {
   return vmax3(vmax3(a0, a1, a2), vmax3(a3, a4, m[15]), a0);
 }
 
-__global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ ExtractParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
+__global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ FastTmaMaps maps,
+                                                         const __grid_constant__ ExtractParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
   // locate (level, cell row, first cell)
   const int tile = blockIdx.x;
   int level = 0;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const LevelParams& L = p.lv[level];
   const int lt = tile - L.tileStart;
   const int ci = lt / L.tilesPerRow;
-  const int j0 = (lt - ci * L.tilesPerRow) * ORBX_FAST_CELLS;
+  const int j0 = (lt - ci * L.tilesPerRow) * L.fastCells;
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const int iniX = ORBX_MINB + j0 * L.wCell;
   if (iniX >= L.maxBX - 6) return;
   // cells j0 .. j0+nc-1 ; the last one of the level may be truncated or skipped
-  int nc = min(ORBX_FAST_CELLS, L.nCols - j0);
+  int nc = min(L.fastCells, L.nCols - j0);
   while (nc > 0 && ORBX_MINB + (j0 + nc - 1) * L.wCell >= L.maxBX - 6) --nc;
   if (nc <= 0) return;
   const int maxX = min(iniX + nc * L.wCell + 6, L.maxBX);
@@ -117,20 +118,42 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
 
   // shared layout: [flags 64 B][image tile th x tpw words][score (hI+2) x sp][survivor flag hI x sp]
   //                [column->cell table][candidate list]
-  const int xa = iniX & ~3;                           // aligned tile origin
-  const int off = iniX - xa;                          // 0..3: byte column of tile column 0
-  const int tpw = (off + tw + 3) / 4 + 1;             // words per tile row (+1: the stage-B window reads word c+1)
-  const int tp = tpw * 4;
+  const int xa = iniX & ~15;                          // tile origin: TMA needs a 16-byte aligned innermost coordinate
+  const int off = iniX - xa;                          // 0..15: byte column of tile column 0
+  const int tp = L.fastTP;                            // >= off + tw + 4 (the stage-B window reads word c+1), multiple of 16
+  const int tpw = tp >> 2;
   const int sp = wI + 2;
-  int* sflag = reinterpret_cast<int*>(smem);          // [0..7] cellHasIni, [8] nCand, [9] nEmit, [10] emit base
-  uint8_t* simg = smem + 64;
+  int* sflag = reinterpret_cast<int*>(smem);          // [0..7] cellHasIni, [8] nCand, [9] nSurv, [10] emit base, [11] emit count, [12] cursor
+  unsigned long long* smbar = reinterpret_cast<unsigned long long*>(smem + 64);   // TMA completion barrier
+  uint8_t* simg = smem + 128;                         // 128-byte aligned: TMA destination
   uint8_t* ssc = simg + (size_t)p.fastTileBytes;
   uint8_t* scell = ssc + (size_t)p.fastTileBytes;     // [wI] cell index of interior column x
   uint16_t* scand = reinterpret_cast<uint16_t*>(scell + 512);
 
   // ---- A: load ----
   const uint8_t* img = L.pyr + (size_t)b * L.imgStride;
-  {
+  if (L.useTma) {
+    // one elected thread arms the mbarrier with the byte count and issues ONE bulk tensor copy for the whole tile
+    // (box fastTP x fastTH at (xa, iniY, b); bytes outside the tensor are zero-filled by the TMA unit)
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(smbar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const unsigned bytes = (unsigned)(L.fastTP * L.fastTH);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(simg);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+      // the descriptor is addressed in place in the kernel-parameter bank (levels compared against constants so the
+      // address stays a parameter-space constant + select)
+      const CUtensorMap* tm = &maps.m[0];
+#pragma unroll
+      for (int l = 1; l < ORBX_TMA_LEVELS; ++l)
+        if (level == l) tm = &maps.m[l];
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(dst), "l"(tm), "r"(xa), "r"(iniY), "r"(b), "r"(mbar)
+          : "memory");
+    }
+  } else {
     uint32_t* simg32 = reinterpret_cast<uint32_t*>(simg);
     const int rowWords = (L.pitch - xa) / 4;          // words readable in a row without leaving the pitch
     const int cw = min(tpw, rowWords);
@@ -139,11 +162,24 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
       uint32_t* d = simg32 + r * tpw;
       for (int c = lane; c < tpw; c += 32) d[c] = c < cw ? __ldg(g + c) : 0u;
     }
+  }
+  {
     for (int i = tid; i < (hI + 2) * sp; i += 256) ssc[i] = 0;
     for (int x = tid; x < wI; x += 256) scell[x] = (uint8_t)(x / L.wCell);
     if (tid < 16) sflag[tid] = 0;
   }
-  __syncthreads();
+  __syncthreads();                                    // (also publishes the mbarrier initialisation)
+  if (L.useTma) {
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(smbar);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(mbar)
+          : "memory");
+    }
+  }
 
   // ---- B: compass early reject, one 4-pixel word per thread-iteration ----
   const int t = p.minTh;
@@ -451,7 +487,7 @@ __device__ __forceinline__ short4 oct_child_bounds(short4 b, int q) {
 }
 
 __global__ void __launch_bounds__(OCT_NT) octree_kernel(const __grid_constant__ ExtractParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(16) uint8_t oct_smem[];
   const int level = blockIdx.x, b = blockIdx.y;
   const LevelParams& L = p.lv[level];
   const int NC = p.nodeCap;
@@ -461,7 +497,7 @@ __global__ void __launch_bounds__(OCT_NT) octree_kernel(const __grid_constant__ 
 
   OctSmem S;
   {
-    uint8_t* q = smem;
+    uint8_t* q = oct_smem;
     S.bnd[0] = (short4*)q; q += sizeof(short4) * NC;
     S.bnd[1] = (short4*)q; q += sizeof(short4) * NC;
     S.best = (unsigned long long*)q; q += sizeof(unsigned long long) * NC;
@@ -823,7 +859,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ E
 // ------------------------------------------------------------------------------------
 // host-side launchers (called from orbx_extract.cu)
 // ------------------------------------------------------------------------------------
-size_t orbx_fast_smem_bytes(int fastTileBytes) { return (size_t)4 * fastTileBytes + 64 + 512; }
+size_t orbx_fast_smem_bytes(int fastTileBytes) { return (size_t)4 * fastTileBytes + 128 + 512; }
 size_t orbx_octree_smem_bytes(int nodeCap) {
   return (size_t)nodeCap * (2 * sizeof(short4) + sizeof(unsigned long long) + 4 * 2 + 16 + 4 * 4);
 }
@@ -836,8 +872,8 @@ int orbx_extract_configure(int nodeCap, int fastTileBytes) {
   return ORBX_OK;
 }
 
-int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, orbx_keypoint* d_kps, uint8_t* d_desc,
-                        int cap, int* d_n, int* d_mono, cudaEvent_t* ev /* [ORBX_EXT_STAGES+1] or null */) {
+int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, const FastTmaMaps& maps, orbx_keypoint* d_kps,
+                        uint8_t* d_desc, int cap, int* d_n, int* d_mono, cudaEvent_t* ev /* [ORBX_EXT_STAGES+1] or null */) {
   const int B = p.B;
   ORBX_CUDA(cudaMemsetAsync(p.candN, 0, sizeof(int) * B * p.nlevels, st));
 #define ORBX_EV(i) do { if (ev) ORBX_CUDA(cudaEventRecord(ev[i], st)); } while (0)
@@ -848,7 +884,7 @@ int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, 
     ORBX_LAUNCH(ctx);
   }
   ORBX_EV(1);
-  fast_cells_kernel<<<dim3(p.totalFastTiles, B), 256, orbx_fast_smem_bytes(p.fastTileBytes), st>>>(p);
+  fast_cells_kernel<<<dim3(p.totalFastTiles, B), 256, orbx_fast_smem_bytes(p.fastTileBytes), st>>>(maps, p);
   ORBX_LAUNCH(ctx);
   ORBX_EV(2);
   gauss7_kernel<<<dim3(p.totalBlurTiles, B), 256, 0, st>>>(p);

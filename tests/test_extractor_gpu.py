@@ -118,3 +118,20 @@ def test_gpu_reproduces_golden_vectors(ctx):
         m, k, d = ex(img, lap)
         assert_kp_equal(k, d, m, gk, gd, gm, name)
         ex.close()
+
+
+def test_fallback_tile_loads_without_tma():
+    """ORBX_NO_TMA=1 (or a layout that breaks TMA's 16-byte rules) switches the FAST tiles to plain 32-bit loads;
+    both paths must give the same bits."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np, orbx, oracle; "
+            "from orbx import synth; img = synth.scene_image(3); c = orbx.Context(0); "
+            "m, k, d = orbx.ORBextractor(c)(img); rc, rk, rd, rm = oracle.Extractor()(img); "
+            "assert len(k) == len(rk) and np.array_equal(d, rd) and all(np.array_equal(k[f], rk[f]) for f in rk.dtype.names); "
+            "print('fallback ok', len(k))") % (root, os.path.join(root, "awesome-orb-slam3-3dvisioncraft-version_b200"))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, ORBX_NO_TMA="1"), capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0 and "fallback ok" in out.stdout, out.stderr[-1500:]
