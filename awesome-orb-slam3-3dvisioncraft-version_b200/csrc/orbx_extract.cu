@@ -10,9 +10,9 @@
 #include <algorithm>
 #include <cstdlib>
 
-int orbx_extract_configure(int nodeCap, int fastTileBytes);
+int orbx_extract_configure(int nodeCap, int fastTileBytes, int fastCandCap);
 size_t orbx_octree_smem_bytes(int nodeCap);
-size_t orbx_fast_smem_bytes(int fastTileBytes);
+size_t orbx_fast_smem_bytes(int fastTileBytes, int fastCandCap);
 int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, const FastTmaMaps& maps, orbx_keypoint* d_kps,
                         uint8_t* d_desc, int cap, int* d_n, int* d_mono, cudaEvent_t* ev);
 
@@ -126,7 +126,7 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   P.minTh = e->minTh;
   P.nodeCap = 0;
   size_t off = 0;
-  int tile = 0, btile = 0, cand = 0, sel = 0, fastBytes = 0;
+  int tile = 0, btile = 0, cand = 0, sel = 0, fastBytes = 0, fastCand = 0;
   std::vector<int16_t> htab;
   for (int l = 0; l < e->nlevels; ++l) {
     LevelParams& L = P.lv[l];
@@ -155,6 +155,7 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
     tile += L.tilesPerRow * L.nRows;
     // one shared-memory plane holds the image tile (fastTP x fastTH) or the score plane ((wI+2) x (hI+2))
     fastBytes = std::max(fastBytes, (int)align_up((size_t)L.fastTP * (L.hCell + 8), 128));
+    fastCand = std::max(fastCand, (int)align_up((size_t)(L.fastCells * L.wCell) * L.hCell, 64));
     L.blurTilesX = div_up(L.w, ORBX_BLUR_TW);        // 128 columns per warp (32 lanes x 4 px)
     L.blurTilesY = div_up(L.h, ORBX_BLUR_TH);        // 8 warps x 32-row strips per CTA
     L.blurTileStart = btile;
@@ -230,6 +231,7 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   P.totalFastTiles = tile;
   P.totalBlurTiles = btile;
   P.fastTileBytes = fastBytes;
+  P.fastCandCap = fastCand;
   P.cand = e->d_cand;
   P.keyNode = e->d_keyNode;
   P.sel = e->d_sel;
@@ -237,12 +239,12 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   P.selN = e->d_counts + e->maxB * e->nlevels;
   P.selLap = e->d_counts + 2 * e->maxB * e->nlevels;
   P.err = e->d_counts + 3 * e->maxB * e->nlevels;
-  if (orbx_fast_smem_bytes(fastBytes) > 200 * 1024 || orbx_octree_smem_bytes(P.nodeCap) > 200 * 1024) {
-    orbx_set_error("orbx: shared-memory budget exceeded (fast %zu, octree %zu)", orbx_fast_smem_bytes(fastBytes),
+  if (orbx_fast_smem_bytes(fastBytes, fastCand) > 200 * 1024 || orbx_octree_smem_bytes(P.nodeCap) > 200 * 1024) {
+    orbx_set_error("orbx: shared-memory budget exceeded (fast %zu, octree %zu)", orbx_fast_smem_bytes(fastBytes, fastCand),
                    orbx_octree_smem_bytes(P.nodeCap));
     return ORBX_ECAP;
   }
-  int rc = orbx_extract_configure(P.nodeCap, fastBytes);
+  int rc = orbx_extract_configure(P.nodeCap, fastBytes, fastCand);
   if (rc != ORBX_OK) return rc;
   for (int l = 1; l < e->nlevels; ++l) {
     LevelParams& L = P.lv[l];

@@ -55,16 +55,21 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
 // K2  per-cell FAST-9-16 + cell-local 3x3 NMS + iniTh->minTh fallback + candidate emission.
 // One CTA = one cell row x up to ORBX_FAST_CELLS cells of one level of one image.
 //
-// Work is staged so that the expensive per-pixel arithmetic only runs on a dense, compacted list:
-//   A. tile -> shared memory with 32-bit loads (tile origin rounded down to a 4-byte boundary)
-//   B. early reject, 4 pixels per instruction stream: VABSDIFF4 of the centre word against the four
-//      compass ring positions (0,4,8,12), SWAR ">t" masks, and the necessary condition "two adjacent
-//      compass points differ by more than t" (every 9-arc of the 16-ring contains two adjacent compass
-//      points).  Survivors are appended to a shared-memory list.
-//   C. exact score of every survivor: the 16 ring differences are packed as (256+d, 256-d) in one
-//      s16x2 register by a single IMAD each, and the max-over-arcs-of-min network runs for both
-//      polarities at once on VIMNMX3.S16x2 (40 instructions).  corner <=> arcmax > minTh.
-//   D. cell-local 3x3 NMS, per-cell "has a corner >= iniTh" flag, emission (one global atomic per tile).
+// The reference runs cv::FAST(cell, iniTh) and, only for a cell that yields nothing, cv::FAST(cell, minTh)
+// (src/ORBextractor.cc:808-828).  The kernel does the same in two passes over the shared-memory tile: pass 0 at iniTh
+// over every pixel, pass 1 at minTh restricted to the pixels of the cells pass 0 left empty (on corner-rich content
+// that is rare, and a threshold of 20 rejects far more pixels early than 7 does).  Every pass is staged so that the
+// expensive per-pixel arithmetic only runs on dense, compacted lists:
+//   A. tile -> shared memory: one TMA bulk tensor copy (or 32-bit loads when the level has no tensor map)
+//   B. early reject, 4 pixels per instruction stream: VABSDIFF4 of the centre word against the four compass ring
+//      positions (0,4,8,12), SWAR ">t" masks, and the necessary condition "two adjacent compass points differ by
+//      more than t" (every 9-arc of the 16-ring contains two adjacent compass points).  Survivors -> list 1.
+//   C. exact score of every survivor: the 16 ring differences are packed as (256+d, 256-d) in one s16x2 register by
+//      a single IMAD each, and the max-over-arcs-of-min network runs for both polarities at once on VIMNMX3.S16x2
+//      (40 instructions).  corner <=> arcmax > t; corners -> score plane + list 2.
+//   D. cell-local 3x3 NMS over list 2 (neighbours across a cell seam count as 0, like the borders of the per-cell
+//      cv::FAST call); kept keypoints -> list 3, which pass 1 appends to.  A pass-0 keypoint marks its cell non-empty.
+//   E. emission: one global atomic per tile, list 3 written out with its scores.
 // =====================================================================================
 __device__ __forceinline__ unsigned swar_gt_u8(unsigned x, unsigned k) {   // k = (0x7f - t) * 0x01010101, t < 128
   return (((x & 0x7f7f7f7fu) + k) | x) & 0x80808080u;
@@ -84,6 +89,42 @@ __device__ __forceinline__ unsigned arc9_maxmin_x2(const unsigned (&X)[16]) {
   const unsigned a0 = vmax3(m[0], m[1], m[2]), a1 = vmax3(m[3], m[4], m[5]), a2 = vmax3(m[6], m[7], m[8]);
   const unsigned a3 = vmax3(m[9], m[10], m[11]), a4 = vmax3(m[12], m[13], m[14]);
   return vmax3(vmax3(a0, a1, a2), vmax3(a3, a4, m[15]), a0);
+}
+
+// shared-memory flag words of fast_cells_kernel
+enum { FF_CELL = 0 /* [0..7] cell has a pass-0 keypoint */, FF_NCAND = 8, FF_NKEPT = 9, FF_BASE = 10, FF_NCORN = 11,
+       FF_OVF = 12, FF_NACT = 13, FF_EMPTY = 14 };
+
+// Stage B for one 4-pixel word of interior row y (word column c of the tile, byte mask m of the pixels to test):
+// appends the surviving pixels to scand.  Must be called by all 32 lanes (warp-aggregated append).
+__device__ __forceinline__ void fast_stage_b(const uint32_t* simg32, int tpw, int y, int c, int xb, unsigned m,
+                                             unsigned kGt, int* sflag, uint16_t* scand, int lane) {
+  const uint32_t* row = simg32 + (y + 3) * tpw + c;
+  const uint32_t V = row[0];
+  const uint32_t r0 = row[3 * tpw], r8 = row[-3 * tpw];
+  const uint32_t r4 = __funnelshift_r(row[0], row[1], 24);     // bytes +3..+6
+  const uint32_t r12 = __funnelshift_r(row[-1], row[0], 8);    // bytes -3..0
+  const unsigned b0 = swar_gt_u8(__vabsdiffu4(r0, V), kGt), b4 = swar_gt_u8(__vabsdiffu4(r4, V), kGt);
+  const unsigned b8 = swar_gt_u8(__vabsdiffu4(r8, V), kGt), b12 = swar_gt_u8(__vabsdiffu4(r12, V), kGt);
+  const unsigned cand = ((b0 | b8) & (b4 | b12)) & m;          // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
+  if (__any_sync(0xffffffffu, cand != 0)) {
+    // warp-aggregated append: one shared-memory atomic per warp
+    const int cnt = __popc(cand);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int wbase = 0;
+    if (lane == 31) wbase = atomicAdd(&sflag[FF_NCAND], total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    int slot = wbase + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (cand & (0x80u << (8 * k))) scand[slot++] = (uint16_t)((y << 9) | (xb + k));
+  }
 }
 
 __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ FastTmaMaps maps,
@@ -116,19 +157,25 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const int wI = tw - 6, hI = th - 6;                 // interior (evaluated) pixels
   if (wI <= 0 || hI <= 0) return;
 
-  // shared layout: [flags 64 B][image tile th x tpw words][score (hI+2) x sp][survivor flag hI x sp]
-  //                [column->cell table][candidate list]
+  // shared layout: [flags 64 B][mbarrier][image tile][score plane (hI+2) x sp][column->cell table 512 B]
+  //                [word masks 256 B][active word list 64 B][list 1: survivors][list 2: corners][list 3: kept]
   const int xa = iniX & ~15;                          // tile origin: TMA needs a 16-byte aligned innermost coordinate
   const int off = iniX - xa;                          // 0..15: byte column of tile column 0
   const int tp = L.fastTP;                            // >= off + tw + 4 (the stage-B window reads word c+1), multiple of 16
   const int tpw = tp >> 2;
   const int sp = wI + 2;
-  int* sflag = reinterpret_cast<int*>(smem);          // [0..7] cellHasIni, [8] nCand, [9] nSurv, [10] emit base, [11] emit count, [12] cursor
+  const int CC = p.fastCandCap;                       // >= interior pixels of any tile, multiple of 64
+  int* sflag = reinterpret_cast<int*>(smem);
   unsigned long long* smbar = reinterpret_cast<unsigned long long*>(smem + 64);   // TMA completion barrier
   uint8_t* simg = smem + 128;                         // 128-byte aligned: TMA destination
   uint8_t* ssc = simg + (size_t)p.fastTileBytes;
   uint8_t* scell = ssc + (size_t)p.fastTileBytes;     // [wI] cell index of interior column x
-  uint16_t* scand = reinterpret_cast<uint16_t*>(scell + 512);
+  uint32_t* smask = reinterpret_cast<uint32_t*>(scell + 512);   // [ncw] bytes of word c that are tested in this pass
+  uint8_t* sact = scell + 512 + 256;                  // pass 1: word columns with a non-zero mask
+  uint16_t* scand = reinterpret_cast<uint16_t*>(scell + 1024);  // [CC]   list 1
+  uint16_t* scorn = scand + CC;                       // [CC/2] list 2
+  uint16_t* skept = scorn + CC / 2;                   // [CC/2] list 3
+  const int capCorn = CC / 2, capKept = CC / 2;
 
   // ---- A: load ----
   const uint8_t* img = L.pyr + (size_t)b * L.imgStride;
@@ -163,10 +210,21 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
       for (int c = lane; c < tpw; c += 32) d[c] = c < cw ? __ldg(g + c) : 0u;
     }
   }
+  const int c0 = (off + 3) / 4, c1 = (off + 3 + wI - 1) / 4;   // words that hold interior pixels
+  const int ncw = c1 - c0 + 1;                                 // <= 64
   {
-    for (int i = tid; i < (hI + 2) * sp; i += 256) ssc[i] = 0;
+    uint32_t* ssc32 = reinterpret_cast<uint32_t*>(ssc);
+    for (int i = tid; i < ((hI + 2) * sp + 3) / 4; i += 256) ssc32[i] = 0;
     for (int x = tid; x < wI; x += 256) scell[x] = (uint8_t)(x / L.wCell);
     if (tid < 16) sflag[tid] = 0;
+    // pass 0 tests every interior pixel: the mask only clips the first / last word to the interior columns
+    for (int k = tid; k < ncw; k += 256) {
+      const int xb = (c0 + k) * 4 - (off + 3);        // interior x of byte 0 (may be negative)
+      unsigned m = 0x80808080u;
+      if (xb < 0) m &= 0xffffffffu << (8 * (-xb));
+      if (xb + 3 >= wI) m &= 0xffffffffu >> (8 * (xb + 4 - wI));
+      smask[k] = m;
+    }
   }
   __syncthreads();                                    // (also publishes the mbarrier initialisation)
   if (L.useTma) {
@@ -181,150 +239,165 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
     }
   }
 
-  // ---- B: compass early reject, one 4-pixel word per thread-iteration ----
-  const int t = p.minTh;
-  const unsigned kGt = (unsigned)(0x7f - t) * 0x01010101u;
-  {
-    const uint32_t* simg32 = reinterpret_cast<const uint32_t*>(simg);
-    const int c0 = (off + 3) / 4, c1 = (off + 3 + wI - 1) / 4;   // words that hold interior pixels
-    const int ncw = c1 - c0 + 1;
-    for (int y = wid; y < hI; y += 8) {               // one warp per interior row, lanes over its 4-pixel words
-      const uint32_t* rowBase = simg32 + (y + 3) * tpw;
-      for (int cb = 0; cb < ncw; cb += 32) {          // warp-uniform trip count
-        const int c = c0 + min(cb + lane, ncw - 1);   // out-of-range lanes redo the last word and drop its result
-        const bool live = cb + lane < ncw;
-        const uint32_t* row = rowBase + c;
-        const uint32_t V = row[0];
-        const uint32_t r0 = row[3 * tpw], r8 = row[-3 * tpw];
-        const uint32_t r4 = __funnelshift_r(row[0], row[1], 24);     // bytes +3..+6
-        const uint32_t r12 = __funnelshift_r(row[-1], row[0], 8);    // bytes -3..0
-        const unsigned b0 = swar_gt_u8(__vabsdiffu4(r0, V), kGt), b4 = swar_gt_u8(__vabsdiffu4(r4, V), kGt);
-        const unsigned b8 = swar_gt_u8(__vabsdiffu4(r8, V), kGt), b12 = swar_gt_u8(__vabsdiffu4(r12, V), kGt);
-        unsigned cand = ((b0 | b8) & (b4 | b12));     // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
-        // drop bytes outside the interior columns
-        const int xb = c * 4 - (off + 3);             // interior x of byte 0 (may be negative)
-        if (xb < 0) cand &= 0xffffffffu << (8 * (-xb));
-        if (xb + 3 >= wI) cand &= 0xffffffffu >> (8 * (xb + 4 - wI));
-        if (!live) cand = 0;
-        if (__any_sync(0xffffffffu, cand != 0)) {
-          // warp-aggregated append: one shared-memory atomic per warp
-          const int cnt = __popc(cand);
-          int incl = cnt;
+  const uint32_t* simg32 = reinterpret_cast<const uint32_t*>(simg);
+  const int nPass = p.minTh < p.iniTh ? 2 : 1;        // a second pass at a threshold >= iniTh could not add anything
+#pragma unroll 1
+  for (int pass = 0; pass < nPass; ++pass) {
+    const int t = pass == 0 ? p.iniTh : p.minTh;
+    const unsigned kGt = (unsigned)(0x7f - t) * 0x01010101u;
+    if (pass == 1) {
+      // which cells did pass 0 leave empty?  (all threads read the flags written before the last barrier of pass 0)
+      int anyEmpty = 0;
+      for (int cidx = 0; cidx < nc; ++cidx) anyEmpty |= sflag[FF_CELL + cidx] == 0;
+      if (!anyEmpty) break;
+      __syncthreads();
+      if (tid == 0) { sflag[FF_NCAND] = 0; sflag[FF_NCORN] = 0; sflag[FF_OVF] = 0; sflag[FF_NACT] = 0; }
+      // restrict the word masks to the pixels of empty cells
+      for (int k = tid; k < ncw; k += 256) {
+        const int xb = (c0 + k) * 4 - (off + 3);
+        unsigned m = 0;
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-          }
-          const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int q = 0; q < 4; ++q) {
+          const int x = xb + q;
+          if (x >= 0 && x < wI && sflag[FF_CELL + scell[x]] == 0) m |= 0x80u << (8 * q);
+        }
+        smask[k] = m;
+      }
+      __syncthreads();
+      if (wid == 0) {                                 // ordered list of the word columns that still have work
+        for (int k0 = 0; k0 < ncw; k0 += 32) {
+          const int k = k0 + lane;
+          const bool a = k < ncw && smask[k] != 0;
+          const unsigned bal = __ballot_sync(0xffffffffu, a);
+          const int base = sflag[FF_NACT];
+          if (a) sact[base + __popc(bal & ((1u << lane) - 1))] = (uint8_t)k;
+          __syncwarp();
+          if (lane == 0) sflag[FF_NACT] = base + __popc(bal);
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- B: compass early reject, one 4-pixel word per thread-iteration ----
+    if (pass == 0) {
+      for (int y = wid; y < hI; y += 8) {               // one warp per interior row, lanes over its 4-pixel words
+        for (int cb = 0; cb < ncw; cb += 32) {          // warp-uniform trip count
+          const int k = min(cb + lane, ncw - 1);        // out-of-range lanes redo the last word and drop its result
+          const unsigned m = cb + lane < ncw ? smask[k] : 0u;
+          fast_stage_b(simg32, tpw, y, c0 + k, (c0 + k) * 4 - (off + 3), m, kGt, sflag, scand, lane);
+        }
+      }
+    } else {
+      const int nAct = sflag[FF_NACT];
+      const int total = hI * nAct;
+      for (int i0 = wid * 32; i0 < total; i0 += 256) {  // items = (row, active word), warp-uniform trip count
+        const int i = min(i0 + lane, total - 1);
+        const int y = i / nAct;
+        const int k = sact[i - y * nAct];
+        const unsigned m = i0 + lane < total ? smask[k] : 0u;
+        fast_stage_b(simg32, tpw, y, c0 + k, (c0 + k) * 4 - (off + 3), m, kGt, sflag, scand, lane);
+      }
+    }
+    __syncthreads();
+
+    // ---- C: exact score of the survivors; corners go to the score plane and to list 2 ----
+    const int nCand = sflag[FF_NCAND];
+    {
+      const int K0 = 256 * 65537;
+      for (int i0 = wid * 32; i0 < nCand; i0 += 256) {
+        const int i = i0 + lane;
+        bool corner = false;
+        int code = 0;
+        if (i < nCand) {
+          code = scand[i];
+          const int y = code >> 9, x = code & 511;
+          const uint8_t* c = simg + (y + 3) * tp + (x + 3 + off);
+          const int Kv = K0 - 65535 * (int)c[0];          // X = 65535*r + Kv = (256 + v - r) | (256 - v + r) << 16
+          unsigned X[16];
+          X[0] = 65535u * c[3 * tp] + Kv;       X[1] = 65535u * c[3 * tp + 1] + Kv;   X[2] = 65535u * c[2 * tp + 2] + Kv;
+          X[3] = 65535u * c[tp + 3] + Kv;       X[4] = 65535u * c[3] + Kv;            X[5] = 65535u * c[-tp + 3] + Kv;
+          X[6] = 65535u * c[-2 * tp + 2] + Kv;  X[7] = 65535u * c[-3 * tp + 1] + Kv;  X[8] = 65535u * c[-3 * tp] + Kv;
+          X[9] = 65535u * c[-3 * tp - 1] + Kv;  X[10] = 65535u * c[-2 * tp - 2] + Kv; X[11] = 65535u * c[-tp - 3] + Kv;
+          X[12] = 65535u * c[-3] + Kv;          X[13] = 65535u * c[tp - 3] + Kv;      X[14] = 65535u * c[2 * tp - 2] + Kv;
+          X[15] = 65535u * c[3 * tp - 1] + Kv;
+          const unsigned am = arc9_maxmin_x2(X);
+          const int arcmax = max((int)(am & 0xffffu), (int)(am >> 16)) - 256;
+          corner = arcmax > t && arcmax > 1;
+          if (corner) ssc[(y + 1) * sp + x + 1] = (uint8_t)(arcmax - 1);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, corner);
+        if (bal) {
           int wbase = 0;
-          if (lane == 31) wbase = atomicAdd(&sflag[8], total);
-          wbase = __shfl_sync(0xffffffffu, wbase, 31);
-          int slot = wbase + incl - cnt;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (cand & (0x80u << (8 * k))) scand[slot++] = (uint16_t)((y << 9) | (xb + k));
+          if (lane == 0) wbase = atomicAdd(&sflag[FF_NCORN], __popc(bal));
+          wbase = __shfl_sync(0xffffffffu, wbase, 0);
+          if (corner) {
+            const int slot = wbase + __popc(bal & ((1u << lane) - 1));
+            if (slot < capCorn) scorn[slot] = (uint16_t)code;
+            else sflag[FF_OVF] = 1;                       // (benign race: every writer stores 1)
+          }
         }
       }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- C: exact score of the survivors ----
-  {
-    const int nCand = sflag[8];
-    const int K0 = 256 * 65537;
-    for (int i = tid; i < nCand; i += 256) {
-      const int code = scand[i];
-      const int y = code >> 9, x = code & 511;
-      const uint8_t* c = simg + (y + 3) * tp + (x + 3 + off);
-      const int Kv = K0 - 65535 * (int)c[0];          // X = 65535*r + Kv = (256 + v - r) | (256 - v + r) << 16
-      unsigned X[16];
-      X[0] = 65535u * c[3 * tp] + Kv;       X[1] = 65535u * c[3 * tp + 1] + Kv;   X[2] = 65535u * c[2 * tp + 2] + Kv;
-      X[3] = 65535u * c[tp + 3] + Kv;       X[4] = 65535u * c[3] + Kv;            X[5] = 65535u * c[-tp + 3] + Kv;
-      X[6] = 65535u * c[-2 * tp + 2] + Kv;  X[7] = 65535u * c[-3 * tp + 1] + Kv;  X[8] = 65535u * c[-3 * tp] + Kv;
-      X[9] = 65535u * c[-3 * tp - 1] + Kv;  X[10] = 65535u * c[-2 * tp - 2] + Kv; X[11] = 65535u * c[-tp - 3] + Kv;
-      X[12] = 65535u * c[-3] + Kv;          X[13] = 65535u * c[tp - 3] + Kv;      X[14] = 65535u * c[2 * tp - 2] + Kv;
-      X[15] = 65535u * c[3 * tp - 1] + Kv;
-      const unsigned am = arc9_maxmin_x2(X);
-      const int arcmax = max((int)(am & 0xffffu), (int)(am >> 16)) - 256;
-      if (arcmax > t && arcmax > 1) ssc[(y + 1) * sp + x + 1] = (uint8_t)(arcmax - 1);
-    }
-  }
-  __syncthreads();
-
-  // ---- D: NMS inside the pixel's own cell (neighbours across a cell seam count as 0), on the candidate list only:
-  //         ~30 % of the pixels are candidates, ~12 % carry a score, ~1 % survive ----
-  uint32_t* ssurv = reinterpret_cast<uint32_t*>(simg);   // survivor list reuses the image plane (dead after stage C)
-  {
-    const int nCand = sflag[8];
-    for (int i0 = 0; i0 < nCand; i0 += 256) {
-      const int i = i0 + tid;
-      bool keep = false;
-      int code = 0, sc = 0;
-      if (i < nCand) {
-        code = scand[i];
-        const int y = code >> 9, x = code & 511;
-        const uint8_t* sp0 = ssc + (y + 1) * sp + x + 1;
-        sc = sp0[0];
-        // branch-free 3x3 maximum of the neighbours inside the pixel's own cell (others count as 0)
-        const int cell = scell[x];
-        const int mL = ((x > 0) & (scell[max(x - 1, 0)] == cell)) ? 0xff : 0, mR = ((x + 1 < wI) & (scell[x + 1] == cell)) ? 0xff : 0;
-        const int nL = max(max((int)sp0[-1], (int)sp0[-sp - 1]), (int)sp0[sp - 1]) & mL;
-        const int nR = max(max((int)sp0[1], (int)sp0[-sp + 1]), (int)sp0[sp + 1]) & mR;
-        const int nmax = max(max((int)sp0[-sp], (int)sp0[sp]), max(nL, nR));
-        keep = sc > nmax;                             // sc == 0 (no corner) can never exceed nmax >= 0
-        if (keep && sc >= p.iniTh) atomicOr(&sflag[cell], 1);
+    // ---- D: NMS inside the pixel's own cell over the corner list (over list 1 if list 2 overflowed) ----
+    {
+      const bool ovf = sflag[FF_OVF] != 0;
+      const uint16_t* src = ovf ? scand : scorn;
+      const int n = ovf ? nCand : sflag[FF_NCORN];
+      for (int i0 = wid * 32; i0 < n; i0 += 256) {
+        const int i = i0 + lane;
+        bool keep = false;
+        int code = 0;
+        if (i < n) {
+          code = src[i];
+          const int y = code >> 9, x = code & 511;
+          const uint8_t* sp0 = ssc + (y + 1) * sp + x + 1;
+          const int sc = sp0[0];
+          // branch-free 3x3 maximum of the neighbours inside the pixel's own cell (others count as 0)
+          const int cell = scell[x];
+          const int mL = ((x > 0) & (scell[max(x - 1, 0)] == cell)) ? 0xff : 0, mR = ((x + 1 < wI) & (scell[x + 1] == cell)) ? 0xff : 0;
+          const int nL = max(max((int)sp0[-1], (int)sp0[-sp - 1]), (int)sp0[sp - 1]) & mL;
+          const int nR = max(max((int)sp0[1], (int)sp0[-sp + 1]), (int)sp0[sp + 1]) & mR;
+          const int nmax = max(max((int)sp0[-sp], (int)sp0[sp]), max(nL, nR));
+          keep = sc > nmax;                             // sc == 0 (no corner) can never exceed nmax >= 0
+          if (keep && pass == 0) sflag[FF_CELL + cell] = 1;   // (benign race)
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+          int wbase = 0;
+          if (lane == 0) wbase = atomicAdd(&sflag[FF_NKEPT], __popc(m));
+          wbase = __shfl_sync(0xffffffffu, wbase, 0);
+          if (keep) {
+            const int slot = wbase + __popc(m & ((1u << lane) - 1));
+            if (slot < capKept) skept[slot] = (uint16_t)code;
+            else atomicExch(p.err, 5);
+          }
+        }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      int wbase = 0;
-      if (lane == 0 && m) wbase = atomicAdd(&sflag[9], __popc(m));
-      wbase = __shfl_sync(0xffffffffu, wbase, 0);
-      if (keep) ssurv[wbase + __popc(m & ((1u << lane) - 1))] = (uint32_t)code | ((uint32_t)sc << 16);
     }
+    __syncthreads();
   }
-  __syncthreads();
-  // cells that own a corner >= iniTh drop their weaker survivors (the 20 -> 7 fallback only applies to empty cells)
-  const int nSurv = sflag[9];
-  {
-    int cnt = 0;
-    for (int i = tid; i < nSurv; i += 256) {
-      const uint32_t v = ssurv[i];
-      const int x = v & 511, sc = v >> 16;
-      const bool out = !(sflag[scell[x]] && sc < p.iniTh);
-      if (!out) ssurv[i] = 0xffffffffu;
-      cnt += out;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0 && cnt) atomicAdd(&sflag[11], cnt);
-  }
-  __syncthreads();
-  int* candN = p.candN + b * p.nlevels + level;
-  if (tid == 0) {
-    sflag[10] = sflag[11] ? atomicAdd(candN, sflag[11]) : 0;   // ONE global atomic per tile
-    sflag[12] = 0;
-  }
+
+  // ---- E: emission (every kept keypoint is final; ONE global atomic per tile) ----
+  const int nKept = min(sflag[FF_NKEPT], capKept);
+  if (nKept == 0) return;
+  if (tid == 0) sflag[FF_BASE] = atomicAdd(p.candN + b * p.nlevels + level, nKept);
   __syncthreads();
   uint32_t* cand = p.cand + (size_t)b * p.candPerImage + L.candOfs;
-  const int base = sflag[10];
-  for (int i0 = 0; i0 < nSurv; i0 += 256) {
-    const int i = i0 + tid;
-    const uint32_t v = i < nSurv ? ssurv[i] : 0xffffffffu;
-    const bool k = v != 0xffffffffu;
-    const unsigned m = __ballot_sync(0xffffffffu, k);
-    int wbase = 0;
-    if (lane == 0 && m) wbase = atomicAdd(&sflag[12], __popc(m));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (k) {
-      const int slot = base + wbase + __popc(m & ((1u << lane) - 1));
-      if (slot < L.candCap) {
-        // coordinates relative to (minBorderX, minBorderY), as the reference stores them (:847-848)
-        const int x = v & 511, y = (v >> 9) & 127, sc = v >> 16;
-        const int rx = iniX + 3 + x - ORBX_MINB, ry = iniY + 3 + y - ORBX_MINB;
-        cand[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)sc << 24);
-      } else {
-        atomicExch(p.err, 1);
-      }
+  const int base = sflag[FF_BASE];
+  for (int i = tid; i < nKept; i += 256) {
+    const int code = skept[i];
+    const int y = code >> 9, x = code & 511;
+    const int sc = ssc[(y + 1) * sp + x + 1];
+    const int slot = base + i;
+    if (slot < L.candCap) {
+      // coordinates relative to (minBorderX, minBorderY), as the reference stores them (:847-848)
+      const int rx = iniX + 3 + x - ORBX_MINB, ry = iniY + 3 + y - ORBX_MINB;
+      cand[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)sc << 24);
+    } else {
+      atomicExch(p.err, 1);
     }
   }
 }
@@ -859,14 +932,16 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ E
 // ------------------------------------------------------------------------------------
 // host-side launchers (called from orbx_extract.cu)
 // ------------------------------------------------------------------------------------
-size_t orbx_fast_smem_bytes(int fastTileBytes) { return (size_t)4 * fastTileBytes + 128 + 512; }
+size_t orbx_fast_smem_bytes(int fastTileBytes, int fastCandCap) {
+  return (size_t)2 * fastTileBytes + 128 + 1024 + (size_t)4 * fastCandCap;   // planes + tables + lists 1..3 (uint16)
+}
 size_t orbx_octree_smem_bytes(int nodeCap) {
   return (size_t)nodeCap * (2 * sizeof(short4) + sizeof(unsigned long long) + 4 * 2 + 16 + 4 * 4);
 }
 
-int orbx_extract_configure(int nodeCap, int fastTileBytes) {
+int orbx_extract_configure(int nodeCap, int fastTileBytes, int fastCandCap) {
   ORBX_CUDA(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)orbx_fast_smem_bytes(fastTileBytes)));
+                                 (int)orbx_fast_smem_bytes(fastTileBytes, fastCandCap)));
   ORBX_CUDA(cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)orbx_octree_smem_bytes(nodeCap)));
   return ORBX_OK;
@@ -884,7 +959,7 @@ int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, 
     ORBX_LAUNCH(ctx);
   }
   ORBX_EV(1);
-  fast_cells_kernel<<<dim3(p.totalFastTiles, B), 256, orbx_fast_smem_bytes(p.fastTileBytes), st>>>(maps, p);
+  fast_cells_kernel<<<dim3(p.totalFastTiles, B), 256, orbx_fast_smem_bytes(p.fastTileBytes, p.fastCandCap), st>>>(maps, p);
   ORBX_LAUNCH(ctx);
   ORBX_EV(2);
   gauss7_kernel<<<dim3(p.totalBlurTiles, B), 256, 0, st>>>(p);

@@ -121,7 +121,7 @@ __device__ SE3d se3_exp(const double* u) {   // SE3Quat::exp, u = [omega, upsilo
     for (int i = 0; i < 9; ++i) { R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
   } else {
     const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta);
-    const double c = (theta - sin(theta)) / pow(theta, 3.0);
+    const double c = (theta - sin(theta)) / (theta * theta * theta);   // pow(theta, 3)
     for (int i = 0; i < 9; ++i) {
       const double id = (i % 4 == 0) ? 1.0 : 0.0;
       R[i] = id + a * O[i] + b * O2[i];
@@ -226,6 +226,21 @@ __device__ __forceinline__ void block_sum(double* v, double* s_red) {
     for (int w = 0; w < nw; ++w) s += s_red[w * NV + k];
     v[k] = s;
   }
+}
+
+// First two stages of block_sum only: lane butterfly, then one partial per warp into s_red[wid*NV + k].
+template <int NV>
+__device__ __forceinline__ void block_partials(double* v, double* s_red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  __syncthreads();   // protect s_red from the previous use
+  if (lane == 0)
+    for (int k = 0; k < NV; ++k) s_red[wid * NV + k] = v[k];
+  __syncthreads();
 }
 
 // Eigen::LDLT-like 6x6 solve with diagonal pivoting (largest |diagonal|); false on a negative pivot.
@@ -337,6 +352,87 @@ __device__ bool ldlt6_solve_warp(double* A, const double* b, double* x, int* per
   return true;
 }
 
+// Register/shuffle version of ldlt6_solve for ONE warp, no shared-memory round trips: lane i (< 6) keeps row i of the
+// symmetric matrix in registers.  Same arithmetic as the serial routine, element for element: the pivot is the first
+// largest |diagonal|, rows are exchanged between lanes and columns inside each lane, the trailing entry (i, j) is
+// A[i][j] - (A[max][k]*d)*A[min][k] exactly as the serial code computes the lower entry and mirrors it.  Lane k also
+// keeps the scaled column k as its row tail (L^T), so the backward substitution reads registers only.
+// A: 36 doubles (symmetric, row-major, lambda already on the diagonal), b: 6, x: 6 (shared or global memory).
+// All 32 lanes of the warp must call; every lane returns the same value.
+__device__ bool ldlt6_solve_shfl(const double* A, const double* b, double* x) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int li = lane < 6 ? lane : 5;            // lanes >= 6 shadow lane 5 (never a shuffle source)
+  double a[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) a[j] = A[li * 6 + j];
+  int perm = li;
+  bool positive = true;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double dg = a[0];
+#pragma unroll
+    for (int j = 1; j < 6; ++j)
+      if (li == j) dg = a[j];
+    int p = k;
+    double best = fabs(__shfl_sync(FULL, dg, k));
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      const double v = fabs(__shfl_sync(FULL, dg, i));
+      if (v > best) { best = v; p = i; }
+    }
+    if (p != k) {                                 // warp-uniform
+      const int src = lane == k ? p : (lane == p ? k : lane);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) a[j] = __shfl_sync(FULL, a[j], src);
+      perm = __shfl_sync(FULL, perm, src);
+      const double t = a[k];
+      double ap = t;
+#pragma unroll
+      for (int j = k + 1; j < 6; ++j)
+        if (p == j) { ap = a[j]; a[j] = t; }
+      a[k] = ap;
+    }
+    const double d = __shfl_sync(FULL, a[k], k);
+    if (d < 0) positive = false;
+    if (d == 0) continue;
+    double lik = a[k];
+    if (li > k) { lik = a[k] / d; a[k] = lik; }
+#pragma unroll
+    for (int j = k + 1; j < 6; ++j) {
+      const double ljk = __shfl_sync(FULL, lik, j);
+      if (li > k) {
+        const double hi = j <= li ? lik : ljk, lo = j <= li ? ljk : lik;   // (A[max(i,j)][k]*d)*A[min(i,j)][k]
+        a[j] = a[j] - hi * d * lo;
+      } else if (li == k) {
+        a[j] = ljk;                               // row k keeps L^T
+      }
+    }
+  }
+  if (!positive) return false;
+  double y = b[perm];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {                   // forward: y[i] -= L[i][j]*y[j], j ascending
+    const double yj = __shfl_sync(FULL, y, j);
+    if (li > j) y -= a[j] * yj;
+  }
+  {
+    double dg = a[0];
+#pragma unroll
+    for (int j = 1; j < 6; ++j)
+      if (li == j) dg = a[j];
+    y = (dg != 0) ? y / dg : 0.0;
+  }
+#pragma unroll
+  for (int j = 5; j > 0; --j) {                   // backward: y[i] -= L[j][i]*y[j], j descending
+    const double yj = __shfl_sync(FULL, y, j);
+    if (li < j) y -= a[j] * yj;
+  }
+  if (lane < 6) x[perm] = y;
+  __syncwarp();
+  return true;
+}
+
 // =====================================================================================
 // K11  PoseOptimization: one CTA per frame
 // =====================================================================================
@@ -363,8 +459,8 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
   const int E = A.edgeStart ? A.edgeCount[prob] : A.edgeOfs[prob + 1] - e0;
   __shared__ SE3d s_est, s_backup, s_init;
   __shared__ double s_red[(PO_NT / 32) * 28];
-  __shared__ double s_H[36], s_b[6], s_x[6], s_A[36], s_y[6];
-  __shared__ int s_ok, s_perm[6];
+  __shared__ double s_H[36], s_b[6], s_x[6], s_A[36], s_tot[28];
+  __shared__ int s_ok;
   const float* xw = A.xw + 3 * (size_t)e0;
   const float* obs = A.obs + 3 * (size_t)e0;
   const float* isg = A.invSigma2 + e0;
@@ -425,18 +521,27 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
           }
         }
       }
-      block_sum<28>(acc, s_red);
-      double currentChi = acc[27];
+      // same fixed-shape tree as block_sum (lane butterfly, then warps in index order), but the cross-warp stage is
+      // done once by 28 threads instead of redundantly by all 256
+      block_partials<28>(acc, s_red);
+      if (tid < 28) {
+        double s = 0;
+        for (int w = 0; w < PO_NT / 32; ++w) s += s_red[w * 28 + tid];
+        s_tot[tid] = s;
+      }
+      __syncthreads();
+      double currentChi = s_tot[27];
       const double iniChi = currentChi;
-      if (tid == 0) {
-        int idx = 0;
-        for (int i = 0; i < 6; ++i)
-          for (int j = i; j < 6; ++j) { s_H[i * 6 + j] = acc[idx]; s_H[j * 6 + i] = acc[idx]; ++idx; }
-        for (int i = 0; i < 6; ++i) s_b[i] = acc[21 + i];
+      if (tid < 36) {                             // unpack the 21 upper-triangle sums into the symmetric 6x6
+        const int i = tid / 6, j = tid - 6 * i;
+        const int lo = min(i, j), hi = max(i, j);
+        s_H[tid] = s_tot[6 * lo - (lo * (lo - 1)) / 2 + (hi - lo)];
+      } else if (tid < 42) {
+        s_b[tid - 36] = s_tot[21 + tid - 36];
       }
       if (it == 0) {
         double m = 0;
-        { int idx = 0; for (int i = 0; i < 6; ++i) { m = fmax(fabs(acc[idx]), m); idx += 6 - i; } }
+        { int idx = 0; for (int i = 0; i < 6; ++i) { m = fmax(fabs(s_tot[idx]), m); idx += 6 - i; } }
         lambda = 1e-50 * m;   // computeLambdaInit with _tau = 1e-50
         ni = 2;
         nBad = 0;
@@ -450,7 +555,7 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
           for (int i = tid; i < 36; i += 32) s_A[i] = s_H[i] + ((i % 7 == 0) ? lambda : 0.0);
           if (tid < 6) s_x[tid] = 0;
           __syncwarp();
-          const bool okSolve = ldlt6_solve_warp(s_A, s_b, s_x, s_perm, s_y);
+          const bool okSolve = ldlt6_solve_shfl(s_A, s_b, s_x);
           if (tid == 0) {
             s_ok = okSolve ? 1 : 0;
             double x[6];
@@ -483,7 +588,8 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
         scale += 1e-3;
         rho /= scale;
         if (rho > 0 && isfinite(tempChi)) {
-          double alpha = 1. - pow((2 * rho - 1), 3.0);
+          const double tr = 2 * rho - 1;
+          double alpha = 1. - tr * tr * tr;   // pow(2*rho-1, 3)
           alpha = fmin(alpha, 2. / 3.);
           const double scaleFactor = fmax(1. / 3., alpha);
           lambda *= scaleFactor;
@@ -907,7 +1013,8 @@ __global__ void __launch_bounds__(LBA_NT) lba_kernel(const LbaArgs A) {
         const double scale = sc[0] + 1e-3;
         rho /= scale;
         if (rho > 0 && isfinite(tempChi)) {
-          double alpha = 1. - pow((2 * rho - 1), 3.0);
+          const double tr = 2 * rho - 1;
+          double alpha = 1. - tr * tr * tr;   // pow(2*rho-1, 3)
           alpha = fmin(alpha, 2. / 3.);
           const double scaleFactor = fmax(1. / 3., alpha);
           lambda *= scaleFactor;
