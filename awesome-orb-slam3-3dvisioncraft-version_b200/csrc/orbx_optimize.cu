@@ -33,18 +33,34 @@ __device__ __forceinline__ Quat quat_from_R(const double* R) {
     q.y = (R[2] - R[6]) * t;
     q.z = (R[3] - R[1]) * t;
   } else {
+    // Eigen's branch on the largest diagonal element, written out per case (no dynamically indexed arrays:
+    // those would live in local memory)
     int i = 0;
-    if (R[4] > R[0]) i = 1;
-    if (R[8] > R[i * 3 + i]) i = 2;
-    const int j = (i + 1) % 3, k = (j + 1) % 3;
-    t = sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1.0);
-    double v[3];
-    v[i] = 0.5 * t;
-    t = 0.5 / t;
-    q.w = (R[k * 3 + j] - R[j * 3 + k]) * t;
-    v[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
-    v[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
-    q.x = v[0]; q.y = v[1]; q.z = v[2];
+    double rii = R[0];
+    if (R[4] > rii) { i = 1; rii = R[4]; }
+    if (R[8] > rii) i = 2;
+    if (i == 0) {
+      t = sqrt(R[0] - R[4] - R[8] + 1.0);
+      q.x = 0.5 * t;
+      t = 0.5 / t;
+      q.w = (R[7] - R[5]) * t;
+      q.y = (R[3] + R[1]) * t;
+      q.z = (R[6] + R[2]) * t;
+    } else if (i == 1) {
+      t = sqrt(R[4] - R[8] - R[0] + 1.0);
+      q.y = 0.5 * t;
+      t = 0.5 / t;
+      q.w = (R[2] - R[6]) * t;
+      q.z = (R[7] + R[5]) * t;
+      q.x = (R[1] + R[3]) * t;
+    } else {
+      t = sqrt(R[8] - R[0] - R[4] + 1.0);
+      q.z = 0.5 * t;
+      t = 0.5 / t;
+      q.w = (R[3] - R[1]) * t;
+      q.x = (R[2] + R[6]) * t;
+      q.y = (R[5] + R[7]) * t;
+    }
   }
   return q;
 }
@@ -115,13 +131,17 @@ __device__ SE3d se3_exp(const double* u) {   // SE3Quat::exp, u = [omega, upsilo
   const double theta = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
   const double O[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};
   double O2[9], R[9], V[9];
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) O2[i * 3 + j] = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
   if (theta < 0.00001) {
+#pragma unroll
     for (int i = 0; i < 9; ++i) { R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
   } else {
     const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta);
     const double c = (theta - sin(theta)) / (theta * theta * theta);   // pow(theta, 3)
+#pragma unroll
     for (int i = 0; i < 9; ++i) {
       const double id = (i % 4 == 0) ? 1.0 : 0.0;
       R[i] = id + a * O[i] + b * O2[i];
@@ -131,6 +151,7 @@ __device__ SE3d se3_exp(const double* u) {   // SE3Quat::exp, u = [omega, upsilo
   SE3d s;
   s.r = quat_from_R(R);
   quat_normalize(s.r);
+#pragma unroll
   for (int i = 0; i < 3; ++i) s.t[i] = V[i * 3] * up[0] + V[i * 3 + 1] * up[1] + V[i * 3 + 2] * up[2];
   return s;
 }
@@ -457,7 +478,7 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
   const int prob = blockIdx.x, tid = threadIdx.x;
   const int e0 = A.edgeStart ? A.edgeStart[prob] : A.edgeOfs[prob];
   const int E = A.edgeStart ? A.edgeCount[prob] : A.edgeOfs[prob + 1] - e0;
-  __shared__ SE3d s_est, s_backup, s_init;
+  __shared__ SE3d s_est, s_trial, s_init;
   __shared__ double s_red[(PO_NT / 32) * 28];
   __shared__ double s_H[36], s_b[6], s_x[6], s_A[36], s_tot[28];
   __shared__ int s_ok;
@@ -549,38 +570,55 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
       __syncthreads();
       double rho = 0;
       int qmax = 0;
+      // The reference's damping policy (tau = 1e-50, up to 100 trials, optimization_algorithm_levenberg.cpp:47-51)
+      // ends every round with ~19 rejected trials whose lambda is still far below one ulp of the diagonal.  A trial
+      // whose damped matrix H + lambda*I is bit-identical to the last SOLVED trial's reproduces that trial exactly
+      // (same update, same estimate, same residuals, same chi2), so it is replayed from the saved results instead of
+      // being solved again; only rho's denominator, which depends on lambda itself, is recomputed.
+      bool haveTrial = false;
+      double lastLambda = 0, trialChi = 0;
       do {
-        if (tid < 32) {                           // warp 0: 6x6 solve cooperatively, then lane 0 applies the update
-          if (tid == 0) s_backup = s_est;         // push()
-          for (int i = tid; i < 36; i += 32) s_A[i] = s_H[i] + ((i % 7 == 0) ? lambda : 0.0);
-          if (tid < 6) s_x[tid] = 0;
-          __syncwarp();
-          const bool okSolve = ldlt6_solve_shfl(s_A, s_b, s_x);
-          if (tid == 0) {
-            s_ok = okSolve ? 1 : 0;
-            double x[6];
-            for (int i = 0; i < 6; ++i) x[i] = s_x[i];
-            s_est = se3_mul(se3_exp(x), s_est);   // oplus: exp(update) * estimate
+        bool same = haveTrial;
+        if (same) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) same = same && (s_H[7 * i] + lambda == s_H[7 * i] + lastLambda);
+        }
+        if (!same) {
+          __syncthreads();                        // every thread is done with s_x / s_ok of the previous trial
+          if (tid < 32) {                         // warp 0: 6x6 solve cooperatively, then lane 0 applies the update
+            for (int i = tid; i < 36; i += 32) s_A[i] = s_H[i] + ((i % 7 == 0) ? lambda : 0.0);
+            if (tid < 6) s_x[tid] = 0;
+            __syncwarp();
+            const bool okSolve = ldlt6_solve_shfl(s_A, s_b, s_x);
+            if (tid == 0) {
+              s_ok = okSolve ? 1 : 0;
+              double x[6];
+              for (int i = 0; i < 6; ++i) x[i] = s_x[i];
+              s_trial = se3_mul(se3_exp(x), s_est);   // push(); oplus: exp(update) * estimate
+            }
           }
+          __syncthreads();
+          const SE3d trial = s_trial;
+          double chi[1] = {0};
+          for (int e = tid; e < E; e += PO_NT) {
+            if (outlier[e]) continue;
+            const double X[3] = {(double)xw[3 * e], (double)xw[3 * e + 1], (double)xw[3 * e + 2]};
+            double p[3], r[3];
+            se3_map(trial, X, p);
+            const bool st = obs[3 * e + 2] >= 0;
+            reproj_error(p, obs + 3 * e, st, A.fx, A.fy, A.cx, A.cy, A.bf, r);
+            err[3 * e] = r[0]; err[3 * e + 1] = r[1]; err[3 * e + 2] = r[2];
+            const double om = (double)isg[e];
+            const double c = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
+            double w;
+            chi[0] += robust ? huber_rho(st ? hStereo : hMono, c, w) : c;
+          }
+          block_sum<1>(chi, s_red);
+          trialChi = chi[0];
+          lastLambda = lambda;
+          haveTrial = true;
         }
-        __syncthreads();
-        const SE3d trial = s_est;
-        double chi[1] = {0};
-        for (int e = tid; e < E; e += PO_NT) {
-          if (outlier[e]) continue;
-          const double X[3] = {(double)xw[3 * e], (double)xw[3 * e + 1], (double)xw[3 * e + 2]};
-          double p[3], r[3];
-          se3_map(trial, X, p);
-          const bool st = obs[3 * e + 2] >= 0;
-          reproj_error(p, obs + 3 * e, st, A.fx, A.fy, A.cx, A.cy, A.bf, r);
-          err[3 * e] = r[0]; err[3 * e + 1] = r[1]; err[3 * e + 2] = r[2];
-          const double om = (double)isg[e];
-          const double c = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
-          double w;
-          chi[0] += robust ? huber_rho(st ? hStereo : hMono, c, w) : c;
-        }
-        block_sum<1>(chi, s_red);
-        double tempChi = chi[0];
+        double tempChi = trialChi;
         if (!s_ok) tempChi = 1.7976931348623157e308;
         rho = currentChi - tempChi;
         double scale = 0;
@@ -595,13 +633,13 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
           lambda *= scaleFactor;
           ni = 2;
           currentChi = tempChi;
-        } else {
-          lambda *= ni;
-          ni *= 2;
+          __syncthreads();                        // every thread has read s_est / s_trial of this trial
+          if (tid == 0) s_est = s_trial;          // keep the update (discardTop)
           __syncthreads();
-          if (tid == 0) s_est = s_backup;         // pop()
+        } else {
+          lambda *= ni;                           // pop(): s_est was never overwritten
+          ni *= 2;
         }
-        __syncthreads();
         ++qmax;
       } while (rho < 0 && qmax < 100);
       ++cj;

@@ -250,6 +250,13 @@ static bool ldlt_solve_plain(int n, const double* Ain, const double* b, double* 
 // ------------------------------------------------------------------------------------------------
 // Levenberg-Marquardt as modified in the reference's g2o.  `P` supplies the problem.
 // ------------------------------------------------------------------------------------------------
+// trial histogram of the last lm_optimize calls on this thread (diagnostics for DESIGN.md: how many damping trials
+// the reference's tau = 1e-50 / 100-trial policy spends per outer iteration); index = min(qmax, 31)
+static thread_local long g_lm_trials[32];
+extern "C" void ork_lm_trial_histogram(long* out32, int reset) {
+  for (int i = 0; i < 32; ++i) { out32[i] = g_lm_trials[i]; if (reset) g_lm_trials[i] = 0; }
+}
+
 template <typename P>
 static int lm_optimize(P& prob, int iterations, double userLambdaInit, const volatile uint8_t* stop) {
   double lambda = -1, ni = 2;
@@ -295,6 +302,7 @@ static int lm_optimize(P& prob, int iterations, double userLambdaInit, const vol
       ++qmax;
     } while (rho < 0 && qmax < 100 && !terminate());
     ++cj;
+    ++g_lm_trials[qmax < 31 ? qmax : 31];
     if (qmax == 100 || rho == 0) { ok = false; continue; }   // Terminate
     if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
     if (nBad >= 3) ok = false;
