@@ -830,22 +830,50 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-__global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ ExtractParams p, orbx_keypoint* kps,
-                                                       uint8_t* desc, int cap, int* nOut, int* monoOut) {
+#define DESC_NT 256
+
+__device__ __forceinline__ int dp4a_us(unsigned a, unsigned b_s8, int c) {   // unsigned bytes x signed bytes
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b_s8), "r"(c));
+  return d;
+}
+
+__global__ void __launch_bounds__(DESC_NT) describe_kernel(const __grid_constant__ ExtractParams p, orbx_keypoint* kps,
+                                                           uint8_t* desc, int cap, int* nOut, int* monoOut) {
   // lanes of a warp read 32 different pattern rows: stage the table in shared memory (constant
   // memory would serialise the divergent addresses)
   __shared__ int s_pat[256];
+  // IC_Angle weights: row |v| of the r=15 disc covers u in [-umax[v], umax[v]].  For the 32 bytes u = -15..16 of a
+  // patch row, s_icw[v*17 + j] packs the signed weights u (0 outside the disc) of bytes 4j..4j+3 and
+  // s_icw[v*17 + 8 + j] the 0/1 membership mask (stride 17: rows of different lanes fall into different banks)
+  __shared__ unsigned s_icw[16 * 17];
+  __shared__ int s_cnt[2 * ORBX_MAX_LEVELS];
+  const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 256; i += blockDim.x)   // transposed: word (byte row r, pair k) at [k*32 + r]
     s_pat[(i & 7) * 32 + (i >> 3)] = reinterpret_cast<const int*>(c_pattern)[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const int v = i >> 4, j = i & 7, isMask = (i >> 3) & 1;
+    const int d = c_umax[v];
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int u = 4 * j + k - 15;
+      if (u >= -d && u <= d) w |= (unsigned)((isMask ? 1 : u) & 0xff) << (8 * k);
+    }
+    s_icw[v * 17 + (isMask ? 8 : 0) + j] = w;
+  }
+  if (threadIdx.x < 2 * p.nlevels) {
+    const int l = threadIdx.x >> 1;
+    s_cnt[threadIdx.x] = (threadIdx.x & 1) ? p.selLap[b * p.nlevels + l] : p.selN[b * p.nlevels + l];
+  }
   __syncthreads();
-  const int b = blockIdx.y;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   // locate (level, i) of this warp's keypoint and the counts it needs for its output slot
   int level = -1, idx = 0, base = 0, lapBefore = 0, total = 0, totalLap = 0;
   {
     int acc = 0, lapAcc = 0;
     for (int l = 0; l < p.nlevels; ++l) {
-      const int nl = p.selN[b * p.nlevels + l];
+      const int nl = s_cnt[2 * l];
       if (level < 0 && warp < acc + nl) {
         level = l;
         idx = warp - acc;
@@ -853,7 +881,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ E
         lapBefore = lapAcc;
       }
       acc += nl;
-      lapAcc += p.selLap[b * p.nlevels + l];
+      lapAcc += s_cnt[2 * l + 1];
     }
     total = acc;
     totalLap = lapAcc;
@@ -869,18 +897,27 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ E
   const int px = rec.x & 0xffff, py = rec.x >> 16;
   const int score = rec.y & 0xff, lap = (rec.y >> 8) & 1, lapPrefix = rec.y >> 16;
 
-  // --- IC_Angle on the un-blurred level: lane = patch row ---
+  // --- IC_Angle on the un-blurred level: lane = patch row.  The 31 pixels of the row are fetched as nine aligned
+  //     32-bit words (the keypoint sits >= 19 px inside the image, so they never leave it), re-aligned with funnel
+  //     shifts and reduced with DP4A against the disc weights: m10 = sum u*I, row sum = sum I (exact integers) ---
   const uint8_t* img = L.pyr + (size_t)b * L.imgStride;
   int m10 = 0, m01 = 0;
   if (lane < 31) {
     const int dy = lane - 15;
-    const int d = c_umax[dy < 0 ? -dy : dy];
-    const uint8_t* row = img + (size_t)(py + dy) * L.pitch + px;
+    const int v = dy < 0 ? -dy : dy;
+    const uint8_t* rowp = img + (size_t)(py + dy) * L.pitch + (px - 15);
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(rowp) & 3);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp - mis);
+    uint32_t w[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) w[j] = __ldg(wp + j);
+    const unsigned* wt = s_icw + v * 17;
     int rs = 0;
-    for (int u = -d; u <= d; ++u) {
-      const int v = __ldg(row + u);
-      rs += v;
-      m10 += u * v;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t pix = __funnelshift_r(w[j], w[j + 1], 8 * mis);   // bytes u = 4j-15 .. 4j-12
+      m10 = dp4a_us(pix, wt[j], m10);
+      rs = (int)__dp4a(pix, wt[8 + j], (unsigned)rs);
     }
     m01 = dy * rs;
   }
@@ -894,7 +931,9 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ E
   // --- steered BRIEF on the blurred level: lane = descriptor byte ---
   const float factorPI = (float)(3.14159265358979323846 / 180.0);
   const float ang = __fmul_rn(angle, factorPI);
-  const float a = (float)cos((double)ang), bsn = (float)sin((double)ang);
+  double sd, cd;
+  sincos((double)ang, &sd, &cd);            // (float)cos((double)angle), (float)sin((double)angle): DESIGN.md §3
+  const float a = (float)cd, bsn = (float)sd;
   const uint8_t* bl = L.blur + (size_t)b * L.blurStride + (size_t)py * L.blurPitch + px;
   int val = 0;
 #pragma unroll
@@ -969,7 +1008,7 @@ int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, 
   ORBX_LAUNCH(ctx);
   ORBX_EV(4);
   const int warpsPerImage = p.selPerImage;
-  describe_kernel<<<dim3(div_up(warpsPerImage * 32, 128), B), 128, 0, st>>>(p, d_kps, d_desc, cap, d_n, d_mono);
+  describe_kernel<<<dim3(div_up(warpsPerImage * 32, DESC_NT), B), DESC_NT, 0, st>>>(p, d_kps, d_desc, cap, d_n, d_mono);
   ORBX_LAUNCH(ctx);
   ORBX_EV(5);
   ORBX_CUDA(cudaGetLastError());

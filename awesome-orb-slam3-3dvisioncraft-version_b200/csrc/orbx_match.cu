@@ -480,33 +480,16 @@ __global__ void __launch_bounds__(32) sbp_frame_resolve_kernel(const FrameDev* f
 //     then one CTA per frame for the median SAD rejection.
 // ------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) stereo_match_kernel(const StereoArgs* __restrict__ args) {
-  const StereoArgs& A = args[blockIdx.y];
-  const int nL = A.nLDev ? *A.nLDev : A.nL, nR = A.nRDev ? *A.nRDev : A.nR;
-  const int iL = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (iL >= nL) return;
-  if (lane == 0) { A.uright[iL] = -1.0f; A.depth[iL] = -1.0f; A.sad[iL] = -1; }
-  const orbx_keypoint kl = A.kpL[iL];
-  const int nRows = A.lh[0];
-  const int row = (int)kl.y;
-  if (row < 0 || row >= nRows) return;
-  const float minZ = A.b, minD = 0.f, maxD = __fdiv_rn(A.bf, minZ);
-  const float minU = __fsub_rn(kl.x, maxD), maxU = __fsub_rn(kl.x, minD);
-  if (maxU < 0) return;
-  const uint4* dl = reinterpret_cast<const uint4*>(A.descL + 32 * (size_t)iL);
-  unsigned key = 0xffffffffu;   // dist<<16 | iR : first minimum in ascending iR
-  for (int iR = lane; iR < nR; iR += 32) {
-    const orbx_keypoint kr = A.kpR[iR];
-    const float r = __fmul_rn(2.0f, A.scale[kr.octave]);
-    const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));
-    if (row < minr || row > maxr) continue;
-    if (kr.octave < kl.octave - 1 || kr.octave > kl.octave + 1) continue;
-    if (kr.x >= minU && kr.x <= maxU) {
-      const int d = hamming256(dl, reinterpret_cast<const uint4*>(A.descR + 32 * (size_t)iR));
-      key = min(key, ((unsigned)d << 16) | (unsigned)iR);
-    }
-  }
-  key = __reduce_min_sync(0xffffffffu, key);
+// Right keypoints are staged once per CTA in shared memory as compact records (x, row band, octave), so the row-band
+// scan of every left keypoint (the reference's vRowIndices lookup, src/Frame.cc:972-982,1011-1038) reads shared memory
+// instead of chasing kpR[i] -> scale[octave] through global memory for each of the nL x nR pairs.
+#define STEREO_NT 256
+#define STEREO_KPW 4          // left keypoints per warp
+#define STEREO_CHUNK 2048     // right keypoints staged per pass
+
+// sub-pixel refinement of one accepted descriptor match: 11x11 SAD over 11 shifts + parabola (src/Frame.cc:1041-1113)
+__device__ __forceinline__ void stereo_refine(const StereoArgs& A, int iL, const orbx_keypoint& kl, unsigned key, int lane,
+                                              float minD, float maxD) {
   if (key == 0xffffffffu) return;
   const int bestDist = key >> 16, bestIdxR = key & 0xffff;
   if (!(bestDist < TH_HIGH)) return;                 // bestDist starts at TH_HIGH: strict <
@@ -569,6 +552,76 @@ __global__ void __launch_bounds__(128) stereo_match_kernel(const StereoArgs* __r
     A.depth[iL] = __fdiv_rn(A.bf, disparity);
     A.uright[iL] = bestuR;
     A.sad[iL] = bestSad;
+  }
+}
+
+__global__ void __launch_bounds__(STEREO_NT) stereo_match_kernel(const StereoArgs* __restrict__ args) {
+  __shared__ float s_x[STEREO_CHUNK];
+  __shared__ int s_rows[STEREO_CHUNK];      // minr (low 16, signed) | maxr << 16
+  __shared__ uint8_t s_oct[STEREO_CHUNK];
+  const StereoArgs& A = args[blockIdx.y];
+  const int nL = A.nLDev ? *A.nLDev : A.nL, nR = A.nRDev ? *A.nRDev : A.nR;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if ((int)blockIdx.x * (STEREO_NT / 32) * STEREO_KPW >= nL) return;     // whole CTA out of range
+  const int iL0 = ((int)blockIdx.x * (STEREO_NT / 32) + wid) * STEREO_KPW;
+  const int nRows = A.lh[0];
+  const float minZ = A.b, minD = 0.f, maxD = __fdiv_rn(A.bf, minZ);
+  orbx_keypoint kl[STEREO_KPW];
+  bool valid[STEREO_KPW];
+  unsigned key[STEREO_KPW];   // dist<<16 | iR : first minimum in ascending iR
+  int row[STEREO_KPW];
+  float minU[STEREO_KPW], maxU[STEREO_KPW];
+#pragma unroll
+  for (int k = 0; k < STEREO_KPW; ++k) {
+    const int iL = iL0 + k;
+    valid[k] = iL < nL;
+    key[k] = 0xffffffffu;
+    row[k] = 0; minU[k] = maxU[k] = 0.f;
+    if (valid[k]) {
+      if (lane == 0) { A.uright[iL] = -1.0f; A.depth[iL] = -1.0f; A.sad[iL] = -1; }
+      kl[k] = A.kpL[iL];
+      row[k] = (int)kl[k].y;
+      minU[k] = __fsub_rn(kl[k].x, maxD);
+      maxU[k] = __fsub_rn(kl[k].x, minD);
+      valid[k] = row[k] >= 0 && row[k] < nRows && !(maxU[k] < 0);
+    }
+  }
+  for (int c0 = 0; c0 < nR; c0 += STEREO_CHUNK) {
+    const int n = min(STEREO_CHUNK, nR - c0);
+    __syncthreads();                                  // the previous chunk has been consumed
+    for (int i = tid; i < n; i += STEREO_NT) {
+      const orbx_keypoint kr = A.kpR[c0 + i];
+      const float r = __fmul_rn(2.0f, A.scale[kr.octave]);
+      const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));
+      s_x[i] = kr.x;
+      s_rows[i] = (minr & 0xffff) | (maxr << 16);
+      s_oct[i] = (uint8_t)kr.octave;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < STEREO_KPW; ++k) {
+      if (!valid[k]) continue;                        // warp-uniform
+      const uint4* dl = reinterpret_cast<const uint4*>(A.descL + 32 * (size_t)(iL0 + k));
+      const int octL = kl[k].octave;
+      for (int i = lane; i < n; i += 32) {
+        const int rows = s_rows[i];
+        const int minr = (int)(short)(rows & 0xffff), maxr = rows >> 16;
+        if (row[k] < minr || row[k] > maxr) continue;
+        const int octR = s_oct[i];
+        if (octR < octL - 1 || octR > octL + 1) continue;
+        const float x = s_x[i];
+        if (x >= minU[k] && x <= maxU[k]) {
+          const int d = hamming256(dl, reinterpret_cast<const uint4*>(A.descR + 32 * (size_t)(c0 + i)));
+          key[k] = min(key[k], ((unsigned)d << 16) | (unsigned)(c0 + i));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < STEREO_KPW; ++k) {
+    if (!valid[k]) continue;
+    const unsigned best = __reduce_min_sync(0xffffffffu, key[k]);
+    stereo_refine(A, iL0 + k, kl[k], best, lane, minD, maxD);
   }
 }
 
@@ -710,7 +763,7 @@ __global__ void __launch_bounds__(256) tri_rot_filter_kernel(const FrameDev* fra
 // batched launchers
 // =====================================================================================
 int orbx_launch_stereo_batch(orbx_ctx* ctx, cudaStream_t st, const StereoArgs* dArgs, int S, int maxL) {
-  stereo_match_kernel<<<dim3(div_up(maxL * 32, 128), S), 128, 0, st>>>(dArgs);
+  stereo_match_kernel<<<dim3(div_up(maxL, (STEREO_NT / 32) * STEREO_KPW), S), STEREO_NT, 0, st>>>(dArgs);
   ORBX_LAUNCH(ctx);
   stereo_median_kernel<<<S, 256, 0, st>>>(dArgs);
   ORBX_LAUNCH(ctx);
@@ -975,7 +1028,7 @@ int orbx_stereo_match(orbx_ctx* ctx, orbx_ext* extL, int bL, orbx_ext* extR, int
   StereoArgs* dA = S.upload(&A, 1);
   if (S.failed) return ORBX_ECUDA;
   if (nL > 0) {
-    stereo_match_kernel<<<dim3(div_up(nL * 32, 128), 1), 128, 0, st>>>(dA);
+    stereo_match_kernel<<<dim3(div_up(nL, (STEREO_NT / 32) * STEREO_KPW), 1), STEREO_NT, 0, st>>>(dA);
     ORBX_LAUNCH(ctx);
     stereo_median_kernel<<<1, 256, 0, st>>>(dA);
     ORBX_LAUNCH(ctx);
