@@ -268,48 +268,76 @@ __global__ void __launch_bounds__(32) sbp_map_resolve_kernel(const FrameDev* fra
   const int lane = threadIdx.x;
   for (int i = lane; i < F.n; i += 32) s_blocked[i] = A.kpBlocked ? A.kpBlocked[i] : 0;
   __syncwarp();
+  // The replay is a serial chain over the queries; what made it slow was three dependent global loads per query
+  // (count -> offset -> candidates).  Counts/offsets/flags of 32 queries are fetched with one coalesced load each and
+  // the first 32 candidates of 8 queries are prefetched together, so the chain itself only touches registers and
+  // shared memory.
+  const unsigned FULL = 0xffffffffu;
   int n = 0;
-  for (int q = 0; q < nq; ++q) {
-    const int cnt = A.candCnt[q];
-    int best = -1;
-    if (cnt > 0) {
-      const int ofs = A.candOfs[q];
-      // two smallest (dist, position) keys among non-blocked candidates
-      unsigned k1 = 0xffffffffu, k2 = 0xffffffffu;   // key = dist<<20 | position
-      for (int b0 = 0; b0 < cnt; b0 += 32) {
-        const int i = b0 + lane;
-        unsigned key = 0xffffffffu;
-        if (i < cnt) {
-          const uint32_t c = A.cand[ofs + i];
-          if (!s_blocked[c & 0xffff]) key = (((c >> 16) & 0x1ff) << 20) | (unsigned)i;
-        }
-        const unsigned m1 = __reduce_min_sync(0xffffffffu, key);
-        const unsigned m2 = __reduce_min_sync(0xffffffffu, key == m1 ? 0xffffffffu : key);
-        // merge (m1,m2) into (k1,k2)
-        if (m1 < k1) { k2 = min(k1, m2); k1 = m1; }
-        else { k2 = min(k2, m1); }
+  for (int q0 = 0; q0 < nq; q0 += 32) {
+    const int qq = q0 + lane;
+    const int myCnt = qq < nq ? A.candCnt[qq] : 0;
+    const int myOfs = qq < nq ? A.candOfs[qq] : 0;
+    const int myFlag = qq < nq ? A.flags[qq] : 0;
+    int myBest = -1;
+    const unsigned anyMask = __ballot_sync(FULL, myCnt > 0);
+#pragma unroll 1
+    for (int g = 0; g < 32; g += 8) {
+      if (((anyMask >> g) & 0xffu) == 0) continue;   // warp-uniform
+      uint32_t c[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int cnt = __shfl_sync(FULL, myCnt, g + u), ofs = __shfl_sync(FULL, myOfs, g + u);
+        c[u] = lane < cnt ? A.cand[ofs + lane] : 0xffffffffu;
       }
-      if (k1 != 0xffffffffu) {
-        const int bestDist = k1 >> 20;
-        const uint32_t c1 = A.cand[ofs + (k1 & 0xfffff)];
-        const int bestLevel = (c1 >> 25) & 0xf;
-        int bestDist2 = 256, bestLevel2 = -1;
-        if (k2 != 0xffffffffu) {
-          bestDist2 = k2 >> 20;
-          bestLevel2 = (A.cand[ofs + (k2 & 0xfffff)] >> 25) & 0xf;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int cnt = __shfl_sync(FULL, myCnt, g + u);
+        if (cnt == 0) continue;                      // warp-uniform
+        const int ofs = __shfl_sync(FULL, myOfs, g + u);
+        const int fl = __shfl_sync(FULL, myFlag, g + u);
+        // two smallest (dist, position) keys among non-blocked candidates
+        unsigned k1 = 0xffffffffu, k2 = 0xffffffffu;   // key = dist<<20 | position
+        for (int b0 = 0; b0 < cnt; b0 += 32) {
+          const int i = b0 + lane;
+          unsigned key = 0xffffffffu;
+          if (i < cnt) {
+            const uint32_t cc = b0 == 0 ? c[u] : A.cand[ofs + i];
+            if (!s_blocked[cc & 0xffff]) key = (((cc >> 16) & 0x1ff) << 20) | (unsigned)i;
+          }
+          const unsigned m1 = __reduce_min_sync(FULL, key);
+          const unsigned m2 = __reduce_min_sync(FULL, key == m1 ? 0xffffffffu : key);
+          // merge (m1,m2) into (k1,k2)
+          if (m1 < k1) { k2 = min(k1, m2); k1 = m1; }
+          else { k2 = min(k2, m1); }
         }
-        if (bestDist <= TH_HIGH) {
-          const bool reject = bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2);
-          if (!reject) {
-            best = c1 & 0xffff;
-            if (lane == 0) s_blocked[best] = (A.flags[q] & 2) ? 1 : 0;
-            ++n;
+        int best = -1;
+        if (k1 != 0xffffffffu) {
+          const int bestDist = k1 >> 20;
+          const int p1 = k1 & 0xfffff;
+          const uint32_t c1 = p1 < 32 ? __shfl_sync(FULL, c[u], p1) : A.cand[ofs + p1];
+          const int bestLevel = (c1 >> 25) & 0xf;
+          int bestDist2 = 256, bestLevel2 = -1;
+          if (k2 != 0xffffffffu) {
+            bestDist2 = k2 >> 20;
+            const int p2 = k2 & 0xfffff;
+            const uint32_t c2 = p2 < 32 ? __shfl_sync(FULL, c[u], p2) : A.cand[ofs + p2];
+            bestLevel2 = (c2 >> 25) & 0xf;
+          }
+          if (bestDist <= TH_HIGH) {
+            const bool reject = bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2);
+            if (!reject) {
+              best = c1 & 0xffff;
+              if (lane == 0) s_blocked[best] = (fl & 2) ? 1 : 0;
+              ++n;
+              __syncwarp();
+            }
           }
         }
+        if (lane == g + u) myBest = best;
       }
-      __syncwarp();
     }
-    if (lane == 0) A.bestIdx[q] = best;
+    if (qq < nq) A.bestIdx[qq] = myBest;
   }
   if (lane == 0) *A.nmatches = n;
 }
@@ -423,34 +451,59 @@ __global__ void __launch_bounds__(32) sbp_frame_resolve_kernel(const FrameDev* f
   for (int i = lane; i < F.n; i += 32) { s_blocked[i] = A.curBlocked ? A.curBlocked[i] : 0; A.curMatch[i] = -1; }
   if (lane < HISTO_LENGTH) s_hist[lane] = 0;
   __syncwarp();
+  // serial replay with coalesced per-32-query metadata and 8-query candidate prefetch (see sbp_map_resolve_kernel)
+  const unsigned FULL = 0xffffffffu;
   int n = 0;
-  for (int q = 0; q < nq; ++q) {
-    const int cnt = A.candCnt[q];
-    int best = -1;
-    if (cnt > 0) {
-      const int ofs = A.candOfs[q];
-      unsigned k1 = 0xffffffffu;
-      for (int b0 = 0; b0 < cnt; b0 += 32) {
-        const int i = b0 + lane;
-        unsigned key = 0xffffffffu;
-        if (i < cnt) {
-          const uint32_t c = A.cand[ofs + i];
-          if (!s_blocked[c & 0xffff]) key = (((c >> 16) & 0x1ff) << 20) | (unsigned)i;
-        }
-        k1 = min(k1, __reduce_min_sync(0xffffffffu, key));
+  for (int q0 = 0; q0 < nq; q0 += 32) {
+    const int qq = q0 + lane;
+    const int myCnt = qq < nq ? A.candCnt[qq] : 0;
+    const int myOfs = qq < nq ? A.candOfs[qq] : 0;
+    const int myFlag = qq < nq ? A.flags[qq] : 0;
+    int myBest = -1;
+    const unsigned anyMask = __ballot_sync(FULL, myCnt > 0);
+#pragma unroll 1
+    for (int g = 0; g < 32; g += 8) {
+      if (((anyMask >> g) & 0xffu) == 0) continue;   // warp-uniform
+      uint32_t c[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int cnt = __shfl_sync(FULL, myCnt, g + u), ofs = __shfl_sync(FULL, myOfs, g + u);
+        c[u] = lane < cnt ? A.cand[ofs + lane] : 0xffffffffu;
       }
-      if (k1 != 0xffffffffu && (int)(k1 >> 20) <= TH_HIGH) {
-        best = A.cand[ofs + (k1 & 0xfffff)] & 0xffff;
-        if (lane == 0) {
-          s_blocked[best] = (A.flags[q] & 2) ? 1 : 0;
-          A.curMatch[best] = q;
-          if (A.checkOri) s_hist[rot_bin(A.angle[q], F.kps[best].angle)]++;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int cnt = __shfl_sync(FULL, myCnt, g + u);
+        if (cnt == 0) continue;                      // warp-uniform
+        const int ofs = __shfl_sync(FULL, myOfs, g + u);
+        const int fl = __shfl_sync(FULL, myFlag, g + u);
+        unsigned k1 = 0xffffffffu;
+        for (int b0 = 0; b0 < cnt; b0 += 32) {
+          const int i = b0 + lane;
+          unsigned key = 0xffffffffu;
+          if (i < cnt) {
+            const uint32_t cc = b0 == 0 ? c[u] : A.cand[ofs + i];
+            if (!s_blocked[cc & 0xffff]) key = (((cc >> 16) & 0x1ff) << 20) | (unsigned)i;
+          }
+          k1 = min(k1, __reduce_min_sync(FULL, key));
         }
-        ++n;
+        int best = -1;
+        if (k1 != 0xffffffffu && (int)(k1 >> 20) <= TH_HIGH) {
+          const int p1 = k1 & 0xfffff;
+          const uint32_t c1 = p1 < 32 ? __shfl_sync(FULL, c[u], p1) : A.cand[ofs + p1];
+          best = c1 & 0xffff;
+          if (lane == 0) {
+            s_blocked[best] = (fl & 2) ? 1 : 0;
+            A.curMatch[best] = q0 + g + u;
+          }
+          ++n;
+          __syncwarp();
+        }
+        if (lane == g + u) myBest = best;
       }
-      __syncwarp();
     }
-    if (lane == 0) { A.matchIdx[q] = best; A.kept[q] = best >= 0; }
+    if (qq < nq) { A.matchIdx[qq] = myBest; A.kept[qq] = myBest >= 0; }
+    // rotation histogram of the accepted matches (counts only: order-independent)
+    if (A.checkOri && myBest >= 0) atomicAdd(&s_hist[rot_bin(A.angle[qq], F.kps[myBest].angle)], 1);
   }
   __syncwarp();
   if (A.checkOri) {
@@ -569,14 +622,14 @@ __global__ void __launch_bounds__(STEREO_NT) stereo_match_kernel(const StereoArg
   orbx_keypoint kl[STEREO_KPW];
   bool valid[STEREO_KPW];
   unsigned key[STEREO_KPW];   // dist<<16 | iR : first minimum in ascending iR
-  int row[STEREO_KPW];
+  int row[STEREO_KPW], octL[STEREO_KPW];
   float minU[STEREO_KPW], maxU[STEREO_KPW];
 #pragma unroll
   for (int k = 0; k < STEREO_KPW; ++k) {
     const int iL = iL0 + k;
     valid[k] = iL < nL;
     key[k] = 0xffffffffu;
-    row[k] = 0; minU[k] = maxU[k] = 0.f;
+    row[k] = 0; octL[k] = 0; minU[k] = maxU[k] = 0.f;
     if (valid[k]) {
       if (lane == 0) { A.uright[iL] = -1.0f; A.depth[iL] = -1.0f; A.sad[iL] = -1; }
       kl[k] = A.kpL[iL];
@@ -584,7 +637,9 @@ __global__ void __launch_bounds__(STEREO_NT) stereo_match_kernel(const StereoArg
       minU[k] = __fsub_rn(kl[k].x, maxD);
       maxU[k] = __fsub_rn(kl[k].x, minD);
       valid[k] = row[k] >= 0 && row[k] < nRows && !(maxU[k] < 0);
+      octL[k] = kl[k].octave;
     }
+    if (!valid[k]) row[k] = -32768;
   }
   for (int c0 = 0; c0 < nR; c0 += STEREO_CHUNK) {
     const int n = min(STEREO_CHUNK, nR - c0);
@@ -598,20 +653,18 @@ __global__ void __launch_bounds__(STEREO_NT) stereo_match_kernel(const StereoArg
       s_oct[i] = (uint8_t)kr.octave;
     }
     __syncthreads();
+    // every staged record is tested against the warp's 4 left keypoints at once (one set of shared-memory loads)
+    for (int i = lane; i < n; i += 32) {
+      const int rows = s_rows[i];
+      const int minr = (int)(short)(rows & 0xffff), maxr = rows >> 16;
+      const int octR = s_oct[i];
+      const float x = s_x[i];
 #pragma unroll
-    for (int k = 0; k < STEREO_KPW; ++k) {
-      if (!valid[k]) continue;                        // warp-uniform
-      const uint4* dl = reinterpret_cast<const uint4*>(A.descL + 32 * (size_t)(iL0 + k));
-      const int octL = kl[k].octave;
-      for (int i = lane; i < n; i += 32) {
-        const int rows = s_rows[i];
-        const int minr = (int)(short)(rows & 0xffff), maxr = rows >> 16;
-        if (row[k] < minr || row[k] > maxr) continue;
-        const int octR = s_oct[i];
-        if (octR < octL - 1 || octR > octL + 1) continue;
-        const float x = s_x[i];
-        if (x >= minU[k] && x <= maxU[k]) {
-          const int d = hamming256(dl, reinterpret_cast<const uint4*>(A.descR + 32 * (size_t)(c0 + i)));
+      for (int k = 0; k < STEREO_KPW; ++k) {
+        // (an invalid left keypoint has row = -32768: outside every band)
+        if (row[k] >= minr && row[k] <= maxr && octR >= octL[k] - 1 && octR <= octL[k] + 1 && x >= minU[k] && x <= maxU[k]) {
+          const int d = hamming256(reinterpret_cast<const uint4*>(A.descL + 32 * (size_t)(iL0 + k)),
+                                   reinterpret_cast<const uint4*>(A.descR + 32 * (size_t)(c0 + i)));
           key[k] = min(key[k], ((unsigned)d << 16) | (unsigned)(c0 + i));
         }
       }
@@ -625,36 +678,60 @@ __global__ void __launch_bounds__(STEREO_NT) stereo_match_kernel(const StereoArg
   }
 }
 
-// median of the accepted SADs (element size/2 of the sorted list) -> reject sad >= 1.5*1.4*median
+// median of the accepted SADs (element size/2 of the sorted list) -> reject sad >= 1.5*1.4*median (src/Frame.cc:1119-1131).
+// A SAD of 121 int16 differences is < 2^16, so the rank-size/2 element is found by a two-level 256-bin radix select.
 __global__ void __launch_bounds__(256) stereo_median_kernel(const StereoArgs* __restrict__ args) {
   const StereoArgs& A = args[blockIdx.x];
   const int nL = A.nLDev ? *A.nLDev : A.nL;
   const int* sad = A.sad;
   float* uright = A.uright;
   float* depth = A.depth;
-  __shared__ int s_m, s_med;
-  if (threadIdx.x == 0) { s_m = 0; s_med = -1; }
+  __shared__ int s_hist[256];
+  __shared__ int s_m, s_bin, s_before, s_med;
+  const int tid = threadIdx.x;
+  s_hist[tid] = 0;
+  if (tid == 0) { s_m = 0; s_med = -1; }
   __syncthreads();
   int local = 0;
-  for (int i = threadIdx.x; i < nL; i += 256) local += sad[i] >= 0;
+  for (int i = tid; i < nL; i += 256) {
+    const int d = sad[i];
+    if (d >= 0) { ++local; atomicAdd(&s_hist[min(d >> 8, 255)], 1); }
+  }
   if (local) atomicAdd(&s_m, local);
   __syncthreads();
   const int M = s_m;
   if (M == 0) return;
   const int target = M / 2;
-  for (int i = threadIdx.x; i < nL; i += 256) {
-    const int d = sad[i];
-    if (d < 0) continue;
-    int rank = 0;
-    for (int j = 0; j < nL; ++j) {
-      const int e = sad[j];
-      rank += (e >= 0) && (e < d || (e == d && j < i));
+  if (tid == 0) {
+    int cum = 0, bin = 0;
+    for (; bin < 255; ++bin) {
+      if (cum + s_hist[bin] > target) break;
+      cum += s_hist[bin];
     }
-    if (rank == target) s_med = d;
+    s_bin = bin;
+    s_before = cum;
+  }
+  __syncthreads();
+  const int bin = s_bin;
+  __syncthreads();
+  s_hist[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < nL; i += 256) {
+    const int d = sad[i];
+    if (d >= 0 && min(d >> 8, 255) == bin) atomicAdd(&s_hist[d & 255], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int cum = s_before, lo = 0;
+    for (; lo < 255; ++lo) {
+      if (cum + s_hist[lo] > target) break;
+      cum += s_hist[lo];
+    }
+    s_med = (bin << 8) | lo;
   }
   __syncthreads();
   const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), (float)s_med);
-  for (int i = threadIdx.x; i < nL; i += 256) {
+  for (int i = tid; i < nL; i += 256) {
     const int d = sad[i];
     if (d >= 0 && !((float)d < thDist)) { uright[i] = -1.0f; depth[i] = -1.0f; }
   }
