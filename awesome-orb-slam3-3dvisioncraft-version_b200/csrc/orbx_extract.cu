@@ -47,6 +47,8 @@ struct orbx_ext {
   uint2* d_sel = nullptr;
   size_t selElems = 0;
   int* d_counts = nullptr;       // candN | selN | selLap | err
+  int4* d_tiles = nullptr;       // FAST tile records of the current geometry
+  size_t tilesCap = 0;
   orbx_keypoint* d_kps = nullptr;
   uint8_t* d_desc = nullptr;
   int* d_nOut = nullptr;         // nOut[maxB] | mono[maxB]
@@ -128,6 +130,7 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   size_t off = 0;
   int tile = 0, btile = 0, cand = 0, sel = 0, fastBytes = 0, fastCand = 0;
   std::vector<int16_t> htab;
+  std::vector<int4> htiles;
   for (int l = 0; l < e->nlevels; ++l) {
     LevelParams& L = P.lv[l];
     level_dims(e, w, h, l, &L.w, &L.h);
@@ -152,7 +155,25 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
     L.useTma = 0;
     L.tilesPerRow = div_up(L.nCols, L.fastCells);
     L.tileStart = tile;
-    tile += L.tilesPerRow * L.nRows;
+    // tile records: one cell row x up to fastCells cells each; cells/rows the reference skips (src/ORBextractor.cc:
+    // 792-804: iniY >= maxBorderY-3, iniX >= maxBorderX-6) are dropped here, so every CTA has work
+    for (int ci = 0; ci < L.nRows; ++ci) {
+      const int iniY = ORBX_MINB + ci * L.hCell;
+      if (iniY >= L.maxBY - 3) continue;
+      const int maxY = std::min(iniY + L.hCell + 6, L.maxBY);
+      for (int j0 = 0; j0 < L.nCols; j0 += L.fastCells) {
+        const int iniX = ORBX_MINB + j0 * L.wCell;
+        if (iniX >= L.maxBX - 6) continue;
+        int nc = std::min(L.fastCells, L.nCols - j0);
+        while (nc > 0 && ORBX_MINB + (j0 + nc - 1) * L.wCell >= L.maxBX - 6) --nc;
+        if (nc <= 0) continue;
+        const int maxX = std::min(iniX + nc * L.wCell + 6, L.maxBX);
+        const int tw = maxX - iniX, th = maxY - iniY;
+        if (tw - 6 <= 0 || th - 6 <= 0) continue;
+        htiles.push_back(make_int4(l | (nc << 8), iniX | (iniY << 16), tw | (th << 16), (65536 + L.wCell - 1) / L.wCell));
+      }
+    }
+    tile = (int)htiles.size();
     // one shared-memory plane holds the image tile (fastTP x fastTH) or the score plane ((wI+2) x (hI+2))
     fastBytes = std::max(fastBytes, (int)align_up((size_t)L.fastTP * (L.hCell + 8), 128));
     fastCand = std::max(fastCand, (int)align_up((size_t)(L.fastCells * L.wCell) * L.hCell, 64));
@@ -224,7 +245,17 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   }
   if (!htab.empty())
     ORBX_CUDA(cudaMemcpyAsync(e->d_tab, htab.data(), htab.size() * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
-  ORBX_CUDA(cudaStreamSynchronize(e->stream));  // htab is a local
+  if (htiles.size() > e->tilesCap) {
+    cudaFree(e->d_tiles);
+    e->d_tiles = nullptr;
+    e->tilesCap = 0;
+    ORBX_CUDA(cudaMalloc(&e->d_tiles, htiles.size() * sizeof(int4)));
+    e->tilesCap = htiles.size();
+  }
+  if (!htiles.empty())
+    ORBX_CUDA(cudaMemcpyAsync(e->d_tiles, htiles.data(), htiles.size() * sizeof(int4), cudaMemcpyHostToDevice, e->stream));
+  ORBX_CUDA(cudaStreamSynchronize(e->stream));  // htab / htiles are locals
+  P.fastTiles = e->d_tiles;
   P.tab = e->d_tab;
   P.candPerImage = cand;
   P.selPerImage = sel;
@@ -360,6 +391,7 @@ void orbx_extractor_destroy(orbx_ext* e) {
   cudaFree(e->d_keyNode);
   cudaFree(e->d_sel);
   cudaFree(e->d_counts);
+  cudaFree(e->d_tiles);
   cudaFree(e->d_kps);
   cudaFree(e->d_desc);
   cudaFree(e->d_nOut);

@@ -44,6 +44,7 @@ struct ExtractParams {
   int fastTileBytes;               // bytes of one FAST shared-memory plane (max over levels, 16-aligned)
   int fastCandCap;                 // >= interior (evaluated) pixels of any FAST tile, multiple of 64
   const int16_t* tab;              // resize coefficient tables
+  const int4* fastTiles;           // [totalFastTiles] host-built FAST tile records (see configure_geometry)
   uint32_t* cand;                  // [B][candPerImage] packed x | y<<12 | score<<24 (coords rel. to minBorder)
   int* candN;                      // [B][nlevels]
   uint16_t* keyNode;               // [B][candPerImage] quadtree scratch

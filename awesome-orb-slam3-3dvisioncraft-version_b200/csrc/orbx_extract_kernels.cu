@@ -91,6 +91,14 @@ __device__ __forceinline__ unsigned arc9_maxmin_x2(const unsigned (&X)[16]) {
   return vmax3(vmax3(a0, a1, a2), vmax3(a3, a4, m[15]), a0);
 }
 
+// atom.shared.add issued exactly as written (nvcc wraps atomicAdd in a warp-aggregation sequence of its own; the callers
+// below already aggregate per warp)
+__device__ __forceinline__ int smem_atomic_add(int* addr, int v) {
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(addr)), "r"(v) : "memory");
+  return old;
+}
+
 // shared-memory flag words of fast_cells_kernel
 enum { FF_CELL = 0 /* [0..7] cell has a pass-0 keypoint */, FF_NCAND = 8, FF_NKEPT = 9, FF_BASE = 10, FF_NCORN = 11,
        FF_OVF = 12, FF_NACT = 13, FF_EMPTY = 14 };
@@ -107,55 +115,36 @@ __device__ __forceinline__ void fast_stage_b(const uint32_t* simg32, int tpw, in
   const unsigned b0 = swar_gt_u8(__vabsdiffu4(r0, V), kGt), b4 = swar_gt_u8(__vabsdiffu4(r4, V), kGt);
   const unsigned b8 = swar_gt_u8(__vabsdiffu4(r8, V), kGt), b12 = swar_gt_u8(__vabsdiffu4(r12, V), kGt);
   const unsigned cand = ((b0 | b8) & (b4 | b12)) & m;          // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
-  if (__any_sync(0xffffffffu, cand != 0)) {
-    // warp-aggregated append: one shared-memory atomic per warp
-    const int cnt = __popc(cand);
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int wbase = 0;
-    if (lane == 31) wbase = atomicAdd(&sflag[FF_NCAND], total);
-    wbase = __shfl_sync(0xffffffffu, wbase, 31);
-    int slot = wbase + incl - cnt;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (cand & (0x80u << (8 * k))) scand[slot++] = (uint16_t)((y << 9) | (xb + k));
-  }
+  // warp-aggregated append (list order is irrelevant): one ballot per byte position gives every surviving pixel
+  // its slot, one shared-memory atomic per warp reserves the range
+  const unsigned ltm = (1u << lane) - 1;
+  const unsigned v0 = __ballot_sync(0xffffffffu, cand & 0x80u), v1 = __ballot_sync(0xffffffffu, cand & 0x8000u);
+  const unsigned v2 = __ballot_sync(0xffffffffu, cand & 0x800000u), v3 = __ballot_sync(0xffffffffu, cand & 0x80000000u);
+  if ((v0 | v1 | v2 | v3) == 0) return;
+  const int n0 = __popc(v0), n1 = __popc(v1), n2 = __popc(v2), n3 = __popc(v3);
+  int wbase = 0;
+  if (lane == 0) wbase = smem_atomic_add(&sflag[FF_NCAND], n0 + n1 + n2 + n3);
+  wbase = __shfl_sync(0xffffffffu, wbase, 0);
+  const unsigned code = (unsigned)((y << 9) + xb);   // xb may be negative in the first word; xb + k never is
+  if (cand & 0x80u) scand[wbase + __popc(v0 & ltm)] = (uint16_t)code;
+  if (cand & 0x8000u) scand[wbase + n0 + __popc(v1 & ltm)] = (uint16_t)(code + 1);
+  if (cand & 0x800000u) scand[wbase + n0 + n1 + __popc(v2 & ltm)] = (uint16_t)(code + 2);
+  if (cand & 0x80000000u) scand[wbase + n0 + n1 + n2 + __popc(v3 & ltm)] = (uint16_t)(code + 3);
 }
 
 __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ FastTmaMaps maps,
                                                          const __grid_constant__ ExtractParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // locate (level, cell row, first cell)
-  const int tile = blockIdx.x;
-  int level = 0;
-#pragma unroll 1
-  for (int l = 1; l < p.nlevels; ++l)
-    if (tile >= p.lv[l].tileStart) level = l;
+  // tile record (host-built: only tiles that own at least one evaluated pixel are listed):
+  //   x = level | nc << 8, y = iniX | iniY << 16, z = tw | th << 16, w = ceil(65536 / wCell)
+  const int4 trec = __ldg(p.fastTiles + blockIdx.x);
+  const int level = trec.x & 0xff, nc = trec.x >> 8;
   const LevelParams& L = p.lv[level];
-  const int lt = tile - L.tileStart;
-  const int ci = lt / L.tilesPerRow;
-  const int j0 = (lt - ci * L.tilesPerRow) * L.fastCells;
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-
-  const int iniY = ORBX_MINB + ci * L.hCell;
-  if (iniY >= L.maxBY - 3) return;
-  const int maxY = min(iniY + L.hCell + 6, L.maxBY);
-  const int iniX = ORBX_MINB + j0 * L.wCell;
-  if (iniX >= L.maxBX - 6) return;
-  // cells j0 .. j0+nc-1 ; the last one of the level may be truncated or skipped
-  int nc = min(L.fastCells, L.nCols - j0);
-  while (nc > 0 && ORBX_MINB + (j0 + nc - 1) * L.wCell >= L.maxBX - 6) --nc;
-  if (nc <= 0) return;
-  const int maxX = min(iniX + nc * L.wCell + 6, L.maxBX);
-  const int tw = maxX - iniX, th = maxY - iniY;       // tile incl. 3-px ring halo
+  const int iniX = trec.y & 0xffff, iniY = trec.y >> 16;
+  const int tw = trec.z & 0xffff, th = trec.z >> 16;  // tile incl. 3-px ring halo
   const int wI = tw - 6, hI = th - 6;                 // interior (evaluated) pixels
-  if (wI <= 0 || hI <= 0) return;
 
   // shared layout: [flags 64 B][mbarrier][image tile][score plane (hI+2) x sp][column->cell table 512 B]
   //                [word masks 256 B][active word list 64 B][list 1: survivors][list 2: corners][list 3: kept]
@@ -215,7 +204,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   {
     uint32_t* ssc32 = reinterpret_cast<uint32_t*>(ssc);
     for (int i = tid; i < ((hI + 2) * sp + 3) / 4; i += 256) ssc32[i] = 0;
-    for (int x = tid; x < wI; x += 256) scell[x] = (uint8_t)(x / L.wCell);
+    for (int x = tid; x < wI; x += 256) scell[x] = (uint8_t)((x * trec.w) >> 16);   // x / wCell, exact for x < 512
     if (tid < 16) sflag[tid] = 0;
     // pass 0 tests every interior pixel: the mask only clips the first / last word to the interior columns
     for (int k = tid; k < ncw; k += 256) {
@@ -329,7 +318,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
         const unsigned bal = __ballot_sync(0xffffffffu, corner);
         if (bal) {
           int wbase = 0;
-          if (lane == 0) wbase = atomicAdd(&sflag[FF_NCORN], __popc(bal));
+          if (lane == 0) wbase = smem_atomic_add(&sflag[FF_NCORN], __popc(bal));
           wbase = __shfl_sync(0xffffffffu, wbase, 0);
           if (corner) {
             const int slot = wbase + __popc(bal & ((1u << lane) - 1));
@@ -367,7 +356,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (m) {
           int wbase = 0;
-          if (lane == 0) wbase = atomicAdd(&sflag[FF_NKEPT], __popc(m));
+          if (lane == 0) wbase = smem_atomic_add(&sflag[FF_NKEPT], __popc(m));
           wbase = __shfl_sync(0xffffffffu, wbase, 0);
           if (keep) {
             const int slot = wbase + __popc(m & ((1u << lane) - 1));
