@@ -97,6 +97,14 @@ def load_library():
     L.orbx_tracker_set_profiling.argtypes = [vp, i]
     L.orbx_tracker_stage_ms.argtypes = [vp, vp]
     L.orbx_pyramid_level.argtypes = [vp, i, i, vp, i, vp, vp]
+    L.orbx_vocabulary_load.restype = vp
+    L.orbx_vocabulary_load.argtypes = [vp, C.c_char_p]
+    L.orbx_vocabulary_from_memory.restype = vp
+    L.orbx_vocabulary_from_memory.argtypes = [vp, vp, C.c_size_t]
+    L.orbx_vocabulary_destroy.argtypes = [vp]
+    L.orbx_vocabulary_info.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.orbx_vocabulary_transform.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp]
+    L.orbx_vocabulary_transform_batch_device.argtypes = [vp, i, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_debug_candidates.argtypes = [vp, i, i, vp, vp, i, vp]
     _LIB = L
     return L
@@ -463,3 +471,42 @@ class Tracker:
         ms = np.zeros(len(self.STAGES), np.float32)
         _check(load_library().orbx_tracker_stage_ms(self.h, _p(ms)), "orbx_tracker_stage_ms")
         return ms
+
+
+class ORBVocabulary:
+    """DBoW2 ORBVocabulary on the device (include/ORBVocabulary.h; Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h).
+    `source` is a path to a DBoW2 binary vocabulary (the reference's Vocabulary/ORBvoc.bin) or its bytes."""
+
+    def __init__(self, ctx, source):
+        L = load_library()
+        self.ctx = ctx
+        if isinstance(source, (bytes, bytearray, memoryview, np.ndarray)):
+            buf = np.frombuffer(bytes(source), np.uint8)
+            self.h = L.orbx_vocabulary_from_memory(ctx.h, _p(buf), buf.size)
+        else:
+            self.h = L.orbx_vocabulary_load(ctx.h, str(source).encode())
+        if not self.h:
+            raise OrbxError("orbx_vocabulary: " + L.orbx_last_error().decode(errors="replace"))
+        v = (C.c_int * 6)()
+        L.orbx_vocabulary_info(self.h, *[C.byref(v, 4 * k) for k in range(6)])
+        self.k, self.L, self.n_nodes, self.n_words, self.scoring, self.weighting = [int(x) for x in v]
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                load_library().orbx_vocabulary_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def transform(self, desc, levelsup=4):
+        """-> (bow_word int32[nb], bow_value float64[nb], fv_node int32[nn], fv_off int32[nn+1], fv_idx int32[...])"""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        bw, bv = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+        fn, fo, fi = np.zeros(max(n, 1), np.int32), np.zeros(n + 1, np.int32), np.zeros(max(n, 1), np.int32)
+        nb, nn = C.c_int32(0), C.c_int32(0)
+        _check(load_library().orbx_vocabulary_transform(self.h, _p(desc), n, levelsup, _p(bw), _p(bv), C.byref(nb), _p(fn),
+                                                        _p(fo), _p(fi), C.byref(nn)), "orbx_vocabulary_transform")
+        nb, nn = nb.value, nn.value
+        return bw[:nb].copy(), bv[:nb].copy(), fn[:nn].copy(), fo[:nn + 1].copy(), fi[:fo[nn]].copy()

@@ -237,6 +237,42 @@ int orbx_search_for_triangulation(orbx_ctx *ctx, const orbx_frame_desc *kf1,
                                   int32_t *nmatches);
 
 /* ====================================================================================
+ * DBoW2 vocabulary: the step that feeds SearchForTriangulation / SearchByBoW.
+ * ================================================================================== */
+typedef struct orbx_voc orbx_voc;
+
+/* TemplatedVocabulary::loadFromBinaryFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1442-1478): the
+ * reference's Vocabulary/ORBvoc.bin format — header {uint32 n_nodes (root included), uint32 node_size = 41,
+ * int32 k, int32 L, int32 scoring, int32 weighting}, then per non-root node {int32 parent, uint8 desc[32],
+ * float32 weight, uint8 is_leaf}.  The tree is uploaded once and stays resident in HBM.  NULL on failure. */
+orbx_voc *orbx_vocabulary_load(orbx_ctx *ctx, const char *path);
+orbx_voc *orbx_vocabulary_from_memory(orbx_ctx *ctx, const void *data, size_t bytes);
+void orbx_vocabulary_destroy(orbx_voc *voc);
+/* m_k, m_L, node count (root included), word count, ScoringType, WeightingType; any pointer may be NULL. */
+int orbx_vocabulary_info(const orbx_voc *voc, int *k, int *L, int *n_nodes, int *n_words, int *scoring,
+                         int *weighting);
+
+/* TemplatedVocabulary::transform(features, BowVector&, FeatureVector&, levelsup)
+ * (TemplatedVocabulary.h:1140-1219; called as transform(vCurrentDesc, mBowVec, mFeatVec, 4) from
+ * Frame::ComputeBoW src/Frame.cc:865-872 and KeyFrame::ComputeBoW src/KeyFrame.cc:125-134).
+ *   desc[n][32]  : the frame's descriptors (HOST)
+ * Out (caller-owned, room for n entries; fv_off n+1):
+ *   bow_word/bow_value[*n_bow] : mBowVec in std::map order (ascending WordId), values as the reference's doubles
+ *   fv_node[*n_fv], fv_off[*n_fv+1], fv_idx[...] : mFeatVec as CSR (ascending NodeId, feature indices ascending)
+ *                 — the layout orbx_search_for_triangulation takes. */
+int orbx_vocabulary_transform(orbx_voc *voc, const uint8_t *desc, int n, int levelsup, int32_t *bow_word,
+                              double *bow_value, int32_t *n_bow, int32_t *fv_node, int32_t *fv_off,
+                              int32_t *fv_idx, int32_t *n_fv);
+/* Many-frame mode, DEVICE pointers, enqueues on orbx_stream(ctx): descriptors [F][cap][32] with d_n[F] valid rows
+ * each; d_leaf/d_node [F][cap] receive the leaf node reached per feature (-1 = stopped word) and the node at level
+ * L - levelsup; outputs [F][cap] (d_fv_off [F][cap+1]), counts [F]. */
+int orbx_vocabulary_transform_batch_device(orbx_voc *voc, int F, const uint8_t *d_desc, const int32_t *d_n,
+                                           int cap, int levelsup, int32_t *d_leaf, int32_t *d_node,
+                                           int32_t *d_bow_word, double *d_bow_value, int32_t *d_n_bow,
+                                           int32_t *d_fv_node, int32_t *d_fv_off, int32_t *d_fv_idx,
+                                           int32_t *d_n_fv);
+
+/* ====================================================================================
  * Optimisers (g2o linearisation + Levenberg-Marquardt as modified by ORB-SLAM3, all fp64 on
  * the device; one thread block runs a whole optimisation).
  * ================================================================================== */

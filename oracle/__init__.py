@@ -51,6 +51,13 @@ def lib():
         L.ork_distribute_octree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int]
+        L.ork_voc_from_memory.restype = C.c_void_p
+        L.ork_voc_from_memory.argtypes = [C.c_void_p, C.c_size_t]
+        L.ork_voc_load.restype = C.c_void_p
+        L.ork_voc_load.argtypes = [C.c_char_p]
+        L.ork_voc_destroy.argtypes = [C.c_void_p]
+        L.ork_voc_info.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.ork_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 9
     return _LIB
 
 
@@ -308,3 +315,43 @@ def local_ba(kf_T, kf_fixed, mp_xyz, e_kf, e_mp, e_obs, e_inv_sigma2, cam, lambd
     f(len(T), _pp(T), _pp(fixed), len(X), _pp(X), E, _pp(ekf), _pp(emp), _pp(obs), _pp(isg), C.byref(cam),
       float(lambda_init), _pp(st), _pp(bad), _pp(iters), C.byref(status))
     return T.reshape(-1, 4, 4), X, bad[:E].copy(), iters, status.value
+
+
+class Vocabulary:
+    """Oracle DBoW2 vocabulary (oracle/ork_vocabulary.cpp)."""
+
+    def __init__(self, source):
+        L = lib()
+        if isinstance(source, (bytes, bytearray, memoryview, np.ndarray)):
+            buf = np.frombuffer(bytes(source), np.uint8)
+            self.h = L.ork_voc_from_memory(_p(buf), buf.size)
+        else:
+            self.h = L.ork_voc_load(str(source).encode())
+        if not self.h:
+            raise RuntimeError("oracle vocabulary: cannot parse")
+        v = (C.c_int * 6)()
+        L.ork_voc_info(self.h, *[C.byref(v, 4 * k) for k in range(6)])
+        self.k, self.L, self.n_nodes, self.n_words, self.scoring, self.weighting = [int(x) for x in v]
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().ork_voc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def transform(self, desc, levelsup=4):
+        """-> dict(word_id, node_id per feature; bow_word, bow_value; fv_node, fv_off, fv_idx)"""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        wid, nid = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+        bw, bv = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+        fn, fo, fi = np.zeros(max(n, 1), np.int32), np.zeros(n + 1, np.int32), np.zeros(max(n, 1), np.int32)
+        nb, nn = C.c_int32(0), C.c_int32(0)
+        rc = lib().ork_voc_transform(self.h, _p(desc), n, levelsup, _p(wid), _p(nid), _p(bw), _p(bv), C.byref(nb), _p(fn),
+                                     _p(fo), _p(fi), C.byref(nn))
+        assert rc == 0
+        nb, nn = nb.value, nn.value
+        return dict(word_id=wid[:n].copy(), node_id=nid[:n].copy(), bow_word=bw[:nb].copy(), bow_value=bv[:nb].copy(),
+                    fv_node=fn[:nn].copy(), fv_off=fo[:nn + 1].copy(), fv_idx=fi[:fo[nn]].copy())
