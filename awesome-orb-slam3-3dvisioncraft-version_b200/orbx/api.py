@@ -97,6 +97,8 @@ def load_library():
     L.orbx_tracker_set_profiling.argtypes = [vp, i]
     L.orbx_tracker_stage_ms.argtypes = [vp, vp]
     L.orbx_pyramid_level.argtypes = [vp, i, i, vp, i, vp, vp]
+    L.orbx_search_by_bow.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, f, i, vp, vp]
+    L.orbx_fuse.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, f, vp, vp, i, f, vp, vp]
     L.orbx_vocabulary_load.restype = vp
     L.orbx_vocabulary_load.argtypes = [vp, C.c_char_p]
     L.orbx_vocabulary_from_memory.restype = vp
@@ -510,3 +512,34 @@ class ORBVocabulary:
                                                         _p(fo), _p(fi), C.byref(nn)), "orbx_vocabulary_transform")
         nb, nn = nb.value, nn.value
         return bw[:nb].copy(), bv[:nb].copy(), fn[:nn].copy(), fo[:nn + 1].copy(), fi[:fo[nn]].copy()
+
+
+def search_by_bow(ctx, kf, frame, kf_has_mp, fv_kf, fv_f, nnratio=0.7, check_orientation=True):
+    """ORBmatcher(nnratio, checkOri).SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:323-591).
+    fv_* = (node, off, idx) CSR triples.  -> (nmatches, match_f[frame.n])"""
+    has = np.ascontiguousarray(kf_has_mp, np.uint8)
+    kn, ko, ki = [np.ascontiguousarray(a, np.int32) for a in fv_kf]
+    fn, fo, fi = [np.ascontiguousarray(a, np.int32) for a in fv_f]
+    out = np.full(max(frame.n, 1), -1, np.int32)
+    nm = C.c_int32(0)
+    _check(load_library().orbx_search_by_bow(ctx.h, kf.ref(), frame.ref(), _p(has), len(kn), _p(kn), _p(ko), _p(ki), len(fn),
+                                             _p(fn), _p(fo), _p(fi), nnratio, int(check_orientation), _p(out), C.byref(nm)),
+           "orbx_search_by_bow")
+    return nm.value, out[:frame.n]
+
+
+def fuse(ctx, kf, cam, Rcw, tcw, Ow, flags, xw, max_dist, min_dist, normal, mp_desc, th, scale_factors, inv_level_sigma2,
+         log_scale_factor):
+    """Search half of ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:1630-1883). -> (nFused, best_idx[nmp])"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)   # noqa: E731
+    Rcw, tcw, Ow, xw, max_dist, min_dist, normal = map(f32, (Rcw, tcw, Ow, xw, max_dist, min_dist, normal))
+    sf, isg = f32(scale_factors), f32(inv_level_sigma2)
+    flags = np.ascontiguousarray(flags, np.uint8)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    n = len(flags)
+    out = np.full(max(n, 1), -1, np.int32)
+    nf = C.c_int32(0)
+    _check(load_library().orbx_fuse(ctx.h, kf.ref(), C.byref(cam), _p(Rcw), _p(tcw), _p(Ow), n, _p(flags), _p(xw), _p(max_dist),
+                                    _p(min_dist), _p(normal), _p(mp_desc), th, _p(sf), _p(isg), len(sf), log_scale_factor,
+                                    _p(out), C.byref(nf)), "orbx_fuse")
+    return nf.value, out[:n]

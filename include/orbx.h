@@ -236,6 +236,40 @@ int orbx_search_for_triangulation(orbx_ctx *ctx, const orbx_frame_desc *kf1,
                                   int coarse, int check_orientation, int32_t *match12,
                                   int32_t *nmatches);
 
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches)
+ * (src/ORBmatcher.cc:323-591; Tracking::TrackReferenceKeyFrame src/Tracking.cc:2186-2210 and relocalisation), SURVEY.md §8 f2.
+ *   kf / frame   : keypoints (angle is read: kf->kps = mvKeysUn, frame->kps = mvKeys) and descriptors
+ *   kf_has_mp[i] : vpMapPointsKF[i] != NULL && !isBad()
+ *   fv_*         : pKF->mFeatVec and F.mFeatVec as CSR (orbx_vocabulary_transform's layout)
+ *   nnratio, check_orientation : the matcher's mfNNratio and mbCheckOrientation
+ * Out: match_f[frame->n] = keyframe feature i whose MapPoint vpMapPointMatches[j] receives, or -1;
+ *      *nmatches = return value.  Pinhole / Nleft == -1 only. */
+int orbx_search_by_bow(orbx_ctx *ctx, const orbx_frame_desc *kf, const orbx_frame_desc *frame,
+                       const uint8_t *kf_has_mp, int nn_kf, const int32_t *fv_kf_node,
+                       const int32_t *fv_kf_off, const int32_t *fv_kf_idx, int nn_f,
+                       const int32_t *fv_f_node, const int32_t *fv_f_off, const int32_t *fv_f_idx,
+                       float nnratio, int check_orientation, int32_t *match_f, int32_t *nmatches);
+
+/* ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th, bRight = false)
+ * (src/ORBmatcher.cc:1630-1883; LocalMapping::SearchInNeighbors src/LocalMapping.cc:1006-1042), SURVEY.md §8 f2 —
+ * the search half: projection, distance / viewing-angle / predicted-scale gates, GetFeaturesInArea, chi2 gates,
+ * best descriptor.  The map surgery after a hit (Replace / AddObservation / AddMapPoint, :1844-1867) stays with the
+ * caller, which replays it over best_idx in increasing i.
+ *   kf           : mvKeysUn, mDescriptors, mvuRight, image bounds of pKF
+ *   Rcw[9], tcw[3], Ow[3] : GetRotation / GetTranslation / GetCameraCenter (row-major float32)
+ *   flags[i] bit0 : pMP && !isBad() && !IsInKeyFrame(pKF)
+ *   xw[i][3] = GetWorldPos(); mp_max_dist / mp_min_dist = the members mfMaxDistance / mfMinDistance (the 1.2 / 0.8
+ *   invariance factors and PredictScale are applied inside, src/MapPoint.cc:566-593); mp_normal[i][3] = GetNormal();
+ *   mp_desc = GetDescriptor(); scale_factors = mvScaleFactors; inv_level_sigma2 = mvInvLevelSigma2;
+ *   log_scale_factor = mfLogScaleFactor.
+ * Out: best_idx[i] = keyframe keypoint the MapPoint fuses into (bestDist <= TH_LOW) or -1; *nfused = number of hits. */
+int orbx_fuse(orbx_ctx *ctx, const orbx_frame_desc *kf, const orbx_camera *cam, const float *Rcw,
+              const float *tcw, const float *Ow, int nmp, const uint8_t *flags, const float *xw,
+              const float *mp_max_dist, const float *mp_min_dist, const float *mp_normal,
+              const uint8_t *mp_desc, float th, const float *scale_factors,
+              const float *inv_level_sigma2, int nlevels, float log_scale_factor, int32_t *best_idx,
+              int32_t *nfused);
+
 /* ====================================================================================
  * DBoW2 vocabulary: the step that feeds SearchForTriangulation / SearchByBoW.
  * ================================================================================== */

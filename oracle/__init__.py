@@ -51,6 +51,10 @@ def lib():
         L.ork_distribute_octree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int]
+        L.ork_search_by_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        L.ork_fuse.argtypes = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                                                                  C.c_float, C.c_void_p, C.c_void_p]
         L.ork_voc_from_memory.restype = C.c_void_p
         L.ork_voc_from_memory.argtypes = [C.c_void_p, C.c_size_t]
         L.ork_voc_load.restype = C.c_void_p
@@ -355,3 +359,33 @@ class Vocabulary:
         nb, nn = nb.value, nn.value
         return dict(word_id=wid[:n].copy(), node_id=nid[:n].copy(), bow_word=bw[:nb].copy(), bow_value=bv[:nb].copy(),
                     fv_node=fn[:nn].copy(), fv_off=fo[:nn + 1].copy(), fv_idx=fi[:fo[nn]].copy())
+
+
+def search_by_bow(kf, frame, kf_has_mp, fv_kf, fv_f, nnratio=0.7, check_orientation=True):
+    """oracle ORBmatcher::SearchByBoW(pKF, F, ...) -> (nmatches, match_f)"""
+    has = np.ascontiguousarray(kf_has_mp, np.uint8)
+    kn, ko, ki = [np.ascontiguousarray(a, np.int32) for a in fv_kf]
+    fn, fo, fi = [np.ascontiguousarray(a, np.int32) for a in fv_f]
+    out = np.full(max(frame.n, 1), -1, np.int32)
+    nm = C.c_int32(0)
+    rc = lib().ork_search_by_bow(kf.ref(), frame.ref(), _p(has), len(kn), _p(kn), _p(ko), _p(ki), len(fn), _p(fn), _p(fo), _p(fi),
+                                 nnratio, int(check_orientation), _p(out), C.byref(nm))
+    assert rc == 0
+    return nm.value, out[:frame.n]
+
+
+def fuse(kf, cam, Rcw, tcw, Ow, flags, xw, max_dist, min_dist, normal, mp_desc, th, scale_factors, inv_level_sigma2,
+         log_scale_factor):
+    """oracle search half of ORBmatcher::Fuse -> (nFused, best_idx)"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)   # noqa: E731
+    Rcw, tcw, Ow, xw, max_dist, min_dist, normal = map(f32, (Rcw, tcw, Ow, xw, max_dist, min_dist, normal))
+    sf, isg = f32(scale_factors), f32(inv_level_sigma2)
+    flags = np.ascontiguousarray(flags, np.uint8)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    n = len(flags)
+    out = np.full(max(n, 1), -1, np.int32)
+    nf = C.c_int32(0)
+    rc = lib().ork_fuse(kf.ref(), C.byref(cam), _p(Rcw), _p(tcw), _p(Ow), n, _p(flags), _p(xw), _p(max_dist), _p(min_dist),
+                        _p(normal), _p(mp_desc), th, _p(sf), _p(isg), len(sf), log_scale_factor, _p(out), C.byref(nf))
+    assert rc == 0
+    return nf.value, out[:n]

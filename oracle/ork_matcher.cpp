@@ -445,3 +445,133 @@ int ork_search_for_triangulation(const orbx_frame_desc* K1, const orbx_frame_des
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// the callers either side of the path
+// ================================================================================================
+extern "C" {
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (src/ORBmatcher.cc:323-591),
+// pinhole / Nleft == -1 configuration.
+//   kf_has_mp[i]  : vpMapPointsKF[i] != NULL && !isBad()
+//   fv*           : FeatureVectors as CSR (ascending node ids)
+// Out: match_f[F.n] = keyframe feature whose MapPoint was assigned to frame keypoint i, or -1; returns nmatches.
+int ork_search_by_bow(const orbx_frame_desc* KF, const orbx_frame_desc* F, const uint8_t* kf_has_mp, int nnK,
+                      const int32_t* fvK_node, const int32_t* fvK_off, const int32_t* fvK_idx, int nnF,
+                      const int32_t* fvF_node, const int32_t* fvF_off, const int32_t* fvF_idx, float nnratio,
+                      int check_orientation, int32_t* match_f, int32_t* nmatches) {
+  for (int i = 0; i < F->n; ++i) match_f[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int n = 0;
+  int a = 0, b = 0;
+  while (a < nnK && b < nnF) {
+    if (fvK_node[a] == fvF_node[b]) {
+      for (int iK = fvK_off[a]; iK < fvK_off[a + 1]; ++iK) {
+        const int realIdxKF = fvK_idx[iK];
+        if (!kf_has_mp[realIdxKF]) continue;
+        const uint8_t* dKF = KF->desc + 32 * (size_t)realIdxKF;
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int iF = fvF_off[b]; iF < fvF_off[b + 1]; ++iF) {
+          const int realIdxF = fvF_idx[iF];
+          if (match_f[realIdxF] >= 0) continue;
+          const int dist = descriptor_distance(dKF, F->desc + 32 * (size_t)realIdxF);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 <= TH_LOW) {
+          if ((float)bestDist1 < nnratio * (float)bestDist2) {
+            match_f[bestIdxF] = realIdxKF;
+            if (check_orientation) rotHist[rot_bin(KF->kps[realIdxKF].angle, F->kps[bestIdxF].angle)].push_back(bestIdxF);
+            ++n;
+          }
+        }
+      }
+      ++a; ++b;
+    } else if (fvK_node[a] < fvF_node[b]) {
+      a = (int)(std::lower_bound(fvK_node, fvK_node + nnK, fvF_node[b]) - fvK_node);
+    } else {
+      b = (int)(std::lower_bound(fvF_node, fvF_node + nnF, fvK_node[a]) - fvF_node);
+    }
+  }
+  if (check_orientation) {
+    int cnt[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; ++i) cnt[i] = (int)rotHist[i].size();
+    int i1, i2, i3;
+    three_maxima(cnt, HISTO_LENGTH, i1, i2, i3);
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      if (i == i1 || i == i2 || i == i3) continue;
+      for (int idx : rotHist[i]) { match_f[idx] = -1; --n; }
+    }
+  }
+  *nmatches = n;
+  return ORBX_OK;
+}
+
+// ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th, bRight = false) (src/ORBmatcher.cc:1630-1883):
+// the search half (projection, gates, best descriptor).  The map surgery that follows a hit (Replace / AddObservation /
+// AddMapPoint, :1844-1867) stays with the caller, which replays it over best_idx in increasing i.
+//   flags[i] bit0 : pMP && !isBad() && !IsInKeyFrame(pKF)
+//   mp_max_dist / mp_min_dist : the raw members mfMaxDistance / mfMinDistance (the 1.2 / 0.8 invariance factors and
+//                               PredictScale's ratio are applied here, src/MapPoint.cc:566-593)
+//   Rcw[9], tcw[3], Ow[3]     : GetRotation / GetTranslation / GetCameraCenter, float32
+//   log_scale_factor          : pKF->mfLogScaleFactor
+// Out: best_idx[i] = keyframe keypoint (bestDist <= TH_LOW) or -1; returns the number of hits (nFused).
+// cv::Mat float algebra (Rcw*p+tcw) is evaluated in fp32 left to right; cv::norm / Mat::dot accumulate in double like
+// OpenCV's normL2_32f / dotProd_32f; PredictScale's log is evaluated in double (the reference's `log(float)` resolves
+// to either overload depending on headers).
+int ork_fuse(const orbx_frame_desc* KF, const orbx_camera* cam, const float* Rcw, const float* tcw, const float* Ow,
+             int nmp, const uint8_t* flags, const float* xw, const float* mp_max_dist, const float* mp_min_dist,
+             const float* mp_normal, const uint8_t* mp_desc, float th, const float* scale_factors,
+             const float* inv_level_sigma2, int nlevels, float log_scale_factor, int32_t* best_idx, int32_t* nfused) {
+  Grid g(KF);
+  std::vector<int> v;
+  int n = 0;
+  for (int i = 0; i < nmp; ++i) {
+    best_idx[i] = -1;
+    if (!(flags[i] & 1)) continue;
+    const float X = xw[3 * i], Y = xw[3 * i + 1], Z = xw[3 * i + 2];
+    const float xc = Rcw[0] * X + Rcw[1] * Y + Rcw[2] * Z + tcw[0];
+    const float yc = Rcw[3] * X + Rcw[4] * Y + Rcw[5] * Z + tcw[1];
+    const float zc = Rcw[6] * X + Rcw[7] * Y + Rcw[8] * Z + tcw[2];
+    if (zc < 0.0f) continue;
+    const float invz = 1 / zc;
+    const float u = cam->fx * xc / zc + cam->cx, vv = cam->fy * yc / zc + cam->cy;   // Pinhole::project
+    if (!(u >= KF->min_x && u < KF->max_x && vv >= KF->min_y && vv < KF->max_y)) continue;   // IsInImage
+    const float ur = u - cam->bf * invz;
+    const float maxDistance = 1.2f * mp_max_dist[i], minDistance = 0.8f * mp_min_dist[i];
+    const float PO[3] = {X - Ow[0], Y - Ow[1], Z - Ow[2]};
+    const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+    if (dist3D < minDistance || dist3D > maxDistance) continue;
+    const double dot = (double)PO[0] * mp_normal[3 * i] + (double)PO[1] * mp_normal[3 * i + 1] + (double)PO[2] * mp_normal[3 * i + 2];
+    if (dot < 0.5 * dist3D) continue;
+    const float ratio = mp_max_dist[i] / dist3D;
+    int level = (int)std::ceil(std::log((double)ratio) / (double)log_scale_factor);
+    if (level < 0) level = 0; else if (level >= nlevels) level = nlevels - 1;
+    const float radius = th * scale_factors[level];
+    g.query(u, vv, radius, -1, -1, v);
+    if (v.empty()) continue;
+    const uint8_t* dMP = mp_desc + 32 * (size_t)i;
+    int bestDist = 256, bestIdx = -1;
+    for (int idx : v) {
+      const orbx_keypoint& kp = KF->kps[idx];
+      const int kpLevel = kp.octave;
+      if (kpLevel < level - 1 || kpLevel > level) continue;
+      if (KF->uright && KF->uright[idx] >= 0) {
+        const float ex = u - kp.x, ey = vv - kp.y, er = ur - KF->uright[idx];
+        const float e2 = ex * ex + ey * ey + er * er;
+        if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+      } else {
+        const float ex = u - kp.x, ey = vv - kp.y;
+        const float e2 = ex * ex + ey * ey;
+        if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+      }
+      const int dist = descriptor_distance(dMP, KF->desc + 32 * (size_t)idx);
+      if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+    }
+    if (bestDist <= TH_LOW) { best_idx[i] = bestIdx; ++n; }
+  }
+  *nfused = n;
+  return ORBX_OK;
+}
+
+}  // extern "C"

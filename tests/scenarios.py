@@ -246,3 +246,100 @@ def lba_scenario(seed, K=20, M=3000, n_fixed=3, obs_range=(3, 10), outlier_frac=
     Pin = P + rng.normal(0, pt_sigma, P.shape)
     return dict(kf_T=Tin.astype(np.float32).reshape(K, 16), kf_fixed=fixed, mp_xyz=Pin.astype(np.float32),
                 e_kf=ekf, e_mp=emp, e_obs=obs, e_inv_sigma2=isg, Tgt=Tgt, Pgt=P)
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY.md §8 f2 scenarios: SearchByBoW(KeyFrame, Frame) and Fuse(KeyFrame, MapPoints)
+# ------------------------------------------------------------------------------------------------
+KP_DT = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4")])
+
+
+def synthetic_keypoints(seed, n, W=752, H=480):
+    """n keypoints with real ORB descriptors (orbvoc sample), geometric octave distribution, random angles."""
+    rng = np.random.default_rng(seed)
+    k = np.zeros(n, KP_DT)
+    k["octave"] = np.minimum(rng.geometric(0.35, n) - 1, 7)
+    sc_ = (np.float32(1.2) ** k["octave"]).astype(np.float32)
+    k["x"] = (rng.uniform(20, W - 20, n)).astype(np.float32)
+    k["y"] = (rng.uniform(20, H - 20, n)).astype(np.float32)
+    k["size"] = np.floor(31 * sc_)
+    k["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    k["response"] = rng.integers(20, 120, n)
+    voc = orbvoc()
+    d = voc[rng.choice(len(voc), n, replace=n > len(voc))].copy()
+    return k, d
+
+
+def bow_scenario(seed, n_kf=900, n_f=950, nwords=60):
+    """A keyframe and a frame that sees ~70 % of its features again (bit-flipped descriptors, rotated by a common
+    angle + noise) plus distractors; FeatureVectors from a shared stand-in vocabulary level."""
+    rng = np.random.default_rng(seed)
+    kK, dK = synthetic_keypoints(seed * 7 + 1, n_kf)
+    kF, dF = synthetic_keypoints(seed * 7 + 2, n_f)
+    common = rng.permutation(min(n_kf, n_f))[:int(0.7 * min(n_kf, n_f))]
+    rot = rng.uniform(0, 40)
+    for j, i in enumerate(common):
+        dF[j] = flip_bits(rng, dK[i], int(rng.integers(0, 30)))
+        kF["angle"][j] = (kK["angle"][i] - rot + (rng.normal(0, 2.0) if rng.random() < 0.85 else rng.uniform(0, 360))) % 360.0
+        kF["octave"][j] = kK["octave"][i]
+    perm = rng.permutation(n_f)
+    kF, dF = kF[perm], dF[perm]
+    # a few exact duplicates so that best == second best and ties occur
+    for _ in range(10):
+        a, b = rng.integers(n_f, size=2)
+        dF[a] = dF[b]
+    words = orbvoc()[rng.choice(4096, nwords, replace=False)]
+    fvK = feature_vector(dK, words)
+    fn, fo, fi = feature_vector(dF, words)
+    keep = rng.random(len(fn)) < 0.9                      # some nodes exist in only one of the two FeatureVectors
+    off, idx = [0], []
+    for j in np.flatnonzero(keep):
+        idx += fi[fo[j]:fo[j + 1]].tolist()
+        off.append(len(idx))
+    fvF = (fn[keep].astype(np.int32), np.array(off, np.int32), np.array(idx, np.int32))
+    has = (rng.random(n_kf) < 0.8).astype(np.uint8)
+    return dict(kK=kK, dK=dK, kF=kF, dF=dF, fvK=fvK, fvF=fvF, has=has)
+
+
+def fuse_scenario(seed, n_kp=900, n_mp=700, stereo=True, th=3.0):
+    rng = np.random.default_rng(seed)
+    kK, dK = synthetic_keypoints(seed * 11 + 3, n_kp)
+    scale = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    inv_sigma2 = (np.float32(1.0) / (scale * scale)).astype(np.float32)
+    R = rot_small(rng, rng.uniform(0.5, 25.0))
+    t = rng.uniform(-0.6, 0.6, 3)
+    Ow = -R.T @ t
+    ur = np.full(n_kp, -1.0, np.float32)
+    voc = orbvoc()
+    xw = np.zeros((n_mp, 3), np.float32)
+    maxd, mind = np.zeros(n_mp, np.float32), np.zeros(n_mp, np.float32)
+    normal = np.zeros((n_mp, 3), np.float32)
+    desc = np.zeros((n_mp, 32), np.uint8)
+    flags = (rng.random(n_mp) < 0.9).astype(np.uint8)
+    for i in range(n_mp):
+        kind = rng.random()
+        if kind < 0.75:
+            j = int(rng.integers(n_kp))
+            z = rng.uniform(1.5, 12.0)
+            u, v = kK["x"][j] + rng.normal(0, 1.5), kK["y"][j] + rng.normal(0, 1.5)
+            Xc = np.array([(u - CX) / FX * z, (v - CY) / FY * z, z])
+            desc[i] = flip_bits(rng, dK[j], int(rng.integers(0, 40))) if rng.random() < 0.85 else voc[int(rng.integers(len(voc)))]
+            lvl = int(np.clip(kK["octave"][j] + rng.choice([0, 0, 0, 1, -1]), 0, 7))
+            if stereo and ur[j] < 0 and rng.random() < 0.6:
+                ur[j] = np.float32(kK["x"][j] - BF / z + rng.normal(0, 0.5))
+        else:
+            z = rng.uniform(-3.0, 14.0)                       # some behind the camera
+            Xc = np.array([rng.uniform(-8, 8), rng.uniform(-5, 5), z])
+            desc[i] = voc[int(rng.integers(len(voc)))]
+            lvl = int(rng.integers(0, 8))
+        Xw = R.T @ (Xc - t)
+        xw[i] = Xw
+        dist = np.linalg.norm(Xw - Ow)
+        maxd[i] = dist * float(scale[lvl]) * rng.choice([1.0, 1.0, 1.0, 0.7, 1.6])
+        mind[i] = maxd[i] / float(scale[7]) * rng.choice([1.0, 1.0, 2.5])
+        nrm = (Xw - Ow) / max(dist, 1e-9)
+        nrm = nrm + rng.normal(0, 0.35, 3) * (rng.random() < 0.4)
+        normal[i] = nrm / np.linalg.norm(nrm) * rng.choice([1.0, 1.0, 1.0, -1.0])
+    return dict(kK=kK, dK=dK, ur=ur if stereo else None, R=R.astype(np.float32).ravel(), t=t.astype(np.float32),
+                Ow=Ow.astype(np.float32), flags=flags, xw=xw, maxd=maxd, mind=mind, normal=normal, desc=desc, th=th,
+                scale=scale, inv_sigma2=inv_sigma2, log_sf=float(np.float32(np.log(np.float32(1.2)))))
