@@ -26,6 +26,21 @@ orbx_ctx* context() {
   return ctx;
 }
 
+// The device-resident DBoW2 vocabulary, uploaded once: ORBX_VOCABULARY names the same ORBvoc.bin the
+// reference's System constructor loads (Examples pass it as argv[1]).
+orbx_voc* vocabulary() {
+  static orbx_voc* voc = [] {
+    const char* path = std::getenv("ORBX_VOCABULARY");
+    orbx_voc* v = path ? orbx_vocabulary_load(context(), path) : nullptr;
+    if (!v) {
+      std::fprintf(stderr, "orbx: vocabulary (%s): %s\n", path ? path : "ORBX_VOCABULARY not set", orbx_last_error());
+      std::abort();
+    }
+    return v;
+  }();
+  return voc;
+}
+
 void die(const char* where, int status) {
   std::fprintf(stderr, "orbx: %s failed (%d): %s\n", where, status, orbx_last_error());
   std::abort();

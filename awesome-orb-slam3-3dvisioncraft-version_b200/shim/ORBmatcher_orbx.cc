@@ -1,6 +1,7 @@
-// ORBmatcher_orbx.cc — drop-in replacements for the four hot ORBmatcher members; the other members of the
-// class (SearchByBoW, Fuse, SearchBySim3, ...) stay in the reference's src/ORBmatcher.cc, from which exactly
-// these bodies are removed.  Each function flattens the pointer graph once into the SoA the C
+// ORBmatcher_orbx.cc — drop-in replacements for the hot ORBmatcher members and the two callers
+// either side of the path (§8 f2: SearchByBoW(KeyFrame*, Frame&), Fuse(KeyFrame*, vector<MapPoint*>, th, bRight)); the
+// other members of the class (SearchBySim3, the Sim3 Fuse / SearchByProjection overloads, ...) stay in the reference's
+// src/ORBmatcher.cc, from which exactly these bodies are removed.  Each function flattens the pointer graph once into the SoA the C
 // ABI takes — under the locks the reference's getters take — and scatters the index results back.
 #include "orbx_shim_config.h"
 #include <cstring>
@@ -171,6 +172,93 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat /
   for (size_t i = 0; i < m12.size(); ++i)
     if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));
   return nmatches;
+}
+
+namespace {
+// DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>) -> CSR, ascending node id
+void fv_to_csr(const DBoW2::FeatureVector& fv, std::vector<int32_t>& id, std::vector<int32_t>& off, std::vector<int32_t>& idx) {
+  off.push_back(0);
+  for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+    id.push_back((int32_t)it->first);
+    for (size_t k = 0; k < it->second.size(); ++k) idx.push_back((int32_t)it->second[k]);
+    off.push_back((int32_t)idx.size());
+  }
+}
+}  // namespace
+
+// src/ORBmatcher.cc:323-591 (pinhole, F.Nleft == -1)
+int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+  const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+  vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
+  FlatFrame fk, ff;
+  flatten(*pKF, pKF->mvKeysUn, pKF->mDescriptors, pKF->mvuRight, fk);
+  flatten(F, F.mvKeys, F.mDescriptors, F.mvuRight, ff);          // the rotation check reads F.mvKeys (:497)
+  std::vector<uint8_t> has(fk.d.n, 0);
+  for (int i = 0; i < fk.d.n; ++i) has[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();
+  std::vector<int32_t> idK, offK, idxK, idF, offF, idxF, match(F.N > 0 ? F.N : 1, -1);
+  fv_to_csr(pKF->mFeatVec, idK, offK, idxK);
+  fv_to_csr(F.mFeatVec, idF, offF, idxF);
+  int32_t nmatches = 0;
+  orbx_shim::check("orbx_search_by_bow",
+                   orbx_search_by_bow(orbx_shim::context(), &fk.d, &ff.d, has.data(), (int)idK.size(), idK.data(), offK.data(),
+                                      idxK.data(), (int)idF.size(), idF.data(), offF.data(), idxF.data(), mfNNratio,
+                                      mbCheckOrientation ? 1 : 0, match.data(), &nmatches));
+  for (int j = 0; j < F.N; ++j)
+    if (match[j] >= 0) vpMapPointMatches[j] = vpMapPointsKF[match[j]];
+  return nmatches;
+}
+
+// src/ORBmatcher.cc:1630-1883 (bRight == false; the stereo-fisheye right-camera variant stays in the reference)
+int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th, const bool bRight) {
+  assert(!bRight);
+  FlatFrame fk;
+  flatten(*pKF, pKF->mvKeysUn, pKF->mDescriptors, pKF->mvuRight, fk);
+  const int nMPs = (int)vpMapPoints.size();
+  std::vector<uint8_t> flags(nMPs, 0), desc((size_t)nMPs * 32);
+  std::vector<float> xw((size_t)nMPs * 3), nrm((size_t)nMPs * 3), maxd(nMPs), mind(nMPs);
+  for (int i = 0; i < nMPs; ++i) {
+    MapPoint* pMP = vpMapPoints[i];
+    if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+    flags[i] = 1;
+    const cv::Mat p = pMP->GetWorldPos(), n = pMP->GetNormal(), d = pMP->GetDescriptor();
+    for (int k = 0; k < 3; ++k) { xw[(size_t)i * 3 + k] = p.at<float>(k); nrm[(size_t)i * 3 + k] = n.at<float>(k); }
+    maxd[i] = pMP->GetMaxDistance();
+    mind[i] = pMP->GetMinDistance();
+    std::memcpy(&desc[(size_t)i * 32], d.data, 32);
+  }
+  float R[9], t[3], O[3];
+  const cv::Mat Rcw = pKF->GetRotation(), tcw = pKF->GetTranslation(), Ow = pKF->GetCameraCenter();
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) R[r * 3 + c] = Rcw.at<float>(r, c);
+    t[r] = tcw.at<float>(r);
+    O[r] = Ow.at<float>(r);
+  }
+  orbx_camera cam{pKF->fx, pKF->fy, pKF->cx, pKF->cy, pKF->mbf, pKF->mb};
+  std::vector<int32_t> best(nMPs > 0 ? nMPs : 1, -1);
+  int32_t nHits = 0;
+  orbx_shim::check("orbx_fuse",
+                   orbx_fuse(orbx_shim::context(), &fk.d, &cam, R, t, O, nMPs, flags.data(), xw.data(), maxd.data(), mind.data(),
+                             nrm.data(), desc.data(), th, pKF->mvScaleFactors.data(), pKF->mvInvLevelSigma2.data(),
+                             (int)pKF->mvScaleFactors.size(), pKF->mfLogScaleFactor, best.data(), &nHits));
+  // the map surgery of :1844-1867, replayed in the reference's order over the search results
+  int nFused = 0;
+  for (int i = 0; i < nMPs; ++i) {
+    if (best[i] < 0) continue;
+    MapPoint* pMP = vpMapPoints[i];
+    if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;   // an earlier Replace() may have retired it
+    MapPoint* pMPinKF = pKF->GetMapPoint(best[i]);
+    if (pMPinKF) {
+      if (!pMPinKF->isBad()) {
+        if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+        else pMPinKF->Replace(pMP);
+      }
+    } else {
+      pMP->AddObservation(pKF, best[i]);
+      pKF->AddMapPoint(pMP, best[i]);
+    }
+    ++nFused;
+  }
+  return nFused;
 }
 
 }  // namespace ORB_SLAM3

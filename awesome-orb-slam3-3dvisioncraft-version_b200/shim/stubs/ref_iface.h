@@ -45,10 +45,14 @@ enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
 void copyMakeBorder(const Mat&, Mat&, int, int, int, int, int);
 }  // namespace cv
 
-namespace DBoW2 { typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector; }
+namespace DBoW2 {
+typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;
+typedef std::map<unsigned int, double> BowVector;
+}
 
 namespace ORB_SLAM3 {
 class Map; class KeyFrame; class Frame; class GeometricCamera;
+class ORBVocabulary;   // DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> in the reference (include/ORBVocabulary.h:36)
 
 class ORBextractor {
  public:
@@ -68,6 +72,8 @@ class MapPoint {
   cv::Mat GetWorldPos(); void SetWorldPos(const cv::Mat&); cv::Mat GetDescriptor();
   std::map<KeyFrame*, std::tuple<int, int> > GetObservations(); int Observations();
   void EraseObservation(KeyFrame*); bool isBad(); void UpdateNormalAndDepth(); Map* GetMap();
+  bool IsInKeyFrame(KeyFrame*); cv::Mat GetNormal(); void Replace(MapPoint*); void AddObservation(KeyFrame*, int);
+  float GetMaxDistance(); float GetMinDistance();   // one-line accessors of mfMaxDistance / mfMinDistance
   long unsigned int mnId, mnBALocalForKF;
   float mTrackProjX, mTrackProjY, mTrackDepth, mTrackProjXR, mTrackViewCos; bool mbTrackInView; int mnTrackScaleLevel;
   static std::mutex mGlobalMutex;
@@ -75,7 +81,8 @@ class MapPoint {
 
 class Frame {
  public:
-  void SetPose(cv::Mat Tcw); void ComputeStereoMatches();
+  void SetPose(cv::Mat Tcw); void ComputeStereoMatches(); void ComputeBoW();
+  ORBVocabulary* mpORBvocabulary; DBoW2::BowVector mBowVec; DBoW2::FeatureVector mFeatVec; int Nleft;
   ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
   static float fx, fy, cx, cy; float mbf, mb; int N;
   std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn; std::vector<MapPoint*> mvpMapPoints;
@@ -89,6 +96,8 @@ class KeyFrame {
   cv::Mat GetPose(); cv::Mat GetRotation(); cv::Mat GetTranslation(); void SetPose(const cv::Mat&);
   std::vector<KeyFrame*> GetVectorCovisibleKeyFrames(); std::vector<MapPoint*> GetMapPointMatches();
   MapPoint* GetMapPoint(const size_t& idx); void EraseMapPointMatch(MapPoint*); bool isBad(); Map* GetMap();
+  cv::Mat GetCameraCenter(); void AddMapPoint(MapPoint*, const size_t& idx); void ComputeBoW();
+  ORBVocabulary* mpORBvocabulary; DBoW2::BowVector mBowVec; float mfLogScaleFactor; int N, NLeft;
   long unsigned int mnId, mnBALocalForKF, mnBAFixedForKF;
   const float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mb = 0;
   std::vector<cv::KeyPoint> mvKeysUn; std::vector<float> mvuRight; cv::Mat mDescriptors; DBoW2::FeatureVector mFeatVec;
@@ -104,6 +113,8 @@ class ORBmatcher {
   static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
   int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false, const float thFarPoints = 50.0f);
   int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+  int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+  int Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th = 3.0, const bool bRight = false);
   int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo, const bool bCoarse = false);
  protected:
   float mfNNratio; bool mbCheckOrientation;
