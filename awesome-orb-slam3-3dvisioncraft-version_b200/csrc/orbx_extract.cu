@@ -593,6 +593,14 @@ int orbx_debug_candidates(orbx_ext* e, int b, int level, int16_t* xy, uint8_t* s
 
 }  // extern "C"
 
+// Internal: the extractor's own level-0 storage (where host-pointer calls upload their images); the asynchronous tracker
+// pipeline copies its staged inputs there so that level 0 is stable while the next step's H2D is already running.
+uint8_t* orbx_ext_level0_storage(orbx_ext* e, size_t* bytes) {
+  if (!e) return nullptr;
+  if (bytes) *bytes = align_up((size_t)pitch_for(e->maxW) * e->maxH * e->maxB, 256);
+  return e->d_pyr;
+}
+
 // Internal: device view of image b's pyramid of the last extract call (used by the stereo matcher).
 int orbx_ext_pyramid_view(orbx_ext* e, int b, int* nlevels, const uint8_t** ptr, int* w, int* h, int* pitch, float* scale,
                           float* invScale, cudaStream_t* st) {

@@ -17,6 +17,7 @@
 #include "orbx_match.cuh"
 
 struct orbx_ext;
+uint8_t* orbx_ext_level0_storage(orbx_ext* e, size_t* bytes);   // orbx_extract.cu
 int orbx_ext_pyramid_view(orbx_ext* e, int b, int* nlevels, const uint8_t** ptr, int* w, int* h, int* pitch, float* scale,
                           float* invScale, cudaStream_t* st);
 int orbx_launch_pose_opt_slices(orbx_ctx* ctx, cudaStream_t st, int P, const int* d_start, const int* d_count, const float* d_xw,
@@ -250,6 +251,15 @@ struct orbx_tracker {
   const uint8_t* argImgs = nullptr;
   bool profiling = false, profiled = false;
   cudaEvent_t ev[ORBX_TRACK_STAGES + 1] = {};
+  // asynchronous host-buffer pipeline (orbx_tracker_submit / orbx_tracker_collect)
+  cudaStream_t stC = nullptr;                       // copy stream: H2D of step t+1 runs under the kernels of step t
+  cudaEvent_t evH2D = nullptr, evStaged = nullptr;  // staging buffer filled / consumed (copied into the pyramid's level 0)
+  bool stagedUsed = false;
+  float *d_aPoseIn[2] = {}, *d_aPoseOut[2] = {}, *h_aPoseIn[2] = {}, *h_aPoseOut[2] = {};
+  int *d_aStats[2] = {}, *h_aStats[2] = {};
+  cudaEvent_t evDone[2] = {};
+  int ringSlot[2] = {0, 0};
+  unsigned long long submitted = 0, collected = 0;
 };
 
 template <typename T>
@@ -359,6 +369,18 @@ void orbx_tracker_destroy(orbx_tracker* t) {
     if (t->slot[k].evB) cudaEventDestroy(t->slot[k].evB);
   }
   if (t->ownB) cudaStreamDestroy(t->ownB);
+  if (t->stC) {
+    cudaStreamSynchronize(t->stC);
+    cudaStreamDestroy(t->stC);
+    cudaEventDestroy(t->evH2D);
+    cudaEventDestroy(t->evStaged);
+    for (int k = 0; k < 2; ++k) {
+      if (t->evDone[k]) cudaEventDestroy(t->evDone[k]);
+      if (t->h_aPoseIn[k]) cudaFreeHost(t->h_aPoseIn[k]);
+      if (t->h_aPoseOut[k]) cudaFreeHost(t->h_aPoseOut[k]);
+      if (t->h_aStats[k]) cudaFreeHost(t->h_aStats[k]);
+    }
+  }
   delete t;
 }
 
@@ -612,6 +634,113 @@ int orbx_tracker_step(orbx_tracker* t, const uint8_t* const* imgs, int w, int h,
   if (sb != sa) ORBX_CUDA(cudaStreamSynchronize(sa));
   memcpy(Tcw_out, t->h_pose + 32 * S, sizeof(float) * 16 * S);
   if (stats) memcpy(stats, t->h_stats, sizeof(int) * ORBX_TRACK_STATS * S);
+  return ORBX_OK;
+}
+
+// Asynchronous host-buffer pipeline: submit() only enqueues — pinned H2D of the 2*S images on a copy stream into a staging
+// buffer, one device-to-device copy of the staging buffer into the pyramid's level 0 at the head of stage A (which
+// frees the staging buffer for the NEXT submit's H2D while this step's kernels run), the whole step in overlap mode,
+// and the D2H of poses + statistics behind stage B.  collect() waits for the oldest outstanding submit.  At most two
+// submits may be outstanding (the tracker is double-buffered).
+int orbx_tracker_submit(orbx_tracker* t, const uint8_t* const* imgs, int w, int h, int stride, const float* Tcw_true,
+                        const float* Tcw_prior) {
+  if (!t || !imgs || !Tcw_true || !Tcw_prior || w <= 0 || h <= 0 || stride < w) return ORBX_EINVAL;
+  if (t->submitted - t->collected >= 2) {
+    orbx_set_error("orbx_tracker_submit: two steps are already outstanding; collect one first");
+    return ORBX_ECAP;
+  }
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  const int S = t->S;
+  const size_t img = (size_t)w * h;
+  if (t->stB == t->stA) {
+    int rc = orbx_tracker_set_overlap(t, 1);
+    if (rc != ORBX_OK) return rc;
+  }
+  if (!t->stC) {
+    ORBX_CUDA(cudaStreamCreateWithFlags(&t->stC, cudaStreamNonBlocking));
+    ORBX_CUDA(cudaEventCreateWithFlags(&t->evH2D, cudaEventDisableTiming));
+    ORBX_CUDA(cudaEventCreateWithFlags(&t->evStaged, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) {
+      ORBX_CUDA(cudaEventCreateWithFlags(&t->evDone[k], cudaEventDisableTiming));
+      ORBX_CUDA(cudaMallocHost(&t->h_aPoseIn[k], sizeof(float) * 32 * S));
+      ORBX_CUDA(cudaMallocHost(&t->h_aPoseOut[k], sizeof(float) * 16 * S));
+      ORBX_CUDA(cudaMallocHost(&t->h_aStats[k], sizeof(int) * ORBX_TRACK_STATS * S));
+      t->d_aPoseIn[k] = talloc<float>(t, 32 * S);
+      t->d_aPoseOut[k] = talloc<float>(t, 16 * S);
+      t->d_aStats[k] = talloc<int>(t, ORBX_TRACK_STATS * S);
+      if (!t->d_aPoseIn[k] || !t->d_aPoseOut[k] || !t->d_aStats[k]) return ORBX_ECUDA;
+    }
+  }
+  if (!t->h_imgs) {
+    ORBX_CUDA(cudaMallocHost(&t->h_imgs, 2 * S * img));
+    ORBX_CUDA(cudaMallocHost(&t->h_pose, sizeof(float) * 16 * S * 3));
+    ORBX_CUDA(cudaMallocHost(&t->h_stats, sizeof(int) * ORBX_TRACK_STATS * S));
+    t->d_imgs = talloc<uint8_t>(t, 2 * S * img);
+    t->d_hposeIn = talloc<float>(t, 32 * S);
+    t->d_hposeOut = talloc<float>(t, 16 * S);
+    t->d_hstats = talloc<int>(t, ORBX_TRACK_STATS * S);
+    if (!t->d_imgs || !t->d_hposeIn || !t->d_hposeOut || !t->d_hstats) return ORBX_ECUDA;
+  }
+  size_t l0bytes = 0;
+  uint8_t* level0 = orbx_ext_level0_storage(t->ext, &l0bytes);
+  if (!level0 || l0bytes < 2 * S * img) {
+    orbx_set_error("orbx_tracker_submit: extractor level-0 storage too small for %d images of %dx%d", 2 * S, w, h);
+    return ORBX_ECAP;
+  }
+  const int k = (int)(t->stepCount & 1);            // the slot orbx_tracker_step_device is about to use
+  cudaStream_t sa = t->stA, sb = t->stB, sc = t->stC;
+  // ---- copy stream: inputs of this step ----
+  if (t->stagedUsed) ORBX_CUDA(cudaStreamWaitEvent(sc, t->evStaged, 0));   // staging buffer consumed by the previous step
+  bool pinned = true, contiguous = stride == w;
+  for (int b = 0; b < 2 * S && pinned; ++b) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, imgs[b]) != cudaSuccess || at.type != cudaMemoryTypeHost) pinned = false;
+    if (b > 0 && imgs[b] != imgs[b - 1] + img) contiguous = false;
+  }
+  cudaGetLastError();
+  if (pinned && contiguous) {
+    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, imgs[0], 2 * S * img, cudaMemcpyHostToDevice, sc));
+  } else if (pinned) {
+    for (int b = 0; b < 2 * S; ++b)
+      ORBX_CUDA(cudaMemcpy2DAsync(t->d_imgs + b * img, w, imgs[b], stride, w, h, cudaMemcpyHostToDevice, sc));
+  } else {
+    if (t->submitted) ORBX_CUDA(cudaEventSynchronize(t->evH2D));          // the pinned bounce buffer is free again
+    for (int b = 0; b < 2 * S; ++b)
+      for (int y = 0; y < h; ++y) memcpy(t->h_imgs + b * img + (size_t)y * w, imgs[b] + (size_t)y * stride, w);
+    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, t->h_imgs, 2 * S * img, cudaMemcpyHostToDevice, sc));
+  }
+  memcpy(t->h_aPoseIn[k], Tcw_true, sizeof(float) * 16 * S);
+  memcpy(t->h_aPoseIn[k] + 16 * S, Tcw_prior, sizeof(float) * 16 * S);
+  ORBX_CUDA(cudaMemcpyAsync(t->d_aPoseIn[k], t->h_aPoseIn[k], sizeof(float) * 32 * S, cudaMemcpyHostToDevice, sc));
+  ORBX_CUDA(cudaEventRecord(t->evH2D, sc));
+  // ---- stage A stream: staging -> level 0, then the step ----
+  ORBX_CUDA(cudaStreamWaitEvent(sa, t->evH2D, 0));
+  ORBX_CUDA(cudaMemcpyAsync(level0, t->d_imgs, 2 * S * img, cudaMemcpyDeviceToDevice, sa));
+  ORBX_CUDA(cudaEventRecord(t->evStaged, sa));
+  t->stagedUsed = true;
+  int rc = orbx_tracker_step_device(t, level0, w, h, w, t->d_aPoseIn[k], t->d_aPoseIn[k] + 16 * S, t->d_aPoseOut[k], t->d_aStats[k]);
+  if (rc != ORBX_OK) return rc;
+  sb = t->stB;
+  ORBX_CUDA(cudaMemcpyAsync(t->h_aPoseOut[k], t->d_aPoseOut[k], sizeof(float) * 16 * S, cudaMemcpyDeviceToHost, sb));
+  ORBX_CUDA(cudaMemcpyAsync(t->h_aStats[k], t->d_aStats[k], sizeof(int) * ORBX_TRACK_STATS * S, cudaMemcpyDeviceToHost, sb));
+  ORBX_CUDA(cudaEventRecord(t->evDone[k], sb));
+  t->ringSlot[t->submitted & 1] = k;
+  t->submitted++;
+  return ORBX_OK;
+}
+
+int orbx_tracker_collect(orbx_tracker* t, float* Tcw_out, int32_t* stats) {
+  if (!t || !Tcw_out) return ORBX_EINVAL;
+  if (t->collected == t->submitted) {
+    orbx_set_error("orbx_tracker_collect: nothing outstanding");
+    return ORBX_EINVAL;
+  }
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  const int k = t->ringSlot[t->collected & 1];
+  ORBX_CUDA(cudaEventSynchronize(t->evDone[k]));
+  memcpy(Tcw_out, t->h_aPoseOut[k], sizeof(float) * 16 * t->S);
+  if (stats) memcpy(stats, t->h_aStats[k], sizeof(int) * ORBX_TRACK_STATS * t->S);
+  t->collected++;
   return ORBX_OK;
 }
 

@@ -90,6 +90,8 @@ def load_library():
     L.orbx_tracker_destroy.argtypes = [vp]
     L.orbx_tracker_step_device.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
     L.orbx_tracker_step.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
+    L.orbx_tracker_submit.argtypes = [vp, vp, i, i, i, vp, vp]
+    L.orbx_tracker_collect.argtypes = [vp, vp, vp]
     L.orbx_tracker_set_overlap.argtypes = [vp, i]
     L.orbx_tracker_result_stream.restype = vp
     L.orbx_tracker_result_stream.argtypes = [vp]
@@ -415,6 +417,20 @@ class Optimizer:
         return T.reshape(-1, 4, 4), X, bad[:E].copy(), iters, status.value
 
 
+class _PreparedImages:
+    """The `const uint8_t* const*` argument of the tracker's host entry points, built once for a list of images."""
+
+    def __init__(self, images):
+        self.keep = [np.ascontiguousarray(im, np.uint8) for im in images]
+        self.n = len(self.keep)
+        self.h, self.w = self.keep[0].shape
+        self.ptrs = (C.c_void_p * self.n)(*[im.ctypes.data for im in self.keep])
+
+
+def prepare_images(images):
+    return _PreparedImages(images)
+
+
 class Tracker:
     """Many-stream tracking replay (orbx_tracker): S stereo streams advance one frame per step()."""
 
@@ -450,6 +466,22 @@ class Tracker:
         stats = np.zeros((self.S, 8), np.int32)
         _check(load_library().orbx_tracker_step(self.h, ptrs, w, h, w, _p(Tt), _p(Tp), _p(out), _p(stats)),
                "orbx_tracker_step")
+        return out.reshape(self.S, 4, 4), stats
+
+    def submit(self, images, Tcw_true, Tcw_prior):
+        """Asynchronous step(): enqueue only (orbx_tracker_submit).  `images` must stay alive until collect()."""
+        if not isinstance(images, _PreparedImages):
+            images = _PreparedImages(images)
+        assert images.n == 2 * self.S
+        Tt = np.ascontiguousarray(Tcw_true, np.float32).reshape(self.S, 16)
+        Tp = np.ascontiguousarray(Tcw_prior, np.float32).reshape(self.S, 16)
+        _check(load_library().orbx_tracker_submit(self.h, images.ptrs, images.w, images.h, images.w, _p(Tt), _p(Tp)),
+               "orbx_tracker_submit")
+
+    def collect(self):
+        out = np.empty((self.S, 16), np.float32)
+        stats = np.zeros((self.S, 8), np.int32)
+        _check(load_library().orbx_tracker_collect(self.h, _p(out), _p(stats)), "orbx_tracker_collect")
         return out.reshape(self.S, 4, 4), stats
 
     def step_device(self, d_imgs, w, h, stride, d_true, d_prior, d_out, d_stats):

@@ -9,8 +9,9 @@ PoseOptimization (orbx_tracker_step).  Multi-GPU = replicas only 
 no data-path collective; NCCL is used for the barrier and the max-over-ranks reduction).
 
   value  : stereo frames/s, inputs resident in HBM (device API), CUDA-event timed on the launch stream
-  e2e    : the same through the host-buffer C ABI (pinned H2D of every image + D2H of keypoints and
-           descriptors inside the timed region), wall clock between synchronisations
+  e2e    : the same through the host-buffer C ABI (orbx_tracker_submit / orbx_tracker_collect: page-locked H2D of
+           every image on a copy stream + D2H of every step's poses and statistics, all inside the timed region, two
+           steps in flight), wall clock between synchronisations
   roofline: dominant kernel = the per-stage CUDA-event time measured live (C ABI stage timers)
   cpu_baseline: the CPU oracle (a port of the reference's CPU path; the reference itself cannot be
            built here) on a bounded sample, one thread
@@ -272,8 +273,10 @@ def main():
                     help="concurrent extractor+tracker pipelines per GPU in the resident arm")
     ap.add_argument("--overlap", type=int, default=1,
                     help="1: pose/matching of step t overlap extraction of step t+1 (two streams, double-buffered)")
-    ap.add_argument("--e2e-pipelines", type=int, default=4,
-                    help="pipelines (one host thread each) in the e2e arm: overlaps H2D staging with compute")
+    ap.add_argument("--e2e-pipelines", type=int, default=1,
+                    help="pipelines in the e2e arm (each keeps two steps in flight through submit/collect)")
+    ap.add_argument("--e2e-sync", type=int, default=0,
+                    help="1: e2e arm uses the blocking orbx_tracker_step, one host thread per pipeline")
     ap.add_argument("--cpu-frames", type=int, default=150, help="stereo frames of the single-thread CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--dry-run", action="store_true",
@@ -419,28 +422,58 @@ def main():
     for P in pipes:
         P["trk"].set_overlap(False)
 
-    # ---------------- e2e arm: host buffers through the C ABI (one host thread per pipeline) ----------------
+    # ---------------- e2e arm: host buffers through the C ABI ----------------
+    # Every step copies its 2*S images from page-locked host memory to the device and reads its poses + statistics
+    # back, all inside the timed region, through orbx_tracker_submit / orbx_tracker_collect: the H2D of step t+1 runs
+    # on a copy stream under the kernels of step t, and matching + pose optimisation of step t overlap the extraction
+    # of step t+1 (overlap mode), so two steps are in flight per pipeline.  --e2e-sync 1 uses the blocking
+    # orbx_tracker_step from one host thread per pipeline instead.
     from concurrent.futures import ThreadPoolExecutor
     e2e_steps = max(3, min(args.steps, 10))
     NPE = max(1, min(args.e2e_pipelines, S))
     res_pipes = pipes
     if NPE != NP:
         pipes = build_pipes(NPE)
+    for P in pipes:
+        P["prep"] = orbx.prepare_images(P["imgs"])
 
-    def e2e_step(P):
-        return P["trk"].step(P["imgs"], P["Tt"], P["Tp"])
+    if args.e2e_sync:
+        def e2e_step(P):
+            return P["trk"].step(P["imgs"], P["Tt"], P["Tp"])
 
-    with ThreadPoolExecutor(NPE) as pool:
-        for _ in range(2):
-            list(pool.map(e2e_step, pipes))
+        with ThreadPoolExecutor(NPE) as pool:
+            for _ in range(2):
+                list(pool.map(e2e_step, pipes))
+            if dist:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                list(pool.map(e2e_step, pipes))
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+    else:
+        def e2e_run(nsteps):
+            last = None
+            for P in pipes:
+                P["trk"].submit(P["prep"], P["Tt"], P["Tp"])
+            for _ in range(nsteps - 1):
+                for P in pipes:
+                    P["trk"].submit(P["prep"], P["Tt"], P["Tp"])
+                    last = P["trk"].collect()
+            for P in pipes:
+                last = P["trk"].collect()
+            return last
+
+        e2e_run(3)
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            list(pool.map(e2e_step, pipes))
+        e2e_last = e2e_run(e2e_steps)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        assert np.array_equal(e2e_last[1], stats[-pipes[-1]["n"]:]) or NPE != NP, "e2e results differ from the resident arm"
     h2d = B * W * H + 2 * S * 64
     d2h = S * 64 + S * 8 * 4
     clocks = sampler.stop() if rank == 0 else None

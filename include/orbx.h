@@ -377,6 +377,14 @@ int orbx_tracker_step_device(orbx_tracker *trk, const uint8_t *d_imgs, int w, in
 /* Same through HOST buffers: copies the 2*S images in, the S poses and stats out, synchronises. */
 int orbx_tracker_step(orbx_tracker *trk, const uint8_t *const *imgs, int w, int h, int stride,
                       const float *Tcw_true, const float *Tcw_prior, float *Tcw_out, int32_t *stats);
+/* Asynchronous form of orbx_tracker_step for a host that keeps the device busy: submit() only ENQUEUES the step —
+ * page-locked H2D of the 2*S images on a copy stream (it runs under the kernels of the previous step), the step
+ * itself in overlap mode, the D2H of poses and statistics behind it — and returns; collect() blocks until the
+ * OLDEST outstanding submit is complete and hands out its results.  At most two submits may be outstanding
+ * (ORBX_ECAP otherwise).  The image memory must stay valid and unchanged until the matching collect() returns. */
+int orbx_tracker_submit(orbx_tracker *trk, const uint8_t *const *imgs, int w, int h, int stride,
+                        const float *Tcw_true, const float *Tcw_prior);
+int orbx_tracker_collect(orbx_tracker *trk, float *Tcw_out, int32_t *stats);
 /* Overlap mode: step t's extraction + stereo matching run on the extractor's stream and its matching +
  * pose stages on a second stream, double-buffered, so the latency-bound fp64 optimisation of step t
  * overlaps the throughput-bound extraction of step t+1 (frames of different steps are independent

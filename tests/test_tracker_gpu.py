@@ -73,3 +73,52 @@ def test_tracker_overlap_mode_gives_identical_results(ctx, ork):
     assert np.array_equal(got[3][0], got[1][0])
     trk.close()
     ex.close()
+
+
+def test_tracker_submit_collect_matches_step(ctx):
+    """The asynchronous host pipeline (copy stream + overlap mode, two steps in flight) returns, step for step, exactly
+    what the synchronous orbx_tracker_step returns — from pageable and from page-locked image memory."""
+    import orbx
+    from orbx import synth
+    S = 2
+    cam = orbx.make_camera()
+    rng = np.random.default_rng(9)
+    batches = []
+    for k in range(3):
+        imgs = []
+        for s in range(S):
+            L, R = synth.stereo_pair(80 + 10 * k + s)
+            imgs += [L, R]
+        batches.append(imgs)
+    Tt, Tp = _poses(rng, S)
+    ex = orbx.ORBextractor(ctx, max_batch=2 * S)
+    trk = orbx.Tracker(ctx, ex, S, cam)
+    ref = [trk.step(im, Tt, Tp) for im in batches]
+    pinned = []
+    for im in batches:
+        buf = orbx.host_array((2 * S,) + im[0].shape, np.uint8)
+        buf[:] = np.stack(im)
+        pinned.append([buf[i] for i in range(2 * S)])
+    for source in (batches, pinned):
+        prepared = [orbx.prepare_images(im) for im in source]
+        order = [0, 1, 2, 0, 1]
+        got = []
+        trk.submit(prepared[order[0]], Tt, Tp)
+        for j in range(1, len(order)):
+            trk.submit(prepared[order[j]], Tt, Tp)       # two in flight
+            got.append(trk.collect())
+        got.append(trk.collect())
+        for j, k in enumerate(order):
+            assert np.array_equal(got[j][0], ref[k][0]) and np.array_equal(got[j][1], ref[k][1]), (j, k)
+    with pytest.raises(orbx.OrbxError):
+        trk.collect()                                      # nothing outstanding
+    trk.submit(prepared[0], Tt, Tp)
+    trk.submit(prepared[1], Tt, Tp)
+    with pytest.raises(orbx.OrbxError):
+        trk.submit(prepared[2], Tt, Tp)                    # a third outstanding step is refused
+    trk.collect()
+    trk.collect()
+    out, st = trk.step(batches[2], Tt, Tp)                 # the synchronous entry point still works afterwards
+    assert np.array_equal(out, ref[2][0]) and np.array_equal(st, ref[2][1])
+    trk.close()
+    ex.close()
