@@ -101,6 +101,8 @@ def load_library():
     L.orbx_pyramid_level.argtypes = [vp, i, i, vp, i, vp, vp]
     L.orbx_search_by_bow.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, f, i, vp, vp]
     L.orbx_fuse.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, f, vp, vp, i, f, vp, vp]
+    L.orbx_is_in_frustum.argtypes = [vp, vp, vp, vp, vp, f, f, f, f, f, i, f, i] + [vp] * 12
+    L.orbx_undistort_keypoints.argtypes = [vp, vp, i, vp, vp, i, vp]
     L.orbx_vocabulary_load.restype = vp
     L.orbx_vocabulary_load.argtypes = [vp, C.c_char_p]
     L.orbx_vocabulary_from_memory.restype = vp
@@ -575,3 +577,36 @@ def fuse(ctx, kf, cam, Rcw, tcw, Ow, flags, xw, max_dist, min_dist, normal, mp_d
                                     _p(min_dist), _p(normal), _p(mp_desc), th, _p(sf), _p(isg), len(sf), log_scale_factor,
                                     _p(out), C.byref(nf)), "orbx_fuse")
     return nf.value, out[:n]
+
+
+def is_in_frustum(ctx, cam, Rcw, tcw, Ow, bounds, cos_limit, nlevels, log_scale_factor, xw, max_dist, min_dist, normal,
+                  stale=None):
+    """Frame::isInFrustum over a whole local map (src/Frame.cc:571-650).  `stale` = dict(proj_xr, depth, level, view_cos)
+    of previous values (kept where the point is not in view).  -> dict of the MapPoint track fields + n."""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)   # noqa: E731
+    Rcw, tcw, Ow, xw, max_dist, min_dist, normal = map(f32, (Rcw, tcw, Ow, xw, max_dist, min_dist, normal))
+    n = len(max_dist)
+    st = stale or {}
+    out = dict(in_view=np.zeros(max(n, 1), np.uint8), proj_x=np.zeros(max(n, 1), np.float32), proj_y=np.zeros(max(n, 1), np.float32),
+               proj_xr=f32(st.get("proj_xr", np.zeros(max(n, 1)))).copy(), depth=f32(st.get("depth", np.zeros(max(n, 1)))).copy(),
+               level=np.ascontiguousarray(st.get("level", np.zeros(max(n, 1))), np.int32).copy(),
+               view_cos=f32(st.get("view_cos", np.zeros(max(n, 1)))).copy())
+    cnt = C.c_int32(0)
+    _check(load_library().orbx_is_in_frustum(ctx.h, C.byref(cam), _p(Rcw), _p(tcw), _p(Ow), bounds[0], bounds[1], bounds[2], bounds[3],
+                                             cos_limit, nlevels, log_scale_factor, n, _p(xw), _p(max_dist), _p(min_dist), _p(normal),
+                                             _p(out["in_view"]), _p(out["proj_x"]), _p(out["proj_y"]), _p(out["proj_xr"]),
+                                             _p(out["depth"]), _p(out["level"]), _p(out["view_cos"]), C.byref(cnt)),
+           "orbx_is_in_frustum")
+    out = {k: v[:n] for k, v in out.items()}
+    out["n"] = cnt.value
+    return out
+
+
+def undistort_keypoints(ctx, xy, cam, dist_coef):
+    """Frame::UndistortKeyPoints (src/Frame.cc:874-924) -> float32 [n, 2]"""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    d = np.ascontiguousarray(dist_coef, np.float32).ravel()
+    out = np.zeros_like(xy)
+    _check(load_library().orbx_undistort_keypoints(ctx.h, _p(xy), len(xy), C.byref(cam), _p(d), len(d), _p(out)),
+           "orbx_undistort_keypoints")
+    return out

@@ -81,7 +81,9 @@ class MapPoint {
 
 class Frame {
  public:
-  void SetPose(cv::Mat Tcw); void ComputeStereoMatches(); void ComputeBoW();
+  void SetPose(cv::Mat Tcw); void ComputeStereoMatches(); void ComputeBoW(); void UndistortKeyPoints();
+  int isInFrustumBatch(const std::vector<MapPoint*>& vpMP, float viewingCosLimit);   // added member
+  cv::Mat mDistCoef, mRcw, mtcw, mOw; int mnScaleLevels; float mfLogScaleFactor;
   ORBVocabulary* mpORBvocabulary; DBoW2::BowVector mBowVec; DBoW2::FeatureVector mFeatVec; int Nleft;
   ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
   static float fx, fy, cx, cy; float mbf, mb; int N;

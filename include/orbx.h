@@ -307,6 +307,33 @@ int orbx_vocabulary_transform_batch_device(orbx_voc *voc, int F, const uint8_t *
                                            int32_t *d_n_fv);
 
 /* ====================================================================================
+ * Per-frame glue between extractor and matcher.
+ * ================================================================================== */
+
+/* Frame::isInFrustum(MapPoint *pMP, float viewingCosLimit) for nmp MapPoints at once (src/Frame.cc:571-650,
+ * Nleft == -1; Tracking::SearchLocalPoints src/Tracking.cc:2884-2900 calls it per local MapPoint with 0.5).
+ *   Rcw[9], tcw[3], Ow[3] : mRcw, mtcw, mOw;  min/max : mnMinX, mnMaxX, mnMinY, mnMaxY;  nlevels = mnScaleLevels;
+ *   log_scale_factor = mfLogScaleFactor;  xw = GetWorldPos();  mp_max_dist / mp_min_dist = mfMaxDistance /
+ *   mfMinDistance (raw members, see orbx_fuse);  mp_normal = GetNormal()
+ * Out, per MapPoint: in_view = mbTrackInView; proj_x/proj_y = mTrackProjX/Y (-1 when behind the camera or outside the
+ * image, otherwise the projection even if a later test fails, as in the reference).  proj_xr, depth, level, view_cos
+ * (mTrackProjXR, mTrackDepth, mnTrackScaleLevel, mTrackViewCos) are IN/OUT: overwritten only where in_view = 1, the
+ * caller's (stale) values survive elsewhere exactly as the MapPoint fields do. */
+int orbx_is_in_frustum(orbx_ctx *ctx, const orbx_camera *cam, const float *Rcw, const float *tcw,
+                       const float *Ow, float min_x, float max_x, float min_y, float max_y,
+                       float viewing_cos_limit, int nlevels, float log_scale_factor, int nmp,
+                       const float *xw, const float *mp_max_dist, const float *mp_min_dist,
+                       const float *mp_normal, uint8_t *in_view, float *proj_x, float *proj_y,
+                       float *proj_xr, float *depth, int32_t *level, float *view_cos,
+                       int32_t *n_in_view);
+
+/* Frame::UndistortKeyPoints (src/Frame.cc:874-924): cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK) on the
+ * n keypoint positions xy[n][2]; dist_coef = (k1, k2, p1, p2[, k3]), n_dist = 4 or 5.  When k1 == 0 the points are
+ * copied (the reference's early return).  out_xy may alias xy. */
+int orbx_undistort_keypoints(orbx_ctx *ctx, const float *xy, int n, const orbx_camera *cam,
+                             const float *dist_coef, int n_dist, float *out_xy);
+
+/* ====================================================================================
  * Optimisers (g2o linearisation + Levenberg-Marquardt as modified by ORB-SLAM3, all fp64 on
  * the device; one thread block runs a whole optimisation).
  * ================================================================================== */

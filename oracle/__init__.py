@@ -55,6 +55,8 @@ def lib():
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
         L.ork_fuse.argtypes = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int,
                                                                                   C.c_float, C.c_void_p, C.c_void_p]
+        L.ork_is_in_frustum.argtypes = [C.c_void_p] * 4 + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 11
+        L.ork_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ork_voc_from_memory.restype = C.c_void_p
         L.ork_voc_from_memory.argtypes = [C.c_void_p, C.c_size_t]
         L.ork_voc_load.restype = C.c_void_p
@@ -389,3 +391,31 @@ def fuse(kf, cam, Rcw, tcw, Ow, flags, xw, max_dist, min_dist, normal, mp_desc, 
                         _p(normal), _p(mp_desc), th, _p(sf), _p(isg), len(sf), log_scale_factor, _p(out), C.byref(nf))
     assert rc == 0
     return nf.value, out[:n]
+
+
+def is_in_frustum(cam, Rcw, tcw, Ow, bounds, cos_limit, nlevels, log_scale_factor, xw, max_dist, min_dist, normal, stale=None):
+    """oracle Frame::isInFrustum batch -> dict of track fields + n"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)   # noqa: E731
+    Rcw, tcw, Ow, xw, max_dist, min_dist, normal = map(f32, (Rcw, tcw, Ow, xw, max_dist, min_dist, normal))
+    n = len(max_dist)
+    st = stale or {}
+    out = dict(in_view=np.zeros(max(n, 1), np.uint8), proj_x=np.zeros(max(n, 1), np.float32), proj_y=np.zeros(max(n, 1), np.float32),
+               proj_xr=f32(st.get("proj_xr", np.zeros(max(n, 1)))).copy(), depth=f32(st.get("depth", np.zeros(max(n, 1)))).copy(),
+               level=np.ascontiguousarray(st.get("level", np.zeros(max(n, 1))), np.int32).copy(),
+               view_cos=f32(st.get("view_cos", np.zeros(max(n, 1)))).copy())
+    cnt = lib().ork_is_in_frustum(C.byref(cam), _p(Rcw), _p(tcw), _p(Ow), bounds[0], bounds[1], bounds[2], bounds[3], cos_limit,
+                                  nlevels, log_scale_factor, n, _p(xw), _p(max_dist), _p(min_dist), _p(normal), _p(out["in_view"]),
+                                  _p(out["proj_x"]), _p(out["proj_y"]), _p(out["proj_xr"]), _p(out["depth"]), _p(out["level"]),
+                                  _p(out["view_cos"]))
+    out = {k: v[:n] for k, v in out.items()}
+    out["n"] = cnt
+    return out
+
+
+def undistort_points(xy, cam, dist_coef):
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    d = np.ascontiguousarray(dist_coef, np.float32).ravel()
+    out = np.zeros_like(xy)
+    rc = lib().ork_undistort_points(_p(xy), len(xy), C.byref(cam), _p(d), len(d), _p(out))
+    assert rc == 0
+    return out
