@@ -14,7 +14,10 @@
 // every expression rounds exactly as in the CPU path (only summation order differs).
 #include <algorithm>
 #include <vector>
+#include <cooperative_groups.h>
 #include "orbx_match.cuh"
+
+namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------
 // SE3 (unit quaternion + translation), fp64 — same expressions as g2o::SE3Quat / Eigen
@@ -714,6 +717,14 @@ struct LbaArgs {
   double *b, *x;              // [n + 3M]
   double *S, *bs;             // [n][n], [n]
   double* db;                 // [M][3]
+  // cooperative (multi-CTA) kernel only
+  double* tmp;                // [max(E, n + 3M)] per-item terms of the canonical sums
+  double* part;               // [3][32] per-warp partial sums
+  double* gmax;               // [1] max |diagonal|
+  int* gflag;                 // [4] stop flag / solver status broadcast
+  unsigned long long* prof;   // [16] optional per-phase nanosecond totals (ORBX_LBA_PROFILE=1), else null
+  const int* blkOfs;          // [nBlocks + 1] offsets of the Schur blocks' edge-pair lists
+  int* pairE2;                // [blkOfs[nBlocks]]
   // outputs
   uint8_t* edgeBad;
   int* iters;                 // [2]
@@ -1100,6 +1111,462 @@ __global__ void __launch_bounds__(LBA_NT) lba_kernel(const LbaArgs A) {
   (void)s_scal;
 }
 
+// =====================================================================================
+// K12b  LocalBundleAdjustment, cooperative multi-CTA form: the same phases as lba_kernel, spread over the whole GPU
+// (one 256-thread CTA per SM, grid-wide barriers between phases).  Every sum keeps lba_kernel's canonical order:
+//   * per-pose / per-block accumulations are warp-local (32 accumulators + butterfly): any warp of the grid can own one;
+//   * the three NT = 1024 sums (robust chi2, the LM scale, the bad-edge count) are evaluated from per-item terms by the
+//     first 1024 threads of the grid exactly as 1024 threads of one CTA would (item i -> accumulator i % 1024, butterfly
+//     per 32, the 32 group sums added in order);
+//   * the dense LDL^T of the reduced camera system and its substitutions run in CTA 0, in shared memory when the system
+//     fits (n <= LBC_MAX_SMEM_N), element for element as before.
+// =====================================================================================
+#define LBC_NT 256
+#define LBC_MAX_SMEM_N 150
+
+__device__ __forceinline__ unsigned long long lbc_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// phase timer (thread 0 of the grid only, when profiling is on): adds the time since `t0` to slot `k`, restarts t0
+#define LBC_TICK(k) do { if (A.prof && gt == 0) { const unsigned long long t1_ = lbc_now(); A.prof[k] += t1_ - t0; t0 = t1_; } } while (0)
+
+// canonical NT = 1024 sum of v[0..count): returns the same value on every thread of the grid
+__device__ double lbc_sum1024(cg::grid_group& grid, const double* v, int count, double* part) {
+  const int gt = blockIdx.x * LBC_NT + threadIdx.x;
+  grid.sync();                                        // the terms are complete
+  if (gt < 1024) {
+    double s = 0;
+    for (int i = gt; i < count; i += 1024) s += v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((gt & 31) == 0) part[gt >> 5] = s;
+  }
+  grid.sync();
+  double tot = 0;
+  for (int w = 0; w < 32; ++w) tot += part[w];
+  return tot;
+}
+
+// residuals + per-edge robust chi2 terms of every edge at the current estimate, then their canonical sum
+__device__ double lbc_errors_chi(cg::grid_group& grid, const LbaArgs& A, const HuberD& hM, const HuberD& hS) {
+  const int gt = blockIdx.x * LBC_NT + threadIdx.x, GS = gridDim.x * LBC_NT;
+  for (int e = gt; e < A.E; e += GS) {
+    double p[3], r[3];
+    se3_map(A.pose[A.ekf[e]], A.pt + 3 * (size_t)A.emp[e], p);
+    const bool st = A.obs[3 * e + 2] >= 0;
+    reproj_error(p, A.obs + 3 * e, st, A.fx, A.fy, A.cx, A.cy, A.bf, r);
+    A.err[3 * e] = r[0]; A.err[3 * e + 1] = r[1]; A.err[3 * e + 2] = r[2];
+    const double om = (double)A.invSigma2[e];
+    const double c = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
+    double w;
+    A.tmp[e] = huber_rho(st ? hS : hM, c, w);
+  }
+  return lbc_sum1024(grid, A.tmp, A.E, A.part);
+}
+
+__device__ bool lbc_stop(cg::grid_group& grid, const LbaArgs& A, int& seq) {
+  const int slot = seq & 1;
+  ++seq;
+  if (blockIdx.x == 0 && threadIdx.x == 0) A.gflag[slot] = (A.stop && *A.stop) ? 1 : 0;
+  grid.sync();
+  return A.gflag[slot] != 0;
+}
+
+__global__ void __launch_bounds__(LBC_NT) lba_coop_kernel(const LbaArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) double s_S[];       // CTA 0: reduced system + right-hand side when n <= LBC_MAX_SMEM_N
+  __shared__ int s_flag;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int gt = blockIdx.x * LBC_NT + tid, GS = gridDim.x * LBC_NT;
+  const int gw = gt >> 5, GW = GS >> 5;
+  const HuberD hM = huber_make(sqrtf(5.991f)), hS = huber_make(sqrtf(7.815f));
+  const double fx = A.fx, fy = A.fy, bf = A.bf;
+  const int n = A.n, NX = A.n + 3 * A.M;
+  int stopSeq = 0;
+  unsigned long long t0 = A.prof ? lbc_now() : 0ull;
+
+  if (gt == 0) { A.iters[0] = A.iters[1] = 0; *A.status = 0; }
+  for (int e = gt; e < A.E; e += GS) A.edgeBad[e] = 0;
+  if (lbc_stop(grid, A, stopSeq)) {   // if(pbStopFlag) if(*pbStopFlag) return;  (src/Optimizer.cc:2195-2197)
+    if (gt == 0) *A.status = 1;
+    return;
+  }
+  for (int k = gt; k < A.K; k += GS) A.pose[k] = se3_from_Tcw(A.kfT + 16 * k);
+  for (int i = gt; i < 3 * A.M; i += GS) A.pt[i] = (double)A.mpXyz[i];
+  {   // static structure of the Schur product: for block (bi, bj) and the q-th edge of pose bi, the edge of the same point in bj
+    const int nBlocks0 = A.nFree * (A.nFree + 1) / 2;
+    for (int blk = gw; blk < nBlocks0; blk += GW) {
+      int bi = 0, rem = blk;
+      while (rem >= A.nFree - bi) { rem -= A.nFree - bi; ++bi; }
+      const int bj = bi + rem;
+      int* pr = A.pairE2 + A.blkOfs[blk] - A.kfOfs[bi];
+      for (int q = A.kfOfs[bi] + lane; q < A.kfOfs[bi + 1]; q += 32) pr[q] = A.obsEdge[(size_t)A.emp[A.kfEdges[q]] * A.nFree + bj];
+    }
+  }
+  grid.sync();
+
+  for (int call = 0; call < 2; ++call) {
+    const int iterations = call == 0 ? 5 : 10;
+    if (call == 1 && lbc_stop(grid, A, stopSeq)) break;   // bDoMore
+    double lambda = -1, ni = 2;
+    int nBad = 0, cj = 0;
+    bool ok = true;
+    for (int it = 0; it < iterations && ok; ++it) {
+      if (lbc_stop(grid, A, stopSeq)) break;
+      // ---- computeActiveErrors / activeRobustChi2 ----
+      LBC_TICK(0);
+      double currentChi = lbc_errors_chi(grid, A, hM, hS);
+      const double iniChi = currentChi;
+      LBC_TICK(1);
+      // ---- buildSystem: per-edge Jacobians, then deterministic gathers per point / per pose ----
+      for (int e = gt; e < A.E; e += GS) {
+        const int k = A.ekf[e];
+        double p[3], R[9];
+        se3_map(A.pose[k], A.pt + 3 * (size_t)A.emp[e], p);
+        quat_to_R(A.pose[k].r, R);
+        const bool st = A.obs[3 * e + 2] >= 0;
+        const int D = st ? 3 : 2;
+        double* Ji = A.Ji + 9 * (size_t)e;
+        double* Jj = A.Jj + 18 * (size_t)e;
+        const double x = p[0], y = p[1], z = p[2];
+        if (!st) {
+          const double j00 = -(fx / z), j02 = fx * x / (z * z), j11 = -(fy / z), j12 = fy * y / (z * z);
+          for (int c = 0; c < 3; ++c) {
+            Ji[c] = j00 * R[c] + j02 * R[6 + c];
+            Ji[3 + c] = j11 * R[3 + c] + j12 * R[6 + c];
+            Ji[6 + c] = 0;
+          }
+        } else {
+          const double z2 = z * z;
+          for (int c = 0; c < 3; ++c) {
+            Ji[c] = -fx * R[c] / z + fx * x * R[6 + c] / z2;
+            Ji[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z2;
+            Ji[6 + c] = Ji[c] - bf * R[6 + c] / z2;
+          }
+        }
+        jac_pose(p, st, true, fx, fy, bf, Jj);
+        if (!st) for (int c = 12; c < 18; ++c) Jj[c] = 0;
+        const double om = (double)A.invSigma2[e];
+        const double* r = A.err + 3 * e;
+        const double c2 = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
+        double w;
+        huber_rho(st ? hS : hM, c2, w);
+        for (int d = 0; d < 3; ++d) A.omr[3 * e + d] = (d < D) ? -om * r[d] * w : 0.0;
+        const double wo = w * om;
+        A.wom[e] = wo;
+        double* hpl = A.Hpl + 18 * (size_t)e;
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 3; ++j) {
+            double a = 0;
+            for (int d = 0; d < D; ++d) a += Jj[d * 6 + i] * wo * Ji[d * 3 + j];
+            hpl[i * 3 + j] = a;
+          }
+      }
+      grid.sync();
+      LBC_TICK(2);
+      // points: Hll, b_l (every edge of the point, fixed poses included)
+      for (int m = gt; m < A.M; m += GS) {
+        double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+        for (int q = A.ptAllOfs[m]; q < A.ptAllOfs[m + 1]; ++q) {
+          const int e = A.ptAllEdges[q];
+          const int D = A.obs[3 * e + 2] >= 0 ? 3 : 2;
+          const double* Ji = A.Ji + 9 * (size_t)e;
+          const double wo = A.wom[e];
+          const double* omr = A.omr + 3 * e;
+          for (int i = 0; i < 3; ++i) {
+            double s = 0;
+            for (int d = 0; d < D; ++d) s += Ji[d * 3 + i] * omr[d];
+            bl[i] += s;
+            for (int j = 0; j < 3; ++j) {
+              double a = 0;
+              for (int d = 0; d < D; ++d) a += Ji[d * 3 + i] * wo * Ji[d * 3 + j];
+              H[i * 3 + j] += a;
+            }
+          }
+        }
+        for (int i = 0; i < 9; ++i) A.Hll[9 * (size_t)m + i] = H[i];
+        for (int i = 0; i < 3; ++i) A.b[n + 3 * m + i] = bl[i];
+      }
+      // free poses: Hpp (upper 21) + b_p.  Every one of the 27 sums of a pose keeps lba_kernel's order (the pose's edges
+      // dealt round-robin to 32 lanes, butterfly), but each sum gets its own warp: 27 short loops instead of one long one
+      for (int item = gw; item < A.nFree * 27; item += GW) {
+        const int hk = item / 27, v = item - 27 * hk;
+        int vi = 0, vj = 0;
+        if (v < 21) { int r = v; while (r >= 6 - vi) { r -= 6 - vi; ++vi; } vj = vi + r; }
+        else vi = v - 21;
+        double acc = 0;
+        // (a mono edge has Jj[12..17] = 0 and omr[2] = 0, so its third term is an exact +0: the loop needs no branch on D)
+        if (v < 21) {
+#pragma unroll 4
+          for (int q = A.kfOfs[hk] + lane; q < A.kfOfs[hk + 1]; q += 32) {
+            const int e = A.kfEdges[q];
+            const double* Jj = A.Jj + 18 * (size_t)e;
+            const double wo = A.wom[e];
+            double t = 0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) t += Jj[d * 6 + vi] * wo * Jj[d * 6 + vj];
+            acc += t;
+          }
+        } else {
+#pragma unroll 4
+          for (int q = A.kfOfs[hk] + lane; q < A.kfOfs[hk + 1]; q += 32) {
+            const int e = A.kfEdges[q];
+            const double* Jj = A.Jj + 18 * (size_t)e;
+            const double* omr = A.omr + 3 * e;
+            double t = 0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) t += Jj[d * 6 + vi] * omr[d];
+            acc += t;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+          if (v < 21) {
+            A.Hpp[36 * (size_t)hk + vi * 6 + vj] = acc;
+            A.Hpp[36 * (size_t)hk + vj * 6 + vi] = acc;
+          } else {
+            A.b[6 * hk + vi] = acc;
+          }
+        }
+      }
+      if (gt == 0) *A.gmax = 0.0;
+      grid.sync();
+      LBC_TICK(3);
+      if (it == 0) {
+        if (A.lambdaInit > 0) lambda = A.lambdaInit;
+        else {
+          double m = 0;   // max |diag| (order-free): doubles >= 0 order like their bit patterns
+          for (int i = gt; i < A.nFree * 6; i += GS) m = fmax(m, fabs(A.Hpp[36 * (size_t)(i / 6) + (i % 6) * 7]));
+          for (int i = gt; i < A.M * 3; i += GS) m = fmax(m, fabs(A.Hll[9 * (size_t)(i / 3) + (i % 3) * 4]));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+          if (lane == 0 && m > 0) atomicMax(reinterpret_cast<unsigned long long*>(A.gmax), (unsigned long long)__double_as_longlong(m));
+          grid.sync();
+          lambda = 1e-50 * *A.gmax;
+        }
+        ni = 2;
+        nBad = 0;
+      }
+      double rho = 0;
+      int qmax = 0;
+      bool stopped = false;
+      do {
+        // ---- push ----
+        for (int k = gt; k < A.K; k += GS) A.poseBak[k] = A.pose[k];
+        for (int i = gt; i < 3 * A.M; i += GS) A.ptBak[i] = A.pt[i];
+        // ---- solve with Schur complement (block_solver.hpp:354-486) ----
+        for (int m = gt; m < A.M; m += GS) {
+          double Dm[9];
+          for (int i = 0; i < 9; ++i) Dm[i] = A.Hll[9 * (size_t)m + i];
+          Dm[0] += lambda; Dm[4] += lambda; Dm[8] += lambda;
+          const double c00 = Dm[4] * Dm[8] - Dm[5] * Dm[7], c01 = Dm[5] * Dm[6] - Dm[3] * Dm[8], c02 = Dm[3] * Dm[7] - Dm[4] * Dm[6];
+          const double det = Dm[0] * c00 + Dm[1] * c01 + Dm[2] * c02, id = 1.0 / det;
+          double* Di = A.Dinv + 9 * (size_t)m;
+          Di[0] = c00 * id; Di[1] = (Dm[2] * Dm[7] - Dm[1] * Dm[8]) * id; Di[2] = (Dm[1] * Dm[5] - Dm[2] * Dm[4]) * id;
+          Di[3] = c01 * id; Di[4] = (Dm[0] * Dm[8] - Dm[2] * Dm[6]) * id; Di[5] = (Dm[2] * Dm[3] - Dm[0] * Dm[5]) * id;
+          Di[6] = c02 * id; Di[7] = (Dm[1] * Dm[6] - Dm[0] * Dm[7]) * id; Di[8] = (Dm[0] * Dm[4] - Dm[1] * Dm[3]) * id;
+          const double* bl = A.b + n + 3 * m;
+          for (int i = 0; i < 3; ++i) A.db[3 * m + i] = Di[i * 3] * bl[0] + Di[i * 3 + 1] * bl[1] + Di[i * 3 + 2] * bl[2];
+        }
+        grid.sync();
+        LBC_TICK(4);
+        // BD[e] = B_e Dinv_m for edges of free poses
+        for (int e = gt; e < A.E; e += GS) {
+          if (A.hidx[A.ekf[e]] < 0) continue;
+          const double* B = A.Hpl + 18 * (size_t)e;
+          const double* Di = A.Dinv + 9 * (size_t)A.emp[e];
+          double* BD = A.BD + 18 * (size_t)e;
+          for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 3; ++j) BD[i * 3 + j] = B[i * 3] * Di[j] + B[i * 3 + 1] * Di[3 + j] + B[i * 3 + 2] * Di[6 + j];
+        }
+        grid.sync();
+        LBC_TICK(5);
+        // reduced system: one warp per (free pose i, free pose j >= i) block, lanes over pose i's edges
+        const int nBlocks = A.nFree * (A.nFree + 1) / 2;
+        // (one warp per ROW of a 6x6 block: the same per-lane sums and butterfly as lba_kernel, six short loops per block)
+        for (int item = gw; item < nBlocks * 6; item += GW) {
+          const int blk = item / 6, i = item - 6 * blk;
+          int bi = 0, rem = blk;
+          while (rem >= A.nFree - bi) { rem -= A.nFree - bi; ++bi; }
+          const int bj = bi + rem;
+          double acc[6] = {0, 0, 0, 0, 0, 0};
+          const int* pr = A.pairE2 + A.blkOfs[blk] - A.kfOfs[bi];
+#pragma unroll 2
+          for (int q = A.kfOfs[bi] + lane; q < A.kfOfs[bi + 1]; q += 32) {
+            const int e2 = pr[q];                       // the observation of the same point in pose bj (or -1), precomputed
+            if (e2 < 0) continue;
+            const int e1 = A.kfEdges[q];
+            const double* BD = A.BD + 18 * (size_t)e1 + 3 * i;
+            const double* B2 = A.Hpl + 18 * (size_t)e2;
+            const double d0 = BD[0], d1 = BD[1], d2 = BD[2];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc[j] += d0 * B2[j * 3] + d1 * B2[j * 3 + 1] + d2 * B2[j * 3 + 2];
+          }
+#pragma unroll
+          for (int j = 0; j < 6; ++j)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+          if (lane == 0) {
+            // lba_kernel writes (i,j) and its mirror for every (i,j) in row-major order; inside a diagonal block the later
+            // write wins, i.e. both positions end up with the value of the pair whose FIRST index is the larger one
+            const int jEnd = bi == bj ? i : 5;
+            for (int j = 0; j <= jEnd; ++j) {
+              double v = -acc[j];
+              if (bi == bj) v += A.Hpp[36 * (size_t)bi + i * 6 + j] + (i == j ? lambda : 0.0);
+              A.S[(size_t)(6 * bi + i) * n + 6 * bj + j] = v;
+              A.S[(size_t)(6 * bj + j) * n + 6 * bi + i] = v;
+            }
+          }
+        }
+        // b_schur = b_p - sum_e B_e db_m, one warp per free pose (warps from the far end of the grid)
+        for (int hk = GW - 1 - gw; hk < A.nFree; hk += GW) {
+          double acc[6] = {0, 0, 0, 0, 0, 0};
+          for (int q = A.kfOfs[hk] + lane; q < A.kfOfs[hk + 1]; q += 32) {
+            const int e = A.kfEdges[q];
+            const double* B = A.Hpl + 18 * (size_t)e;
+            const double* db = A.db + 3 * (size_t)A.emp[e];
+            for (int i = 0; i < 6; ++i) acc[i] += B[i * 3] * db[0] + B[i * 3 + 1] * db[1] + B[i * 3 + 2] * db[2];
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+          if (lane == 0)
+            for (int i = 0; i < 6; ++i) A.bs[6 * hk + i] = A.b[6 * hk + i] - acc[i];
+        }
+        for (int i = gt; i < NX; i += GS) A.x[i] = 0;
+        grid.sync();
+        LBC_TICK(6);
+        // ---- CTA 0: dense LDL^T of S (lower, un-pivoted; stand-in for SimplicialLDLT) + substitutions ----
+        if (blockIdx.x == 0) {
+          const bool inSmem = n <= LBC_MAX_SMEM_N;
+          double* Sm = inSmem ? s_S : A.S;
+          if (inSmem) {
+            for (int i = tid; i < n * n; i += LBC_NT) Sm[i] = A.S[i];
+          }
+          double* xs = inSmem ? (s_S + (size_t)n * n) : A.x;     // x_p lives next to the factor
+          for (int i = tid; i < n; i += LBC_NT) xs[i] = A.bs[i];
+          if (tid == 0) s_flag = 1;
+          __syncthreads();
+          // right-looking LDL^T; the forward substitution rides along (after column k is scaled, y_k is final and
+          // y_i -= L[i][k] * y_k is the k-th term of y_i, in the same ascending order as a separate sweep)
+          const int wid = tid >> 5;
+          for (int k = 0; k < n; ++k) {
+            const double d = Sm[(size_t)k * n + k];
+            if (d == 0 || !isfinite(d)) { if (tid == 0) s_flag = 0; break; }
+            for (int i = k + 1 + tid; i < n; i += LBC_NT) Sm[(size_t)i * n + k] /= d;
+            __syncthreads();
+            const double yk = xs[k];
+            for (int i = k + 1 + wid; i < n; i += LBC_NT / 32) {      // one warp per row, lanes over the row's lower part
+              const double lik = Sm[(size_t)i * n + k];
+              for (int j = k + 1 + lane; j <= i; j += 32) Sm[(size_t)i * n + j] -= lik * d * Sm[(size_t)j * n + k];
+              if (lane == 0) xs[i] -= lik * yk;
+            }
+            __syncthreads();
+          }
+          __syncthreads();
+          const bool solvedLocal = s_flag != 0;
+          if (tid == 0) A.gflag[2] = solvedLocal ? 1 : 0;
+          if (!solvedLocal && !inSmem)
+            for (int i = tid; i < n; i += LBC_NT) A.x[i] = 0;    // (the global x doubled as y: restore the "not solved" zeros)
+          if (solvedLocal && n > 0) {
+            for (int i = tid; i < n; i += LBC_NT) xs[i] /= Sm[(size_t)i * n + i];
+            __syncthreads();
+            for (int j = n - 1; j >= 0; --j) {
+              const double yj = xs[j];
+              for (int i = tid; i < j; i += LBC_NT) xs[i] -= Sm[(size_t)j * n + i] * yj;
+              __syncthreads();
+            }
+            if (inSmem)
+              for (int i = tid; i < n; i += LBC_NT) A.x[i] = xs[i];
+          }
+        }
+        grid.sync();
+        LBC_TICK(7);
+        const bool solved = A.gflag[2] != 0;
+        if (solved && n > 0) {
+          // landmarks: x_l = Dinv (b_l - sum_e B_e^T x_p)
+          for (int m = gt; m < A.M; m += GS) {
+            double cl[3] = {A.b[n + 3 * m], A.b[n + 3 * m + 1], A.b[n + 3 * m + 2]};
+            for (int q = A.ptOfs[m]; q < A.ptOfs[m + 1]; ++q) {
+              const int e = A.ptEdges[q];
+              const int hk = A.hidx[A.ekf[e]];
+              const double* B = A.Hpl + 18 * (size_t)e;
+              for (int j = 0; j < 3; ++j)
+                for (int i = 0; i < 6; ++i) cl[j] -= B[i * 3 + j] * A.x[6 * hk + i];
+            }
+            const double* Di = A.Dinv + 9 * (size_t)m;
+            for (int i = 0; i < 3; ++i) A.x[n + 3 * m + i] = Di[i * 3] * cl[0] + Di[i * 3 + 1] * cl[1] + Di[i * 3 + 2] * cl[2];
+          }
+        }
+        grid.sync();
+        LBC_TICK(8);
+        // ---- update (oplus) ----
+        for (int k = gt; k < A.K; k += GS)
+          if (A.hidx[k] >= 0) A.pose[k] = se3_mul(se3_exp(A.x + 6 * A.hidx[k]), A.pose[k]);
+        for (int i = gt; i < 3 * A.M; i += GS) A.pt[i] += A.x[n + i];
+        grid.sync();
+        LBC_TICK(9);
+        double tempChi = lbc_errors_chi(grid, A, hM, hS);
+        LBC_TICK(10);
+        if (!solved) tempChi = 1.7976931348623157e308;
+        rho = currentChi - tempChi;
+        for (int j = gt; j < NX; j += GS) A.tmp[j] = A.x[j] * (lambda * A.x[j] + A.b[j]);
+        const double scale = lbc_sum1024(grid, A.tmp, NX, A.part + 32) + 1e-3;
+        LBC_TICK(11);
+        rho /= scale;
+        if (rho > 0 && isfinite(tempChi)) {
+          const double tr = 2 * rho - 1;
+          double alpha = 1. - tr * tr * tr;   // pow(2*rho-1, 3)
+          alpha = fmin(alpha, 2. / 3.);
+          const double scaleFactor = fmax(1. / 3., alpha);
+          lambda *= scaleFactor;
+          ni = 2;
+          currentChi = tempChi;
+        } else {
+          lambda *= ni;
+          ni *= 2;
+          for (int k = gt; k < A.K; k += GS) A.pose[k] = A.poseBak[k];   // pop
+          for (int i = gt; i < 3 * A.M; i += GS) A.pt[i] = A.ptBak[i];
+        }
+        ++qmax;
+        stopped = lbc_stop(grid, A, stopSeq);       // (grid-wide barrier: the pop is complete)
+        LBC_TICK(12);
+        if (A.prof && gt == 0) A.prof[15] += 1;
+      } while (rho < 0 && qmax < 100 && !stopped);
+      ++cj;
+      if (qmax == 100 || rho == 0) { ok = false; continue; }
+      if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
+      if (nBad >= 3) ok = false;
+    }
+    if (gt == 0) A.iters[call] = cj;
+  }
+  grid.sync();
+  // ---- final chi2 / depth test on the residuals of the last evaluated state (src/Optimizer.cc:2295-2352) ----
+  for (int e = gt; e < A.E; e += GS) {
+    const bool st = A.obs[3 * e + 2] >= 0;
+    const double om = (double)A.invSigma2[e];
+    const double* r = A.err + 3 * e;
+    const double c = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
+    double p[3];
+    se3_map(A.pose[A.ekf[e]], A.pt + 3 * (size_t)A.emp[e], p);
+    const bool isBad = c > (st ? 7.815 : 5.991) || !(p[2] > 0.0);
+    A.edgeBad[e] = isBad ? 1 : 0;
+    A.tmp[e] = isBad ? 1.0 : 0.0;
+  }
+  const double nBadEdges = lbc_sum1024(grid, A.tmp, A.E, A.part + 64);
+  if (nBadEdges >= A.E * 0.5) {
+    if (gt == 0) *A.status = 2;
+    return;
+  }
+  for (int k = gt; k < A.K; k += GS)
+    if (!A.kfFixed[k]) se3_to_Tcw(A.pose[k], A.kfT + 16 * k);
+  for (int i = gt; i < 3 * A.M; i += GS) A.mpXyz[i] = (float)A.pt[i];
+}
+
 // internal (orbx_track.cu): P problems with fixed-capacity slices
 int orbx_launch_pose_opt_slices(orbx_ctx* ctx, cudaStream_t st, int P, const int* d_start, const int* d_count, const float* d_xw,
                                 const float* d_obs, const float* d_isg, const orbx_camera* cam, float* d_Tcw, uint8_t* d_outlier,
@@ -1265,6 +1732,27 @@ int orbx_local_ba(orbx_ctx* ctx, int n_kf, float* kf_Tcw, const uint8_t* kf_fixe
   A.S = S.alloc<double>((size_t)std::max(A.n, 1) * std::max(A.n, 1));
   A.bs = S.alloc<double>(std::max(A.n, 1));
   A.db = S.alloc<double>((size_t)3 * n_mp);
+  A.tmp = S.alloc<double>(std::max((size_t)n_edges, (size_t)A.n + 3 * n_mp));
+  A.part = S.alloc<double>(96);
+  A.gmax = S.alloc<double>(1);
+  A.gflag = S.alloc<int>(4);
+  {
+    const int nBlocks = nFree * (nFree + 1) / 2;
+    std::vector<int> blkOfs(nBlocks + 1, 0);
+    int blk = 0;
+    for (int bi = 0; bi < nFree; ++bi)
+      for (int bj = bi; bj < nFree; ++bj, ++blk) blkOfs[blk + 1] = blkOfs[blk] + (kfOfs[bi + 1] - kfOfs[bi]);
+    A.blkOfs = S.upload(blkOfs.data(), blkOfs.size());
+    A.pairE2 = S.alloc<int>(std::max(blkOfs[nBlocks], 1));
+  }
+  A.prof = nullptr;
+  {
+    const char* pe = getenv("ORBX_LBA_PROFILE");
+    if (pe && pe[0] == '1') {
+      A.prof = S.alloc<unsigned long long>(16);
+      if (A.prof) cudaMemsetAsync(A.prof, 0, 16 * sizeof(unsigned long long), st);
+    }
+  }
   A.edgeBad = S.alloc<uint8_t>(n_edges);
   int* d_res = S.alloc<int>(3);
   A.iters = d_res;
@@ -1279,7 +1767,33 @@ int orbx_local_ba(orbx_ctx* ctx, int n_kf, float* kf_Tcw, const uint8_t* kf_fixe
   }
   A.stop = d_flag;
   if (S.failed) { if (h_flag) cudaFreeHost(h_flag); return ORBX_ECUDA; }
-  lba_kernel<<<1, LBA_NT, 0, st>>>(A);
+  // cooperative multi-CTA kernel (one CTA per SM) whenever the device can co-schedule it; the single-CTA kernel
+  // otherwise (ORBX_LBA_SINGLE_CTA=1 forces it, for A/B timing)
+  bool launched = false;
+  {
+    static int coopOk = -1, maxCtasPerSm = 0, smemConfigured = 0;
+    const size_t smem = A.n <= LBC_MAX_SMEM_N ? sizeof(double) * ((size_t)A.n * A.n + A.n) : 0;
+    if (coopOk < 0) {
+      int v = 0;
+      cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, ctx->device);
+      const char* env = getenv("ORBX_LBA_SINGLE_CTA");
+      coopOk = (v && !(env && env[0] == '1')) ? 1 : 0;
+    }
+    if (coopOk == 1) {
+      if ((int)smem > smemConfigured) {
+        const int want = (int)(sizeof(double) * ((size_t)LBC_MAX_SMEM_N * LBC_MAX_SMEM_N + LBC_MAX_SMEM_N));
+        if (cudaFuncSetAttribute(lba_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want) == cudaSuccess) smemConfigured = want;
+      }
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxCtasPerSm, lba_coop_kernel, LBC_NT, smem) == cudaSuccess && maxCtasPerSm >= 1 &&
+          ctx->sm_count * LBC_NT >= 1024) {
+        void* kargs[] = {(void*)&A};
+        cudaError_t ce = cudaLaunchCooperativeKernel((void*)lba_coop_kernel, dim3(ctx->sm_count), dim3(LBC_NT), kargs, smem, st);
+        if (ce == cudaSuccess) launched = true;
+        else cudaGetLastError();
+      }
+    }
+  }
+  if (!launched) lba_kernel<<<1, LBA_NT, 0, st>>>(A);
   ORBX_LAUNCH(ctx);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
@@ -1307,6 +1821,16 @@ int orbx_local_ba(orbx_ctx* ctx, int n_kf, float* kf_Tcw, const uint8_t* kf_fixe
   iters[0] = h[0];
   iters[1] = h[1];
   *status = h[2];
+  if (A.prof) {
+    unsigned long long hp[16];
+    if (cudaMemcpy(hp, A.prof, sizeof hp, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      static const char* name[13] = {"stop poll", "errors+chi2", "edge Jacobians", "Hll+Hpp", "Dinv", "B*Dinv", "Schur+b", "LDLT+subst (CTA 0)",
+                                     "landmark x", "oplus", "trial errors+chi2", "scale", "accept/pop+stop"};
+      fprintf(stderr, "orbx_local_ba phases (us, %llu trials):", hp[15]);
+      for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%.0f", name[i], hp[i] * 1e-3);
+      fprintf(stderr, "\n");
+    }
+  }
   if (h[2] == 0) {
     ORBX_CUDA(cudaMemcpyAsync(kf_Tcw, A.kfT, sizeof(float) * 16 * n_kf, cudaMemcpyDeviceToHost, st));
     ORBX_CUDA(cudaMemcpyAsync(mp_xyz, A.mpXyz, sizeof(float) * 3 * n_mp, cudaMemcpyDeviceToHost, st));

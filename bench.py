@@ -299,8 +299,8 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: exactly ONE JSON line
+        # exactly ONE JSON line on stdout: whatever NCCL logs (its version banner at NCCL_DEBUG >= VERSION) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sampler = ClockSampler(local)
