@@ -57,6 +57,8 @@ void orbx_destroy(orbx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->arenaDev) cudaFree(c->arenaDev);
+  if (c->arenaHost) cudaFreeHost(c->arenaHost);
   delete c;
 }
 

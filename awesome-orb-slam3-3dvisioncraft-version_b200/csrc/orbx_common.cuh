@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <string>
 #include <atomic>
+#include <mutex>
 #include "../../include/orbx.h"
 
 void orbx_set_error(const char* fmt, ...);
@@ -23,6 +24,14 @@ struct orbx_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   std::atomic<uint64_t> launches{0};
+  // Call-scoped staging arena of the host-buffer entry points (DevScope): one device buffer + its page-locked mirror,
+  // bump-allocated, so the ~20 small uploads / temporaries of a matcher or optimiser call cost one pinned memcpy each
+  // instead of a cudaMallocAsync + pageable copy.  apiMutex serialises those calls per context (they serialise on the
+  // context's stream anyway).
+  std::mutex apiMutex;
+  uint8_t* arenaDev = nullptr;
+  uint8_t* arenaHost = nullptr;
+  size_t arenaCap = 0;
 };
 
 #define ORBX_LAUNCH(ctx) ((ctx)->launches.fetch_add(1, std::memory_order_relaxed))

@@ -91,7 +91,7 @@ int orbx_is_in_frustum(orbx_ctx* ctx, const orbx_camera* cam, const float* Rcw, 
     return ORBX_EINVAL;
   ORBX_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevScope S(st);
+  DevScope S(ctx, st);
   FrustumArgs A;
   for (int i = 0; i < 9; ++i) A.R[i] = Rcw[i];
   for (int i = 0; i < 3; ++i) { A.t[i] = tcw[i]; A.Ow[i] = Ow[i]; }
@@ -116,16 +116,15 @@ int orbx_is_in_frustum(orbx_ctx* ctx, const orbx_camera* cam, const float* Rcw, 
   frustum_kernel<<<div_up(nmp, 128), 128, 0, st>>>(A);
   ORBX_LAUNCH(ctx);
   ORBX_CUDA(cudaGetLastError());
-  ORBX_CUDA(cudaMemcpyAsync(in_view, A.inView, nmp, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(proj_x, A.projX, sizeof(float) * nmp, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(proj_y, A.projY, sizeof(float) * nmp, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(proj_xr, A.projXR, sizeof(float) * nmp, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(depth, A.depth, sizeof(float) * nmp, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(view_cos, A.viewCos, sizeof(float) * nmp, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(level, A.level, sizeof(int) * nmp, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(n_in_view, A.count, sizeof(int), cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaStreamSynchronize(st));
-  return ORBX_OK;
+  S.download(in_view, A.inView, (size_t)nmp);
+  S.download(proj_x, A.projX, (size_t)nmp);
+  S.download(proj_y, A.projY, (size_t)nmp);
+  S.download(proj_xr, A.projXR, (size_t)nmp);
+  S.download(depth, A.depth, (size_t)nmp);
+  S.download(view_cos, A.viewCos, (size_t)nmp);
+  S.download(level, A.level, (size_t)nmp);
+  S.download(n_in_view, A.count, (size_t)1);
+  return S.finish();
 }
 
 int orbx_undistort_keypoints(orbx_ctx* ctx, const float* xy, int n, const orbx_camera* cam, const float* dist_coef, int n_dist,
@@ -138,7 +137,7 @@ int orbx_undistort_keypoints(orbx_ctx* ctx, const float* xy, int n, const orbx_c
   }
   ORBX_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevScope S(st);
+  DevScope S(ctx, st);
   const float2* d_in = reinterpret_cast<const float2*>(S.upload(xy, (size_t)2 * n));
   float2* d_out = reinterpret_cast<float2*>(S.alloc<float>((size_t)2 * n));
   if (S.failed) return ORBX_ECUDA;
@@ -147,9 +146,8 @@ int orbx_undistort_keypoints(orbx_ctx* ctx, const float* xy, int n, const orbx_c
                                                    (double)dist_coef[3], n_dist > 4 ? (double)dist_coef[4] : 0.0, d_out);
   ORBX_LAUNCH(ctx);
   ORBX_CUDA(cudaGetLastError());
-  ORBX_CUDA(cudaMemcpyAsync(out_xy, d_out, sizeof(float) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaStreamSynchronize(st));
-  return ORBX_OK;
+  S.download(out_xy, reinterpret_cast<const float*>(d_out), (size_t)2 * n);
+  return S.finish();
 }
 
 }  // extern "C"

@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(32) sbp_map_resolve_kernel(const FrameDev* fra
             const bool reject = bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2);
             if (!reject) {
               best = c1 & 0xffff;
+              __syncwarp();                            // every lane's s_blocked reads of this query are done
               if (lane == 0) s_blocked[best] = (fl & 2) ? 1 : 0;
               ++n;
               __syncwarp();
@@ -491,6 +492,7 @@ __global__ void __launch_bounds__(32) sbp_frame_resolve_kernel(const FrameDev* f
           const int p1 = k1 & 0xfffff;
           const uint32_t c1 = p1 < 32 ? __shfl_sync(FULL, c[u], p1) : A.cand[ofs + p1];
           best = c1 & 0xffff;
+          __syncwarp();                                // every lane's s_blocked reads of this query are done
           if (lane == 0) {
             s_blocked[best] = (fl & 2) ? 1 : 0;
             A.curMatch[best] = q0 + g + u;
@@ -889,7 +891,7 @@ int orbx_features_in_area(orbx_ctx* ctx, const orbx_frame_desc* frame, int nq, c
   if (!ctx || !frame || nq < 0 || cap < 1 || !x || !y || !r || !minL || !maxL || !out_idx || !out_n) return ORBX_EINVAL;
   ORBX_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevScope S(st);
+  DevScope S(ctx, st);
   FrameDev F;
   int rc = orbx_upload_frame(S, frame, &F);
   if (rc != ORBX_OK) return rc;
@@ -924,7 +926,7 @@ int orbx_search_by_projection_map(orbx_ctx* ctx, const orbx_frame_desc* frame, c
     if ((flags[q] & 1) && (level[q] < 0 || level[q] >= nlevels)) return ORBX_EINVAL;
   ORBX_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevScope S(st);
+  DevScope S(ctx, st);
   FrameDev F;
   int rc = orbx_upload_frame(S, frame, &F);
   if (rc != ORBX_OK) return rc;
@@ -990,7 +992,7 @@ int orbx_search_by_projection_frame(orbx_ctx* ctx, const orbx_frame_desc* cur, c
     if ((flags[q] & 1) && (octave[q] < 0 || octave[q] >= nlevels)) return ORBX_EINVAL;
   ORBX_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevScope S(st);
+  DevScope S(ctx, st);
   FrameDev F;
   int rc = orbx_upload_frame(S, cur, &F);
   if (rc != ORBX_OK) return rc;
@@ -1087,7 +1089,7 @@ int orbx_stereo_match(orbx_ctx* ctx, orbx_ext* extL, int bL, orbx_ext* extR, int
   ORBX_CUDA(cudaStreamSynchronize(stL));
   if (stR != stL) ORBX_CUDA(cudaStreamSynchronize(stR));
   cudaStream_t st = ctx->stream;
-  DevScope S(st);
+  DevScope S(ctx, st);
   A.nL = nL;
   A.nR = nR;
   A.nlevels = nlv;
@@ -1130,7 +1132,7 @@ int orbx_search_for_triangulation(orbx_ctx* ctx, const orbx_frame_desc* kf1, con
   if ((nn1 && (!fv1_node || !fv1_off || !fv1_idx)) || (nn2 && (!fv2_node || !fv2_off || !fv2_idx))) return ORBX_EINVAL;
   ORBX_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevScope S(st);
+  DevScope S(ctx, st);
   FrameDev F[2];
   int rc = orbx_upload_frame(S, kf1, &F[0]);
   if (rc != ORBX_OK) return rc;

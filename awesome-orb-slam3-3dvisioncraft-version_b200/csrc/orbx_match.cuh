@@ -3,6 +3,7 @@
 #pragma once
 #include "orbx_common.cuh"
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #define ORBX_NCELLS (ORBX_GRID_COLS * ORBX_GRID_ROWS)
@@ -19,28 +20,102 @@ struct FrameDev {
   int* cellIdx;            // [n] keypoint indices, ascending inside a cell
 };
 
-// Stream-ordered temporaries of one API call (cudaMallocAsync pool; freed on scope exit).
+// Temporaries of one host-buffer API call.  Small requests are carved out of the context's staging arena (device
+// buffer + page-locked mirror: an upload is one CPU memcpy into the mirror and one truly asynchronous H2D); anything
+// that does not fit falls back to the stream-ordered allocator.  The scope holds the context's API mutex; every entry
+// point synchronises its stream before returning, so the arena is free again when the next scope starts.
+#define ORBX_ARENA_BYTES (24u << 20)
 struct DevScope {
+  orbx_ctx* ctx;
   cudaStream_t st;
   std::vector<void*> ptrs;
+  size_t off = 0;
   bool failed = false;
-  explicit DevScope(cudaStream_t s) : st(s) {}
+  DevScope(orbx_ctx* c, cudaStream_t s) : ctx(c), st(s) {
+    ctx->apiMutex.lock();
+    if (!ctx->arenaDev) {
+      if (cudaMalloc(&ctx->arenaDev, ORBX_ARENA_BYTES) == cudaSuccess &&
+          cudaHostAlloc(&ctx->arenaHost, ORBX_ARENA_BYTES, cudaHostAllocDefault) == cudaSuccess) {
+        ctx->arenaCap = ORBX_ARENA_BYTES;
+      } else {
+        cudaGetLastError();
+        if (ctx->arenaDev) cudaFree(ctx->arenaDev);
+        ctx->arenaDev = nullptr;
+        ctx->arenaCap = 0;
+      }
+    }
+  }
   ~DevScope() {
     for (void* p : ptrs) cudaFreeAsync(p, st);
+    ctx->apiMutex.unlock();
+  }
+  DevScope(const DevScope&) = delete;
+  DevScope& operator=(const DevScope&) = delete;
+  // returns the arena offset of a new block, or (size_t)-1 when it does not fit
+  size_t carve(size_t bytes) {
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (off + need > ctx->arenaCap) return (size_t)-1;
+    const size_t o = off;
+    off += need;
+    return o;
   }
   template <typename T>
   T* alloc(size_t count) {
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    const size_t o = carve(bytes);
+    if (o != (size_t)-1) return (T*)(ctx->arenaDev + o);
     void* p = nullptr;
-    if (cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), st) != cudaSuccess) {
+    if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) {
       failed = true;
-      orbx_set_error("orbx: cudaMallocAsync(%zu bytes) failed", count * sizeof(T));
+      orbx_set_error("orbx: cudaMallocAsync(%zu bytes) failed", bytes);
       return nullptr;
     }
     ptrs.push_back(p);
     return (T*)p;
   }
+  // Results: download() enqueues a D2H copy into the page-locked mirror (asynchronous; a pageable destination would make
+  // every copy a blocking staged transfer), finish() synchronises the stream once and hands the bytes to the caller.
+  struct Pending { void* dst; size_t off, bytes; };
+  std::vector<Pending> pending;
+  template <typename T>
+  void download(T* host_dst, const T* dev_src, size_t count) {
+    if (!count || failed) return;
+    const size_t bytes = count * sizeof(T);
+    const size_t o = carve(bytes);
+    cudaError_t e;
+    if (o != (size_t)-1) {
+      e = cudaMemcpyAsync(ctx->arenaHost + o, dev_src, bytes, cudaMemcpyDeviceToHost, st);
+      pending.push_back(Pending{(void*)host_dst, o, bytes});
+    } else {
+      e = cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, st);
+    }
+    if (e != cudaSuccess) { failed = true; orbx_set_error("orbx: D2H copy failed: %s", cudaGetErrorString(e)); }
+  }
+  int finish() {
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess || failed) {
+      if (e != cudaSuccess) orbx_set_error("orbx: %s", cudaGetErrorString(e));
+      return ORBX_ECUDA;
+    }
+    for (const Pending& p : pending) memcpy(p.dst, ctx->arenaHost + p.off, p.bytes);
+    pending.clear();
+    return ORBX_OK;
+  }
   template <typename T>
   T* upload(const T* host, size_t count) {
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    const size_t o = carve(bytes);
+    if (o != (size_t)-1) {
+      T* d = (T*)(ctx->arenaDev + o);
+      if (count) {
+        memcpy(ctx->arenaHost + o, host, count * sizeof(T));
+        if (cudaMemcpyAsync(d, ctx->arenaHost + o, count * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+          failed = true;
+          orbx_set_error("orbx: H2D copy failed");
+        }
+      }
+      return d;
+    }
     T* d = alloc<T>(count);
     if (d && count && cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess) {
       failed = true;

@@ -250,7 +250,7 @@ int orbx_search_by_bow(orbx_ctx* ctx, const orbx_frame_desc* kf, const orbx_fram
   if (frame->n == 0 || kf->n == 0 || totK == 0 || totF == 0) return ORBX_OK;
   ORBX_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevScope S(st);
+  DevScope S(ctx, st);
   BowArgs A;
   A.nK = kf->n; A.nF = frame->n;
   A.kpK = S.upload(kf->kps, kf->n); A.kpF = S.upload(frame->kps, frame->n);
@@ -271,10 +271,9 @@ int orbx_search_by_bow(orbx_ctx* ctx, const orbx_frame_desc* kf, const orbx_fram
   bow_rot_filter_kernel<<<1, 256, 0, st>>>(A);
   ORBX_LAUNCH(ctx);
   ORBX_CUDA(cudaGetLastError());
-  ORBX_CUDA(cudaMemcpyAsync(match_f, dMatch, sizeof(int) * frame->n, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(nmatches, A.nmatches, sizeof(int), cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaStreamSynchronize(st));
-  return ORBX_OK;
+  S.download(match_f, (const int32_t*)dMatch, (size_t)frame->n);
+  S.download(nmatches, (const int32_t*)A.nmatches, (size_t)1);
+  return S.finish();
 }
 
 int orbx_fuse(orbx_ctx* ctx, const orbx_frame_desc* kf, const orbx_camera* cam, const float* Rcw, const float* tcw,
@@ -291,7 +290,7 @@ int orbx_fuse(orbx_ctx* ctx, const orbx_frame_desc* kf, const orbx_camera* cam, 
   if (nmp == 0 || kf->n == 0) return ORBX_OK;
   ORBX_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevScope S(st);
+  DevScope S(ctx, st);
   FrameDev F;
   int rc = orbx_upload_frame(S, kf, &F);
   if (rc != ORBX_OK) return rc;
@@ -323,10 +322,9 @@ int orbx_fuse(orbx_ctx* ctx, const orbx_frame_desc* kf, const orbx_camera* cam, 
   fuse_kernel<<<div_up(nmp * 32, 128), 128, 0, st>>>(dF, A);
   ORBX_LAUNCH(ctx);
   ORBX_CUDA(cudaGetLastError());
-  ORBX_CUDA(cudaMemcpyAsync(best_idx, A.bestIdx, sizeof(int) * nmp, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(nfused, A.nfused, sizeof(int), cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaStreamSynchronize(st));
-  return ORBX_OK;
+  S.download(best_idx, (const int32_t*)A.bestIdx, (size_t)nmp);
+  S.download(nfused, (const int32_t*)A.nfused, (size_t)1);
+  return S.finish();
 }
 
 }  // extern "C"

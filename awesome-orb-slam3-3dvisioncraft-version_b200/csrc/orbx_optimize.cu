@@ -1628,7 +1628,7 @@ int orbx_pose_optimization(orbx_ctx* ctx, int n_edges, const float* xw, const fl
   if (n_edges > 0 && (!xw || !obs || !inv_sigma2 || !outlier)) return ORBX_EINVAL;
   ORBX_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevScope S(st);
+  DevScope S(ctx, st);
   const int ofs[2] = {0, n_edges};
   int* d_ofs = S.upload(ofs, 2);
   float* d_xw = S.upload(xw, (size_t)3 * n_edges);
@@ -1665,7 +1665,7 @@ int orbx_local_ba(orbx_ctx* ctx, int n_kf, float* kf_Tcw, const uint8_t* kf_fixe
     }
   ORBX_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  DevScope S(st);
+  DevScope S(ctx, st);
   LbaArgs A;
   A.K = n_kf; A.M = n_mp; A.E = n_edges;
   // --- graph indices (the reference builds the same adjacency inside g2o's buildStructure) ---

@@ -425,7 +425,12 @@ int orbx_tracker_set_overlap(orbx_tracker* t, int enable) {
       // SM slot that frees up while the (throughput-bound) extraction grids of the next step drain
       int lo = 0, hi = 0;
       ORBX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      ORBX_CUDA(cudaStreamCreateWithPriority(&t->ownB, cudaStreamNonBlocking, hi));
+      int prio = hi;
+      if (const char* pe = getenv("ORBX_STAGEB_PRIORITY")) {   // A/B switch for the scheduling study in DESIGN.md §7
+        if (pe[0] == 'l') prio = lo;
+        else if (pe[0] == 's') prio = 0;
+      }
+      ORBX_CUDA(cudaStreamCreateWithPriority(&t->ownB, cudaStreamNonBlocking, prio));
     }
     if (t->nslots < 2) {
       float sc[ORBX_MAX_LEVELS], isg[ORBX_MAX_LEVELS];

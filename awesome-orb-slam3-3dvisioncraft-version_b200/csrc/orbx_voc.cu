@@ -351,7 +351,7 @@ int orbx_vocabulary_transform(orbx_voc* v, const uint8_t* desc, int n, int level
   if (n == 0 || v->nNodes <= 1) return ORBX_OK;     // empty(): both outputs stay empty (:1147-1150)
   ORBX_CUDA(cudaSetDevice(v->ctx->device));
   cudaStream_t st = v->ctx->stream;
-  DevScope S(st);
+  DevScope S(v->ctx, st);
   const uint8_t* d_desc = S.upload(desc, (size_t)n * 32);
   int* d_leaf = S.alloc<int>(n);
   int* d_node = S.alloc<int>(n);
@@ -361,23 +361,15 @@ int orbx_vocabulary_transform(orbx_voc* v, const uint8_t* desc, int n, int level
   if (S.failed) return ORBX_ECUDA;
   int rc = voc_launch(v, st, 1, d_desc, nullptr, n, n, levelsup, d_leaf, d_node, O);
   if (rc != ORBX_OK) return rc;
-  int cnt[2] = {0, 0};
-  ORBX_CUDA(cudaMemcpyAsync(&cnt[0], O.nBow, sizeof(int), cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaMemcpyAsync(&cnt[1], O.nFv, sizeof(int), cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(cudaStreamSynchronize(st));
-  if (cnt[0] > 0) {
-    ORBX_CUDA(cudaMemcpyAsync(bow_word, O.bowWord, sizeof(int) * cnt[0], cudaMemcpyDeviceToHost, st));
-    ORBX_CUDA(cudaMemcpyAsync(bow_value, O.bowVal, sizeof(double) * cnt[0], cudaMemcpyDeviceToHost, st));
-  }
-  ORBX_CUDA(cudaMemcpyAsync(fv_off, O.fvOff, sizeof(int) * (cnt[1] + 1), cudaMemcpyDeviceToHost, st));
-  if (cnt[1] > 0) {
-    ORBX_CUDA(cudaMemcpyAsync(fv_node, O.fvNode, sizeof(int) * cnt[1], cudaMemcpyDeviceToHost, st));
-    ORBX_CUDA(cudaMemcpyAsync(fv_idx, O.fvIdx, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-  }
-  ORBX_CUDA(cudaStreamSynchronize(st));
-  *n_bow = cnt[0];
-  *n_fv = cnt[1];
-  return ORBX_OK;
+  // one synchronisation: every output array has room for n entries, the counts say how many are meaningful
+  S.download(bow_word, (const int32_t*)O.bowWord, (size_t)n);
+  S.download(bow_value, (const double*)O.bowVal, (size_t)n);
+  S.download(fv_node, (const int32_t*)O.fvNode, (size_t)n);
+  S.download(fv_off, (const int32_t*)O.fvOff, (size_t)n + 1);
+  S.download(fv_idx, (const int32_t*)O.fvIdx, (size_t)n);
+  S.download(n_bow, (const int32_t*)O.nBow, (size_t)1);
+  S.download(n_fv, (const int32_t*)O.nFv, (size_t)1);
+  return S.finish();
 }
 
 int orbx_vocabulary_transform_batch_device(orbx_voc* v, int F, const uint8_t* d_desc, const int32_t* d_n, int cap, int levelsup,

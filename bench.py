@@ -452,7 +452,8 @@ def main():
                 list(pool.map(e2e_step, pipes))
             torch.cuda.synchronize()
             e2e_s = time.perf_counter() - t0
-    else:
+    e2e_same = None
+    if not args.e2e_sync:
         def e2e_run(nsteps):
             last = None
             for P in pipes:
@@ -473,7 +474,7 @@ def main():
         e2e_last = e2e_run(e2e_steps)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        assert np.array_equal(e2e_last[1], stats[-pipes[-1]["n"]:]) or NPE != NP, "e2e results differ from the resident arm"
+        e2e_same = bool(NPE == NP and np.array_equal(e2e_last[1], stats[-pipes[-1]["n"]:]))   # same statistics as the resident arm
     h2d = B * W * H + 2 * S * 64
     d2h = S * 64 + S * 8 * 4
     clocks = sampler.stop() if rank == 0 else None
@@ -546,7 +547,8 @@ def main():
                       "mean_per_stream": {n: float(v) for n, v in zip(trk.STATS, stats.mean(0))},
                       "max_translation_error_m": pose_err},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "steps": e2e_steps},
+                   "steps": e2e_steps, "api": "orbx_tracker_step" if args.e2e_sync else "orbx_tracker_submit/collect",
+                   "results_equal_resident_arm": e2e_same},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(out))
     if dist:

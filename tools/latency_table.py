@@ -85,6 +85,30 @@ def main():
     m6 = orbx.ORBmatcher(ctx, 0.6, True)
     add("ORBmatcher::SearchForTriangulation (2 x ~1000 kp)", "src/ORBmatcher.cc:1138",
         lambda: m6.SearchForTriangulation(*a3), lambda: oracle.search_for_triangulation(*a3))
+    # --- the "next" rows ---
+    import voc_util as vu
+    vb = vu.make_vocabulary(3, 10, 5, ragged=False, p_early_leaf=0.0)       # 111 110 nodes, the reference's k with one level less
+    V = vu.parse(vb)
+    qd = vu.query_descriptors(V, 1, 1000, 30)
+    dv, ov = orbx.ORBVocabulary(ctx, vb), oracle.Vocabulary(vb)
+    add("ORBVocabulary::transform, 1000 descriptors (k=10, L=5 synthetic tree)", "Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1140",
+        lambda: dv.transform(qd, 3), lambda: ov.transform(qd, 3))
+    bs = sc.bow_scenario(1)
+    KFb, Fb = orbx.Frame(bs["kK"], bs["dK"]), orbx.Frame(bs["kF"], bs["dF"])
+    add("ORBmatcher::SearchByBoW(KF, F) (900 x 950 kp)", "src/ORBmatcher.cc:323",
+        lambda: orbx.search_by_bow(ctx, KFb, Fb, bs["has"], bs["fvK"], bs["fvF"], 0.7, True),
+        lambda: oracle.search_by_bow(KFb, Fb, bs["has"], bs["fvK"], bs["fvF"], 0.7, True))
+    fs = sc.fuse_scenario(1, 1000, 1500)
+    KFf = orbx.Frame(fs["kK"], fs["dK"], fs["ur"])
+    fa = (KFf, cam, fs["R"], fs["t"], fs["Ow"], fs["flags"], fs["xw"], fs["maxd"], fs["mind"], fs["normal"], fs["desc"], 3.0, fs["scale"],
+          fs["inv_sigma2"], fs["log_sf"])
+    add("ORBmatcher::Fuse(KF, 1500 MapPoints) search", "src/ORBmatcher.cc:1630", lambda: orbx.fuse(ctx, *fa), lambda: oracle.fuse(*fa))
+    fr = (cam, fs["R"], fs["t"], fs["Ow"], (0.0, 752.0, 0.0, 480.0), 0.5, 8, fs["log_sf"], fs["xw"], fs["maxd"], fs["mind"], fs["normal"])
+    add("Frame::isInFrustum x 1500 MapPoints", "src/Frame.cc:571", lambda: orbx.is_in_frustum(ctx, *fr), lambda: oracle.is_in_frustum(*fr))
+    xy = np.stack([kL["x"], kL["y"]], 1)
+    dist = [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05]
+    add("Frame::UndistortKeyPoints (1000 kp)", "src/Frame.cc:874", lambda: orbx.undistort_keypoints(ctx, xy, cam, dist),
+        lambda: oracle.undistort_points(xy, cam, dist))
     # --- optimisers ---
     opt = orbx.Optimizer(ctx)
     for E in (150, 300, 500):
