@@ -299,10 +299,24 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        # exactly ONE JSON line on stdout: whatever NCCL logs (its version banner at NCCL_DEBUG >= VERSION) goes to stderr
+        # exactly ONE JSON line on stdout: NCCL prints its version banner to stdout when its debug level is VERSION
+        # (this image's default) -- send NCCL's log to stderr, and keep fd 1 pointed at stderr while the communicator is
+        # created (process-group init + the first collective), whatever else chats during initialisation
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL_DEBUG_FILE is only honoured above VERSION
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
