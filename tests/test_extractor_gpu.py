@@ -135,3 +135,32 @@ def test_fallback_tile_loads_without_tma():
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, ORBX_NO_TMA="1"), capture_output=True,
                          text=True, timeout=300)
     assert out.returncode == 0 and "fallback ok" in out.stdout, out.stderr[-1500:]
+
+
+def test_threshold_fallback_cells(ctx, ork):
+    """The iniTh -> minTh fallback (src/ORBextractor.cc:808-828) is decided per 30-px cell.  Low-contrast content makes
+    most cells fall back, mixed content makes some do, equal thresholds disable the fallback; candidates (every level)
+    and the final keypoints / descriptors stay bit-exact in all of them."""
+    import orbx
+    from orbx import synth
+    base = synth.scene_image(21, 752, 480).astype(np.float32)
+    low = np.clip(np.rint((base - 128) * 0.22 + 128), 0, 255).astype(np.uint8)        # almost every cell falls back to 7
+    mixed = base.copy()
+    mixed[:, 376:] = (mixed[:, 376:] - 128) * 0.18 + 128                               # right half falls back
+    mixed = np.clip(np.rint(mixed), 0, 255).astype(np.uint8)
+    flat = synth.constant_image(90)
+    flat[100:140, 200:260] = 98                                                        # one weak rectangle: corners only at 7
+    cb = synth.checkerboard(752, 480, 16, 120, 134)                                    # ties + only sub-iniTh corners
+    for name, img, kw in (("low", low, {}), ("mixed", mixed, {}), ("flat", flat, {}), ("checker", cb, {}),
+                          ("equal thresholds", mixed, dict(iniThFAST=12, minThFAST=12))):
+        ex = orbx.ORBextractor(ctx, **kw)
+        orc = ork.Extractor(1000, 1.2, 8, kw.get("iniThFAST", 20), kw.get("minThFAST", 7))
+        want, got = orc(img), ex(img)
+        _assert_same(want, got, name)
+        for lvl in range(8):
+            gxy, gsc = ex.debug_candidates(lvl)
+            oxy, osc = orc.candidates(lvl)
+            a = sorted(zip(gxy[:, 1].tolist(), gxy[:, 0].tolist(), gsc.tolist()))
+            b = sorted(zip(oxy[:, 1].tolist(), oxy[:, 0].tolist(), osc.tolist()))
+            assert a == b, (name, lvl, len(a), len(b))
+        ex.close()
