@@ -57,6 +57,8 @@ def lib():
                                                                                   C.c_float, C.c_void_p, C.c_void_p]
         L.ork_is_in_frustum.argtypes = [C.c_void_p] * 4 + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 11
         L.ork_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ork_pose_inertial_opt_last_kf.argtypes = [C.c_int] + [C.c_void_p] * 14 + [C.c_int] + [C.c_void_p] * 4
+        L.ork_inertial_debug.argtypes = [C.c_void_p] * 5
         L.ork_voc_from_memory.restype = C.c_void_p
         L.ork_voc_from_memory.argtypes = [C.c_void_p, C.c_size_t]
         L.ork_voc_load.restype = C.c_void_p
@@ -419,3 +421,31 @@ def undistort_points(xy, cam, dist_coef):
     rc = lib().ork_undistort_points(_p(xy), len(xy), C.byref(cam), _p(d), len(d), _p(out))
     assert rc == 0
     return out
+
+
+def pose_inertial_optimization_last_keyframe(s, cam, rec_init=False):
+    """oracle Optimizer::PoseInertialOptimizationLastKeyFrame on a scenario dict (tests/scenarios.inertial_scenario).
+    -> dict(state[21], outlier[E], H[15,15], n, iters[4])"""
+    E = len(s["isg"])
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)   # noqa: E731
+    f64 = lambda a: np.ascontiguousarray(a, np.float64)   # noqa: E731
+    xw, obs, isg, Tcw, Tcb, Tbc = map(f32, (s["xw"], s["obs"], s["isg"], s["Tcw"], s["Tcb"], s["Tbc"]))
+    close = np.ascontiguousarray(s["close"], np.uint8)
+    state, kf, pre, iI, iG, iA = map(f64, (np.array(s["state"]).copy(), s["kf"], s["preint"], s["infoI"], s["infoG"], s["infoA"]))
+    outlier = np.zeros(max(E, 1), np.uint8)
+    H = np.zeros(225, np.float64)
+    n = C.c_int(0)
+    iters = np.zeros(4, np.int32)
+    rc = lib().ork_pose_inertial_opt_last_kf(E, _p(xw), _p(obs), _p(isg), _p(close), C.byref(cam), _p(Tcw), _p(Tcb), _p(Tbc), _p(state),
+                                             _p(kf), _p(pre), _p(iI), _p(iG), _p(iA), int(rec_init), _p(outlier), _p(H), C.byref(n),
+                                             _p(iters))
+    assert rc == 0
+    return dict(state=state, outlier=outlier[:E], H=H.reshape(15, 15), n=n.value, iters=iters)
+
+
+def inertial_debug(state, kf, preint):
+    f64 = lambda a: np.ascontiguousarray(a, np.float64)   # noqa: E731
+    state, kf, preint = map(f64, (state, kf, preint))
+    e9, J = np.zeros(9), np.zeros(81)
+    lib().ork_inertial_debug(_p(state), _p(kf), _p(preint), _p(e9), _p(J))
+    return e9, J.reshape(9, 9)

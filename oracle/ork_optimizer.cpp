@@ -819,3 +819,371 @@ int ork_local_ba(int K, float* kfT, const uint8_t* kfFixed, int M, float* mpXyz,
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// Optimizer::PoseInertialOptimizationLastKeyFrame (src/Optimizer.cc:7665-8066)
+//
+// Graph: VertexPose / VertexVelocity / VertexGyroBias / VertexAccBias of the frame (free: 6+3+3+3 = 15 unknowns), the
+// same four of the last keyframe (fixed); unary EdgeMonoOnlyPose / EdgeStereoOnlyPose (include/G2oTypes.h:387-491,
+// src/G2oTypes.cc:385-407,496-520), one EdgeInertial (src/G2oTypes.cc:730-812), EdgeGyroRW, EdgeAccRW;
+// OptimizationAlgorithmGaussNewton + LinearSolverDense (pivoted LDL^T), 4 rounds x 10 iterations, Huber on the visual
+// edges for the first three rounds, chi2 classification {12, 7.5, 5.991, 5.991} / {15.6, 9.8, 7.815, 7.815} with the
+// "close point" rule, then the 15x15 Hessian handed to the next frame's prior (ConstraintPoseImu, :8030-8063).
+//
+// PARITY CONVENTIONS (the reference is not reproducible on these points):
+//  * ImuCamPose::Update re-orthonormalises Rwb every third update with NormalizeRotation = svd.matrixU()*svd.matrixV()
+//    (src/G2oTypes.cc:1085-1089: V is NOT transposed in this fork) and ExpSO3 round-trips through a float32 cv::SVDecomp
+//    (:1012-1017).  Here both are "rotation matrix -> unit quaternion -> rotation matrix" in double: the intended
+//    orthonormalisation, identical on CPU and GPU.  Results are therefore tolerance-level w.r.t. a reference binary.
+//  * what depends only on the fixed keyframe bias — GetDeltaRotation/Velocity/Position(b1) and the information
+//    matrices (inverse + eigenvalue clamp of C.block<9,9>, EdgeInertial ctor :700-727) — is an INPUT, computed once by
+//    the caller exactly as the reference's constructors do.
+//  * sums over the visual edges use the same canonical 256-way tree order as PoseOptimization.
+// ================================================================================================
+namespace ork {
+
+static void m3_mul(const double* A, const double* B, double* C) { mat3_mul(A, B, C); }
+static void m3_t(const double* A, double* T) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) T[i * 3 + j] = A[j * 3 + i]; }
+static void m3_v(const double* A, const double* v, double* o) { for (int i = 0; i < 3; ++i) o[i] = A[i * 3] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2]; }
+static void orthonormalize(double* R) {   // convention, see above
+  Quat q = quat_from_R(R);
+  quat_normalize(q);
+  quat_to_R(q, R);
+}
+static void exp_so3(const double* w, double* R) {   // ExpSO3 (src/G2oTypes.cc:1003-1019)
+  const double x = w[0], y = w[1], z = w[2];
+  const double d2 = x * x + y * y + z * z, d = std::sqrt(d2);
+  const double W[9] = {0.0, -z, y, z, 0.0, -x, -y, x, 0.0};
+  double W2[9];
+  m3_mul(W, W, W2);
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (d < 1e-5) { for (int i = 0; i < 9; ++i) R[i] = I[i] + W[i] + 0.5 * W2[i]; }
+  else { const double a = std::sin(d) / d, b = (1.0 - std::cos(d)) / d2; for (int i = 0; i < 9; ++i) R[i] = I[i] + W[i] * a + W2[i] * b; }
+  orthonormalize(R);
+}
+static void log_so3(const double* R, double* w) {   // LogSO3 (:1021-1035)
+  const double tr = R[0] + R[4] + R[8];
+  w[0] = (R[7] - R[5]) / 2; w[1] = (R[2] - R[6]) / 2; w[2] = (R[3] - R[1]) / 2;
+  const double costheta = (tr - 1.0) * 0.5f;
+  if (costheta > 1 || costheta < -1) return;
+  const double theta = std::acos(costheta), s = std::sin(theta);
+  if (std::fabs(s) < 1e-5) return;
+  for (int i = 0; i < 3; ++i) w[i] = theta * w[i] / s;
+}
+static void inv_right_jac_so3(const double* v, double* J) {   // InverseRightJacobianSO3 (:1042-1055)
+  const double x = v[0], y = v[1], z = v[2];
+  const double d2 = x * x + y * y + z * z, d = std::sqrt(d2);
+  const double W[9] = {0.0, -z, y, z, 0.0, -x, -y, x, 0.0};
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (d < 1e-5) { for (int i = 0; i < 9; ++i) J[i] = I[i]; return; }
+  double W2[9];
+  m3_mul(W, W, W2);
+  const double c = 1.0 / d2 - (1.0 + std::cos(d)) / (2.0 * d * std::sin(d));
+  for (int i = 0; i < 9; ++i) J[i] = I[i] + W[i] / 2 + W2[i] * c;
+}
+
+struct InertialProblem {
+  // inputs
+  int E;
+  const float *xw, *obs, *invSigma2;
+  const uint8_t* closePt;
+  orbx_camera cam;
+  double Rcb[9], tcb[3], Rbc[9], tbc[3];
+  double Rwb1[9], twb1[3], v1[3], bg1[3], ba1[3];     // keyframe (fixed)
+  double dR[9], dV[3], dP[3], dt, g[3];
+  double infoI[81], infoG[9], infoA[9];
+  // state
+  double Rwb[9], twb[3], Rcw[9], tcw[3], v[3], bg[3], ba[3];
+  int its = 0;
+  std::vector<uint8_t> active, stereo;
+  std::vector<double> err;
+  bool robust = true;
+  Huber hMono{std::sqrt(5.991f)}, hStereo{std::sqrt(7.815f)};
+  double H[225], b[15], x[15];
+
+  void refresh_camera() {   // ImuCamPose::Update tail (:211-218)
+    double Rbw[9], tbw[3];
+    m3_t(Rwb, Rbw);
+    m3_v(Rbw, twb, tbw);
+    for (int i = 0; i < 3; ++i) tbw[i] = -tbw[i];
+    m3_mul(Rcb, Rbw, Rcw);
+    m3_v(Rcb, tbw, tcw);
+    for (int i = 0; i < 3; ++i) tcw[i] += tcb[i];
+  }
+  void cam_point(int e, double* Xc) const {
+    const double X[3] = {xw[3 * e], xw[3 * e + 1], xw[3 * e + 2]};
+    m3_v(Rcw, X, Xc);
+    for (int i = 0; i < 3; ++i) Xc[i] += tcw[i];
+  }
+  void edge_error(int e, double* out) const {   // obs - Project / ProjectStereo (:170-185)
+    double Xc[3];
+    cam_point(e, Xc);
+    const double u = (double)cam.fx * Xc[0] / Xc[2] + (double)cam.cx, vv = (double)cam.fy * Xc[1] / Xc[2] + (double)cam.cy;
+    out[0] = (double)obs[3 * e] - u;
+    out[1] = (double)obs[3 * e + 1] - vv;
+    out[2] = 0;
+    if (stereo[e]) { const double invZ = 1 / Xc[2]; out[2] = (double)obs[3 * e + 2] - (u - (double)cam.bf * invZ); }
+  }
+  bool depth_positive(int e) const {   // ImuCamPose::isDepthPositive (:187-190)
+    return (Rcw[6] * xw[3 * e] + Rcw[7] * xw[3 * e + 1] + Rcw[8] * xw[3 * e + 2] + tcw[2]) > 0.0;
+  }
+  void edge_jacobian(int e, double* J /*[3][6]*/) const {   // EdgeMonoOnlyPose / EdgeStereoOnlyPose::linearizeOplus
+    double Xc[3], Xb[3];
+    cam_point(e, Xc);
+    m3_v(Rbc, Xc, Xb);
+    for (int i = 0; i < 3; ++i) Xb[i] += tbc[i];
+    double pj[9] = {(double)cam.fx / Xc[2], 0.0, -(double)cam.fx * Xc[0] / (Xc[2] * Xc[2]),
+                    0.0, (double)cam.fy / Xc[2], -(double)cam.fy * Xc[1] / (Xc[2] * Xc[2]), 0, 0, 0};
+    if (stereo[e]) {
+      const double inv_z2 = 1.0 / (Xc[2] * Xc[2]);
+      pj[6] = pj[0]; pj[7] = pj[1]; pj[8] = pj[2] + (double)cam.bf * inv_z2;
+    }
+    double PR[9];
+    m3_mul(pj, Rcb, PR);               // proj_jac * Rcb
+    const double x_ = Xb[0], y_ = Xb[1], z_ = Xb[2];
+    const double S[18] = {0.0, z_, -y_, 1.0, 0.0, 0.0, -z_, 0.0, x_, 0.0, 1.0, 0.0, y_, -x_, 0.0, 0.0, 0.0, 1.0};
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 6; ++c) J[r * 6 + c] = PR[r * 3] * S[c] + PR[r * 3 + 1] * S[6 + c] + PR[r * 3 + 2] * S[12 + c];
+  }
+  double chi2(int e) const {
+    const double w = (double)invSigma2[e];
+    const double* r = &err[3 * e];
+    return r[0] * w * r[0] + r[1] * w * r[1] + (stereo[e] ? r[2] * w * r[2] : 0.0);
+  }
+  void inertial_error(double* e9) const {   // EdgeInertial::computeError (:730-750)
+    double Rbw1[9], dRt[9], T1[9], eR[9];
+    m3_t(Rwb1, Rbw1);
+    m3_t(dR, dRt);
+    m3_mul(dRt, Rbw1, T1);
+    m3_mul(T1, Rwb, eR);
+    log_so3(eR, e9);
+    double a[3], c[3];
+    for (int i = 0; i < 3; ++i) a[i] = v[i] - v1[i] - g[i] * dt;
+    m3_v(Rbw1, a, c);
+    for (int i = 0; i < 3; ++i) e9[3 + i] = c[i] - dV[i];
+    for (int i = 0; i < 3; ++i) a[i] = twb[i] - twb1[i] - v1[i] * dt - g[i] * dt * dt / 2;
+    m3_v(Rbw1, a, c);
+    for (int i = 0; i < 3; ++i) e9[6 + i] = c[i] - dP[i];
+  }
+  void inertial_jacobian(double* J /*[9][9]: columns 0-5 pose 2, 6-8 velocity 2*/) const {   // linearizeOplus (:752-812)
+    double Rbw1[9], dRt[9], T1[9], eR[9], er[3], invJr[9], RR[9];
+    m3_t(Rwb1, Rbw1);
+    m3_t(dR, dRt);
+    m3_mul(dRt, Rbw1, T1);
+    m3_mul(T1, Rwb, eR);
+    log_so3(eR, er);
+    inv_right_jac_so3(er, invJr);
+    m3_mul(Rbw1, Rwb, RR);
+    for (int i = 0; i < 81; ++i) J[i] = 0;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        J[r * 9 + c] = invJr[r * 3 + c];            // d er / d rotation 2
+        J[(6 + r) * 9 + 3 + c] = RR[r * 3 + c];      // d ep / d translation 2
+        J[(3 + r) * 9 + 6 + c] = Rbw1[r * 3 + c];    // d ev / d velocity 2
+      }
+  }
+  void computeErrors() {
+    for (int e = 0; e < E; ++e)
+      if (active[e]) edge_error(e, &err[3 * e]);
+  }
+  // buildSystem over the free vertices (pose 0-5, velocity 6-8, gyro bias 9-11, acc bias 12-14)
+  void buildSystem() {
+    TreeAcc<27> acc(256);
+    for (int e = 0; e < E; ++e) {
+      if (!active[e]) continue;
+      double J[18];
+      edge_jacobian(e, J);
+      const int D = stereo[e] ? 3 : 2;
+      const double om = (double)invSigma2[e];
+      double w = 1.0;
+      if (robust) (stereo[e] ? hStereo : hMono).robustify(chi2(e), w);
+      const double* r = &err[3 * e];
+      std::array<double, 27>& a27 = acc.slot(e);
+      int idx = 0;
+      for (int i = 0; i < 6; ++i) {
+        double sg = 0;
+        for (int d = 0; d < D; ++d) sg += J[d * 6 + i] * om * r[d];
+        a27[21 + i] -= w * sg;
+        for (int j = i; j < 6; ++j) {
+          double a = 0;
+          for (int d = 0; d < D; ++d) a += J[d * 6 + i] * (w * om) * J[d * 6 + j];
+          a27[idx++] += a;
+        }
+      }
+    }
+    double out[27];
+    acc.finish(out);
+    for (int i = 0; i < 225; ++i) H[i] = 0;
+    for (int i = 0; i < 15; ++i) b[i] = 0;
+    int idx = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) { H[i * 15 + j] = out[idx]; H[j * 15 + i] = out[idx]; ++idx; }
+    for (int i = 0; i < 6; ++i) b[i] = out[21 + i];
+    // EdgeInertial: H += J^T Omega J, b -= J^T Omega e over (pose 2, velocity 2)
+    double e9[9], J[81], OJ[81], Oe[9];
+    inertial_error(e9);
+    inertial_jacobian(J);
+    for (int r = 0; r < 9; ++r) {
+      double s = 0;
+      for (int k = 0; k < 9; ++k) s += infoI[r * 9 + k] * e9[k];
+      Oe[r] = s;
+      for (int c = 0; c < 9; ++c) {
+        double t = 0;
+        for (int k = 0; k < 9; ++k) t += infoI[r * 9 + k] * J[k * 9 + c];
+        OJ[r * 9 + c] = t;
+      }
+    }
+    for (int i = 0; i < 9; ++i) {
+      double s = 0;
+      for (int k = 0; k < 9; ++k) s += J[k * 9 + i] * Oe[k];
+      b[i] -= s;
+      for (int j = 0; j < 9; ++j) {
+        double t = 0;
+        for (int k = 0; k < 9; ++k) t += J[k * 9 + i] * OJ[k * 9 + j];
+        H[i * 15 + j] += t;
+      }
+    }
+    // EdgeGyroRW / EdgeAccRW: error = bias2 - bias1, Jacobian wrt bias2 = I
+    for (int i = 0; i < 3; ++i) {
+      double sg = 0, sa = 0;
+      for (int k = 0; k < 3; ++k) { sg += infoG[i * 3 + k] * (bg[k] - bg1[k]); sa += infoA[i * 3 + k] * (ba[k] - ba1[k]); }
+      b[9 + i] -= sg;
+      b[12 + i] -= sa;
+      for (int j = 0; j < 3; ++j) { H[(9 + i) * 15 + 9 + j] += infoG[i * 3 + j]; H[(12 + i) * 15 + 12 + j] += infoA[i * 3 + j]; }
+    }
+  }
+  bool solve() { return ldlt_solve_pivoted(15, H, b, x); }   // a failed solve leaves _x as it was (LinearSolverDense)
+  void update() {   // VertexPose::oplusImpl -> ImuCamPose::Update (:192-220); velocity / biases: plain addition
+    double d[3], E3[9], Rn[9];
+    m3_v(Rwb, x + 3, d);
+    for (int i = 0; i < 3; ++i) twb[i] += d[i];
+    exp_so3(x, E3);
+    m3_mul(Rwb, E3, Rn);
+    for (int i = 0; i < 9; ++i) Rwb[i] = Rn[i];
+    if (++its >= 3) { orthonormalize(Rwb); its = 0; }
+    refresh_camera();
+    for (int i = 0; i < 3; ++i) { v[i] += x[6 + i]; bg[i] += x[9 + i]; ba[i] += x[12 + i]; }
+  }
+};
+
+}  // namespace ork
+
+extern "C" {
+
+// state15 in/out (double): Rwb[9], twb[3], v[3], bg[3], ba[3] of the frame; kf_state (double[21]): the same of the
+// keyframe.  Tcw/Tcb/Tbc: float 4x4 row-major (pFrame->mTcw, mImuCalib.Tcb, mImuCalib.Tbc).  preint: dR[9], dV[3], dP[3],
+// dt (16 doubles) evaluated at the keyframe's bias; gravity = (0, 0, -9.81).  info_inertial[81], info_gyro[9], info_acc[9].
+// obs[e][2] < 0 -> mono edge; inv_sigma2 already divided by uncertainty2 (= 1 for Pinhole); close_pt[e] = mTrackDepth < 10.
+// Out: outlier[E], H15[225] (ConstraintPoseImu), *n_ret = nInitialCorrespondences - nBad, iters[4] = GN iterations run.
+int ork_pose_inertial_opt_last_kf(int E, const float* xw, const float* obs, const float* invSigma2, const uint8_t* closePt,
+                                  const orbx_camera* cam, const float* Tcw, const float* Tcb, const float* Tbc, double* state,
+                                  const double* kfState, const double* preint, const double* infoI, const double* infoG,
+                                  const double* infoA, int recInit, uint8_t* outlier, double* H15, int* nRet, int* iters) {
+  InertialProblem P;
+  for (int i = 0; i < 15; ++i) P.x[i] = 0;
+  P.E = E; P.xw = xw; P.obs = obs; P.invSigma2 = invSigma2; P.closePt = closePt; P.cam = *cam;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) { P.Rcb[i * 3 + j] = Tcb[i * 4 + j]; P.Rcw[i * 3 + j] = Tcw[i * 4 + j]; }
+    P.tcb[i] = Tcb[i * 4 + 3]; P.tbc[i] = Tbc[i * 4 + 3]; P.tcw[i] = Tcw[i * 4 + 3];
+  }
+  m3_t(P.Rcb, P.Rbc);
+  std::memcpy(P.Rwb, state, sizeof(double) * 9); std::memcpy(P.twb, state + 9, 24); std::memcpy(P.v, state + 12, 24);
+  std::memcpy(P.bg, state + 15, 24); std::memcpy(P.ba, state + 18, 24);
+  std::memcpy(P.Rwb1, kfState, sizeof(double) * 9); std::memcpy(P.twb1, kfState + 9, 24); std::memcpy(P.v1, kfState + 12, 24);
+  std::memcpy(P.bg1, kfState + 15, 24); std::memcpy(P.ba1, kfState + 18, 24);
+  std::memcpy(P.dR, preint, sizeof(double) * 9); std::memcpy(P.dV, preint + 9, 24); std::memcpy(P.dP, preint + 12, 24);
+  P.dt = preint[15];
+  P.g[0] = 0; P.g[1] = 0; P.g[2] = -9.81;   // IMU::GRAVITY_VALUE (include/ImuTypes.h)
+  std::memcpy(P.infoI, infoI, sizeof(double) * 81); std::memcpy(P.infoG, infoG, 72); std::memcpy(P.infoA, infoA, 72);
+  P.active.assign(E, 1);
+  P.stereo.resize(E);
+  P.err.assign((size_t)3 * E, 0.0);
+  for (int e = 0; e < E; ++e) { P.stereo[e] = obs[3 * e + 2] >= 0; outlier[e] = 0; }
+  const float chi2Mono[4] = {12, 7.5, 5.991, 5.991}, chi2Stereo[4] = {15.6, 9.8, 7.815, 7.815};
+  int nBad = 0, nInliers = 0;
+  for (int it = 0; it < 4; ++it) {
+    iters[it] = 0;
+    bool ok = true;
+    for (int k = 0; k < 10 && ok; ++k) {   // OptimizationAlgorithmGaussNewton::solve
+      P.computeErrors();
+      P.buildSystem();
+      ok = P.solve();
+      P.update();                          // g2o applies _solver->x() even when the solve failed (stale update), then stops
+      ++iters[it];
+    }
+    nBad = 0; nInliers = 0;
+    const float chi2close = 1.5 * chi2Mono[it];
+    for (int e = 0; e < E; ++e) {
+      if (outlier[e]) P.edge_error(e, &P.err[3 * e]);
+      const float chi2 = (float)P.chi2(e);
+      bool bad;
+      if (!P.stereo[e]) {
+        const bool bClose = closePt[e] != 0;
+        bad = (chi2 > chi2Mono[it] && !bClose) || (bClose && chi2 > chi2close) || !P.depth_positive(e);
+      } else {
+        bad = chi2 > chi2Stereo[it];
+      }
+      outlier[e] = bad;
+      P.active[e] = !bad;
+      if (bad) ++nBad; else ++nInliers;
+    }
+    if (it == 2) P.robust = false;
+    if (E + 3 < 10) break;                 // optimizer.edges().size() < 10 (visual edges + inertial + 2 random walks)
+  }
+  if (nInliers < 30 && !recInit) {         // recovery of edges that are not too bad (:7990-8020)
+    nBad = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int e = 0; e < E; ++e) {
+        if ((pass == 0) == (bool)P.stereo[e]) continue;   // mono edges first, then stereo
+        P.edge_error(e, &P.err[3 * e]);
+        if (P.chi2(e) < (P.stereo[e] ? 24.f : 18.f)) outlier[e] = 0; else ++nBad;
+      }
+  }
+  std::memcpy(state, P.Rwb, 72); std::memcpy(state + 9, P.twb, 24); std::memcpy(state + 12, P.v, 24);
+  std::memcpy(state + 15, P.bg, 24); std::memcpy(state + 18, P.ba, 24);
+  // H for the next frame's prior: inertial (9x9 at pose/velocity), random walks, visual inliers without robust weights
+  for (int i = 0; i < 225; ++i) H15[i] = 0;
+  {
+    double J[81], OJ[81];
+    P.inertial_jacobian(J);
+    for (int r = 0; r < 9; ++r)
+      for (int c = 0; c < 9; ++c) { double t = 0; for (int k = 0; k < 9; ++k) t += P.infoI[r * 9 + k] * J[k * 9 + c]; OJ[r * 9 + c] = t; }
+    for (int i = 0; i < 9; ++i)
+      for (int j = 0; j < 9; ++j) { double t = 0; for (int k = 0; k < 9; ++k) t += J[k * 9 + i] * OJ[k * 9 + j]; H15[i * 15 + j] += t; }
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) { H15[(9 + i) * 15 + 9 + j] += P.infoG[i * 3 + j]; H15[(12 + i) * 15 + 12 + j] += P.infoA[i * 3 + j]; }
+    TreeAcc<36> acc(256);
+    for (int e = 0; e < E; ++e) {
+      if (outlier[e]) continue;
+      double Je[18];
+      P.edge_jacobian(e, Je);
+      const int D = P.stereo[e] ? 3 : 2;
+      const double om = (double)invSigma2[e];
+      std::array<double, 36>& a = acc.slot(e);
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) { double t = 0; for (int d = 0; d < D; ++d) t += Je[d * 6 + i] * om * Je[d * 6 + j]; a[i * 6 + j] += t; }
+    }
+    double out[36];
+    acc.finish(out);
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) H15[i * 15 + j] += out[i * 6 + j];
+  }
+  *nRet = E - nBad;
+  return ORBX_OK;
+}
+
+// test hooks: the analytic Jacobians against the error functions (finite differences are taken by the test)
+int ork_inertial_debug(const double* state, const double* kfState, const double* preint, double* e9, double* J81) {
+  InertialProblem P;
+  std::memcpy(P.Rwb, state, 72); std::memcpy(P.twb, state + 9, 24); std::memcpy(P.v, state + 12, 24);
+  std::memcpy(P.bg, state + 15, 24); std::memcpy(P.ba, state + 18, 24);
+  std::memcpy(P.Rwb1, kfState, 72); std::memcpy(P.twb1, kfState + 9, 24); std::memcpy(P.v1, kfState + 12, 24);
+  std::memcpy(P.dR, preint, 72); std::memcpy(P.dV, preint + 9, 24); std::memcpy(P.dP, preint + 12, 24);
+  P.dt = preint[15];
+  P.g[0] = 0; P.g[1] = 0; P.g[2] = -9.81;
+  P.inertial_error(e9);
+  P.inertial_jacobian(J81);
+  return ORBX_OK;
+}
+
+}  // extern "C"

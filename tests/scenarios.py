@@ -343,3 +343,76 @@ def fuse_scenario(seed, n_kp=900, n_mp=700, stereo=True, th=3.0):
     return dict(kK=kK, dK=dK, ur=ur if stereo else None, R=R.astype(np.float32).ravel(), t=t.astype(np.float32),
                 Ow=Ow.astype(np.float32), flags=flags, xw=xw, maxd=maxd, mind=mind, normal=normal, desc=desc, th=th,
                 scale=scale, inv_sigma2=inv_sigma2, log_sf=float(np.float32(np.log(np.float32(1.2)))))
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY.md §8 f3 scenario: PoseInertialOptimizationLastKeyFrame
+# ------------------------------------------------------------------------------------------------
+def _exp_so3(w):
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+
+
+def inertial_scenario(seed, E=300, stereo_frac=0.6, outlier_frac=0.1, dt=0.25, noise_px=0.7, perturb=True):
+    """A keyframe and a frame dt seconds later with known body states; the pre-integrated IMU deltas are the exact relative
+    motion (so the inertial residual vanishes at the truth), E map points observed by the frame's left camera with pixel
+    noise and a few gross outliers.  The frame's initial state is the truth perturbed by (1 deg, 3 cm, 5 cm/s, small biases)."""
+    rng = np.random.default_rng(seed)
+    g = np.array([0.0, 0.0, -9.81])
+    # EuRoC-like body-camera extrinsics
+    Rbc = _exp_so3(np.array([0.01, -0.02, 1.55]))
+    tbc = np.array([-0.02, -0.06, 0.01])
+    Tbc = np.eye(4); Tbc[:3, :3] = Rbc; Tbc[:3, 3] = tbc
+    Tcb = np.linalg.inv(Tbc)
+    Rwb1 = _exp_so3(rng.normal(0, 0.3, 3)); twb1 = rng.uniform(-1, 1, 3); v1 = rng.normal(0, 0.5, 3)
+    bg1 = rng.normal(0, 0.002, 3); ba1 = rng.normal(0, 0.02, 3)
+    Rwb2 = Rwb1 @ _exp_so3(rng.normal(0, 0.08, 3)); v2 = v1 + rng.normal(0, 0.3, 3); twb2 = twb1 + v1 * dt + rng.normal(0, 0.03, 3)
+    dR = Rwb1.T @ Rwb2
+    dV = Rwb1.T @ (v2 - v1 - g * dt)
+    dP = Rwb1.T @ (twb2 - twb1 - v1 * dt - 0.5 * g * dt * dt)
+    # camera pose of the frame
+    Rbw2 = Rwb2.T
+    Rcw = Tcb[:3, :3] @ Rbw2
+    tcw = Tcb[:3, :3] @ (-Rbw2 @ twb2) + Tcb[:3, 3]
+    xw = np.zeros((E, 3), np.float32); obs = np.zeros((E, 3), np.float32); isg = np.zeros(E, np.float32); close = np.zeros(E, np.uint8)
+    scale = 1.2 ** np.arange(8)
+    for e in range(E):
+        z = rng.uniform(1.5, 18.0)
+        u, v = rng.uniform(30, 720), rng.uniform(30, 450)
+        Xc = np.array([(u - CX) / FX * z, (v - CY) / FY * z, z])
+        Xw = Rcw.T @ (Xc - tcw)
+        xw[e] = Xw
+        Xc = Rcw @ xw[e].astype(np.float64) + tcw
+        lvl = min(int(rng.geometric(0.4)) - 1, 7)
+        s = noise_px * scale[lvl]
+        uu = FX * Xc[0] / Xc[2] + CX + rng.normal(0, s)
+        vv = FY * Xc[1] / Xc[2] + CY + rng.normal(0, s)
+        ur = -1.0
+        if rng.random() < stereo_frac:
+            ur = uu - BF / Xc[2] + rng.normal(0, s)
+        if rng.random() < outlier_frac:
+            uu += rng.choice([-1, 1]) * rng.uniform(15, 60)
+        obs[e] = (uu, vv, ur)
+        isg[e] = 1.0 / (scale[lvl] ** 2)
+        close[e] = Xc[2] < 10.0
+    Tcw = np.eye(4); Tcw[:3, :3] = Rcw; Tcw[:3, 3] = tcw
+    truth = np.concatenate([Rwb2.ravel(), twb2, v2, bg1, ba1])
+    state = truth.copy()
+    if perturb:
+        Rp = Rwb2 @ _exp_so3(rng.normal(0, 0.01, 3))
+        tp = twb2 + rng.normal(0, 0.03, 3)
+        state = np.concatenate([Rp.ravel(), tp, v2 + rng.normal(0, 0.05, 3), bg1 + rng.normal(0, 1e-4, 3), ba1 + rng.normal(0, 1e-3, 3)])
+        Rbw = Rp.T
+        Tcw[:3, :3] = Tcb[:3, :3] @ Rbw
+        Tcw[:3, 3] = Tcb[:3, :3] @ (-Rbw @ tp) + Tcb[:3, 3]
+    kf = np.concatenate([Rwb1.ravel(), twb1, v1, bg1, ba1])
+    preint = np.concatenate([dR.ravel(), dV, dP, [dt]])
+    A = rng.normal(0, 1, (9, 9))
+    infoI = A @ A.T + np.diag([4e4] * 3 + [2e3] * 3 + [8e3] * 3)      # SPD, magnitudes of a 0.25 s pre-integration covariance inverse
+    infoG = np.eye(3) * 1e7 + 0.0
+    infoA = np.eye(3) * 1e4 + 0.0
+    return dict(xw=xw, obs=obs, isg=isg, close=close, Tcw=Tcw.astype(np.float32), Tcb=Tcb.astype(np.float32), Tbc=Tbc.astype(np.float32),
+                state=state, truth=truth, kf=kf, preint=preint, infoI=infoI, infoG=infoG, infoA=infoA)
