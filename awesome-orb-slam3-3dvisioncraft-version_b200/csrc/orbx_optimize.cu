@@ -383,37 +383,38 @@ __device__ bool ldlt6_solve_warp(double* A, const double* b, double* x, int* per
 // keeps the scaled column k as its row tail (L^T), so the backward substitution reads registers only.
 // A: 36 doubles (symmetric, row-major, lambda already on the diagonal), b: 6, x: 6 (shared or global memory).
 // All 32 lanes of the warp must call; every lane returns the same value.
-__device__ bool ldlt6_solve_shfl(const double* A, const double* b, double* x) {
+template <int N>
+__device__ bool ldlt_solve_shfl(const double* A, const double* b, double* x) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int li = lane < 6 ? lane : 5;            // lanes >= 6 shadow lane 5 (never a shuffle source)
-  double a[6];
+  const int li = lane < N ? lane : N - 1;        // lanes >= N shadow lane N-1 (never a shuffle source)
+  double a[N];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) a[j] = A[li * 6 + j];
+  for (int j = 0; j < N; ++j) a[j] = A[li * N + j];
   int perm = li;
   bool positive = true;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
+  for (int k = 0; k < N; ++k) {
     double dg = a[0];
 #pragma unroll
-    for (int j = 1; j < 6; ++j)
+    for (int j = 1; j < N; ++j)
       if (li == j) dg = a[j];
     int p = k;
     double best = fabs(__shfl_sync(FULL, dg, k));
 #pragma unroll
-    for (int i = k + 1; i < 6; ++i) {
+    for (int i = k + 1; i < N; ++i) {
       const double v = fabs(__shfl_sync(FULL, dg, i));
       if (v > best) { best = v; p = i; }
     }
     if (p != k) {                                 // warp-uniform
       const int src = lane == k ? p : (lane == p ? k : lane);
 #pragma unroll
-      for (int j = 0; j < 6; ++j) a[j] = __shfl_sync(FULL, a[j], src);
+      for (int j = 0; j < N; ++j) a[j] = __shfl_sync(FULL, a[j], src);
       perm = __shfl_sync(FULL, perm, src);
       const double t = a[k];
       double ap = t;
 #pragma unroll
-      for (int j = k + 1; j < 6; ++j)
+      for (int j = k + 1; j < N; ++j)
         if (p == j) { ap = a[j]; a[j] = t; }
       a[k] = ap;
     }
@@ -423,7 +424,7 @@ __device__ bool ldlt6_solve_shfl(const double* A, const double* b, double* x) {
     double lik = a[k];
     if (li > k) { lik = a[k] / d; a[k] = lik; }
 #pragma unroll
-    for (int j = k + 1; j < 6; ++j) {
+    for (int j = k + 1; j < N; ++j) {
       const double ljk = __shfl_sync(FULL, lik, j);
       if (li > k) {
         const double hi = j <= li ? lik : ljk, lo = j <= li ? ljk : lik;   // (A[max(i,j)][k]*d)*A[min(i,j)][k]
@@ -436,26 +437,28 @@ __device__ bool ldlt6_solve_shfl(const double* A, const double* b, double* x) {
   if (!positive) return false;
   double y = b[perm];
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {                   // forward: y[i] -= L[i][j]*y[j], j ascending
+  for (int j = 0; j < N - 1; ++j) {               // forward: y[i] -= L[i][j]*y[j], j ascending
     const double yj = __shfl_sync(FULL, y, j);
     if (li > j) y -= a[j] * yj;
   }
   {
     double dg = a[0];
 #pragma unroll
-    for (int j = 1; j < 6; ++j)
+    for (int j = 1; j < N; ++j)
       if (li == j) dg = a[j];
     y = (dg != 0) ? y / dg : 0.0;
   }
 #pragma unroll
-  for (int j = 5; j > 0; --j) {                   // backward: y[i] -= L[j][i]*y[j], j descending
+  for (int j = N - 1; j > 0; --j) {               // backward: y[i] -= L[j][i]*y[j], j descending
     const double yj = __shfl_sync(FULL, y, j);
     if (li < j) y -= a[j] * yj;
   }
-  if (lane < 6) x[perm] = y;
+  if (lane < N) x[perm] = y;
   __syncwarp();
   return true;
 }
+
+__device__ __forceinline__ bool ldlt6_solve_shfl(const double* A, const double* b, double* x) { return ldlt_solve_shfl<6>(A, b, x); }
 
 // =====================================================================================
 // K11  PoseOptimization: one CTA per frame
@@ -1591,6 +1594,389 @@ int orbx_launch_pose_opt_slices(orbx_ctx* ctx, cudaStream_t st, int P, const int
 }
 
 // =====================================================================================
+// K20  PoseInertialOptimizationLastKeyFrame (src/Optimizer.cc:7665-8066, src/G2oTypes.cc:170-220,385-407,
+//      496-520,730-812,995-1090): one CTA per problem.  15 unknowns (pose 6, velocity 3, gyro bias 3, acc bias 3),
+//      Gauss-Newton 4 x 10 iterations, visual only-pose edges reduced with the canonical 256-way tree of K11, the
+//      inertial / random-walk edges added by 81 threads with a fixed per-element summation order (k ascending), 15x15 pivoted
+//      LDL^T in registers + shuffles (one warp), ImuCamPose::Update by one thread.  Conventions for the two points where
+//      the reference is not reproducible (re-orthonormalisation, ExpSO3's float SVD): DESIGN.md §7.
+// =====================================================================================
+struct PioArgs {
+  int E;
+  const float *xw, *obs, *invSigma2;
+  const uint8_t* closePt;
+  float fx, fy, cx, cy, bf;
+  double Rcb[9], tcb[3], Rbc[9], tbc[3], Rcw0[9], tcw0[3];
+  double state[21], kf[21];          // Rwb, twb, v, bg, ba
+  double dR[9], dV[3], dP[3], dt;
+  double infoI[81], infoG[9], infoA[9];
+  int recInit;
+  uint8_t* outlier;                  // [E]
+  double* err;                       // [3E] scratch
+  double* outState;                  // [21]
+  double* H15;                       // [225]
+  int* nRet;
+  int* iters;                        // [4]
+};
+
+__device__ __forceinline__ void d_m3_mul(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+__device__ __forceinline__ void d_m3_t(const double* A, double* T) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) T[i * 3 + j] = A[j * 3 + i];
+}
+__device__ __forceinline__ void d_m3_v(const double* A, const double* v, double* o) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = A[i * 3] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2];
+}
+__device__ __forceinline__ void d_orthonormalize(double* R) {
+  Quat q = quat_from_R(R);
+  quat_normalize(q);
+  quat_to_R(q, R);
+}
+__device__ void d_exp_so3(const double* w, double* R) {
+  const double x = w[0], y = w[1], z = w[2];
+  const double d2 = x * x + y * y + z * z, d = sqrt(d2);
+  const double W[9] = {0.0, -z, y, z, 0.0, -x, -y, x, 0.0};
+  double W2[9];
+  d_m3_mul(W, W, W2);
+  if (d < 1e-5) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + W[i] + 0.5 * W2[i];
+  } else {
+    const double a = sin(d) / d, b = (1.0 - cos(d)) / d2;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + W[i] * a + W2[i] * b;
+  }
+  d_orthonormalize(R);
+}
+__device__ void d_log_so3(const double* R, double* w) {
+  const double tr = R[0] + R[4] + R[8];
+  w[0] = (R[7] - R[5]) / 2; w[1] = (R[2] - R[6]) / 2; w[2] = (R[3] - R[1]) / 2;
+  const double costheta = (tr - 1.0) * 0.5;
+  if (costheta > 1 || costheta < -1) return;
+  const double theta = acos(costheta), sn = sin(theta);
+  if (fabs(sn) < 1e-5) return;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) w[i] = theta * w[i] / sn;
+}
+__device__ void d_inv_right_jac(const double* v, double* J) {
+  const double x = v[0], y = v[1], z = v[2];
+  const double d2 = x * x + y * y + z * z, d = sqrt(d2);
+  const double W[9] = {0.0, -z, y, z, 0.0, -x, -y, x, 0.0};
+  if (d < 1e-5) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) J[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  double W2[9];
+  d_m3_mul(W, W, W2);
+  const double c = 1.0 / d2 - (1.0 + cos(d)) / (2.0 * d * sin(d));
+#pragma unroll
+  for (int i = 0; i < 9; ++i) J[i] = ((i % 4 == 0) ? 1.0 : 0.0) + W[i] / 2 + W2[i] * c;
+}
+
+struct PioShared {
+  double Rwb[9], twb[3], Rcw[9], tcw[3], v[3], bg[3], ba[3];
+  double H[225], b[15], x[15], tot[36];
+  double e9[9], J[81], OJ[81], Oe[9];
+  double red[(256 / 32) * 36];
+  int its, ok;
+};
+
+// residual of a visual edge at the shared camera pose
+__device__ __forceinline__ void pio_edge_error(const PioArgs& A, const PioShared& S, int e, bool st, double* out, double* Xc) {
+  const double X[3] = {(double)A.xw[3 * e], (double)A.xw[3 * e + 1], (double)A.xw[3 * e + 2]};
+  d_m3_v(S.Rcw, X, Xc);
+  Xc[0] += S.tcw[0]; Xc[1] += S.tcw[1]; Xc[2] += S.tcw[2];
+  const double u = (double)A.fx * Xc[0] / Xc[2] + (double)A.cx, v = (double)A.fy * Xc[1] / Xc[2] + (double)A.cy;
+  out[0] = (double)A.obs[3 * e] - u;
+  out[1] = (double)A.obs[3 * e + 1] - v;
+  out[2] = 0;
+  if (st) { const double invZ = 1 / Xc[2]; out[2] = (double)A.obs[3 * e + 2] - (u - (double)A.bf * invZ); }
+}
+__device__ __forceinline__ void pio_edge_jacobian(const PioArgs& A, const double* Xc, bool st, double* J) {
+  double Xb[3];
+  d_m3_v(A.Rbc, Xc, Xb);
+  Xb[0] += A.tbc[0]; Xb[1] += A.tbc[1]; Xb[2] += A.tbc[2];
+  double pj[9] = {(double)A.fx / Xc[2], 0.0, -(double)A.fx * Xc[0] / (Xc[2] * Xc[2]),
+                  0.0, (double)A.fy / Xc[2], -(double)A.fy * Xc[1] / (Xc[2] * Xc[2]), 0, 0, 0};
+  if (st) {
+    const double inv_z2 = 1.0 / (Xc[2] * Xc[2]);
+    pj[6] = pj[0]; pj[7] = pj[1]; pj[8] = pj[2] + (double)A.bf * inv_z2;
+  }
+  double PR[9];
+  d_m3_mul(pj, A.Rcb, PR);
+  const double x_ = Xb[0], y_ = Xb[1], z_ = Xb[2];
+  const double Sd[18] = {0.0, z_, -y_, 1.0, 0.0, 0.0, -z_, 0.0, x_, 0.0, 1.0, 0.0, y_, -x_, 0.0, 0.0, 0.0, 1.0};
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) J[r * 6 + c] = PR[r * 3] * Sd[c] + PR[r * 3 + 1] * Sd[6 + c] + PR[r * 3 + 2] * Sd[12 + c];
+}
+// EdgeInertial error + Jacobian (pose 2: columns 0-5, velocity 2: columns 6-8) by one thread into shared memory
+__device__ void pio_inertial(const PioArgs& A, PioShared& S, bool withError) {
+  const double* Rwb1 = A.kf;
+  double Rbw1[9], dRt[9], T1[9], eR[9], er[3], invJr[9], RR[9];
+  d_m3_t(Rwb1, Rbw1);
+  d_m3_t(A.dR, dRt);
+  d_m3_mul(dRt, Rbw1, T1);
+  d_m3_mul(T1, S.Rwb, eR);
+  d_log_so3(eR, er);
+  if (withError) {
+    double a[3], c[3];
+    S.e9[0] = er[0]; S.e9[1] = er[1]; S.e9[2] = er[2];
+    for (int i = 0; i < 3; ++i) a[i] = S.v[i] - A.kf[12 + i] - (i == 2 ? -9.81 : 0.0) * A.dt;
+    d_m3_v(Rbw1, a, c);
+    for (int i = 0; i < 3; ++i) S.e9[3 + i] = c[i] - A.dV[i];
+    for (int i = 0; i < 3; ++i) a[i] = S.twb[i] - A.kf[9 + i] - A.kf[12 + i] * A.dt - (i == 2 ? -9.81 : 0.0) * A.dt * A.dt / 2;
+    d_m3_v(Rbw1, a, c);
+    for (int i = 0; i < 3; ++i) S.e9[6 + i] = c[i] - A.dP[i];
+  }
+  d_inv_right_jac(er, invJr);
+  d_m3_mul(Rbw1, S.Rwb, RR);
+  for (int i = 0; i < 81; ++i) S.J[i] = 0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      S.J[r * 9 + c] = invJr[r * 3 + c];
+      S.J[(6 + r) * 9 + 3 + c] = RR[r * 3 + c];
+      S.J[(3 + r) * 9 + 6 + c] = Rbw1[r * 3 + c];
+    }
+}
+
+__global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __restrict__ args) {
+  const PioArgs& A = args[blockIdx.x];
+  __shared__ PioShared S;
+  const int tid = threadIdx.x, E = A.E;
+  const float* isg = A.invSigma2;
+  uint8_t* outlier = A.outlier;
+  double* err = A.err;
+  if (tid < 9) { S.Rwb[tid] = A.state[tid]; S.Rcw[tid] = A.Rcw0[tid]; }
+  if (tid < 3) { S.twb[tid] = A.state[9 + tid]; S.v[tid] = A.state[12 + tid]; S.bg[tid] = A.state[15 + tid]; S.ba[tid] = A.state[18 + tid]; S.tcw[tid] = A.tcw0[tid]; }
+  if (tid < 15) S.x[tid] = 0;
+  if (tid == 0) S.its = 0;
+  if (tid < 4) A.iters[tid] = 0;
+  for (int e = tid; e < E; e += 256) outlier[e] = 0;
+  __syncthreads();
+  const HuberD hMono = huber_make(sqrtf(5.991f)), hStereo = huber_make(sqrtf(7.815f));
+  const float chi2Mono[4] = {12.f, 7.5f, 5.991f, 5.991f}, chi2Stereo[4] = {15.6f, 9.8f, 7.815f, 7.815f};
+  bool robust = true;
+  int nBad = 0, nInliers = 0;
+  for (int round = 0; round < 4; ++round) {
+    int cj = 0;
+    bool ok = true;
+    for (int it = 0; it < 10 && ok; ++it) {
+      // ---- computeActiveErrors + buildSystem of the visual edges (canonical 256-way tree) ----
+      double acc[27];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) acc[k] = 0;
+      for (int e = tid; e < E; e += 256) {
+        if (outlier[e]) continue;
+        const bool st = A.obs[3 * e + 2] >= 0;
+        double r[3], Xc[3], J[18];
+        pio_edge_error(A, S, e, st, r, Xc);
+        err[3 * e] = r[0]; err[3 * e + 1] = r[1]; err[3 * e + 2] = r[2];
+        pio_edge_jacobian(A, Xc, st, J);
+        const int D = st ? 3 : 2;
+        const double om = (double)isg[e];
+        double w = 1.0;
+        if (robust) huber_rho(st ? hStereo : hMono, r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0), w);
+        int idx = 0;
+        for (int i = 0; i < 6; ++i) {
+          double sg = 0;
+          for (int d = 0; d < D; ++d) sg += J[d * 6 + i] * om * r[d];
+          acc[21 + i] -= w * sg;
+          for (int j = i; j < 6; ++j) {
+            double a = 0;
+            for (int d = 0; d < D; ++d) a += J[d * 6 + i] * (w * om) * J[d * 6 + j];
+            acc[idx++] += a;
+          }
+        }
+      }
+      block_partials<27>(acc, S.red);
+      if (tid < 27) {
+        double s = 0;
+        for (int w = 0; w < 8; ++w) s += S.red[w * 27 + tid];
+        S.tot[tid] = s;
+      }
+      if (tid == 32) pio_inertial(A, S, true);      // (another warp: runs beside the cross-warp sums)
+      __syncthreads();
+      // ---- assemble H (15x15), b ----
+      if (tid < 225) S.H[tid] = 0;
+      if (tid < 15) S.b[tid] = 0;
+      __syncthreads();
+      if (tid < 36) {
+        const int i = tid / 6, j = tid - 6 * i, lo = min(i, j), hi = max(i, j);
+        S.H[i * 15 + j] = S.tot[6 * lo - (lo * (lo - 1)) / 2 + (hi - lo)];
+      } else if (tid < 42) {
+        S.b[tid - 36] = S.tot[21 + tid - 36];
+      }
+      if (tid >= 64 && tid < 64 + 81) {             // Omega * J, Omega * e (per element, k ascending)
+        const int r = (tid - 64) / 9, c = (tid - 64) - 9 * r;
+        double t = 0;
+        for (int k = 0; k < 9; ++k) t += A.infoI[r * 9 + k] * S.J[k * 9 + c];
+        S.OJ[r * 9 + c] = t;
+        if (c == 0) {
+          double s2 = 0;
+          for (int k = 0; k < 9; ++k) s2 += A.infoI[r * 9 + k] * S.e9[k];
+          S.Oe[r] = s2;
+        }
+      }
+      __syncthreads();
+      if (tid < 81) {                               // H += J^T (Omega J), b -= J^T (Omega e)
+        const int i = tid / 9, j = tid - 9 * i;
+        double t = 0;
+        for (int k = 0; k < 9; ++k) t += S.J[k * 9 + i] * S.OJ[k * 9 + j];
+        S.H[i * 15 + j] += t;
+        if (j == 0) {
+          double s2 = 0;
+          for (int k = 0; k < 9; ++k) s2 += S.J[k * 9 + i] * S.Oe[k];
+          S.b[i] -= s2;
+        }
+      } else if (tid >= 96 && tid < 99) {           // random-walk edges: error = bias - bias_kf, Jacobian I
+        const int i = tid - 96;
+        double sg = 0, sa = 0;
+        for (int k = 0; k < 3; ++k) { sg += A.infoG[i * 3 + k] * (S.bg[k] - A.kf[15 + k]); sa += A.infoA[i * 3 + k] * (S.ba[k] - A.kf[18 + k]); }
+        S.b[9 + i] -= sg;
+        S.b[12 + i] -= sa;
+        for (int j = 0; j < 3; ++j) { S.H[(9 + i) * 15 + 9 + j] += A.infoG[i * 3 + j]; S.H[(12 + i) * 15 + 12 + j] += A.infoA[i * 3 + j]; }
+      }
+      __syncthreads();
+      // ---- solve (LinearSolverDense: pivoted LDL^T; a failure leaves x as it was) + update ----
+      if (tid < 32) {
+        const bool okSolve = ldlt_solve_shfl<15>(S.H, S.b, S.x);
+        if (tid == 0) {
+          S.ok = okSolve ? 1 : 0;
+          double d[3], E3[9], Rn[9];
+          d_m3_v(S.Rwb, S.x + 3, d);
+          for (int i = 0; i < 3; ++i) S.twb[i] += d[i];
+          d_exp_so3(S.x, E3);
+          d_m3_mul(S.Rwb, E3, Rn);
+          for (int i = 0; i < 9; ++i) S.Rwb[i] = Rn[i];
+          if (++S.its >= 3) { d_orthonormalize(S.Rwb); S.its = 0; }
+          double Rbw[9], tbw[3];
+          d_m3_t(S.Rwb, Rbw);
+          d_m3_v(Rbw, S.twb, tbw);
+          for (int i = 0; i < 3; ++i) tbw[i] = -tbw[i];
+          d_m3_mul(A.Rcb, Rbw, S.Rcw);
+          d_m3_v(A.Rcb, tbw, S.tcw);
+          for (int i = 0; i < 3; ++i) { S.tcw[i] += A.tcb[i]; S.v[i] += S.x[6 + i]; S.bg[i] += S.x[9 + i]; S.ba[i] += S.x[12 + i]; }
+        }
+      }
+      __syncthreads();
+      ok = S.ok != 0;
+      ++cj;
+    }
+    if (tid == 0) A.iters[round] = cj;
+    // ---- chi2 classification (src/Optimizer.cc:7900-7975) ----
+    const float chi2close = 1.5f * chi2Mono[round];
+    double cnt[2] = {0, 0};
+    for (int e = tid; e < E; e += 256) {
+      const bool st = A.obs[3 * e + 2] >= 0;
+      if (outlier[e]) {
+        double r[3], Xc[3];
+        pio_edge_error(A, S, e, st, r, Xc);
+        err[3 * e] = r[0]; err[3 * e + 1] = r[1]; err[3 * e + 2] = r[2];
+      }
+      const double om = (double)isg[e];
+      const double* r = err + 3 * e;
+      const float chi2 = (float)(r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0));
+      bool bad;
+      if (!st) {
+        const bool bClose = A.closePt[e] != 0;
+        const bool depthPos = (S.Rcw[6] * (double)A.xw[3 * e] + S.Rcw[7] * (double)A.xw[3 * e + 1] + S.Rcw[8] * (double)A.xw[3 * e + 2] + S.tcw[2]) > 0.0;
+        bad = (chi2 > chi2Mono[round] && !bClose) || (bClose && chi2 > chi2close) || !depthPos;
+      } else {
+        bad = chi2 > chi2Stereo[round];
+      }
+      outlier[e] = bad ? 1 : 0;
+      cnt[0] += bad ? 1.0 : 0.0;
+      cnt[1] += bad ? 0.0 : 1.0;
+    }
+    block_sum<2>(cnt, S.red);
+    nBad = (int)cnt[0];
+    nInliers = (int)cnt[1];
+    if (round == 2) robust = false;
+    if (E + 3 < 10) break;
+  }
+  __syncthreads();
+  if (nInliers < 30 && !A.recInit) {               // recovery (:7990-8020)
+    double cnt[1] = {0};
+    for (int e = tid; e < E; e += 256) {
+      const bool st = A.obs[3 * e + 2] >= 0;
+      double r[3], Xc[3];
+      pio_edge_error(A, S, e, st, r, Xc);
+      err[3 * e] = r[0]; err[3 * e + 1] = r[1]; err[3 * e + 2] = r[2];
+      const double om = (double)isg[e];
+      const double c2 = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
+      if (c2 < (double)(st ? 24.f : 18.f)) outlier[e] = 0; else cnt[0] += 1.0;
+    }
+    block_sum<1>(cnt, S.red);
+    nBad = (int)cnt[0];
+  }
+  __syncthreads();
+  // ---- outputs: state, prior Hessian ----
+  if (tid < 9) A.outState[tid] = S.Rwb[tid];
+  if (tid < 3) { A.outState[9 + tid] = S.twb[tid]; A.outState[12 + tid] = S.v[tid]; A.outState[15 + tid] = S.bg[tid]; A.outState[18 + tid] = S.ba[tid]; }
+  if (tid == 0) *A.nRet = E - nBad;
+  double a36[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) a36[k] = 0;
+  for (int e = tid; e < E; e += 256) {
+    if (outlier[e]) continue;
+    const bool st = A.obs[3 * e + 2] >= 0;
+    double r[3], Xc[3], J[18];
+    pio_edge_error(A, S, e, st, r, Xc);
+    pio_edge_jacobian(A, Xc, st, J);
+    const int D = st ? 3 : 2;
+    const double om = (double)isg[e];
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) {
+        double t = 0;
+        for (int d = 0; d < D; ++d) t += J[d * 6 + i] * om * J[d * 6 + j];
+        a36[i * 6 + j] += t;
+      }
+  }
+  block_partials<36>(a36, S.red);
+  if (tid < 36) {
+    double s = 0;
+    for (int w = 0; w < 8; ++w) s += S.red[w * 36 + tid];
+    S.tot[tid] = s;
+  }
+  if (tid == 32) pio_inertial(A, S, false);
+  __syncthreads();
+  if (tid < 225) S.H[tid] = 0;
+  __syncthreads();
+  if (tid >= 64 && tid < 64 + 81) {
+    const int r = (tid - 64) / 9, c = (tid - 64) - 9 * r;
+    double t = 0;
+    for (int k = 0; k < 9; ++k) t += A.infoI[r * 9 + k] * S.J[k * 9 + c];
+    S.OJ[r * 9 + c] = t;
+  }
+  __syncthreads();
+  if (tid < 81) {
+    const int i = tid / 9, j = tid - 9 * i;
+    double t = 0;
+    for (int k = 0; k < 9; ++k) t += S.J[k * 9 + i] * S.OJ[k * 9 + j];
+    S.H[i * 15 + j] += t;
+  } else if (tid >= 96 && tid < 105) {
+    const int i = (tid - 96) / 3, j = (tid - 96) - 3 * i;
+    S.H[(9 + i) * 15 + 9 + j] += A.infoG[i * 3 + j];
+    S.H[(12 + i) * 15 + 12 + j] += A.infoA[i * 3 + j];
+  }
+  __syncthreads();
+  if (tid < 36) { const int i = tid / 6, j = tid - 6 * i; S.H[i * 15 + j] += S.tot[tid]; }
+  __syncthreads();
+  if (tid < 225) A.H15[tid] = S.H[tid];
+}
+
+// =====================================================================================
 // host entry points
 // =====================================================================================
 extern "C" {
@@ -1837,6 +2223,59 @@ int orbx_local_ba(orbx_ctx* ctx, int n_kf, float* kf_Tcw, const uint8_t* kf_fixe
     ORBX_CUDA(cudaStreamSynchronize(st));
   }
   if (h_flag) cudaFreeHost(h_flag);
+  return ORBX_OK;
+}
+
+int orbx_pose_inertial_optimization_last_keyframe(orbx_ctx* ctx, int n_edges, const float* xw, const float* obs, const float* inv_sigma2,
+                                                  const uint8_t* close_pt, const orbx_camera* cam, const float* Tcw, const float* Tcb,
+                                                  const float* Tbc, double* state, const double* kf_state, const double* preint,
+                                                  const double* info_inertial, const double* info_gyro, const double* info_acc,
+                                                  int rec_init, uint8_t* outlier, double* H15, int32_t* n_ret, int32_t* iters) {
+  if (!ctx || n_edges < 0 || !cam || !Tcw || !Tcb || !Tbc || !state || !kf_state || !preint || !info_inertial || !info_gyro ||
+      !info_acc || !H15 || !n_ret || !iters)
+    return ORBX_EINVAL;
+  if (n_edges > 0 && (!xw || !obs || !inv_sigma2 || !close_pt || !outlier)) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevScope S(ctx, st);
+  PioArgs A;
+  A.E = n_edges;
+  A.xw = S.upload(xw, (size_t)3 * n_edges);
+  A.obs = S.upload(obs, (size_t)3 * n_edges);
+  A.invSigma2 = S.upload(inv_sigma2, n_edges);
+  A.closePt = S.upload(close_pt, n_edges);
+  A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) { A.Rcb[i * 3 + j] = Tcb[i * 4 + j]; A.Rbc[j * 3 + i] = Tcb[i * 4 + j]; A.Rcw0[i * 3 + j] = Tcw[i * 4 + j]; }
+    A.tcb[i] = Tcb[i * 4 + 3]; A.tbc[i] = Tbc[i * 4 + 3]; A.tcw0[i] = Tcw[i * 4 + 3];
+  }
+  memcpy(A.state, state, sizeof A.state);
+  memcpy(A.kf, kf_state, sizeof A.kf);
+  memcpy(A.dR, preint, sizeof(double) * 9); memcpy(A.dV, preint + 9, 24); memcpy(A.dP, preint + 12, 24);
+  A.dt = preint[15];
+  memcpy(A.infoI, info_inertial, sizeof A.infoI); memcpy(A.infoG, info_gyro, sizeof A.infoG); memcpy(A.infoA, info_acc, sizeof A.infoA);
+  A.recInit = rec_init;
+  A.outlier = S.alloc<uint8_t>(n_edges);
+  A.err = S.alloc<double>((size_t)3 * n_edges);
+  A.outState = S.alloc<double>(21);
+  A.H15 = S.alloc<double>(225);
+  int* d_res = S.alloc<int>(5);
+  A.nRet = d_res;
+  A.iters = d_res + 1;
+  PioArgs* dA = S.upload(&A, 1);
+  if (S.failed) return ORBX_ECUDA;
+  pose_inertial_kernel<<<1, 256, 0, st>>>(dA);
+  ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
+  int32_t res[5] = {0, 0, 0, 0, 0};
+  S.download(state, (const double*)A.outState, (size_t)21);
+  S.download(H15, (const double*)A.H15, (size_t)225);
+  S.download(res, (const int32_t*)d_res, (size_t)5);
+  if (n_edges > 0) S.download(outlier, (const uint8_t*)A.outlier, (size_t)n_edges);
+  int rc = S.finish();
+  if (rc != ORBX_OK) return rc;
+  *n_ret = res[0];
+  for (int i = 0; i < 4; ++i) iters[i] = res[1 + i];
   return ORBX_OK;
 }
 

@@ -377,6 +377,30 @@ int orbx_local_ba(orbx_ctx *ctx, int n_kf, float *kf_Tcw, const uint8_t *kf_fixe
                   double lambda_init, const volatile uint8_t *stop_flag, uint8_t *edge_bad,
                   int32_t *iters, int32_t *status);
 
+/* Optimizer::PoseInertialOptimizationLastKeyFrame(Frame*, bool bRecInit) (src/Optimizer.cc:7665-8066;
+ * vertices/edges: include/G2oTypes.h:387-491, src/G2oTypes.cc:170-220,385-407,496-520,730-812) — the
+ * visual-inertial replacement of PoseOptimization that Tracking::TrackLocalMap calls when the map was
+ * updated (src/Tracking.cc:2974-2990).  15 free unknowns (pose, velocity, gyro bias, acc bias of the
+ * frame), the last keyframe's four vertices fixed, Gauss-Newton + dense LDL^T, 4 x 10 iterations.
+ *   xw/obs/inv_sigma2 : as orbx_pose_optimization (inv_sigma2 already divided by uncertainty2)
+ *   close_pt[e]       : pMP->mTrackDepth < 10.f
+ *   Tcw/Tcb/Tbc[16]   : pFrame->mTcw, mImuCalib.Tcb, mImuCalib.Tbc (row-major float32)
+ *   state[21]         : in/out, double: Rwb[9], twb[3], velocity[3], gyro bias[3], acc bias[3] of the frame
+ *   kf_state[21]      : the same of pFrame->mpLastKeyFrame (fixed)
+ *   preint[16]        : mpImuPreintegrated->GetDeltaRotation/Velocity/Position(keyframe bias), dT
+ *   info_inertial[81] : EdgeInertial's information (ctor, src/G2oTypes.cc:700-727);
+ *   info_gyro/acc[9]  : C.block<3,3>(9,9).inverse(), C.block<3,3>(12,12).inverse()
+ *   rec_init          : bRecInit
+ * Out: outlier[e] (pFrame->mvbOutlier), H15[225] row-major (the Hessian handed to ConstraintPoseImu,
+ *      :8030-8063), *n_ret = nInitialCorrespondences - nBad, iters[4] = Gauss-Newton iterations per round.
+ * Conventions where the reference cannot be reproduced bit for bit (re-orthonormalisation): DESIGN.md §7. */
+int orbx_pose_inertial_optimization_last_keyframe(
+    orbx_ctx *ctx, int n_edges, const float *xw, const float *obs, const float *inv_sigma2,
+    const uint8_t *close_pt, const orbx_camera *cam, const float *Tcw, const float *Tcb,
+    const float *Tbc, double *state, const double *kf_state, const double *preint,
+    const double *info_inertial, const double *info_gyro, const double *info_acc, int rec_init,
+    uint8_t *outlier, double *H15, int32_t *n_ret, int32_t *iters);
+
 /* ====================================================================================
  * Many-stream tracking replay: S independent stereo streams
  * advance one frame per call, everything device-resident between stages:

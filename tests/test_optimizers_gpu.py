@@ -126,3 +126,54 @@ def test_lba_is_deterministic(ctx):
     r1 = opt.LocalBundleAdjustment(*a)
     r2 = opt.LocalBundleAdjustment(*a)
     assert np.array_equal(r1[0], r2[0]) and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
+
+
+def _inertial_call(opt, s, cam, rec_init=False):
+    return opt.PoseInertialOptimizationLastKeyFrame(s["xw"], s["obs"], s["isg"], s["close"], cam, s["Tcw"], s["Tcb"], s["Tbc"],
+                                                    s["state"], s["kf"], s["preint"], s["infoI"], s["infoG"], s["infoA"],
+                                                    rec_init=rec_init)
+
+
+@pytest.mark.parametrize("E,stereo_frac", [(300, 0.6), (150, 0.0), (500, 1.0), (60, 0.5), (1000, 0.7)])
+def test_pose_inertial_optimization_matches_oracle(ctx, ork, E, stereo_frac):
+    """same expressions, same summation trees, same LDL^T pivoting on both sides -> the 21-value state and
+    the 15x15 prior Hessian agree to fp64 rounding (1e-9 relative), the classification exactly."""
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    for seed in range(6):
+        s = sc.inertial_scenario(1000 * E + seed, E, stereo_frac)
+        r = ork.pose_inertial_optimization_last_keyframe(s, cam)
+        g = _inertial_call(opt, s, cam)
+        assert np.array_equal(g["iters"], r["iters"])
+        assert np.array_equal(g["outlier"], r["outlier"]) and g["n"] == r["n"]
+        assert np.abs(g["state"] - r["state"]).max() < 1e-9, (seed, np.abs(g["state"] - r["state"]).max())
+        assert np.abs(g["H"] - r["H"]).max() <= 1e-9 * np.abs(r["H"]).max()
+        # north_star tolerance w.r.t. the oracle, and the job done w.r.t. the truth
+        assert np.linalg.norm(g["state"][:9] - r["state"][:9]) / np.sqrt(2) < ROT_TOL_RAD
+        assert np.abs(g["state"][9:12] - s["truth"][9:12]).max() < 1e-2
+
+
+def test_pose_inertial_optimization_edge_cases(ctx, ork):
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    # fewer than 30 inliers: the recovery branch and bRecInit (src/Optimizer.cc:7990-8020)
+    s = sc.inertial_scenario(7, 24, 0.5, outlier_frac=0.3)
+    for rec in (False, True):
+        r = ork.pose_inertial_optimization_last_keyframe(s, cam, rec_init=rec)
+        g = _inertial_call(opt, s, cam, rec_init=rec)
+        assert np.array_equal(g["outlier"], r["outlier"]) and g["n"] == r["n"] and np.array_equal(g["iters"], r["iters"])
+        assert np.abs(g["state"] - r["state"]).max() < 1e-9
+    # fewer than 10 graph edges: one round only (:7893)
+    s = sc.inertial_scenario(8, 5, 0.5, outlier_frac=0.0)
+    r = ork.pose_inertial_optimization_last_keyframe(s, cam)
+    g = _inertial_call(opt, s, cam)
+    assert list(g["iters"]) == list(r["iters"]) == [10, 0, 0, 0]
+    assert np.abs(g["state"] - r["state"]).max() < 1e-9 and np.array_equal(g["outlier"], r["outlier"])
+    # no visual edges at all: the inertial and random-walk edges alone
+    s = sc.inertial_scenario(9, 0, 0.5)
+    r = ork.pose_inertial_optimization_last_keyframe(s, cam)
+    g = _inertial_call(opt, s, cam)
+    assert np.abs(g["state"] - r["state"]).max() < 1e-9 and g["n"] == r["n"] == 0
+    assert np.abs(g["H"] - r["H"]).max() <= 1e-9 * np.abs(r["H"]).max()
