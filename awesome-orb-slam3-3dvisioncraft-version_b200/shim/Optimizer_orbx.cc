@@ -1,11 +1,13 @@
-// Optimizer_orbx.cc — drop-in replacements for Optimizer::PoseOptimization (src/Optimizer.cc:907-1272) and
-// Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1811-2523); the rest of the class stays in the reference.
+// Optimizer_orbx.cc — drop-in replacements for Optimizer::PoseOptimization (src/Optimizer.cc:907-1272),
+// Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1811-2523) and Optimizer::PoseInertialOptimizationLastKeyFrame
+// (src/Optimizer.cc:7665-8066); the rest of the class stays in the reference.
 // Graph *collection* and *write-back* walk the reference's pointer graph exactly as the reference does (same
 // locks, same bookkeeping fields); only the numeric core — g2o graph, LM, Schur, chi2 tests — is delegated.
 #include "orbx_shim_config.h"
 #include <list>
 #include <map>
 #include <set>
+#include <stdexcept>
 
 namespace ORB_SLAM3 {
 
@@ -57,6 +59,99 @@ int Optimizer::PoseOptimization(Frame* pFrame) {
   for (int e = 0; e < E; ++e) pFrame->mvbOutlier[index[e]] = outlier[e] != 0;
   pFrame->SetPose(array_to_pose(T));
   return nInliers;
+}
+
+// Visual-inertial pose refinement against the last keyframe (pinhole rigs, Nleft == -1).  Everything that the reference's
+// vertex / edge constructors derive from the Frame, the KeyFrame and the pre-integration (ImuCamPose, the delta
+// measurements at the keyframe's bias, the eigenvalue-clamped information matrices) is obtained from those very
+// constructors; the Gauss-Newton rounds, the chi2 classification and the 15x15 Hessian are delegated.
+int Optimizer::PoseInertialOptimizationLastKeyFrame(Frame* pFrame, bool bRecInit) {
+  const int N = pFrame->N;
+  if (pFrame->Nleft != -1) throw std::runtime_error("orbx: PoseInertialOptimizationLastKeyFrame covers pinhole rigs (Nleft == -1)");
+  std::vector<float> xw, obs, isg;
+  std::vector<uint8_t> closePt;
+  std::vector<int> index;
+  {
+    std::unique_lock<std::mutex> lock(MapPoint::mGlobalMutex);   // src/Optimizer.cc:7720
+    for (int i = 0; i < N; i++) {
+      MapPoint* pMP = pFrame->mvpMapPoints[i];
+      if (!pMP) continue;
+      pFrame->mvbOutlier[i] = false;
+      const cv::KeyPoint& kpUn = pFrame->mvKeysUn[i];
+      Eigen::Vector2d o2;
+      o2(0) = kpUn.pt.x;
+      o2(1) = kpUn.pt.y;
+      const float unc2 = pFrame->mpCamera->uncertainty2(o2);    // 1 for Pinhole (:7749, :7781)
+      const cv::Mat Xw = pMP->GetWorldPos();
+      for (int k = 0; k < 3; ++k) xw.push_back(Xw.at<float>(k));
+      obs.push_back(kpUn.pt.x);
+      obs.push_back(kpUn.pt.y);
+      obs.push_back(pFrame->mvuRight[i]);                        // < 0: EdgeMonoOnlyPose, else EdgeStereoOnlyPose
+      isg.push_back(pFrame->mvInvLevelSigma2[kpUn.octave] / unc2);
+      closePt.push_back(pMP->mTrackDepth < 10.f ? 1 : 0);        // :7912
+      index.push_back(i);
+    }
+  }
+  const int E = (int)index.size();
+  KeyFrame* pKF = pFrame->mpLastKeyFrame;
+  const VertexPose VP(pFrame), VPk(pKF);                          // ImuCamPose(Frame*) / ImuCamPose(KeyFrame*)
+  const ImuCamPose& P = VP.estimate();
+  const ImuCamPose& Pk = VPk.estimate();
+  double state[21], kf[21], preint[16], infoI[81], infoG[9], infoA[9];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) { state[r * 3 + c] = P.Rwb(r, c); kf[r * 3 + c] = Pk.Rwb(r, c); }
+    state[9 + r] = P.twb(r);
+    kf[9 + r] = Pk.twb(r);
+    state[12 + r] = pFrame->mVw.at<float>(r);                    // VertexVelocity(Frame*) (src/G2oTypes.cc:668-672)
+    kf[12 + r] = pKF->GetVelocity().at<float>(r);
+  }
+  const IMU::Bias bF = pFrame->mImuBias, bK = pKF->GetImuBias();
+  const float gF[3] = {bF.bwx, bF.bwy, bF.bwz}, aF[3] = {bF.bax, bF.bay, bF.baz};
+  const float gK[3] = {bK.bwx, bK.bwy, bK.bwz}, aK[3] = {bK.bax, bK.bay, bK.baz};
+  for (int r = 0; r < 3; ++r) { state[15 + r] = gF[r]; state[18 + r] = aF[r]; kf[15 + r] = gK[r]; kf[18 + r] = aK[r]; }
+  IMU::Preintegrated* pInt = pFrame->mpImuPreintegrated;
+  const cv::Mat dR = pInt->GetDeltaRotation(bK), dV = pInt->GetDeltaVelocity(bK), dP = pInt->GetDeltaPosition(bK);   // :739-741
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) preint[r * 3 + c] = dR.at<float>(r, c);
+    preint[9 + r] = dV.at<float>(r);
+    preint[12 + r] = dP.at<float>(r);
+  }
+  preint[15] = pInt->dT;
+  const EdgeInertial ei(pInt);                                    // inverse + eigenvalue clamp (src/G2oTypes.cc:706-727)
+  for (int r = 0; r < 9; ++r)
+    for (int c = 0; c < 9; ++c) infoI[r * 9 + c] = ei.information()(r, c);
+  const cv::Mat cvInfoG = pInt->C.rowRange(9, 12).colRange(9, 12).inv(cv::DECOMP_SVD);       // :7861
+  const cv::Mat cvInfoA = pInt->C.rowRange(12, 15).colRange(12, 15).inv(cv::DECOMP_SVD);     // :7872
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) { infoG[r * 3 + c] = cvInfoG.at<float>(r, c); infoA[r * 3 + c] = cvInfoA.at<float>(r, c); }
+  float Tcw[16], Tcb[16], Tbc[16];
+  pose_to_array(pFrame->mTcw, Tcw);
+  pose_to_array(pFrame->mImuCalib.Tcb, Tcb);
+  pose_to_array(pFrame->mImuCalib.Tbc, Tbc);
+  orbx_camera cam{pFrame->fx, pFrame->fy, pFrame->cx, pFrame->cy, pFrame->mbf, pFrame->mb};
+  std::vector<uint8_t> outlier(E > 0 ? E : 1, 0);
+  double H15[225];
+  int32_t nRet = 0, iters[4];
+  orbx_shim::check("orbx_pose_inertial_optimization_last_keyframe",
+                   orbx_pose_inertial_optimization_last_keyframe(orbx_shim::context(), E, xw.data(), obs.data(), isg.data(),
+                                                                 closePt.data(), &cam, Tcw, Tcb, Tbc, state, kf, preint, infoI,
+                                                                 infoG, infoA, bRecInit ? 1 : 0, outlier.data(), H15, &nRet,
+                                                                 iters));
+  for (int e = 0; e < E; ++e) pFrame->mvbOutlier[index[e]] = outlier[e] != 0;
+  // recover pose, velocity, biases and the prior for the next frame (:8022-8063)
+  Eigen::Matrix3d Rwb;
+  Eigen::Vector3d twb, vwb, bg, ba;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) Rwb(r, c) = state[r * 3 + c];
+    twb(r) = state[9 + r]; vwb(r) = state[12 + r]; bg(r) = state[15 + r]; ba(r) = state[18 + r];
+  }
+  pFrame->SetImuPoseVelocity(Converter::toCvMat(Rwb), Converter::toCvMat(twb), Converter::toCvMat(vwb));
+  pFrame->mImuBias = IMU::Bias(state[18], state[19], state[20], state[15], state[16], state[17]);
+  Matrix15d H;
+  for (int r = 0; r < 15; ++r)
+    for (int c = 0; c < 15; ++c) H(r, c) = H15[r * 15 + c];
+  pFrame->mpcpi = new ConstraintPoseImu(Rwb, twb, vwb, bg, ba, H);
+  return nRet;
 }
 
 void Optimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, int& num_fixedKF) {

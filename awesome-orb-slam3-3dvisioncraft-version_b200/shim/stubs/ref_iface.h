@@ -32,6 +32,7 @@ struct Mat {
   Mat() {}
   Mat(int r, int c, int type);
   Mat operator()(const Rect&) const;
+  Mat rowRange(int, int) const; Mat colRange(int, int) const; Mat inv(int method = 0) const;
   int type() const;
   bool empty() const;
   template <typename T> T& at(int r, int c = 0);
@@ -42,6 +43,7 @@ struct Mat {
 struct InputArray { bool empty() const; Mat getMat() const; };
 struct OutputArray { void release() const; void create(int, int, int) const; Mat getMat() const; };
 enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
+enum { DECOMP_SVD = 1 };
 void copyMakeBorder(const Mat&, Mat&, int, int, int, int, int);
 }  // namespace cv
 
@@ -50,8 +52,39 @@ typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;
 typedef std::map<unsigned int, double> BowVector;
 }
 
+namespace Eigen {
+template <typename T, int R, int C> struct Matrix {
+  T& operator()(int r, int c); const T& operator()(int r, int c) const;
+  T& operator()(int i); const T& operator()(int i) const;
+};
+typedef Matrix<double, 3, 3> Matrix3d; typedef Matrix<double, 3, 1> Vector3d; typedef Matrix<double, 2, 1> Vector2d;
+}
+
 namespace ORB_SLAM3 {
-class Map; class KeyFrame; class Frame; class GeometricCamera;
+class Map; class KeyFrame; class Frame;
+typedef Eigen::Matrix<double, 9, 9> Matrix9d; typedef Eigen::Matrix<double, 15, 15> Matrix15d;
+class GeometricCamera { public: float uncertainty2(const Eigen::Vector2d& p2D); };
+namespace IMU {                                          // include/ImuTypes.h
+struct Bias { Bias() {} Bias(float ax, float ay, float az, float wx, float wy, float wz); float bax, bay, baz, bwx, bwy, bwz; };
+struct Calib { cv::Mat Tcb, Tbc; };
+class Preintegrated {
+ public:
+  cv::Mat GetDeltaRotation(const Bias& b); cv::Mat GetDeltaVelocity(const Bias& b); cv::Mat GetDeltaPosition(const Bias& b);
+  float dT; cv::Mat C;
+};
+}  // namespace IMU
+class ImuCamPose {                                       // include/G2oTypes.h:58-103
+ public:
+  Eigen::Vector3d twb; Eigen::Matrix3d Rwb;          // (per-camera Rcw/tcw/Rcb/tcb/Rbc/tbc vectors are not read by the shim)
+};
+class VertexPose { public: VertexPose(Frame*); VertexPose(KeyFrame*); const ImuCamPose& estimate() const; };   // :106-137
+class EdgeInertial { public: EdgeInertial(IMU::Preintegrated*); const Matrix9d& information() const; };         // :497-545
+class ConstraintPoseImu {                                // :704-749
+ public:
+  ConstraintPoseImu(const Eigen::Matrix3d& Rwb, const Eigen::Vector3d& twb, const Eigen::Vector3d& vwb, const Eigen::Vector3d& bg,
+                    const Eigen::Vector3d& ba, const Matrix15d& H);
+};
+namespace Converter { cv::Mat toCvMat(const Eigen::Matrix3d&); cv::Mat toCvMat(const Eigen::Vector3d&); }
 class ORBVocabulary;   // DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> in the reference (include/ORBVocabulary.h:36)
 
 class ORBextractor {
@@ -83,6 +116,9 @@ class Frame {
  public:
   void SetPose(cv::Mat Tcw); void ComputeStereoMatches(); void ComputeBoW(); void UndistortKeyPoints();
   int isInFrustumBatch(const std::vector<MapPoint*>& vpMP, float viewingCosLimit);   // added member
+  void SetImuPoseVelocity(const cv::Mat& Rwb, const cv::Mat& twb, const cv::Mat& Vwb);
+  KeyFrame* mpLastKeyFrame; IMU::Preintegrated* mpImuPreintegrated; IMU::Calib mImuCalib; IMU::Bias mImuBias; cv::Mat mVw;
+  ConstraintPoseImu* mpcpi; GeometricCamera* mpCamera;
   cv::Mat mDistCoef, mRcw, mtcw, mOw; int mnScaleLevels; float mfLogScaleFactor;
   ORBVocabulary* mpORBvocabulary; DBoW2::BowVector mBowVec; DBoW2::FeatureVector mFeatVec; int Nleft;
   ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
@@ -100,6 +136,7 @@ class KeyFrame {
   MapPoint* GetMapPoint(const size_t& idx); void EraseMapPointMatch(MapPoint*); bool isBad(); Map* GetMap();
   cv::Mat GetCameraCenter(); void AddMapPoint(MapPoint*, const size_t& idx); void ComputeBoW();
   ORBVocabulary* mpORBvocabulary; DBoW2::BowVector mBowVec; float mfLogScaleFactor; int N, NLeft;
+  cv::Mat GetVelocity(); IMU::Bias GetImuBias();
   long unsigned int mnId, mnBALocalForKF, mnBAFixedForKF;
   const float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mb = 0;
   std::vector<cv::KeyPoint> mvKeysUn; std::vector<float> mvuRight; cv::Mat mDescriptors; DBoW2::FeatureVector mFeatVec;
@@ -126,5 +163,6 @@ class Optimizer {
  public:
   static void LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, int& num_fixedKF);
   static int PoseOptimization(Frame* pFrame);
+  static int PoseInertialOptimizationLastKeyFrame(Frame* pFrame, bool bRecInit = false);
 };
 }  // namespace ORB_SLAM3

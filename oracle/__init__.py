@@ -58,6 +58,7 @@ def lib():
         L.ork_is_in_frustum.argtypes = [C.c_void_p] * 4 + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 11
         L.ork_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ork_pose_inertial_opt_last_kf.argtypes = [C.c_int] + [C.c_void_p] * 14 + [C.c_int] + [C.c_void_p] * 4
+        L.ork_pose_inertial_opt_last_frame.argtypes = [C.c_int] + [C.c_void_p] * 18 + [C.c_int] + [C.c_void_p] * 4
         L.ork_inertial_debug.argtypes = [C.c_void_p] * 5
         L.ork_voc_from_memory.restype = C.c_void_p
         L.ork_voc_from_memory.argtypes = [C.c_void_p, C.c_size_t]
@@ -441,6 +442,51 @@ def pose_inertial_optimization_last_keyframe(s, cam, rec_init=False):
                                              _p(iters))
     assert rc == 0
     return dict(state=state, outlier=outlier[:E], H=H.reshape(15, 15), n=n.value, iters=iters)
+
+
+def pose_inertial_optimization_last_frame(s, cam, rec_init=False):
+    """oracle Optimizer::PoseInertialOptimizationLastFrame on tests/scenarios.inertial_lf_scenario.
+    -> dict(state[21], outlier[E], H[15,15] (previous frame marginalised out), n, iters[4])"""
+    E = len(s["isg"])
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)   # noqa: E731
+    f64 = lambda a: np.ascontiguousarray(a, np.float64)   # noqa: E731
+    xw, obs, isg, Tcw, Tcb, Tbc = map(f32, (s["xw"], s["obs"], s["isg"], s["Tcw"], s["Tcb"], s["Tbc"]))
+    close = np.ascontiguousarray(s["close"], np.uint8)
+    state = f64(np.array(s["state"]).copy())
+    prev, pre, pj, pb, iI, iG, iA, ps, pH = map(f64, (s["prev"], s["preint"], s["preint_jac"], s["preint_bias"], s["infoI"], s["infoG"],
+                                                       s["infoA"], s["prior_state"], s["prior_H"]))
+    outlier = np.zeros(max(E, 1), np.uint8)
+    H = np.zeros(225, np.float64)
+    n = C.c_int(0)
+    iters = np.zeros(4, np.int32)
+    rc = lib().ork_pose_inertial_opt_last_frame(E, _p(xw), _p(obs), _p(isg), _p(close), C.byref(cam), _p(Tcw), _p(Tcb), _p(Tbc),
+                                                _p(state), _p(prev), _p(pre), _p(pj), _p(pb), _p(iI), _p(iG), _p(iA), _p(ps), _p(pH),
+                                                int(rec_init), _p(outlier), _p(H), C.byref(n), _p(iters))
+    assert rc == 0
+    return dict(state=state, outlier=outlier[:E], H=H.reshape(15, 15), n=n.value, iters=iters)
+
+
+def inertial_lf_debug(state, prev, s):
+    f64 = lambda a: np.ascontiguousarray(a, np.float64)   # noqa: E731
+    state, prev, pre, pj, pb, ps = map(f64, (state, prev, s["preint"], s["preint_jac"], s["preint_bias"], s["prior_state"]))
+    e9, J, e15, Jp = np.zeros(9), np.zeros(216), np.zeros(15), np.zeros(225)
+    lib().ork_inertial_lf_debug(_p(state), _p(prev), _p(pre), _p(pj), _p(pb), _p(ps), _p(e9), _p(J), _p(e15), _p(Jp))
+    return e9, J.reshape(9, 24), e15, Jp.reshape(15, 15)
+
+
+def jacobi_eig(A):
+    A = np.ascontiguousarray(A, np.float64).copy()
+    n = len(A)
+    V = np.zeros((n, n))
+    lib().ork_jacobi_eig(n, _p(A), _p(V))
+    return np.diag(A).copy(), V, A
+
+
+def marginalize_prev(H30):
+    H30 = np.ascontiguousarray(H30, np.float64)
+    out = np.zeros((15, 15))
+    lib().ork_marginalize_prev(_p(H30), _p(out))
+    return out
 
 
 def inertial_debug(state, kf, preint):

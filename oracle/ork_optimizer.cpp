@@ -987,7 +987,7 @@ struct InertialProblem {
       if (active[e]) edge_error(e, &err[3 * e]);
   }
   // buildSystem over the free vertices (pose 0-5, velocity 6-8, gyro bias 9-11, acc bias 12-14)
-  void buildSystem() {
+  void visualSystem(double* out /*[27]: upper triangle of the 6x6 pose block, then -gradient*/) {
     TreeAcc<27> acc(256);
     for (int e = 0; e < E; ++e) {
       if (!active[e]) continue;
@@ -1011,8 +1011,11 @@ struct InertialProblem {
         }
       }
     }
-    double out[27];
     acc.finish(out);
+  }
+  void buildSystem() {
+    double out[27];
+    visualSystem(out);
     for (int i = 0; i < 225; ++i) H[i] = 0;
     for (int i = 0; i < 15; ++i) b[i] = 0;
     int idx = 0;
@@ -1171,6 +1174,400 @@ int ork_pose_inertial_opt_last_kf(int E, const float* xw, const float* obs, cons
   *nRet = E - nBad;
   return ORBX_OK;
 }
+
+}  // extern "C"
+
+// ================================================================================================
+// SURVEY.md §8 f3 (second function): Optimizer::PoseInertialOptimizationLastFrame (src/Optimizer.cc:8068-8603)
+//
+// Same visual edges on the frame's pose; the PREVIOUS FRAME's four vertices are free too (30 unknowns; g2o orders the
+// Hessian by vertex id: frame pose 0-5, velocity 6-8, gyro bias 9-11, acc bias 12-14, previous frame 15-29 likewise);
+// EdgeInertial over all six vertices with its full Jacobians (src/G2oTypes.cc:752-812) and bias-corrected deltas
+// (src/ImuTypes.cc:367-394), the two random-walk edges with both ends free, EdgePriorPoseImu on the previous frame
+// (src/G2oTypes.cc:941-981, Huber delta 5), chi2 thresholds {5.991 x4} / {15.6, 9.8, 7.815, 7.815}, and at the end the
+// 30x30 Hessian with the previous frame marginalised out (Optimizer::Marginalize, :5366-5450).
+//
+// PARITY CONVENTIONS in addition to the ones above:
+//  * the reference evaluates the bias-corrected deltas in float32 cv::Mat arithmetic on biases rounded to float32
+//    (IMU::Bias has float members) and re-normalises dR with a float32 SVD; here: double, quaternion orthonormalisation.
+//  * Marginalize takes the pseudo-inverse of the 15x15 previous-frame block from Eigen::JacobiSVD with the absolute
+//    threshold 1e-6; here the block is symmetrised and its eigen-decomposition comes from a cyclic Jacobi sweep
+//    (same threshold on |eigenvalue|), the same code on the device.
+// ================================================================================================
+namespace ork {
+
+static void right_jac_so3(const double* v, double* J) {   // RightJacobianSO3 (src/G2oTypes.cc:1060-1075)
+  const double x = v[0], y = v[1], z = v[2];
+  const double d2 = x * x + y * y + z * z, d = std::sqrt(d2);
+  const double W[9] = {0.0, -z, y, z, 0.0, -x, -y, x, 0.0};
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (d < 1e-5) { for (int i = 0; i < 9; ++i) J[i] = I[i]; return; }
+  double W2[9];
+  m3_mul(W, W, W2);
+  const double a = (1.0 - std::cos(d)) / d2, b = (d - std::sin(d)) / (d2 * d);
+  for (int i = 0; i < 9; ++i) J[i] = I[i] - W[i] * a + W2[i] * b;
+}
+static void skew3(const double* v, double* S) {
+  S[0] = 0; S[1] = -v[2]; S[2] = v[1]; S[3] = v[2]; S[4] = 0; S[5] = -v[0]; S[6] = -v[1]; S[7] = v[0]; S[8] = 0;
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major A, destroyed; V columns = eigenvectors).
+// Fixed sweep order (p < q ascending), fixed sweep count, no libm beyond sqrt: bit-reproducible on the device.
+static void jacobi_eig(int n, double* A, double* V, int sweeps = 12) {
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) V[i * n + j] = i == j ? 1.0 : 0.0;
+  for (int s = 0; s < sweeps; ++s)
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < n; ++k) {   // A <- A * G
+          const double akp = A[k * n + p], akq = A[k * n + q];
+          A[k * n + p] = c * akp - sn * akq;
+          A[k * n + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {   // A <- G^T * A
+          const double apk = A[p * n + k], aqk = A[q * n + k];
+          A[p * n + k] = c * apk - sn * aqk;
+          A[q * n + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = V[k * n + p], vkq = V[k * n + q];
+          V[k * n + p] = c * vkp - sn * vkq;
+          V[k * n + q] = sn * vkp + c * vkq;
+        }
+      }
+}
+
+// Optimizer::Marginalize(H, 0, 14) on the 30x30 Hessian (previous frame first): Hcc - Hcp * pinv(Hpp) * Hpc -> out[15][15]
+static void marginalize_prev(const double* Hf, double* H15) {
+  double A[225], Vv[225], inv[225];
+  for (int i = 0; i < 15; ++i)
+    for (int j = 0; j < 15; ++j) A[i * 15 + j] = 0.5 * (Hf[i * 30 + j] + Hf[j * 30 + i]);
+  jacobi_eig(15, A, Vv);
+  for (int i = 0; i < 15; ++i)
+    for (int j = 0; j < 15; ++j) {
+      double s = 0;
+      for (int k = 0; k < 15; ++k) {
+        const double ev = A[k * 15 + k];
+        const double iv = std::fabs(ev) > 1e-6 ? 1.0 / ev : 0.0;
+        s += Vv[i * 15 + k] * iv * Vv[j * 15 + k];
+      }
+      inv[i * 15 + j] = s;
+    }
+  for (int i = 0; i < 15; ++i)
+    for (int j = 0; j < 15; ++j) {
+      double s = 0;
+      for (int k = 0; k < 15; ++k) {
+        double t = 0;
+        for (int l = 0; l < 15; ++l) t += Hf[(15 + i) * 30 + l] * inv[l * 15 + k];
+        s += t * Hf[k * 30 + 15 + j];
+      }
+      H15[i * 15 + j] = Hf[(15 + i) * 30 + 15 + j] - s;
+    }
+}
+
+struct BodyState {
+  double Rwb[9], twb[3], v[3], bg[3], ba[3];
+  int its = 0;
+  void load(const double* s) { std::memcpy(Rwb, s, 72); std::memcpy(twb, s + 9, 24); std::memcpy(v, s + 12, 24); std::memcpy(bg, s + 15, 24); std::memcpy(ba, s + 18, 24); }
+  void store(double* s) const { std::memcpy(s, Rwb, 72); std::memcpy(s + 9, twb, 24); std::memcpy(s + 12, v, 24); std::memcpy(s + 15, bg, 24); std::memcpy(s + 18, ba, 24); }
+  void update(const double* x) {   // ImuCamPose::Update (pose) + plain additions
+    double d[3], E3[9], Rn[9];
+    m3_v(Rwb, x + 3, d);
+    for (int i = 0; i < 3; ++i) twb[i] += d[i];
+    exp_so3(x, E3);
+    m3_mul(Rwb, E3, Rn);
+    for (int i = 0; i < 9; ++i) Rwb[i] = Rn[i];
+    if (++its >= 3) { orthonormalize(Rwb); its = 0; }
+    for (int i = 0; i < 3; ++i) { v[i] += x[6 + i]; bg[i] += x[9 + i]; ba[i] += x[12 + i]; }
+  }
+};
+
+struct InertialProblemLF {
+  InertialProblem V;                 // the visual part (edges, camera, Rcw/tcw of the frame) — its Rwb/twb/... mirror `cur`
+  BodyState cur, prev;
+  double dR0[9], dV0[3], dP0[3], dt, JRg[9], JVg[9], JVa[9], JPg[9], JPa[9], bpre[6] /* gyro, acc */;
+  double infoI[81], infoG[9], infoA[9];
+  double pR[9], pt[3], pv[3], pbg[3], pba[3], Hp[225];   // ConstraintPoseImu of the previous frame
+  Huber hPrior{5.0f};
+  double H[900], b[30], x[30];
+
+  void sync_camera() {
+    std::memcpy(V.Rwb, cur.Rwb, 72); std::memcpy(V.twb, cur.twb, 24);
+    V.refresh_camera();
+  }
+  // EdgeInertial::computeError + linearizeOplus at the current estimates: e9, J[9][24] in the edge's own vertex order
+  // (pose1 0-5, velocity1 6-8, gyro1 9-11, acc1 12-14, pose2 15-20, velocity2 21-23)
+  void inertial(double* e9, double* J) const {
+    double dbg[3], dba[3], w[3], Ew[9], dRc[9], dV[3], dP[3];
+    for (int i = 0; i < 3; ++i) { dbg[i] = prev.bg[i] - bpre[i]; dba[i] = prev.ba[i] - bpre[3 + i]; }
+    m3_v(JRg, dbg, w);
+    exp_so3(w, Ew);
+    m3_mul(dR0, Ew, dRc);
+    orthonormalize(dRc);
+    double t1[3], t2[3];
+    m3_v(JVg, dbg, t1); m3_v(JVa, dba, t2);
+    for (int i = 0; i < 3; ++i) dV[i] = dV0[i] + t1[i] + t2[i];
+    m3_v(JPg, dbg, t1); m3_v(JPa, dba, t2);
+    for (int i = 0; i < 3; ++i) dP[i] = dP0[i] + t1[i] + t2[i];
+    const double g[3] = {0, 0, -9.81};
+    double Rbw1[9], dRt[9], T1[9], eR[9], er[3];
+    m3_t(prev.Rwb, Rbw1);
+    m3_t(dRc, dRt);
+    m3_mul(dRt, Rbw1, T1);
+    m3_mul(T1, cur.Rwb, eR);
+    log_so3(eR, er);
+    double a[3], cv[3], cp[3];
+    for (int i = 0; i < 3; ++i) a[i] = cur.v[i] - prev.v[i] - g[i] * dt;
+    m3_v(Rbw1, a, cv);
+    for (int i = 0; i < 3; ++i) a[i] = cur.twb[i] - prev.twb[i] - prev.v[i] * dt - g[i] * dt * dt / 2;
+    m3_v(Rbw1, a, cp);
+    for (int i = 0; i < 3; ++i) { e9[i] = er[i]; e9[3 + i] = cv[i] - dV[i]; e9[6 + i] = cp[i] - dP[i]; }
+    if (!J) return;
+    double invJr[9], Rbw2[9], M1[9], M2[9], Sv[9], Sp[9], eRt[9], RJ[9], RR[9];
+    inv_right_jac_so3(er, invJr);
+    m3_t(cur.Rwb, Rbw2);
+    m3_mul(invJr, Rbw2, M1);
+    m3_mul(M1, prev.Rwb, M2);                 // invJr * Rwb2^T * Rwb1
+    skew3(cv, Sv);
+    for (int i = 0; i < 3; ++i) a[i] = cur.twb[i] - prev.twb[i] - prev.v[i] * dt - 0.5 * g[i] * dt * dt;
+    double cp2[3];
+    m3_v(Rbw1, a, cp2);
+    skew3(cp2, Sp);
+    m3_t(eR, eRt);
+    right_jac_so3(w, RJ);
+    m3_mul(invJr, eRt, M1);
+    double M3[9], M4[9];
+    m3_mul(M1, RJ, M3);
+    m3_mul(M3, JRg, M4);                      // invJr * eR^T * Jr(JRg dbg) * JRg
+    m3_mul(Rbw1, cur.Rwb, RR);
+    for (int i = 0; i < 9 * 24; ++i) J[i] = 0;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        const int k = r * 3 + c;
+        J[r * 24 + c] = -M2[k];
+        J[(3 + r) * 24 + c] = Sv[k];
+        J[(6 + r) * 24 + c] = Sp[k];
+        J[(6 + r) * 24 + 3 + c] = r == c ? -1.0 : 0.0;
+        J[(3 + r) * 24 + 6 + c] = -Rbw1[k];
+        J[(6 + r) * 24 + 6 + c] = -Rbw1[k] * dt;
+        J[r * 24 + 9 + c] = -M4[k];
+        J[(3 + r) * 24 + 9 + c] = -JVg[k];
+        J[(6 + r) * 24 + 9 + c] = -JPg[k];
+        J[(3 + r) * 24 + 12 + c] = -JVa[k];
+        J[(6 + r) * 24 + 12 + c] = -JPa[k];
+        J[r * 24 + 15 + c] = invJr[k];
+        J[(6 + r) * 24 + 18 + c] = RR[k];
+        J[(3 + r) * 24 + 21 + c] = Rbw1[k];
+      }
+  }
+  // EdgePriorPoseImu::computeError + linearizeOplus: e15, J[15][15] (pose 0-5, velocity 6-8, gyro 9-11, acc 12-14)
+  void prior(double* e15, double* J) const {
+    double pRt[9], eR[9], er[3], d[3], et[3];
+    m3_t(pR, pRt);
+    m3_mul(pRt, prev.Rwb, eR);
+    log_so3(eR, er);
+    for (int i = 0; i < 3; ++i) d[i] = prev.twb[i] - pt[i];
+    m3_v(pRt, d, et);
+    for (int i = 0; i < 3; ++i) { e15[i] = er[i]; e15[3 + i] = et[i]; e15[6 + i] = prev.v[i] - pv[i]; e15[9 + i] = prev.bg[i] - pbg[i]; e15[12 + i] = prev.ba[i] - pba[i]; }
+    if (!J) return;
+    double invJr[9];
+    inv_right_jac_so3(er, invJr);
+    for (int i = 0; i < 225; ++i) J[i] = 0;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) { J[r * 15 + c] = invJr[r * 3 + c]; J[(3 + r) * 15 + 3 + c] = eR[r * 3 + c]; }
+    for (int i = 6; i < 15; ++i) J[i * 15 + i] = 1.0;
+  }
+  // J^T Omega J (and J^T Omega e) of an m-row edge with n local columns scattered through map[] into Hd (ld) / bd;
+  // per-element sums with k ascending, weight applied to Omega first (g2o's robustInformation)
+  static void add_edge(int m, int n, const double* J, const double* Om, const double* e, double w, const int* map, double* Hd, int ld,
+                       double* bd) {
+    std::vector<double> OJ((size_t)m * n), Oe(m);
+    for (int r = 0; r < m; ++r) {
+      if (e) { double s = 0; for (int k = 0; k < m; ++k) s += (w * Om[r * m + k]) * e[k]; Oe[r] = s; }
+      for (int c = 0; c < n; ++c) { double t = 0; for (int k = 0; k < m; ++k) t += (w * Om[r * m + k]) * J[k * n + c]; OJ[(size_t)r * n + c] = t; }
+    }
+    for (int i = 0; i < n; ++i) {
+      if (e) { double s = 0; for (int k = 0; k < m; ++k) s += J[k * n + i] * Oe[k]; bd[map[i]] -= s; }
+      for (int j = 0; j < n; ++j) { double t = 0; for (int k = 0; k < m; ++k) t += J[k * n + i] * OJ[(size_t)k * n + j]; Hd[map[i] * ld + map[j]] += t; }
+    }
+  }
+  void buildSystem() {
+    double out[27];
+    V.visualSystem(out);
+    for (int i = 0; i < 900; ++i) H[i] = 0;
+    for (int i = 0; i < 30; ++i) b[i] = 0;
+    int idx = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) { H[i * 30 + j] = out[idx]; H[j * 30 + i] = out[idx]; ++idx; }
+    for (int i = 0; i < 6; ++i) b[i] = out[21 + i];
+    static const int mapI[24] = {15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 0, 1, 2, 3, 4, 5, 6, 7, 8};
+    double e9[9], J[9 * 24];
+    inertial(e9, J);
+    add_edge(9, 24, J, infoI, e9, 1.0, mapI, H, 30, b);
+    for (int i = 0; i < 3; ++i) {                      // EdgeGyroRW / EdgeAccRW: e = bias(frame) - bias(previous), J = (-I, +I)
+      double sg = 0, sa = 0;
+      for (int k = 0; k < 3; ++k) { sg += infoG[i * 3 + k] * (cur.bg[k] - prev.bg[k]); sa += infoA[i * 3 + k] * (cur.ba[k] - prev.ba[k]); }
+      b[9 + i] -= sg;  b[24 + i] += sg;
+      b[12 + i] -= sa; b[27 + i] += sa;
+      for (int j = 0; j < 3; ++j) {
+        const double gI = infoG[i * 3 + j], aI = infoA[i * 3 + j];
+        H[(9 + i) * 30 + 9 + j] += gI;  H[(24 + i) * 30 + 24 + j] += gI;  H[(9 + i) * 30 + 24 + j] -= gI;  H[(24 + i) * 30 + 9 + j] -= gI;
+        H[(12 + i) * 30 + 12 + j] += aI; H[(27 + i) * 30 + 27 + j] += aI; H[(12 + i) * 30 + 27 + j] -= aI; H[(27 + i) * 30 + 12 + j] -= aI;
+      }
+    }
+    static const int mapP[15] = {15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29};
+    double e15[15], Jp[225];
+    prior(e15, Jp);
+    double chi = 0;
+    for (int r = 0; r < 15; ++r) { double s = 0; for (int k = 0; k < 15; ++k) s += Hp[r * 15 + k] * e15[k]; chi += e15[r] * s; }
+    double w = 1.0;
+    hPrior.robustify(chi, w);
+    add_edge(15, 15, Jp, Hp, e15, w, mapP, H, 30, b);
+  }
+};
+
+}  // namespace ork
+
+extern "C" {
+
+// Optimizer::PoseInertialOptimizationLastFrame.  state / prev_state: in/out resp. in, double[21] as above (the previous
+// frame's optimised state is not handed back by the reference either).  preint[16]: the RAW pre-integrated dR, dV, dP, dT of
+// pFrame->mpImuPreintegratedFrame; preint_jac[45]: JRg, JVg, JVa, JPg, JPa; preint_bias[6]: its bias (gyro xyz, acc xyz).
+// prior_state[21] + prior_H[225]: pFp->mpcpi.  Out: as above; H15 = the marginalised 15x15 prior of the frame.
+int ork_pose_inertial_opt_last_frame(int E, const float* xw, const float* obs, const float* invSigma2, const uint8_t* closePt,
+                                     const orbx_camera* cam, const float* Tcw, const float* Tcb, const float* Tbc, double* state,
+                                     const double* prevState, const double* preint, const double* preintJac, const double* preintBias,
+                                     const double* infoI, const double* infoG, const double* infoA, const double* priorState,
+                                     const double* priorH, int recInit, uint8_t* outlier, double* H15, int* nRet, int* iters) {
+  InertialProblemLF P;
+  InertialProblem& V = P.V;
+  for (int i = 0; i < 30; ++i) P.x[i] = 0;
+  V.E = E; V.xw = xw; V.obs = obs; V.invSigma2 = invSigma2; V.closePt = closePt; V.cam = *cam;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) { V.Rcb[i * 3 + j] = Tcb[i * 4 + j]; V.Rcw[i * 3 + j] = Tcw[i * 4 + j]; }
+    V.tcb[i] = Tcb[i * 4 + 3]; V.tbc[i] = Tbc[i * 4 + 3]; V.tcw[i] = Tcw[i * 4 + 3];
+  }
+  m3_t(V.Rcb, V.Rbc);
+  P.cur.load(state);
+  P.prev.load(prevState);
+  std::memcpy(V.Rwb, P.cur.Rwb, 72); std::memcpy(V.twb, P.cur.twb, 24);
+  std::memcpy(P.dR0, preint, 72); std::memcpy(P.dV0, preint + 9, 24); std::memcpy(P.dP0, preint + 12, 24);
+  P.dt = preint[15];
+  std::memcpy(P.JRg, preintJac, 72); std::memcpy(P.JVg, preintJac + 9, 72); std::memcpy(P.JVa, preintJac + 18, 72);
+  std::memcpy(P.JPg, preintJac + 27, 72); std::memcpy(P.JPa, preintJac + 36, 72);
+  std::memcpy(P.bpre, preintBias, 48);
+  std::memcpy(P.infoI, infoI, sizeof(double) * 81); std::memcpy(P.infoG, infoG, 72); std::memcpy(P.infoA, infoA, 72);
+  std::memcpy(P.pR, priorState, 72); std::memcpy(P.pt, priorState + 9, 24); std::memcpy(P.pv, priorState + 12, 24);
+  std::memcpy(P.pbg, priorState + 15, 24); std::memcpy(P.pba, priorState + 18, 24);
+  std::memcpy(P.Hp, priorH, sizeof(double) * 225);
+  V.active.assign(E, 1);
+  V.stereo.resize(E);
+  V.err.assign((size_t)3 * E, 0.0);
+  for (int e = 0; e < E; ++e) { V.stereo[e] = obs[3 * e + 2] >= 0; outlier[e] = 0; }
+  const float chi2Mono[4] = {5.991, 5.991, 5.991, 5.991}, chi2Stereo[4] = {15.6f, 9.8f, 7.815f, 7.815f};
+  int nBad = 0, nInliers = 0;
+  for (int it = 0; it < 4; ++it) {
+    iters[it] = 0;
+    bool ok = true;
+    for (int k = 0; k < 10 && ok; ++k) {
+      V.computeErrors();
+      P.buildSystem();
+      ok = ldlt_solve_pivoted(30, P.H, P.b, P.x);
+      P.cur.update(P.x);
+      P.prev.update(P.x + 15);
+      P.sync_camera();
+      ++iters[it];
+    }
+    nBad = 0; nInliers = 0;
+    const float chi2close = 1.5 * chi2Mono[it];
+    for (int e = 0; e < E; ++e) {
+      if (outlier[e]) V.edge_error(e, &V.err[3 * e]);
+      const float chi2 = (float)V.chi2(e);
+      bool bad;
+      if (!V.stereo[e]) {
+        const bool bClose = closePt[e] != 0;
+        bad = (chi2 > chi2Mono[it] && !bClose) || (bClose && chi2 > chi2close) || !V.depth_positive(e);
+      } else {
+        bad = chi2 > chi2Stereo[it];
+      }
+      outlier[e] = bad;
+      V.active[e] = !bad;
+      if (bad) ++nBad; else ++nInliers;
+    }
+    if (it == 2) V.robust = false;
+    if (E + 4 < 10) break;                   // visual edges + inertial + 2 random walks + prior
+  }
+  if (nInliers < 30 && !recInit) {
+    nBad = 0;
+    for (int e = 0; e < E; ++e) {
+      V.edge_error(e, &V.err[3 * e]);
+      if (V.chi2(e) < (V.stereo[e] ? 24.f : 18.f)) outlier[e] = 0; else ++nBad;
+    }
+  }
+  P.cur.store(state);
+  // 30x30 Hessian in the reference's order (previous frame 0-14, frame 15-29), previous frame marginalised out
+  static double Hf[900];
+  for (int i = 0; i < 900; ++i) Hf[i] = 0;
+  {
+    static const int mapI[24] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23};
+    double e9[9], J[9 * 24];
+    P.inertial(e9, J);
+    InertialProblemLF::add_edge(9, 24, J, P.infoI, nullptr, 1.0, mapI, Hf, 30, nullptr);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const double gI = P.infoG[i * 3 + j], aI = P.infoA[i * 3 + j];
+        Hf[(9 + i) * 30 + 9 + j] += gI;  Hf[(9 + i) * 30 + 24 + j] -= gI;  Hf[(24 + i) * 30 + 9 + j] -= gI;  Hf[(24 + i) * 30 + 24 + j] += gI;
+        Hf[(12 + i) * 30 + 12 + j] += aI; Hf[(12 + i) * 30 + 27 + j] -= aI; Hf[(27 + i) * 30 + 12 + j] -= aI; Hf[(27 + i) * 30 + 27 + j] += aI;
+      }
+    static const int mapP[15] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14};
+    double e15[15], Jp[225];
+    P.prior(e15, Jp);
+    InertialProblemLF::add_edge(15, 15, Jp, P.Hp, nullptr, 1.0, mapP, Hf, 30, nullptr);
+    TreeAcc<36> acc(256);
+    for (int e = 0; e < E; ++e) {
+      if (outlier[e]) continue;
+      double Je[18];
+      V.edge_jacobian(e, Je);
+      const int D = V.stereo[e] ? 3 : 2;
+      const double om = (double)invSigma2[e];
+      std::array<double, 36>& a = acc.slot(e);
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) { double t = 0; for (int d = 0; d < D; ++d) t += Je[d * 6 + i] * om * Je[d * 6 + j]; a[i * 6 + j] += t; }
+    }
+    double out[36];
+    acc.finish(out);
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) Hf[(15 + i) * 30 + 15 + j] += out[i * 6 + j];
+  }
+  marginalize_prev(Hf, H15);
+  *nRet = E - nBad;
+  return ORBX_OK;
+}
+
+// test hooks for the second function: EdgeInertial (all six vertices) and EdgePriorPoseImu residuals / Jacobians at given
+// states, the Jacobi eigen-solver and the marginalisation
+int ork_inertial_lf_debug(const double* state, const double* prevState, const double* preint, const double* preintJac,
+                          const double* preintBias, const double* priorState, double* e9, double* J216, double* e15, double* J225) {
+  InertialProblemLF P;
+  P.cur.load(state);
+  P.prev.load(prevState);
+  std::memcpy(P.dR0, preint, 72); std::memcpy(P.dV0, preint + 9, 24); std::memcpy(P.dP0, preint + 12, 24);
+  P.dt = preint[15];
+  std::memcpy(P.JRg, preintJac, 72); std::memcpy(P.JVg, preintJac + 9, 72); std::memcpy(P.JVa, preintJac + 18, 72);
+  std::memcpy(P.JPg, preintJac + 27, 72); std::memcpy(P.JPa, preintJac + 36, 72);
+  std::memcpy(P.bpre, preintBias, 48);
+  std::memcpy(P.pR, priorState, 72); std::memcpy(P.pt, priorState + 9, 24); std::memcpy(P.pv, priorState + 12, 24);
+  std::memcpy(P.pbg, priorState + 15, 24); std::memcpy(P.pba, priorState + 18, 24);
+  P.inertial(e9, J216);
+  P.prior(e15, J225);
+  return ORBX_OK;
+}
+int ork_jacobi_eig(int n, double* A, double* V) { jacobi_eig(n, A, V); return ORBX_OK; }
+int ork_marginalize_prev(const double* H30, double* H15) { marginalize_prev(H30, H15); return ORBX_OK; }
 
 // test hooks: the analytic Jacobians against the error functions (finite differences are taken by the test)
 int ork_inertial_debug(const double* state, const double* kfState, const double* preint, double* e9, double* J81) {

@@ -416,3 +416,37 @@ def inertial_scenario(seed, E=300, stereo_frac=0.6, outlier_frac=0.1, dt=0.25, n
     infoA = np.eye(3) * 1e4 + 0.0
     return dict(xw=xw, obs=obs, isg=isg, close=close, Tcw=Tcw.astype(np.float32), Tcb=Tcb.astype(np.float32), Tbc=Tbc.astype(np.float32),
                 state=state, truth=truth, kf=kf, preint=preint, infoI=infoI, infoG=infoG, infoA=infoA)
+
+
+def inertial_lf_scenario(seed, E=300, stereo_frac=0.6, outlier_frac=0.1, dt=0.05, noise_px=0.7):
+    """PoseInertialOptimizationLastFrame: inertial_scenario's frame pair read as (previous frame, frame), plus what the second
+    function needs — the RAW pre-integration (taken at a bias that differs slightly from the previous frame's, with bias
+    Jacobians, so the bias-corrected deltas explain the motion exactly at the truth) and the previous frame's
+    ConstraintPoseImu (mean = its current estimate, SPD information)."""
+    s = inertial_scenario(seed, E, stereo_frac, outlier_frac, dt, noise_px)
+    rng = np.random.default_rng(seed + 77777)
+    prev_truth = s["kf"].copy()
+    dRc, dVc, dPc = s["preint"][:9].reshape(3, 3), s["preint"][9:12], s["preint"][12:15]
+    dg, da = rng.normal(0, 3e-4, 3), rng.normal(0, 3e-3, 3)                 # previous-frame bias - pre-integration bias
+    bpre = np.concatenate([prev_truth[15:18] - dg, prev_truth[18:21] - da])
+    JRg = -dt * (np.eye(3) + rng.normal(0, 0.02, (3, 3)))
+    JVg = rng.normal(0, 0.02, (3, 3))
+    JVa = -dt * (np.eye(3) + rng.normal(0, 0.05, (3, 3)))
+    JPg = rng.normal(0, 0.002, (3, 3))
+    JPa = -0.5 * dt * dt * (np.eye(3) + rng.normal(0, 0.05, (3, 3)))
+    dR0 = dRc @ _exp_so3(JRg @ dg).T
+    dV0 = dVc - JVg @ dg - JVa @ da
+    dP0 = dPc - JPg @ dg - JPa @ da
+    # previous frame: estimate = prior mean = truth perturbed a little
+    R1 = prev_truth[:9].reshape(3, 3) @ _exp_so3(rng.normal(0, 0.002, 3))
+    prev = np.concatenate([R1.ravel(), prev_truth[9:12] + rng.normal(0, 0.005, 3), prev_truth[12:15] + rng.normal(0, 0.01, 3),
+                           prev_truth[15:18] + rng.normal(0, 5e-5, 3), prev_truth[18:21] + rng.normal(0, 5e-4, 3)])
+    sc_ = np.sqrt(np.array([3e5] * 3 + [2e5] * 3 + [5e3] * 3 + [1e8] * 3 + [1e5] * 3))
+    Q = rng.normal(0, 1, (15, 15))
+    Hp = (sc_[:, None] * (np.eye(15) + 0.02 * (Q @ Q.T) / 15) * sc_[None, :])
+    Hp = 0.5 * (Hp + Hp.T)
+    s.update(prev=prev, prev_truth=prev_truth, preint=np.concatenate([dR0.ravel(), dV0, dP0, [dt]]),
+             preint_jac=np.concatenate([JRg.ravel(), JVg.ravel(), JVa.ravel(), JPg.ravel(), JPa.ravel()]), preint_bias=bpre,
+             prior_state=prev.copy(), prior_H=Hp)
+    del s["kf"]
+    return s

@@ -69,3 +69,99 @@ def test_few_inliers_recovery_branch(ork):
     b = ork.pose_inertial_optimization_last_keyframe(s, cam, rec_init=True)
     assert np.array_equal(a["state"], b["state"])             # same optimisation, different bookkeeping
     assert a["outlier"].sum() <= b["outlier"].sum()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PoseInertialOptimizationLastFrame (src/Optimizer.cc:8068-8603)
+# ---------------------------------------------------------------------------------------------------------------------
+def _oplus(p, d):
+    """ImuCamPose::Update + plain additions on a 21-value body state; d = (rot, trans, vel, gyro bias, acc bias)."""
+    q = p.copy()
+    R = p[:9].reshape(3, 3)
+    q[9:12] = p[9:12] + R @ d[3:6]
+    q[:9] = (R @ sc._exp_so3(d[:3])).ravel()
+    q[12:21] = p[12:21] + d[6:15]
+    return q
+
+
+def test_last_frame_edge_jacobians_match_finite_differences(ork):
+    s = sc.inertial_lf_scenario(5)
+    cur, prev = np.array(s["state"]), np.array(s["prev"])
+    # move the previous frame away from the prior mean so that the prior residual and its Jacobian are not trivial
+    prev = _oplus(prev, np.concatenate([[0.02, -0.01, 0.015], [0.01, 0.02, -0.01], [0.03, 0.0, -0.02], [1e-3, -5e-4, 2e-4], [5e-3, 1e-3, -2e-3]]))
+    e0, J, p0, Jp = ork.inertial_lf_debug(cur, prev, s)
+    h = 1e-6
+    for k in range(15):                                    # previous frame: pose 0-5, velocity 6-8, gyro 9-11, acc 12-14
+        d = np.zeros(15); d[k] = h
+        e1, _, p1, _ = ork.inertial_lf_debug(cur, _oplus(prev, d), s)
+        assert np.allclose((e1 - e0) / h, J[:, k], atol=3e-4), (k, (e1 - e0) / h, J[:, k])
+        assert np.allclose((p1 - p0) / h, Jp[:, k], atol=3e-4), (k, (p1 - p0) / h, Jp[:, k])
+    for k in range(9):                                     # frame: pose 15-20, velocity 21-23
+        d = np.zeros(15); d[k] = h
+        e1, _, _, _ = ork.inertial_lf_debug(_oplus(cur, d), prev, s)
+        assert np.allclose((e1 - e0) / h, J[:, 15 + k], atol=3e-4), (k, (e1 - e0) / h, J[:, 15 + k])
+    # at the truth the bias-corrected deltas explain the motion exactly
+    et, _, _, _ = ork.inertial_lf_debug(s["truth"], s["prev_truth"], s)
+    assert np.abs(et).max() < 1e-9
+
+
+def test_jacobi_eigensolver_and_marginalisation_match_numpy(ork):
+    rng = np.random.default_rng(3)
+    for n, cond in [(15, 1e3), (15, 1e10), (9, 1e6)]:
+        Q, _ = np.linalg.qr(rng.normal(0, 1, (n, n)))
+        w = np.geomspace(1.0, cond, n)
+        A = (Q * w) @ Q.T
+        A = 0.5 * (A + A.T)
+        ev, V, D = ork.jacobi_eig(A)
+        assert np.allclose(np.sort(ev), np.linalg.eigvalsh(A), rtol=1e-10, atol=1e-14 * cond * n)   # absolute accuracy ~ eps * ||A||
+        assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12 and np.abs((V * ev) @ V.T - A).max() < 1e-10 * cond
+        assert np.abs(D - np.diag(np.diag(D))).max() < 1e-12 * cond       # converged: off-diagonal gone
+    # Schur complement with a rank-deficient previous-frame block (pseudo-inverse, threshold 1e-6)
+    B = rng.normal(0, 1, (30, 40))
+    H = B @ B.T
+    P = rng.normal(0, 1, (15, 12))
+    H[:15, :15] = P @ P.T                                                  # rank 12
+    H[:15, 15:] = (P @ rng.normal(0, 1, (12, 15)))
+    H[15:, :15] = H[:15, 15:].T
+    want = H[15:, 15:] - H[15:, :15] @ np.linalg.pinv(H[:15, :15], rcond=1e-12, hermitian=True) @ H[:15, 15:]
+    assert np.allclose(ork.marginalize_prev(H), want, rtol=0, atol=1e-8 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("seed,E,stereo_frac", [(1, 300, 0.6), (2, 150, 0.0), (3, 500, 1.0), (4, 60, 0.5)])
+def test_last_frame_recovers_ground_truth(ork, seed, E, stereo_frac):
+    s = sc.inertial_lf_scenario(seed, E, stereo_frac)
+    cam = abi.make_camera()
+    r = ork.pose_inertial_optimization_last_frame(s, cam)
+    t = s["truth"]
+    assert list(r["iters"]) == [10, 10, 10, 10]
+    assert rot_err_deg(r["state"][:9], t[:9]) < 0.1 < rot_err_deg(np.array(s["state"])[:9], t[:9])
+    assert np.abs(r["state"][9:12] - t[9:12]).max() < 5e-3
+    assert np.abs(r["state"][12:15] - t[12:15]).max() < 3e-2
+    gross = np.abs(s["obs"][:, 0] - _project(s, t)[:, 0]) > 10
+    assert np.all(r["outlier"][gross] == 1) and r["outlier"][~gross].mean() < 0.12
+    assert r["n"] == E - int(r["outlier"].sum())
+    H = r["H"]
+    assert np.abs(H - H.T).max() < 1e-9 * np.abs(H).max() and np.linalg.eigvalsh(0.5 * (H + H.T)).min() > 0
+    # marginalising the previous frame couples the frame's biases with its pose / velocity (unlike the keyframe variant)
+    assert np.abs(H[:9, 9:]).max() > 0
+
+
+def test_last_frame_prior_pulls_previous_state(ork):
+    """A very stiff prior on the previous frame must give (almost) the keyframe variant's answer: the previous frame then
+    acts as a fixed vertex.  Here the two functions are run on the same data with thresholds that differ only in the
+    first two rounds, so the final states agree to the pixel-noise level."""
+    s = sc.inertial_lf_scenario(11, 400, 0.7, outlier_frac=0.0)
+    s["prior_H"] = s["prior_H"] * 1e6
+    cam = abi.make_camera()
+    a = ork.pose_inertial_optimization_last_frame(s, cam)
+    k = dict(s)
+    k["kf"] = s["prev"]
+    # the keyframe variant takes deltas already evaluated at the keyframe's bias
+    dg, da = s["prev"][15:18] - s["preint_bias"][:3], s["prev"][18:21] - s["preint_bias"][3:]
+    J = s["preint_jac"].reshape(5, 3, 3)
+    dR = s["preint"][:9].reshape(3, 3) @ sc._exp_so3(J[0] @ dg)
+    k["preint"] = np.concatenate([dR.ravel(), s["preint"][9:12] + J[1] @ dg + J[2] @ da, s["preint"][12:15] + J[3] @ dg + J[4] @ da,
+                                  s["preint"][15:]])
+    b = ork.pose_inertial_optimization_last_keyframe(k, cam)
+    assert rot_err_deg(a["state"][:9], b["state"][:9]) < 0.02
+    assert np.abs(a["state"][9:15] - b["state"][9:15]).max() < 5e-3

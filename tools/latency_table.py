@@ -120,6 +120,12 @@ def main():
     a5 = (l["kf_T"], l["kf_fixed"], l["mp_xyz"], l["e_kf"], l["e_mp"], l["e_obs"], l["e_inv_sigma2"], cam)
     add("Optimizer::LocalBundleAdjustment 20 KF / %d MP / %d edges" % (len(l["mp_xyz"]), len(l["e_kf"])),
         "src/Optimizer.cc:1811", lambda: opt.LocalBundleAdjustment(*a5), lambda: oracle.local_ba(*a5), 10, 5)
+    for E in (300, 1000):
+        i = sc.inertial_scenario(E, E, 0.6)
+        a6 = (i["xw"], i["obs"], i["isg"], i["close"], cam, i["Tcw"], i["Tcb"], i["Tbc"], i["state"], i["kf"], i["preint"], i["infoI"],
+              i["infoG"], i["infoA"])
+        add("Optimizer::PoseInertialOptimizationLastKeyFrame, %d edges" % E, "src/Optimizer.cc:7665",
+            lambda: opt.PoseInertialOptimizationLastKeyFrame(*a6), lambda: oracle.pose_inertial_optimization_last_keyframe(i, cam))
     out = ["# Single-call latency through the C ABI vs the CPU oracle (%s)" % tag, "",
            "Host buffers in, host buffers out, median of repeated synchronous calls (p95 in brackets); CPU = the oracle on "
            "one thread of the same host (%d cores).  This is the call-level view of BASELINE.json configs 1-4; the "
