@@ -1691,7 +1691,8 @@ struct PioShared {
 };
 
 // residual of a visual edge at the shared camera pose
-__device__ __forceinline__ void pio_edge_error(const PioArgs& A, const PioShared& S, int e, bool st, double* out, double* Xc) {
+template <class AT, class ST>
+__device__ __forceinline__ void pio_edge_error(const AT& A, const ST& S, int e, bool st, double* out, double* Xc) {
   const double X[3] = {(double)A.xw[3 * e], (double)A.xw[3 * e + 1], (double)A.xw[3 * e + 2]};
   d_m3_v(S.Rcw, X, Xc);
   Xc[0] += S.tcw[0]; Xc[1] += S.tcw[1]; Xc[2] += S.tcw[2];
@@ -1701,7 +1702,8 @@ __device__ __forceinline__ void pio_edge_error(const PioArgs& A, const PioShared
   out[2] = 0;
   if (st) { const double invZ = 1 / Xc[2]; out[2] = (double)A.obs[3 * e + 2] - (u - (double)A.bf * invZ); }
 }
-__device__ __forceinline__ void pio_edge_jacobian(const PioArgs& A, const double* Xc, bool st, double* J) {
+template <class AT>
+__device__ __forceinline__ void pio_edge_jacobian(const AT& A, const double* Xc, bool st, double* J) {
   double Xb[3];
   d_m3_v(A.Rbc, Xc, Xb);
   Xb[0] += A.tbc[0]; Xb[1] += A.tbc[1]; Xb[2] += A.tbc[2];
@@ -1974,6 +1976,493 @@ __global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __res
   if (tid < 36) { const int i = tid / 6, j = tid - 6 * i; S.H[i * 15 + j] += S.tot[tid]; }
   __syncthreads();
   if (tid < 225) A.H15[tid] = S.H[tid];
+}
+
+// =====================================================================================
+// K21  PoseInertialOptimizationLastFrame (second function; src/Optimizer.cc:8068-8603, EdgeInertial with all
+//      six vertices free src/G2oTypes.cc:730-812, EdgePriorPoseImu :941-981, bias-corrected deltas src/ImuTypes.cc:367-394,
+//      Optimizer::Marginalize :5366-5450): one CTA per problem, 30 unknowns (g2o's vertex-id order: frame 0-14, previous
+//      frame 15-29).  Warps 0-7 own the visual edges (the canonical 256-way tree), warp 8 linearises the inertial edge and
+//      warp 9 the prior edge at the same time; the 30x30 system is assembled edge by edge in a fixed order, solved by one
+//      warp (pivoted LDL^T, lane i = row i) and applied to the two body states by two threads.  The final 30x30 Hessian is
+//      reduced to the frame's 15x15 prior with a warp-parallel cyclic Jacobi eigen-solver (pseudo-inverse, 1e-6 threshold).
+// =====================================================================================
+#define PLF_NT 320
+struct PlfArgs {
+  int E;
+  const float *xw, *obs, *invSigma2;
+  const uint8_t* closePt;
+  float fx, fy, cx, cy, bf;
+  double Rcb[9], tcb[3], Rbc[9], tbc[3], Rcw0[9], tcw0[3];
+  double state[21], prev[21];        // Rwb, twb, v, bg, ba
+  double dR0[9], dV0[3], dP0[3], dt, JRg[9], JVg[9], JVa[9], JPg[9], JPa[9], bpre[6];
+  double infoI[81], infoG[9], infoA[9];
+  double prior[21], Hp[225];
+  int recInit;
+  uint8_t* outlier;
+  double* err;
+  double* outState;
+  double* H15;
+  int* nRet;
+  int* iters;
+};
+struct PlfShared {
+  double cur[21], prev[21], Rcw[9], tcw[3];
+  double H[900], b[30], x[30], tot[36];
+  double e9[9], J[216], OJ[216], Oe[9];
+  double e15[15], Jp[225], OJp[225], Oep[15], wPrior;
+  double mA[225], mV[225], mInv[225], mT[225];
+  double red[(PLF_NT / 32) * 36];
+  int itsCur, itsPrev, ok;
+};
+
+__device__ void d_right_jac(const double* v, double* J) {
+  const double x = v[0], y = v[1], z = v[2];
+  const double d2 = x * x + y * y + z * z, d = sqrt(d2);
+  const double W[9] = {0.0, -z, y, z, 0.0, -x, -y, x, 0.0};
+  if (d < 1e-5) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) J[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  double W2[9];
+  d_m3_mul(W, W, W2);
+  const double a = (1.0 - cos(d)) / d2, b = (d - sin(d)) / (d2 * d);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) J[i] = ((i % 4 == 0) ? 1.0 : 0.0) - W[i] * a + W2[i] * b;
+}
+__device__ __forceinline__ void d_skew(const double* v, double* S) {
+  S[0] = 0; S[1] = -v[2]; S[2] = v[1]; S[3] = v[2]; S[4] = 0; S[5] = -v[0]; S[6] = -v[1]; S[7] = v[0]; S[8] = 0;
+}
+// body state (Rwb 0-8, twb 9-11, v 12-14, bg 15-17, ba 18-20) (+)= x[15]: ImuCamPose::Update + plain additions
+__device__ void d_body_update(double* B, int& its, const double* x) {
+  double d[3], E3[9], Rn[9];
+  d_m3_v(B, x + 3, d);
+  for (int i = 0; i < 3; ++i) B[9 + i] += d[i];
+  d_exp_so3(x, E3);
+  d_m3_mul(B, E3, Rn);
+  for (int i = 0; i < 9; ++i) B[i] = Rn[i];
+  if (++its >= 3) { d_orthonormalize(B); its = 0; }
+  for (int i = 0; i < 9; ++i) B[12 + i] += x[6 + i];
+}
+// EdgeInertial::computeError + linearizeOplus (one thread): S.e9, S.J[9][24] in the edge's vertex order
+__device__ void plf_inertial(const PlfArgs& A, PlfShared& S) {
+  const double* cur = S.cur;
+  const double* prev = S.prev;
+  double dbg[3], dba[3], w[3], Ew[9], dRc[9], dV[3], dP[3], t1[3], t2[3];
+  for (int i = 0; i < 3; ++i) { dbg[i] = prev[15 + i] - A.bpre[i]; dba[i] = prev[18 + i] - A.bpre[3 + i]; }
+  d_m3_v(A.JRg, dbg, w);
+  d_exp_so3(w, Ew);
+  d_m3_mul(A.dR0, Ew, dRc);
+  d_orthonormalize(dRc);
+  d_m3_v(A.JVg, dbg, t1); d_m3_v(A.JVa, dba, t2);
+  for (int i = 0; i < 3; ++i) dV[i] = A.dV0[i] + t1[i] + t2[i];
+  d_m3_v(A.JPg, dbg, t1); d_m3_v(A.JPa, dba, t2);
+  for (int i = 0; i < 3; ++i) dP[i] = A.dP0[i] + t1[i] + t2[i];
+  const double dt = A.dt;
+  double Rbw1[9], dRt[9], T1[9], eR[9], er[3], a[3], cv[3], cp[3];
+  d_m3_t(prev, Rbw1);
+  d_m3_t(dRc, dRt);
+  d_m3_mul(dRt, Rbw1, T1);
+  d_m3_mul(T1, cur, eR);
+  d_log_so3(eR, er);
+  for (int i = 0; i < 3; ++i) a[i] = cur[12 + i] - prev[12 + i] - (i == 2 ? -9.81 : 0.0) * dt;
+  d_m3_v(Rbw1, a, cv);
+  for (int i = 0; i < 3; ++i) a[i] = cur[9 + i] - prev[9 + i] - prev[12 + i] * dt - (i == 2 ? -9.81 : 0.0) * dt * dt / 2;
+  d_m3_v(Rbw1, a, cp);
+  for (int i = 0; i < 3; ++i) { S.e9[i] = er[i]; S.e9[3 + i] = cv[i] - dV[i]; S.e9[6 + i] = cp[i] - dP[i]; }
+  double invJr[9], Rbw2[9], M1[9], M2[9], Sv[9], Sp[9], eRt[9], RJ[9], RR[9], M3[9], M4[9], cp2[3];
+  d_inv_right_jac(er, invJr);
+  d_m3_t(cur, Rbw2);
+  d_m3_mul(invJr, Rbw2, M1);
+  d_m3_mul(M1, prev, M2);
+  d_skew(cv, Sv);
+  for (int i = 0; i < 3; ++i) a[i] = cur[9 + i] - prev[9 + i] - prev[12 + i] * dt - 0.5 * (i == 2 ? -9.81 : 0.0) * dt * dt;
+  d_m3_v(Rbw1, a, cp2);
+  d_skew(cp2, Sp);
+  d_m3_t(eR, eRt);
+  d_right_jac(w, RJ);
+  d_m3_mul(invJr, eRt, M1);
+  d_m3_mul(M1, RJ, M3);
+  d_m3_mul(M3, A.JRg, M4);
+  d_m3_mul(Rbw1, cur, RR);
+  double* J = S.J;
+  for (int i = 0; i < 216; ++i) J[i] = 0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      const int k = r * 3 + c;
+      J[r * 24 + c] = -M2[k];
+      J[(3 + r) * 24 + c] = Sv[k];
+      J[(6 + r) * 24 + c] = Sp[k];
+      J[(6 + r) * 24 + 3 + c] = r == c ? -1.0 : 0.0;
+      J[(3 + r) * 24 + 6 + c] = -Rbw1[k];
+      J[(6 + r) * 24 + 6 + c] = -Rbw1[k] * dt;
+      J[r * 24 + 9 + c] = -M4[k];
+      J[(3 + r) * 24 + 9 + c] = -A.JVg[k];
+      J[(6 + r) * 24 + 9 + c] = -A.JPg[k];
+      J[(3 + r) * 24 + 12 + c] = -A.JVa[k];
+      J[(6 + r) * 24 + 12 + c] = -A.JPa[k];
+      J[r * 24 + 15 + c] = invJr[k];
+      J[(6 + r) * 24 + 18 + c] = RR[k];
+      J[(3 + r) * 24 + 21 + c] = Rbw1[k];
+    }
+}
+// EdgePriorPoseImu::computeError + linearizeOplus + Huber weight (one thread): S.e15, S.Jp, S.wPrior
+__device__ void plf_prior(const PlfArgs& A, PlfShared& S, bool robust) {
+  const double* prev = S.prev;
+  double pRt[9], eR[9], er[3], d[3], et[3], invJr[9];
+  d_m3_t(A.prior, pRt);
+  d_m3_mul(pRt, prev, eR);
+  d_log_so3(eR, er);
+  for (int i = 0; i < 3; ++i) d[i] = prev[9 + i] - A.prior[9 + i];
+  d_m3_v(pRt, d, et);
+  for (int i = 0; i < 3; ++i) {
+    S.e15[i] = er[i]; S.e15[3 + i] = et[i]; S.e15[6 + i] = prev[12 + i] - A.prior[12 + i];
+    S.e15[9 + i] = prev[15 + i] - A.prior[15 + i]; S.e15[12 + i] = prev[18 + i] - A.prior[18 + i];
+  }
+  d_inv_right_jac(er, invJr);
+  for (int i = 0; i < 225; ++i) S.Jp[i] = 0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) { S.Jp[r * 15 + c] = invJr[r * 3 + c]; S.Jp[(3 + r) * 15 + 3 + c] = eR[r * 3 + c]; }
+  for (int i = 6; i < 15; ++i) S.Jp[i * 15 + i] = 1.0;
+  double w = 1.0;
+  if (robust) {
+    double chi = 0;
+    for (int r = 0; r < 15; ++r) {
+      double s = 0;
+      for (int k = 0; k < 15; ++k) s += A.Hp[r * 15 + k] * S.e15[k];
+      chi += S.e15[r] * s;
+    }
+    huber_rho(huber_make(5.0f), chi, w);
+  }
+  S.wPrior = w;
+}
+// Assembly of the inertial, random-walk and prior edges into S.H (ld 30) / S.b, edge by edge in a fixed order.  `fin`:
+// the reference's final ordering (previous frame first), no gradient, no robust weight.
+__device__ void plf_assemble(const PlfArgs& A, PlfShared& S, bool fin) {
+  const int tid = threadIdx.x;
+  const int oI = fin ? 0 : 15;    // inertial local column c -> (c < 15 ? oI + c : oC + c - 15)
+  const int oC = fin ? 15 : 0;
+  for (int t = tid; t < 216 + 9 + 225 + 15; t += PLF_NT) {
+    if (t < 216) {
+      const int r = t / 24, c = t - 24 * r;
+      double v = 0;
+      for (int k = 0; k < 9; ++k) v += (1.0 * A.infoI[r * 9 + k]) * S.J[k * 24 + c];
+      S.OJ[t] = v;
+    } else if (t < 225) {
+      const int r = t - 216;
+      double v = 0;
+      for (int k = 0; k < 9; ++k) v += (1.0 * A.infoI[r * 9 + k]) * S.e9[k];
+      S.Oe[r] = v;
+    } else if (t < 450) {
+      const int u = t - 225, r = u / 15, c = u - 15 * r;
+      const double w = S.wPrior;
+      double v = 0;
+      for (int k = 0; k < 15; ++k) v += (w * A.Hp[r * 15 + k]) * S.Jp[k * 15 + c];
+      S.OJp[u] = v;
+    } else {
+      const int r = t - 450;
+      const double w = S.wPrior;
+      double v = 0;
+      for (int k = 0; k < 15; ++k) v += (w * A.Hp[r * 15 + k]) * S.e15[k];
+      S.Oep[r] = v;
+    }
+  }
+  __syncthreads();
+  // EdgeInertial
+  for (int t = tid; t < 576 + 24; t += PLF_NT) {
+    if (t < 576) {
+      const int i = t / 24, j = t - 24 * i;
+      double v = 0;
+      for (int k = 0; k < 9; ++k) v += S.J[k * 24 + i] * S.OJ[k * 24 + j];
+      const int gi = i < 15 ? oI + i : oC + i - 15, gj = j < 15 ? oI + j : oC + j - 15;
+      S.H[gi * 30 + gj] += v;
+    } else if (!fin) {
+      const int i = t - 576;
+      double v = 0;
+      for (int k = 0; k < 9; ++k) v += S.J[k * 24 + i] * S.Oe[k];
+      S.b[i < 15 ? oI + i : oC + i - 15] -= v;
+    }
+  }
+  __syncthreads();
+  // EdgeGyroRW / EdgeAccRW: e = bias(frame) - bias(previous), Jacobians (-I, +I)
+  if (tid < 9) {
+    const int i = tid / 3, j = tid - 3 * i;
+    const double gI = A.infoG[tid], aI = A.infoA[tid];
+    const int c = oC, p = oI;
+    S.H[(c + 9 + i) * 30 + c + 9 + j] += gI;  S.H[(p + 9 + i) * 30 + p + 9 + j] += gI;
+    S.H[(c + 9 + i) * 30 + p + 9 + j] -= gI;  S.H[(p + 9 + i) * 30 + c + 9 + j] -= gI;
+    S.H[(c + 12 + i) * 30 + c + 12 + j] += aI; S.H[(p + 12 + i) * 30 + p + 12 + j] += aI;
+    S.H[(c + 12 + i) * 30 + p + 12 + j] -= aI; S.H[(p + 12 + i) * 30 + c + 12 + j] -= aI;
+  } else if (tid >= 32 && tid < 35 && !fin) {
+    const int i = tid - 32;
+    double sg = 0, sa = 0;
+    for (int k = 0; k < 3; ++k) {
+      sg += A.infoG[i * 3 + k] * (S.cur[15 + k] - S.prev[15 + k]);
+      sa += A.infoA[i * 3 + k] * (S.cur[18 + k] - S.prev[18 + k]);
+    }
+    S.b[9 + i] -= sg;  S.b[24 + i] += sg;
+    S.b[12 + i] -= sa; S.b[27 + i] += sa;
+  }
+  __syncthreads();
+  // EdgePriorPoseImu
+  for (int t = tid; t < 225 + 15; t += PLF_NT) {
+    if (t < 225) {
+      const int i = t / 15, j = t - 15 * i;
+      double v = 0;
+      for (int k = 0; k < 15; ++k) v += S.Jp[k * 15 + i] * S.OJp[k * 15 + j];
+      S.H[(oI + i) * 30 + oI + j] += v;
+    } else if (!fin) {
+      const int i = t - 225;
+      double v = 0;
+      for (int k = 0; k < 15; ++k) v += S.Jp[k * 15 + i] * S.Oep[k];
+      S.b[oI + i] -= v;
+    }
+  }
+  __syncthreads();
+}
+// warp 0: cyclic Jacobi on S.mA (15x15, symmetric) -> eigenvalues on the diagonal, eigenvectors in S.mV's columns
+__device__ void plf_jacobi15(PlfShared& S) {
+  const int k = threadIdx.x;   // lane
+  double* Am = S.mA;
+  double* V = S.mV;
+  if (k < 15) for (int j = 0; j < 15; ++j) V[k * 15 + j] = k == j ? 1.0 : 0.0;
+  __syncwarp();
+  for (int s = 0; s < 16; ++s) {
+    int nrot = 0;
+    for (int p = 0; p < 14; ++p)
+      for (int q = p + 1; q < 15; ++q) {
+        const double apq = Am[p * 15 + q], app = Am[p * 15 + p], aqq = Am[q * 15 + q];
+        if (fabs(apq) <= 1e-20 * (fabs(app) + fabs(aqq))) continue;   // (uniform across the warp)
+        ++nrot;
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        __syncwarp();
+        if (k < 15) {
+          const double akp = Am[k * 15 + p], akq = Am[k * 15 + q];
+          Am[k * 15 + p] = c * akp - sn * akq;
+          Am[k * 15 + q] = sn * akp + c * akq;
+        }
+        __syncwarp();
+        if (k < 15) {
+          const double apk = Am[p * 15 + k], aqk = Am[q * 15 + k];
+          Am[p * 15 + k] = c * apk - sn * aqk;
+          Am[q * 15 + k] = sn * apk + c * aqk;
+          const double vkp = V[k * 15 + p], vkq = V[k * 15 + q];
+          V[k * 15 + p] = c * vkp - sn * vkq;
+          V[k * 15 + q] = sn * vkp + c * vkq;
+        }
+        __syncwarp();
+      }
+    if (!nrot) break;
+  }
+}
+
+__global__ void __launch_bounds__(PLF_NT) pose_inertial_lf_kernel(const PlfArgs* __restrict__ args) {
+  const PlfArgs& A = args[blockIdx.x];
+  __shared__ PlfShared S;
+  const int tid = threadIdx.x, E = A.E;
+  const bool edgeThread = tid < 256;
+  const float* isg = A.invSigma2;
+  uint8_t* outlier = A.outlier;
+  double* err = A.err;
+  if (tid < 21) { S.cur[tid] = A.state[tid]; S.prev[tid] = A.prev[tid]; }
+  if (tid < 9) S.Rcw[tid] = A.Rcw0[tid];
+  if (tid < 3) S.tcw[tid] = A.tcw0[tid];
+  if (tid < 30) S.x[tid] = 0;
+  if (tid == 0) { S.itsCur = 0; S.itsPrev = 0; }
+  if (tid < 4) A.iters[tid] = 0;
+  for (int e = tid; e < E; e += PLF_NT) outlier[e] = 0;
+  __syncthreads();
+  const HuberD hMono = huber_make(sqrtf(5.991f)), hStereo = huber_make(sqrtf(7.815f));
+  const float chi2Mono[4] = {5.991f, 5.991f, 5.991f, 5.991f}, chi2Stereo[4] = {15.6f, 9.8f, 7.815f, 7.815f};
+  bool robust = true;
+  int nBad = 0, nInliers = 0;
+  for (int round = 0; round < 4; ++round) {
+    int cj = 0;
+    bool ok = true;
+    for (int it = 0; it < 10 && ok; ++it) {
+      double acc[27];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) acc[k] = 0;
+      if (tid == 256) plf_inertial(A, S);
+      if (tid == 288) plf_prior(A, S, true);
+      if (edgeThread)
+        for (int e = tid; e < E; e += 256) {
+          if (outlier[e]) continue;
+          const bool st = A.obs[3 * e + 2] >= 0;
+          double r[3], Xc[3], J[18];
+          pio_edge_error(A, S, e, st, r, Xc);
+          err[3 * e] = r[0]; err[3 * e + 1] = r[1]; err[3 * e + 2] = r[2];
+          pio_edge_jacobian(A, Xc, st, J);
+          const int D = st ? 3 : 2;
+          const double om = (double)isg[e];
+          double w = 1.0;
+          if (robust) huber_rho(st ? hStereo : hMono, r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0), w);
+          int idx = 0;
+          for (int i = 0; i < 6; ++i) {
+            double sg = 0;
+            for (int d = 0; d < D; ++d) sg += J[d * 6 + i] * om * r[d];
+            acc[21 + i] -= w * sg;
+            for (int j = i; j < 6; ++j) {
+              double a = 0;
+              for (int d = 0; d < D; ++d) a += J[d * 6 + i] * (w * om) * J[d * 6 + j];
+              acc[idx++] += a;
+            }
+          }
+        }
+      block_partials<27>(acc, S.red);
+      if (tid < 27) {
+        double s = 0;
+        for (int w = 0; w < 8; ++w) s += S.red[w * 27 + tid];
+        S.tot[tid] = s;
+      }
+      for (int t = tid; t < 900; t += PLF_NT) S.H[t] = 0;
+      if (tid >= 288 && tid < 318) S.b[tid - 288] = 0;
+      __syncthreads();
+      if (tid < 36) {
+        const int i = tid / 6, j = tid - 6 * i, lo = min(i, j), hi = max(i, j);
+        S.H[i * 30 + j] = S.tot[6 * lo - (lo * (lo - 1)) / 2 + (hi - lo)];
+      } else if (tid < 42) {
+        S.b[tid - 36] = S.tot[21 + tid - 36];
+      }
+      __syncthreads();
+      plf_assemble(A, S, false);
+      if (tid < 32) {
+        const bool okSolve = ldlt_solve_shfl<30>(S.H, S.b, S.x);
+        if (tid == 0) S.ok = okSolve ? 1 : 0;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        d_body_update(S.cur, S.itsCur, S.x);
+        double Rbw[9], tbw[3];
+        d_m3_t(S.cur, Rbw);
+        d_m3_v(Rbw, S.cur + 9, tbw);
+        for (int i = 0; i < 3; ++i) tbw[i] = -tbw[i];
+        d_m3_mul(A.Rcb, Rbw, S.Rcw);
+        d_m3_v(A.Rcb, tbw, S.tcw);
+        for (int i = 0; i < 3; ++i) S.tcw[i] += A.tcb[i];
+      } else if (tid == 32) {
+        d_body_update(S.prev, S.itsPrev, S.x + 15);
+      }
+      __syncthreads();
+      ok = S.ok != 0;
+      ++cj;
+    }
+    if (tid == 0) A.iters[round] = cj;
+    const float chi2close = 1.5f * chi2Mono[round];
+    double cnt[2] = {0, 0};
+    if (edgeThread)
+      for (int e = tid; e < E; e += 256) {
+        const bool st = A.obs[3 * e + 2] >= 0;
+        if (outlier[e]) {
+          double r[3], Xc[3];
+          pio_edge_error(A, S, e, st, r, Xc);
+          err[3 * e] = r[0]; err[3 * e + 1] = r[1]; err[3 * e + 2] = r[2];
+        }
+        const double om = (double)isg[e];
+        const double* r = err + 3 * e;
+        const float chi2 = (float)(r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0));
+        bool bad;
+        if (!st) {
+          const bool bClose = A.closePt[e] != 0;
+          const bool depthPos = (S.Rcw[6] * (double)A.xw[3 * e] + S.Rcw[7] * (double)A.xw[3 * e + 1] + S.Rcw[8] * (double)A.xw[3 * e + 2] + S.tcw[2]) > 0.0;
+          bad = (chi2 > chi2Mono[round] && !bClose) || (bClose && chi2 > chi2close) || !depthPos;
+        } else {
+          bad = chi2 > chi2Stereo[round];
+        }
+        outlier[e] = bad ? 1 : 0;
+        cnt[0] += bad ? 1.0 : 0.0;
+        cnt[1] += bad ? 0.0 : 1.0;
+      }
+    block_sum<2>(cnt, S.red);
+    nBad = (int)cnt[0];
+    nInliers = (int)cnt[1];
+    if (round == 2) robust = false;
+    if (E + 4 < 10) break;
+  }
+  __syncthreads();
+  if (nInliers < 30 && !A.recInit) {
+    double cnt[1] = {0};
+    if (edgeThread)
+      for (int e = tid; e < E; e += 256) {
+        const bool st = A.obs[3 * e + 2] >= 0;
+        double r[3], Xc[3];
+        pio_edge_error(A, S, e, st, r, Xc);
+        err[3 * e] = r[0]; err[3 * e + 1] = r[1]; err[3 * e + 2] = r[2];
+        const double om = (double)isg[e];
+        const double c2 = r[0] * om * r[0] + r[1] * om * r[1] + (st ? r[2] * om * r[2] : 0.0);
+        if (c2 < (double)(st ? 24.f : 18.f)) outlier[e] = 0; else cnt[0] += 1.0;
+      }
+    block_sum<1>(cnt, S.red);
+    nBad = (int)cnt[0];
+  }
+  __syncthreads();
+  if (tid < 21) A.outState[tid] = S.cur[tid];
+  if (tid == 0) *A.nRet = E - nBad;
+  // ---- 30x30 Hessian in the reference's order (previous frame 0-14, frame 15-29) at the final estimates ----
+  double a36[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) a36[k] = 0;
+  if (tid == 256) plf_inertial(A, S);
+  if (tid == 288) plf_prior(A, S, false);
+  if (edgeThread)
+    for (int e = tid; e < E; e += 256) {
+      if (outlier[e]) continue;
+      const bool st = A.obs[3 * e + 2] >= 0;
+      double r[3], Xc[3], J[18];
+      pio_edge_error(A, S, e, st, r, Xc);
+      pio_edge_jacobian(A, Xc, st, J);
+      const int D = st ? 3 : 2;
+      const double om = (double)isg[e];
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+          double t = 0;
+          for (int d = 0; d < D; ++d) t += J[d * 6 + i] * om * J[d * 6 + j];
+          a36[i * 6 + j] += t;
+        }
+    }
+  block_partials<36>(a36, S.red);
+  if (tid < 36) {
+    double s = 0;
+    for (int w = 0; w < 8; ++w) s += S.red[w * 36 + tid];
+    S.tot[tid] = s;
+  }
+  for (int t = tid; t < 900; t += PLF_NT) S.H[t] = 0;
+  __syncthreads();
+  plf_assemble(A, S, true);
+  if (tid < 36) { const int i = tid / 6, j = tid - 6 * i; S.H[(15 + i) * 30 + 15 + j] += S.tot[tid]; }
+  __syncthreads();
+  // ---- Marginalize(H, 0, 14): Hcc - Hcp * pinv(Hpp) * Hpc ----
+  if (tid < 225) { const int i = tid / 15, j = tid - 15 * i; S.mA[tid] = 0.5 * (S.H[i * 30 + j] + S.H[j * 30 + i]); }
+  __syncthreads();
+  if (tid < 32) plf_jacobi15(S);
+  __syncthreads();
+  if (tid < 225) {
+    const int i = tid / 15, j = tid - 15 * i;
+    double s = 0;
+    for (int k = 0; k < 15; ++k) {
+      const double ev = S.mA[k * 15 + k];
+      const double iv = fabs(ev) > 1e-6 ? 1.0 / ev : 0.0;
+      s += S.mV[i * 15 + k] * iv * S.mV[j * 15 + k];
+    }
+    S.mInv[tid] = s;
+  }
+  __syncthreads();
+  if (tid < 225) {
+    const int i = tid / 15, k = tid - 15 * i;
+    double t = 0;
+    for (int l = 0; l < 15; ++l) t += S.H[(15 + i) * 30 + l] * S.mInv[l * 15 + k];
+    S.mT[tid] = t;
+  }
+  __syncthreads();
+  if (tid < 225) {
+    const int i = tid / 15, j = tid - 15 * i;
+    double s = 0;
+    for (int k = 0; k < 15; ++k) s += S.mT[i * 15 + k] * S.H[k * 30 + 15 + j];
+    A.H15[tid] = S.H[(15 + i) * 30 + 15 + j] - s;
+  }
 }
 
 // =====================================================================================
@@ -2265,6 +2754,66 @@ int orbx_pose_inertial_optimization_last_keyframe(orbx_ctx* ctx, int n_edges, co
   PioArgs* dA = S.upload(&A, 1);
   if (S.failed) return ORBX_ECUDA;
   pose_inertial_kernel<<<1, 256, 0, st>>>(dA);
+  ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
+  int32_t res[5] = {0, 0, 0, 0, 0};
+  S.download(state, (const double*)A.outState, (size_t)21);
+  S.download(H15, (const double*)A.H15, (size_t)225);
+  S.download(res, (const int32_t*)d_res, (size_t)5);
+  if (n_edges > 0) S.download(outlier, (const uint8_t*)A.outlier, (size_t)n_edges);
+  int rc = S.finish();
+  if (rc != ORBX_OK) return rc;
+  *n_ret = res[0];
+  for (int i = 0; i < 4; ++i) iters[i] = res[1 + i];
+  return ORBX_OK;
+}
+
+int orbx_pose_inertial_optimization_last_frame(orbx_ctx* ctx, int n_edges, const float* xw, const float* obs, const float* inv_sigma2,
+                                               const uint8_t* close_pt, const orbx_camera* cam, const float* Tcw, const float* Tcb,
+                                               const float* Tbc, double* state, const double* prev_state, const double* preint,
+                                               const double* preint_jac, const double* preint_bias, const double* info_inertial,
+                                               const double* info_gyro, const double* info_acc, const double* prior_state,
+                                               const double* prior_H, int rec_init, uint8_t* outlier, double* H15, int32_t* n_ret,
+                                               int32_t* iters) {
+  if (!ctx || n_edges < 0 || !cam || !Tcw || !Tcb || !Tbc || !state || !prev_state || !preint || !preint_jac || !preint_bias ||
+      !info_inertial || !info_gyro || !info_acc || !prior_state || !prior_H || !H15 || !n_ret || !iters)
+    return ORBX_EINVAL;
+  if (n_edges > 0 && (!xw || !obs || !inv_sigma2 || !close_pt || !outlier)) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevScope S(ctx, st);
+  PlfArgs A;
+  A.E = n_edges;
+  A.xw = S.upload(xw, (size_t)3 * n_edges);
+  A.obs = S.upload(obs, (size_t)3 * n_edges);
+  A.invSigma2 = S.upload(inv_sigma2, n_edges);
+  A.closePt = S.upload(close_pt, n_edges);
+  A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) { A.Rcb[i * 3 + j] = Tcb[i * 4 + j]; A.Rbc[j * 3 + i] = Tcb[i * 4 + j]; A.Rcw0[i * 3 + j] = Tcw[i * 4 + j]; }
+    A.tcb[i] = Tcb[i * 4 + 3]; A.tbc[i] = Tbc[i * 4 + 3]; A.tcw0[i] = Tcw[i * 4 + 3];
+  }
+  memcpy(A.state, state, sizeof A.state);
+  memcpy(A.prev, prev_state, sizeof A.prev);
+  memcpy(A.dR0, preint, 72); memcpy(A.dV0, preint + 9, 24); memcpy(A.dP0, preint + 12, 24);
+  A.dt = preint[15];
+  memcpy(A.JRg, preint_jac, 72); memcpy(A.JVg, preint_jac + 9, 72); memcpy(A.JVa, preint_jac + 18, 72);
+  memcpy(A.JPg, preint_jac + 27, 72); memcpy(A.JPa, preint_jac + 36, 72);
+  memcpy(A.bpre, preint_bias, 48);
+  memcpy(A.infoI, info_inertial, sizeof A.infoI); memcpy(A.infoG, info_gyro, sizeof A.infoG); memcpy(A.infoA, info_acc, sizeof A.infoA);
+  memcpy(A.prior, prior_state, sizeof A.prior);
+  memcpy(A.Hp, prior_H, sizeof A.Hp);
+  A.recInit = rec_init;
+  A.outlier = S.alloc<uint8_t>(n_edges);
+  A.err = S.alloc<double>((size_t)3 * n_edges);
+  A.outState = S.alloc<double>(21);
+  A.H15 = S.alloc<double>(225);
+  int* d_res = S.alloc<int>(5);
+  A.nRet = d_res;
+  A.iters = d_res + 1;
+  PlfArgs* dA = S.upload(&A, 1);
+  if (S.failed) return ORBX_ECUDA;
+  pose_inertial_lf_kernel<<<1, PLF_NT, 0, st>>>(dA);
   ORBX_LAUNCH(ctx);
   ORBX_CUDA(cudaGetLastError());
   int32_t res[5] = {0, 0, 0, 0, 0};

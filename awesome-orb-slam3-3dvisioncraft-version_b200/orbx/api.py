@@ -86,6 +86,7 @@ def load_library():
     L.orbx_pose_optimization_batch_device.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_local_ba.argtypes = [vp, i, vp, vp, i, vp, i, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
     L.orbx_pose_inertial_optimization_last_keyframe.argtypes = [vp, i] + [vp] * 14 + [i] + [vp] * 4
+    L.orbx_pose_inertial_optimization_last_frame.argtypes = [vp, i] + [vp] * 18 + [i] + [vp] * 4
     L.orbx_tracker_create.restype = vp
     L.orbx_tracker_create.argtypes = [vp, vp, i, vp, f, f, f]
     L.orbx_tracker_destroy.argtypes = [vp]
@@ -382,7 +383,7 @@ def stereo_match(ctx, extL, bL, extR, bR, kpL, descL, kpR, descR, bf, b):
 
 
 class Optimizer:
-    """Mirror of the static ORB_SLAM3::Optimizer entry points on the hot path (include/Optimizer.h:58,62,101)."""
+    """Mirror of the static ORB_SLAM3::Optimizer entry points on the hot path (include/Optimizer.h:58,62,64,65)."""
 
     def __init__(self, ctx):
         self.ctx = ctx
@@ -421,7 +422,7 @@ class Optimizer:
 
     def PoseInertialOptimizationLastKeyFrame(self, xw, obs, inv_sigma2, close_pt, cam, Tcw, Tcb, Tbc, state, kf_state,
                                              preint, info_inertial, info_gyro, info_acc, rec_init=False):
-        """include/Optimizer.h:101.  -> dict(state[21], outlier[E], H[15,15], n, iters[4]); argument layout: include/orbx.h"""
+        """include/Optimizer.h:64.  -> dict(state[21], outlier[E], H[15,15], n, iters[4]); argument layout: include/orbx.h"""
         f64 = lambda a, n: np.ascontiguousarray(np.asarray(a, np.float64).reshape(-1)[:n])   # noqa: E731
         xw, obs, isg = _c32(xw, np.float32), _c32(obs, np.float32), _c32(inv_sigma2, np.float32)
         close = _c32(close_pt, np.uint8)
@@ -437,6 +438,28 @@ class Optimizer:
             self.ctx.h, E, _ptr(xw), _ptr(obs), _ptr(isg), _ptr(close), C.byref(cam), _p(T), _p(Tcb), _p(Tbc), _p(st), _p(kf),
             _p(pre), _p(iI), _p(iG), _p(iA), int(rec_init), _p(outl), _p(H), C.byref(n), _p(iters))
         _check(rc, "orbx_pose_inertial_optimization_last_keyframe")
+        return dict(state=st, outlier=outl[:E].copy(), H=H.reshape(15, 15), n=n.value, iters=iters)
+
+    def PoseInertialOptimizationLastFrame(self, xw, obs, inv_sigma2, close_pt, cam, Tcw, Tcb, Tbc, state, prev_state, preint,
+                                          preint_jac, preint_bias, info_inertial, info_gyro, info_acc, prior_state, prior_H,
+                                          rec_init=False):
+        """include/Optimizer.h:65.  -> dict(state[21], outlier[E], H[15,15], n, iters[4]); argument layout: include/orbx.h"""
+        f64 = lambda a, n: np.ascontiguousarray(np.asarray(a, np.float64).reshape(-1)[:n])   # noqa: E731
+        xw, obs, isg = _c32(xw, np.float32), _c32(obs, np.float32), _c32(inv_sigma2, np.float32)
+        close = _c32(close_pt, np.uint8)
+        T, Tcb, Tbc = (np.ascontiguousarray(np.asarray(a, np.float32).reshape(4, 4)) for a in (Tcw, Tcb, Tbc))
+        st = f64(state, 21).copy()
+        pv, pre, pj, pb = f64(prev_state, 21), f64(preint, 16), f64(preint_jac, 45), f64(preint_bias, 6)
+        iI, iG, iA, ps, pH = f64(info_inertial, 81), f64(info_gyro, 9), f64(info_acc, 9), f64(prior_state, 21), f64(prior_H, 225)
+        E = len(isg)
+        outl = np.zeros(max(E, 1), np.uint8)
+        H = np.zeros(225, np.float64)
+        n = C.c_int(0)
+        iters = np.zeros(4, np.int32)
+        rc = load_library().orbx_pose_inertial_optimization_last_frame(
+            self.ctx.h, E, _ptr(xw), _ptr(obs), _ptr(isg), _ptr(close), C.byref(cam), _p(T), _p(Tcb), _p(Tbc), _p(st), _p(pv),
+            _p(pre), _p(pj), _p(pb), _p(iI), _p(iG), _p(iA), _p(ps), _p(pH), int(rec_init), _p(outl), _p(H), C.byref(n), _p(iters))
+        _check(rc, "orbx_pose_inertial_optimization_last_frame")
         return dict(state=st, outlier=outl[:E].copy(), H=H.reshape(15, 15), n=n.value, iters=iters)
 
 

@@ -401,6 +401,28 @@ int orbx_pose_inertial_optimization_last_keyframe(
     const double *info_inertial, const double *info_gyro, const double *info_acc, int rec_init,
     uint8_t *outlier, double *H15, int32_t *n_ret, int32_t *iters);
 
+/* Optimizer::PoseInertialOptimizationLastFrame(Frame*, bool bRecInit) (src/Optimizer.cc:8068-8603) — what
+ * Tracking::TrackLocalMap calls on every other visual-inertial frame (src/Tracking.cc:2974-2990).  The previous
+ * frame's four vertices are free too (30 unknowns), tied down by EdgePriorPoseImu (src/G2oTypes.cc:941-981,
+ * Huber delta 5) built from pFp->mpcpi; EdgeInertial is linearised with respect to all six vertices
+ * (:752-812) with bias-corrected deltas (src/ImuTypes.cc:367-394); at the end the previous frame is
+ * marginalised out of the 30x30 Hessian (Optimizer::Marginalize, :5366-5450).
+ *   state[21]       : in/out, the frame (layout as above);  prev_state[21]: pFrame->mpPrevFrame (in)
+ *   preint[16]      : RAW dR[9], dV[3], dP[3], dT of pFrame->mpImuPreintegratedFrame
+ *   preint_jac[45]  : its JRg, JVg, JVa, JPg, JPa (3x3 row-major each);  preint_bias[6]: its bias, gyro xyz then acc xyz
+ *   info_*          : as above, from mpImuPreintegratedFrame->C
+ *   prior_state[21] : pFp->mpcpi->Rwb, twb, vwb, bg, ba;  prior_H[225]: pFp->mpcpi->H
+ * Out: as above; H15 = H.block<15,15>(15,15) after Marginalize(H, 0, 14), i.e. the argument of the new
+ *      ConstraintPoseImu. */
+int orbx_pose_inertial_optimization_last_frame(
+    orbx_ctx *ctx, int n_edges, const float *xw, const float *obs, const float *inv_sigma2,
+    const uint8_t *close_pt, const orbx_camera *cam, const float *Tcw, const float *Tcb,
+    const float *Tbc, double *state, const double *prev_state, const double *preint,
+    const double *preint_jac, const double *preint_bias, const double *info_inertial,
+    const double *info_gyro, const double *info_acc, const double *prior_state,
+    const double *prior_H, int rec_init, uint8_t *outlier, double *H15, int32_t *n_ret,
+    int32_t *iters);
+
 /* ====================================================================================
  * Many-stream tracking replay: S independent stereo streams
  * advance one frame per call, everything device-resident between stages:

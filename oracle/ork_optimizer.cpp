@@ -1211,16 +1211,20 @@ static void skew3(const double* v, double* S) {
   S[0] = 0; S[1] = -v[2]; S[2] = v[1]; S[3] = v[2]; S[4] = 0; S[5] = -v[0]; S[6] = -v[1]; S[7] = v[0]; S[8] = 0;
 }
 
-// Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major A, destroyed; V columns = eigenvectors).
-// Fixed sweep order (p < q ascending), fixed sweep count, no libm beyond sqrt: bit-reproducible on the device.
-static void jacobi_eig(int n, double* A, double* V, int sweeps = 12) {
+// Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major A, destroyed: eigenvalues on its diagonal;
+// V columns = eigenvectors).  Fixed order (p < q ascending); a rotation is skipped when |a_pq| <= 1e-20 (|a_pp| + |a_qq|)
+// (far below what double arithmetic resolves); stops after a sweep without rotations, at most 16 sweeps.  No libm beyond
+// sqrt, so the device runs the very same arithmetic.
+static void jacobi_eig(int n, double* A, double* V) {
   for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) V[i * n + j] = i == j ? 1.0 : 0.0;
-  for (int s = 0; s < sweeps; ++s)
+  for (int s = 0; s < 16; ++s) {
+    int nrot = 0;
     for (int p = 0; p < n - 1; ++p)
       for (int q = p + 1; q < n; ++q) {
-        const double apq = A[p * n + q];
-        if (apq == 0.0) continue;
-        const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+        const double apq = A[p * n + q], app = A[p * n + p], aqq = A[q * n + q];
+        if (std::fabs(apq) <= 1e-20 * (std::fabs(app) + std::fabs(aqq))) continue;
+        ++nrot;
+        const double theta = (aqq - app) / (2.0 * apq);
         const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
         const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
         for (int k = 0; k < n; ++k) {   // A <- A * G
@@ -1239,6 +1243,8 @@ static void jacobi_eig(int n, double* A, double* V, int sweeps = 12) {
           V[k * n + q] = sn * vkp + c * vkq;
         }
       }
+    if (!nrot) break;
+  }
 }
 
 // Optimizer::Marginalize(H, 0, 14) on the 30x30 Hessian (previous frame first): Hcc - Hcp * pinv(Hpp) * Hpc -> out[15][15]

@@ -177,3 +177,61 @@ def test_pose_inertial_optimization_edge_cases(ctx, ork):
     g = _inertial_call(opt, s, cam)
     assert np.abs(g["state"] - r["state"]).max() < 1e-9 and g["n"] == r["n"] == 0
     assert np.abs(g["H"] - r["H"]).max() <= 1e-9 * np.abs(r["H"]).max()
+
+
+def _inertial_lf_call(opt, s, cam, rec_init=False):
+    return opt.PoseInertialOptimizationLastFrame(s["xw"], s["obs"], s["isg"], s["close"], cam, s["Tcw"], s["Tcb"], s["Tbc"], s["state"],
+                                                 s["prev"], s["preint"], s["preint_jac"], s["preint_bias"], s["infoI"], s["infoG"],
+                                                 s["infoA"], s["prior_state"], s["prior_H"], rec_init=rec_init)
+
+
+@pytest.mark.parametrize("E,stereo_frac", [(300, 0.6), (150, 0.0), (500, 1.0), (60, 0.5), (1000, 0.7)])
+def test_pose_inertial_optimization_last_frame_matches_oracle(ctx, ork, E, stereo_frac):
+    """SURVEY.md §8 f3, second function (30 unknowns, prior edge, marginalisation): state and marginalised 15x15 prior to fp64
+    rounding, classification and iteration counts exactly."""
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    for seed in range(6):
+        s = sc.inertial_lf_scenario(2000 * E + seed, E, stereo_frac)
+        r = ork.pose_inertial_optimization_last_frame(s, cam)
+        g = _inertial_lf_call(opt, s, cam)
+        assert np.array_equal(g["iters"], r["iters"])
+        assert np.array_equal(g["outlier"], r["outlier"]) and g["n"] == r["n"]
+        assert np.abs(g["state"] - r["state"]).max() < 1e-9, (seed, np.abs(g["state"] - r["state"]).max())
+        assert np.abs(g["H"] - r["H"]).max() <= 1e-9 * np.abs(r["H"]).max(), (seed, np.abs(g["H"] - r["H"]).max(), np.abs(r["H"]).max())
+        assert np.linalg.norm(g["state"][:9] - r["state"][:9]) / np.sqrt(2) < ROT_TOL_RAD
+        assert np.abs(g["state"][9:12] - s["truth"][9:12]).max() < 1e-2
+
+
+def test_pose_inertial_optimization_last_frame_edge_cases(ctx, ork):
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    s = sc.inertial_lf_scenario(7, 24, 0.5, outlier_frac=0.3)           # < 30 inliers: recovery branch / bRecInit
+    for rec in (False, True):
+        r = ork.pose_inertial_optimization_last_frame(s, cam, rec_init=rec)
+        g = _inertial_lf_call(opt, s, cam, rec_init=rec)
+        assert np.array_equal(g["outlier"], r["outlier"]) and g["n"] == r["n"] and np.array_equal(g["iters"], r["iters"])
+        assert np.abs(g["state"] - r["state"]).max() < 1e-9
+    s = sc.inertial_lf_scenario(8, 5, 0.5, outlier_frac=0.0)            # 5 + 4 graph edges < 10: one round only
+    r = ork.pose_inertial_optimization_last_frame(s, cam)
+    g = _inertial_lf_call(opt, s, cam)
+    assert list(g["iters"]) == list(r["iters"]) == [10, 0, 0, 0]
+    assert np.abs(g["state"] - r["state"]).max() < 1e-9 and np.array_equal(g["outlier"], r["outlier"])
+    s = sc.inertial_lf_scenario(9, 0, 0.5)                              # no visual edges: IMU + prior alone
+    r = ork.pose_inertial_optimization_last_frame(s, cam)
+    g = _inertial_lf_call(opt, s, cam)
+    assert np.abs(g["state"] - r["state"]).max() < 1e-9 and g["n"] == r["n"] == 0
+    assert np.abs(g["H"] - r["H"]).max() <= 1e-9 * np.abs(r["H"]).max()
+    # a stiff and a rank-deficient prior (pseudo-inverse path of the marginalisation)
+    s = sc.inertial_lf_scenario(10, 200, 0.6)
+    Hp = s["prior_H"].copy()
+    Hp[9:, :] = 0
+    Hp[:, 9:] = 0
+    s["prior_H"] = Hp
+    r = ork.pose_inertial_optimization_last_frame(s, cam)
+    g = _inertial_lf_call(opt, s, cam)
+    assert np.array_equal(g["iters"], r["iters"]) and np.array_equal(g["outlier"], r["outlier"])
+    assert np.abs(g["state"] - r["state"]).max() < 1e-8
+    assert np.abs(g["H"] - r["H"]).max() <= 1e-8 * np.abs(r["H"]).max()
