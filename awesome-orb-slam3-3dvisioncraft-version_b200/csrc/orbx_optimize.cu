@@ -460,6 +460,68 @@ __device__ bool ldlt_solve_shfl(const double* A, const double* b, double* x) {
 
 __device__ __forceinline__ bool ldlt6_solve_shfl(const double* A, const double* b, double* x) { return ldlt_solve_shfl<6>(A, b, x); }
 
+// The same factorisation for 6 < N <= 32 with the matrix in shared memory (leading dimension LD, odd => conflict-free
+// column accesses; destroyed): lane i owns row i, computes the lower entries (i, j <= i) of the trailing update
+// A[i][j] - (A[i][k]*d)*A[j][k] and mirrors them, exactly the serial routine's arithmetic; the pivot is the first largest
+// |diagonal| (butterfly arg-max with index tie-break).  One warp; all 32 lanes must call; every lane returns the same.
+template <int N, int LD>
+__device__ bool ldlt_solve_smem(double* A, const double* b, double* x) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool row = lane < N;
+  int perm = lane;
+  bool positive = true;
+  __syncwarp();
+  for (int k = 0; k < N; ++k) {
+    double v = (row && lane >= k) ? fabs(A[lane * LD + lane]) : -1.0;
+    int p = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(FULL, v, o);
+      const int op = __shfl_xor_sync(FULL, p, o);
+      if (ov > v || (ov == v && op < p)) { v = ov; p = op; }
+    }
+    if (p != k) {                                 // warp-uniform
+      if (row) { const double t = A[k * LD + lane]; A[k * LD + lane] = A[p * LD + lane]; A[p * LD + lane] = t; }
+      __syncwarp();
+      if (row) { const double t = A[lane * LD + k]; A[lane * LD + k] = A[lane * LD + p]; A[lane * LD + p] = t; }
+      const int pk = __shfl_sync(FULL, perm, k), pp = __shfl_sync(FULL, perm, p);
+      if (lane == k) perm = pp; else if (lane == p) perm = pk;
+      __syncwarp();
+    }
+    const double d = A[k * LD + k];
+    if (d < 0) positive = false;
+    if (d == 0) continue;
+    const bool below = row && lane > k;
+    double lik = 0;
+    if (below) { lik = A[lane * LD + k] / d; A[lane * LD + k] = lik; }
+    __syncwarp();
+    if (below) {
+      const double lid = lik * d;
+      for (int j = k + 1; j <= lane; ++j) {
+        const double nv = A[lane * LD + j] - lid * A[j * LD + k];
+        A[lane * LD + j] = nv;
+        A[j * LD + lane] = nv;
+      }
+    }
+    __syncwarp();
+  }
+  if (!positive) return false;
+  double y = row ? b[perm] : 0.0;
+  for (int j = 0; j < N - 1; ++j) {               // forward: y[i] -= L[i][j]*y[j], j ascending
+    const double yj = __shfl_sync(FULL, y, j);
+    if (row && lane > j) y -= A[lane * LD + j] * yj;
+  }
+  if (row) { const double dg = A[lane * LD + lane]; y = (dg != 0) ? y / dg : 0.0; }
+  for (int j = N - 1; j > 0; --j) {               // backward: y[i] -= L[j][i]*y[j], j descending
+    const double yj = __shfl_sync(FULL, y, j);
+    if (lane < j) y -= A[j * LD + lane] * yj;
+  }
+  if (row) x[perm] = y;
+  __syncwarp();
+  return true;
+}
+
 // =====================================================================================
 // K11  PoseOptimization: one CTA per frame
 // =====================================================================================
@@ -1601,6 +1663,7 @@ int orbx_launch_pose_opt_slices(orbx_ctx* ctx, cudaStream_t st, int P, const int
 //      LDL^T in registers + shuffles (one warp), ImuCamPose::Update by one thread.  Conventions for the two points where
 //      the reference is not reproducible (re-orthonormalisation, ExpSO3's float SVD): DESIGN.md §7.
 // =====================================================================================
+#define PIO_NT 288
 struct PioArgs {
   int E;
   const float *xw, *obs, *invSigma2;
@@ -1686,7 +1749,7 @@ struct PioShared {
   double Rwb[9], twb[3], Rcw[9], tcw[3], v[3], bg[3], ba[3];
   double H[225], b[15], x[15], tot[36];
   double e9[9], J[81], OJ[81], Oe[9];
-  double red[(256 / 32) * 36];
+  double red[(PIO_NT / 32) * 36];
   int its, ok;
 };
 
@@ -1752,10 +1815,11 @@ __device__ void pio_inertial(const PioArgs& A, PioShared& S, bool withError) {
     }
 }
 
-__global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __restrict__ args) {
+__global__ void __launch_bounds__(PIO_NT) pose_inertial_kernel(const PioArgs* __restrict__ args) {
   const PioArgs& A = args[blockIdx.x];
   __shared__ PioShared S;
   const int tid = threadIdx.x, E = A.E;
+  const bool edgeThread = tid < 256;     // warps 0-7: the visual edges; warp 8 linearises the inertial edge beside them
   const float* isg = A.invSigma2;
   uint8_t* outlier = A.outlier;
   double* err = A.err;
@@ -1764,7 +1828,7 @@ __global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __res
   if (tid < 15) S.x[tid] = 0;
   if (tid == 0) S.its = 0;
   if (tid < 4) A.iters[tid] = 0;
-  for (int e = tid; e < E; e += 256) outlier[e] = 0;
+  for (int e = edgeThread ? tid : E; e < E; e += 256) outlier[e] = 0;
   __syncthreads();
   const HuberD hMono = huber_make(sqrtf(5.991f)), hStereo = huber_make(sqrtf(7.815f));
   const float chi2Mono[4] = {12.f, 7.5f, 5.991f, 5.991f}, chi2Stereo[4] = {15.6f, 9.8f, 7.815f, 7.815f};
@@ -1778,7 +1842,8 @@ __global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __res
       double acc[27];
 #pragma unroll
       for (int k = 0; k < 27; ++k) acc[k] = 0;
-      for (int e = tid; e < E; e += 256) {
+      if (tid == 256) pio_inertial(A, S, true);
+      for (int e = edgeThread ? tid : E; e < E; e += 256) {
         if (outlier[e]) continue;
         const bool st = A.obs[3 * e + 2] >= 0;
         double r[3], Xc[3], J[18];
@@ -1807,7 +1872,6 @@ __global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __res
         for (int w = 0; w < 8; ++w) s += S.red[w * 27 + tid];
         S.tot[tid] = s;
       }
-      if (tid == 32) pio_inertial(A, S, true);      // (another warp: runs beside the cross-warp sums)
       __syncthreads();
       // ---- assemble H (15x15), b ----
       if (tid < 225) S.H[tid] = 0;
@@ -1852,7 +1916,7 @@ __global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __res
       __syncthreads();
       // ---- solve (LinearSolverDense: pivoted LDL^T; a failure leaves x as it was) + update ----
       if (tid < 32) {
-        const bool okSolve = ldlt_solve_shfl<15>(S.H, S.b, S.x);
+        const bool okSolve = ldlt_solve_smem<15, 15>(S.H, S.b, S.x);
         if (tid == 0) {
           S.ok = okSolve ? 1 : 0;
           double d[3], E3[9], Rn[9];
@@ -1879,7 +1943,7 @@ __global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __res
     // ---- chi2 classification (src/Optimizer.cc:7900-7975) ----
     const float chi2close = 1.5f * chi2Mono[round];
     double cnt[2] = {0, 0};
-    for (int e = tid; e < E; e += 256) {
+    for (int e = edgeThread ? tid : E; e < E; e += 256) {
       const bool st = A.obs[3 * e + 2] >= 0;
       if (outlier[e]) {
         double r[3], Xc[3];
@@ -1910,7 +1974,7 @@ __global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __res
   __syncthreads();
   if (nInliers < 30 && !A.recInit) {               // recovery (:7990-8020)
     double cnt[1] = {0};
-    for (int e = tid; e < E; e += 256) {
+    for (int e = edgeThread ? tid : E; e < E; e += 256) {
       const bool st = A.obs[3 * e + 2] >= 0;
       double r[3], Xc[3];
       pio_edge_error(A, S, e, st, r, Xc);
@@ -1930,7 +1994,8 @@ __global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __res
   double a36[36];
 #pragma unroll
   for (int k = 0; k < 36; ++k) a36[k] = 0;
-  for (int e = tid; e < E; e += 256) {
+  if (tid == 256) pio_inertial(A, S, false);
+  for (int e = edgeThread ? tid : E; e < E; e += 256) {
     if (outlier[e]) continue;
     const bool st = A.obs[3 * e + 2] >= 0;
     double r[3], Xc[3], J[18];
@@ -1951,7 +2016,6 @@ __global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __res
     for (int w = 0; w < 8; ++w) s += S.red[w * 36 + tid];
     S.tot[tid] = s;
   }
-  if (tid == 32) pio_inertial(A, S, false);
   __syncthreads();
   if (tid < 225) S.H[tid] = 0;
   __syncthreads();
@@ -1988,6 +2052,7 @@ __global__ void __launch_bounds__(256) pose_inertial_kernel(const PioArgs* __res
 //      reduced to the frame's 15x15 prior with a warp-parallel cyclic Jacobi eigen-solver (pseudo-inverse, 1e-6 threshold).
 // =====================================================================================
 #define PLF_NT 320
+#define PLF_LD 31     // leading dimension of the 30x30 system in shared memory (odd: conflict-free columns)
 struct PlfArgs {
   int E;
   const float *xw, *obs, *invSigma2;
@@ -2008,7 +2073,7 @@ struct PlfArgs {
 };
 struct PlfShared {
   double cur[21], prev[21], Rcw[9], tcw[3];
-  double H[900], b[30], x[30], tot[36];
+  double H[30 * PLF_LD], b[30], x[30], tot[36];
   double e9[9], J[216], OJ[216], Oe[9];
   double e15[15], Jp[225], OJp[225], Oep[15], wPrior;
   double mA[225], mV[225], mInv[225], mT[225];
@@ -2137,7 +2202,7 @@ __device__ void plf_prior(const PlfArgs& A, PlfShared& S, bool robust) {
   }
   S.wPrior = w;
 }
-// Assembly of the inertial, random-walk and prior edges into S.H (ld 30) / S.b, edge by edge in a fixed order.  `fin`:
+// Assembly of the inertial, random-walk and prior edges into S.H (ld PLF_LD) / S.b, edge by edge in a fixed order.  `fin`:
 // the reference's final ordering (previous frame first), no gradient, no robust weight.
 __device__ void plf_assemble(const PlfArgs& A, PlfShared& S, bool fin) {
   const int tid = threadIdx.x;
@@ -2176,7 +2241,7 @@ __device__ void plf_assemble(const PlfArgs& A, PlfShared& S, bool fin) {
       double v = 0;
       for (int k = 0; k < 9; ++k) v += S.J[k * 24 + i] * S.OJ[k * 24 + j];
       const int gi = i < 15 ? oI + i : oC + i - 15, gj = j < 15 ? oI + j : oC + j - 15;
-      S.H[gi * 30 + gj] += v;
+      S.H[gi * PLF_LD + gj] += v;
     } else if (!fin) {
       const int i = t - 576;
       double v = 0;
@@ -2190,10 +2255,10 @@ __device__ void plf_assemble(const PlfArgs& A, PlfShared& S, bool fin) {
     const int i = tid / 3, j = tid - 3 * i;
     const double gI = A.infoG[tid], aI = A.infoA[tid];
     const int c = oC, p = oI;
-    S.H[(c + 9 + i) * 30 + c + 9 + j] += gI;  S.H[(p + 9 + i) * 30 + p + 9 + j] += gI;
-    S.H[(c + 9 + i) * 30 + p + 9 + j] -= gI;  S.H[(p + 9 + i) * 30 + c + 9 + j] -= gI;
-    S.H[(c + 12 + i) * 30 + c + 12 + j] += aI; S.H[(p + 12 + i) * 30 + p + 12 + j] += aI;
-    S.H[(c + 12 + i) * 30 + p + 12 + j] -= aI; S.H[(p + 12 + i) * 30 + c + 12 + j] -= aI;
+    S.H[(c + 9 + i) * PLF_LD + c + 9 + j] += gI;  S.H[(p + 9 + i) * PLF_LD + p + 9 + j] += gI;
+    S.H[(c + 9 + i) * PLF_LD + p + 9 + j] -= gI;  S.H[(p + 9 + i) * PLF_LD + c + 9 + j] -= gI;
+    S.H[(c + 12 + i) * PLF_LD + c + 12 + j] += aI; S.H[(p + 12 + i) * PLF_LD + p + 12 + j] += aI;
+    S.H[(c + 12 + i) * PLF_LD + p + 12 + j] -= aI; S.H[(p + 12 + i) * PLF_LD + c + 12 + j] -= aI;
   } else if (tid >= 32 && tid < 35 && !fin) {
     const int i = tid - 32;
     double sg = 0, sa = 0;
@@ -2211,7 +2276,7 @@ __device__ void plf_assemble(const PlfArgs& A, PlfShared& S, bool fin) {
       const int i = t / 15, j = t - 15 * i;
       double v = 0;
       for (int k = 0; k < 15; ++k) v += S.Jp[k * 15 + i] * S.OJp[k * 15 + j];
-      S.H[(oI + i) * 30 + oI + j] += v;
+      S.H[(oI + i) * PLF_LD + oI + j] += v;
     } else if (!fin) {
       const int i = t - 225;
       double v = 0;
@@ -2318,19 +2383,19 @@ __global__ void __launch_bounds__(PLF_NT) pose_inertial_lf_kernel(const PlfArgs*
         for (int w = 0; w < 8; ++w) s += S.red[w * 27 + tid];
         S.tot[tid] = s;
       }
-      for (int t = tid; t < 900; t += PLF_NT) S.H[t] = 0;
+      for (int t = tid; t < 30 * PLF_LD; t += PLF_NT) S.H[t] = 0;
       if (tid >= 288 && tid < 318) S.b[tid - 288] = 0;
       __syncthreads();
       if (tid < 36) {
         const int i = tid / 6, j = tid - 6 * i, lo = min(i, j), hi = max(i, j);
-        S.H[i * 30 + j] = S.tot[6 * lo - (lo * (lo - 1)) / 2 + (hi - lo)];
+        S.H[i * PLF_LD + j] = S.tot[6 * lo - (lo * (lo - 1)) / 2 + (hi - lo)];
       } else if (tid < 42) {
         S.b[tid - 36] = S.tot[21 + tid - 36];
       }
       __syncthreads();
       plf_assemble(A, S, false);
       if (tid < 32) {
-        const bool okSolve = ldlt_solve_shfl<30>(S.H, S.b, S.x);
+        const bool okSolve = ldlt_solve_smem<30, PLF_LD>(S.H, S.b, S.x);
         if (tid == 0) S.ok = okSolve ? 1 : 0;
       }
       __syncthreads();
@@ -2429,13 +2494,13 @@ __global__ void __launch_bounds__(PLF_NT) pose_inertial_lf_kernel(const PlfArgs*
     for (int w = 0; w < 8; ++w) s += S.red[w * 36 + tid];
     S.tot[tid] = s;
   }
-  for (int t = tid; t < 900; t += PLF_NT) S.H[t] = 0;
+  for (int t = tid; t < 30 * PLF_LD; t += PLF_NT) S.H[t] = 0;
   __syncthreads();
   plf_assemble(A, S, true);
-  if (tid < 36) { const int i = tid / 6, j = tid - 6 * i; S.H[(15 + i) * 30 + 15 + j] += S.tot[tid]; }
+  if (tid < 36) { const int i = tid / 6, j = tid - 6 * i; S.H[(15 + i) * PLF_LD + 15 + j] += S.tot[tid]; }
   __syncthreads();
   // ---- Marginalize(H, 0, 14): Hcc - Hcp * pinv(Hpp) * Hpc ----
-  if (tid < 225) { const int i = tid / 15, j = tid - 15 * i; S.mA[tid] = 0.5 * (S.H[i * 30 + j] + S.H[j * 30 + i]); }
+  if (tid < 225) { const int i = tid / 15, j = tid - 15 * i; S.mA[tid] = 0.5 * (S.H[i * PLF_LD + j] + S.H[j * PLF_LD + i]); }
   __syncthreads();
   if (tid < 32) plf_jacobi15(S);
   __syncthreads();
@@ -2453,15 +2518,15 @@ __global__ void __launch_bounds__(PLF_NT) pose_inertial_lf_kernel(const PlfArgs*
   if (tid < 225) {
     const int i = tid / 15, k = tid - 15 * i;
     double t = 0;
-    for (int l = 0; l < 15; ++l) t += S.H[(15 + i) * 30 + l] * S.mInv[l * 15 + k];
+    for (int l = 0; l < 15; ++l) t += S.H[(15 + i) * PLF_LD + l] * S.mInv[l * 15 + k];
     S.mT[tid] = t;
   }
   __syncthreads();
   if (tid < 225) {
     const int i = tid / 15, j = tid - 15 * i;
     double s = 0;
-    for (int k = 0; k < 15; ++k) s += S.mT[i * 15 + k] * S.H[k * 30 + 15 + j];
-    A.H15[tid] = S.H[(15 + i) * 30 + 15 + j] - s;
+    for (int k = 0; k < 15; ++k) s += S.mT[i * 15 + k] * S.H[k * PLF_LD + 15 + j];
+    A.H15[tid] = S.H[(15 + i) * PLF_LD + 15 + j] - s;
   }
 }
 
@@ -2753,7 +2818,7 @@ int orbx_pose_inertial_optimization_last_keyframe(orbx_ctx* ctx, int n_edges, co
   A.iters = d_res + 1;
   PioArgs* dA = S.upload(&A, 1);
   if (S.failed) return ORBX_ECUDA;
-  pose_inertial_kernel<<<1, 256, 0, st>>>(dA);
+  pose_inertial_kernel<<<1, PIO_NT, 0, st>>>(dA);
   ORBX_LAUNCH(ctx);
   ORBX_CUDA(cudaGetLastError());
   int32_t res[5] = {0, 0, 0, 0, 0};

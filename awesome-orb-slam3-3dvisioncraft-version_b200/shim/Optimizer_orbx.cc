@@ -1,6 +1,6 @@
 // Optimizer_orbx.cc — drop-in replacements for Optimizer::PoseOptimization (src/Optimizer.cc:907-1272),
-// Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1811-2523) and Optimizer::PoseInertialOptimizationLastKeyFrame
-// (src/Optimizer.cc:7665-8066); the rest of the class stays in the reference.
+// Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1811-2523) and Optimizer::PoseInertialOptimizationLastKeyFrame /
+// LastFrame (src/Optimizer.cc:7665-8066, :8068-8603); the rest of the class stays in the reference.
 // Graph *collection* and *write-back* walk the reference's pointer graph exactly as the reference does (same
 // locks, same bookkeeping fields); only the numeric core — g2o graph, LM, Schur, chi2 tests — is delegated.
 #include "orbx_shim_config.h"
@@ -61,84 +61,63 @@ int Optimizer::PoseOptimization(Frame* pFrame) {
   return nInliers;
 }
 
-// Visual-inertial pose refinement against the last keyframe (pinhole rigs, Nleft == -1).  Everything that the reference's
-// vertex / edge constructors derive from the Frame, the KeyFrame and the pre-integration (ImuCamPose, the delta
-// measurements at the keyframe's bias, the eigenvalue-clamped information matrices) is obtained from those very
-// constructors; the Gauss-Newton rounds, the chi2 classification and the 15x15 Hessian are delegated.
-int Optimizer::PoseInertialOptimizationLastKeyFrame(Frame* pFrame, bool bRecInit) {
-  const int N = pFrame->N;
-  if (pFrame->Nleft != -1) throw std::runtime_error("orbx: PoseInertialOptimizationLastKeyFrame covers pinhole rigs (Nleft == -1)");
+// ---- visual-inertial pose refinement (pinhole rigs, Nleft == -1) ----------------------------------------------------
+// Everything that the reference's vertex / edge constructors derive from the Frame, the KeyFrame and the pre-integration
+// (ImuCamPose, delta measurements, the eigenvalue-clamped information matrices) is obtained from those very
+// constructors; the Gauss-Newton rounds, the chi2 classification and the Hessian / marginalisation are delegated.
+namespace {
+struct VisualEdges {
   std::vector<float> xw, obs, isg;
   std::vector<uint8_t> closePt;
   std::vector<int> index;
-  {
-    std::unique_lock<std::mutex> lock(MapPoint::mGlobalMutex);   // src/Optimizer.cc:7720
-    for (int i = 0; i < N; i++) {
-      MapPoint* pMP = pFrame->mvpMapPoints[i];
-      if (!pMP) continue;
-      pFrame->mvbOutlier[i] = false;
-      const cv::KeyPoint& kpUn = pFrame->mvKeysUn[i];
-      Eigen::Vector2d o2;
-      o2(0) = kpUn.pt.x;
-      o2(1) = kpUn.pt.y;
-      const float unc2 = pFrame->mpCamera->uncertainty2(o2);    // 1 for Pinhole (:7749, :7781)
-      const cv::Mat Xw = pMP->GetWorldPos();
-      for (int k = 0; k < 3; ++k) xw.push_back(Xw.at<float>(k));
-      obs.push_back(kpUn.pt.x);
-      obs.push_back(kpUn.pt.y);
-      obs.push_back(pFrame->mvuRight[i]);                        // < 0: EdgeMonoOnlyPose, else EdgeStereoOnlyPose
-      isg.push_back(pFrame->mvInvLevelSigma2[kpUn.octave] / unc2);
-      closePt.push_back(pMP->mTrackDepth < 10.f ? 1 : 0);        // :7912
-      index.push_back(i);
-    }
+};
+void collect_visual_edges(Frame* pFrame, VisualEdges& V) {   // src/Optimizer.cc:7719-7823 == :8161-8273
+  if (pFrame->Nleft != -1) throw std::runtime_error("orbx: PoseInertialOptimization* covers pinhole rigs (Nleft == -1)");
+  const int N = pFrame->N;
+  std::unique_lock<std::mutex> lock(MapPoint::mGlobalMutex);
+  for (int i = 0; i < N; i++) {
+    MapPoint* pMP = pFrame->mvpMapPoints[i];
+    if (!pMP) continue;
+    pFrame->mvbOutlier[i] = false;
+    const cv::KeyPoint& kpUn = pFrame->mvKeysUn[i];
+    Eigen::Vector2d o2;
+    o2(0) = kpUn.pt.x;
+    o2(1) = kpUn.pt.y;
+    const float unc2 = pFrame->mpCamera->uncertainty2(o2);    // 1 for Pinhole
+    const cv::Mat Xw = pMP->GetWorldPos();
+    for (int k = 0; k < 3; ++k) V.xw.push_back(Xw.at<float>(k));
+    V.obs.push_back(kpUn.pt.x);
+    V.obs.push_back(kpUn.pt.y);
+    V.obs.push_back(pFrame->mvuRight[i]);                        // < 0: EdgeMonoOnlyPose, else EdgeStereoOnlyPose
+    V.isg.push_back(pFrame->mvInvLevelSigma2[kpUn.octave] / unc2);
+    V.closePt.push_back(pMP->mTrackDepth < 10.f ? 1 : 0);        // :7912 / :8412
+    V.index.push_back(i);
   }
-  const int E = (int)index.size();
-  KeyFrame* pKF = pFrame->mpLastKeyFrame;
-  const VertexPose VP(pFrame), VPk(pKF);                          // ImuCamPose(Frame*) / ImuCamPose(KeyFrame*)
-  const ImuCamPose& P = VP.estimate();
-  const ImuCamPose& Pk = VPk.estimate();
-  double state[21], kf[21], preint[16], infoI[81], infoG[9], infoA[9];
+}
+void body_state(const ImuCamPose& P, const cv::Mat& vel, const IMU::Bias& b, double* s) {
   for (int r = 0; r < 3; ++r) {
-    for (int c = 0; c < 3; ++c) { state[r * 3 + c] = P.Rwb(r, c); kf[r * 3 + c] = Pk.Rwb(r, c); }
-    state[9 + r] = P.twb(r);
-    kf[9 + r] = Pk.twb(r);
-    state[12 + r] = pFrame->mVw.at<float>(r);                    // VertexVelocity(Frame*) (src/G2oTypes.cc:668-672)
-    kf[12 + r] = pKF->GetVelocity().at<float>(r);
+    for (int c = 0; c < 3; ++c) s[r * 3 + c] = P.Rwb(r, c);
+    s[9 + r] = P.twb(r);
+    s[12 + r] = vel.at<float>(r);
   }
-  const IMU::Bias bF = pFrame->mImuBias, bK = pKF->GetImuBias();
-  const float gF[3] = {bF.bwx, bF.bwy, bF.bwz}, aF[3] = {bF.bax, bF.bay, bF.baz};
-  const float gK[3] = {bK.bwx, bK.bwy, bK.bwz}, aK[3] = {bK.bax, bK.bay, bK.baz};
-  for (int r = 0; r < 3; ++r) { state[15 + r] = gF[r]; state[18 + r] = aF[r]; kf[15 + r] = gK[r]; kf[18 + r] = aK[r]; }
-  IMU::Preintegrated* pInt = pFrame->mpImuPreintegrated;
-  const cv::Mat dR = pInt->GetDeltaRotation(bK), dV = pInt->GetDeltaVelocity(bK), dP = pInt->GetDeltaPosition(bK);   // :739-741
-  for (int r = 0; r < 3; ++r) {
-    for (int c = 0; c < 3; ++c) preint[r * 3 + c] = dR.at<float>(r, c);
-    preint[9 + r] = dV.at<float>(r);
-    preint[12 + r] = dP.at<float>(r);
-  }
-  preint[15] = pInt->dT;
+  s[15] = b.bwx; s[16] = b.bwy; s[17] = b.bwz; s[18] = b.bax; s[19] = b.bay; s[20] = b.baz;
+}
+void information_matrices(IMU::Preintegrated* pInt, double* infoI, double* infoG, double* infoA) {
   const EdgeInertial ei(pInt);                                    // inverse + eigenvalue clamp (src/G2oTypes.cc:706-727)
   for (int r = 0; r < 9; ++r)
     for (int c = 0; c < 9; ++c) infoI[r * 9 + c] = ei.information()(r, c);
-  const cv::Mat cvInfoG = pInt->C.rowRange(9, 12).colRange(9, 12).inv(cv::DECOMP_SVD);       // :7861
-  const cv::Mat cvInfoA = pInt->C.rowRange(12, 15).colRange(12, 15).inv(cv::DECOMP_SVD);     // :7872
+  const cv::Mat cvInfoG = pInt->C.rowRange(9, 12).colRange(9, 12).inv(cv::DECOMP_SVD);       // :7861 / :8316
+  const cv::Mat cvInfoA = pInt->C.rowRange(12, 15).colRange(12, 15).inv(cv::DECOMP_SVD);     // :7872 / :8334
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) { infoG[r * 3 + c] = cvInfoG.at<float>(r, c); infoA[r * 3 + c] = cvInfoA.at<float>(r, c); }
-  float Tcw[16], Tcb[16], Tbc[16];
-  pose_to_array(pFrame->mTcw, Tcw);
-  pose_to_array(pFrame->mImuCalib.Tcb, Tcb);
-  pose_to_array(pFrame->mImuCalib.Tbc, Tbc);
-  orbx_camera cam{pFrame->fx, pFrame->fy, pFrame->cx, pFrame->cy, pFrame->mbf, pFrame->mb};
-  std::vector<uint8_t> outlier(E > 0 ? E : 1, 0);
-  double H15[225];
-  int32_t nRet = 0, iters[4];
-  orbx_shim::check("orbx_pose_inertial_optimization_last_keyframe",
-                   orbx_pose_inertial_optimization_last_keyframe(orbx_shim::context(), E, xw.data(), obs.data(), isg.data(),
-                                                                 closePt.data(), &cam, Tcw, Tcb, Tbc, state, kf, preint, infoI,
-                                                                 infoG, infoA, bRecInit ? 1 : 0, outlier.data(), H15, &nRet,
-                                                                 iters));
-  for (int e = 0; e < E; ++e) pFrame->mvbOutlier[index[e]] = outlier[e] != 0;
-  // recover pose, velocity, biases and the prior for the next frame (:8022-8063)
+}
+void mat3_to(const cv::Mat& M, double* out) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) out[r * 3 + c] = M.at<float>(r, c);
+}
+// recover pose, velocity, biases and the prior for the next frame (:8022-8063 / :8533-8598)
+void write_back(Frame* pFrame, const VisualEdges& V, const std::vector<uint8_t>& outlier, const double* state, const double* H15) {
+  for (size_t e = 0; e < V.index.size(); ++e) pFrame->mvbOutlier[V.index[e]] = outlier[e] != 0;
   Eigen::Matrix3d Rwb;
   Eigen::Vector3d twb, vwb, bg, ba;
   for (int r = 0; r < 3; ++r) {
@@ -151,6 +130,83 @@ int Optimizer::PoseInertialOptimizationLastKeyFrame(Frame* pFrame, bool bRecInit
   for (int r = 0; r < 15; ++r)
     for (int c = 0; c < 15; ++c) H(r, c) = H15[r * 15 + c];
   pFrame->mpcpi = new ConstraintPoseImu(Rwb, twb, vwb, bg, ba, H);
+}
+}  // namespace
+
+int Optimizer::PoseInertialOptimizationLastKeyFrame(Frame* pFrame, bool bRecInit) {
+  VisualEdges V;
+  collect_visual_edges(pFrame, V);
+  const int E = (int)V.index.size();
+  KeyFrame* pKF = pFrame->mpLastKeyFrame;
+  const VertexPose VP(pFrame), VPk(pKF);                          // ImuCamPose(Frame*) / ImuCamPose(KeyFrame*)
+  double state[21], kf[21], preint[16], infoI[81], infoG[9], infoA[9];
+  body_state(VP.estimate(), pFrame->mVw, pFrame->mImuBias, state);
+  const IMU::Bias bK = pKF->GetImuBias();
+  body_state(VPk.estimate(), pKF->GetVelocity(), bK, kf);
+  IMU::Preintegrated* pInt = pFrame->mpImuPreintegrated;
+  const cv::Mat dR = pInt->GetDeltaRotation(bK), dV = pInt->GetDeltaVelocity(bK), dP = pInt->GetDeltaPosition(bK);   // :739-741
+  mat3_to(dR, preint);
+  for (int r = 0; r < 3; ++r) { preint[9 + r] = dV.at<float>(r); preint[12 + r] = dP.at<float>(r); }
+  preint[15] = pInt->dT;
+  information_matrices(pInt, infoI, infoG, infoA);
+  float Tcw[16], Tcb[16], Tbc[16];
+  pose_to_array(pFrame->mTcw, Tcw);
+  pose_to_array(pFrame->mImuCalib.Tcb, Tcb);
+  pose_to_array(pFrame->mImuCalib.Tbc, Tbc);
+  orbx_camera cam{pFrame->fx, pFrame->fy, pFrame->cx, pFrame->cy, pFrame->mbf, pFrame->mb};
+  std::vector<uint8_t> outlier(E > 0 ? E : 1, 0);
+  double H15[225];
+  int32_t nRet = 0, iters[4];
+  orbx_shim::check("orbx_pose_inertial_optimization_last_keyframe",
+                   orbx_pose_inertial_optimization_last_keyframe(orbx_shim::context(), E, V.xw.data(), V.obs.data(), V.isg.data(),
+                                                                 V.closePt.data(), &cam, Tcw, Tcb, Tbc, state, kf, preint, infoI,
+                                                                 infoG, infoA, bRecInit ? 1 : 0, outlier.data(), H15, &nRet,
+                                                                 iters));
+  write_back(pFrame, V, outlier, state, H15);
+  return nRet;
+}
+
+int Optimizer::PoseInertialOptimizationLastFrame(Frame* pFrame, bool bRecInit) {
+  VisualEdges V;
+  collect_visual_edges(pFrame, V);
+  const int E = (int)V.index.size();
+  Frame* pFp = pFrame->mpPrevFrame;
+  const VertexPose VP(pFrame), VPk(pFp);
+  double state[21], prev[21], preint[16], jac[45], bias[6], infoI[81], infoG[9], infoA[9], prior[21], priorH[225];
+  body_state(VP.estimate(), pFrame->mVw, pFrame->mImuBias, state);
+  body_state(VPk.estimate(), pFp->mVw, pFp->mImuBias, prev);
+  IMU::Preintegrated* pInt = pFrame->mpImuPreintegratedFrame;     // :8303
+  mat3_to(pInt->dR, preint);
+  for (int r = 0; r < 3; ++r) { preint[9 + r] = pInt->dV.at<float>(r); preint[12 + r] = pInt->dP.at<float>(r); }
+  preint[15] = pInt->dT;
+  mat3_to(pInt->JRg, jac); mat3_to(pInt->JVg, jac + 9); mat3_to(pInt->JVa, jac + 18); mat3_to(pInt->JPg, jac + 27); mat3_to(pInt->JPa, jac + 36);
+  const IMU::Bias b0 = pInt->GetOriginalBias();                   // the bias the deltas were integrated with (`b`, src/ImuTypes.cc:367)
+  bias[0] = b0.bwx; bias[1] = b0.bwy; bias[2] = b0.bwz; bias[3] = b0.bax; bias[4] = b0.bay; bias[5] = b0.baz;
+  information_matrices(pInt, infoI, infoG, infoA);
+  const ConstraintPoseImu* c = pFp->mpcpi;                        // EdgePriorPoseImu(pFp->mpcpi), :8345
+  if (!c) throw std::runtime_error("orbx: PoseInertialOptimizationLastFrame needs pFrame->mpPrevFrame->mpcpi");
+  for (int r = 0; r < 3; ++r) {
+    for (int k = 0; k < 3; ++k) prior[r * 3 + k] = c->Rwb(r, k);
+    prior[9 + r] = c->twb(r); prior[12 + r] = c->vwb(r); prior[15 + r] = c->bg(r); prior[18 + r] = c->ba(r);
+  }
+  for (int r = 0; r < 15; ++r)
+    for (int k = 0; k < 15; ++k) priorH[r * 15 + k] = c->H(r, k);
+  float Tcw[16], Tcb[16], Tbc[16];
+  pose_to_array(pFrame->mTcw, Tcw);
+  pose_to_array(pFrame->mImuCalib.Tcb, Tcb);
+  pose_to_array(pFrame->mImuCalib.Tbc, Tbc);
+  orbx_camera cam{pFrame->fx, pFrame->fy, pFrame->cx, pFrame->cy, pFrame->mbf, pFrame->mb};
+  std::vector<uint8_t> outlier(E > 0 ? E : 1, 0);
+  double H15[225];
+  int32_t nRet = 0, iters[4];
+  orbx_shim::check("orbx_pose_inertial_optimization_last_frame",
+                   orbx_pose_inertial_optimization_last_frame(orbx_shim::context(), E, V.xw.data(), V.obs.data(), V.isg.data(),
+                                                              V.closePt.data(), &cam, Tcw, Tcb, Tbc, state, prev, preint, jac, bias,
+                                                              infoI, infoG, infoA, prior, priorH, bRecInit ? 1 : 0, outlier.data(),
+                                                              H15, &nRet, iters));
+  write_back(pFrame, V, outlier, state, H15);
+  delete pFp->mpcpi;                                              // :8599-8600
+  pFp->mpcpi = NULL;
   return nRet;
 }
 

@@ -70,7 +70,7 @@ struct Calib { cv::Mat Tcb, Tbc; };
 class Preintegrated {
  public:
   cv::Mat GetDeltaRotation(const Bias& b); cv::Mat GetDeltaVelocity(const Bias& b); cv::Mat GetDeltaPosition(const Bias& b);
-  float dT; cv::Mat C;
+  Bias GetOriginalBias(); float dT; cv::Mat C, dR, dV, dP, JRg, JVg, JVa, JPg, JPa;
 };
 }  // namespace IMU
 class ImuCamPose {                                       // include/G2oTypes.h:58-103
@@ -83,6 +83,7 @@ class ConstraintPoseImu {                                // :704-749
  public:
   ConstraintPoseImu(const Eigen::Matrix3d& Rwb, const Eigen::Vector3d& twb, const Eigen::Vector3d& vwb, const Eigen::Vector3d& bg,
                     const Eigen::Vector3d& ba, const Matrix15d& H);
+  Eigen::Matrix3d Rwb; Eigen::Vector3d twb, vwb, bg, ba; Matrix15d H;
 };
 namespace Converter { cv::Mat toCvMat(const Eigen::Matrix3d&); cv::Mat toCvMat(const Eigen::Vector3d&); }
 class ORBVocabulary;   // DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> in the reference (include/ORBVocabulary.h:36)
@@ -117,7 +118,7 @@ class Frame {
   void SetPose(cv::Mat Tcw); void ComputeStereoMatches(); void ComputeBoW(); void UndistortKeyPoints();
   int isInFrustumBatch(const std::vector<MapPoint*>& vpMP, float viewingCosLimit);   // added member
   void SetImuPoseVelocity(const cv::Mat& Rwb, const cv::Mat& twb, const cv::Mat& Vwb);
-  KeyFrame* mpLastKeyFrame; IMU::Preintegrated* mpImuPreintegrated; IMU::Calib mImuCalib; IMU::Bias mImuBias; cv::Mat mVw;
+  KeyFrame* mpLastKeyFrame; Frame* mpPrevFrame; IMU::Preintegrated *mpImuPreintegrated, *mpImuPreintegratedFrame; IMU::Calib mImuCalib; IMU::Bias mImuBias; cv::Mat mVw;
   ConstraintPoseImu* mpcpi; GeometricCamera* mpCamera;
   cv::Mat mDistCoef, mRcw, mtcw, mOw; int mnScaleLevels; float mfLogScaleFactor;
   ORBVocabulary* mpORBvocabulary; DBoW2::BowVector mBowVec; DBoW2::FeatureVector mFeatVec; int Nleft;
@@ -164,5 +165,6 @@ class Optimizer {
   static void LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, int& num_fixedKF);
   static int PoseOptimization(Frame* pFrame);
   static int PoseInertialOptimizationLastKeyFrame(Frame* pFrame, bool bRecInit = false);
+  static int PoseInertialOptimizationLastFrame(Frame* pFrame, bool bRecInit = false);
 };
 }  // namespace ORB_SLAM3

@@ -126,6 +126,12 @@ def main():
               i["infoG"], i["infoA"])
         add("Optimizer::PoseInertialOptimizationLastKeyFrame, %d edges" % E, "src/Optimizer.cc:7665",
             lambda: opt.PoseInertialOptimizationLastKeyFrame(*a6), lambda: oracle.pose_inertial_optimization_last_keyframe(i, cam))
+    for E in (300, 1000):
+        j = sc.inertial_lf_scenario(E, E, 0.6)
+        a7 = (j["xw"], j["obs"], j["isg"], j["close"], cam, j["Tcw"], j["Tcb"], j["Tbc"], j["state"], j["prev"], j["preint"],
+              j["preint_jac"], j["preint_bias"], j["infoI"], j["infoG"], j["infoA"], j["prior_state"], j["prior_H"])
+        add("Optimizer::PoseInertialOptimizationLastFrame, %d edges" % E, "src/Optimizer.cc:8068",
+            lambda: opt.PoseInertialOptimizationLastFrame(*a7), lambda: oracle.pose_inertial_optimization_last_frame(j, cam))
     out = ["# Single-call latency through the C ABI vs the CPU oracle (%s)" % tag, "",
            "Host buffers in, host buffers out, median of repeated synchronous calls (p95 in brackets); CPU = the oracle on "
            "one thread of the same host (%d cores).  This is the call-level view of BASELINE.json configs 1-4; the "
