@@ -473,14 +473,15 @@ __device__ bool ldlt_solve_smem(double* A, const double* b, double* x) {
   bool positive = true;
   __syncwarp();
   for (int k = 0; k < N; ++k) {
-    double v = (row && lane >= k) ? fabs(A[lane * LD + lane]) : -1.0;
-    int p = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(FULL, v, o);
-      const int op = __shfl_xor_sync(FULL, p, o);
-      if (ov > v || (ov == v && op < p)) { v = ov; p = op; }
-    }
+    // first largest |diagonal| among rows >= k: |x| bit patterns order like unsigned integers, so two 32-bit warp
+    // maxima (high word, then low word among the lanes that tie on the high word) and a find-first-set do it
+    const bool cand = row && lane >= k;
+    const unsigned long long key = cand ? (unsigned long long)__double_as_longlong(fabs(A[lane * LD + lane])) : 0ull;
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_max_sync(FULL, hi);
+    const unsigned mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+    const unsigned win = __ballot_sync(FULL, cand && hi == mhi && lo == mlo);
+    const int p = __ffs(win) - 1;
     if (p != k) {                                 // warp-uniform
       if (row) { const double t = A[k * LD + lane]; A[k * LD + lane] = A[p * LD + lane]; A[p * LD + lane] = t; }
       __syncwarp();
@@ -498,7 +499,15 @@ __device__ bool ldlt_solve_smem(double* A, const double* b, double* x) {
     __syncwarp();
     if (below) {
       const double lid = lik * d;
-      for (int j = k + 1; j <= lane; ++j) {
+      int j = k + 1;
+      for (; j + 3 <= lane; j += 4) {             // loads first: the stores below cannot alias them, the compiler cannot know
+        const double a0 = A[lane * LD + j], a1 = A[lane * LD + j + 1], a2 = A[lane * LD + j + 2], a3 = A[lane * LD + j + 3];
+        const double c0 = A[j * LD + k], c1 = A[(j + 1) * LD + k], c2 = A[(j + 2) * LD + k], c3 = A[(j + 3) * LD + k];
+        const double n0 = a0 - lid * c0, n1 = a1 - lid * c1, n2 = a2 - lid * c2, n3 = a3 - lid * c3;
+        A[lane * LD + j] = n0; A[lane * LD + j + 1] = n1; A[lane * LD + j + 2] = n2; A[lane * LD + j + 3] = n3;
+        A[j * LD + lane] = n0; A[(j + 1) * LD + lane] = n1; A[(j + 2) * LD + lane] = n2; A[(j + 3) * LD + lane] = n3;
+      }
+      for (; j <= lane; ++j) {
         const double nv = A[lane * LD + j] - lid * A[j * LD + k];
         A[lane * LD + j] = nv;
         A[j * LD + lane] = nv;
@@ -2070,7 +2079,9 @@ struct PlfArgs {
   double* H15;
   int* nRet;
   int* iters;
+  unsigned long long* prof;   // [8] optional per-phase nanosecond totals (ORBX_PIO_PROFILE=1), else null
 };
+#define PLF_TICK(n) do { if (A.prof && tid == 0) { const unsigned long long t1_ = lbc_now(); A.prof[n] += t1_ - t0; t0 = t1_; } } while (0)
 struct PlfShared {
   double cur[21], prev[21], Rcw[9], tcw[3];
   double H[30 * PLF_LD], b[30], x[30], tot[36];
@@ -2344,6 +2355,7 @@ __global__ void __launch_bounds__(PLF_NT) pose_inertial_lf_kernel(const PlfArgs*
   const float chi2Mono[4] = {5.991f, 5.991f, 5.991f, 5.991f}, chi2Stereo[4] = {15.6f, 9.8f, 7.815f, 7.815f};
   bool robust = true;
   int nBad = 0, nInliers = 0;
+  unsigned long long t0 = A.prof ? lbc_now() : 0ull;
   for (int round = 0; round < 4; ++round) {
     int cj = 0;
     bool ok = true;
@@ -2377,7 +2389,9 @@ __global__ void __launch_bounds__(PLF_NT) pose_inertial_lf_kernel(const PlfArgs*
             }
           }
         }
+      PLF_TICK(0);
       block_partials<27>(acc, S.red);
+      PLF_TICK(1);
       if (tid < 27) {
         double s = 0;
         for (int w = 0; w < 8; ++w) s += S.red[w * 27 + tid];
@@ -2393,11 +2407,14 @@ __global__ void __launch_bounds__(PLF_NT) pose_inertial_lf_kernel(const PlfArgs*
         S.b[tid - 36] = S.tot[21 + tid - 36];
       }
       __syncthreads();
+      PLF_TICK(2);
       plf_assemble(A, S, false);
+      PLF_TICK(3);
       if (tid < 32) {
         const bool okSolve = ldlt_solve_smem<30, PLF_LD>(S.H, S.b, S.x);
         if (tid == 0) S.ok = okSolve ? 1 : 0;
       }
+      PLF_TICK(4);
       __syncthreads();
       if (tid == 0) {
         d_body_update(S.cur, S.itsCur, S.x);
@@ -2412,6 +2429,7 @@ __global__ void __launch_bounds__(PLF_NT) pose_inertial_lf_kernel(const PlfArgs*
         d_body_update(S.prev, S.itsPrev, S.x + 15);
       }
       __syncthreads();
+      PLF_TICK(5);
       ok = S.ok != 0;
       ++cj;
     }
@@ -2464,6 +2482,7 @@ __global__ void __launch_bounds__(PLF_NT) pose_inertial_lf_kernel(const PlfArgs*
     nBad = (int)cnt[0];
   }
   __syncthreads();
+  PLF_TICK(6);
   if (tid < 21) A.outState[tid] = S.cur[tid];
   if (tid == 0) *A.nRet = E - nBad;
   // ---- 30x30 Hessian in the reference's order (previous frame 0-14, frame 15-29) at the final estimates ----
@@ -2528,6 +2547,7 @@ __global__ void __launch_bounds__(PLF_NT) pose_inertial_lf_kernel(const PlfArgs*
     for (int k = 0; k < 15; ++k) s += S.mT[i * 15 + k] * S.H[k * PLF_LD + 15 + j];
     A.H15[tid] = S.H[(15 + i) * PLF_LD + 15 + j] - s;
   }
+  PLF_TICK(7);
 }
 
 // =====================================================================================
@@ -2876,6 +2896,14 @@ int orbx_pose_inertial_optimization_last_frame(orbx_ctx* ctx, int n_edges, const
   int* d_res = S.alloc<int>(5);
   A.nRet = d_res;
   A.iters = d_res + 1;
+  A.prof = nullptr;
+  {
+    const char* pe = getenv("ORBX_PIO_PROFILE");
+    if (pe && pe[0] == '1') {
+      A.prof = S.alloc<unsigned long long>(8);
+      if (A.prof) cudaMemsetAsync(A.prof, 0, 8 * sizeof(unsigned long long), st);
+    }
+  }
   PlfArgs* dA = S.upload(&A, 1);
   if (S.failed) return ORBX_ECUDA;
   pose_inertial_lf_kernel<<<1, PLF_NT, 0, st>>>(dA);
@@ -2888,6 +2916,12 @@ int orbx_pose_inertial_optimization_last_frame(orbx_ctx* ctx, int n_edges, const
   if (n_edges > 0) S.download(outlier, (const uint8_t*)A.outlier, (size_t)n_edges);
   int rc = S.finish();
   if (rc != ORBX_OK) return rc;
+  if (A.prof) {
+    unsigned long long hp[8];
+    if (cudaMemcpy(hp, A.prof, sizeof hp, cudaMemcpyDeviceToHost) == cudaSuccess)
+      fprintf(stderr, "[orbx pio-lf] us: edges+inertial %.1f partials %.1f fill %.1f assemble %.1f solve %.1f update %.1f | classify/tail %.1f final-H+marginalise %.1f\n",
+              hp[0] / 1e3, hp[1] / 1e3, hp[2] / 1e3, hp[3] / 1e3, hp[4] / 1e3, hp[5] / 1e3, hp[6] / 1e3, hp[7] / 1e3);
+  }
   *n_ret = res[0];
   for (int i = 0; i < 4; ++i) iters[i] = res[1 + i];
   return ORBX_OK;
