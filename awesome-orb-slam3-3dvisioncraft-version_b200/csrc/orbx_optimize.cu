@@ -2335,7 +2335,7 @@ __device__ void plf_jacobi15(PlfShared& S) {
   }
 }
 
-__global__ void __launch_bounds__(PLF_NT) pose_inertial_lf_kernel(const PlfArgs* __restrict__ args) {
+__global__ void __launch_bounds__(PLF_NT, 2) pose_inertial_lf_kernel(const PlfArgs* __restrict__ args) {
   const PlfArgs& A = args[blockIdx.x];
   __shared__ PlfShared S;
   const int tid = threadIdx.x, E = A.E;
@@ -2924,6 +2924,89 @@ int orbx_pose_inertial_optimization_last_frame(orbx_ctx* ctx, int n_edges, const
   }
   *n_ret = res[0];
   for (int i = 0; i < 4; ++i) iters[i] = res[1 + i];
+  return ORBX_OK;
+}
+
+// Many-problem form of orbx_pose_inertial_optimization_last_frame (one CTA per problem, one launch): P independent streams'
+// frames.  edge_ofs[P+1] delimits each problem's slice of xw/obs/inv_sigma2/close_pt/outlier; every other per-problem array
+// is the single-call argument with a leading [P] dimension; Tcb/Tbc/cam are shared.
+int orbx_pose_inertial_optimization_last_frame_batch(orbx_ctx* ctx, int P, const int32_t* edge_ofs, const float* xw, const float* obs,
+                                                     const float* inv_sigma2, const uint8_t* close_pt, const orbx_camera* cam,
+                                                     const float* Tcw, const float* Tcb, const float* Tbc, double* state,
+                                                     const double* prev_state, const double* preint, const double* preint_jac,
+                                                     const double* preint_bias, const double* info_inertial, const double* info_gyro,
+                                                     const double* info_acc, const double* prior_state, const double* prior_H,
+                                                     int rec_init, uint8_t* outlier, double* H15, int32_t* n_ret, int32_t* iters) {
+  if (!ctx || P < 0 || !edge_ofs || !cam || !Tcw || !Tcb || !Tbc || !state || !prev_state || !preint || !preint_jac || !preint_bias ||
+      !info_inertial || !info_gyro || !info_acc || !prior_state || !prior_H || !H15 || !n_ret || !iters)
+    return ORBX_EINVAL;
+  if (P == 0) return ORBX_OK;
+  const int total = edge_ofs[P];
+  if (edge_ofs[0] != 0 || total < 0) return ORBX_EINVAL;
+  for (int p = 0; p < P; ++p) if (edge_ofs[p + 1] < edge_ofs[p]) return ORBX_EINVAL;
+  if (total > 0 && (!xw || !obs || !inv_sigma2 || !close_pt || !outlier)) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevScope S(ctx, st);
+  const float* d_xw = S.upload(xw, (size_t)3 * total);
+  const float* d_obs = S.upload(obs, (size_t)3 * total);
+  const float* d_isg = S.upload(inv_sigma2, total);
+  const uint8_t* d_close = S.upload(close_pt, total);
+  uint8_t* d_outlier = S.alloc<uint8_t>(total);
+  double* d_err = S.alloc<double>((size_t)3 * total);
+  double* d_state = S.alloc<double>((size_t)21 * P);
+  double* d_H = S.alloc<double>((size_t)225 * P);
+  int* d_res = S.alloc<int>((size_t)5 * P);
+  std::vector<PlfArgs> args(P);
+  for (int p = 0; p < P; ++p) {
+    PlfArgs& A = args[p];
+    const int o = edge_ofs[p];
+    A.E = edge_ofs[p + 1] - o;
+    A.xw = d_xw + 3 * (size_t)o; A.obs = d_obs + 3 * (size_t)o; A.invSigma2 = d_isg + o; A.closePt = d_close + o;
+    A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
+    const float* T = Tcw + 16 * (size_t)p;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) { A.Rcb[i * 3 + j] = Tcb[i * 4 + j]; A.Rbc[j * 3 + i] = Tcb[i * 4 + j]; A.Rcw0[i * 3 + j] = T[i * 4 + j]; }
+      A.tcb[i] = Tcb[i * 4 + 3]; A.tbc[i] = Tbc[i * 4 + 3]; A.tcw0[i] = T[i * 4 + 3];
+    }
+    memcpy(A.state, state + 21 * (size_t)p, sizeof A.state);
+    memcpy(A.prev, prev_state + 21 * (size_t)p, sizeof A.prev);
+    const double* pr = preint + 16 * (size_t)p;
+    memcpy(A.dR0, pr, 72); memcpy(A.dV0, pr + 9, 24); memcpy(A.dP0, pr + 12, 24);
+    A.dt = pr[15];
+    const double* pj = preint_jac + 45 * (size_t)p;
+    memcpy(A.JRg, pj, 72); memcpy(A.JVg, pj + 9, 72); memcpy(A.JVa, pj + 18, 72); memcpy(A.JPg, pj + 27, 72); memcpy(A.JPa, pj + 36, 72);
+    memcpy(A.bpre, preint_bias + 6 * (size_t)p, 48);
+    memcpy(A.infoI, info_inertial + 81 * (size_t)p, sizeof A.infoI);
+    memcpy(A.infoG, info_gyro + 9 * (size_t)p, sizeof A.infoG);
+    memcpy(A.infoA, info_acc + 9 * (size_t)p, sizeof A.infoA);
+    memcpy(A.prior, prior_state + 21 * (size_t)p, sizeof A.prior);
+    memcpy(A.Hp, prior_H + 225 * (size_t)p, sizeof A.Hp);
+    A.recInit = rec_init;
+    A.outlier = d_outlier + o;
+    A.err = d_err + 3 * (size_t)o;
+    A.outState = d_state + 21 * (size_t)p;
+    A.H15 = d_H + 225 * (size_t)p;
+    A.nRet = d_res + 5 * (size_t)p;
+    A.iters = d_res + 5 * (size_t)p + 1;
+    A.prof = nullptr;
+  }
+  PlfArgs* dA = S.upload(args.data(), (size_t)P);
+  if (S.failed) return ORBX_ECUDA;
+  pose_inertial_lf_kernel<<<P, PLF_NT, 0, st>>>(dA);
+  ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
+  std::vector<int32_t> res((size_t)5 * P, 0);
+  S.download(state, (const double*)d_state, (size_t)21 * P);
+  S.download(H15, (const double*)d_H, (size_t)225 * P);
+  S.download(res.data(), (const int32_t*)d_res, (size_t)5 * P);
+  if (total > 0) S.download(outlier, (const uint8_t*)d_outlier, (size_t)total);
+  int rc = S.finish();
+  if (rc != ORBX_OK) return rc;
+  for (int p = 0; p < P; ++p) {
+    n_ret[p] = res[5 * (size_t)p];
+    for (int i = 0; i < 4; ++i) iters[4 * (size_t)p + i] = res[5 * (size_t)p + 1 + i];
+  }
   return ORBX_OK;
 }
 

@@ -423,6 +423,19 @@ int orbx_pose_inertial_optimization_last_frame(
     const double *prior_H, int rec_init, uint8_t *outlier, double *H15, int32_t *n_ret,
     int32_t *iters);
 
+/* Many-stream form: P independent frames in one launch (one CTA per problem).  edge_ofs[P+1] delimits
+ * each problem's slice of xw/obs/inv_sigma2/close_pt/outlier; every other per-problem argument is the
+ * single-call argument with a leading [P] dimension (Tcw [P][16], state [P][21], ... H15 [P][225],
+ * n_ret [P], iters [P][4]); cam, Tcb and Tbc are shared by the rig.  Results are identical to P single calls. */
+int orbx_pose_inertial_optimization_last_frame_batch(
+    orbx_ctx *ctx, int P, const int32_t *edge_ofs, const float *xw, const float *obs,
+    const float *inv_sigma2, const uint8_t *close_pt, const orbx_camera *cam, const float *Tcw,
+    const float *Tcb, const float *Tbc, double *state, const double *prev_state,
+    const double *preint, const double *preint_jac, const double *preint_bias,
+    const double *info_inertial, const double *info_gyro, const double *info_acc,
+    const double *prior_state, const double *prior_H, int rec_init, uint8_t *outlier, double *H15,
+    int32_t *n_ret, int32_t *iters);
+
 /* ====================================================================================
  * Many-stream tracking replay: S independent stereo streams
  * advance one frame per call, everything device-resident between stages:

@@ -235,3 +235,19 @@ def test_pose_inertial_optimization_last_frame_edge_cases(ctx, ork):
     assert np.array_equal(g["iters"], r["iters"]) and np.array_equal(g["outlier"], r["outlier"])
     assert np.abs(g["state"] - r["state"]).max() < 1e-8
     assert np.abs(g["H"] - r["H"]).max() <= 1e-8 * np.abs(r["H"]).max()
+
+
+def test_pose_inertial_last_frame_batch_equals_single_calls(ctx, ork):
+    """Many-stream launch (one CTA per problem): bit-identical to the single calls, ragged sizes including an empty problem."""
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    sizes = [300, 0, 57, 1000, 150, 24, 5, 411] * 5
+    probs = [sc.inertial_lf_scenario(9000 + i, E, 0.6) for i, E in enumerate(sizes)]
+    got = opt.PoseInertialOptimizationLastFrameBatch(probs, cam)
+    for i, (s, g) in enumerate(zip(probs, got)):
+        r = _inertial_lf_call(opt, s, cam)
+        assert np.array_equal(g["state"], r["state"]) and np.array_equal(g["H"], r["H"]), i
+        assert np.array_equal(g["outlier"], r["outlier"]) and g["n"] == r["n"] and np.array_equal(g["iters"], r["iters"])
+    o = ork.pose_inertial_optimization_last_frame(probs[3], cam)
+    assert np.abs(got[3]["state"] - o["state"]).max() < 1e-9
