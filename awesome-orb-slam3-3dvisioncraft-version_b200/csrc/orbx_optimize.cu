@@ -1824,7 +1824,7 @@ __device__ void pio_inertial(const PioArgs& A, PioShared& S, bool withError) {
     }
 }
 
-__global__ void __launch_bounds__(PIO_NT) pose_inertial_kernel(const PioArgs* __restrict__ args) {
+__global__ void __launch_bounds__(PIO_NT, 2) pose_inertial_kernel(const PioArgs* __restrict__ args) {
   const PioArgs& A = args[blockIdx.x];
   __shared__ PioShared S;
   const int tid = threadIdx.x, E = A.E;
@@ -2800,131 +2800,90 @@ int orbx_local_ba(orbx_ctx* ctx, int n_kf, float* kf_Tcw, const uint8_t* kf_fixe
   return ORBX_OK;
 }
 
+// Many-problem form (one CTA per problem, one launch); the single call below is the P = 1 case.
+int orbx_pose_inertial_optimization_last_keyframe_batch(orbx_ctx* ctx, int P, const int32_t* edge_ofs, const float* xw, const float* obs,
+                                                        const float* inv_sigma2, const uint8_t* close_pt, const orbx_camera* cam,
+                                                        const float* Tcw, const float* Tcb, const float* Tbc, double* state,
+                                                        const double* kf_state, const double* preint, const double* info_inertial,
+                                                        const double* info_gyro, const double* info_acc, int rec_init, uint8_t* outlier,
+                                                        double* H15, int32_t* n_ret, int32_t* iters) {
+  if (!ctx || P < 0 || !edge_ofs || !cam || !Tcw || !Tcb || !Tbc || !state || !kf_state || !preint || !info_inertial || !info_gyro ||
+      !info_acc || !H15 || !n_ret || !iters)
+    return ORBX_EINVAL;
+  if (P == 0) return ORBX_OK;
+  const int total = edge_ofs[P];
+  if (edge_ofs[0] != 0 || total < 0) return ORBX_EINVAL;
+  for (int p = 0; p < P; ++p) if (edge_ofs[p + 1] < edge_ofs[p]) return ORBX_EINVAL;
+  if (total > 0 && (!xw || !obs || !inv_sigma2 || !close_pt || !outlier)) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevScope S(ctx, st);
+  const float* d_xw = S.upload(xw, (size_t)3 * total);
+  const float* d_obs = S.upload(obs, (size_t)3 * total);
+  const float* d_isg = S.upload(inv_sigma2, total);
+  const uint8_t* d_close = S.upload(close_pt, total);
+  uint8_t* d_outlier = S.alloc<uint8_t>(total);
+  double* d_err = S.alloc<double>((size_t)3 * total);
+  double* d_state = S.alloc<double>((size_t)21 * P);
+  double* d_H = S.alloc<double>((size_t)225 * P);
+  int* d_res = S.alloc<int>((size_t)5 * P);
+  std::vector<PioArgs> args(P);
+  for (int p = 0; p < P; ++p) {
+    PioArgs& A = args[p];
+    const int o = edge_ofs[p];
+    A.E = edge_ofs[p + 1] - o;
+    A.xw = d_xw + 3 * (size_t)o; A.obs = d_obs + 3 * (size_t)o; A.invSigma2 = d_isg + o; A.closePt = d_close + o;
+    A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
+    const float* T = Tcw + 16 * (size_t)p;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) { A.Rcb[i * 3 + j] = Tcb[i * 4 + j]; A.Rbc[j * 3 + i] = Tcb[i * 4 + j]; A.Rcw0[i * 3 + j] = T[i * 4 + j]; }
+      A.tcb[i] = Tcb[i * 4 + 3]; A.tbc[i] = Tbc[i * 4 + 3]; A.tcw0[i] = T[i * 4 + 3];
+    }
+    memcpy(A.state, state + 21 * (size_t)p, sizeof A.state);
+    memcpy(A.kf, kf_state + 21 * (size_t)p, sizeof A.kf);
+    const double* pr = preint + 16 * (size_t)p;
+    memcpy(A.dR, pr, 72); memcpy(A.dV, pr + 9, 24); memcpy(A.dP, pr + 12, 24);
+    A.dt = pr[15];
+    memcpy(A.infoI, info_inertial + 81 * (size_t)p, sizeof A.infoI);
+    memcpy(A.infoG, info_gyro + 9 * (size_t)p, sizeof A.infoG);
+    memcpy(A.infoA, info_acc + 9 * (size_t)p, sizeof A.infoA);
+    A.recInit = rec_init;
+    A.outlier = d_outlier + o;
+    A.err = d_err + 3 * (size_t)o;
+    A.outState = d_state + 21 * (size_t)p;
+    A.H15 = d_H + 225 * (size_t)p;
+    A.nRet = d_res + 5 * (size_t)p;
+    A.iters = d_res + 5 * (size_t)p + 1;
+  }
+  PioArgs* dA = S.upload(args.data(), (size_t)P);
+  if (S.failed) return ORBX_ECUDA;
+  pose_inertial_kernel<<<P, PIO_NT, 0, st>>>(dA);
+  ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
+  std::vector<int32_t> res((size_t)5 * P, 0);
+  S.download(state, (const double*)d_state, (size_t)21 * P);
+  S.download(H15, (const double*)d_H, (size_t)225 * P);
+  S.download(res.data(), (const int32_t*)d_res, (size_t)5 * P);
+  if (total > 0) S.download(outlier, (const uint8_t*)d_outlier, (size_t)total);
+  int rc = S.finish();
+  if (rc != ORBX_OK) return rc;
+  for (int p = 0; p < P; ++p) {
+    n_ret[p] = res[5 * (size_t)p];
+    for (int i = 0; i < 4; ++i) iters[4 * (size_t)p + i] = res[5 * (size_t)p + 1 + i];
+  }
+  return ORBX_OK;
+}
+
 int orbx_pose_inertial_optimization_last_keyframe(orbx_ctx* ctx, int n_edges, const float* xw, const float* obs, const float* inv_sigma2,
                                                   const uint8_t* close_pt, const orbx_camera* cam, const float* Tcw, const float* Tcb,
                                                   const float* Tbc, double* state, const double* kf_state, const double* preint,
                                                   const double* info_inertial, const double* info_gyro, const double* info_acc,
                                                   int rec_init, uint8_t* outlier, double* H15, int32_t* n_ret, int32_t* iters) {
-  if (!ctx || n_edges < 0 || !cam || !Tcw || !Tcb || !Tbc || !state || !kf_state || !preint || !info_inertial || !info_gyro ||
-      !info_acc || !H15 || !n_ret || !iters)
-    return ORBX_EINVAL;
-  if (n_edges > 0 && (!xw || !obs || !inv_sigma2 || !close_pt || !outlier)) return ORBX_EINVAL;
-  ORBX_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  DevScope S(ctx, st);
-  PioArgs A;
-  A.E = n_edges;
-  A.xw = S.upload(xw, (size_t)3 * n_edges);
-  A.obs = S.upload(obs, (size_t)3 * n_edges);
-  A.invSigma2 = S.upload(inv_sigma2, n_edges);
-  A.closePt = S.upload(close_pt, n_edges);
-  A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) { A.Rcb[i * 3 + j] = Tcb[i * 4 + j]; A.Rbc[j * 3 + i] = Tcb[i * 4 + j]; A.Rcw0[i * 3 + j] = Tcw[i * 4 + j]; }
-    A.tcb[i] = Tcb[i * 4 + 3]; A.tbc[i] = Tbc[i * 4 + 3]; A.tcw0[i] = Tcw[i * 4 + 3];
-  }
-  memcpy(A.state, state, sizeof A.state);
-  memcpy(A.kf, kf_state, sizeof A.kf);
-  memcpy(A.dR, preint, sizeof(double) * 9); memcpy(A.dV, preint + 9, 24); memcpy(A.dP, preint + 12, 24);
-  A.dt = preint[15];
-  memcpy(A.infoI, info_inertial, sizeof A.infoI); memcpy(A.infoG, info_gyro, sizeof A.infoG); memcpy(A.infoA, info_acc, sizeof A.infoA);
-  A.recInit = rec_init;
-  A.outlier = S.alloc<uint8_t>(n_edges);
-  A.err = S.alloc<double>((size_t)3 * n_edges);
-  A.outState = S.alloc<double>(21);
-  A.H15 = S.alloc<double>(225);
-  int* d_res = S.alloc<int>(5);
-  A.nRet = d_res;
-  A.iters = d_res + 1;
-  PioArgs* dA = S.upload(&A, 1);
-  if (S.failed) return ORBX_ECUDA;
-  pose_inertial_kernel<<<1, PIO_NT, 0, st>>>(dA);
-  ORBX_LAUNCH(ctx);
-  ORBX_CUDA(cudaGetLastError());
-  int32_t res[5] = {0, 0, 0, 0, 0};
-  S.download(state, (const double*)A.outState, (size_t)21);
-  S.download(H15, (const double*)A.H15, (size_t)225);
-  S.download(res, (const int32_t*)d_res, (size_t)5);
-  if (n_edges > 0) S.download(outlier, (const uint8_t*)A.outlier, (size_t)n_edges);
-  int rc = S.finish();
-  if (rc != ORBX_OK) return rc;
-  *n_ret = res[0];
-  for (int i = 0; i < 4; ++i) iters[i] = res[1 + i];
-  return ORBX_OK;
-}
-
-int orbx_pose_inertial_optimization_last_frame(orbx_ctx* ctx, int n_edges, const float* xw, const float* obs, const float* inv_sigma2,
-                                               const uint8_t* close_pt, const orbx_camera* cam, const float* Tcw, const float* Tcb,
-                                               const float* Tbc, double* state, const double* prev_state, const double* preint,
-                                               const double* preint_jac, const double* preint_bias, const double* info_inertial,
-                                               const double* info_gyro, const double* info_acc, const double* prior_state,
-                                               const double* prior_H, int rec_init, uint8_t* outlier, double* H15, int32_t* n_ret,
-                                               int32_t* iters) {
-  if (!ctx || n_edges < 0 || !cam || !Tcw || !Tcb || !Tbc || !state || !prev_state || !preint || !preint_jac || !preint_bias ||
-      !info_inertial || !info_gyro || !info_acc || !prior_state || !prior_H || !H15 || !n_ret || !iters)
-    return ORBX_EINVAL;
-  if (n_edges > 0 && (!xw || !obs || !inv_sigma2 || !close_pt || !outlier)) return ORBX_EINVAL;
-  ORBX_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  DevScope S(ctx, st);
-  PlfArgs A;
-  A.E = n_edges;
-  A.xw = S.upload(xw, (size_t)3 * n_edges);
-  A.obs = S.upload(obs, (size_t)3 * n_edges);
-  A.invSigma2 = S.upload(inv_sigma2, n_edges);
-  A.closePt = S.upload(close_pt, n_edges);
-  A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.bf = cam->bf;
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) { A.Rcb[i * 3 + j] = Tcb[i * 4 + j]; A.Rbc[j * 3 + i] = Tcb[i * 4 + j]; A.Rcw0[i * 3 + j] = Tcw[i * 4 + j]; }
-    A.tcb[i] = Tcb[i * 4 + 3]; A.tbc[i] = Tbc[i * 4 + 3]; A.tcw0[i] = Tcw[i * 4 + 3];
-  }
-  memcpy(A.state, state, sizeof A.state);
-  memcpy(A.prev, prev_state, sizeof A.prev);
-  memcpy(A.dR0, preint, 72); memcpy(A.dV0, preint + 9, 24); memcpy(A.dP0, preint + 12, 24);
-  A.dt = preint[15];
-  memcpy(A.JRg, preint_jac, 72); memcpy(A.JVg, preint_jac + 9, 72); memcpy(A.JVa, preint_jac + 18, 72);
-  memcpy(A.JPg, preint_jac + 27, 72); memcpy(A.JPa, preint_jac + 36, 72);
-  memcpy(A.bpre, preint_bias, 48);
-  memcpy(A.infoI, info_inertial, sizeof A.infoI); memcpy(A.infoG, info_gyro, sizeof A.infoG); memcpy(A.infoA, info_acc, sizeof A.infoA);
-  memcpy(A.prior, prior_state, sizeof A.prior);
-  memcpy(A.Hp, prior_H, sizeof A.Hp);
-  A.recInit = rec_init;
-  A.outlier = S.alloc<uint8_t>(n_edges);
-  A.err = S.alloc<double>((size_t)3 * n_edges);
-  A.outState = S.alloc<double>(21);
-  A.H15 = S.alloc<double>(225);
-  int* d_res = S.alloc<int>(5);
-  A.nRet = d_res;
-  A.iters = d_res + 1;
-  A.prof = nullptr;
-  {
-    const char* pe = getenv("ORBX_PIO_PROFILE");
-    if (pe && pe[0] == '1') {
-      A.prof = S.alloc<unsigned long long>(8);
-      if (A.prof) cudaMemsetAsync(A.prof, 0, 8 * sizeof(unsigned long long), st);
-    }
-  }
-  PlfArgs* dA = S.upload(&A, 1);
-  if (S.failed) return ORBX_ECUDA;
-  pose_inertial_lf_kernel<<<1, PLF_NT, 0, st>>>(dA);
-  ORBX_LAUNCH(ctx);
-  ORBX_CUDA(cudaGetLastError());
-  int32_t res[5] = {0, 0, 0, 0, 0};
-  S.download(state, (const double*)A.outState, (size_t)21);
-  S.download(H15, (const double*)A.H15, (size_t)225);
-  S.download(res, (const int32_t*)d_res, (size_t)5);
-  if (n_edges > 0) S.download(outlier, (const uint8_t*)A.outlier, (size_t)n_edges);
-  int rc = S.finish();
-  if (rc != ORBX_OK) return rc;
-  if (A.prof) {
-    unsigned long long hp[8];
-    if (cudaMemcpy(hp, A.prof, sizeof hp, cudaMemcpyDeviceToHost) == cudaSuccess)
-      fprintf(stderr, "[orbx pio-lf] us: edges+inertial %.1f partials %.1f fill %.1f assemble %.1f solve %.1f update %.1f | classify/tail %.1f final-H+marginalise %.1f\n",
-              hp[0] / 1e3, hp[1] / 1e3, hp[2] / 1e3, hp[3] / 1e3, hp[4] / 1e3, hp[5] / 1e3, hp[6] / 1e3, hp[7] / 1e3);
-  }
-  *n_ret = res[0];
-  for (int i = 0; i < 4; ++i) iters[i] = res[1 + i];
-  return ORBX_OK;
+  if (n_edges < 0) return ORBX_EINVAL;
+  const int32_t ofs[2] = {0, n_edges};
+  return orbx_pose_inertial_optimization_last_keyframe_batch(ctx, 1, ofs, xw, obs, inv_sigma2, close_pt, cam, Tcw, Tcb, Tbc, state, kf_state,
+                                                             preint, info_inertial, info_gyro, info_acc, rec_init, outlier, H15, n_ret,
+                                                             iters);
 }
 
 // Many-problem form of orbx_pose_inertial_optimization_last_frame (one CTA per problem, one launch): P independent streams'
@@ -2991,6 +2950,13 @@ int orbx_pose_inertial_optimization_last_frame_batch(orbx_ctx* ctx, int P, const
     A.iters = d_res + 5 * (size_t)p + 1;
     A.prof = nullptr;
   }
+  {
+    const char* pe = getenv("ORBX_PIO_PROFILE");                   // phase timers of problem 0 (single calls)
+    if (pe && pe[0] == '1' && P == 1) {
+      args[0].prof = S.alloc<unsigned long long>(8);
+      if (args[0].prof) cudaMemsetAsync(args[0].prof, 0, 8 * sizeof(unsigned long long), st);
+    }
+  }
   PlfArgs* dA = S.upload(args.data(), (size_t)P);
   if (S.failed) return ORBX_ECUDA;
   pose_inertial_lf_kernel<<<P, PLF_NT, 0, st>>>(dA);
@@ -3003,11 +2969,31 @@ int orbx_pose_inertial_optimization_last_frame_batch(orbx_ctx* ctx, int P, const
   if (total > 0) S.download(outlier, (const uint8_t*)d_outlier, (size_t)total);
   int rc = S.finish();
   if (rc != ORBX_OK) return rc;
+  if (args[0].prof) {
+    unsigned long long hp[8];
+    if (cudaMemcpy(hp, args[0].prof, sizeof hp, cudaMemcpyDeviceToHost) == cudaSuccess)
+      fprintf(stderr, "[orbx pio-lf] us: edges+inertial %.1f partials %.1f fill %.1f assemble %.1f solve %.1f update %.1f | classify/tail %.1f final-H+marginalise %.1f\n",
+              hp[0] / 1e3, hp[1] / 1e3, hp[2] / 1e3, hp[3] / 1e3, hp[4] / 1e3, hp[5] / 1e3, hp[6] / 1e3, hp[7] / 1e3);
+  }
   for (int p = 0; p < P; ++p) {
     n_ret[p] = res[5 * (size_t)p];
     for (int i = 0; i < 4; ++i) iters[4 * (size_t)p + i] = res[5 * (size_t)p + 1 + i];
   }
   return ORBX_OK;
+}
+
+int orbx_pose_inertial_optimization_last_frame(orbx_ctx* ctx, int n_edges, const float* xw, const float* obs, const float* inv_sigma2,
+                                               const uint8_t* close_pt, const orbx_camera* cam, const float* Tcw, const float* Tcb,
+                                               const float* Tbc, double* state, const double* prev_state, const double* preint,
+                                               const double* preint_jac, const double* preint_bias, const double* info_inertial,
+                                               const double* info_gyro, const double* info_acc, const double* prior_state,
+                                               const double* prior_H, int rec_init, uint8_t* outlier, double* H15, int32_t* n_ret,
+                                               int32_t* iters) {
+  if (n_edges < 0) return ORBX_EINVAL;
+  const int32_t ofs[2] = {0, n_edges};
+  return orbx_pose_inertial_optimization_last_frame_batch(ctx, 1, ofs, xw, obs, inv_sigma2, close_pt, cam, Tcw, Tcb, Tbc, state, prev_state,
+                                                          preint, preint_jac, preint_bias, info_inertial, info_gyro, info_acc, prior_state,
+                                                          prior_H, rec_init, outlier, H15, n_ret, iters);
 }
 
 }  // extern "C"

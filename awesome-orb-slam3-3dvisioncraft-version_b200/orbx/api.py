@@ -88,6 +88,7 @@ def load_library():
     L.orbx_pose_inertial_optimization_last_keyframe.argtypes = [vp, i] + [vp] * 14 + [i] + [vp] * 4
     L.orbx_pose_inertial_optimization_last_frame.argtypes = [vp, i] + [vp] * 18 + [i] + [vp] * 4
     L.orbx_pose_inertial_optimization_last_frame_batch.argtypes = [vp, i] + [vp] * 19 + [i] + [vp] * 4
+    L.orbx_pose_inertial_optimization_last_keyframe_batch.argtypes = [vp, i] + [vp] * 15 + [i] + [vp] * 4
     L.orbx_tracker_create.restype = vp
     L.orbx_tracker_create.argtypes = [vp, vp, i, vp, f, f, f]
     L.orbx_tracker_destroy.argtypes = [vp]
@@ -479,6 +480,33 @@ class Optimizer:
                     state=st64("state", 21), prev=st64("prev", 21), preint=st64("preint", 16), preint_jac=st64("preint_jac", 45),
                     preint_bias=st64("preint_bias", 6), infoI=st64("infoI", 81), infoG=st64("infoG", 9), infoA=st64("infoA", 9),
                     prior_state=st64("prior_state", 21), prior_H=st64("prior_H", 225))
+
+    def PoseInertialOptimizationLastKeyFrameBatch(self, problems, cam, rec_init=False):
+        """Many-stream form of PoseInertialOptimizationLastKeyFrame; `problems`: list of dicts (xw, obs, isg, close, Tcw, Tcb, Tbc,
+        state, kf, preint, infoI, infoG, infoA).  -> list of dict(state, outlier, H, n, iters), identical to single calls."""
+        P = len(problems)
+        cat32 = lambda k, w: np.ascontiguousarray(np.concatenate([np.asarray(q[k], np.float32).reshape(-1, w) for q in problems]))  # noqa: E731
+        st64 = lambda k, n: np.ascontiguousarray(np.stack([np.asarray(q[k], np.float64).reshape(-1)[:n] for q in problems]))     # noqa: E731
+        ofs = np.zeros(P + 1, np.int32)
+        ofs[1:] = np.cumsum([len(q["isg"]) for q in problems])
+        xw, obs, isg = cat32("xw", 3), cat32("obs", 3), cat32("isg", 1)
+        close = np.ascontiguousarray(np.concatenate([np.asarray(q["close"], np.uint8).reshape(-1) for q in problems]))
+        Tcw = np.ascontiguousarray(np.stack([np.asarray(q["Tcw"], np.float32).reshape(16) for q in problems]))
+        Tcb = np.ascontiguousarray(np.asarray(problems[0]["Tcb"], np.float32).reshape(4, 4))
+        Tbc = np.ascontiguousarray(np.asarray(problems[0]["Tbc"], np.float32).reshape(4, 4))
+        st = st64("state", 21).copy()
+        kf, pre, iI, iG, iA = st64("kf", 21), st64("preint", 16), st64("infoI", 81), st64("infoG", 9), st64("infoA", 9)
+        total = int(ofs[-1])
+        outl = np.zeros(max(total, 1), np.uint8)
+        H = np.zeros((P, 225), np.float64)
+        n = np.zeros(P, np.int32)
+        iters = np.zeros((P, 4), np.int32)
+        rc = load_library().orbx_pose_inertial_optimization_last_keyframe_batch(
+            self.ctx.h, P, _p(ofs), _ptr(xw), _ptr(obs), _ptr(isg), _ptr(close), C.byref(cam), _p(Tcw), _p(Tcb), _p(Tbc), _p(st),
+            _p(kf), _p(pre), _p(iI), _p(iG), _p(iA), int(rec_init), _p(outl), _p(H), _p(n), _p(iters))
+        _check(rc, "orbx_pose_inertial_optimization_last_keyframe_batch")
+        return [dict(state=st[p].copy(), outlier=outl[ofs[p]:ofs[p + 1]].copy(), H=H[p].reshape(15, 15), n=int(n[p]), iters=iters[p].copy())
+                for p in range(P)]
 
     def PoseInertialOptimizationLastFrameBatch(self, problems, cam, rec_init=False):
         """Many-stream form: `problems` = list of dicts with the keys of the single call (xw, obs, isg, close, Tcw, state, prev,

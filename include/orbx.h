@@ -401,6 +401,15 @@ int orbx_pose_inertial_optimization_last_keyframe(
     const double *info_inertial, const double *info_gyro, const double *info_acc, int rec_init,
     uint8_t *outlier, double *H15, int32_t *n_ret, int32_t *iters);
 
+/* Many-stream form of the call above: P independent frames in one launch (one CTA per problem);
+ * argument layout as orbx_pose_inertial_optimization_last_frame_batch below. */
+int orbx_pose_inertial_optimization_last_keyframe_batch(
+    orbx_ctx *ctx, int P, const int32_t *edge_ofs, const float *xw, const float *obs,
+    const float *inv_sigma2, const uint8_t *close_pt, const orbx_camera *cam, const float *Tcw,
+    const float *Tcb, const float *Tbc, double *state, const double *kf_state, const double *preint,
+    const double *info_inertial, const double *info_gyro, const double *info_acc, int rec_init,
+    uint8_t *outlier, double *H15, int32_t *n_ret, int32_t *iters);
+
 /* Optimizer::PoseInertialOptimizationLastFrame(Frame*, bool bRecInit) (src/Optimizer.cc:8068-8603) — what
  * Tracking::TrackLocalMap calls on every other visual-inertial frame (src/Tracking.cc:2974-2990).  The previous
  * frame's four vertices are free too (30 unknowns), tied down by EdgePriorPoseImu (src/G2oTypes.cc:941-981,

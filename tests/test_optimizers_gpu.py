@@ -251,3 +251,16 @@ def test_pose_inertial_last_frame_batch_equals_single_calls(ctx, ork):
         assert np.array_equal(g["outlier"], r["outlier"]) and g["n"] == r["n"] and np.array_equal(g["iters"], r["iters"])
     o = ork.pose_inertial_optimization_last_frame(probs[3], cam)
     assert np.abs(got[3]["state"] - o["state"]).max() < 1e-9
+
+
+def test_pose_inertial_last_keyframe_batch_equals_single_calls(ctx):
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    sizes = [300, 0, 57, 1000, 150, 24, 5, 411] * 5
+    probs = [sc.inertial_scenario(9500 + i, E, 0.6) for i, E in enumerate(sizes)]
+    got = opt.PoseInertialOptimizationLastKeyFrameBatch(probs, cam)
+    for i, (s, g) in enumerate(zip(probs, got)):
+        r = _inertial_call(opt, s, cam)
+        assert np.array_equal(g["state"], r["state"]) and np.array_equal(g["H"], r["H"]), i
+        assert np.array_equal(g["outlier"], r["outlier"]) and g["n"] == r["n"] and np.array_equal(g["iters"], r["iters"])
