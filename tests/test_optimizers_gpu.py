@@ -264,3 +264,31 @@ def test_pose_inertial_last_keyframe_batch_equals_single_calls(ctx):
         r = _inertial_call(opt, s, cam)
         assert np.array_equal(g["state"], r["state"]) and np.array_equal(g["H"], r["H"]), i
         assert np.array_equal(g["outlier"], r["outlier"]) and g["n"] == r["n"] and np.array_equal(g["iters"], r["iters"])
+
+
+def test_pose_inertial_argument_errors(ctx):
+    """Error behaviour of the f3 entry points: invalid offsets / missing arrays are refused with ORBX_EINVAL, not launched."""
+    import ctypes as C
+    import orbx
+    from orbx import api
+    L = api.load_library()
+    cam = orbx.make_camera()
+    s = sc.inertial_lf_scenario(1, 40, 0.5)
+    k = orbx.Optimizer.pack_inertial_lf([s, s])
+    st = k["state"].copy()
+    outl = np.zeros(80, np.uint8); H = np.zeros((2, 225)); n = np.zeros(2, np.int32); it = np.zeros((2, 4), np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+
+    def call(ofs, xw=k["xw"], prior_H=k["prior_H"]):
+        return L.orbx_pose_inertial_optimization_last_frame_batch(
+            ctx.h, 2, p(ofs), p(xw) if xw is not None else None, p(k["obs"]), p(k["isg"]), p(k["close"]), C.byref(cam), p(k["Tcw"]),
+            p(k["Tcb"]), p(k["Tbc"]), p(st), p(k["prev"]), p(k["preint"]), p(k["preint_jac"]), p(k["preint_bias"]), p(k["infoI"]),
+            p(k["infoG"]), p(k["infoA"]), p(k["prior_state"]), p(prior_H) if prior_H is not None else None, 0, p(outl), p(H), p(n), p(it))
+
+    assert call(k["ofs"]) == 0
+    assert call(np.array([0, 50, 40], np.int32)) != 0          # decreasing offsets
+    assert call(np.array([1, 40, 80], np.int32)) != 0          # does not start at 0
+    assert call(k["ofs"], xw=None) != 0                        # edges without coordinates
+    assert call(k["ofs"], prior_H=None) != 0                   # missing prior
+    with pytest.raises(orbx.OrbxError):
+        api._check(call(np.array([0, 50, 40], np.int32)), "orbx_pose_inertial_optimization_last_frame_batch")
