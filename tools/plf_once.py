@@ -1,3 +1,4 @@
+"""One PoseInertialOptimizationLastFrame call on cuda:0 (for `ncu -k regex:pose_inertial_lf` and ORBX_PIO_PROFILE=1)."""
 import sys; sys.path.insert(0, "tests"); sys.path.insert(0, "awesome-orb-slam3-3dvisioncraft-version_b200")
 import orbx, scenarios as sc
 ctx = orbx.Context(0); cam = orbx.make_camera(); opt = orbx.Optimizer(ctx)
