@@ -408,14 +408,41 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return min(max(i, 0), n - 1);
 }
 
-// 32-bit word of pixels [4c, 4c+4) of a row, with BORDER_REFLECT_101 outside [0, w)
-__device__ __forceinline__ uint32_t blur_word(const uint8_t* __restrict__ row, int c, int w) {
-  const int x = 4 * c;
-  if (x >= 0 && x + 4 <= w) return __ldg(reinterpret_cast<const uint32_t*>(row) + c);
-  uint32_t v = 0;
+// The three words (columns 4c-4 .. 4c+7) a thread needs from a row, with BORDER_REFLECT_101 outside [0, w), branch-free:
+// the words are loaded at clamped indices and the reflected bytes are patched in with byte permutes whose selectors
+// depend only on the thread's column (computed once per strip).  Reflected pixels always lie within the two words next
+// to the border, so every patch is one PRMT of an adjacent word pair.
+struct BlurCols {
+  int ia, ib, ic;              // clamped word indices
+  unsigned selB, selC;         // PRMT selectors
+  bool fixA, fixB, fixCab, fixCbc;
+};
+__device__ __forceinline__ BlurCols blur_cols(int c, int w) {
+  BlurCols q;
+  const int E = (w - 1) >> 2, m = (w - 1) & 3;   // last word, byte of the last valid pixel in it
+  q.ia = max(c - 1, 0); q.ib = c; q.ic = min(c + 1, E);
+  q.fixA = c == 0;                               // pixels -4..-1 = pixels 4,3,2,1 = PRMT(word0, word1, 0x1234)
+  q.fixB = c == E && m < 3;
+  q.fixCab = c == E;                             // word E+1 mirrors into (word E-1, word E)
+  q.fixCbc = c == E - 1 && m < 3;                // word E holds invalid bytes k > m: mirror from (word E-1, word E)
+  unsigned sb = 0, sc = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) v |= (uint32_t)__ldg(row + reflect101(x + k, w)) << (8 * k);
-  return v;
+  for (int k = 0; k < 4; ++k) {
+    // selectors index the pair (lo word: 0-3, hi word: 4-7); for fixB / fixCbc the hi word is word E, for fixCab too
+    sb |= (unsigned)(k <= m ? 4 + k : 4 + 2 * m - k) << (4 * k);
+    const int nc = (c == E) ? max(2 * m - k, 0)   // word E+1, byte k -> pixel 4E + 2m - 4 - k (only k < m is ever used)
+                            : (k <= m ? 4 + k : 4 + 2 * m - k);
+    sc |= (unsigned)nc << (4 * k);
+  }
+  q.selB = sb; q.selC = sc;
+  return q;
+}
+__device__ __forceinline__ void blur_words(const uint8_t* __restrict__ row, const BlurCols& q, uint32_t& a, uint32_t& b, uint32_t& c) {
+  const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row);
+  const uint32_t a0 = __ldg(r32 + q.ia), b0 = __ldg(r32 + q.ib), c0 = __ldg(r32 + q.ic);
+  a = q.fixA ? __byte_perm(b0, c0, 0x1234) : a0;
+  b = q.fixB ? __byte_perm(a0, b0, q.selB) : b0;
+  c = q.fixCab ? __byte_perm(a0, b0, q.selC) : (q.fixCbc ? __byte_perm(b0, c0, q.selC) : c0);
 }
 
 // horizontal 7-tap sums of the 4 pixels of word `b`, given its left/right neighbours
@@ -447,12 +474,15 @@ __global__ void __launch_bounds__(256) gauss7_kernel(const __grid_constant__ Ext
   const uint8_t* img = L.pyr + (size_t)blockIdx.y * L.imgStride;
   uint8_t* out = L.blur + (size_t)blockIdx.y * L.blurStride;
   const int y1 = min(y0 + BLUR_STRIP, L.h);
+  const BlurCols q = blur_cols(c, L.w);
   int h[7][4];   // horizontal sums of rows y-3..y+3 (statically indexed: the row loop is unrolled by 7)
   // prologue: rows y0-3 .. y0+2
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
     const uint8_t* row = img + (size_t)reflect101(y0 - 3 + r, L.h) * L.pitch;
-    blur_hrow(blur_word(row, c - 1, L.w), blur_word(row, c, L.w), blur_word(row, c + 1, L.w), h[r]);
+    uint32_t wa, wb, wc;
+    blur_words(row, q, wa, wb, wc);
+    blur_hrow(wa, wb, wc, h[r]);
   }
   for (int yb = y0; yb < y1; yb += 7) {
 #pragma unroll
@@ -461,7 +491,9 @@ __global__ void __launch_bounds__(256) gauss7_kernel(const __grid_constant__ Ext
       if (y < y1) {
         // newest row y+3 goes to slot (6+u)%7; rows y-3..y+3 sit in slots (u+j)%7, j = 0..6
         const uint8_t* row = img + (size_t)reflect101(y + 3, L.h) * L.pitch;
-        blur_hrow(blur_word(row, c - 1, L.w), blur_word(row, c, L.w), blur_word(row, c + 1, L.w), h[(6 + u) % 7]);
+        uint32_t wa, wb, wc;
+        blur_words(row, q, wa, wb, wc);
+        blur_hrow(wa, wb, wc, h[(6 + u) % 7]);
         uint32_t o = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
