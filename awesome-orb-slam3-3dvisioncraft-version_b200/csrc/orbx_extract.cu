@@ -570,6 +570,20 @@ int orbx_pyramid_level(orbx_ext* e, int b, int level, uint8_t* dst, int dst_stri
   return ORBX_OK;
 }
 
+int orbx_debug_blur_level(orbx_ext* e, int b, int level, uint8_t* dst, int dst_stride, int* w_out, int* h_out) {
+  if (!e || e->curW < 0 || level < 0 || level >= e->nlevels || b < 0 || b >= e->lastB) return ORBX_EINVAL;
+  const LevelParams& L = e->P.lv[level];
+  if (w_out) *w_out = L.w;
+  if (h_out) *h_out = L.h;
+  if (!dst) return ORBX_OK;
+  if (dst_stride < L.w) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(e->ctx->device));
+  ORBX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, L.blur + (size_t)b * L.blurStride, L.blurPitch, L.w, L.h,
+                              cudaMemcpyDeviceToHost, e->stream));
+  ORBX_CUDA(cudaStreamSynchronize(e->stream));
+  return ORBX_OK;
+}
+
 int orbx_debug_candidates(orbx_ext* e, int b, int level, int16_t* xy, uint8_t* score, int cap, int* n_out) {
   if (!e || e->curW < 0 || level < 0 || level >= e->nlevels || b < 0 || b >= e->lastB) return ORBX_EINVAL;
   ORBX_CUDA(cudaSetDevice(e->ctx->device));

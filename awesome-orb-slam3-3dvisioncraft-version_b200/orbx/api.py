@@ -116,6 +116,7 @@ def load_library():
     L.orbx_vocabulary_transform.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_vocabulary_transform_batch_device.argtypes = [vp, i, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_debug_candidates.argtypes = [vp, i, i, vp, vp, i, vp]
+    L.orbx_debug_blur_level.argtypes = [vp, i, i, vp, i, vp, vp]
     _LIB = L
     return L
 
@@ -282,6 +283,15 @@ class ORBextractor:
         out = np.empty((h.value, w.value), np.uint8)
         _check(load_library().orbx_pyramid_level(self.h, b, level, _p(out), w.value, C.byref(w), C.byref(h)),
                "orbx_pyramid_level")
+        return out
+
+    def debug_blur_level(self, level, b=0):
+        """The blurred copy of mvImagePyramid[level] that the descriptors are sampled from (test hook)."""
+        w, h = C.c_int(0), C.c_int(0)
+        _check(load_library().orbx_debug_blur_level(self.h, b, level, None, 0, C.byref(w), C.byref(h)), "orbx_debug_blur_level")
+        out = np.empty((h.value, w.value), np.uint8)
+        _check(load_library().orbx_debug_blur_level(self.h, b, level, _p(out), w.value, C.byref(w), C.byref(h)),
+               "orbx_debug_blur_level")
         return out
 
     def debug_candidates(self, level, b=0):

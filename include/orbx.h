@@ -130,6 +130,12 @@ int orbx_pyramid_level(orbx_ext *ext, int b, int level, uint8_t *dst, int dst_st
 int orbx_extractor_set_profiling(orbx_ext *ext, int enable);
 int orbx_extractor_stage_ms(orbx_ext *ext, float *ms, int *launches);
 
+/* Test hook: the Gaussian-blurred copy of level `level` of image `b` of the LAST extract call (the
+ * plane computeOrbDescriptor samples; src/ORBextractor.cc:1120-1121), same conventions as
+ * orbx_pyramid_level. */
+int orbx_debug_blur_level(orbx_ext *ext, int b, int level, uint8_t *dst, int dst_stride,
+                          int *w_out, int *h_out);
+
 /* Test/diagnostic view: FAST candidates of (image b, level) of the last call, i.e. the
  * contents of `vToDistributeKeys` (src/ORBextractor.cc:775,845-851) in an unspecified
  * order.  xy = [n][2] int16 (coordinates relative to minBorder), score = [n] uint8. */
