@@ -123,6 +123,9 @@ static bool encode_fast_map(CUtensorMap* m, const LevelParams& L, const uint8_t*
 // Fill P.lv[] geometry for (w,h); level-0 pointer/pitch are set by the caller.
 static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   ExtractParams& P = e->P;
+  // a failed configuration must not leave a half-written geometry behind a still-valid (curW, curH)
+  e->curW = e->curH = -1;
+  e->tmaL0 = nullptr;
   P.nlevels = e->nlevels;
   P.iniTh = e->iniTh;
   P.minTh = e->minTh;
@@ -149,8 +152,15 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
     // down to 16 bytes (the TMA unit faults on an unaligned innermost coordinate -- tools/tma_probe), so up to 15
     // leading bytes are dead: pitch = align16(15 + n*wCell + 6 + 4)
     L.fastCells = std::min(ORBX_FAST_CELLS, L.nCols);
-    while (L.fastCells > 1 && align_up((size_t)15 + L.fastCells * L.wCell + 6 + 4, 16) > 256) --L.fastCells;
-    L.fastTP = (int)align_up((size_t)15 + L.fastCells * L.wCell + 6 + 4, 16);
+    while (L.fastCells > 1 && 15 + L.fastCells * L.wCell + 6 + 4 > ORBX_FAST_TP) --L.fastCells;
+    if (15 + L.fastCells * L.wCell + 6 + 4 > ORBX_FAST_TP) {
+      orbx_set_error("orbx: FAST cell of %d px does not fit the %d-byte tile", L.wCell, ORBX_FAST_TP);
+      e->curW = e->curH = -1;
+      return ORBX_ECAP;
+    }
+    // balance the tiles of a cell row (24 columns: 6+6+6+6 instead of 7+7+7+3)
+    L.fastCells = div_up(L.nCols, div_up(L.nCols, L.fastCells));
+    L.fastTP = ORBX_FAST_TP;
     L.fastTH = L.hCell + 6;
     L.useTma = 0;
     L.tilesPerRow = div_up(L.nCols, L.fastCells);
@@ -175,7 +185,8 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
     }
     tile = (int)htiles.size();
     // one shared-memory plane holds the image tile (fastTP x fastTH) or the score plane ((wI+2) x (hI+2))
-    fastBytes = std::max(fastBytes, (int)align_up((size_t)L.fastTP * (L.hCell + 8), 128));
+    // (the 8-row strips of stage B read up to 7 + 6 rows past the last interior row)
+    fastBytes = std::max(fastBytes, ORBX_FAST_TP * (L.hCell + 14));
     fastCand = std::max(fastCand, (int)align_up((size_t)(L.fastCells * L.wCell) * L.hCell, 64));
     L.blurTilesX = div_up(L.w, ORBX_BLUR_TW);        // 128 columns per warp (32 lanes x 4 px)
     L.blurTilesY = div_up(L.h, ORBX_BLUR_TH);        // 8 warps x 32-row strips per CTA

@@ -6,6 +6,7 @@
 #define ORBX_EDGE 19          // EDGE_THRESHOLD, src/ORBextractor.cc:72
 #define ORBX_MINB 16          // minBorderX = EDGE_THRESHOLD-3, src/ORBextractor.cc:771
 #define ORBX_FAST_CELLS 8     // cells per FAST tile (one cell row x up to 8 cells)
+#define ORBX_FAST_TP 240      // row pitch in bytes of the FAST shared-memory planes = TMA box width (compile-time: immediate offsets; a multiple of 16 for TMA; 60 words = -4 banks per row, so the 8 rows of a strip column hit 8 different banks: 256 B measured 5x the bank conflicts and 2.4 ms instead of 1.75)
 #define ORBX_BLUR_TW 128
 #define ORBX_BLUR_TH 256
 
@@ -21,7 +22,7 @@ struct LevelParams {
   int nCols, nRows, wCell, hCell, maxBX, maxBY;
   int tileStart, tilesPerRow;      // flattened FAST tile ids of this level
   int fastCells;                   // cells per FAST tile (<= ORBX_FAST_CELLS, chosen so the TMA box is <= 256 B wide)
-  int fastTP, fastTH;              // FAST shared-memory tile: row pitch in bytes (= TMA box width) and rows
+  int fastTP, fastTH;              // FAST shared-memory tile: row pitch in bytes (= TMA box width = ORBX_FAST_TP) and rows
   int useTma;                      // 1: the tile is fetched by one cp.async.bulk.tensor, 0: by 32-bit loads
   int blurTileStart, blurTilesX, blurTilesY;
   // resize tables (level l from l-1): offsets into ExtractParams::tab (int16 units)
@@ -41,7 +42,7 @@ struct ExtractParams {
   int candPerImage, selPerImage;   // per-image strides of cand / sel buffers
   int totalFastTiles, totalBlurTiles;
   int nodeCap;
-  int fastTileBytes;               // bytes of one FAST shared-memory plane (max over levels, 16-aligned)
+  int fastTileBytes;               // bytes of one FAST shared-memory plane: ORBX_FAST_TP x (max hCell + 14) rows (8-row strips over-read)
   int fastCandCap;                 // >= interior (evaluated) pixels of any FAST tile, multiple of 64
   const int16_t* tab;              // resize coefficient tables
   const int4* fastTiles;           // [totalFastTiles] host-built FAST tile records (see configure_geometry)

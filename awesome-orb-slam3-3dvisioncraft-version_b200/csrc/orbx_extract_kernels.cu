@@ -57,38 +57,54 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
 //
 // The reference runs cv::FAST(cell, iniTh) and, only for a cell that yields nothing, cv::FAST(cell, minTh)
 // (src/ORBextractor.cc:808-828).  The kernel does the same in two passes over the shared-memory tile: pass 0 at iniTh
-// over every pixel, pass 1 at minTh restricted to the pixels of the cells pass 0 left empty (on corner-rich content
-// that is rare, and a threshold of 20 rejects far more pixels early than 7 does).  Every pass is staged so that the
-// expensive per-pixel arithmetic only runs on dense, compacted lists:
-//   A. tile -> shared memory: one TMA bulk tensor copy (or 32-bit loads when the level has no tensor map)
-//   B. early reject, 4 pixels per instruction stream: VABSDIFF4 of the centre word against the four compass ring
-//      positions (0,4,8,12), SWAR ">t" masks, and the necessary condition "two adjacent compass points differ by
-//      more than t" (every 9-arc of the 16-ring contains two adjacent compass points).  Survivors -> list 1.
-//   C. exact score of every survivor: the 16 ring differences are packed as (256+d, 256-d) in one s16x2 register by
-//      a single IMAD each, and the max-over-arcs-of-min network runs for both polarities at once on VIMNMX3.S16x2
-//      (40 instructions).  corner <=> arcmax > t; corners -> score plane + list 2.
-//   D. cell-local 3x3 NMS over list 2 (neighbours across a cell seam count as 0, like the borders of the per-cell
-//      cv::FAST call); kept keypoints -> list 3, which pass 1 appends to.  A pass-0 keypoint marks its cell non-empty.
+// over every pixel, pass 1 at minTh restricted to the pixels of the cells pass 0 left empty.  The kernel is bound by
+// instruction issue, not by memory, so every stage is built to spend as few issue slots per pixel as
+// exactness allows:
+//   A. tile -> shared memory: ONE TMA bulk tensor copy (box ORBX_FAST_TP x fastTH; 32-bit loads when the level has no
+//      tensor map).  The shared pitch is the compile-time constant ORBX_FAST_TP for every level, so all ring / neighbour
+//      addresses below are immediate offsets.
+//   B. dense early reject, 4 pixels per instruction: a thread owns one 4-pixel word column and an 8-row strip, keeps the
+//      14 rows it needs in registers, and tests VABSDIFF4 of the centre word against the four compass ring positions
+//      (0,4,8,12) with SWAR ">t" masks: "two adjacent compass points differ by more than t" is necessary for a corner
+//      (every 9-arc of the 16-ring contains two adjacent compass points).  The 32 flags of the strip (4 px x 8 rows)
+//      accumulate in ONE register; the survivors are appended to list 1 with one warp prefix sum + one shared atomic
+//      per strip (the previous version paid 4 ballots + 4 prefix popcounts per word: 70 of its 115 instructions/word).
+//   C. exact score of every survivor: the 16 ring differences are packed as (256+d, 256-d) in one s16x2 register by a
+//      single IMAD each, and the max-over-arcs-of-min network runs for both polarities at once on VIMNMX(3).S16x2
+//      (36 instructions: two neighbouring arcs share their 8 common elements).  corner <=> arcmax > t.
+//   D. cell-local 3x3 NMS over the corner list (neighbours across a cell seam count as 0, like the borders of the
+//      per-cell cv::FAST call); kept keypoints -> list 3, which pass 1 appends to.
 //   E. emission: one global atomic per tile, list 3 written out with its scores.
 // =====================================================================================
+#define FAST_TP ORBX_FAST_TP
+#define FAST_TPW (ORBX_FAST_TP / 4)
+#define FAST_STRIP 8
+// row of a pixel code (code / FAST_TP by multiplication; exact for code < 23831, codes stay below 48 * FAST_TP)
+#define FAST_CODE_Y(code) ((int)(((unsigned)(code) * (unsigned)((4194304 + FAST_TP - 1) / FAST_TP)) >> 22))
+static_assert(FAST_TP == 240, "FAST_CODE_Y's exactness bound was derived for a pitch of 240");
+
 __device__ __forceinline__ unsigned swar_gt_u8(unsigned x, unsigned k) {   // k = (0x7f - t) * 0x01010101, t < 128
   return (((x & 0x7f7f7f7fu) + k) | x) & 0x80808080u;
 }
 
+__device__ __forceinline__ unsigned vmin2(unsigned a, unsigned b) { return __vmins2(a, b); }
+__device__ __forceinline__ unsigned vmax2(unsigned a, unsigned b) { return __vmaxs2(a, b); }
 __device__ __forceinline__ unsigned vmin3(unsigned a, unsigned b, unsigned c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ unsigned vmax3(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
 
-// X[k] = (256 + d_k) | (256 - d_k) << 16 ; returns max over the 16 cyclic 9-arcs of the lane-wise minimum
+// X[k] = (256 + d_k) | (256 - d_k) << 16 ; returns max over the 16 cyclic 9-arcs of the lane-wise minimum.
+// Arcs j and j+1 (j even) share X[j+1..j+8]: max(arc_j, arc_j+1) = min(min(X[j+1..j+8]), max(X[j], X[j+9])).
 __device__ __forceinline__ unsigned arc9_maxmin_x2(const unsigned (&X)[16]) {
-  unsigned t[16];
+  unsigned pr[8], s4[8], r[8];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) t[k] = vmin3(X[k], X[(k + 1) & 15], X[(k + 2) & 15]);
-  unsigned m[16];
+  for (int i = 0; i < 8; ++i) pr[i] = vmin2(X[2 * i + 1], X[(2 * i + 2) & 15]);            // min X[2i+1 .. 2i+2]
 #pragma unroll
-  for (int k = 0; k < 16; ++k) m[k] = vmin3(t[k], t[(k + 3) & 15], t[(k + 6) & 15]);
-  const unsigned a0 = vmax3(m[0], m[1], m[2]), a1 = vmax3(m[3], m[4], m[5]), a2 = vmax3(m[6], m[7], m[8]);
-  const unsigned a3 = vmax3(m[9], m[10], m[11]), a4 = vmax3(m[12], m[13], m[14]);
-  return vmax3(vmax3(a0, a1, a2), vmax3(a3, a4, m[15]), a0);
+  for (int i = 0; i < 8; ++i) s4[i] = vmin2(pr[i], pr[(i + 1) & 7]);                        // min X[2i+1 .. 2i+4]
+#pragma unroll
+  for (int i = 0; i < 8; ++i)                                                               // j = 2i
+    r[i] = vmin3(s4[i], s4[(i + 2) & 7], vmax2(X[2 * i], X[(2 * i + 9) & 15]));
+  const unsigned a = vmax3(r[0], r[1], r[2]), b = vmax3(r[3], r[4], r[5]);
+  return vmax2(vmax3(r[6], r[7], a), b);
 }
 
 // atom.shared.add issued exactly as written (nvcc wraps atomicAdd in a warp-aggregation sequence of its own; the callers
@@ -101,36 +117,7 @@ __device__ __forceinline__ int smem_atomic_add(int* addr, int v) {
 
 // shared-memory flag words of fast_cells_kernel
 enum { FF_CELL = 0 /* [0..7] cell has a pass-0 keypoint */, FF_NCAND = 8, FF_NKEPT = 9, FF_BASE = 10, FF_NCORN = 11,
-       FF_OVF = 12, FF_NACT = 13, FF_EMPTY = 14 };
-
-// Stage B for one 4-pixel word of interior row y (word column c of the tile, byte mask m of the pixels to test):
-// appends the surviving pixels to scand.  Must be called by all 32 lanes (warp-aggregated append).
-__device__ __forceinline__ void fast_stage_b(const uint32_t* simg32, int tpw, int y, int c, int xb, unsigned m,
-                                             unsigned kGt, int* sflag, uint16_t* scand, int lane) {
-  const uint32_t* row = simg32 + (y + 3) * tpw + c;
-  const uint32_t V = row[0];
-  const uint32_t r0 = row[3 * tpw], r8 = row[-3 * tpw];
-  const uint32_t r4 = __funnelshift_r(row[0], row[1], 24);     // bytes +3..+6
-  const uint32_t r12 = __funnelshift_r(row[-1], row[0], 8);    // bytes -3..0
-  const unsigned b0 = swar_gt_u8(__vabsdiffu4(r0, V), kGt), b4 = swar_gt_u8(__vabsdiffu4(r4, V), kGt);
-  const unsigned b8 = swar_gt_u8(__vabsdiffu4(r8, V), kGt), b12 = swar_gt_u8(__vabsdiffu4(r12, V), kGt);
-  const unsigned cand = ((b0 | b8) & (b4 | b12)) & m;          // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
-  // warp-aggregated append (list order is irrelevant): one ballot per byte position gives every surviving pixel
-  // its slot, one shared-memory atomic per warp reserves the range
-  const unsigned ltm = (1u << lane) - 1;
-  const unsigned v0 = __ballot_sync(0xffffffffu, cand & 0x80u), v1 = __ballot_sync(0xffffffffu, cand & 0x8000u);
-  const unsigned v2 = __ballot_sync(0xffffffffu, cand & 0x800000u), v3 = __ballot_sync(0xffffffffu, cand & 0x80000000u);
-  if ((v0 | v1 | v2 | v3) == 0) return;
-  const int n0 = __popc(v0), n1 = __popc(v1), n2 = __popc(v2), n3 = __popc(v3);
-  int wbase = 0;
-  if (lane == 0) wbase = smem_atomic_add(&sflag[FF_NCAND], n0 + n1 + n2 + n3);
-  wbase = __shfl_sync(0xffffffffu, wbase, 0);
-  const unsigned code = (unsigned)((y << 9) + xb);   // xb may be negative in the first word; xb + k never is
-  if (cand & 0x80u) scand[wbase + __popc(v0 & ltm)] = (uint16_t)code;
-  if (cand & 0x8000u) scand[wbase + n0 + __popc(v1 & ltm)] = (uint16_t)(code + 1);
-  if (cand & 0x800000u) scand[wbase + n0 + n1 + __popc(v2 & ltm)] = (uint16_t)(code + 2);
-  if (cand & 0x80000000u) scand[wbase + n0 + n1 + n2 + __popc(v3 & ltm)] = (uint16_t)(code + 3);
-}
+       FF_OVF = 12 };
 
 __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ FastTmaMaps maps,
                                                          const __grid_constant__ ExtractParams p) {
@@ -144,24 +131,22 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int iniX = trec.y & 0xffff, iniY = trec.y >> 16;
   const int tw = trec.z & 0xffff, th = trec.z >> 16;  // tile incl. 3-px ring halo
-  const int wI = tw - 6, hI = th - 6;                 // interior (evaluated) pixels
+  const int wI = tw - 6, hI = th - 6;                 // interior (evaluated) pixels; wI <= FAST_TP - 25
 
-  // shared layout: [flags 64 B][mbarrier][image tile][score plane (hI+2) x sp][column->cell table 512 B]
-  //                [word masks 256 B][active word list 64 B][list 1: survivors][list 2: corners][list 3: kept]
+  // shared layout: [flags 64 B][mbarrier][image plane FAST_TP x (rows)][score plane FAST_TP x (rows)][column table 256 B]
+  //                [word masks 256 B][list 1: survivors][list 2: corners][list 3: kept]
+  // A pixel is named by code = y * FAST_TP + x (interior coordinates); image byte = code + 3*FAST_TP + 3 + off, score
+  // byte = code + FAST_TP + 1.
   const int xa = iniX & ~15;                          // tile origin: TMA needs a 16-byte aligned innermost coordinate
   const int off = iniX - xa;                          // 0..15: byte column of tile column 0
-  const int tp = L.fastTP;                            // >= off + tw + 4 (the stage-B window reads word c+1), multiple of 16
-  const int tpw = tp >> 2;
-  const int sp = wI + 2;
   const int CC = p.fastCandCap;                       // >= interior pixels of any tile, multiple of 64
   int* sflag = reinterpret_cast<int*>(smem);
   unsigned long long* smbar = reinterpret_cast<unsigned long long*>(smem + 64);   // TMA completion barrier
   uint8_t* simg = smem + 128;                         // 128-byte aligned: TMA destination
   uint8_t* ssc = simg + (size_t)p.fastTileBytes;
-  uint8_t* scell = ssc + (size_t)p.fastTileBytes;     // [wI] cell index of interior column x
-  uint32_t* smask = reinterpret_cast<uint32_t*>(scell + 512);   // [ncw] bytes of word c that are tested in this pass
-  uint8_t* sact = scell + 512 + 256;                  // pass 1: word columns with a non-zero mask
-  uint16_t* scand = reinterpret_cast<uint16_t*>(scell + 1024);  // [CC]   list 1
+  uint8_t* scell = ssc + (size_t)p.fastTileBytes;     // [wI] cell index of interior column x | 16: first | 32: last column of its cell
+  uint32_t* smask = reinterpret_cast<uint32_t*>(scell + 256);   // [ncw] bytes of word c that are tested in this pass
+  uint16_t* scand = reinterpret_cast<uint16_t*>(scell + 512);   // [CC]   list 1
   uint16_t* scorn = scand + CC;                       // [CC/2] list 2
   uint16_t* skept = scorn + CC / 2;                   // [CC/2] list 3
   const int capCorn = CC / 2, capKept = CC / 2;
@@ -170,12 +155,12 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const uint8_t* img = L.pyr + (size_t)b * L.imgStride;
   if (L.useTma) {
     // one elected thread arms the mbarrier with the byte count and issues ONE bulk tensor copy for the whole tile
-    // (box fastTP x fastTH at (xa, iniY, b); bytes outside the tensor are zero-filled by the TMA unit)
+    // (box FAST_TP x fastTH at (xa, iniY, b); bytes outside the tensor are zero-filled by the TMA unit)
     const unsigned mbar = (unsigned)__cvta_generic_to_shared(smbar);
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      const unsigned bytes = (unsigned)(L.fastTP * L.fastTH);
+      const unsigned bytes = (unsigned)(FAST_TP * L.fastTH);
       const unsigned dst = (unsigned)__cvta_generic_to_shared(simg);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
       // the descriptor is addressed in place in the kernel-parameter bank (levels compared against constants so the
@@ -192,19 +177,23 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   } else {
     uint32_t* simg32 = reinterpret_cast<uint32_t*>(simg);
     const int rowWords = (L.pitch - xa) / 4;          // words readable in a row without leaving the pitch
-    const int cw = min(tpw, rowWords);
+    const int cw = min(FAST_TPW, rowWords);
     for (int r = wid; r < th; r += 8) {               // one warp per tile row: coalesced 128-byte segments, no division
       const uint32_t* g = reinterpret_cast<const uint32_t*>(img + (size_t)(iniY + r) * L.pitch + xa);
-      uint32_t* d = simg32 + r * tpw;
-      for (int c = lane; c < tpw; c += 32) d[c] = c < cw ? __ldg(g + c) : 0u;
+      uint32_t* d = simg32 + r * FAST_TPW;
+      for (int c = lane; c < FAST_TPW; c += 32) d[c] = c < cw ? __ldg(g + c) : 0u;
     }
   }
   const int c0 = (off + 3) / 4, c1 = (off + 3 + wI - 1) / 4;   // words that hold interior pixels
-  const int ncw = c1 - c0 + 1;                                 // <= 64
+  const int ncw = c1 - c0 + 1;                                 // <= 58
   {
     uint32_t* ssc32 = reinterpret_cast<uint32_t*>(ssc);
-    for (int i = tid; i < ((hI + 2) * sp + 3) / 4; i += 256) ssc32[i] = 0;
-    for (int x = tid; x < wI; x += 256) scell[x] = (uint8_t)((x * trec.w) >> 16);   // x / wCell, exact for x < 512
+    for (int i = tid; i < (hI + 2) * FAST_TPW; i += 256) ssc32[i] = 0;
+    for (int x = tid; x < wI; x += 256) {
+      const int cell = (x * trec.w) >> 16;            // x / wCell, exact for x < 512
+      const int cl = x > 0 ? ((x - 1) * trec.w) >> 16 : -1, cr = x + 1 < wI ? ((x + 1) * trec.w) >> 16 : -1;
+      scell[x] = (uint8_t)(cell | (cl != cell ? 16 : 0) | (cr != cell ? 32 : 0));
+    }
     if (tid < 16) sflag[tid] = 0;
     // pass 0 tests every interior pixel: the mask only clips the first / last word to the interior columns
     for (int k = tid; k < ncw; k += 256) {
@@ -229,6 +218,9 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   }
 
   const uint32_t* simg32 = reinterpret_cast<const uint32_t*>(simg);
+  const int nStrips = (hI + FAST_STRIP - 1) / FAST_STRIP;
+  const int nItems = nStrips * ncw;                   // (strip, word column) items of stage B, <= 5 * 58
+  const int rcpNcw = (65536 + ncw - 1) / ncw;         // item / ncw == (item * rcpNcw) >> 16 for item < 512, ncw <= 64
   const int nPass = p.minTh < p.iniTh ? 2 : 1;        // a second pass at a threshold >= iniTh could not add anything
 #pragma unroll 1
   for (int pass = 0; pass < nPass; ++pass) {
@@ -240,7 +232,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
       for (int cidx = 0; cidx < nc; ++cidx) anyEmpty |= sflag[FF_CELL + cidx] == 0;
       if (!anyEmpty) break;
       __syncthreads();
-      if (tid == 0) { sflag[FF_NCAND] = 0; sflag[FF_NCORN] = 0; sflag[FF_OVF] = 0; sflag[FF_NACT] = 0; }
+      if (tid == 0) { sflag[FF_NCAND] = 0; sflag[FF_NCORN] = 0; sflag[FF_OVF] = 0; }
       // restrict the word masks to the pixels of empty cells
       for (int k = tid; k < ncw; k += 256) {
         const int xb = (c0 + k) * 4 - (off + 3);
@@ -248,45 +240,63 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int x = xb + q;
-          if (x >= 0 && x < wI && sflag[FF_CELL + scell[x]] == 0) m |= 0x80u << (8 * q);
+          if (x >= 0 && x < wI && sflag[FF_CELL + (scell[x] & 15)] == 0) m |= 0x80u << (8 * q);
         }
         smask[k] = m;
       }
       __syncthreads();
-      if (wid == 0) {                                 // ordered list of the word columns that still have work
-        for (int k0 = 0; k0 < ncw; k0 += 32) {
-          const int k = k0 + lane;
-          const bool a = k < ncw && smask[k] != 0;
-          const unsigned bal = __ballot_sync(0xffffffffu, a);
-          const int base = sflag[FF_NACT];
-          if (a) sact[base + __popc(bal & ((1u << lane) - 1))] = (uint8_t)k;
-          __syncwarp();
-          if (lane == 0) sflag[FF_NACT] = base + __popc(bal);
-          __syncwarp();
-        }
-      }
-      __syncthreads();
     }
 
-    // ---- B: compass early reject, one 4-pixel word per thread-iteration ----
-    if (pass == 0) {
-      for (int y = wid; y < hI; y += 8) {               // one warp per interior row, lanes over its 4-pixel words
-        for (int cb = 0; cb < ncw; cb += 32) {          // warp-uniform trip count
-          const int k = min(cb + lane, ncw - 1);        // out-of-range lanes redo the last word and drop its result
-          const unsigned m = cb + lane < ncw ? smask[k] : 0u;
-          fast_stage_b(simg32, tpw, y, c0 + k, (c0 + k) * 4 - (off + 3), m, kGt, sflag, scand, lane);
+    // ---- B: compass early reject; one (8-row strip, 4-pixel word column) item per thread-iteration ----
+#pragma unroll 1
+    for (int it0 = 0; it0 < nItems; it0 += 256) {       // warp-uniform trip count (the warp scan below needs all lanes)
+      const int item = it0 + tid;
+      unsigned M = 0;                                   // bit 8*q + u: pixel q of the word, row u of the strip survives
+      int code0 = 0;
+      if (item < nItems) {
+        const int s = (item * rcpNcw) >> 16, k = item - s * ncw;
+        const unsigned m = smask[k];
+        const int y0 = s * FAST_STRIP;
+        code0 = y0 * FAST_TP + (c0 + k) * 4 - (off + 3);   // code of (row y0, byte 0); byte 0 may lie left of the interior
+        if (m) {
+          const uint32_t* colp = simg32 + y0 * FAST_TPW + (c0 + k);   // tile row y0 = ring row -3 of interior row y0
+          const int nrow = hI - y0;                     // rows of this strip that exist (>= 1)
+          uint32_t A[FAST_STRIP + 6];
+#pragma unroll
+          for (int j = 0; j < FAST_STRIP + 6; ++j) A[j] = colp[j * FAST_TPW];   // rows past the tile: ignored below
+#pragma unroll
+          for (int u = 0; u < FAST_STRIP; ++u) {
+            const uint32_t V = A[u + 3];
+            const uint32_t Lw = colp[(u + 3) * FAST_TPW - 1], Rw = colp[(u + 3) * FAST_TPW + 1];
+            const uint32_t r4 = __funnelshift_r(V, Rw, 24);      // bytes +3..+6
+            const uint32_t r12 = __funnelshift_r(Lw, V, 8);      // bytes -3..0
+            const unsigned b0 = swar_gt_u8(__vabsdiffu4(A[u + 6], V), kGt), b4 = swar_gt_u8(__vabsdiffu4(r4, V), kGt);
+            const unsigned b8 = swar_gt_u8(__vabsdiffu4(A[u], V), kGt), b12 = swar_gt_u8(__vabsdiffu4(r12, V), kGt);
+            const unsigned mu = u < nrow ? m : 0u;
+            const unsigned cand = ((b0 | b8) & (b4 | b12)) & mu;   // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
+            M = (M >> 1) | cand;
+          }
         }
       }
-    } else {
-      const int nAct = sflag[FF_NACT];
-      const int total = hI * nAct;
-      for (int i0 = wid * 32; i0 < total; i0 += 256) {  // items = (row, active word), warp-uniform trip count
-        const int i = min(i0 + lane, total - 1);
-        const int y = i / nAct;
-        const int k = sact[i - y * nAct];
-        const unsigned m = i0 + lane < total ? smask[k] : 0u;
-        fast_stage_b(simg32, tpw, y, c0 + k, (c0 + k) * 4 - (off + 3), m, kGt, sflag, scand, lane);
+      // append: warp prefix sum of the per-thread survivor counts, one shared atomic per warp
+      const int cnt = __popc(M);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
       }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total == 0) continue;
+      int wbase = 0;
+      if (lane == 31) wbase = smem_atomic_add(&sflag[FF_NCAND], total);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      uint16_t* q = scand + wbase + incl - cnt;
+#pragma unroll
+      for (int px = 0; px < 4; ++px)
+#pragma unroll
+        for (int u = 0; u < FAST_STRIP; ++u)
+          if (M & (1u << (8 * px + u))) *q++ = (uint16_t)(code0 + u * FAST_TP + px);
     }
     __syncthreads();
 
@@ -294,26 +304,26 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
     const int nCand = sflag[FF_NCAND];
     {
       const int K0 = 256 * 65537;
+      const uint8_t* cbase = simg + 3 * FAST_TP + 3 + off;
       for (int i0 = wid * 32; i0 < nCand; i0 += 256) {
         const int i = i0 + lane;
         bool corner = false;
         int code = 0;
         if (i < nCand) {
           code = scand[i];
-          const int y = code >> 9, x = code & 511;
-          const uint8_t* c = simg + (y + 3) * tp + (x + 3 + off);
+          const uint8_t* c = cbase + code;
           const int Kv = K0 - 65535 * (int)c[0];          // X = 65535*r + Kv = (256 + v - r) | (256 - v + r) << 16
           unsigned X[16];
-          X[0] = 65535u * c[3 * tp] + Kv;       X[1] = 65535u * c[3 * tp + 1] + Kv;   X[2] = 65535u * c[2 * tp + 2] + Kv;
-          X[3] = 65535u * c[tp + 3] + Kv;       X[4] = 65535u * c[3] + Kv;            X[5] = 65535u * c[-tp + 3] + Kv;
-          X[6] = 65535u * c[-2 * tp + 2] + Kv;  X[7] = 65535u * c[-3 * tp + 1] + Kv;  X[8] = 65535u * c[-3 * tp] + Kv;
-          X[9] = 65535u * c[-3 * tp - 1] + Kv;  X[10] = 65535u * c[-2 * tp - 2] + Kv; X[11] = 65535u * c[-tp - 3] + Kv;
-          X[12] = 65535u * c[-3] + Kv;          X[13] = 65535u * c[tp - 3] + Kv;      X[14] = 65535u * c[2 * tp - 2] + Kv;
-          X[15] = 65535u * c[3 * tp - 1] + Kv;
+          X[0] = 65535u * c[3 * FAST_TP] + Kv;       X[1] = 65535u * c[3 * FAST_TP + 1] + Kv;   X[2] = 65535u * c[2 * FAST_TP + 2] + Kv;
+          X[3] = 65535u * c[FAST_TP + 3] + Kv;       X[4] = 65535u * c[3] + Kv;                 X[5] = 65535u * c[-FAST_TP + 3] + Kv;
+          X[6] = 65535u * c[-2 * FAST_TP + 2] + Kv;  X[7] = 65535u * c[-3 * FAST_TP + 1] + Kv;  X[8] = 65535u * c[-3 * FAST_TP] + Kv;
+          X[9] = 65535u * c[-3 * FAST_TP - 1] + Kv;  X[10] = 65535u * c[-2 * FAST_TP - 2] + Kv; X[11] = 65535u * c[-FAST_TP - 3] + Kv;
+          X[12] = 65535u * c[-3] + Kv;               X[13] = 65535u * c[FAST_TP - 3] + Kv;      X[14] = 65535u * c[2 * FAST_TP - 2] + Kv;
+          X[15] = 65535u * c[3 * FAST_TP - 1] + Kv;
           const unsigned am = arc9_maxmin_x2(X);
           const int arcmax = max((int)(am & 0xffffu), (int)(am >> 16)) - 256;
           corner = arcmax > t && arcmax > 1;
-          if (corner) ssc[(y + 1) * sp + x + 1] = (uint8_t)(arcmax - 1);
+          if (corner) ssc[code + FAST_TP + 1] = (uint8_t)(arcmax - 1);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, corner);
         if (bal) {
@@ -341,17 +351,16 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
         int code = 0;
         if (i < n) {
           code = src[i];
-          const int y = code >> 9, x = code & 511;
-          const uint8_t* sp0 = ssc + (y + 1) * sp + x + 1;
+          const uint8_t* sp0 = ssc + code + FAST_TP + 1;
           const int sc = sp0[0];
           // branch-free 3x3 maximum of the neighbours inside the pixel's own cell (others count as 0)
-          const int cell = scell[x];
-          const int mL = ((x > 0) & (scell[max(x - 1, 0)] == cell)) ? 0xff : 0, mR = ((x + 1 < wI) & (scell[x + 1] == cell)) ? 0xff : 0;
-          const int nL = max(max((int)sp0[-1], (int)sp0[-sp - 1]), (int)sp0[sp - 1]) & mL;
-          const int nR = max(max((int)sp0[1], (int)sp0[-sp + 1]), (int)sp0[sp + 1]) & mR;
-          const int nmax = max(max((int)sp0[-sp], (int)sp0[sp]), max(nL, nR));
+          const int cf = scell[code - FAST_CODE_Y(code) * FAST_TP];
+          const int mL = (cf & 16) ? 0 : 0xff, mR = (cf & 32) ? 0 : 0xff;
+          const int nL = max(max((int)sp0[-1], (int)sp0[-FAST_TP - 1]), (int)sp0[FAST_TP - 1]) & mL;
+          const int nR = max(max((int)sp0[1], (int)sp0[-FAST_TP + 1]), (int)sp0[FAST_TP + 1]) & mR;
+          const int nmax = max(max((int)sp0[-FAST_TP], (int)sp0[FAST_TP]), max(nL, nR));
           keep = sc > nmax;                             // sc == 0 (no corner) can never exceed nmax >= 0
-          if (keep && pass == 0) sflag[FF_CELL + cell] = 1;   // (benign race)
+          if (keep && pass == 0) sflag[FF_CELL + (cf & 15)] = 1;   // (benign race)
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (m) {
@@ -378,8 +387,8 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const int base = sflag[FF_BASE];
   for (int i = tid; i < nKept; i += 256) {
     const int code = skept[i];
-    const int y = code >> 9, x = code & 511;
-    const int sc = ssc[(y + 1) * sp + x + 1];
+    const int y = FAST_CODE_Y(code), x = code - y * FAST_TP;
+    const int sc = ssc[code + FAST_TP + 1];
     const int slot = base + i;
     if (slot < L.candCap) {
       // coordinates relative to (minBorderX, minBorderY), as the reference stores them (:847-848)
@@ -993,17 +1002,30 @@ __global__ void __launch_bounds__(DESC_NT) describe_kernel(const __grid_constant
 // host-side launchers (called from orbx_extract.cu)
 // ------------------------------------------------------------------------------------
 size_t orbx_fast_smem_bytes(int fastTileBytes, int fastCandCap) {
-  return (size_t)2 * fastTileBytes + 128 + 1024 + (size_t)4 * fastCandCap;   // planes + tables + lists 1..3 (uint16)
+  return (size_t)2 * fastTileBytes + 128 + 512 + (size_t)4 * fastCandCap;   // planes + tables + lists 1..3 (uint16)
 }
 size_t orbx_octree_smem_bytes(int nodeCap) {
   return (size_t)nodeCap * (2 * sizeof(short4) + sizeof(unsigned long long) + 4 * 2 + 16 + 4 * 4);
 }
 
+// The dynamic shared-memory opt-in is a per-kernel, process-wide attribute while every extractor configures its own
+// need: it is only ever RAISED (a later, smaller extractor must not lower it under an earlier one that is still live).
 int orbx_extract_configure(int nodeCap, int fastTileBytes, int fastCandCap) {
-  ORBX_CUDA(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)orbx_fast_smem_bytes(fastTileBytes, fastCandCap)));
-  ORBX_CUDA(cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)orbx_octree_smem_bytes(nodeCap)));
+  static std::mutex mu;
+  static int fastMax[64] = {}, octMax[64] = {};          // per device
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  ORBX_CUDA(cudaGetDevice(&dev));
+  dev &= 63;
+  const int fastNeed = (int)orbx_fast_smem_bytes(fastTileBytes, fastCandCap), octNeed = (int)orbx_octree_smem_bytes(nodeCap);
+  if (fastNeed > fastMax[dev]) {
+    ORBX_CUDA(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fastNeed));
+    fastMax[dev] = fastNeed;
+  }
+  if (octNeed > octMax[dev]) {
+    ORBX_CUDA(cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, octNeed));
+    octMax[dev] = octNeed;
+  }
   return ORBX_OK;
 }
 

@@ -1,0 +1,280 @@
+// cvstub.cpp — TEST INFRASTRUCTURE: the numerical side of the OpenCV stand-in (cvstub.h).  Every primitive delegates
+// to the oracle's restatement in ork_primitives.cpp, which tests/test_oracle_primitives.py pins bit-exactly to Python
+// cv2 4.13; tests/test_ref_stub.py pins the float matrix algebra below to cv2 as well.
+#include "cvstub.h"
+#include "../ork.h"
+
+namespace cv {
+
+void KeyPointsFilter::retainBest(std::vector<KeyPoint>& kps, int n) {
+  // cv::KeyPointsFilter::retainBest: nth_element by response, then keep everything tied with the n-th
+  if (n >= 0 && kps.size() > (size_t)n) {
+    if (n == 0) { kps.clear(); return; }
+    std::nth_element(kps.begin(), kps.begin() + n - 1, kps.end(),
+                     [](const KeyPoint& a, const KeyPoint& b) { return a.response > b.response; });
+    const float amb = kps[n - 1].response;
+    auto end = std::partition(kps.begin() + n, kps.end(), [amb](const KeyPoint& k) { return k.response >= amb; });
+    kps.resize(end - kps.begin());
+  }
+}
+
+void Mat::copyTo(OutputArray dst) const {
+  dst.create(rows, cols, flags_type);
+  Mat d = dst.getMat();
+  if (d.data == data && d.step.v == step.v) return;
+  for (int y = 0; y < rows; ++y) std::memmove(d.data + (size_t)y * d.step.v, data + (size_t)y * step.v, (size_t)cols * elemSize());
+}
+
+static double get_elem(const Mat& m, int y, int x) {
+  switch (m.type()) {
+    case CV_8U: return m.at<uchar>(y, x);
+    case CV_32S: return m.at<int>(y, x);
+    case CV_32F: return m.at<float>(y, x);
+    default: return m.at<double>(y, x);
+  }
+}
+static void set_elem(Mat& m, int y, int x, double v) {
+  switch (m.type()) {
+    case CV_8U: m.at<uchar>(y, x) = saturate_cast<uchar>(v); break;
+    case CV_32S: m.at<int>(y, x) = cvRound(v); break;
+    case CV_32F: m.at<float>(y, x) = (float)v; break;
+    default: m.at<double>(y, x) = v;
+  }
+}
+
+void Mat::convertTo(Mat& dst, int type) const {
+  Mat out(rows, cols, type);
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) set_elem(out, y, x, get_elem(*this, y, x));
+  dst = out;
+}
+
+Mat Mat::ones(int r, int c, int type) {
+  Mat m(r, c, type);
+  for (int y = 0; y < r; ++y)
+    for (int x = 0; x < c; ++x) set_elem(m, y, x, 1.0);
+  return m;
+}
+Mat Mat::eye(int r, int c, int type) {
+  Mat m = zeros(r, c, type);
+  for (int i = 0; i < std::min(r, c); ++i) set_elem(m, i, i, 1.0);
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// image primitives
+// ---------------------------------------------------------------------------------------------------------------
+void resize(InputArray src_, OutputArray dst_, Size dsize, double, double, int interpolation) {
+  assert(interpolation == INTER_LINEAR);
+  Mat src = src_.getMat();
+  assert(src.type() == CV_8U);
+  dst_.create(dsize.height, dsize.width, CV_8U);   // keeps a fitting ROI (the pyramid level inside its bordered buffer)
+  Mat dst = dst_.getMat();
+  ork::resize_linear_u8(src.data, src.cols, src.rows, (int)src.step.v, dst.data, dst.cols, dst.rows, (int)dst.step.v);
+}
+
+static inline int border101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
+  return i;
+}
+
+void copyMakeBorder(InputArray src_, OutputArray dst_, int top, int bottom, int left, int right, int borderType) {
+  assert((borderType & ~BORDER_ISOLATED) == BORDER_REFLECT_101);
+  Mat src = src_.getMat();
+  dst_.create(src.rows + top + bottom, src.cols + left + right, src.type());
+  Mat dst = dst_.getMat();
+  // Without BORDER_ISOLATED OpenCV would read real pixels around an ROI; the reference only passes a non-isolated
+  // source for level 0, whose source is a whole image, so both cases reduce to reflection about the ROI's own edges.
+  const int w = src.cols, h = src.rows;
+  std::vector<uchar> tmp((size_t)w * h);
+  for (int y = 0; y < h; ++y) std::memcpy(tmp.data() + (size_t)y * w, src.ptr(y), w);   // src may live inside dst
+  for (int y = 0; y < dst.rows; ++y) {
+    const uchar* s = tmp.data() + (size_t)border101(y - top, h) * w;
+    uchar* d = dst.ptr(y);
+    for (int x = 0; x < dst.cols; ++x) d[x] = s[border101(x - left, w)];
+  }
+}
+
+void FAST(InputArray image, std::vector<KeyPoint>& keypoints, int threshold, bool nms) {
+  Mat img = image.getMat();
+  assert(img.type() == CV_8U);
+  std::vector<ork::FastPoint> pts;
+  ork::fast9_16(img.data, img.cols, img.rows, (int)img.step.v, threshold, nms, pts);
+  keypoints.clear();
+  keypoints.reserve(pts.size());
+  for (const ork::FastPoint& p : pts) keypoints.push_back(KeyPoint((float)p.x, (float)p.y, 7.f, -1.f, (float)p.score));
+}
+
+void GaussianBlur(InputArray src_, OutputArray dst_, Size ksize, double sigmaX, double sigmaY, int borderType) {
+  assert(ksize.width == 7 && ksize.height == 7 && sigmaX == 2 && sigmaY == 2 && borderType == BORDER_REFLECT_101);
+  (void)ksize; (void)sigmaX; (void)sigmaY; (void)borderType;
+  Mat src = src_.getMat();
+  assert(src.type() == CV_8U);
+  Mat out(src.rows, src.cols, CV_8U);
+  ork::gaussian_blur7_s2(src.data, src.cols, src.rows, (int)src.step.v, out.data, (int)out.step.v);
+  dst_.create(src.rows, src.cols, CV_8U);
+  Mat dst = dst_.getMat();
+  for (int y = 0; y < src.rows; ++y) std::memcpy(dst.ptr(y), out.ptr(y), src.cols);
+}
+
+float fastAtan2(float y, float x) { return ork::fast_atan2(y, x); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// float / double matrix algebra.  OpenCV evaluates A*B for CV_32F through gemm: products and the running sum are
+// taken in double (GEMMSingleMul<float,double>) in k order and rounded to float once per element; the element-wise
+// operators work in the matrix type.  tests/test_ref_stub.py checks these rules against cv2 on random matrices.
+// ---------------------------------------------------------------------------------------------------------------
+Mat operator*(const Mat& a, const Mat& b) {
+  assert(a.cols == b.rows && a.type() == b.type() && (a.type() == CV_32F || a.type() == CV_64F));
+  Mat c(a.rows, b.cols, a.type());
+  for (int i = 0; i < a.rows; ++i)
+    for (int j = 0; j < b.cols; ++j) {
+      double s = 0;
+      for (int k = 0; k < a.cols; ++k) s += get_elem(a, i, k) * get_elem(b, k, j);
+      set_elem(c, i, j, s);
+    }
+  return c;
+}
+template <typename F> static Mat elementwise(const Mat& a, const Mat& b, F f) {
+  assert(a.rows == b.rows && a.cols == b.cols && a.type() == b.type());
+  Mat c(a.rows, a.cols, a.type());
+  for (int i = 0; i < a.rows; ++i)
+    for (int j = 0; j < a.cols; ++j) {
+      if (a.type() == CV_32F) c.at<float>(i, j) = f(a.at<float>(i, j), b.at<float>(i, j));
+      else if (a.type() == CV_64F) c.at<double>(i, j) = f(a.at<double>(i, j), b.at<double>(i, j));
+      else set_elem(c, i, j, f(get_elem(a, i, j), get_elem(b, i, j)));
+    }
+  return c;
+}
+Mat operator+(const Mat& a, const Mat& b) { return elementwise(a, b, [](auto x, auto y) { return x + y; }); }
+Mat operator-(const Mat& a, const Mat& b) { return elementwise(a, b, [](auto x, auto y) { return x - y; }); }
+Mat Mat::mul(const Mat& m) const { return elementwise(*this, m, [](auto x, auto y) { return x * y; }); }
+Mat operator-(const Mat& a) { return a * -1.0; }
+Mat operator*(const Mat& a, double s) {
+  Mat c(a.rows, a.cols, a.type());
+  for (int i = 0; i < a.rows; ++i)
+    for (int j = 0; j < a.cols; ++j) {
+      if (a.type() == CV_32F) c.at<float>(i, j) = (float)(a.at<float>(i, j) * s);   // cvt: saturate_cast<float>(src*alpha) in double
+      else set_elem(c, i, j, get_elem(a, i, j) * s);
+    }
+  return c;
+}
+Mat operator*(double s, const Mat& a) { return a * s; }
+Mat operator/(const Mat& a, double s) { return a * (1.0 / s); }
+
+Mat Mat::t() const {
+  Mat c(cols, rows, flags_type);
+  for (int i = 0; i < rows; ++i)
+    for (int j = 0; j < cols; ++j) std::memcpy(c.data + (size_t)j * c.step.v + (size_t)i * elemSize(), data + (size_t)i * step.v + (size_t)j * elemSize(), elemSize());
+  return c;
+}
+
+double Mat::dot(const Mat& m) const {
+  // dotProd_32f: double accumulator over float products taken in double
+  double s = 0;
+  for (int i = 0; i < rows; ++i)
+    for (int j = 0; j < cols; ++j) s += get_elem(*this, i, j) * get_elem(m, i, j);
+  return s;
+}
+
+double norm(InputArray a_) {
+  Mat a = a_.getMat();
+  double s = 0;
+  for (int i = 0; i < a.rows; ++i)
+    for (int j = 0; j < a.cols; ++j) { const double v = get_elem(a, i, j); s += v * v; }
+  return std::sqrt(s);
+}
+double norm(InputArray a, InputArray b) { return norm(a.getMat() - b.getMat()); }
+
+double determinant(InputArray a_) {
+  Mat a = a_.getMat();
+  assert(a.rows == a.cols);
+  if (a.rows == 2) return get_elem(a, 0, 0) * get_elem(a, 1, 1) - get_elem(a, 0, 1) * get_elem(a, 1, 0);
+  assert(a.rows == 3);
+  auto e = [&](int i, int j) { return get_elem(a, i, j); };
+  return e(0, 0) * (e(1, 1) * e(2, 2) - e(1, 2) * e(2, 1)) - e(0, 1) * (e(1, 0) * e(2, 2) - e(1, 2) * e(2, 0)) +
+         e(0, 2) * (e(1, 0) * e(2, 1) - e(1, 1) * e(2, 0));
+}
+
+Mat Mat::inv(int) const {
+  // cv::invert, DECOMP_LU: closed forms for 2x2 / 3x3 evaluated in double (Sf/Df macros of lapack.cpp), general case
+  // Gauss-Jordan in double.
+  assert(rows == cols);
+  const int n = rows;
+  Mat out(n, n, flags_type);
+  auto e = [&](int i, int j) { return get_elem(*this, i, j); };
+  if (n == 2) {
+    double d = e(0, 0) * e(1, 1) - e(0, 1) * e(1, 0);
+    if (d != 0) {
+      d = 1. / d;
+      const double t0 = e(0, 0) * d, t1 = e(1, 1) * d;
+      set_elem(out, 1, 1, t0); set_elem(out, 0, 0, t1);
+      set_elem(out, 0, 1, -e(0, 1) * d); set_elem(out, 1, 0, -e(1, 0) * d);
+    }
+    return out;
+  }
+  if (n == 3) {
+    double d = determinant(*this);
+    if (d != 0) {
+      d = 1. / d;
+      double t[9];
+      t[0] = (e(1, 1) * e(2, 2) - e(1, 2) * e(2, 1)) * d;
+      t[1] = (e(0, 2) * e(2, 1) - e(0, 1) * e(2, 2)) * d;
+      t[2] = (e(0, 1) * e(1, 2) - e(0, 2) * e(1, 1)) * d;
+      t[3] = (e(1, 2) * e(2, 0) - e(1, 0) * e(2, 2)) * d;
+      t[4] = (e(0, 0) * e(2, 2) - e(0, 2) * e(2, 0)) * d;
+      t[5] = (e(0, 2) * e(1, 0) - e(0, 0) * e(1, 2)) * d;
+      t[6] = (e(1, 0) * e(2, 1) - e(1, 1) * e(2, 0)) * d;
+      t[7] = (e(0, 1) * e(2, 0) - e(0, 0) * e(2, 1)) * d;
+      t[8] = (e(0, 0) * e(1, 1) - e(0, 1) * e(1, 0)) * d;
+      for (int i = 0; i < 9; ++i) set_elem(out, i / 3, i % 3, t[i]);
+    }
+    return out;
+  }
+  std::vector<double> A((size_t)n * 2 * n, 0.0);
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) A[(size_t)i * 2 * n + j] = e(i, j);
+    A[(size_t)i * 2 * n + n + i] = 1;
+  }
+  for (int c = 0; c < n; ++c) {
+    int p = c;
+    for (int r = c + 1; r < n; ++r) if (std::fabs(A[(size_t)r * 2 * n + c]) > std::fabs(A[(size_t)p * 2 * n + c])) p = r;
+    if (A[(size_t)p * 2 * n + c] == 0) return Mat::zeros(n, n, flags_type);
+    if (p != c) for (int j = 0; j < 2 * n; ++j) std::swap(A[(size_t)p * 2 * n + j], A[(size_t)c * 2 * n + j]);
+    const double d = 1. / A[(size_t)c * 2 * n + c];
+    for (int j = 0; j < 2 * n; ++j) A[(size_t)c * 2 * n + j] *= d;
+    for (int r = 0; r < n; ++r) if (r != c) {
+      const double f = A[(size_t)r * 2 * n + c];
+      if (f != 0) for (int j = 0; j < 2 * n; ++j) A[(size_t)r * 2 * n + j] -= f * A[(size_t)c * 2 * n + j];
+    }
+  }
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) set_elem(out, i, j, A[(size_t)i * 2 * n + n + j]);
+  return out;
+}
+
+void hconcat(InputArray a_, InputArray b_, OutputArray dst) {
+  Mat a = a_.getMat(), b = b_.getMat();
+  Mat out(a.rows, a.cols + b.cols, a.type());
+  a.copyTo(out.colRange(0, a.cols));
+  b.copyTo(out.colRange(a.cols, a.cols + b.cols));
+  dst.getMatRef() = out;
+}
+void vconcat(InputArray a_, InputArray b_, OutputArray dst) {
+  Mat a = a_.getMat(), b = b_.getMat();
+  Mat out(a.rows + b.rows, a.cols, a.type());
+  a.copyTo(out.rowRange(0, a.rows));
+  b.copyTo(out.rowRange(a.rows, a.rows + b.rows));
+  dst.getMatRef() = out;
+}
+
+std::ostream& operator<<(std::ostream& os, const Mat& m) {
+  os << "[";
+  for (int i = 0; i < m.rows; ++i) {
+    for (int j = 0; j < m.cols; ++j) os << get_elem(m, i, j) << (j + 1 < m.cols ? ", " : "");
+    os << (i + 1 < m.rows ? ";\n " : "");
+  }
+  return os << "]";
+}
+
+}  // namespace cv
