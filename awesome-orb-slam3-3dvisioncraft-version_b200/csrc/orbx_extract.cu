@@ -10,9 +10,9 @@
 #include <algorithm>
 #include <cstdlib>
 
-int orbx_extract_configure(int nodeCap, int fastTileBytes, int fastCandCap);
+int orbx_extract_configure(int nodeCap, int fastTileBytes, int fastScoreBytes, int fastCandCap);
 size_t orbx_octree_smem_bytes(int nodeCap);
-size_t orbx_fast_smem_bytes(int fastTileBytes, int fastCandCap);
+size_t orbx_fast_smem_bytes(int fastTileBytes, int fastScoreBytes, int fastCandCap);
 int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, const FastTmaMaps& maps, orbx_keypoint* d_kps,
                         uint8_t* d_desc, int cap, int* d_n, int* d_mono, cudaEvent_t* ev);
 
@@ -131,7 +131,7 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   P.minTh = e->minTh;
   P.nodeCap = 0;
   size_t off = 0;
-  int tile = 0, btile = 0, cand = 0, sel = 0, fastBytes = 0, fastCand = 0;
+  int tile = 0, btile = 0, cand = 0, sel = 0, fastBytes = 0, fastScore = 0, fastCand = 0;
   std::vector<int16_t> htab;
   std::vector<int4> htiles;
   for (int l = 0; l < e->nlevels; ++l) {
@@ -180,13 +180,17 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
         const int maxX = std::min(iniX + nc * L.wCell + 6, L.maxBX);
         const int tw = maxX - iniX, th = maxY - iniY;
         if (tw - 6 <= 0 || th - 6 <= 0) continue;
-        htiles.push_back(make_int4(l | (nc << 8), iniX | (iniY << 16), tw | (th << 16), (65536 + L.wCell - 1) / L.wCell));
+        // words of a tile row that hold interior pixels (the kernel's ncw) and the reciprocal it divides items by
+        const int off = iniX & 15, ncw = (off + 3 + tw - 6 - 1) / 4 - (off + 3) / 4 + 1;
+        htiles.push_back(make_int4(l | (nc << 8) | (((65536 + ncw - 1) / ncw) << 16), iniX | (iniY << 16), tw | (th << 16),
+                                   (65536 + L.wCell - 1) / L.wCell));
       }
     }
     tile = (int)htiles.size();
     // one shared-memory plane holds the image tile (fastTP x fastTH) or the score plane ((wI+2) x (hI+2))
     // (the 8-row strips of stage B read up to 7 + 6 rows past the last interior row)
     fastBytes = std::max(fastBytes, ORBX_FAST_TP * (L.hCell + 14));
+    fastScore = std::max(fastScore, ORBX_FAST_TP * (L.hCell + 2));
     fastCand = std::max(fastCand, (int)align_up((size_t)(L.fastCells * L.wCell) * L.hCell, 64));
     L.blurTilesX = div_up(L.w, ORBX_BLUR_TW);        // 128 columns per warp (32 lanes x 4 px)
     L.blurTilesY = div_up(L.h, ORBX_BLUR_TH);        // 8 warps x 32-row strips per CTA
@@ -273,6 +277,7 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   P.totalFastTiles = tile;
   P.totalBlurTiles = btile;
   P.fastTileBytes = fastBytes;
+  P.fastScoreBytes = fastScore;
   P.fastCandCap = fastCand;
   P.cand = e->d_cand;
   P.keyNode = e->d_keyNode;
@@ -281,12 +286,12 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
   P.selN = e->d_counts + e->maxB * e->nlevels;
   P.selLap = e->d_counts + 2 * e->maxB * e->nlevels;
   P.err = e->d_counts + 3 * e->maxB * e->nlevels;
-  if (orbx_fast_smem_bytes(fastBytes, fastCand) > 200 * 1024 || orbx_octree_smem_bytes(P.nodeCap) > 200 * 1024) {
-    orbx_set_error("orbx: shared-memory budget exceeded (fast %zu, octree %zu)", orbx_fast_smem_bytes(fastBytes, fastCand),
+  if (orbx_fast_smem_bytes(fastBytes, fastScore, fastCand) > 200 * 1024 || orbx_octree_smem_bytes(P.nodeCap) > 200 * 1024) {
+    orbx_set_error("orbx: shared-memory budget exceeded (fast %zu, octree %zu)", orbx_fast_smem_bytes(fastBytes, fastScore, fastCand),
                    orbx_octree_smem_bytes(P.nodeCap));
     return ORBX_ECAP;
   }
-  int rc = orbx_extract_configure(P.nodeCap, fastBytes, fastCand);
+  int rc = orbx_extract_configure(P.nodeCap, fastBytes, fastScore, fastCand);
   if (rc != ORBX_OK) return rc;
   for (int l = 1; l < e->nlevels; ++l) {
     LevelParams& L = P.lv[l];

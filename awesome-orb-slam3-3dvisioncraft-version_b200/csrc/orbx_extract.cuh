@@ -43,6 +43,7 @@ struct ExtractParams {
   int totalFastTiles, totalBlurTiles;
   int nodeCap;
   int fastTileBytes;               // bytes of one FAST shared-memory plane: ORBX_FAST_TP x (max hCell + 14) rows (8-row strips over-read)
+  int fastScoreBytes;              // bytes of the FAST score plane: ORBX_FAST_TP x (max hCell + 2) rows
   int fastCandCap;                 // >= interior (evaluated) pixels of any FAST tile, multiple of 64
   const int16_t* tab;              // resize coefficient tables
   const int4* fastTiles;           // [totalFastTiles] host-built FAST tile records (see configure_geometry)

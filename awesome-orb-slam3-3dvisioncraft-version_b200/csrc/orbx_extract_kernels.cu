@@ -116,16 +116,16 @@ __device__ __forceinline__ int smem_atomic_add(int* addr, int v) {
 }
 
 // shared-memory flag words of fast_cells_kernel
-enum { FF_CELL = 0 /* [0..7] cell has a pass-0 keypoint */, FF_NCAND = 8, FF_NKEPT = 9, FF_BASE = 10, FF_NCORN = 11,
-       FF_OVF = 12 };
+enum { FF_CELL = 0 /* [0..7] cell has a pass-0 keypoint */, FF_NCAND = 8, FF_NKEPT = 9, FF_BASE = 10,
+       FF_WCORN = 16 /* [16..23] corners found by warp w (they sit at the front of its share of list 1) */ };
 
 __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ FastTmaMaps maps,
                                                          const __grid_constant__ ExtractParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // tile record (host-built: only tiles that own at least one evaluated pixel are listed):
-  //   x = level | nc << 8, y = iniX | iniY << 16, z = tw | th << 16, w = ceil(65536 / wCell)
+  //   x = level | nc << 8 | ceil(65536 / ncw) << 16, y = iniX | iniY << 16, z = tw | th << 16, w = ceil(65536 / wCell)
   const int4 trec = __ldg(p.fastTiles + blockIdx.x);
-  const int level = trec.x & 0xff, nc = trec.x >> 8;
+  const int level = trec.x & 0xff, nc = (trec.x >> 8) & 0xff;
   const LevelParams& L = p.lv[level];
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -133,23 +133,22 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const int tw = trec.z & 0xffff, th = trec.z >> 16;  // tile incl. 3-px ring halo
   const int wI = tw - 6, hI = th - 6;                 // interior (evaluated) pixels; wI <= FAST_TP - 25
 
-  // shared layout: [flags 64 B][mbarrier][image plane FAST_TP x (rows)][score plane FAST_TP x (rows)][column table 256 B]
-  //                [word masks 256 B][list 1: survivors][list 2: corners][list 3: kept]
+  // shared layout: [flags 128 B][mbarrier][image plane FAST_TP x (rows)][score plane FAST_TP x (rows)][column table 256 B]
+  //                [word masks 256 B][list 1: survivors, compacted in place to the corners][list 3: kept]
   // A pixel is named by code = y * FAST_TP + x (interior coordinates); image byte = code + 3*FAST_TP + 3 + off, score
   // byte = code + FAST_TP + 1.
   const int xa = iniX & ~15;                          // tile origin: TMA needs a 16-byte aligned innermost coordinate
   const int off = iniX - xa;                          // 0..15: byte column of tile column 0
   const int CC = p.fastCandCap;                       // >= interior pixels of any tile, multiple of 64
   int* sflag = reinterpret_cast<int*>(smem);
-  unsigned long long* smbar = reinterpret_cast<unsigned long long*>(smem + 64);   // TMA completion barrier
-  uint8_t* simg = smem + 128;                         // 128-byte aligned: TMA destination
-  uint8_t* ssc = simg + (size_t)p.fastTileBytes;
-  uint8_t* scell = ssc + (size_t)p.fastTileBytes;     // [wI] cell index of interior column x | 16: first | 32: last column of its cell
+  unsigned long long* smbar = reinterpret_cast<unsigned long long*>(smem + 128);  // TMA completion barrier
+  uint8_t* simg = smem + 256;                         // 128-byte aligned: TMA destination
+  uint8_t* ssc = simg + (size_t)p.fastTileBytes;      // 16-byte aligned (both plane sizes are multiples of FAST_TP)
+  uint8_t* scell = ssc + (size_t)p.fastScoreBytes;    // [wI] cell index of interior column x | 16: first | 32: last column of its cell
   uint32_t* smask = reinterpret_cast<uint32_t*>(scell + 256);   // [ncw] bytes of word c that are tested in this pass
   uint16_t* scand = reinterpret_cast<uint16_t*>(scell + 512);   // [CC]   list 1
-  uint16_t* scorn = scand + CC;                       // [CC/2] list 2
-  uint16_t* skept = scorn + CC / 2;                   // [CC/2] list 3
-  const int capCorn = CC / 2, capKept = CC / 2;
+  uint16_t* skept = scand + CC;                       // [CC/2] list 3
+  const int capKept = CC / 2;
 
   // ---- A: load ----
   const uint8_t* img = L.pyr + (size_t)b * L.imgStride;
@@ -187,14 +186,14 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const int c0 = (off + 3) / 4, c1 = (off + 3 + wI - 1) / 4;   // words that hold interior pixels
   const int ncw = c1 - c0 + 1;                                 // <= 58
   {
-    uint32_t* ssc32 = reinterpret_cast<uint32_t*>(ssc);
-    for (int i = tid; i < (hI + 2) * FAST_TPW; i += 256) ssc32[i] = 0;
+    uint4* ssc128 = reinterpret_cast<uint4*>(ssc);
+    for (int i = tid; i < (hI + 2) * (FAST_TP / 16); i += 256) ssc128[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int x = tid; x < wI; x += 256) {
       const int cell = (x * trec.w) >> 16;            // x / wCell, exact for x < 512
       const int cl = x > 0 ? ((x - 1) * trec.w) >> 16 : -1, cr = x + 1 < wI ? ((x + 1) * trec.w) >> 16 : -1;
       scell[x] = (uint8_t)(cell | (cl != cell ? 16 : 0) | (cr != cell ? 32 : 0));
     }
-    if (tid < 16) sflag[tid] = 0;
+    if (tid < 32) sflag[tid] = 0;
     // pass 0 tests every interior pixel: the mask only clips the first / last word to the interior columns
     for (int k = tid; k < ncw; k += 256) {
       const int xb = (c0 + k) * 4 - (off + 3);        // interior x of byte 0 (may be negative)
@@ -220,7 +219,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const uint32_t* simg32 = reinterpret_cast<const uint32_t*>(simg);
   const int nStrips = (hI + FAST_STRIP - 1) / FAST_STRIP;
   const int nItems = nStrips * ncw;                   // (strip, word column) items of stage B, <= 5 * 58
-  const int rcpNcw = (65536 + ncw - 1) / ncw;         // item / ncw == (item * rcpNcw) >> 16 for item < 512, ncw <= 64
+  const int rcpNcw = (int)((unsigned)trec.x >> 16);   // ceil(65536 / ncw): item / ncw == (item * rcpNcw) >> 16 for item < 512, ncw <= 64
   const int nPass = p.minTh < p.iniTh ? 2 : 1;        // a second pass at a threshold >= iniTh could not add anything
 #pragma unroll 1
   for (int pass = 0; pass < nPass; ++pass) {
@@ -232,7 +231,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
       for (int cidx = 0; cidx < nc; ++cidx) anyEmpty |= sflag[FF_CELL + cidx] == 0;
       if (!anyEmpty) break;
       __syncthreads();
-      if (tid == 0) { sflag[FF_NCAND] = 0; sflag[FF_NCORN] = 0; sflag[FF_OVF] = 0; }
+      if (tid == 0) sflag[FF_NCAND] = 0;
       // restrict the word masks to the pixels of empty cells
       for (int k = tid; k < ncw; k += 256) {
         const int xb = (c0 + k) * 4 - (off + 3);
@@ -300,16 +299,23 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
     }
     __syncthreads();
 
-    // ---- C: exact score of the survivors; corners go to the score plane and to list 2 ----
+    // ---- C: exact score of the survivors; corners go to the score plane and are compacted IN PLACE: warp w owns the
+    //      survivors [w*chunk, (w+1)*chunk) of list 1 and moves its corners to the front of that range (the write
+    //      position never passes the read position, and a warp is convergent at the ballot), so no second list, no
+    //      atomics and no capacity check are needed ----
     const int nCand = sflag[FF_NCAND];
+    const int chunk = ((nCand + 255) >> 8) << 5;        // per-warp share, a multiple of 32
+    const int cbeg = wid * chunk, cend = min(cbeg + chunk, nCand);
     {
       const int K0 = 256 * 65537;
       const uint8_t* cbase = simg + 3 * FAST_TP + 3 + off;
-      for (int i0 = wid * 32; i0 < nCand; i0 += 256) {
+      const unsigned ltm = (1u << lane) - 1;
+      int wcnt = 0;
+      for (int i0 = cbeg; i0 < cend; i0 += 32) {
         const int i = i0 + lane;
         bool corner = false;
         int code = 0;
-        if (i < nCand) {
+        if (i < cend) {
           code = scand[i];
           const uint8_t* c = cbase + code;
           const int Kv = K0 - 65535 * (int)c[0];          // X = 65535*r + Kv = (256 + v - r) | (256 - v + r) << 16
@@ -326,31 +332,22 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
           if (corner) ssc[code + FAST_TP + 1] = (uint8_t)(arcmax - 1);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, corner);
-        if (bal) {
-          int wbase = 0;
-          if (lane == 0) wbase = smem_atomic_add(&sflag[FF_NCORN], __popc(bal));
-          wbase = __shfl_sync(0xffffffffu, wbase, 0);
-          if (corner) {
-            const int slot = wbase + __popc(bal & ((1u << lane) - 1));
-            if (slot < capCorn) scorn[slot] = (uint16_t)code;
-            else sflag[FF_OVF] = 1;                       // (benign race: every writer stores 1)
-          }
-        }
+        if (corner) scand[cbeg + wcnt + __popc(bal & ltm)] = (uint16_t)code;
+        wcnt += __popc(bal);
       }
+      if (lane == 0) sflag[FF_WCORN + wid] = wcnt;
     }
     __syncthreads();
 
-    // ---- D: NMS inside the pixel's own cell over the corner list (over list 1 if list 2 overflowed) ----
+    // ---- D: NMS inside the pixel's own cell over the corners (warp w: the corners at the front of warp w's share) ----
     {
-      const bool ovf = sflag[FF_OVF] != 0;
-      const uint16_t* src = ovf ? scand : scorn;
-      const int n = ovf ? nCand : sflag[FF_NCORN];
-      for (int i0 = wid * 32; i0 < n; i0 += 256) {
+      const int n = cbeg + sflag[FF_WCORN + wid];
+      for (int i0 = cbeg; i0 < n; i0 += 32) {
         const int i = i0 + lane;
         bool keep = false;
         int code = 0;
         if (i < n) {
-          code = src[i];
+          code = scand[i];
           const uint8_t* sp0 = ssc + code + FAST_TP + 1;
           const int sc = sp0[0];
           // branch-free 3x3 maximum of the neighbours inside the pixel's own cell (others count as 0)
@@ -359,7 +356,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
           const int nL = max(max((int)sp0[-1], (int)sp0[-FAST_TP - 1]), (int)sp0[FAST_TP - 1]) & mL;
           const int nR = max(max((int)sp0[1], (int)sp0[-FAST_TP + 1]), (int)sp0[FAST_TP + 1]) & mR;
           const int nmax = max(max((int)sp0[-FAST_TP], (int)sp0[FAST_TP]), max(nL, nR));
-          keep = sc > nmax;                             // sc == 0 (no corner) can never exceed nmax >= 0
+          keep = sc > nmax;
           if (keep && pass == 0) sflag[FF_CELL + (cf & 15)] = 1;   // (benign race)
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -1001,8 +998,8 @@ __global__ void __launch_bounds__(DESC_NT) describe_kernel(const __grid_constant
 // ------------------------------------------------------------------------------------
 // host-side launchers (called from orbx_extract.cu)
 // ------------------------------------------------------------------------------------
-size_t orbx_fast_smem_bytes(int fastTileBytes, int fastCandCap) {
-  return (size_t)2 * fastTileBytes + 128 + 512 + (size_t)4 * fastCandCap;   // planes + tables + lists 1..3 (uint16)
+size_t orbx_fast_smem_bytes(int fastTileBytes, int fastScoreBytes, int fastCandCap) {
+  return (size_t)fastTileBytes + fastScoreBytes + 256 + 512 + (size_t)3 * fastCandCap;   // planes + tables + lists 1 and 3 (uint16)
 }
 size_t orbx_octree_smem_bytes(int nodeCap) {
   return (size_t)nodeCap * (2 * sizeof(short4) + sizeof(unsigned long long) + 4 * 2 + 16 + 4 * 4);
@@ -1010,14 +1007,14 @@ size_t orbx_octree_smem_bytes(int nodeCap) {
 
 // The dynamic shared-memory opt-in is a per-kernel, process-wide attribute while every extractor configures its own
 // need: it is only ever RAISED (a later, smaller extractor must not lower it under an earlier one that is still live).
-int orbx_extract_configure(int nodeCap, int fastTileBytes, int fastCandCap) {
+int orbx_extract_configure(int nodeCap, int fastTileBytes, int fastScoreBytes, int fastCandCap) {
   static std::mutex mu;
   static int fastMax[64] = {}, octMax[64] = {};          // per device
   std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   ORBX_CUDA(cudaGetDevice(&dev));
   dev &= 63;
-  const int fastNeed = (int)orbx_fast_smem_bytes(fastTileBytes, fastCandCap), octNeed = (int)orbx_octree_smem_bytes(nodeCap);
+  const int fastNeed = (int)orbx_fast_smem_bytes(fastTileBytes, fastScoreBytes, fastCandCap), octNeed = (int)orbx_octree_smem_bytes(nodeCap);
   if (fastNeed > fastMax[dev]) {
     ORBX_CUDA(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fastNeed));
     fastMax[dev] = fastNeed;
@@ -1041,7 +1038,7 @@ int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, 
     ORBX_LAUNCH(ctx);
   }
   ORBX_EV(1);
-  fast_cells_kernel<<<dim3(p.totalFastTiles, B), 256, orbx_fast_smem_bytes(p.fastTileBytes, p.fastCandCap), st>>>(maps, p);
+  fast_cells_kernel<<<dim3(p.totalFastTiles, B), 256, orbx_fast_smem_bytes(p.fastTileBytes, p.fastScoreBytes, p.fastCandCap), st>>>(maps, p);
   ORBX_LAUNCH(ctx);
   ORBX_EV(2);
   gauss7_kernel<<<dim3(p.totalBlurTiles, B), 256, 0, st>>>(p);
