@@ -72,9 +72,10 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__
 //   C. exact score of every survivor: the 16 ring differences are packed as (256+d, 256-d) in one s16x2 register by a
 //      single IMAD each, and the max-over-arcs-of-min network runs for both polarities at once on VIMNMX(3).S16x2
 //      (36 instructions: two neighbouring arcs share their 8 common elements).  corner <=> arcmax > t.
-//   D. cell-local 3x3 NMS over the corner list (neighbours across a cell seam count as 0, like the borders of the
-//      per-cell cv::FAST call); kept keypoints -> list 3, which pass 1 appends to.
-//   E. emission: one global atomic per tile, list 3 written out with its scores.
+//   D. cell-local 3x3 NMS over the corners (neighbours across a cell seam count as 0, like the borders of the
+//      per-cell cv::FAST call); a kept pass-0 keypoint marks its cell non-empty.
+//   E. emission: the kept keypoints of a warp (compacted in place once more) go straight to the global candidate
+//      list with their scores, one global atomic per warp and pass.
 // =====================================================================================
 #define FAST_TP ORBX_FAST_TP
 #define FAST_TPW (ORBX_FAST_TP / 4)
@@ -116,7 +117,7 @@ __device__ __forceinline__ int smem_atomic_add(int* addr, int v) {
 }
 
 // shared-memory flag words of fast_cells_kernel
-enum { FF_CELL = 0 /* [0..7] cell has a pass-0 keypoint */, FF_NCAND = 8, FF_NKEPT = 9, FF_BASE = 10,
+enum { FF_CELL = 0 /* [0..7] cell has a pass-0 keypoint */, FF_NCAND = 8,
        FF_WCORN = 16 /* [16..23] corners found by warp w (they sit at the front of its share of list 1) */ };
 
 __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ FastTmaMaps maps,
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   const int wI = tw - 6, hI = th - 6;                 // interior (evaluated) pixels; wI <= FAST_TP - 25
 
   // shared layout: [flags 128 B][mbarrier][image plane FAST_TP x (rows)][score plane FAST_TP x (rows)][column table 256 B]
-  //                [word masks 256 B][list 1: survivors, compacted in place to the corners][list 3: kept]
+  //                [word masks 256 B][list 1: survivors, compacted in place to the corners, then to the kept keypoints]
   // A pixel is named by code = y * FAST_TP + x (interior coordinates); image byte = code + 3*FAST_TP + 3 + off, score
   // byte = code + FAST_TP + 1.
   const int xa = iniX & ~15;                          // tile origin: TMA needs a 16-byte aligned innermost coordinate
@@ -147,8 +148,6 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
   uint8_t* scell = ssc + (size_t)p.fastScoreBytes;    // [wI] cell index of interior column x | 16: first | 32: last column of its cell
   uint32_t* smask = reinterpret_cast<uint32_t*>(scell + 256);   // [ncw] bytes of word c that are tested in this pass
   uint16_t* scand = reinterpret_cast<uint16_t*>(scell + 512);   // [CC]   list 1
-  uint16_t* skept = scand + CC;                       // [CC/2] list 3
-  const int capKept = CC / 2;
 
   // ---- A: load ----
   const uint8_t* img = L.pyr + (size_t)b * L.imgStride;
@@ -339,9 +338,13 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
     }
     __syncthreads();
 
-    // ---- D: NMS inside the pixel's own cell over the corners (warp w: the corners at the front of warp w's share) ----
+    // ---- D: NMS inside the pixel's own cell over the corners (warp w: the corners at the front of warp w's share),
+    //      kept keypoints compacted in place again, then written straight to the global candidate list: one global
+    //      atomic per warp and pass (every kept keypoint is final; the order of the list is irrelevant downstream) ----
     {
       const int n = cbeg + sflag[FF_WCORN + wid];
+      const unsigned ltm = (1u << lane) - 1;
+      int wkept = 0;
       for (int i0 = cbeg; i0 < n; i0 += 32) {
         const int i = i0 + lane;
         bool keep = false;
@@ -360,40 +363,30 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
           if (keep && pass == 0) sflag[FF_CELL + (cf & 15)] = 1;   // (benign race)
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m) {
-          int wbase = 0;
-          if (lane == 0) wbase = smem_atomic_add(&sflag[FF_NKEPT], __popc(m));
-          wbase = __shfl_sync(0xffffffffu, wbase, 0);
-          if (keep) {
-            const int slot = wbase + __popc(m & ((1u << lane) - 1));
-            if (slot < capKept) skept[slot] = (uint16_t)code;
-            else atomicExch(p.err, 5);
+        if (keep) scand[cbeg + wkept + __popc(m & ltm)] = (uint16_t)code;
+        wkept += __popc(m);
+      }
+      if (wkept > 0) {                                    // warp-uniform
+        int gbase = 0;
+        if (lane == 0) gbase = atomicAdd(p.candN + b * p.nlevels + level, wkept);
+        gbase = __shfl_sync(0xffffffffu, gbase, 0);
+        uint32_t* cand = p.cand + (size_t)b * p.candPerImage + L.candOfs;
+        for (int i = lane; i < wkept; i += 32) {
+          const int code = scand[cbeg + i];
+          const int y = FAST_CODE_Y(code), x = code - y * FAST_TP;
+          const int sc = ssc[code + FAST_TP + 1];
+          const int slot = gbase + i;
+          if (slot < L.candCap) {
+            // coordinates relative to (minBorderX, minBorderY), as the reference stores them (:847-848)
+            const int rx = iniX + 3 + x - ORBX_MINB, ry = iniY + 3 + y - ORBX_MINB;
+            cand[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)sc << 24);
+          } else {
+            atomicExch(p.err, 1);
           }
         }
       }
     }
     __syncthreads();
-  }
-
-  // ---- E: emission (every kept keypoint is final; ONE global atomic per tile) ----
-  const int nKept = min(sflag[FF_NKEPT], capKept);
-  if (nKept == 0) return;
-  if (tid == 0) sflag[FF_BASE] = atomicAdd(p.candN + b * p.nlevels + level, nKept);
-  __syncthreads();
-  uint32_t* cand = p.cand + (size_t)b * p.candPerImage + L.candOfs;
-  const int base = sflag[FF_BASE];
-  for (int i = tid; i < nKept; i += 256) {
-    const int code = skept[i];
-    const int y = FAST_CODE_Y(code), x = code - y * FAST_TP;
-    const int sc = ssc[code + FAST_TP + 1];
-    const int slot = base + i;
-    if (slot < L.candCap) {
-      // coordinates relative to (minBorderX, minBorderY), as the reference stores them (:847-848)
-      const int rx = iniX + 3 + x - ORBX_MINB, ry = iniY + 3 + y - ORBX_MINB;
-      cand[slot] = (uint32_t)rx | ((uint32_t)ry << 12) | ((uint32_t)sc << 24);
-    } else {
-      atomicExch(p.err, 1);
-    }
   }
 }
 
@@ -999,7 +992,7 @@ __global__ void __launch_bounds__(DESC_NT) describe_kernel(const __grid_constant
 // host-side launchers (called from orbx_extract.cu)
 // ------------------------------------------------------------------------------------
 size_t orbx_fast_smem_bytes(int fastTileBytes, int fastScoreBytes, int fastCandCap) {
-  return (size_t)fastTileBytes + fastScoreBytes + 256 + 512 + (size_t)3 * fastCandCap;   // planes + tables + lists 1 and 3 (uint16)
+  return (size_t)fastTileBytes + fastScoreBytes + 256 + 512 + (size_t)2 * fastCandCap;   // planes + tables + list 1 (uint16)
 }
 size_t orbx_octree_smem_bytes(int nodeCap) {
   return (size_t)nodeCap * (2 * sizeof(short4) + sizeof(unsigned long long) + 4 * 2 + 16 + 4 * 4);
