@@ -109,6 +109,17 @@ extern "C" {
 
 int ork_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
 
+// Persistent grid handle (used by oracle/ref_stub/ref_matcher_glue.cpp: the reference's ORBmatcher.cc compiled
+// unmodified calls Frame::GetFeaturesInArea, which lives in src/Frame.cc; the stand-in Frame answers it with this grid).
+void* ork_grid_create(const orbx_frame_desc* F) { return new Grid(F); }
+void ork_grid_destroy(void* g) { delete (Grid*)g; }
+int ork_grid_query(const void* g, float x, float y, float r, int minL, int maxL, int32_t* out, int cap) {
+  std::vector<int> v;
+  ((const Grid*)g)->query(x, y, r, minL, maxL, v);
+  for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[i];
+  return (int)v.size();
+}
+
 int ork_features_in_area(const orbx_frame_desc* F, int nq, const float* x, const float* y, const float* r,
                          const int32_t* minL, const int32_t* maxL, int32_t* out_idx, int cap, int32_t* out_n) {
   Grid g(F);

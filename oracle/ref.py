@@ -151,3 +151,119 @@ class Vocabulary:
     def distance(self, a, b):
         a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
         return self.L.ref_forb_distance(_p(a), _p(b))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ORBmatcher of the reference (src/ORBmatcher.cc, unmodified) behind the flat argument lists of the oracle / C ABI.
+# `F`, `Cur`, `KF1` ... are orbx.Frame objects (POD mirrors of orbx_frame_desc), `cam` an orbx camera struct.
+# ---------------------------------------------------------------------------------------------------------------------
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dt)
+
+
+def _pp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _ml():
+    return _lib("libref_matcher.so")
+
+
+def descriptor_distance(a, b):
+    a, b = _c(a, np.uint8), _c(b, np.uint8)
+    f = _ml().ref_descriptor_distance
+    f.argtypes = [C.c_void_p, C.c_void_p]
+    return f(_pp(a), _pp(b))
+
+
+def three_maxima(counts):
+    counts = _c(counts, np.int32)
+    out = np.zeros(3, np.int32)
+    f = _ml().ref_three_maxima
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    f(_pp(counts), len(counts), _pp(out))
+    return tuple(int(v) for v in out)
+
+
+def search_by_projection_map(F, kp_blocked, projX, projY, projXR, level, viewCos, mpDesc, flags, th, nnratio, scaleFactors):
+    """-> (nmatches, cur_mp[n]): final F.mvpMapPoints as MapPoint index (-1 none, -2 a keypoint blocked at entry)"""
+    nq = len(projX)
+    a = [_c(kp_blocked, np.uint8), _c(projX, np.float32), _c(projY, np.float32), _c(projXR, np.float32), _c(level, np.int32),
+         _c(viewCos, np.float32), _c(mpDesc, np.uint8), _c(flags, np.uint8)]
+    if a[0] is None:
+        a[0] = np.zeros(F.n, np.uint8)
+    if a[3] is None:
+        a[3] = np.zeros(nq, np.float32)
+    sf = _c(scaleFactors, np.float32)
+    cur = np.full(max(F.n, 1), -1, np.int32)
+    nm = C.c_int(0)
+    f = _ml().ref_search_by_projection_map
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    f(F.ref(), _pp(a[0]), nq, *[_pp(v) for v in a[1:]], float(th), float(nnratio), _pp(sf), len(sf), _pp(cur), C.byref(nm))
+    return nm.value, cur[:F.n]
+
+
+def search_by_projection_frame(Cur, cur_blocked, cam, Tcw_cur, Tcw_last, flags, xw, octave, angle, mpDesc, th, bMono, checkOri,
+                               scaleFactors):
+    """-> (nmatches, cur_match[n]): final CurrentFrame.mvpMapPoints as last-frame index (-1 none, -2 blocked at entry)"""
+    nq = len(flags)
+    blk = _c(cur_blocked, np.uint8)
+    if blk is None:
+        blk = np.zeros(Cur.n, np.uint8)
+    a = [_c(Tcw_cur, np.float32), _c(Tcw_last, np.float32)]
+    b = [_c(flags, np.uint8), _c(xw, np.float32), _c(octave, np.int32), _c(angle, np.float32), _c(mpDesc, np.uint8)]
+    sf = _c(scaleFactors, np.float32)
+    cur = np.full(max(Cur.n, 1), -1, np.int32)
+    nm = C.c_int(0)
+    f = _ml().ref_search_by_projection_frame
+    f.argtypes = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 2
+    f(Cur.ref(), _pp(blk), C.byref(cam), _pp(a[0]), _pp(a[1]), nq, *[_pp(v) for v in b], float(th), int(bMono), int(checkOri),
+      _pp(sf), len(sf), _pp(cur), C.byref(nm))
+    return nm.value, cur[:Cur.n]
+
+
+def search_for_triangulation(KF1, KF2, has1, has2, fv1, fv2, cam1, cam2, R1w, t1w, R2w, t2w, sigma2, scaleFactors,
+                             bOnlyStereo=False, bCoarse=False, checkOri=True):
+    m12 = np.full(max(KF1.n, 1), -1, np.int32)
+    nm = C.c_int(0)
+    f1 = [_c(v, np.int32) for v in fv1]
+    f2 = [_c(v, np.int32) for v in fv2]
+    a = [_c(has1, np.uint8), _c(has2, np.uint8)]
+    g = [_c(R1w, np.float32), _c(t1w, np.float32), _c(R2w, np.float32), _c(t2w, np.float32), _c(sigma2, np.float32),
+         _c(scaleFactors, np.float32)]
+    f = _ml().ref_search_for_triangulation
+    f.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_void_p] * 8 + [C.c_int] * 4 + \
+                 [C.c_void_p, C.c_void_p]
+    f(KF1.ref(), KF2.ref(), _pp(a[0]), _pp(a[1]), len(f1[0]), _pp(f1[0]), _pp(f1[1]), _pp(f1[2]), len(f2[0]), _pp(f2[0]), _pp(f2[1]),
+      _pp(f2[2]), C.byref(cam1), C.byref(cam2), *[_pp(v) for v in g], len(g[5]), int(bOnlyStereo), int(bCoarse), int(checkOri),
+      _pp(m12), C.byref(nm))
+    return nm.value, m12[:KF1.n]
+
+
+def search_by_bow(kf, frame, kf_has_mp, fv_kf, fv_f, nnratio=0.7, check_orientation=True):
+    has = np.ascontiguousarray(kf_has_mp, np.uint8)
+    kn, ko, ki = [np.ascontiguousarray(a, np.int32) for a in fv_kf]
+    fn, fo, fi = [np.ascontiguousarray(a, np.int32) for a in fv_f]
+    out = np.full(max(frame.n, 1), -1, np.int32)
+    nm = C.c_int32(0)
+    f = _ml().ref_search_by_bow
+    f.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    f(kf.ref(), frame.ref(), _p(has), len(kn), _p(kn), _p(ko), _p(ki), len(fn), _p(fn), _p(fo), _p(fi), nnratio,
+      int(check_orientation), _p(out), C.byref(nm))
+    return nm.value, out[:frame.n]
+
+
+def fuse(kf, cam, Rcw, tcw, Ow, flags, xw, max_dist, min_dist, normal, mp_desc, th, scale_factors, inv_level_sigma2, log_scale_factor):
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)   # noqa: E731
+    Rcw, tcw, Ow, xw, max_dist, min_dist, normal = map(f32, (Rcw, tcw, Ow, xw, max_dist, min_dist, normal))
+    sf, isg = f32(scale_factors), f32(inv_level_sigma2)
+    flags = np.ascontiguousarray(flags, np.uint8)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    n = len(flags)
+    out = np.full(max(n, 1), -1, np.int32)
+    nf = C.c_int32(0)
+    f = _ml().ref_fuse
+    f.argtypes = [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    f(kf.ref(), C.byref(cam), _p(Rcw), _p(tcw), _p(Ow), n, _p(flags), _p(xw), _p(max_dist), _p(min_dist), _p(normal), _p(mp_desc), th,
+      _p(sf), _p(isg), len(sf), log_scale_factor, _p(out), C.byref(nf))
+    return nf.value, out[:n]

@@ -121,18 +121,27 @@ void GaussianBlur(InputArray src_, OutputArray dst_, Size ksize, double sigmaX, 
 float fastAtan2(float y, float x) { return ork::fast_atan2(y, x); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// float / double matrix algebra.  OpenCV evaluates A*B for CV_32F through gemm: products and the running sum are
-// taken in double (GEMMSingleMul<float,double>) in k order and rounded to float once per element; the element-wise
-// operators work in the matrix type.  tests/test_ref_stub.py checks these rules against cv2 on random matrices.
+// float / double matrix algebra, pinned to cv2 4.13 by tests/test_ref_stub.py.  cv::gemm has a small-matrix path:
+// for CV_32F with inner dimension 2..4 equal to the result's width or height, every element is the plain fp32
+// expression a0*b0 + a1*b1 (+ a2*b2 (+ a3*b3)) evaluated left to right (no FMA); everything else goes through
+// GEMMSingleMul<float,double>: products and running sum in double, rounded to float once per element.
 // ---------------------------------------------------------------------------------------------------------------
 Mat operator*(const Mat& a, const Mat& b) {
   assert(a.cols == b.rows && a.type() == b.type() && (a.type() == CV_32F || a.type() == CV_64F));
   Mat c(a.rows, b.cols, a.type());
+  const int len = a.cols;
+  const bool small32 = a.type() == CV_32F && len >= 2 && len <= 4 && (len == c.cols || len == c.rows);
   for (int i = 0; i < a.rows; ++i)
     for (int j = 0; j < b.cols; ++j) {
-      double s = 0;
-      for (int k = 0; k < a.cols; ++k) s += get_elem(a, i, k) * get_elem(b, k, j);
-      set_elem(c, i, j, s);
+      if (small32) {
+        volatile float s = a.at<float>(i, 0) * b.at<float>(0, j);   // volatile: one rounding per operation, whatever the flags
+        for (int k = 1; k < len; ++k) { volatile float p = a.at<float>(i, k) * b.at<float>(k, j); s = s + p; }
+        c.at<float>(i, j) = s;
+      } else {
+        double s = 0;
+        for (int k = 0; k < len; ++k) s += get_elem(a, i, k) * get_elem(b, k, j);
+        set_elem(c, i, j, s);
+      }
     }
   return c;
 }
