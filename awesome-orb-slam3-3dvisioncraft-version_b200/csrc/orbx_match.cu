@@ -756,10 +756,9 @@ struct TriArgs {
   int* nmatches;
 };
 
-__global__ void __launch_bounds__(128) tri_match_kernel(const FrameDev* frames, TriArgs A) {
-  const FrameDev K1 = frames[0], K2 = frames[1];
+__device__ __forceinline__ void tri_match_body(const FrameDev& K1, const FrameDev& K2, const TriArgs& A) {
   const int p1 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (p1 >= A.n1off[A.nn1]) return;
+  if (A.nn1 == 0 || A.nn2 == 0 || p1 >= A.n1off[A.nn1]) return;
   // node of position p1 (upper_bound on offsets), then the same node id in KF2
   int lo = 0, hi = A.nn1;
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (A.n1off[mid] <= p1) lo = mid; else hi = mid; }
@@ -805,8 +804,14 @@ __global__ void __launch_bounds__(128) tri_match_kernel(const FrameDev* frames, 
   if (lane == 0 && key != 0xffffffffu) A.match12[idx1] = A.n2idx[b2 + (0xfffff - (key & 0xfffff))];
 }
 
-__global__ void __launch_bounds__(256) tri_rot_filter_kernel(const FrameDev* frames, TriArgs A) {
-  const FrameDev K1 = frames[0], K2 = frames[1];
+__global__ void __launch_bounds__(128) tri_match_kernel(const FrameDev* frames, TriArgs A) { tri_match_body(frames[0], frames[1], A); }
+// many (KF1, KF2) pairs per launch: blockIdx.y = pair, its frames at frames[2q], frames[2q+1]
+__global__ void __launch_bounds__(128) tri_match_batch_kernel(const FrameDev* frames, const TriArgs* args) {
+  const int q = blockIdx.y;
+  tri_match_body(frames[2 * q], frames[2 * q + 1], args[q]);
+}
+
+__device__ __forceinline__ void tri_rot_filter_body(const FrameDev& K1, const FrameDev& K2, const TriArgs& A) {
   __shared__ int s_hist[HISTO_LENGTH];
   __shared__ int s_keep[3];
   __shared__ int s_n;
@@ -836,6 +841,11 @@ __global__ void __launch_bounds__(256) tri_rot_filter_kernel(const FrameDev* fra
     __syncthreads();
   }
   if (threadIdx.x == 0) *A.nmatches = s_n;
+}
+__global__ void __launch_bounds__(256) tri_rot_filter_kernel(const FrameDev* frames, TriArgs A) { tri_rot_filter_body(frames[0], frames[1], A); }
+__global__ void __launch_bounds__(256) tri_rot_filter_batch_kernel(const FrameDev* frames, const TriArgs* args) {
+  const int q = blockIdx.x;
+  tri_rot_filter_body(frames[2 * q], frames[2 * q + 1], args[q]);
 }
 
 // =====================================================================================
@@ -874,6 +884,37 @@ int orbx_launch_sbp_map_batch(orbx_ctx* ctx, cudaStream_t st, const FrameDev* dF
 struct orbx_ext;
 int orbx_ext_pyramid_view(orbx_ext* e, int b, int* nlevels, const uint8_t** ptr, int* w, int* h, int* pitch, float* scale,
                           float* invScale, cudaStream_t* st);
+
+// Epipole and fundamental matrix of a keyframe pair, fp32 with a fixed evaluation order (no FMA on the host: this TU's
+// host code is compiled with -ffp-contract=off).  The reference rebuilds F12 for every candidate pair
+// (src/CameraModels/Pinhole.cpp:155-160); it only depends on the two keyframes.
+static void tri_epipolar_geometry(const orbx_camera* cam1, const orbx_camera* cam2, const float* R1w, const float* t1w,
+                                  const float* R2w, const float* t2w, TriArgs& A) {
+  float Cw[3], C2[3], R12[9], t12[3], Am[9], Bm[9];
+  for (int i = 0; i < 3; ++i) Cw[i] = -(R1w[0 * 3 + i] * t1w[0] + R1w[1 * 3 + i] * t1w[1] + R1w[2 * 3 + i] * t1w[2]);
+  for (int i = 0; i < 3; ++i) C2[i] = R2w[i * 3 + 0] * Cw[0] + R2w[i * 3 + 1] * Cw[1] + R2w[i * 3 + 2] * Cw[2] + t2w[i];
+  A.epx = cam2->fx * C2[0] / C2[2] + cam2->cx;
+  A.epy = cam2->fy * C2[1] / C2[2] + cam2->cy;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      R12[i * 3 + j] = R1w[i * 3 + 0] * R2w[j * 3 + 0] + R1w[i * 3 + 1] * R2w[j * 3 + 1] + R1w[i * 3 + 2] * R2w[j * 3 + 2];
+  for (int i = 0; i < 3; ++i) t12[i] = -(R12[i * 3 + 0] * t2w[0] + R12[i * 3 + 1] * t2w[1] + R12[i * 3 + 2] * t2w[2]) + t1w[i];
+  const float tx[9] = {0, -t12[2], t12[1], t12[2], 0, -t12[0], -t12[1], t12[0], 0};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Am[i * 3 + j] = tx[i * 3 + 0] * R12[0 * 3 + j] + tx[i * 3 + 1] * R12[1 * 3 + j] + tx[i * 3 + 2] * R12[2 * 3 + j];
+  const float i1x = 1.0f / cam1->fx, i1y = 1.0f / cam1->fy, c1x = -cam1->cx * i1x, c1y = -cam1->cy * i1y;
+  const float i2x = 1.0f / cam2->fx, i2y = 1.0f / cam2->fy, c2x = -cam2->cx * i2x, c2y = -cam2->cy * i2y;
+  for (int j = 0; j < 3; ++j) {
+    Bm[0 * 3 + j] = i1x * Am[0 * 3 + j];
+    Bm[1 * 3 + j] = i1y * Am[1 * 3 + j];
+    Bm[2 * 3 + j] = c1x * Am[0 * 3 + j] + c1y * Am[1 * 3 + j] + Am[2 * 3 + j];
+  }
+  for (int i = 0; i < 3; ++i) {
+    A.F12[i * 3 + 0] = Bm[i * 3 + 0] * i2x;
+    A.F12[i * 3 + 1] = Bm[i * 3 + 1] * i2y;
+    A.F12[i * 3 + 2] = Bm[i * 3 + 0] * c2x + Bm[i * 3 + 1] * c2y + Bm[i * 3 + 2];
+  }
+}
 
 static int candidate_capacity(int nq, int n) { return std::max(1 << 16, std::min(nq, 1 << 16) * 128 + n); }
 
@@ -1154,35 +1195,7 @@ int orbx_search_for_triangulation(orbx_ctx* ctx, const orbx_frame_desc* kf1, con
   A.n2id = S.upload(nn2 ? fv2_node : &zero, std::max(nn2, 1));
   A.n2off = S.upload(nn2 ? fv2_off : &zero, nn2 + 1);
   A.n2idx = S.upload(tot2 ? fv2_idx : &zero, std::max(tot2, 1));
-  {
-    // Epipole and fundamental matrix, fp32 with a fixed evaluation order (no FMA on the host: this TU's
-    // host code is compiled with -ffp-contract=off).  The reference rebuilds F12 for every candidate pair
-    // (src/CameraModels/Pinhole.cpp:155-160); it only depends on the two keyframes.
-    float Cw[3], C2[3], R12[9], t12[3], Am[9], Bm[9];
-    for (int i = 0; i < 3; ++i) Cw[i] = -(R1w[0 * 3 + i] * t1w[0] + R1w[1 * 3 + i] * t1w[1] + R1w[2 * 3 + i] * t1w[2]);
-    for (int i = 0; i < 3; ++i) C2[i] = R2w[i * 3 + 0] * Cw[0] + R2w[i * 3 + 1] * Cw[1] + R2w[i * 3 + 2] * Cw[2] + t2w[i];
-    A.epx = cam2->fx * C2[0] / C2[2] + cam2->cx;
-    A.epy = cam2->fy * C2[1] / C2[2] + cam2->cy;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j)
-        R12[i * 3 + j] = R1w[i * 3 + 0] * R2w[j * 3 + 0] + R1w[i * 3 + 1] * R2w[j * 3 + 1] + R1w[i * 3 + 2] * R2w[j * 3 + 2];
-    for (int i = 0; i < 3; ++i) t12[i] = -(R12[i * 3 + 0] * t2w[0] + R12[i * 3 + 1] * t2w[1] + R12[i * 3 + 2] * t2w[2]) + t1w[i];
-    const float tx[9] = {0, -t12[2], t12[1], t12[2], 0, -t12[0], -t12[1], t12[0], 0};
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) Am[i * 3 + j] = tx[i * 3 + 0] * R12[0 * 3 + j] + tx[i * 3 + 1] * R12[1 * 3 + j] + tx[i * 3 + 2] * R12[2 * 3 + j];
-    const float i1x = 1.0f / cam1->fx, i1y = 1.0f / cam1->fy, c1x = -cam1->cx * i1x, c1y = -cam1->cy * i1y;
-    const float i2x = 1.0f / cam2->fx, i2y = 1.0f / cam2->fy, c2x = -cam2->cx * i2x, c2y = -cam2->cy * i2y;
-    for (int j = 0; j < 3; ++j) {
-      Bm[0 * 3 + j] = i1x * Am[0 * 3 + j];
-      Bm[1 * 3 + j] = i1y * Am[1 * 3 + j];
-      Bm[2 * 3 + j] = c1x * Am[0 * 3 + j] + c1y * Am[1 * 3 + j] + Am[2 * 3 + j];
-    }
-    for (int i = 0; i < 3; ++i) {
-      A.F12[i * 3 + 0] = Bm[i * 3 + 0] * i2x;
-      A.F12[i * 3 + 1] = Bm[i * 3 + 1] * i2y;
-      A.F12[i * 3 + 2] = Bm[i * 3 + 0] * c2x + Bm[i * 3 + 1] * c2y + Bm[i * 3 + 2];
-    }
-  }
+  tri_epipolar_geometry(cam1, cam2, R1w, t1w, R2w, t2w, A);
   A.sigma2 = S.upload(level_sigma2, nlevels);
   A.scaleFactors = S.upload(scale_factors, nlevels);
   A.onlyStereo = only_stereo;
@@ -1203,6 +1216,160 @@ int orbx_search_for_triangulation(orbx_ctx* ctx, const orbx_frame_desc* kf1, con
   ORBX_CUDA(cudaMemcpyAsync(nmatches, A.nmatches, sizeof(int), cudaMemcpyDeviceToHost, st));
   ORBX_CUDA(cudaStreamSynchronize(st));
   return ORBX_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Many SearchForTriangulation calls per launch (the keyframe-rate half of the batched mode: LocalMapping::
+// CreateNewMapPoints runs one call per covisible neighbour, src/LocalMapping.cc:501-628).  prepare() uploads the Q
+// problems once into one device pool; run() only enqueues (two memsets + two launches) on the given stream, so a
+// replay can overlap the per-frame chain; fetch() synchronises that stream and copies the matches out.
+// ------------------------------------------------------------------------------------------------------------------
+struct orbx_tri_batch {
+  orbx_ctx* ctx = nullptr;
+  int Q = 0, maxTot1 = 0;
+  uint8_t* pool = nullptr;
+  FrameDev* dFrames = nullptr;
+  TriArgs* dArgs = nullptr;
+  int* dMatch = nullptr;        // all problems' match12, back to back
+  size_t matchInts = 0;
+  int* dNm = nullptr;           // [Q]
+  std::vector<int> matchOfs, n1;
+  cudaStream_t lastStream = nullptr;
+};
+
+orbx_tri_batch* orbx_tri_batch_prepare(orbx_ctx* ctx, int Q, const orbx_tri_problem* pr, const float* level_sigma2,
+                                       const float* scale_factors, int nlevels, int check_orientation) {
+  if (!ctx || Q < 1 || !pr || !level_sigma2 || !scale_factors || nlevels < 1 || nlevels > ORBX_MAX_LEVELS) {
+    orbx_set_error("orbx_tri_batch_prepare: invalid argument");
+    return nullptr;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+  PoolBuilder B;
+  const size_t oSig = B.add(level_sigma2, sizeof(float) * nlevels), oSc = B.add(scale_factors, sizeof(float) * nlevels);
+  struct Ofs { size_t kps[2], desc[2], ur[2], has[2], id[2], off[2], idx[2]; };
+  std::vector<Ofs> O(Q);
+  std::vector<int> matchOfs(Q + 1, 0), n1(Q);
+  int maxTot1 = 0;
+  static const int zero = 0;
+  for (int q = 0; q < Q; ++q) {
+    const orbx_tri_problem& P = pr[q];
+    const orbx_frame_desc* kf[2] = {P.kf1, P.kf2};
+    const uint8_t* has[2] = {P.has_mp1, P.has_mp2};
+    const int nn[2] = {P.nn1, P.nn2};
+    const int32_t *id[2] = {P.fv1_node, P.fv2_node}, *off[2] = {P.fv1_off, P.fv2_off}, *idx[2] = {P.fv1_idx, P.fv2_idx};
+    if (!P.kf1 || !P.kf2 || !P.has_mp1 || !P.has_mp2 || !P.cam1 || !P.cam2 || !P.R1w || !P.t1w || !P.R2w || !P.t2w || P.nn1 < 0 || P.nn2 < 0 ||
+        (P.nn1 && (!P.fv1_node || !P.fv1_off || !P.fv1_idx)) || (P.nn2 && (!P.fv2_node || !P.fv2_off || !P.fv2_idx))) {
+      orbx_set_error("orbx_tri_batch_prepare: problem %d has a NULL field", q);
+      return nullptr;
+    }
+    for (int k = 0; k < 2; ++k) {
+      const orbx_frame_desc* f = kf[k];
+      if (f->n < 0 || (f->n > 0 && (!f->kps || !f->desc))) { orbx_set_error("orbx_tri_batch_prepare: invalid frame"); return nullptr; }
+      O[q].kps[k] = B.add(f->kps, sizeof(orbx_keypoint) * (size_t)f->n);
+      O[q].desc[k] = B.add(f->desc, (size_t)32 * f->n);
+      O[q].ur[k] = f->uright ? B.add(f->uright, sizeof(float) * (size_t)f->n) : (size_t)-1;
+      O[q].has[k] = B.add(has[k], (size_t)f->n);
+      const int tot = nn[k] ? off[k][nn[k]] : 0;
+      O[q].id[k] = B.add(nn[k] ? id[k] : &zero, sizeof(int) * (size_t)std::max(nn[k], 1));
+      O[q].off[k] = B.add(nn[k] ? off[k] : &zero, sizeof(int) * (size_t)(nn[k] + 1));
+      O[q].idx[k] = B.add(tot ? idx[k] : &zero, sizeof(int) * (size_t)std::max(tot, 1));
+      if (k == 0) maxTot1 = std::max(maxTot1, tot);
+    }
+    n1[q] = P.kf1->n;
+    matchOfs[q + 1] = matchOfs[q] + std::max(P.kf1->n, 1);
+  }
+  const size_t oMatch = B.reserve(sizeof(int) * (size_t)matchOfs[Q]), oNm = B.reserve(sizeof(int) * (size_t)Q);
+  const size_t oFrames = B.reserve(sizeof(FrameDev) * 2 * (size_t)Q), oArgs = B.reserve(sizeof(TriArgs) * (size_t)Q);
+  orbx_tri_batch* T = new orbx_tri_batch();
+  T->ctx = ctx; T->Q = Q; T->maxTot1 = maxTot1; T->matchOfs = matchOfs; T->n1 = n1; T->matchInts = (size_t)matchOfs[Q];
+  if (cudaMalloc(&T->pool, B.size()) != cudaSuccess) {
+    orbx_set_error("orbx_tri_batch_prepare: cudaMalloc(%zu) failed", B.size());
+    cudaGetLastError();
+    delete T;
+    return nullptr;
+  }
+  uint8_t* base = T->pool;
+  std::vector<FrameDev> F(2 * (size_t)Q);
+  std::vector<TriArgs> A(Q);
+  for (int q = 0; q < Q; ++q) {
+    const orbx_tri_problem& P = pr[q];
+    const orbx_frame_desc* kf[2] = {P.kf1, P.kf2};
+    for (int k = 0; k < 2; ++k) {
+      FrameDev& f = F[2 * (size_t)q + k];
+      memset(&f, 0, sizeof f);
+      f.n = kf[k]->n;
+      f.kps = (const orbx_keypoint*)(base + O[q].kps[k]);
+      f.desc = base + O[q].desc[k];
+      f.uright = O[q].ur[k] == (size_t)-1 ? nullptr : (const float*)(base + O[q].ur[k]);
+      f.minX = kf[k]->min_x; f.minY = kf[k]->min_y; f.maxX = kf[k]->max_x; f.maxY = kf[k]->max_y;
+    }
+    TriArgs& a = A[q];
+    a.n1 = P.kf1->n; a.n2 = P.kf2->n;
+    a.has1 = base + O[q].has[0]; a.has2 = base + O[q].has[1];
+    a.nn1 = P.nn1; a.nn2 = P.nn2;
+    a.n1id = (const int*)(base + O[q].id[0]); a.n1off = (const int*)(base + O[q].off[0]); a.n1idx = (const int*)(base + O[q].idx[0]);
+    a.n2id = (const int*)(base + O[q].id[1]); a.n2off = (const int*)(base + O[q].off[1]); a.n2idx = (const int*)(base + O[q].idx[1]);
+    tri_epipolar_geometry(P.cam1, P.cam2, P.R1w, P.t1w, P.R2w, P.t2w, a);
+    a.sigma2 = (const float*)(base + oSig);
+    a.scaleFactors = (const float*)(base + oSc);
+    a.onlyStereo = P.only_stereo; a.coarse = P.coarse; a.checkOri = check_orientation;
+    a.match12 = (int*)(base + oMatch) + matchOfs[q];
+    a.nmatches = (int*)(base + oNm) + q;
+  }
+  memcpy(B.h.data() + oFrames, F.data(), sizeof(FrameDev) * F.size());
+  memcpy(B.h.data() + oArgs, A.data(), sizeof(TriArgs) * A.size());
+  if (cudaMemcpy(T->pool, B.h.data(), B.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    orbx_set_error("orbx_tri_batch_prepare: upload failed");
+    cudaGetLastError();
+    cudaFree(T->pool);
+    delete T;
+    return nullptr;
+  }
+  T->dFrames = (FrameDev*)(base + oFrames);
+  T->dArgs = (TriArgs*)(base + oArgs);
+  T->dMatch = (int*)(base + oMatch);
+  T->dNm = (int*)(base + oNm);
+  return T;
+}
+
+int orbx_tri_batch_run(orbx_tri_batch* T, void* cuda_stream) {
+  if (!T) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(T->ctx->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : T->ctx->stream;
+  ORBX_CUDA(cudaMemsetAsync(T->dMatch, 0xff, sizeof(int) * T->matchInts, st));
+  ORBX_CUDA(cudaMemsetAsync(T->dNm, 0, sizeof(int) * (size_t)T->Q, st));
+  if (T->maxTot1 > 0) {
+    tri_match_batch_kernel<<<dim3(div_up(T->maxTot1 * 32, 128), T->Q), 128, 0, st>>>(T->dFrames, T->dArgs);
+    ORBX_LAUNCH(T->ctx);
+  }
+  tri_rot_filter_batch_kernel<<<T->Q, 256, 0, st>>>(T->dFrames, T->dArgs);
+  ORBX_LAUNCH(T->ctx);
+  ORBX_CUDA(cudaGetLastError());
+  T->lastStream = st;
+  return ORBX_OK;
+}
+
+int orbx_tri_batch_fetch(orbx_tri_batch* T, orbx_tri_problem* pr) {
+  if (!T || !pr) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(T->ctx->device));
+  ORBX_CUDA(cudaStreamSynchronize(T->lastStream ? T->lastStream : T->ctx->stream));
+  std::vector<int> m(T->matchInts), nm(T->Q);
+  ORBX_CUDA(cudaMemcpy(m.data(), T->dMatch, sizeof(int) * T->matchInts, cudaMemcpyDeviceToHost));
+  ORBX_CUDA(cudaMemcpy(nm.data(), T->dNm, sizeof(int) * (size_t)T->Q, cudaMemcpyDeviceToHost));
+  for (int q = 0; q < T->Q; ++q) {
+    if (pr[q].match12 && T->n1[q] > 0) memcpy(pr[q].match12, m.data() + T->matchOfs[q], sizeof(int) * (size_t)T->n1[q]);
+    pr[q].nmatches = nm[q];
+  }
+  return ORBX_OK;
+}
+
+void orbx_tri_batch_destroy(orbx_tri_batch* T) {
+  if (!T) return;
+  cudaSetDevice(T->ctx->device);
+  if (T->lastStream) cudaStreamSynchronize(T->lastStream);
+  cudaFree(T->pool);
+  delete T;
 }
 
 }  // extern "C"

@@ -125,6 +125,25 @@ struct DevScope {
   }
 };
 
+// Layout of a persistent device pool built on the host first: add() copies bytes into the host image and returns their
+// offset, reserve() leaves room for device-side scratch / outputs; the owner then does ONE cudaMalloc(size()) + ONE
+// cudaMemcpy and turns offsets into pointers.  Used by the prepared many-problem plans (orbx_tri_batch, orbx_lba_batch).
+struct PoolBuilder {
+  std::vector<uint8_t> h;
+  size_t reserve(size_t bytes) {
+    const size_t o = (h.size() + 255) & ~(size_t)255;
+    h.resize(o + std::max<size_t>(bytes, 1), 0);
+    return o;
+  }
+  size_t add(const void* src, size_t bytes) {
+    const size_t o = reserve(bytes);
+    if (bytes) memcpy(h.data() + o, src, bytes);
+    return o;
+  }
+  template <typename T> size_t addv(const std::vector<T>& v) { return add(v.data(), sizeof(T) * v.size()); }
+  size_t size() const { return (h.size() + 255) & ~(size_t)255; }
+};
+
 // Upload one orbx_frame_desc and allocate its grid; fills `out` (host copy of the device view).
 int orbx_upload_frame(DevScope& S, const orbx_frame_desc* f, FrameDev* out);
 // grid build for nFrames frames (d_frames = device array); one CTA per frame

@@ -830,7 +830,7 @@ __device__ double lba_errors_chi(const LbaArgs& A, const HuberD& hM, const Huber
   return chi[0];
 }
 
-__global__ void __launch_bounds__(LBA_NT) lba_kernel(const LbaArgs A) {
+static __device__ void lba_single_cta(const LbaArgs& A) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NW = LBA_NT / 32;
   __shared__ double s_red[(LBA_NT / 32) * 2];
   __shared__ int s_flag;
@@ -1183,6 +1183,22 @@ __global__ void __launch_bounds__(LBA_NT) lba_kernel(const LbaArgs A) {
     if (!A.kfFixed[k]) se3_to_Tcw(A.pose[k], A.kfT + 16 * k);
   for (int i = tid; i < 3 * A.M; i += LBA_NT) A.mpXyz[i] = (float)A.pt[i];
   (void)s_scal;
+}
+
+__global__ void __launch_bounds__(LBA_NT) lba_kernel(const LbaArgs A) { lba_single_cta(A); }
+
+// Many problems per launch, one 1024-thread CTA each (the keyframe-rate step of S independent streams): the problem's
+// argument block is staged in shared memory once, then the CTA runs exactly the single-problem code, so every result is
+// bit-identical to orbx_local_ba's single-CTA path.
+__global__ void __launch_bounds__(LBA_NT, 1) lba_batch_kernel(const LbaArgs* __restrict__ args) {
+  __shared__ LbaArgs sA;
+  {
+    const int* src = reinterpret_cast<const int*>(args + blockIdx.x);
+    int* dst = reinterpret_cast<int*>(&sA);
+    for (int i = threadIdx.x; i < (int)(sizeof(LbaArgs) / sizeof(int)); i += LBA_NT) dst[i] = src[i];
+  }
+  __syncthreads();
+  lba_single_cta(sA);
 }
 
 // =====================================================================================
@@ -2798,6 +2814,217 @@ int orbx_local_ba(orbx_ctx* ctx, int n_kf, float* kf_Tcw, const uint8_t* kf_fixe
   }
   if (h_flag) cudaFreeHost(h_flag);
   return ORBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Prepared many-problem LocalBundleAdjustment (include/orbx.h: orbx_lba_batch_*): P independent problems, one CTA each,
+// one launch.  prepare() builds every problem's adjacency exactly as orbx_local_ba does, lays inputs, indices and
+// scratch out in ONE device pool and keeps a pristine copy of the in/out arrays; run() restores them (two device copies)
+// and launches; fetch() synchronises and downloads poses, points, edge flags, iteration counts and status.
+// ------------------------------------------------------------------------------------------------------------------
+struct orbx_lba_batch {
+  orbx_ctx* ctx = nullptr;
+  int P = 0;
+  uint8_t* pool = nullptr;
+  size_t poolBytes = 0;
+  LbaArgs* dArgs = nullptr;
+  float *dKfT = nullptr, *dKfT0 = nullptr, *dMp = nullptr, *dMp0 = nullptr;   // all problems back to back
+  size_t kfFloats = 0, mpFloats = 0;
+  uint8_t* dBad = nullptr;
+  size_t badBytes = 0;
+  int* dRes = nullptr;                                                         // [P][3] iters[2], status
+  std::vector<size_t> kfOfs, mpOfs, badOfs;
+  std::vector<int> nKf, nMp, nE;
+  cudaStream_t lastStream = nullptr;
+};
+
+orbx_lba_batch* orbx_lba_batch_prepare(orbx_ctx* ctx, int P, const orbx_lba_problem* pr, const orbx_camera* cam) {
+  if (!ctx || P < 1 || !pr || !cam) {
+    orbx_set_error("orbx_lba_batch_prepare: invalid argument");
+    return nullptr;
+  }
+  for (int p = 0; p < P; ++p) {
+    const orbx_lba_problem& Q = pr[p];
+    if (Q.n_kf < 1 || Q.n_mp < 1 || Q.n_edges < 1 || !Q.kf_Tcw || !Q.kf_fixed || !Q.mp_xyz || !Q.e_kf || !Q.e_mp || !Q.e_obs || !Q.e_inv_sigma2) {
+      orbx_set_error("orbx_lba_batch_prepare: problem %d is incomplete", p);
+      return nullptr;
+    }
+    for (int e = 0; e < Q.n_edges; ++e)
+      if (Q.e_kf[e] < 0 || Q.e_kf[e] >= Q.n_kf || Q.e_mp[e] < 0 || Q.e_mp[e] >= Q.n_mp) {
+        orbx_set_error("orbx_lba_batch_prepare: problem %d, edge %d references a vertex out of range", p, e);
+        return nullptr;
+      }
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+  orbx_lba_batch* L = new orbx_lba_batch();
+  L->ctx = ctx; L->P = P;
+  L->kfOfs.assign(P + 1, 0); L->mpOfs.assign(P + 1, 0); L->badOfs.assign(P + 1, 0);
+  L->nKf.resize(P); L->nMp.resize(P); L->nE.resize(P);
+  for (int p = 0; p < P; ++p) {
+    L->nKf[p] = pr[p].n_kf; L->nMp[p] = pr[p].n_mp; L->nE[p] = pr[p].n_edges;
+    L->kfOfs[p + 1] = L->kfOfs[p] + (size_t)16 * pr[p].n_kf;
+    L->mpOfs[p + 1] = L->mpOfs[p] + (size_t)3 * pr[p].n_mp;
+    L->badOfs[p + 1] = L->badOfs[p] + (((size_t)pr[p].n_edges + 15) & ~(size_t)15);
+  }
+  L->kfFloats = L->kfOfs[P]; L->mpFloats = L->mpOfs[P]; L->badBytes = L->badOfs[P];
+  PoolBuilder B;
+  // in/out arrays of all problems, back to back, pristine copies first
+  const size_t oKf0 = B.reserve(sizeof(float) * L->kfFloats), oMp0 = B.reserve(sizeof(float) * L->mpFloats);
+  for (int p = 0; p < P; ++p) {
+    memcpy(B.h.data() + oKf0 + sizeof(float) * L->kfOfs[p], pr[p].kf_Tcw, sizeof(float) * 16 * (size_t)pr[p].n_kf);
+    memcpy(B.h.data() + oMp0 + sizeof(float) * L->mpOfs[p], pr[p].mp_xyz, sizeof(float) * 3 * (size_t)pr[p].n_mp);
+  }
+  const size_t oKf = B.reserve(sizeof(float) * L->kfFloats), oMp = B.reserve(sizeof(float) * L->mpFloats);
+  const size_t oBad = B.reserve(L->badBytes), oRes = B.reserve(sizeof(int) * 3 * (size_t)P);
+  struct Ofs { size_t fixed, ekf, emp, obs, isg, hidx, ptOfs, ptEdges, ptAllOfs, ptAllEdges, kfOfs, kfEdges, obsEdge, pose, poseBak, pt, ptBak,
+                      err, Ji, Jj, wom, omr, Hpl, BD, Hll, Dinv, Hpp, b, x, S, bs, db; int nFree; };
+  std::vector<Ofs> O(P);
+  for (int p = 0; p < P; ++p) {
+    const orbx_lba_problem& Q = pr[p];
+    const int n_kf = Q.n_kf, n_mp = Q.n_mp, n_edges = Q.n_edges;
+    // --- graph indices: identical to orbx_local_ba (the reference builds the same adjacency in g2o's buildStructure) ---
+    std::vector<int> hidx(n_kf, -1);
+    int nFree = 0;
+    for (int k = 0; k < n_kf; ++k)
+      if (!Q.kf_fixed[k]) hidx[k] = nFree++;
+    std::vector<int> ptAllOfs(n_mp + 1, 0), ptOfs(n_mp + 1, 0), kfOfs(nFree + 1, 0);
+    for (int e = 0; e < n_edges; ++e) {
+      ++ptAllOfs[Q.e_mp[e] + 1];
+      if (hidx[Q.e_kf[e]] >= 0) { ++ptOfs[Q.e_mp[e] + 1]; ++kfOfs[hidx[Q.e_kf[e]] + 1]; }
+    }
+    for (int m = 0; m < n_mp; ++m) { ptAllOfs[m + 1] += ptAllOfs[m]; ptOfs[m + 1] += ptOfs[m]; }
+    for (int k = 0; k < nFree; ++k) kfOfs[k + 1] += kfOfs[k];
+    std::vector<int> ptAllEdges(std::max(n_edges, 1)), ptEdges(std::max(ptOfs[n_mp], 1)), kfEdges(std::max(kfOfs[nFree], 1));
+    std::vector<int> obsEdge((size_t)n_mp * std::max(nFree, 1), -1);
+    {
+      std::vector<int> a(ptAllOfs.begin(), ptAllOfs.end() - 1), b(ptOfs.begin(), ptOfs.end() - 1), c(kfOfs.begin(), kfOfs.end() - 1);
+      for (int e = 0; e < n_edges; ++e) {
+        ptAllEdges[a[Q.e_mp[e]]++] = e;
+        const int hk = hidx[Q.e_kf[e]];
+        if (hk >= 0) {
+          ptEdges[b[Q.e_mp[e]]++] = e;
+          kfEdges[c[hk]++] = e;
+          obsEdge[(size_t)Q.e_mp[e] * nFree + hk] = e;
+        }
+      }
+    }
+    Ofs& o = O[p];
+    o.nFree = nFree;
+    const int n = 6 * nFree;
+    o.fixed = B.add(Q.kf_fixed, n_kf);
+    o.ekf = B.add(Q.e_kf, sizeof(int) * (size_t)n_edges);
+    o.emp = B.add(Q.e_mp, sizeof(int) * (size_t)n_edges);
+    o.obs = B.add(Q.e_obs, sizeof(float) * 3 * (size_t)n_edges);
+    o.isg = B.add(Q.e_inv_sigma2, sizeof(float) * (size_t)n_edges);
+    o.hidx = B.addv(hidx); o.ptOfs = B.addv(ptOfs); o.ptEdges = B.addv(ptEdges); o.ptAllOfs = B.addv(ptAllOfs);
+    o.ptAllEdges = B.addv(ptAllEdges); o.kfOfs = B.addv(kfOfs); o.kfEdges = B.addv(kfEdges); o.obsEdge = B.addv(obsEdge);
+    const size_t E = (size_t)n_edges, M = (size_t)n_mp, D = sizeof(double);
+    o.pose = B.reserve(sizeof(SE3d) * n_kf); o.poseBak = B.reserve(sizeof(SE3d) * n_kf);
+    o.pt = B.reserve(D * 3 * M); o.ptBak = B.reserve(D * 3 * M);
+    o.err = B.reserve(D * 3 * E); o.Ji = B.reserve(D * 9 * E); o.Jj = B.reserve(D * 18 * E); o.wom = B.reserve(D * E); o.omr = B.reserve(D * 3 * E);
+    o.Hpl = B.reserve(D * 18 * E); o.BD = B.reserve(D * 18 * E); o.Hll = B.reserve(D * 9 * M); o.Dinv = B.reserve(D * 9 * M);
+    o.Hpp = B.reserve(D * 36 * (size_t)std::max(nFree, 1));
+    o.b = B.reserve(D * ((size_t)n + 3 * M)); o.x = B.reserve(D * ((size_t)n + 3 * M));
+    o.S = B.reserve(D * (size_t)std::max(n, 1) * std::max(n, 1)); o.bs = B.reserve(D * (size_t)std::max(n, 1)); o.db = B.reserve(D * 3 * M);
+  }
+  const size_t oArgs = B.reserve(sizeof(LbaArgs) * (size_t)P);
+  if (cudaMalloc(&L->pool, B.size()) != cudaSuccess) {
+    orbx_set_error("orbx_lba_batch_prepare: cudaMalloc(%zu bytes) failed", B.size());
+    cudaGetLastError();
+    delete L;
+    return nullptr;
+  }
+  L->poolBytes = B.size();
+  uint8_t* base = L->pool;
+  std::vector<LbaArgs> A(P);
+  for (int p = 0; p < P; ++p) {
+    const orbx_lba_problem& Q = pr[p];
+    const Ofs& o = O[p];
+    LbaArgs& a = A[p];
+    memset(&a, 0, sizeof a);
+    a.K = Q.n_kf; a.M = Q.n_mp; a.E = Q.n_edges; a.nFree = o.nFree; a.n = 6 * o.nFree;
+    a.kfT = (float*)(base + oKf) + L->kfOfs[p];
+    a.kfFixed = base + o.fixed;
+    a.mpXyz = (float*)(base + oMp) + L->mpOfs[p];
+    a.ekf = (const int*)(base + o.ekf); a.emp = (const int*)(base + o.emp);
+    a.obs = (const float*)(base + o.obs); a.invSigma2 = (const float*)(base + o.isg);
+    a.fx = cam->fx; a.fy = cam->fy; a.cx = cam->cx; a.cy = cam->cy; a.bf = cam->bf;
+    a.lambdaInit = Q.lambda_init;
+    a.stop = nullptr;
+    a.hidx = (const int*)(base + o.hidx); a.ptOfs = (const int*)(base + o.ptOfs); a.ptEdges = (const int*)(base + o.ptEdges);
+    a.ptAllOfs = (const int*)(base + o.ptAllOfs); a.ptAllEdges = (const int*)(base + o.ptAllEdges);
+    a.kfOfs = (const int*)(base + o.kfOfs); a.kfEdges = (const int*)(base + o.kfEdges); a.obsEdge = (const int*)(base + o.obsEdge);
+    a.pose = (SE3d*)(base + o.pose); a.poseBak = (SE3d*)(base + o.poseBak);
+    a.pt = (double*)(base + o.pt); a.ptBak = (double*)(base + o.ptBak);
+    a.err = (double*)(base + o.err); a.Ji = (double*)(base + o.Ji); a.Jj = (double*)(base + o.Jj); a.wom = (double*)(base + o.wom);
+    a.omr = (double*)(base + o.omr); a.Hpl = (double*)(base + o.Hpl); a.BD = (double*)(base + o.BD); a.Hll = (double*)(base + o.Hll);
+    a.Dinv = (double*)(base + o.Dinv); a.Hpp = (double*)(base + o.Hpp); a.b = (double*)(base + o.b); a.x = (double*)(base + o.x);
+    a.S = (double*)(base + o.S); a.bs = (double*)(base + o.bs); a.db = (double*)(base + o.db);
+    a.edgeBad = base + oBad + L->badOfs[p];
+    a.iters = (int*)(base + oRes) + 3 * p;
+    a.status = (int*)(base + oRes) + 3 * p + 2;
+  }
+  memcpy(B.h.data() + oArgs, A.data(), sizeof(LbaArgs) * (size_t)P);
+  if (cudaMemcpy(L->pool, B.h.data(), B.h.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    orbx_set_error("orbx_lba_batch_prepare: upload failed");
+    cudaGetLastError();
+    cudaFree(L->pool);
+    delete L;
+    return nullptr;
+  }
+  L->dArgs = (LbaArgs*)(base + oArgs);
+  L->dKfT0 = (float*)(base + oKf0); L->dMp0 = (float*)(base + oMp0);
+  L->dKfT = (float*)(base + oKf); L->dMp = (float*)(base + oMp);
+  L->dBad = base + oBad;
+  L->dRes = (int*)(base + oRes);
+  return L;
+}
+
+size_t orbx_lba_batch_device_bytes(const orbx_lba_batch* L) { return L ? L->poolBytes : 0; }
+
+int orbx_lba_batch_run(orbx_lba_batch* L, void* cuda_stream) {
+  if (!L) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(L->ctx->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : L->ctx->stream;
+  ORBX_CUDA(cudaMemcpyAsync(L->dKfT, L->dKfT0, sizeof(float) * L->kfFloats, cudaMemcpyDeviceToDevice, st));
+  ORBX_CUDA(cudaMemcpyAsync(L->dMp, L->dMp0, sizeof(float) * L->mpFloats, cudaMemcpyDeviceToDevice, st));
+  lba_batch_kernel<<<L->P, LBA_NT, 0, st>>>(L->dArgs);
+  ORBX_LAUNCH(L->ctx);
+  ORBX_CUDA(cudaGetLastError());
+  L->lastStream = st;
+  return ORBX_OK;
+}
+
+int orbx_lba_batch_fetch(orbx_lba_batch* L, orbx_lba_problem* pr) {
+  if (!L || !pr) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(L->ctx->device));
+  ORBX_CUDA(cudaStreamSynchronize(L->lastStream ? L->lastStream : L->ctx->stream));
+  std::vector<float> kf(L->kfFloats), mp(L->mpFloats);
+  std::vector<uint8_t> bad(L->badBytes);
+  std::vector<int> res(3 * (size_t)L->P);
+  ORBX_CUDA(cudaMemcpy(kf.data(), L->dKfT, sizeof(float) * L->kfFloats, cudaMemcpyDeviceToHost));
+  ORBX_CUDA(cudaMemcpy(mp.data(), L->dMp, sizeof(float) * L->mpFloats, cudaMemcpyDeviceToHost));
+  ORBX_CUDA(cudaMemcpy(bad.data(), L->dBad, L->badBytes, cudaMemcpyDeviceToHost));
+  ORBX_CUDA(cudaMemcpy(res.data(), L->dRes, sizeof(int) * res.size(), cudaMemcpyDeviceToHost));
+  for (int p = 0; p < L->P; ++p) {
+    pr[p].iters[0] = res[3 * (size_t)p];
+    pr[p].iters[1] = res[3 * (size_t)p + 1];
+    pr[p].status = res[3 * (size_t)p + 2];
+    if (pr[p].edge_bad) memcpy(pr[p].edge_bad, bad.data() + L->badOfs[p], (size_t)L->nE[p]);
+    if (pr[p].status == 0) {   // an aborted optimisation leaves the caller's poses and points as they were
+      if (pr[p].kf_Tcw) memcpy(pr[p].kf_Tcw, kf.data() + L->kfOfs[p], sizeof(float) * 16 * (size_t)L->nKf[p]);
+      if (pr[p].mp_xyz) memcpy(pr[p].mp_xyz, mp.data() + L->mpOfs[p], sizeof(float) * 3 * (size_t)L->nMp[p]);
+    }
+  }
+  return ORBX_OK;
+}
+
+void orbx_lba_batch_destroy(orbx_lba_batch* L) {
+  if (!L) return;
+  cudaSetDevice(L->ctx->device);
+  if (L->lastStream) cudaStreamSynchronize(L->lastStream);
+  cudaFree(L->pool);
+  delete L;
 }
 
 // Many-problem form (one CTA per problem, one launch); the single call below is the P = 1 case.

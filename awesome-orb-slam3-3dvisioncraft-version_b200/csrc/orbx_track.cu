@@ -7,12 +7,19 @@
 //   Tracking::TrackLocalMap         src/Tracking.cc:2436-2480 -> SearchLocalPoints (:2848-2967: frustum test, points
 //                                                                 already matched are skipped), SearchByProjection(F,
 //                                                                 local points, th), PoseOptimization
-// The map each stream tracks against is synthesised from the frame itself (no dataset offline): stereo points
-// back-projected at the true pose stand in for the last frame's / local map's MapPoints.  The glue kernels
-// here (back-projection, edge gathering, frustum projection) are the device form of that harness and of
-// Frame::isInFrustum's projection (src/Frame.cc:571-660); the heavy kernels are the ones behind the
-// single-frame C ABI.
+// Two sources for the map each stream tracks against (no dataset offline):
+//   * self-map (round 1, kept for continuity): the frame's own stereo points back-projected at the true pose stand in
+//     for the last frame's / local map's MapPoints, with the frame's own descriptors (every true match has Hamming 0);
+//   * given map (orbx_tracker_set_map): the caller supplies, per stream, the local map as flat arrays —
+//     world positions, descriptors (bit-flipped copies + distractors), last-frame bookkeeping, distance-invariance
+//     range and normals — as the shim would flatten Tracking's mvpLocalMapPoints; the local-map search then runs the
+//     full Frame::isInFrustum test (src/Frame.cc:571-650) with MapPoint::PredictScale.
+// With orbx_tracker_set_chain the motion-model prior of step t+1 is built on the device from the pose step t produced
+// (Tracking::TrackWithMotionModel: mCurrentFrame.SetPose(mVelocity*mLastFrame.mTcw), src/Tracking.cc:2354).
+// The glue kernels here (back-projection, edge gathering, frustum test) are the device form of that harness; the heavy
+// kernels are the ones behind the single-frame C ABI.
 #include <algorithm>
+#include <cmath>
 #include <vector>
 #include "orbx_match.cuh"
 
@@ -26,6 +33,13 @@ int orbx_launch_pose_opt_slices(orbx_ctx* ctx, cudaStream_t st, int P, const int
 
 struct TrackDev {
   int S, cap;
+  int mcap;                   // stride of the map-indexed arrays (== cap in self-map mode)
+  int useMap;                 // 1: map given by the caller (orbx_tracker_set_map)
+  const int* nMap;            // [S] map points per stream (given map) or null
+  const uint8_t* gMapFlags;   // [S][mcap] given map: bit0 in the local map && !isBad, bit1 Observations()>0
+  const float *gMaxDist, *gMinDist, *gNormal;
+  float logScale;
+  int nlevels;
   float fx, fy, cx, cy, bf;
   float invSigma2[ORBX_MAX_LEVELS];
   const orbx_keypoint* kps;   // [2S][cap]
@@ -33,11 +47,12 @@ struct TrackDev {
   const int* n;               // [2S]
   float *uright, *depth;      // [S][cap]
   // "map points" = the frame's own stereo points
-  uint8_t* mpFlags;           // [S][cap] local map: bit0 has MapPoint, bit1 Observations()>0
-  uint8_t* lastFlags;         // [S][cap] subset of the map the *last frame* had tracked (3 of every 5 points)
-  float* xw;                  // [S][cap][3]
-  int* octave;                // [S][cap]
-  float* angle;               // [S][cap]
+  uint8_t* mpFlags;           // [S][mcap] local map: bit0 has MapPoint, bit1 Observations()>0 (self-map mode)
+  uint8_t* lastFlags;         // [S][mcap] subset of the map the *last frame* had tracked (self-map: 3 of every 5 points)
+  const float* xw;            // [S][mcap][3]
+  int* octave;                // [S][mcap] (self-map mode)
+  float* angle;               // [S][mcap]
+  float* xwOwn;               // self-map mode: the tracker's own storage behind xw
   // search 1 outputs
   int *matchIdx, *curMatch, *nm1;
   uint8_t* kept;
@@ -58,21 +73,21 @@ struct TrackDev {
 __global__ void __launch_bounds__(128) backproject_kernel(const TrackDev D) {
   const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= D.cap) return;
-  const size_t o = (size_t)s * D.cap + i;
+  const size_t o = (size_t)s * D.mcap + i;           // map-indexed arrays (keypoint i is map point i in this mode)
   const int n = D.n[2 * s];
   uint8_t fl = 0, lfl = 0;
   if (i < n) {
     const orbx_keypoint kp = D.kps[(size_t)(2 * s) * D.cap + i];
-    const float z = D.depth[o];
+    const float z = D.depth[(size_t)s * D.cap + i];
     D.octave[o] = kp.octave;
     D.angle[o] = kp.angle;
     if (z > 0) {
       const float* T = D.Ttrue + 16 * s;
       const float xc = (kp.x - D.cx) * z / D.fx, yc = (kp.y - D.cy) * z / D.fy;
       const float dx = xc - T[3], dy = yc - T[7], dz = z - T[11];
-      D.xw[3 * o] = T[0] * dx + T[4] * dy + T[8] * dz;
-      D.xw[3 * o + 1] = T[1] * dx + T[5] * dy + T[9] * dz;
-      D.xw[3 * o + 2] = T[2] * dx + T[6] * dy + T[10] * dz;
+      D.xwOwn[3 * o] = T[0] * dx + T[4] * dy + T[8] * dz;
+      D.xwOwn[3 * o + 1] = T[1] * dx + T[5] * dy + T[9] * dz;
+      D.xwOwn[3 * o + 2] = T[2] * dx + T[6] * dy + T[10] * dz;
       fl = 3;
       // the last frame had tracked ~60 % of the local map; the rest is only reachable through TrackLocalMap
       lfl = (((unsigned)i * 2654435761u) >> 16) % 5u < 3u ? 3 : 0;
@@ -87,7 +102,7 @@ __global__ void __launch_bounds__(128) backproject_kernel(const TrackDev D) {
 __global__ void __launch_bounds__(256) gather_edges_kernel(const TrackDev D, int mode) {
   const int s = blockIdx.x, tid = threadIdx.x;
   const int n = D.n[2 * s];
-  const size_t base = (size_t)s * D.cap;
+  const size_t base = (size_t)s * D.cap, mb = (size_t)s * D.mcap;
   const int* src = (mode == 0 ? D.curMatch : D.kpMp) + base;
   __shared__ int s_warp[9];
   __shared__ int s_run;
@@ -108,9 +123,9 @@ __global__ void __launch_bounds__(256) gather_edges_kernel(const TrackDev D, int
     if (has) {
       const orbx_keypoint kp = D.kps[(size_t)(2 * s) * D.cap + i];
       const size_t e = base + slot;
-      D.exw[3 * e] = D.xw[3 * (base + q)];
-      D.exw[3 * e + 1] = D.xw[3 * (base + q) + 1];
-      D.exw[3 * e + 2] = D.xw[3 * (base + q) + 2];
+      D.exw[3 * e] = D.xw[3 * (mb + q)];
+      D.exw[3 * e + 1] = D.xw[3 * (mb + q) + 1];
+      D.exw[3 * e + 2] = D.xw[3 * (mb + q) + 2];
       D.eobs[3 * e] = kp.x;
       D.eobs[3 * e + 1] = kp.y;
       D.eobs[3 * e + 2] = D.uright[base + i];
@@ -136,7 +151,7 @@ __global__ void __launch_bounds__(128) after_pose1_kernel(const TrackDev D) {
   if (q >= 0) {
     const int e = D.kpEdge[o];
     if (D.eoutlier[(size_t)s * D.cap + e]) D.curMatch[o] = -1;
-    else { blk = 1; D.mpTaken[(size_t)s * D.cap + q] = 1; }
+    else { blk = 1; D.mpTaken[(size_t)s * D.mcap + q] = 1; }
   }
   D.blocked[o] = blk;
 }
@@ -145,7 +160,7 @@ __global__ void __launch_bounds__(128) after_pose1_kernel(const TrackDev D) {
 __global__ void __launch_bounds__(128) project_map_kernel(const TrackDev D, float minX, float minY, float maxX, float maxY) {
   const int s = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= D.cap) return;
-  const size_t o = (size_t)s * D.cap + q;
+  const size_t o = (size_t)s * D.mcap + q;
   uint8_t fl = 0;
   if (q < D.n[2 * s] && (D.mpFlags[o] & 1) && !D.mpTaken[o]) {
     const float* T = D.T1 + 16 * s;
@@ -169,17 +184,76 @@ __global__ void __launch_bounds__(128) project_map_kernel(const TrackDev D, floa
   D.mapFlags[o] = fl;
 }
 
+// K-glue 4b (given map): Tracking::SearchLocalPoints (src/Tracking.cc:2848-2967) = Frame::isInFrustum(pMP, 0.5) for every local
+// MapPoint that is not already matched, with the pose of PoseOptimization #1.  Same arithmetic as frustum_kernel
+// (orbx_frame.cu, src/Frame.cc:571-650 + MapPoint::PredictScale src/MapPoint.cc:578-594); Ow = -Rcw^T tcw per stream.
+__global__ void __launch_bounds__(128) frustum_map_kernel(const TrackDev D, float minX, float minY, float maxX, float maxY) {
+  const int s = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= D.mcap) return;
+  const size_t o = (size_t)s * D.mcap + q;
+  uint8_t fl = 0;
+  if (q < D.nMap[s] && (D.gMapFlags[o] & 1) && !D.mpTaken[o]) {
+    const float* T = D.T1 + 16 * s;
+    const float Ow0 = -(T[0] * T[3] + T[4] * T[7] + T[8] * T[11]), Ow1 = -(T[1] * T[3] + T[5] * T[7] + T[9] * T[11]),
+                Ow2 = -(T[2] * T[3] + T[6] * T[7] + T[10] * T[11]);
+    const float X = D.xw[3 * o], Y = D.xw[3 * o + 1], Z = D.xw[3 * o + 2];
+    const float xc = T[0] * X + T[1] * Y + T[2] * Z + T[3];
+    const float yc = T[4] * X + T[5] * Y + T[6] * Z + T[7];
+    const float zc = T[8] * X + T[9] * Y + T[10] * Z + T[11];
+    if (!(zc < 0.0f)) {
+      const float invz = 1.0f / zc;
+      const float u = D.fx * xc / zc + D.cx, v = D.fy * yc / zc + D.cy;
+      if (!(u < minX || u > maxX) && !(v < minY || v > maxY)) {
+        const float maxDistance = 1.2f * D.gMaxDist[o], minDistance = 0.8f * D.gMinDist[o];
+        const float P0 = X - Ow0, P1 = Y - Ow1, P2 = Z - Ow2;
+        const float dist = (float)sqrt((double)P0 * (double)P0 + (double)P1 * (double)P1 + (double)P2 * (double)P2);
+        if (!(dist < minDistance || dist > maxDistance)) {
+          const double dot = (double)P0 * (double)D.gNormal[3 * o] + (double)P1 * (double)D.gNormal[3 * o + 1] + (double)P2 * (double)D.gNormal[3 * o + 2];
+          const float viewCos = (float)(dot / (double)dist);
+          if (!(viewCos < 0.5f)) {
+            const float ratio = D.gMaxDist[o] / dist;
+            int lvl = (int)ceil(log((double)ratio) / (double)D.logScale);
+            if (lvl < 0) lvl = 0; else if (lvl >= D.nlevels) lvl = D.nlevels - 1;
+            D.projX[o] = u;
+            D.projY[o] = v;
+            D.projXR[o] = u - D.bf * invz;
+            D.level[o] = lvl;
+            D.viewCos[o] = viewCos;
+            fl = (uint8_t)(1 | (D.gMapFlags[o] & 2));
+          }
+        }
+      }
+    }
+  }
+  D.mapFlags[o] = fl;
+}
+
+// K-glue 0 (chain mode): prior = dT * Tlast (4x4 row-major, fp32, fixed order), one thread per stream
+__global__ void chain_prior_kernel(const float* dT, const float* Tlast, float* prior, float* T1, int S) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const float *A = dT + 16 * s, *B = Tlast + 16 * s;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[4 * i], B[j]), __fmul_rn(A[4 * i + 1], B[4 + j])), __fmul_rn(A[4 * i + 2], B[8 + j])),
+                                __fmul_rn(A[4 * i + 3], B[12 + j]));
+      prior[16 * s + 4 * i + j] = v;
+      T1[16 * s + 4 * i + j] = v;
+    }
+}
+
 // K-glue 5: MapPoint of each keypoint after the local-map search, then per-stream stats
 __global__ void __launch_bounds__(256) merge_matches_kernel(const TrackDev D) {
   const int s = blockIdx.x, tid = threadIdx.x;
   const int n = D.n[2 * s];
-  const size_t base = (size_t)s * D.cap;
+  const size_t base = (size_t)s * D.cap, mb = (size_t)s * D.mcap;
   for (int i = tid; i < n; i += 256) D.kpMp[base + i] = D.curMatch[base + i];
   __syncthreads();
-  // replay  F.mvpMapPoints[bestIdx[q]] = pMP_q.  Every MapPoint of this harness has Observations() > 0, so a
-  // keypoint is claimed by at most one query and the scatter order is immaterial.
-  for (int q = tid; q < n; q += 256) {
-    const int b = D.bestIdx[base + q];
+  // replay  F.mvpMapPoints[bestIdx[q]] = pMP_q.  Every MapPoint of this harness has Observations() > 0 (checked by
+  // orbx_tracker_set_map's callers), so a keypoint is claimed by at most one query and the scatter order is immaterial.
+  const int nq = D.useMap ? D.nMap[s] : n;
+  for (int q = tid; q < nq; q += 256) {
+    const int b = D.bestIdx[mb + q];
     if (b >= 0) D.kpMp[base + b] = q;
   }
 }
@@ -226,6 +300,15 @@ struct TrackSlot {
   int* d_misc = nullptr;      // per-frame candidate totals / error flags
   cudaEvent_t evA = nullptr, evB = nullptr;
   bool usedB = false;
+  // host copies of the per-stream argument blocks (pointer fields follow the map binding) + the binding they hold
+  std::vector<SbpFrameArgs> hF;
+  std::vector<SbpMapArgs> hM;
+  unsigned long long mapVersion = ~0ull;
+  float* dT = nullptr;        // [S][16] chain mode: the relative motion handed to the step
+  // device copy of a host-side map (orbx_tracker_upload_map), one per slot: the map of step t is read until stage B
+  // of step t has finished, while step t+1's map is already being uploaded into the other slot
+  uint8_t* mapBuf = nullptr;
+  cudaEvent_t evMap = nullptr;
 };
 
 struct orbx_tracker {
@@ -260,6 +343,21 @@ struct orbx_tracker {
   cudaEvent_t evDone[2] = {};
   int ringSlot[2] = {0, 0};
   unsigned long long submitted = 0, collected = 0;
+  // given map + pose chaining
+  int mcap = 0;
+  float logScale = 1.f;
+  bool haveMap = false;
+  orbx_track_map map{};
+  unsigned long long mapVersion = 0;
+  bool chain = false;
+  float* d_Tlast = nullptr;
+  // keyframe-rate work (LocalMapping's share: CreateNewMapPoints searches + LocalBundleAdjustment of every stream),
+  // enqueued every kfPeriod-th step on its own lowest-priority stream
+  orbx_tri_batch* kfTri = nullptr;
+  orbx_lba_batch* kfLba = nullptr;
+  int kfPeriod = 0;
+  cudaStream_t stK = nullptr;
+  unsigned long long kfRuns = 0;
 };
 
 template <typename T>
@@ -272,12 +370,18 @@ static T* talloc(orbx_tracker* t, size_t count) {
 }
 
 static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float thFrame, float thMap, float nnMap) {
-  const int S = t->S, cap = t->cap;
-  const size_t SC = (size_t)S * cap;
+  const int S = t->S, cap = t->cap, mcap = t->mcap;
+  const size_t SC = (size_t)S * cap, SM = (size_t)S * mcap;
   const orbx_camera* cam = &t->cam;
   TrackDev& D = K.D;
   D.S = S;
   D.cap = cap;
+  D.mcap = mcap;
+  D.useMap = 0;
+  D.nMap = nullptr;
+  D.gMapFlags = nullptr; D.gMaxDist = D.gMinDist = D.gNormal = nullptr;
+  D.nlevels = t->nlevels;
+  D.logScale = t->logScale;
   D.fx = cam->fx; D.fy = cam->fy; D.cx = cam->cx; D.cy = cam->cy; D.bf = cam->bf;
   for (int l = 0; l < t->nlevels; ++l) D.invSigma2[l] = isg[l];
   K.d_kps = talloc<orbx_keypoint>(t, 2 * SC);
@@ -286,17 +390,19 @@ static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float th
   K.d_mono = talloc<int>(t, 2 * S);
   D.kps = K.d_kps; D.desc = K.d_desc; D.n = K.d_n;
   D.uright = talloc<float>(t, SC); D.depth = talloc<float>(t, SC);
-  D.mpFlags = talloc<uint8_t>(t, SC); D.lastFlags = talloc<uint8_t>(t, SC); D.xw = talloc<float>(t, 3 * SC);
-  D.octave = talloc<int>(t, SC); D.angle = talloc<float>(t, SC);
-  D.matchIdx = talloc<int>(t, SC); D.curMatch = talloc<int>(t, SC); D.nm1 = talloc<int>(t, S);
-  D.kept = talloc<uint8_t>(t, SC);
+  D.mpFlags = talloc<uint8_t>(t, SM); D.lastFlags = talloc<uint8_t>(t, SM); D.xwOwn = talloc<float>(t, 3 * SM);
+  D.xw = D.xwOwn;
+  D.octave = talloc<int>(t, SM); D.angle = talloc<float>(t, SM);
+  D.matchIdx = talloc<int>(t, SM); D.curMatch = talloc<int>(t, SC); D.nm1 = talloc<int>(t, S);
+  D.kept = talloc<uint8_t>(t, SM);
+  K.dT = talloc<float>(t, 16 * S);
   D.exw = talloc<float>(t, 3 * SC); D.eobs = talloc<float>(t, 3 * SC); D.eisg = talloc<float>(t, SC);
   D.ekp = talloc<int>(t, SC); D.ecount = talloc<int>(t, S); D.estart = talloc<int>(t, S); D.kpEdge = talloc<int>(t, SC);
   D.eoutlier = talloc<uint8_t>(t, SC);
   D.ninl = talloc<int>(t, 2 * S); D.iters = talloc<int>(t, 8 * S);
-  D.blocked = talloc<uint8_t>(t, SC); D.mpTaken = talloc<uint8_t>(t, SC); D.mapFlags = talloc<uint8_t>(t, SC);
-  D.projX = talloc<float>(t, SC); D.projY = talloc<float>(t, SC); D.projXR = talloc<float>(t, SC); D.viewCos = talloc<float>(t, SC);
-  D.level = talloc<int>(t, SC); D.bestIdx = talloc<int>(t, SC); D.nm2 = talloc<int>(t, S); D.kpMp = talloc<int>(t, SC);
+  D.blocked = talloc<uint8_t>(t, SC); D.mpTaken = talloc<uint8_t>(t, SM); D.mapFlags = talloc<uint8_t>(t, SM);
+  D.projX = talloc<float>(t, SM); D.projY = talloc<float>(t, SM); D.projXR = talloc<float>(t, SM); D.viewCos = talloc<float>(t, SM);
+  D.level = talloc<int>(t, SM); D.bestIdx = talloc<int>(t, SM); D.nm2 = talloc<int>(t, S); D.kpMp = talloc<int>(t, SC);
   D.Ttrue = talloc<float>(t, 16 * S); D.Tprior = talloc<float>(t, 16 * S); D.T1 = talloc<float>(t, 16 * S); D.T2 = talloc<float>(t, 16 * S);
   D.stats = talloc<int>(t, ORBX_TRACK_STATS * S);
   K.d_frames = talloc<FrameDev>(t, S);
@@ -307,11 +413,11 @@ static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float th
   K.d_misc = talloc<int>(t, 8 * S);
   int* cellStart = talloc<int>(t, (size_t)S * (ORBX_NCELLS + 1));
   int* cellIdx = talloc<int>(t, SC);
-  const int candCap = cap * 96;
+  const int candCap = mcap * 96;
   uint32_t* cand = talloc<uint32_t>(t, (size_t)S * candCap);
-  int* candOfs = talloc<int>(t, SC);
-  int* candCnt = talloc<int>(t, SC);
-  if (!cand || !candCnt || !D.stats || !K.d_scratch || !K.d_misc) return false;
+  int* candOfs = talloc<int>(t, SM);
+  int* candCnt = talloc<int>(t, SM);
+  if (!cand || !candCnt || !D.stats || !K.d_scratch || !K.d_misc || !K.dT) return false;
   if (cudaEventCreateWithFlags(&K.evA, cudaEventDisableTiming) != cudaSuccess) return false;
   if (cudaEventCreateWithFlags(&K.evB, cudaEventDisableTiming) != cudaSuccess) return false;
   // static parts of the per-frame argument blocks
@@ -319,7 +425,7 @@ static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float th
   std::vector<SbpFrameArgs> AF(S);
   std::vector<SbpMapArgs> AM(S);
   for (int s = 0; s < S; ++s) {
-    const size_t o = (size_t)s * cap;
+    const size_t o = (size_t)s * cap, m = (size_t)s * mcap;
     F[s].n = 0;
     F[s].nDev = K.d_n + 2 * s;
     F[s].kps = K.d_kps + (size_t)(2 * s) * cap;
@@ -330,21 +436,24 @@ static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float th
     F[s].minX = F[s].minY = 0; F[s].maxX = F[s].maxY = 1; F[s].wInv = F[s].hInv = 1;   // set per image size
     SbpFrameArgs& a = AF[s];
     a.nq = 0; a.nqDev = K.d_n + 2 * s; a.TcDev = D.Tprior + 16 * s;
-    a.flags = D.lastFlags + o; a.xw = D.xw + 3 * o; a.octave = D.octave + o; a.angle = D.angle + o;
+    a.flags = D.lastFlags + m; a.xw = D.xwOwn + 3 * m; a.octave = D.octave + m; a.angle = D.angle + m;
     a.mpDesc = F[s].desc;
     a.fx = cam->fx; a.fy = cam->fy; a.cx = cam->cx; a.cy = cam->cy; a.bf = cam->bf;
     a.th = thFrame; a.mode = 0; a.checkOri = 1; a.scaleFactors = t->d_scale;
-    a.candOfs = candOfs + o; a.candCnt = candCnt + o; a.cand = cand + (size_t)s * candCap; a.candCap = candCap;
+    a.candOfs = candOfs + m; a.candCnt = candCnt + m; a.cand = cand + (size_t)s * candCap; a.candCap = candCap;
     a.total = K.d_misc + 8 * s; a.err = K.d_misc + 8 * s + 1;
-    a.curBlocked = nullptr; a.matchIdx = D.matchIdx + o; a.kept = D.kept + o; a.curMatch = D.curMatch + o; a.nmatches = D.nm1 + s;
-    SbpMapArgs& m = AM[s];
-    m.nq = 0; m.nqDev = K.d_n + 2 * s;
-    m.projX = D.projX + o; m.projY = D.projY + o; m.projXR = D.projXR + o; m.viewCos = D.viewCos + o; m.level = D.level + o;
-    m.mpDesc = F[s].desc; m.flags = D.mapFlags + o; m.th = thMap; m.nnratio = nnMap; m.scaleFactors = t->d_scale;
-    m.candOfs = candOfs + o; m.candCnt = candCnt + o; m.cand = cand + (size_t)s * candCap; m.candCap = candCap;
-    m.total = K.d_misc + 8 * s + 2; m.err = K.d_misc + 8 * s + 3;
-    m.kpBlocked = D.blocked + o; m.bestIdx = D.bestIdx + o; m.nmatches = D.nm2 + s;
+    a.curBlocked = nullptr; a.matchIdx = D.matchIdx + m; a.kept = D.kept + m; a.curMatch = D.curMatch + o; a.nmatches = D.nm1 + s;
+    SbpMapArgs& g = AM[s];
+    g.nq = 0; g.nqDev = K.d_n + 2 * s;
+    g.projX = D.projX + m; g.projY = D.projY + m; g.projXR = D.projXR + m; g.viewCos = D.viewCos + m; g.level = D.level + m;
+    g.mpDesc = F[s].desc; g.flags = D.mapFlags + m; g.th = thMap; g.nnratio = nnMap; g.scaleFactors = t->d_scale;
+    g.candOfs = candOfs + m; g.candCnt = candCnt + m; g.cand = cand + (size_t)s * candCap; g.candCap = candCap;
+    g.total = K.d_misc + 8 * s + 2; g.err = K.d_misc + 8 * s + 3;
+    g.kpBlocked = D.blocked + o; g.bestIdx = D.bestIdx + m; g.nmatches = D.nm2 + s;
   }
+  K.hF = AF;
+  K.hM = AM;
+  K.mapVersion = ~0ull;
   cudaMemcpy(K.d_frames, F.data(), sizeof(FrameDev) * S, cudaMemcpyHostToDevice);
   cudaMemcpy(K.d_sbpf, AF.data(), sizeof(SbpFrameArgs) * S, cudaMemcpyHostToDevice);
   cudaMemcpy(K.d_sbpm, AM.data(), sizeof(SbpMapArgs) * S, cudaMemcpyHostToDevice);
@@ -367,8 +476,13 @@ void orbx_tracker_destroy(orbx_tracker* t) {
   for (int k = 0; k < 2; ++k) {
     if (t->slot[k].evA) cudaEventDestroy(t->slot[k].evA);
     if (t->slot[k].evB) cudaEventDestroy(t->slot[k].evB);
+    if (t->slot[k].evMap) cudaEventDestroy(t->slot[k].evMap);
   }
   if (t->ownB) cudaStreamDestroy(t->ownB);
+  if (t->stK) {
+    cudaStreamSynchronize(t->stK);
+    cudaStreamDestroy(t->stK);
+  }
   if (t->stC) {
     cudaStreamSynchronize(t->stC);
     cudaStreamDestroy(t->stC);
@@ -397,6 +511,7 @@ orbx_tracker* orbx_tracker_create(orbx_ctx* ctx, orbx_ext* ext, int S, const orb
   t->stA = t->stB = (cudaStream_t)orbx_extractor_stream(ext);
   t->S = S;
   t->cap = orbx_extractor_max_keypoints(ext);
+  t->mcap = std::max(t->cap, ORBX_TRACK_MAP_CAP);
   t->nlevels = orbx_extractor_levels(ext);
   t->cam = *cam;
   t->thFrame = th_frame;
@@ -404,6 +519,8 @@ orbx_tracker* orbx_tracker_create(orbx_ctx* ctx, orbx_ext* ext, int S, const orb
   t->nnMap = nnratio_map;
   float sc[ORBX_MAX_LEVELS], isg[ORBX_MAX_LEVELS];
   orbx_extractor_scale_tables(ext, sc, nullptr, nullptr, isg);
+  // Frame::mfLogScaleFactor = log(mfScaleFactor) (src/Frame.cc:99; the scale factor is level 1 of the extractor's table)
+  t->logScale = t->nlevels > 1 ? (float)std::log((double)sc[1]) : 1.0f;
   t->d_scale = talloc<float>(t, ORBX_MAX_LEVELS);
   if (!t->d_scale || cudaMemcpy(t->d_scale, sc, sizeof(float) * t->nlevels, cudaMemcpyHostToDevice) != cudaSuccess ||
       !slot_alloc(t, t->slot[0], isg, th_frame, th_map, nnratio_map)) {
@@ -457,8 +574,119 @@ int orbx_tracker_synchronize(orbx_tracker* t) {
   ORBX_CUDA(cudaSetDevice(t->ctx->device));
   ORBX_CUDA(cudaStreamSynchronize(t->stA));
   if (t->stB != t->stA) ORBX_CUDA(cudaStreamSynchronize(t->stB));
+  if (t->stK) ORBX_CUDA(cudaStreamSynchronize(t->stK));
   return ORBX_OK;
 }
+
+// Keyframe-rate work.  In the reference LocalMapping runs in its own thread beside Tracking (src/LocalMapping.cc:68-200):
+// a new keyframe triggers CreateNewMapPoints (one SearchForTriangulation per covisible neighbour, :501-628) and
+// Optimizer::LocalBundleAdjustment (:201) while frames keep being tracked.  Here the two prepared many-stream plans are
+// enqueued every `period`-th step on a third stream of the lowest priority, so they fill the SMs the per-frame chain
+// leaves idle; a new round is only enqueued behind the previous one (stream order).
+int orbx_tracker_set_keyframe_work(orbx_tracker* t, orbx_tri_batch* tri, orbx_lba_batch* lba, int period) {
+  if (!t || period < 0 || ((tri || lba) && period < 1)) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  if (t->stK) ORBX_CUDA(cudaStreamSynchronize(t->stK));
+  if ((tri || lba) && !t->stK) {
+    int lo = 0, hi = 0;
+    ORBX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    ORBX_CUDA(cudaStreamCreateWithPriority(&t->stK, cudaStreamNonBlocking, lo));
+  }
+  t->kfTri = tri;
+  t->kfLba = lba;
+  t->kfPeriod = (tri || lba) ? period : 0;
+  t->kfRuns = 0;
+  return ORBX_OK;
+}
+
+int orbx_tracker_map_capacity(const orbx_tracker* t) { return t ? t->mcap : ORBX_EINVAL; }
+
+int orbx_tracker_set_map(orbx_tracker* t, const orbx_track_map* map) {
+  if (!t) return ORBX_EINVAL;
+  if (map) {
+    if (map->m_cap != t->mcap || !map->n_map || !map->xw || !map->desc || !map->last_flags || !map->last_octave || !map->last_angle ||
+        !map->map_flags || !map->max_dist || !map->min_dist || !map->normal) {
+      orbx_set_error("orbx_tracker_set_map: incomplete map, or m_cap != orbx_tracker_map_capacity() = %d", t->mcap);
+      return ORBX_EINVAL;
+    }
+    t->map = *map;
+    t->haveMap = true;
+  } else {
+    t->haveMap = false;
+  }
+  t->mapVersion++;
+  return ORBX_OK;
+}
+
+// Host-side map -> the next step's slot (page-locked caller memory is DMA'd directly, on the copy stream when the
+// asynchronous pipeline is in use so that it overlaps the previous step's kernels), then bound like orbx_tracker_set_map.
+int orbx_tracker_upload_map(orbx_tracker* t, const orbx_track_map* hm) {
+  if (!t || !hm) return ORBX_EINVAL;
+  if (hm->m_cap != t->mcap || !hm->n_map || !hm->xw || !hm->desc || !hm->last_flags || !hm->last_octave || !hm->last_angle ||
+      !hm->map_flags || !hm->max_dist || !hm->min_dist || !hm->normal) {
+    orbx_set_error("orbx_tracker_upload_map: incomplete map, or m_cap != orbx_tracker_map_capacity() = %d", t->mcap);
+    return ORBX_EINVAL;
+  }
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  const bool overlap = t->stB != t->stA;
+  TrackSlot& K = t->slot[overlap ? (int)(t->stepCount & 1) : 0];
+  const size_t S = (size_t)t->S, SM = S * t->mcap;
+  // layout of the slot's map buffer
+  const size_t oN = 0, oXw = align_up(oN + 4 * S, 256), oDesc = align_up(oXw + 12 * SM, 256), oLf = align_up(oDesc + 32 * SM, 256),
+               oLo = align_up(oLf + SM, 256), oLa = align_up(oLo + 4 * SM, 256), oMf = align_up(oLa + 4 * SM, 256),
+               oMx = align_up(oMf + SM, 256), oMn = align_up(oMx + 4 * SM, 256), oNr = align_up(oMn + 4 * SM, 256),
+               total = align_up(oNr + 12 * SM, 256);
+  if (!K.mapBuf) {
+    K.mapBuf = talloc<uint8_t>(t, total);
+    if (!K.mapBuf || cudaEventCreateWithFlags(&K.evMap, cudaEventDisableTiming) != cudaSuccess) return ORBX_ECUDA;
+  }
+  cudaStream_t sc = t->stC ? t->stC : t->stA;
+  if (overlap && K.usedB) ORBX_CUDA(cudaStreamWaitEvent(sc, K.evB, 0));   // the slot's previous map is no longer read
+  uint8_t* b = K.mapBuf;
+  ORBX_CUDA(cudaMemcpyAsync(b + oN, hm->n_map, 4 * S, cudaMemcpyHostToDevice, sc));
+  ORBX_CUDA(cudaMemcpyAsync(b + oXw, hm->xw, 12 * SM, cudaMemcpyHostToDevice, sc));
+  ORBX_CUDA(cudaMemcpyAsync(b + oDesc, hm->desc, 32 * SM, cudaMemcpyHostToDevice, sc));
+  ORBX_CUDA(cudaMemcpyAsync(b + oLf, hm->last_flags, SM, cudaMemcpyHostToDevice, sc));
+  ORBX_CUDA(cudaMemcpyAsync(b + oLo, hm->last_octave, 4 * SM, cudaMemcpyHostToDevice, sc));
+  ORBX_CUDA(cudaMemcpyAsync(b + oLa, hm->last_angle, 4 * SM, cudaMemcpyHostToDevice, sc));
+  ORBX_CUDA(cudaMemcpyAsync(b + oMf, hm->map_flags, SM, cudaMemcpyHostToDevice, sc));
+  ORBX_CUDA(cudaMemcpyAsync(b + oMx, hm->max_dist, 4 * SM, cudaMemcpyHostToDevice, sc));
+  ORBX_CUDA(cudaMemcpyAsync(b + oMn, hm->min_dist, 4 * SM, cudaMemcpyHostToDevice, sc));
+  ORBX_CUDA(cudaMemcpyAsync(b + oNr, hm->normal, 12 * SM, cudaMemcpyHostToDevice, sc));
+  if (sc != t->stA) {
+    ORBX_CUDA(cudaEventRecord(K.evMap, sc));
+    ORBX_CUDA(cudaStreamWaitEvent(t->stA, K.evMap, 0));
+  }
+  orbx_track_map dm;
+  dm.m_cap = t->mcap;
+  dm.n_map = (const int32_t*)(b + oN); dm.xw = (const float*)(b + oXw); dm.desc = b + oDesc; dm.last_flags = b + oLf;
+  dm.last_octave = (const int32_t*)(b + oLo); dm.last_angle = (const float*)(b + oLa); dm.map_flags = b + oMf;
+  dm.max_dist = (const float*)(b + oMx); dm.min_dist = (const float*)(b + oMn); dm.normal = (const float*)(b + oNr);
+  dm.log_scale_factor = hm->log_scale_factor;
+  return orbx_tracker_set_map(t, &dm);
+}
+size_t orbx_tracker_map_bytes(const orbx_tracker* t) {
+  if (!t) return 0;
+  const size_t S = (size_t)t->S, SM = S * t->mcap;
+  return 4 * S + SM * (12 + 32 + 1 + 4 + 4 + 1 + 4 + 4 + 12);
+}
+
+int orbx_tracker_set_chain(orbx_tracker* t, int enable, const float* d_Tcw_init) {
+  if (!t || (enable && !d_Tcw_init)) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  int rc = orbx_tracker_synchronize(t);
+  if (rc != ORBX_OK) return rc;
+  if (enable) {
+    if (!t->d_Tlast) t->d_Tlast = talloc<float>(t, 16 * (size_t)t->S);
+    if (!t->d_Tlast) return ORBX_ECUDA;
+    ORBX_CUDA(cudaMemcpy(t->d_Tlast, d_Tcw_init, sizeof(float) * 16 * t->S, cudaMemcpyDeviceToDevice));
+  }
+  t->chain = enable != 0;
+  return ORBX_OK;
+}
+
+void* orbx_tracker_keyframe_stream(orbx_tracker* t) { return t ? (void*)t->stK : nullptr; }
+long long orbx_tracker_keyframe_runs(const orbx_tracker* t) { return t ? (long long)t->kfRuns : -1; }
 
 // image-size dependent argument blocks (stereo pyramids, grid bounds): rebuilt when (w,h) or the input binding changes
 static int tracker_bind_geometry(orbx_tracker* t, int w, int h) {
@@ -517,6 +745,36 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
 #define TRK_EV(i, st) do { if (ev) ORBX_CUDA(cudaEventRecord(ev[i], st)); } while (0)
   // the slot's buffers are free once stage B of the step that last used them has finished
   if (overlap && K.usedB) ORBX_CUDA(cudaStreamWaitEvent(sa, K.evB, 0));
+  if (K.mapVersion != t->mapVersion) {
+    // (re)bind the map-side pointers of this slot's argument blocks: the caller's flat map or the tracker's own self-map
+    const bool gm = t->haveMap;
+    const orbx_track_map& M = t->map;
+    D.useMap = gm ? 1 : 0;
+    D.nMap = gm ? M.n_map : nullptr;
+    D.xw = gm ? M.xw : D.xwOwn;
+    D.gMapFlags = gm ? M.map_flags : nullptr;
+    D.gMaxDist = gm ? M.max_dist : nullptr;
+    D.gMinDist = gm ? M.min_dist : nullptr;
+    D.gNormal = gm ? M.normal : nullptr;
+    if (gm && M.log_scale_factor > 0) D.logScale = M.log_scale_factor;
+    for (int s = 0; s < S; ++s) {
+      const size_t m = (size_t)s * t->mcap;
+      SbpFrameArgs& a = K.hF[s];
+      SbpMapArgs& g = K.hM[s];
+      const uint8_t* ownDesc = K.d_desc + (size_t)(2 * s) * cap * 32;
+      a.nqDev = gm ? M.n_map + s : K.d_n + 2 * s;
+      a.flags = gm ? M.last_flags + m : D.lastFlags + m;
+      a.xw = D.xw + 3 * m;
+      a.octave = gm ? M.last_octave + m : D.octave + m;
+      a.angle = gm ? M.last_angle + m : D.angle + m;
+      a.mpDesc = gm ? M.desc + 32 * m : ownDesc;
+      g.nqDev = a.nqDev;
+      g.mpDesc = a.mpDesc;
+    }
+    ORBX_CUDA(cudaMemcpyAsync(K.d_sbpf, K.hF.data(), sizeof(SbpFrameArgs) * S, cudaMemcpyHostToDevice, sa));
+    ORBX_CUDA(cudaMemcpyAsync(K.d_sbpm, K.hM.data(), sizeof(SbpMapArgs) * S, cudaMemcpyHostToDevice, sa));
+    K.mapVersion = t->mapVersion;
+  }
   TRK_EV(0, sa);
   // 1. Frame::Frame(stereo): ORB extraction of the 2*S images (src/Frame.cc:111-114)
   int rc = orbx_extract_batch_device(t->ext, 2 * S, d_imgs, w, h, stride, 0, 0, K.d_kps, K.d_desc, cap, K.d_n, K.d_mono);
@@ -529,10 +787,14 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
   }
   TRK_EV(1, sa);
   ORBX_CUDA(cudaMemcpyAsync(D.Ttrue, d_Tcw_true, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sa));
-  ORBX_CUDA(cudaMemcpyAsync(D.Tprior, d_Tcw_prior, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sa));
-  ORBX_CUDA(cudaMemcpyAsync(D.T1, d_Tcw_prior, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sa));
+  if (t->chain) {
+    ORBX_CUDA(cudaMemcpyAsync(K.dT, d_Tcw_prior, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sa));   // relative motion
+  } else {
+    ORBX_CUDA(cudaMemcpyAsync(D.Tprior, d_Tcw_prior, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sa));
+    ORBX_CUDA(cudaMemcpyAsync(D.T1, d_Tcw_prior, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sa));
+  }
   ORBX_CUDA(cudaMemsetAsync(K.d_misc, 0, sizeof(int) * 8 * S, sa));
-  ORBX_CUDA(cudaMemsetAsync(D.mpTaken, 0, (size_t)S * cap, sa));
+  ORBX_CUDA(cudaMemsetAsync(D.mpTaken, 0, (size_t)S * t->mcap, sa));
   // 2. ComputeStereoMatches (src/Frame.cc:132)
   rc = orbx_launch_stereo_batch(t->ctx, sa, K.d_stereo, S, cap);
   if (rc != ORBX_OK) return rc;
@@ -542,12 +804,19 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
   }
   TRK_EV(2, sb);
   // 3. synthetic map + AssignFeaturesToGrid + SearchByProjection(Cur, Last, th) (src/Tracking.cc:2370)
-  const dim3 gk(div_up(cap, 128), S);
-  backproject_kernel<<<gk, 128, 0, sb>>>(D);
-  ORBX_LAUNCH(t->ctx);
+  const dim3 gk(div_up(cap, 128), S), gm(div_up(t->mcap, 128), S);
+  const int maxQ = D.useMap ? t->mcap : cap;
+  if (t->chain) {   // motion model: prior = dT * (pose the previous step produced); stage B of that step precedes us on sb
+    chain_prior_kernel<<<div_up(S, 128), 128, 0, sb>>>(K.dT, t->d_Tlast, D.Tprior, D.T1, S);
+    ORBX_LAUNCH(t->ctx);
+  }
+  if (!D.useMap) {
+    backproject_kernel<<<gk, 128, 0, sb>>>(D);
+    ORBX_LAUNCH(t->ctx);
+  }
   rc = orbx_launch_grid_build(t->ctx, sb, K.d_frames, S);
   if (rc != ORBX_OK) return rc;
-  rc = orbx_launch_sbp_frame_batch(t->ctx, sb, K.d_frames, K.d_sbpf, S, cap, cap);
+  rc = orbx_launch_sbp_frame_batch(t->ctx, sb, K.d_frames, K.d_sbpf, S, maxQ, cap);
   if (rc != ORBX_OK) return rc;
   TRK_EV(3, sb);
   // 4. PoseOptimization (src/Tracking.cc:2395)
@@ -560,9 +829,10 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
   // 5. TrackLocalMap: SearchLocalPoints + SearchByProjection(F, local points, th) (src/Tracking.cc:2449,:2964)
   after_pose1_kernel<<<gk, 128, 0, sb>>>(D);
   ORBX_LAUNCH(t->ctx);
-  project_map_kernel<<<gk, 128, 0, sb>>>(D, 0.f, 0.f, (float)w, (float)h);
+  if (D.useMap) frustum_map_kernel<<<gm, 128, 0, sb>>>(D, 0.f, 0.f, (float)w, (float)h);
+  else project_map_kernel<<<gk, 128, 0, sb>>>(D, 0.f, 0.f, (float)w, (float)h);
   ORBX_LAUNCH(t->ctx);
-  rc = orbx_launch_sbp_map_batch(t->ctx, sb, K.d_frames, K.d_sbpm, S, cap, cap);
+  rc = orbx_launch_sbp_map_batch(t->ctx, sb, K.d_frames, K.d_sbpm, S, maxQ, cap);
   if (rc != ORBX_OK) return rc;
   TRK_EV(5, sb);
   // 6. PoseOptimization (src/Tracking.cc:2468), starting from the pose of step 4
@@ -577,6 +847,7 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
   if (rc != ORBX_OK) return rc;
   TRK_EV(6, sb);
   ORBX_CUDA(cudaMemcpyAsync(d_Tcw_out, D.T2, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sb));
+  if (t->chain) ORBX_CUDA(cudaMemcpyAsync(t->d_Tlast, D.T2, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sb));
   if (d_stats) {
     stats_kernel<<<S, 256, 0, sb>>>(D);
     ORBX_LAUNCH(t->ctx);
@@ -585,6 +856,11 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
   if (overlap) {
     ORBX_CUDA(cudaEventRecord(K.evB, sb));
     K.usedB = true;
+  }
+  if (t->kfPeriod > 0 && (t->stepCount + 1) % (unsigned long long)t->kfPeriod == 0) {
+    if (t->kfTri) { rc = orbx_tri_batch_run(t->kfTri, t->stK); if (rc != ORBX_OK) return rc; }
+    if (t->kfLba) { rc = orbx_lba_batch_run(t->kfLba, t->stK); if (rc != ORBX_OK) return rc; }
+    t->kfRuns++;
   }
   t->stepCount++;
   t->profiled = t->profiling;

@@ -14,6 +14,34 @@ class Camera(C.Structure):
                 ("bf", C.c_float), ("b", C.c_float)]
 
 
+class TriProblem(C.Structure):
+    """orbx_tri_problem (include/orbx.h): one SearchForTriangulation call of a prepared batch."""
+    _fields_ = [("kf1", C.c_void_p), ("kf2", C.c_void_p), ("has_mp1", C.c_void_p), ("has_mp2", C.c_void_p),
+                ("nn1", C.c_int32), ("fv1_node", C.c_void_p), ("fv1_off", C.c_void_p), ("fv1_idx", C.c_void_p),
+                ("nn2", C.c_int32), ("fv2_node", C.c_void_p), ("fv2_off", C.c_void_p), ("fv2_idx", C.c_void_p),
+                ("cam1", C.c_void_p), ("cam2", C.c_void_p), ("R1w", C.c_void_p), ("t1w", C.c_void_p), ("R2w", C.c_void_p),
+                ("t2w", C.c_void_p), ("only_stereo", C.c_int32), ("coarse", C.c_int32), ("match12", C.c_void_p),
+                ("nmatches", C.c_int32)]
+
+
+class LbaProblem(C.Structure):
+    """orbx_lba_problem (include/orbx.h): one LocalBundleAdjustment of a prepared batch."""
+    _fields_ = [("n_kf", C.c_int32), ("n_mp", C.c_int32), ("n_edges", C.c_int32), ("kf_Tcw", C.c_void_p), ("kf_fixed", C.c_void_p),
+                ("mp_xyz", C.c_void_p), ("e_kf", C.c_void_p), ("e_mp", C.c_void_p), ("e_obs", C.c_void_p), ("e_inv_sigma2", C.c_void_p),
+                ("lambda_init", C.c_double), ("edge_bad", C.c_void_p), ("iters", C.c_int32 * 2), ("status", C.c_int32)]
+
+
+class TrackMap(C.Structure):
+    """orbx_track_map (include/orbx.h): the flat local map of every stream for one step."""
+    _fields_ = [("m_cap", C.c_int32), ("n_map", C.c_void_p), ("xw", C.c_void_p), ("desc", C.c_void_p), ("last_flags", C.c_void_p),
+                ("last_octave", C.c_void_p), ("last_angle", C.c_void_p), ("map_flags", C.c_void_p), ("max_dist", C.c_void_p),
+                ("min_dist", C.c_void_p), ("normal", C.c_void_p), ("log_scale_factor", C.c_float)]
+
+    FIELDS = (("n_map", np.int32), ("xw", np.float32), ("desc", np.uint8), ("last_flags", np.uint8), ("last_octave", np.int32),
+              ("last_angle", np.float32), ("map_flags", np.uint8), ("max_dist", np.float32), ("min_dist", np.float32),
+              ("normal", np.float32))
+
+
 def ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

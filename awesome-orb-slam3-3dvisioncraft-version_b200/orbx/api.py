@@ -4,6 +4,7 @@ import os
 import re
 import subprocess
 import numpy as np
+from . import abi
 from .abi import Frame, Camera, make_camera, ptr as _ptr, c32 as _c32  # noqa: F401
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -85,6 +86,18 @@ def load_library():
     L.orbx_pose_optimization.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_pose_optimization_batch_device.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_local_ba.argtypes = [vp, i, vp, vp, i, vp, i, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
+    L.orbx_tri_batch_prepare.restype = vp
+    L.orbx_tri_batch_prepare.argtypes = [vp, i, vp, vp, vp, i, i]
+    L.orbx_tri_batch_run.argtypes = [vp, vp]
+    L.orbx_tri_batch_fetch.argtypes = [vp, vp]
+    L.orbx_tri_batch_destroy.argtypes = [vp]
+    L.orbx_lba_batch_prepare.restype = vp
+    L.orbx_lba_batch_prepare.argtypes = [vp, i, vp, vp]
+    L.orbx_lba_batch_run.argtypes = [vp, vp]
+    L.orbx_lba_batch_fetch.argtypes = [vp, vp]
+    L.orbx_lba_batch_destroy.argtypes = [vp]
+    L.orbx_lba_batch_device_bytes.restype = C.c_size_t
+    L.orbx_lba_batch_device_bytes.argtypes = [vp]
     L.orbx_pose_inertial_optimization_last_keyframe.argtypes = [vp, i] + [vp] * 14 + [i] + [vp] * 4
     L.orbx_pose_inertial_optimization_last_frame.argtypes = [vp, i] + [vp] * 18 + [i] + [vp] * 4
     L.orbx_pose_inertial_optimization_last_frame_batch.argtypes = [vp, i] + [vp] * 19 + [i] + [vp] * 4
@@ -100,6 +113,17 @@ def load_library():
     L.orbx_tracker_result_stream.restype = vp
     L.orbx_tracker_result_stream.argtypes = [vp]
     L.orbx_tracker_synchronize.argtypes = [vp]
+    L.orbx_tracker_set_keyframe_work.argtypes = [vp, vp, vp, i]
+    L.orbx_tracker_map_capacity.argtypes = [vp]
+    L.orbx_tracker_map_bytes.restype = C.c_size_t
+    L.orbx_tracker_map_bytes.argtypes = [vp]
+    L.orbx_tracker_set_map.argtypes = [vp, vp]
+    L.orbx_tracker_upload_map.argtypes = [vp, vp]
+    L.orbx_tracker_set_chain.argtypes = [vp, i, vp]
+    L.orbx_tracker_keyframe_stream.restype = vp
+    L.orbx_tracker_keyframe_stream.argtypes = [vp]
+    L.orbx_tracker_keyframe_runs.restype = C.c_longlong
+    L.orbx_tracker_keyframe_runs.argtypes = [vp]
     L.orbx_tracker_set_profiling.argtypes = [vp, i]
     L.orbx_tracker_stage_ms.argtypes = [vp, vp]
     L.orbx_pyramid_level.argtypes = [vp, i, i, vp, i, vp, vp]
@@ -394,6 +418,104 @@ def stereo_match(ctx, extL, bL, extR, bR, kpL, descL, kpR, descR, bf, b):
     return ur, dp
 
 
+class TriangulationBatch:
+    """Prepared plan of many ORBmatcher::SearchForTriangulation calls (orbx_tri_batch_*, include/orbx.h): the
+    CreateNewMapPoints searches of the keyframe-rate step of many streams, one launch sequence.
+
+    problems: list of dicts with the arguments of ORBmatcher.SearchForTriangulation
+              (KF1, KF2, has1, has2, fv1, fv2, cam1, cam2, R1w, t1w, R2w, t2w, only_stereo, coarse)."""
+
+    def __init__(self, ctx, problems, sigma2, scaleFactors, check_orientation=True):
+        self.ctx, self.Q = ctx, len(problems)
+        self._keep = []
+        self.P = (abi.TriProblem * self.Q)()
+        self.match = []
+        for q, pr in enumerate(problems):
+            f1 = [_c32(v, np.int32) for v in pr["fv1"]]
+            f2 = [_c32(v, np.int32) for v in pr["fv2"]]
+            a = [_c32(pr["has1"], np.uint8), _c32(pr["has2"], np.uint8), _c32(pr["R1w"], np.float32), _c32(pr["t1w"], np.float32),
+                 _c32(pr["R2w"], np.float32), _c32(pr["t2w"], np.float32)]
+            m = np.full(max(pr["KF1"].n, 1), -1, np.int32)
+            self._keep += [f1, f2, a, pr["KF1"], pr["KF2"], pr["cam1"], pr["cam2"]]
+            self.match.append(m)
+            P = self.P[q]
+            P.kf1, P.kf2 = C.addressof(pr["KF1"].c), C.addressof(pr["KF2"].c)
+            P.has_mp1, P.has_mp2 = a[0].ctypes.data, a[1].ctypes.data
+            P.nn1, P.fv1_node, P.fv1_off, P.fv1_idx = len(f1[0]), f1[0].ctypes.data, f1[1].ctypes.data, f1[2].ctypes.data
+            P.nn2, P.fv2_node, P.fv2_off, P.fv2_idx = len(f2[0]), f2[0].ctypes.data, f2[1].ctypes.data, f2[2].ctypes.data
+            P.cam1, P.cam2 = C.addressof(pr["cam1"]), C.addressof(pr["cam2"])
+            P.R1w, P.t1w, P.R2w, P.t2w = a[2].ctypes.data, a[3].ctypes.data, a[4].ctypes.data, a[5].ctypes.data
+            P.only_stereo, P.coarse = int(pr.get("only_stereo", False)), int(pr.get("coarse", False))
+            P.match12 = m.ctypes.data
+        sg, sf = _c32(sigma2, np.float32), _c32(scaleFactors, np.float32)
+        self.h = load_library().orbx_tri_batch_prepare(ctx.h, self.Q, C.byref(self.P), _p(sg), _p(sf), len(sf), int(check_orientation))
+        if not self.h:
+            raise OrbxError("orbx_tri_batch_prepare: " + load_library().orbx_last_error().decode(errors="replace"))
+
+    def run(self, stream=None):
+        _check(load_library().orbx_tri_batch_run(self.h, stream), "orbx_tri_batch_run")
+
+    def fetch(self):
+        """-> list of (nmatches, match12[n1])"""
+        _check(load_library().orbx_tri_batch_fetch(self.h, C.byref(self.P)), "orbx_tri_batch_fetch")
+        return [(int(self.P[q].nmatches), self.match[q][:self._keep[7 * q + 3].n].copy()) for q in range(self.Q)]
+
+    def close(self):
+        if getattr(self, "h", None):
+            load_library().orbx_tri_batch_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class LocalBABatch:
+    """Prepared plan of many Optimizer::LocalBundleAdjustment problems (orbx_lba_batch_*, include/orbx.h), one CTA per
+    problem in one launch.  problems: list of dicts (kf_T, kf_fixed, mp_xyz, e_kf, e_mp, e_obs, e_inv_sigma2[, lambda_init])."""
+
+    def __init__(self, ctx, problems, cam):
+        self.ctx, self.n = ctx, len(problems)
+        self.P = (abi.LbaProblem * self.n)()
+        self._keep, self.out = [cam], []
+        for q, pr in enumerate(problems):
+            T = np.array(pr["kf_T"], np.float32).reshape(-1, 16).copy()
+            X = np.array(pr["mp_xyz"], np.float32).reshape(-1, 3).copy()
+            a = [_c32(pr["kf_fixed"], np.uint8), _c32(pr["e_kf"], np.int32), _c32(pr["e_mp"], np.int32), _c32(pr["e_obs"], np.float32),
+                 _c32(pr["e_inv_sigma2"], np.float32)]
+            bad = np.zeros(max(len(a[1]), 1), np.uint8)
+            self._keep.append(a)
+            self.out.append((T, X, bad))
+            P = self.P[q]
+            P.n_kf, P.n_mp, P.n_edges = len(T), len(X), len(a[1])
+            P.kf_Tcw, P.kf_fixed, P.mp_xyz = T.ctypes.data, a[0].ctypes.data, X.ctypes.data
+            P.e_kf, P.e_mp, P.e_obs, P.e_inv_sigma2 = a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, a[4].ctypes.data
+            P.lambda_init = float(pr.get("lambda_init", 0.0))
+            P.edge_bad = bad.ctypes.data
+        self.h = load_library().orbx_lba_batch_prepare(ctx.h, self.n, C.byref(self.P), C.byref(cam))
+        if not self.h:
+            raise OrbxError("orbx_lba_batch_prepare: " + load_library().orbx_last_error().decode(errors="replace"))
+        self.device_bytes = load_library().orbx_lba_batch_device_bytes(self.h)
+
+    def run(self, stream=None):
+        _check(load_library().orbx_lba_batch_run(self.h, stream), "orbx_lba_batch_run")
+
+    def fetch(self):
+        """-> list of (kf_T[K,4,4], mp_xyz[M,3], edge_bad[E], iters[2], status), like Optimizer.LocalBundleAdjustment"""
+        _check(load_library().orbx_lba_batch_fetch(self.h, C.byref(self.P)), "orbx_lba_batch_fetch")
+        res = []
+        for q in range(self.n):
+            T, X, bad = self.out[q]
+            res.append((T.reshape(-1, 4, 4).copy(), X.copy(), bad[:self.P[q].n_edges].copy(),
+                        np.array([self.P[q].iters[0], self.P[q].iters[1]], np.int32), int(self.P[q].status)))
+        return res
+
+    def close(self):
+        if getattr(self, "h", None):
+            load_library().orbx_lba_batch_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
 class Optimizer:
     """Mirror of the static ORB_SLAM3::Optimizer entry points on the hot path (include/Optimizer.h:58,62,64,65)."""
 
@@ -617,6 +739,61 @@ class Tracker:
     @property
     def result_stream(self):
         return load_library().orbx_tracker_result_stream(self.h)
+
+    @property
+    def map_capacity(self):
+        return load_library().orbx_tracker_map_capacity(self.h)
+
+    @property
+    def map_bytes(self):
+        return load_library().orbx_tracker_map_bytes(self.h)
+
+    def _track_map(self, fields, log_scale_factor):
+        m = abi.TrackMap()
+        m.m_cap = self.map_capacity
+        m.log_scale_factor = float(log_scale_factor)
+        for name, _ in abi.TrackMap.FIELDS:
+            setattr(m, name, fields[name])
+        return m
+
+    def set_map(self, device_ptrs, log_scale_factor=0.0):
+        """device_ptrs: dict name -> device address of the arrays of orbx_track_map (stride map_capacity); None detaches."""
+        if device_ptrs is None:
+            _check(load_library().orbx_tracker_set_map(self.h, None), "orbx_tracker_set_map")
+            return
+        m = self._track_map(device_ptrs, log_scale_factor)
+        _check(load_library().orbx_tracker_set_map(self.h, C.byref(m)), "orbx_tracker_set_map")
+
+    def upload_map(self, host_arrays, log_scale_factor=0.0):
+        """host_arrays: dict name -> numpy array ([S, map_capacity(, 3|32)], dtypes of abi.TrackMap.FIELDS); copied to
+        the device for the NEXT step (call right before step / submit)."""
+        keep = {}
+        for name, dt in abi.TrackMap.FIELDS:
+            a = host_arrays[name]
+            assert a.dtype == dt and a.flags["C_CONTIGUOUS"], name
+            keep[name] = a.ctypes.data
+        self._map_keep = host_arrays
+        m = self._track_map(keep, log_scale_factor)
+        _check(load_library().orbx_tracker_upload_map(self.h, C.byref(m)), "orbx_tracker_upload_map")
+
+    def set_chain(self, enable, d_Tcw_init=None):
+        """Motion-model chaining: Tcw_prior of the following steps is the relative motion; d_Tcw_init = device [S,16]."""
+        _check(load_library().orbx_tracker_set_chain(self.h, int(bool(enable)), d_Tcw_init), "orbx_tracker_set_chain")
+
+    def set_keyframe_work(self, tri_batch, lba_batch, period):
+        """Every `period`-th step enqueue the keyframe-rate plans (TriangulationBatch, LocalBABatch) on a third stream."""
+        self._kf = (tri_batch, lba_batch)
+        _check(load_library().orbx_tracker_set_keyframe_work(self.h, tri_batch.h if tri_batch else None,
+                                                             lba_batch.h if lba_batch else None, int(period)),
+               "orbx_tracker_set_keyframe_work")
+
+    @property
+    def keyframe_stream(self):
+        return load_library().orbx_tracker_keyframe_stream(self.h)
+
+    @property
+    def keyframe_runs(self):
+        return load_library().orbx_tracker_keyframe_runs(self.h)
 
     def synchronize(self):
         _check(load_library().orbx_tracker_synchronize(self.h), "orbx_tracker_synchronize")

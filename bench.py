@@ -36,11 +36,33 @@ import numpy as np  # noqa: E402
 W, H, NFEAT, NLEVELS = 752, 480, 1000, 8
 METRIC = "tracking frames/sec (extract+match+poseopt) EuRoC 752x480"
 UNIT = "stereo frames/s"
-WORKLOAD = ("EuRoC MH01-shaped stereo 752x480, 1000 feat, 8 levels: ORB extraction L+R, ComputeStereoMatches, "
-            "SearchByProjection(last frame), PoseOptimization, SearchByProjection(local map), PoseOptimization")
+CHAIN = ("ORB extraction L+R, ComputeStereoMatches, SearchByProjection(last frame), PoseOptimization, "
+         "isInFrustum + SearchByProjection(local map), PoseOptimization")
+# BASELINE.json configs[1] (the configuration the metric is quoted on) and configs[3]
+CONFIGS = {
+    "c2": dict(w=752, h=480, nfeat=1000, streams=256, n_map=1500,
+               name="EuRoC MH01-shaped stereo 752x480, 1000 feat, 8 levels"),
+    "c4": dict(w=1920, h=1080, nfeat=2000, streams=32, n_map=3000,
+               name="synthetic 1920x1080 stereo, 2000 feat, 8 levels (BASELINE config 4)"),
+}
+WORKLOAD = CONFIGS["c2"]["name"] + ": " + CHAIN
+MAP_NOTE = ("SURVEY 8(d) map per stream: every keypoint as a MapPoint (descriptor with Binomial(mean 0..40) bit flips, pixel "
+            "noise 0.6 px x scale, 20 % gross outliers displaced 3-6 px x scale) + ORBvoc distractors up to n_map points; "
+            "60 % tracked by the last frame; a ring of 3 different image sets, the prior of step t+1 = dT x pose(step t) "
+            "composed on the device")
 
 
-def level_sizes(w=W, h=H, nlevels=NLEVELS, sf=1.2):
+def set_config(name):
+    """Select the image geometry / feature budget the module-level helpers below work on."""
+    global W, H, NFEAT, WORKLOAD
+    c = CONFIGS[name]
+    W, H, NFEAT = c["w"], c["h"], c["nfeat"]
+    WORKLOAD = c["name"] + ": " + CHAIN
+    return c
+
+
+def level_sizes(w=None, h=None, nlevels=NLEVELS, sf=1.2):
+    w, h = w or W, h or H
     out, s = [], np.float32(1.0)
     for l in range(nlevels):
         inv = np.float32(1.0) / s
@@ -49,7 +71,8 @@ def level_sizes(w=W, h=H, nlevels=NLEVELS, sf=1.2):
     return out
 
 
-def algorithmic_bytes(k_per_image=NFEAT):
+def algorithmic_bytes(k_per_image=None):
+    k_per_image = k_per_image or NFEAT
     """SURVEY.md §8(d): per-image algorithmic bytes of the extractor, split per stage."""
     P = [w * h for w, h in level_sizes()]
     resize = sum(P[l - 1] + P[l] for l in range(1, len(P)))
@@ -113,22 +136,22 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def _rot(rng, deg):
+    w = rng.normal(0, 1, 3)
+    w = w / np.linalg.norm(w) * np.deg2rad(deg)
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+
+
 def make_poses(n_streams, seed=7):
     """Ground-truth pose per stream and the motion-model guess tracking starts from (0.4 deg, 1 cm off)."""
     rng = np.random.default_rng(seed)
-
-    def rot(deg):
-        w = rng.normal(0, 1, 3)
-        w = w / np.linalg.norm(w) * np.deg2rad(deg)
-        th = np.linalg.norm(w)
-        K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
-        return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
-
     Tt = np.zeros((n_streams, 4, 4), np.float32)
     Tp = np.zeros((n_streams, 4, 4), np.float32)
     for s in range(n_streams):
-        R, t = rot(rng.uniform(0.1, 10)), rng.uniform(-0.5, 0.5, 3)
-        Rp = rot(0.4)
+        R, t = _rot(rng, rng.uniform(0.1, 10)), rng.uniform(-0.5, 0.5, 3)
+        Rp = _rot(rng, 0.4)
         Tt[s] = np.eye(4)
         Tt[s][:3, :3], Tt[s][:3, 3] = R, t
         Tp[s] = np.eye(4)
@@ -136,62 +159,184 @@ def make_poses(n_streams, seed=7):
     return Tt, Tp
 
 
-def cpu_oracle_frames_per_s(n_frames, threads=1):
-    """Time the CPU oracle chain (tests/replay_reference.track_frame) on n_frames stereo frames."""
+def make_sequence(n_streams, ring, seed=7):
+    """A ring of `ring` frames per stream: true poses Tt[r][s], the relative motion dT[r][s] that takes the pose of frame
+    r-1 to the motion-model guess of frame r (true relative motion x a 0.4 deg / 1 cm model error), and the absolute
+    prior of the very first step."""
+    rng = np.random.default_rng(seed)
+    Tt = np.zeros((ring, n_streams, 4, 4), np.float64)
+    for r in range(ring):
+        for s in range(n_streams):
+            Tt[r, s] = np.eye(4)
+            Tt[r, s][:3, :3], Tt[r, s][:3, 3] = _rot(rng, rng.uniform(0.1, 10)), rng.uniform(-0.5, 0.5, 3)
+    dT = np.zeros_like(Tt)
+    for r in range(ring):
+        for s in range(n_streams):
+            E = np.eye(4)
+            E[:3, :3], E[:3, 3] = _rot(rng, 0.4), rng.normal(0, 0.01, 3)
+            dT[r, s] = E @ Tt[r, s] @ np.linalg.inv(Tt[(r - 1) % ring, s])
+    T_init = Tt[ring - 1].copy()          # the pose "before" the first step is the last frame of the ring
+    return Tt.astype(np.float32), dT.astype(np.float32), T_init.astype(np.float32)
+
+
+def build_maps(frames, Tt, n_map, m_cap, seed0):
+    """frames[s] = (kL, dL, uright, depth) of stream s -> stacked host arrays of orbx_track_map (tests/scenarios.py generator)."""
+    import scenarios as sc
+    maps = [sc.track_map_scenario(seed0 + s, f[0], f[1], f[2], f[3], Tt[s], m_cap=m_cap, n_map=min(n_map, m_cap), W=W, H=H)
+            for s, f in enumerate(frames)]
+    host = sc.stack_track_maps(maps)
+    gt = {"true_points": float(np.mean([m["gt"]["n_true"] for m in maps])),
+          "gross_outliers": float(np.mean([m["gt"]["is_outlier"].sum() for m in maps])),
+          "mean_bit_flips": float(np.mean([m["gt"]["mean_flips"] for m in maps])),
+          "map_points": int(min(n_map, m_cap))}
+    return host, gt
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU side (the ONLY places bench.py executes oracle/): cpu_baseline of the default run and `--impl reference`
+# ---------------------------------------------------------------------------------------------------------------------
+def cv2_anchor_ms(img, reps=3):
+    """Per-image time of the OpenCV primitives the reference's extractor spends its time in (cv2 4.13, one thread):
+    7 resizes, per-30-px-cell FAST at 20 with the fall-back to 7, 8 Gaussian blurs.  An ANCHOR for the oracle's speed, not
+    the reference: quadtree, orientation and descriptors are not included."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    cv2.setNumThreads(1)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        pyr = [img]
+        for l in range(1, NLEVELS):
+            w, h = level_sizes(img.shape[1], img.shape[0])[l]
+            pyr.append(cv2.resize(pyr[-1], (w, h), interpolation=cv2.INTER_LINEAR))
+        t1 = time.perf_counter()
+        f20, f7 = cv2.FastFeatureDetector_create(20, True), cv2.FastFeatureDetector_create(7, True)
+        for im in pyr:
+            h, w = im.shape
+            minb, maxbx, maxby = 16, w - 16, h - 16
+            nc, nr = int((maxbx - minb) / 30), int((maxby - minb) / 30)
+            wc, hc = int(np.ceil((maxbx - minb) / nc)), int(np.ceil((maxby - minb) / nr))
+            for i in range(nr):
+                y0 = minb + i * hc
+                if y0 >= maxby - 3:
+                    continue
+                y1 = min(y0 + hc + 6, maxby)
+                for j in range(nc):
+                    x0 = minb + j * wc
+                    if x0 >= maxbx - 6:
+                        continue
+                    cell = im[y0:y1, x0:min(x0 + wc + 6, maxbx)]
+                    if not f20.detect(cell):
+                        f7.detect(cell)
+        t2 = time.perf_counter()
+        for im in pyr:
+            cv2.GaussianBlur(im, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        t3 = time.perf_counter()
+        cur = {"pyramid": 1e3 * (t1 - t0), "fast_cells": 1e3 * (t2 - t1), "blur": 1e3 * (t3 - t2), "sum": 1e3 * (t3 - t0)}
+        if best is None or cur["sum"] < best["sum"]:
+            best = cur
+    return best
+
+
+class _CpuStreams:
+    """The CPU arm's inputs: a pool of stereo pairs, their poses and 8(d) maps (generated from the oracle's own features)."""
+
+    def __init__(self, npool=8, n_map=1500):
+        import oracle
+        import scenarios as sc
+        from orbx import abi
+        self.oracle, self.cam = oracle, abi.make_camera()
+        self.imgs = make_streams(npool)
+        self.Tt, self.Tp = make_poses(npool)
+        self.maps = []
+        ex = (oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7), oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7))
+        for j in range(npool):
+            _, kL, dL, _ = ex[0](self.imgs[2 * j])
+            _, kR, dR, _ = ex[1](self.imgs[2 * j + 1])
+            ur, dp = oracle.stereo_match([ex[0].pyramid_level(l) for l in range(NLEVELS)], [ex[1].pyramid_level(l) for l in range(NLEVELS)],
+                                         kL, dL, kR, dR, ex[0].scale, ex[0].inv_scale, sc.BF, sc.BF / sc.FX)
+            self.maps.append(sc.track_map_scenario(900 + j, kL, dL, ur, dp, self.Tt[j], n_map=n_map, W=W, H=H))
+        self.n = npool
+
+    def frame(self, j, extractors, two_threads=None):
+        from replay_reference import track_frame_map
+        j %= self.n
+        return track_frame_map(self.oracle, self.cam, self.imgs[2 * j], self.imgs[2 * j + 1], self.maps[j], self.Tp[j],
+                               nfeatures=NFEAT, extractors=extractors)
+
+
+def cpu_baseline(n_frames, warm=20):
+    """The CPU oracle chain on ONE thread over a bounded sample: per-frame latencies after `warm` warm-up frames, the
+    oracle's extraction time next to the cv2 anchor, and a 2-thread variant that extracts left and right concurrently as
+    the reference's Frame constructor does (src/Frame.cc:111-114)."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
-    from orbx import abi
-    from replay_reference import track_frame
-    imgs = make_streams(min(n_frames, 12))
-    npool = len(imgs) // 2
-    Tt, Tp = make_poses(npool)
-    cam = abi.make_camera()
-    oracle.lib()
-
-    def work(tid, count):
-        ex = (oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7), oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7))
-        for i in range(count):
-            j = (tid * 5 + i) % npool
-            track_frame(oracle, cam, imgs[2 * j], imgs[2 * j + 1], Tt[j], Tp[j], extractors=ex)
-        return count
-
-    per = [n_frames // threads + (1 if t < n_frames % threads else 0) for t in range(threads)]
-    work(0, 1)  # warm caches / page in
+    cs = _CpuStreams()
+    ex = (oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7), oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7))
+    for i in range(warm):
+        cs.frame(i, ex)
+    lat = []
+    t_all = time.perf_counter()
+    for i in range(n_frames):
+        t0 = time.perf_counter()
+        cs.frame(i, ex)
+        lat.append(time.perf_counter() - t0)
+    total = time.perf_counter() - t_all
+    lat = np.array(lat)
+    # extraction alone (oracle) vs the cv2 primitives it restates
     t0 = time.perf_counter()
-    if threads == 1:
-        work(0, per[0])
-    else:
-        with ThreadPoolExecutor(threads) as pool:
-            list(pool.map(lambda a: work(*a), enumerate(per)))
-    dt = time.perf_counter() - t0
-    return n_frames / dt, dt
+    for i in range(10):
+        ex[0](cs.imgs[(2 * i) % (2 * cs.n)])
+    ext_ms = 1e3 * (time.perf_counter() - t0) / 10
+    anchor = cv2_anchor_ms(cs.imgs[0])
+    # reference-like: left and right extraction on two threads (ctypes releases the GIL), the rest on the caller's thread
+    pool = ThreadPoolExecutor(2)
+    m = min(n_frames, 40)
+    t0 = time.perf_counter()
+    for i in range(m):
+        j = i % cs.n
+        fl, fr = pool.submit(ex[0], cs.imgs[2 * j]), pool.submit(ex[1], cs.imgs[2 * j + 1])
+        fl.result(), fr.result()
+    two_thread_ext = (time.perf_counter() - t0) / m
+    one_thread_ext = 2 * ext_ms * 1e-3
+    med = float(np.median(lat))
+    pool.shutdown()
+    return {"value": 1.0 / med, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d stereo frames of the same chain and 8(d) map workload after %d warm-up frames, %.1f s, 1 thread "
+                      "(host has %d cores); value = 1 / median frame time" % (n_frames, warm, total, os.cpu_count() or 0),
+            "frame_ms": {"median": 1e3 * med, "p95": 1e3 * float(np.percentile(lat, 95)), "mean": 1e3 * float(lat.mean())},
+            "oracle_extraction_ms_per_image": ext_ms,
+            "cv2_anchor_ms_per_image": anchor,
+            "oracle_over_cv2_primitives": (ext_ms / anchor["sum"]) if anchor else None,
+            "reference_like_two_thread": {"value": 1.0 / (med - one_thread_ext + two_thread_ext), "unit": UNIT, "cores": 2,
+                                          "note": "L/R extraction on two threads (src/Frame.cc:111-114), rest of the chain on one"},
+            "note": "the oracle is a scalar port; the cv2 anchor shows how much faster OpenCV's own primitives are than the "
+                    "oracle's (divide GPU/CPU ratios by oracle_over_cv2_primitives for an OpenCV-backed estimate)"}
 
 
 def _ref_worker(job):
     tid, count = job
     import oracle
-    from orbx import abi
-    from replay_reference import track_frame
     g = _ref_worker.__dict__
-    if "imgs" not in g:
-        g["imgs"] = make_streams(12)
-        g["poses"] = make_poses(12)
-        g["cam"] = abi.make_camera()
+    if "cs" not in g:
+        g["cs"] = _CpuStreams()
         g["ex"] = (oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7), oracle.Extractor(NFEAT, 1.2, NLEVELS, 20, 7))
-    imgs, (Tt, Tp) = g["imgs"], g["poses"]
     for i in range(count):
-        j = (tid * 5 + i) % 12
-        track_frame(oracle, g["cam"], imgs[2 * j], imgs[2 * j + 1], Tt[j], Tp[j], extractors=g["ex"])
+        g["cs"].frame(tid * 5 + i, g["ex"])
     return count
 
 
 def run_reference(args):
-    """The reference arm: the reference's CPU implementation cannot be built here (needs OpenCV 3/Eigen/Boost/
-    Pangolin), so this times the CPU oracle — a line-by-line port of it — on all host cores, one independent
-    stream per process, on a bounded sample of the same workload."""
+    """The reference arm: the reference's CMake build cannot run here (OpenCV 3 / Eigen / Boost / Pangolin are not
+    installed; oracle/_ref holds the extractor, matcher and DBoW2 compiled from the reference sources but g2o needs
+    Eigen, so the chain cannot be closed with reference code), so this times the CPU oracle — the restatement pinned to
+    those sources — on all host cores, one independent stream per process, on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    set_config(args.config)
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
@@ -212,7 +357,7 @@ def run_reference(args):
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic", "impl": "reference",
-           "config": {"workload": WORKLOAD + " (CPU oracle, %d frames/step)" % frames_per_step},
+           "config": {"workload": WORKLOAD, "map": MAP_NOTE, "sample": "CPU oracle, %d frames/step" % frames_per_step},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
                             "sample": "%d stereo frames per step x %d steps on %d processes (host has %d cores)"
                                       % (frames_per_step, args.steps, procs, cores)},
@@ -221,22 +366,18 @@ def run_reference(args):
     print(json.dumps(out))
 
 
-def reduce_over_ranks(dist, dev_ms, e2e_s, streams_per_rank, steps, e2e_steps, world, device=None):
-    """Replicas only: every rank processed `streams_per_rank` streams per step; the job's time is the
-    MAX over ranks, its throughput the total frames of all ranks over that time."""
+def reduce_over_ranks(dist, times_ms, device=None):
+    """Replicas only: the job's time for each timed region is the MAX over ranks."""
     import torch
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=device)
+    t = torch.tensor(times_ms, dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = float(t[0]), float(t[1])
-    frames = streams_per_rank * world
-    return dev_ms, e2e_s, frames * steps / (dev_ms / 1e3), frames * e2e_steps / e2e_s
+    return [float(v) for v in t]
 
 
 def run_dry(args):
     """Multi-rank plumbing on CPU (gloo): same rendezvous / barrier / reduction / JSON path as the GPU run, with the
     GPU step replaced by a deterministic synthetic timing (rank r takes (10 + r) ms per step)."""
-    import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,18 +386,17 @@ def run_dry(args):
         dist.init_process_group("gloo")
         d = dist
         dist.barrier()
-    dev_ms = (10.0 + rank) * args.steps
-    e2e_s = (20.0 + rank) * 1e-3 * 3
-    dev_ms, e2e_s, value, e2e_value = reduce_over_ranks(d, dev_ms, e2e_s, args.streams, args.steps, 3, world)
+    dev_ms, e2e_ms = reduce_over_ranks(d, [(10.0 + rank) * args.steps, (20.0 + rank) * 3])
     if d:
         dist.barrier()
+    frames = args.streams * world
     if rank == 0:
-        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        print(json.dumps({"metric": METRIC, "value": frames * args.steps / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
                           "config": {"workload": "dry-run of the multi-rank plumbing (no GPU work)",
                                      "streams_per_gpu": args.streams, "parallelism": "replicas x%d" % world},
-                          "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "e2e": {"value": frames * 3 / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0, "dry_run": True}))
     if d:
         dist.destroy_process_group()
@@ -268,21 +408,26 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
-    ap.add_argument("--streams", type=int, default=256, help="independent stereo streams per GPU per step")
-    ap.add_argument("--pipelines", type=int, default=1,
-                    help="concurrent extractor+tracker pipelines per GPU in the resident arm")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="c2: EuRoC 752x480 stereo (the metric's configuration); "
+                    "c4: 1920x1080 stereo, 2000 features (BASELINE config 4)")
+    ap.add_argument("--streams", type=int, default=0, help="independent stereo streams per GPU per step (0: the config's default)")
+    ap.add_argument("--workload", default="sec8d", choices=["sec8d", "selfmap"],
+                    help="sec8d: SURVEY 8(d) map per stream, temporal pose chain; selfmap: the round-1 best-case harness")
+    ap.add_argument("--ring", type=int, default=3, help="different image sets cycled through (sec8d)")
+    ap.add_argument("--kf-period", type=int, default=10, help="keyframe-rate work (10 x SearchForTriangulation + LocalBA per stream) "
+                    "every this many steps in the with_keyframe_step region; 0 skips the region")
     ap.add_argument("--overlap", type=int, default=1,
                     help="1: pose/matching of step t overlap extraction of step t+1 (two streams, double-buffered)")
-    ap.add_argument("--e2e-pipelines", type=int, default=1,
-                    help="pipelines in the e2e arm (each keeps two steps in flight through submit/collect)")
-    ap.add_argument("--e2e-sync", type=int, default=0,
-                    help="1: e2e arm uses the blocking orbx_tracker_step, one host thread per pipeline")
-    ap.add_argument("--cpu-frames", type=int, default=150, help="stereo frames of the single-thread CPU sample")
+    ap.add_argument("--cpu-frames", type=int, default=200, help="stereo frames of the single-thread CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dry-run", action="store_true",
                     help="CPU-only check of the multi-rank plumbing (gloo): rendezvous, barrier, MAX-over-ranks "
                          "reduction and rank-0 JSON with synthetic per-rank timings; no GPU work")
     args = ap.parse_args()
+    cfg = set_config(args.config)
+    if not args.streams:
+        args.streams = cfg["streams"]
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -291,6 +436,7 @@ def main():
 
     import torch
     import orbx
+    import scenarios as sc
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -323,180 +469,246 @@ def main():
 
     S = args.streams
     B = 2 * S
-    NP = max(1, min(args.pipelines, S))
+    RING = max(1, args.ring) if args.workload == "sec8d" else 1
     cam = orbx.make_camera()
     ctx = orbx.Context(local)
-    imgs = make_streams(S, seed0=100 + 1000 * rank)
-    Tt, Tp = make_poses(S, seed=7 + rank)
-    # NP independent pipelines (extractor + tracker, each on its own CUDA stream) over S/NP streams each: the
-    # latency-bound stages of one pipeline (fp64 pose optimisation, ordered match replay) overlap with the
-    # throughput-bound extraction of the other.  Streams are independent, so this is pure scheduling.
-    def build_pipes(npipes):
-        bounds = [S * k // npipes for k in range(npipes + 1)]
-        out = []
-        for k in range(npipes):
-            s0, s1 = bounds[k], bounds[k + 1]
-            n = s1 - s0
-            ex = orbx.ORBextractor(ctx, NFEAT, 1.2, NLEVELS, 20, 7, max_w=W, max_h=H, max_batch=2 * n)
-            trk = orbx.Tracker(ctx, ex, n, cam, th_frame=7.0, th_map=1.0, nnratio_map=0.8)
-            pin = orbx.host_array((2 * n, H, W), np.uint8)     # page-locked inputs for the e2e arm
-            pin[:] = np.stack(imgs[2 * s0:2 * s1])
-            out.append(dict(
-                n=n, ex=ex, trk=trk, imgs=[pin[i] for i in range(2 * n)], Tt=Tt[s0:s1], Tp=Tp[s0:s1],
-                stream=torch.cuda.ExternalStream(ex.stream, device=local),
-                d_img=torch.from_numpy(np.stack(imgs[2 * s0:2 * s1])).cuda(),
-                d_true=torch.from_numpy(Tt[s0:s1].reshape(n, 16)).cuda(),
-                d_prior=torch.from_numpy(Tp[s0:s1].reshape(n, 16)).cuda(),
-                d_out=torch.zeros((n, 16), dtype=torch.float32, device="cuda"),
-                d_stats=torch.zeros((n, 8), dtype=torch.int32, device="cuda")))
-        return out
-
-    pipes = build_pipes(NP)
+    ex = orbx.ORBextractor(ctx, NFEAT, 1.2, NLEVELS, 20, 7, max_w=W, max_h=H, max_batch=B)
+    trk = orbx.Tracker(ctx, ex, S, cam, th_frame=7.0, th_map=1.0, nnratio_map=0.8)
+    mcap = trk.map_capacity
+    Tt, dT, T_init = make_sequence(S, RING, seed=7 + rank)
+    _, Tp_abs = make_poses(S, seed=7 + rank)
+    sets = []
+    map_gt = None
+    for r in range(RING):
+        imgs = make_streams(S, seed0=100 + 1000 * rank + 37 * r)
+        pin = orbx.host_array((B, H, W), np.uint8)          # page-locked inputs for the e2e arm
+        pin[:] = np.stack(imgs)
+        entry = dict(pin=pin, imgs=[pin[i] for i in range(B)], d_img=torch.from_numpy(pin).cuda(),
+                     Tt=Tt[r], dT=dT[r], d_true=torch.from_numpy(Tt[r].reshape(S, 16)).cuda(),
+                     d_dT=torch.from_numpy(dT[r].reshape(S, 16)).cuda())
+        if args.workload == "sec8d":
+            # the map is built from THIS pipeline's own features (device extraction + device stereo matching, untimed)
+            feats = ex.extract_batch(imgs)
+            frames = []
+            for s in range(S):
+                (_, kL, dL), (_, kR, dR) = feats[2 * s], feats[2 * s + 1]
+                ur, dp = orbx.stereo_match(ctx, ex, 2 * s, ex, 2 * s + 1, kL, dL, kR, dR, cam.bf, cam.b)
+                frames.append((kL, dL, ur, dp))
+            host, gt = build_maps(frames, Tt[r], cfg["n_map"], mcap, 5000 + 100 * r + 100000 * rank)
+            map_gt = gt
+            pm = {}
+            for name, dtp in orbx.abi.TrackMap.FIELDS:      # page-locked copies for the e2e arm, device copies for the resident arm
+                a = orbx.host_array(host[name].shape, dtp)
+                a[...] = host[name]
+                pm[name] = a
+            entry["map_host"] = pm
+            entry["map_dev_t"] = {k: torch.from_numpy(v).cuda() for k, v in pm.items()}
+            entry["map_dev"] = {k: v.data_ptr() for k, v in entry["map_dev_t"].items()}
+        sets.append(entry)
+    d_prior_abs = torch.from_numpy(Tp_abs.reshape(S, 16)).cuda()
+    d_init = torch.from_numpy(T_init.reshape(S, 16).copy()).cuda()
+    d_out = torch.zeros((S, 16), dtype=torch.float32, device="cuda")
+    d_stats = torch.zeros((S, 8), dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    stream = torch.cuda.ExternalStream(ex.stream, device=local)
     torch.cuda.synchronize()
+    step_no = [0]
 
-    def step_device(P):
-        P["trk"].step_device(P["d_img"].data_ptr(), W, H, W, P["d_true"].data_ptr(), P["d_prior"].data_ptr(),
-                             P["d_out"].data_ptr(), P["d_stats"].data_ptr())
+    def step_device():
+        E = sets[step_no[0] % RING]
+        if args.workload == "sec8d":
+            trk.set_map(E["map_dev"])
+            trk.step_device(E["d_img"].data_ptr(), W, H, W, E["d_true"].data_ptr(), E["d_dT"].data_ptr(), d_out.data_ptr(),
+                            d_stats.data_ptr())
+        else:
+            trk.step_device(E["d_img"].data_ptr(), W, H, W, E["d_true"].data_ptr(), d_prior_abs.data_ptr(), d_out.data_ptr(),
+                            d_stats.data_ptr())
+        step_no[0] += 1
 
-    # ---------------- resident arm: inputs already in HBM ----------------
-    for _ in range(args.warmup):
-        for P in pipes:
-            step_device(P)
-    torch.cuda.synchronize()
-    # pass 1 — serial steps (each synchronised, L2 flushed in between) with the C ABI's stage timers on: this is
-    # where the per-kernel durations for the roofline come from (a kernel timed without anything overlapping it)
-    for P in pipes:
-        P["ex"].set_profiling(True)
-        P["trk"].set_profiling(True)
-    ext_sum = np.zeros(len(pipes[0]["ex"].STAGES))
-    trk_sum = np.zeros(len(pipes[0]["trk"].STAGES))
-    main = torch.cuda.current_stream()
-    serial_ms = 0.0
-    for k in range(args.steps):
-        flush.zero_()                      # L2 flush between iterations (not timed)
+    def restart_chain():
+        trk.synchronize()
+        step_no[0] = 0
+        if args.workload == "sec8d":
+            trk.set_chain(True, d_init.data_ptr())
+
+    def timed_region(nsteps, extra_streams=()):
+        """EXACTLY nsteps steps back to back, CUDA-event timed on the launch stream, ending when every stream is done."""
+        main = torch.cuda.current_stream()
+        rstream = torch.cuda.ExternalStream(trk.result_stream, device=local)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
         start = torch.cuda.Event(enable_timing=True)
         start.record(main)
+        stream.wait_event(start)
+        for _ in range(nsteps):
+            step_device()
         ends = []
-        for P in pipes:
-            P["stream"].wait_event(start)
-            step_device(P)
-            e = torch.cuda.Event(enable_timing=True)
-            e.record(P["stream"])
-            ends.append(e)
-        for e in ends:
-            e.synchronize()
-        serial_ms += max(start.elapsed_time(e) for e in ends)
-        for P in pipes:                    # per-stage CUDA-event times, summed over the pipelines
-            ext_sum += P["ex"].stage_ms()[0]
-            trk_sum += P["trk"].stage_ms()
-    for P in pipes:
-        P["ex"].set_profiling(False)
-        P["trk"].set_profiling(False)
-    torch.cuda.synchronize()
-    # pass 2 — the timed region: EXACTLY `steps` steps back to back.  With --overlap (default) the tracker runs
-    # extraction+stereo of step t+1 on one CUDA stream while matching+pose optimisation of step t finish on a
-    # second one (double-buffered); every step re-reads its 2*S images (185 MB at S=256) and rebuilds 1.3 GB of
-    # pyramid, far more than the 126 MB L2, so no explicit flush is needed inside the region.
-    for P in pipes:
-        P["trk"].set_overlap(bool(args.overlap))
-        P["rstream"] = torch.cuda.ExternalStream(P["trk"].result_stream, device=local)
-    for _ in range(2):
-        for P in pipes:
-            step_device(P)
-    for P in pipes:
-        P["trk"].synchronize()
-    launches0 = ctx.launches
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    start = torch.cuda.Event(enable_timing=True)
-    start.record(main)
-    for P in pipes:
-        P["stream"].wait_event(start)
-    for k in range(args.steps):
-        for P in pipes:
-            step_device(P)
-    ends = []
-    for P in pipes:
-        for st in (P["stream"], P["rstream"]):
+        for st in (stream, rstream) + tuple(extra_streams):
             e = torch.cuda.Event(enable_timing=True)
             e.record(st)
             ends.append(e)
-    for e in ends:
-        e.synchronize()
-    dev_ms = max(start.elapsed_time(e) for e in ends)
+        for e in ends:
+            e.synchronize()
+        ms = max(start.elapsed_time(e) for e in ends)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        return ms
+
+    # ---------------- resident arm: inputs already in HBM ----------------
+    restart_chain()
+    for _ in range(args.warmup):
+        step_device()
     torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
+    # pass 1 — serial steps (each synchronised, L2 flushed in between) with the C ABI's stage timers on: this is
+    # where the per-kernel durations for the roofline come from (a kernel timed without anything overlapping it)
+    ex.set_profiling(True)
+    trk.set_profiling(True)
+    ext_sum = np.zeros(len(ex.STAGES))
+    trk_sum = np.zeros(len(trk.STAGES))
+    serial_ms = 0.0
+    main_stream = torch.cuda.current_stream()
+    for k in range(args.steps):
+        flush.zero_()                      # L2 flush between iterations (not timed)
+        start = torch.cuda.Event(enable_timing=True)
+        start.record(main_stream)
+        stream.wait_event(start)
+        step_device()
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        e.synchronize()
+        serial_ms += start.elapsed_time(e)
+        ext_sum += ex.stage_ms()[0]
+        trk_sum += trk.stage_ms()
+    ex.set_profiling(False)
+    trk.set_profiling(False)
+    torch.cuda.synchronize()
+    # pass 2 — the timed region: EXACTLY `steps` steps back to back.  With --overlap (default) the tracker runs
+    # extraction+stereo of step t+1 on one CUDA stream while matching+pose optimisation of step t finish on a
+    # second one (double-buffered); every step re-reads its 2*S images and rebuilds the whole pyramid, far more than the
+    # 126 MB L2, so no explicit flush is needed inside the region.
+    trk.set_overlap(bool(args.overlap))
+    restart_chain()
+    for _ in range(2):
+        step_device()
+    trk.synchronize()
+    launches0 = ctx.launches
+    dev_ms = timed_region(args.steps)
     launches = ctx.launches - launches0
-    stats = np.concatenate([P["d_stats"].cpu().numpy() for P in pipes])
-    Tout = np.concatenate([P["d_out"].cpu().numpy().reshape(-1, 4, 4) for P in pipes])
-    pose_err = float(np.abs(Tout[:, :3, 3] - Tt[:, :3, 3]).max())
-    for P in pipes:
-        P["trk"].set_overlap(False)
+    stats = d_stats.cpu().numpy()
+    Tout = d_out.cpu().numpy().reshape(-1, 4, 4)
+    last_set = sets[(step_no[0] - 1) % RING]
+    pose_err = float(np.abs(Tout[:, :3, 3] - last_set["Tt"][:, :3, 3]).max())
+
+    # ---------------- the same with the keyframe-rate work of every stream beside it (BASELINE config 5) ----------------
+    kf = None
+    kf_ms = 0.0
+    if args.kf_period > 0:
+        kps, desc = sc.synthetic_keypoints(1, NFEAT, W, H)
+        ur = np.where(np.arange(NFEAT) % 2 == 0, kps["x"] - 10.0, -1.0).astype(np.float32)
+        pairs = []
+        for q in range(10):                      # nn = 10 covisible neighbours (src/LocalMapping.cc:506-509)
+            t = sc.tri_scenario(200 + q, kps, desc, ur)
+            pairs.append(dict(KF1=orbx.Frame(t["k1"], t["d1"], t["ur1"], bounds=(0, 0, W, H)), KF2=orbx.Frame(t["k2"], t["d2"], t["ur2"], bounds=(0, 0, W, H)),
+                              has1=t["has1"], has2=t["has2"], fv1=t["fv1"], fv2=t["fv2"], cam1=cam, cam2=cam, R1w=t["R1w"], t1w=t["t1w"],
+                              R2w=t["R2w"], t2w=t["t2w"]))
+        lbas = [sc.lba_scenario(i, K=20, M=3000, n_fixed=3) for i in range(4)]
+        tri_b = orbx.TriangulationBatch(ctx, [pairs[q % 10] for q in range(10 * S)], t["sigma2"], t["scaleFactors"], True)
+        lba_b = orbx.LocalBABatch(ctx, [lbas[p % 4] for p in range(S)], cam)
+        trk.set_keyframe_work(tri_b, lba_b, args.kf_period)
+        restart_chain()
+        for _ in range(args.kf_period):          # warm-up incl. one keyframe round
+            step_device()
+        trk.synchronize()
+        kstream = torch.cuda.ExternalStream(trk.keyframe_stream, device=local)
+        kf_steps = 2 * args.kf_period
+        runs0 = trk.keyframe_runs
+        kf_ms = timed_region(kf_steps, (kstream,))
+        kf = dict(steps=kf_steps, period=args.kf_period, rounds=int(trk.keyframe_runs - runs0),
+                  work_per_round="per stream: 10 x SearchForTriangulation (1000 features) + 1 LocalBundleAdjustment "
+                                 "(20 KF / 3000 MP / %d observations), prepared plans on a third, low-priority stream" % len(lbas[0]["e_kf"]),
+                  lba_pool_GB=lba_b.device_bytes / 1e9)
+        trk.set_keyframe_work(None, None, 0)
+
+    # ---------------- continuity with round 1: the best-case self-map harness, resident ----------------
+    self_ms = None
+    if args.workload == "sec8d":
+        trk.synchronize()
+        trk.set_chain(False)
+        trk.set_map(None)
+        wl = args.workload
+        args.workload = "selfmap"
+        for _ in range(3):
+            step_device()
+        trk.synchronize()
+        self_steps = min(args.steps, 10)
+        self_ms = timed_region(self_steps)
+        self_stats = d_stats.cpu().numpy()
+        args.workload = wl
 
     # ---------------- e2e arm: host buffers through the C ABI ----------------
-    # Every step copies its 2*S images from page-locked host memory to the device and reads its poses + statistics
-    # back, all inside the timed region, through orbx_tracker_submit / orbx_tracker_collect: the H2D of step t+1 runs
-    # on a copy stream under the kernels of step t, and matching + pose optimisation of step t overlap the extraction
-    # of step t+1 (overlap mode), so two steps are in flight per pipeline.  --e2e-sync 1 uses the blocking
-    # orbx_tracker_step from one host thread per pipeline instead.
-    from concurrent.futures import ThreadPoolExecutor
+    # Every step copies its 2*S images AND its flattened local map from page-locked host memory to the device and reads
+    # its poses + statistics back, all inside the timed region, through orbx_tracker_upload_map + orbx_tracker_submit /
+    # orbx_tracker_collect: the H2D of step t+1 runs on a copy stream under the kernels of step t, and matching + pose
+    # optimisation of step t overlap the extraction of step t+1, so two steps are in flight.
     e2e_steps = max(3, min(args.steps, 10))
-    NPE = max(1, min(args.e2e_pipelines, S))
-    res_pipes = pipes
-    if NPE != NP:
-        pipes = build_pipes(NPE)
-    for P in pipes:
-        P["prep"] = orbx.prepare_images(P["imgs"])
+    e2e_ms, e2e_same = 0.0, None
+    if not args.no_e2e:
+        trk.set_overlap(True)
+        for E in sets:
+            E["prep"] = orbx.prepare_images(E["imgs"])
+        eno = [0]
 
-    if args.e2e_sync:
-        def e2e_step(P):
-            return P["trk"].step(P["imgs"], P["Tt"], P["Tp"])
+        def e2e_submit():
+            E = sets[eno[0] % RING]
+            if args.workload == "sec8d":
+                trk.upload_map(E["map_host"])
+                trk.submit(E["prep"], E["Tt"], E["dT"])
+            else:
+                trk.submit(E["prep"], E["Tt"], Tp_abs)
+            eno[0] += 1
 
-        with ThreadPoolExecutor(NPE) as pool:
-            for _ in range(2):
-                list(pool.map(e2e_step, pipes))
-            if dist:
-                dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                list(pool.map(e2e_step, pipes))
-            torch.cuda.synchronize()
-            e2e_s = time.perf_counter() - t0
-    e2e_same = None
-    if not args.e2e_sync:
         def e2e_run(nsteps):
             last = None
-            for P in pipes:
-                P["trk"].submit(P["prep"], P["Tt"], P["Tp"])
+            e2e_submit()
             for _ in range(nsteps - 1):
-                for P in pipes:
-                    P["trk"].submit(P["prep"], P["Tt"], P["Tp"])
-                    last = P["trk"].collect()
-            for P in pipes:
-                last = P["trk"].collect()
-            return last
+                e2e_submit()
+                last = trk.collect()
+            return trk.collect() if nsteps else last
 
-        e2e_run(3)
+        trk.synchronize()
+        if args.workload == "sec8d":
+            trk.set_chain(True, d_init.data_ptr())
+        e2e_run(RING)
+        trk.synchronize()
+        if args.workload == "sec8d":
+            trk.set_chain(True, d_init.data_ptr())
+        eno[0] = 0
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         e2e_last = e2e_run(e2e_steps)
         torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        e2e_same = bool(NPE == NP and np.array_equal(e2e_last[1], stats[-pipes[-1]["n"]:]))   # same statistics as the resident arm
-    h2d = B * W * H + 2 * S * 64
+        e2e_ms = 1e3 * (time.perf_counter() - t0)
+        # same inputs as resident step number e2e_steps of a fresh chain -> compare against a resident replay
+        trk.synchronize()
+        restart_chain()
+        for _ in range(e2e_steps):
+            step_device()
+        trk.synchronize()
+        e2e_same = bool(np.array_equal(e2e_last[1], d_stats.cpu().numpy()))
+    map_bytes = trk.map_bytes if args.workload == "sec8d" else 0
+    h2d = B * W * H + 2 * S * 64 + map_bytes
     d2h = S * 64 + S * 8 * 4
     clocks = sampler.stop() if rank == 0 else None
-    ex, trk = res_pipes[0]["ex"], res_pipes[0]["trk"]
 
     # ---------------- reduce over ranks (max time) ----------------
-    dev_ms, e2e_s, value, e2e_value = reduce_over_ranks(dist, dev_ms, e2e_s, S, args.steps, e2e_steps, world,
-                                                        device="cuda")
+    dev_ms, kf_ms, e2e_ms, self_ms_r = reduce_over_ranks(dist, [dev_ms, kf_ms, e2e_ms, self_ms or 0.0], device="cuda")
+    frames = S * world
+    value = frames * args.steps / (dev_ms / 1e3)
+    e2e_value = frames * e2e_steps / (e2e_ms / 1e3) if e2e_ms > 0 else None
 
     if rank != 0:
         if dist:
@@ -519,51 +731,67 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     short = dom_name.split(".")[-1]
     if dom_name.startswith("extract."):
-        n_launch = ((NLEVELS - 1) if short == "pyramid" else 1) * NP
+        n_launch = (NLEVELS - 1) if short == "pyramid" else 1
         dom_bytes = alg[short] * B
     else:   # matcher / optimiser stages: bytes of the arrays the stage must touch once
-        n_launch = 2 * NP
+        n_launch = 2
         dom_bytes = int(S * kp_mean * (32 + 24 + 16) * 2)
     achieved = dom_bytes / (kernel_ms[dom_name] * 1e-3) / 1e9 if kernel_ms[dom_name] > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.config == "c2":
         try:
             traffic = json.load(open(tp)).get(short)
         except Exception:
             traffic = None
     ext_total_ms = float(ext_ms.sum())
+    per_stage = {}
+    for n in ex.STAGES:
+        if alg.get(n, 0) > 0 and kernel_ms["extract." + n] > 0:
+            gbs = alg[n] * B / (kernel_ms["extract." + n] * 1e-3) / 1e9
+            per_stage[n] = {"ms": kernel_ms["extract." + n], "GB/s": gbs, "frac": gbs / peak}
     roof = {"bound": "hbm", "kernel": dom_name, "launches_per_step": n_launch, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
             "algorithmic_bytes_per_launch": dom_bytes // n_launch, "stage_ms": kernel_ms,
-            "stage_ms_note": "CUDA-event time per stage summed over the %d concurrent pipelines "
-                             "(overlap inflates a stage's wall time; the sum exceeds ms_per_step)" % NP,
+            "stage_ms_note": "CUDA-event time per stage in the serial, L2-flushed pass (nothing overlapping the kernel)",
+            "extractor_stages": per_stage,
             "extractor_total": {"achieved": alg["total"] * B / (ext_total_ms * 1e-3) / 1e9,
                                 "frac": alg["total"] * B / (ext_total_ms * 1e-3) / 1e9 / peak,
                                 "bytes_per_image": alg["total"], "ms": ext_total_ms}}
 
     cpu = None
-    if not args.no_cpu:
-        fps, dt = cpu_oracle_frames_per_s(args.cpu_frames, 1)
-        cpu = {"value": fps, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "%d stereo frames of the same chain, %.1f s, 1 thread (host has %d cores)"
-                         % (args.cpu_frames, dt, os.cpu_count() or 0)}
+    if not args.no_cpu and world == 1 and args.config == "c2":
+        cpu = cpu_baseline(args.cpu_frames)
 
+    mean_stats = {n: float(v) for n, v in zip(trk.STATS, stats.mean(0))}
+    mean_stats["outliers_1"] = mean_stats["matches_frame"] - mean_stats["inliers_1"]
+    cfg_out = {"workload": WORKLOAD, "config": args.config, "streams_per_gpu": S, "images_per_step_per_gpu": B,
+               "parallelism": "replicas x%d" % world,
+               "l2": "inputs larger than L2: each step streams 2*S fresh images (%d MB) and rebuilds %d MB of pyramid; a ring of %d "
+                     "different image sets" % (B * W * H >> 20, int(B * sum(w * h for w, h in level_sizes()) * 2) >> 20, RING),
+               "overlap_steps": bool(args.overlap), "ms_per_step_serial_flushed": serial_ms / args.steps,
+               "mean_per_stream": mean_stats, "max_translation_error_m": pose_err}
+    if args.workload == "sec8d":
+        cfg_out["map"] = MAP_NOTE
+        cfg_out["map_generator"] = map_gt
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "streams_per_gpu": S, "images_per_step_per_gpu": B,
-                      "pipelines_per_gpu": {"resident": NP, "e2e": NPE},
-                      "parallelism": "replicas x%d" % world,
-                      "l2": "inputs larger than L2: each step streams 2*S fresh images + 1.3 GB of pyramid (S=256)",
-                      "overlap_steps": bool(args.overlap), "ms_per_step_serial_flushed": serial_ms / args.steps,
-                      "mean_per_stream": {n: float(v) for n, v in zip(trk.STATS, stats.mean(0))},
-                      "max_translation_error_m": pose_err},
+           "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic", "config": cfg_out,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "steps": e2e_steps, "api": "orbx_tracker_step" if args.e2e_sync else "orbx_tracker_submit/collect",
+                   "steps": e2e_steps, "api": "orbx_tracker_upload_map + orbx_tracker_submit/collect",
                    "results_equal_resident_arm": e2e_same},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    if kf:
+        kf["value"] = frames * kf["steps"] / (kf_ms / 1e3)
+        kf["unit"] = UNIT
+        kf["ms_per_step"] = kf_ms / kf["steps"]
+        out["with_keyframe_step"] = kf
+    if self_ms:
+        out["selfmap_round1_workload"] = {"value": frames * min(args.steps, 10) / (self_ms_r / 1e3), "unit": UNIT,
+                                          "ms_per_step": self_ms_r / min(args.steps, 10),
+                                          "mean_per_stream": {n: float(v) for n, v in zip(trk.STATS, self_stats.mean(0))},
+                                          "note": "round-1 harness (map = the frame's own stereo points and descriptors), kept for continuity"}
     print(json.dumps(out))
     if dist:
         dist.destroy_process_group()

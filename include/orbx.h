@@ -383,6 +383,55 @@ int orbx_local_ba(orbx_ctx *ctx, int n_kf, float *kf_Tcw, const uint8_t *kf_fixe
                   double lambda_init, const volatile uint8_t *stop_flag, uint8_t *edge_bad,
                   int32_t *iters, int32_t *status);
 
+/* ---- keyframe-rate half of the batched many-stream mode (BASELINE.json config 5: "full track+LocalBA") ----
+ * LocalMapping::Run (src/LocalMapping.cc:128) processes every new keyframe with CreateNewMapPoints (:501-628: one
+ * ORBmatcher::SearchForTriangulation per covisible neighbour, nn = 10 for stereo) and Optimizer::LocalBundleAdjustment
+ * (:201).  One camera stream yields one such step per keyframe; S independent streams yield S of them, which these two
+ * PREPARED PLANS run in one launch sequence each: prepare() uploads the problems once into one device pool, run() only
+ * enqueues on a CUDA stream (cuda_stream = NULL: the context's) and may be repeated (every run restarts from the
+ * inputs given to prepare), fetch() waits for the last run and copies the results into the problem structs.
+ * Per-problem results are bit-identical to the single-call entry points (tests/test_keyframe_gpu.py). */
+typedef struct orbx_tri_problem { /* one orbx_search_for_triangulation call; host pointers, same meaning */
+  const orbx_frame_desc *kf1, *kf2;
+  const uint8_t *has_mp1, *has_mp2;
+  int32_t nn1;
+  const int32_t *fv1_node, *fv1_off, *fv1_idx;
+  int32_t nn2;
+  const int32_t *fv2_node, *fv2_off, *fv2_idx;
+  const orbx_camera *cam1, *cam2;
+  const float *R1w, *t1w, *R2w, *t2w;
+  int32_t only_stereo, coarse;
+  int32_t *match12; /* out [kf1->n], may be NULL */
+  int32_t nmatches; /* out */
+} orbx_tri_problem;
+typedef struct orbx_tri_batch orbx_tri_batch;
+orbx_tri_batch *orbx_tri_batch_prepare(orbx_ctx *ctx, int n_problems, const orbx_tri_problem *problems,
+                                       const float *level_sigma2, const float *scale_factors, int nlevels,
+                                       int check_orientation);
+int orbx_tri_batch_run(orbx_tri_batch *batch, void *cuda_stream);
+int orbx_tri_batch_fetch(orbx_tri_batch *batch, orbx_tri_problem *problems);
+void orbx_tri_batch_destroy(orbx_tri_batch *batch);
+
+typedef struct orbx_lba_problem { /* one orbx_local_ba call; host pointers, same meaning */
+  int32_t n_kf, n_mp, n_edges;
+  float *kf_Tcw; /* in (prepare) / out (fetch) [n_kf][16] */
+  const uint8_t *kf_fixed;
+  float *mp_xyz; /* in / out [n_mp][3] */
+  const int32_t *e_kf, *e_mp;
+  const float *e_obs, *e_inv_sigma2;
+  double lambda_init;
+  uint8_t *edge_bad; /* out [n_edges], may be NULL */
+  int32_t iters[2];  /* out */
+  int32_t status;    /* out: 0 done, 2 rejected (>= 50 % bad: poses / points left as given) */
+} orbx_lba_problem;
+typedef struct orbx_lba_batch orbx_lba_batch;
+orbx_lba_batch *orbx_lba_batch_prepare(orbx_ctx *ctx, int n_problems, const orbx_lba_problem *problems,
+                                       const orbx_camera *cam);
+int orbx_lba_batch_run(orbx_lba_batch *batch, void *cuda_stream);
+int orbx_lba_batch_fetch(orbx_lba_batch *batch, orbx_lba_problem *problems);
+void orbx_lba_batch_destroy(orbx_lba_batch *batch);
+size_t orbx_lba_batch_device_bytes(const orbx_lba_batch *batch);
+
 /* Optimizer::PoseInertialOptimizationLastKeyFrame(Frame*, bool bRecInit) (src/Optimizer.cc:7665-8066;
  * vertices/edges: include/G2oTypes.h:387-491, src/G2oTypes.cc:170-220,385-407,496-520,730-812) — the
  * visual-inertial replacement of PoseOptimization that Tracking::TrackLocalMap calls when the map was
@@ -494,6 +543,47 @@ int orbx_tracker_collect(orbx_tracker *trk, float *Tcw_out, int32_t *stats);
 int orbx_tracker_set_overlap(orbx_tracker *trk, int enable);
 void *orbx_tracker_result_stream(orbx_tracker *trk);
 int orbx_tracker_synchronize(orbx_tracker *trk);
+/* The local map of every stream for the NEXT step(s), as flat DEVICE arrays with stride m_cap = orbx_tracker_map_capacity()
+ * (>= 2048): what the shim would flatten from Tracking::mvpLocalMapPoints and mLastFrame (SURVEY.md §8(d) workload).
+ * With a map set, SearchByProjection(Cur, Last) runs over the entries flagged in last_flags, TrackLocalMap's
+ * SearchLocalPoints runs the full Frame::isInFrustum(pMP, 0.5) test (distance-invariance range, viewing angle,
+ * MapPoint::PredictScale) over the entries flagged in map_flags that are not matched yet, and PoseOptimization's edges
+ * take xw from here.  The arrays must stay valid until the steps using them have finished; every valid entry must have
+ * bit1 (Observations() > 0) set.  NULL returns to the self-map harness of round 1. */
+#define ORBX_TRACK_MAP_CAP 2048
+typedef struct orbx_track_map {
+  int32_t m_cap;
+  const int32_t *n_map;       /* [S] */
+  const float *xw;            /* [S][m_cap][3] GetWorldPos() */
+  const uint8_t *desc;        /* [S][m_cap][32] GetDescriptor() */
+  const uint8_t *last_flags;  /* [S][m_cap] bit0: mLastFrame.mvpMapPoints holds it && !mvbOutlier, bit1: Observations() > 0 */
+  const int32_t *last_octave; /* [S][m_cap] octave / angle of the last frame's keypoint that observed it */
+  const float *last_angle;
+  const uint8_t *map_flags;   /* [S][m_cap] bit0: in mvpLocalMapPoints && !isBad(), bit1: Observations() > 0 */
+  const float *max_dist, *min_dist; /* [S][m_cap] mfMaxDistance / mfMinDistance */
+  const float *normal;        /* [S][m_cap][3] GetNormal() */
+  float log_scale_factor;     /* Frame::mfLogScaleFactor; <= 0: log of the extractor's scale factor */
+} orbx_track_map;
+int orbx_tracker_map_capacity(const orbx_tracker *trk);
+int orbx_tracker_set_map(orbx_tracker *trk, const orbx_track_map *map);
+/* The same from HOST arrays, for the host-buffer entry points (orbx_tracker_step / _submit): call it right before the
+ * step it belongs to; the arrays are copied into the tracker's own device buffer of that step's slot (page-locked
+ * caller memory is DMA'd directly; with the asynchronous pipeline the copy runs on the copy stream under the previous
+ * step's kernels).  orbx_tracker_map_bytes() = bytes copied per call. */
+int orbx_tracker_upload_map(orbx_tracker *trk, const orbx_track_map *host_map);
+size_t orbx_tracker_map_bytes(const orbx_tracker *trk);
+/* Motion-model chaining (Tracking::TrackWithMotionModel, src/Tracking.cc:2354: SetPose(mVelocity * mLastFrame.mTcw)):
+ * when enabled, the Tcw_prior argument of the step functions is the RELATIVE motion dT (last -> current, [S][16]) and
+ * the prior used is dT * (pose the previous step produced), composed on the device; d_Tcw_init [S][16] (device) is
+ * the pose before the first chained step. */
+int orbx_tracker_set_chain(orbx_tracker *trk, int enable, const float *d_Tcw_init);
+/* Keyframe-rate work of the S streams (LocalMapping's share, which the reference runs in its own thread beside
+ * Tracking, src/LocalMapping.cc:68-200): every `period`-th step the two prepared plans — the CreateNewMapPoints
+ * searches (10 SearchForTriangulation calls per stream) and one LocalBundleAdjustment per stream — are enqueued on a
+ * third CUDA stream of the lowest priority.  orbx_tracker_synchronize() waits for it as well.  NULL plans detach. */
+int orbx_tracker_set_keyframe_work(orbx_tracker *trk, orbx_tri_batch *tri, orbx_lba_batch *lba, int period);
+void *orbx_tracker_keyframe_stream(orbx_tracker *trk);
+long long orbx_tracker_keyframe_runs(const orbx_tracker *trk);
 /* Per-stage device time of the last step (CUDA events on the stream), ORBX_TRACK_STAGES entries:
  * 0 extract, 1 stereo match, 2 search-by-projection (last frame), 3 pose optimisation #1,
  * 4 search-by-projection (local map), 5 pose optimisation #2. */

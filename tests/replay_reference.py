@@ -80,3 +80,61 @@ def track_frame(ork, cam, L, R, Tcw_true, Tcw_prior, th_frame=7.0, th_map=1.0, n
     T2, out2, nin2, it2 = ork.pose_optimization(exw2, eobs2, eisg2, cam, T1)
     stats = np.array([n, len(kR), int((ur >= 0).sum()), nm1, nin1, nm2, nin2, int(it1.sum() + it2.sum())], np.int32)
     return T2, stats
+
+
+def track_frame_map(ork, cam, L, R, mp, Tcw_prior, th_frame=7.0, th_map=1.0, nn_map=0.8, nfeatures=1000, extractors=None,
+                    log_sf=None):
+    """The chain of orbx_tracker_step with a GIVEN map (orbx_tracker_set_map; mp = one stream's arrays as produced by
+    scenarios.track_map_scenario), composed from the oracle's functions: extract L+R, ComputeStereoMatches,
+    SearchByProjection(Cur, Last) over the last-frame entries, PoseOptimization, outliers dropped, isInFrustum over the
+    unmatched local map, SearchByProjection(F, local map), PoseOptimization."""
+    from orbx import abi
+    exL, exR = extractors if extractors else (ork.Extractor(nfeatures), ork.Extractor(nfeatures))
+    _, kL, dL, _ = exL(L)
+    _, kR, dR, _ = exR(R)
+    scale, inv_scale, isg = exL.scale, exL.inv_scale, exL.inv_sigma2
+    pyrL = [exL.pyramid_level(l) for l in range(exL.nlevels)]
+    pyrR = [exR.pyramid_level(l) for l in range(exR.nlevels)]
+    ur, dp = ork.stereo_match(pyrL, pyrR, kL, dL, kR, dR, scale, inv_scale, float(F32(cam.bf)), float(F32(cam.b)))
+    n, M = len(kL), int(mp["n_map"])
+    H, W = L.shape
+    Fr = abi.Frame(kL, dL, ur, bounds=(0, 0, W, H))
+    xw = mp["xw"][:M]
+    Tp = np.asarray(Tcw_prior, F32).reshape(4, 4)
+    # (the device harness fixes the octave-window mode to "neither forward nor backward", i.e. |tlc.z| <= mb: the last
+    #  frame's pose is taken equal to the prior here, so tlc = 0)
+    nm1, match, kept, cur = ork.search_by_projection_frame(Fr, None, cam, Tp, Tp, mp["last_flags"][:M], xw,
+                                                           mp["last_octave"][:M], mp["last_angle"][:M], mp["desc"][:M], th_frame,
+                                                           False, True, scale)
+
+    def edges(assign):
+        idx = np.flatnonzero(assign >= 0)
+        q = assign[idx]
+        obs = np.stack([kL["x"][idx], kL["y"][idx], ur[idx]], 1).astype(F32)
+        return idx, xw[q], obs, isg[kL["octave"][idx]].astype(F32)
+
+    idx1, exw, eobs, eisg = edges(cur)
+    T1, out1, nin1, it1 = ork.pose_optimization(exw, eobs, eisg, cam, Tp)
+    cur2 = cur.copy()
+    cur2[idx1[out1 == 1]] = -1
+    blocked = (cur2 >= 0).astype(np.uint8)
+    taken = np.zeros(M, bool)
+    taken[cur2[cur2 >= 0]] = True
+    # Ow = -Rcw^T tcw in the kernel's fp32 expression order
+    Ow = np.array([-(T1[0, i] * T1[0, 3] + T1[1, i] * T1[1, 3] + T1[2, i] * T1[2, 3]) for i in range(3)], F32)
+    if log_sf is None:
+        log_sf = float(F32(np.log(np.float64(scale[1]))))
+    fr = ork.is_in_frustum(cam, T1[:3, :3], T1[:3, 3], Ow, (0.0, float(W), 0.0, float(H)), 0.5, exL.nlevels, log_sf, xw,
+                           mp["max_dist"][:M], mp["min_dist"][:M], mp["normal"][:M])
+    vis = (fr["in_view"][:M] > 0) & ((mp["map_flags"][:M] & 1) > 0) & ~taken
+    mflags = np.where(vis, 1 | (mp["map_flags"][:M] & 2), 0).astype(np.uint8)
+    nm2, best = ork.search_by_projection_map(Fr, blocked, fr["proj_x"][:M], fr["proj_y"][:M], fr["proj_xr"][:M], fr["level"][:M],
+                                             fr["view_cos"][:M], mp["desc"][:M], mflags, th_map, nn_map, scale)
+    kpmp = cur2.copy()
+    for q in range(M):
+        if best[q] >= 0:
+            kpmp[best[q]] = q
+    idx2, exw2, eobs2, eisg2 = edges(kpmp)
+    T2, out2, nin2, it2 = ork.pose_optimization(exw2, eobs2, eisg2, cam, T1)
+    stats = np.array([n, len(kR), int((ur >= 0).sum()), nm1, nin1, nm2, nin2, int(it1.sum() + it2.sum())], np.int32)
+    return T2, stats

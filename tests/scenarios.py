@@ -450,3 +450,92 @@ def inertial_lf_scenario(seed, E=300, stereo_frac=0.6, outlier_frac=0.1, dt=0.05
              prior_state=prev.copy(), prior_H=Hp)
     del s["kf"]
     return s
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The local map of one stream for the many-stream tracker (orbx_track_map; SURVEY.md §8(d) workload): what Tracking
+# would hold when the frame with keypoints (kps, desc, uright, depth) arrives at the true pose Tcw_true.
+#   * "true" MapPoints: every keypoint, back-projected at its stereo depth (monocular keypoints get a random depth) from
+#     a pixel position jittered by N(0, noise_px * scale[octave]); descriptor = the keypoint's with 0..flip_max random
+#     bit flips; `outlier_frac` of them are GROSS outliers (displaced by 3..6 px * scale[octave], still inside the search
+#     windows, so they are matched by descriptor and PoseOptimization has to reject them);
+#   * distractors up to n_map points: genuine ORB descriptors from the reference's vocabulary at random positions;
+#   * ~60 % of the true points (and 30 % of the distractors) were tracked by the last frame;
+#   * mfMaxDistance / mfMinDistance / normal as MapPoint::UpdateNormalAndDepth (src/MapPoint.cc:496-560) leaves them,
+#     seen from a reference keyframe near the true pose (the max distance is spread by +-12 % so that PredictScale does
+#     not sit on an integer).
+# Returned arrays are padded to m_cap; "gt" carries generator-side truth for assertions.
+# ------------------------------------------------------------------------------------------------------------------
+def track_map_scenario(seed, kps, desc, uright, depth, Tcw_true, m_cap=2048, n_map=1500, noise_px=0.6, outlier_frac=0.2,
+                       flip_max=40, W=752, H=480):
+    rng = np.random.default_rng(seed)
+    voc = orbvoc()
+    n = min(len(kps), n_map)
+    nd = n_map - n
+    scale = (np.float32(1.2) ** np.arange(8)).astype(np.float64)
+    T = np.asarray(Tcw_true, np.float64).reshape(4, 4)
+    R, t = T[:3, :3], T[:3, 3]
+    Ow = -R.T @ t
+    ref_center = Ow + rng.normal(0, 0.05, 3)
+    # ---- true points (vectorised over the n keypoints) ----
+    o = np.asarray(kps["octave"][:n], np.int64)
+    z = rng.uniform(1.0, 15.0, n)
+    if depth is not None:
+        d = np.asarray(depth[:n], np.float64)
+        z = np.where(d > 0, d, z)
+    is_out = rng.random(n) < outlier_frac
+    r, a = rng.uniform(3.0, 6.0, n) * scale[o], rng.uniform(0, 2 * np.pi, n)
+    nx, ny = rng.normal(0, 1, n) * noise_px * scale[o], rng.normal(0, 1, n) * noise_px * scale[o]
+    px = kps["x"][:n].astype(np.float64) + np.where(is_out, r * np.cos(a), nx)
+    py = kps["y"][:n].astype(np.float64) + np.where(is_out, r * np.sin(a), ny)
+    Pc = np.stack([(px - CX) * z / FX, (py - CY) * z / FY, z], 1)
+    # each bit flips independently with probability k/256, k ~ U{0..flip_max}: the flip count is Binomial with mean k
+    k = rng.integers(0, flip_max + 1, n)
+    flips = rng.random((n, 256)) < (k[:, None] / 256.0)
+    tdesc = np.packbits(np.unpackbits(np.ascontiguousarray(desc[:n]), axis=1) ^ flips.astype(np.uint8), axis=1)
+    tang = kps["angle"][:n].astype(np.float64) + rng.normal(0, 2.0, n)
+    tlast = rng.random(n) < 0.6
+    # ---- distractors ----
+    zd = rng.uniform(1.0, 15.0, nd)
+    Pd = np.stack([(rng.uniform(0, W, nd) - CX) * zd / FX, (rng.uniform(0, H, nd) - CY) * zd / FY, zd], 1)
+    od = rng.integers(0, 8, nd)
+    ddesc = voc[rng.integers(0, len(voc), nd)]
+    dang = rng.uniform(0, 360, nd)
+    dlast = rng.random(nd) < 0.3
+    # ---- assemble, padded to m_cap ----
+    Pw = (np.concatenate([Pc, Pd]) - t) @ R                       # R^T (Pc - t), row-wise
+    octv = np.concatenate([o, od])
+    dist = np.linalg.norm(Pw - Ow, axis=1)
+    md = dist * scale[octv] * rng.uniform(0.88, 1.12, n_map)
+    v = Pw - ref_center
+    xw = np.zeros((m_cap, 3), np.float32)
+    xw[:n_map] = Pw
+    mdesc = np.zeros((m_cap, 32), np.uint8)
+    mdesc[:n] = tdesc
+    mdesc[n:n_map] = ddesc
+    last_flags, map_flags = np.zeros(m_cap, np.uint8), np.zeros(m_cap, np.uint8)
+    map_flags[:n_map] = 3
+    last_flags[:n_map] = np.where(np.concatenate([tlast, dlast]), 3, 0)
+    last_octave, last_angle = np.zeros(m_cap, np.int32), np.zeros(m_cap, np.float32)
+    last_octave[:n_map] = octv
+    last_angle[:n_map] = np.concatenate([tang, dang])
+    maxd, mind = np.ones(m_cap, np.float32), np.ones(m_cap, np.float32)
+    maxd[:n_map] = md
+    mind[:n_map] = md / scale[7]
+    normal = np.zeros((m_cap, 3), np.float32)
+    normal[:, 2] = 1
+    normal[:n_map] = v / np.linalg.norm(v, axis=1, keepdims=True)
+    is_outlier = np.zeros(m_cap, bool)
+    is_outlier[:n] = is_out
+    return dict(n_map=np.int32(n_map), xw=xw, desc=mdesc, last_flags=last_flags, last_octave=last_octave, last_angle=last_angle,
+                map_flags=map_flags, max_dist=maxd, min_dist=mind, normal=normal,
+                gt=dict(n_true=n, is_outlier=is_outlier, mean_flips=float(flips.sum(1).mean()) if n else 0.0))
+
+
+def stack_track_maps(maps):
+    """list of per-stream track_map_scenario dicts -> the [S, m_cap, ...] host arrays of orbx_track_map"""
+    out = {}
+    for k in ("xw", "desc", "last_flags", "last_octave", "last_angle", "map_flags", "max_dist", "min_dist", "normal"):
+        out[k] = np.ascontiguousarray(np.stack([m[k] for m in maps]))
+    out["n_map"] = np.array([m["n_map"] for m in maps], np.int32)
+    return out

@@ -122,3 +122,120 @@ def test_tracker_submit_collect_matches_step(ctx):
     assert np.array_equal(out, ref[2][0]) and np.array_equal(st, ref[2][1])
     trk.close()
     ex.close()
+
+
+def _map_setup(ork, S, seed0):
+    """S stereo pairs, their true poses / priors and the §8(d) map of every stream (generated from the oracle's features)."""
+    from orbx import synth
+    rng = np.random.default_rng(seed0)
+    imgs, maps = [], []
+    Tt, Tp = _poses(rng, S)
+    for s in range(S):
+        L, R = synth.stereo_pair(seed0 + s)
+        imgs += [L, R]
+        exL, kL, dL = sc.extract_frame(ork, L)
+        exR, kR, dR = sc.extract_frame(ork, R)
+        ur, dp = ork.stereo_match([exL.pyramid_level(l) for l in range(8)], [exR.pyramid_level(l) for l in range(8)], kL, dL, kR, dR,
+                                  exL.scale, exL.inv_scale, sc.BF, sc.BF / sc.FX)
+        maps.append(sc.track_map_scenario(seed0 + 100 + s, kL, dL, ur, dp, Tt[s]))
+    return imgs, Tt, Tp, maps
+
+
+def test_tracker_given_map_matches_oracle_chain(ctx, ork):
+    """§8(d) workload: bit-flipped descriptors, distractors, pixel noise, 20 % gross outliers, full isInFrustum test."""
+    import orbx
+    from replay_reference import track_frame_map
+    S = 2
+    cam = orbx.make_camera()
+    imgs, Tt, Tp, maps = _map_setup(ork, S, 140)
+    ex = orbx.ORBextractor(ctx, max_batch=2 * S)
+    trk = orbx.Tracker(ctx, ex, S, cam)
+    assert trk.map_capacity == 2048
+    host = sc.stack_track_maps(maps)
+    for rep in range(2):
+        trk.upload_map(host)
+        Tout, stats = trk.step(imgs, Tt, Tp)
+        for s in range(S):
+            T2, st = track_frame_map(ork, cam, imgs[2 * s], imgs[2 * s + 1], maps[s], Tp[s])
+            assert np.array_equal(stats[s], st), (s, stats[s], st)
+            assert np.abs(Tout[s] - T2).max() < 2e-6, (s, np.abs(Tout[s] - T2).max())
+            # the workload is not a best case any more: outliers are found, and the pose still comes back
+            assert st[3] - st[4] > 20 and st[5] > 50, st           # PoseOptimization #1 rejected the gross outliers
+            assert np.abs(Tout[s][:3, 3] - Tt[s][:3, 3]).max() < 2e-2
+    # back to the self-map harness: identical to a tracker that never saw a map
+    trk.set_map(None)
+    a = trk.step(imgs, Tt, Tp)
+    trk2 = orbx.Tracker(ctx, ex, S, cam)
+    b = trk2.step(imgs, Tt, Tp)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    trk.close()
+    trk2.close()
+    ex.close()
+
+
+def test_tracker_chain_mode_composes_the_prior_on_the_device(ctx, ork):
+    """Motion-model chaining: step t+1 starts from dT * (pose step t produced).  Equal to feeding that product from the host."""
+    import orbx
+    import torch
+    S = 2
+    cam = orbx.make_camera()
+    imgs, Tt, Tp, maps = _map_setup(ork, S, 150)
+    host = sc.stack_track_maps(maps)
+    ex = orbx.ORBextractor(ctx, max_batch=2 * S)
+    trk = orbx.Tracker(ctx, ex, S, cam)
+    trk.upload_map(host)
+    T1, st1 = trk.step(imgs, Tt, Tp)                               # step 1 (absolute prior)
+    rng = np.random.default_rng(3)
+    dT = np.stack([sc.se3_matrix(sc.rot_small(rng, 0.2), rng.normal(0, 0.004, 3)).astype(np.float32) for _ in range(S)])
+    # host-side product in the kernel's order: ((a0*b0 + a1*b1) + a2*b2) + a3*b3, fp32
+    prior = np.zeros((S, 4, 4), np.float32)
+    for s in range(S):
+        for i in range(4):
+            for j in range(4):
+                acc = np.float32(dT[s, i, 0] * T1[s, 0, j])
+                for k in range(1, 4):
+                    acc = np.float32(acc + np.float32(dT[s, i, k] * T1[s, k, j]))
+                prior[s, i, j] = acc
+    trk.upload_map(host)
+    want = trk.step(imgs, Tt, prior)                               # step 2 with the prior composed on the host
+    d_init = torch.from_numpy(T1.reshape(S, 16).copy()).cuda()
+    trk.set_chain(True, d_init.data_ptr())
+    trk.upload_map(host)
+    got = trk.step(imgs, Tt, dT)                                   # the same, composed on the device
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    trk.upload_map(host)
+    third = trk.step(imgs, Tt, np.stack([np.eye(4, dtype=np.float32)] * S))   # dT = I: starts from step 2's output
+    assert np.abs(third[0] - got[0]).max() < 1e-3 and third[1][0][6] > 100
+    trk.set_chain(False)
+    trk.close()
+    ex.close()
+
+
+def test_tracker_keyframe_work_runs_beside_the_frame_chain(ctx, ork):
+    """The keyframe-rate plans attached to a tracker run every `period`-th step on their own stream: same per-frame
+    results as without them, and the plans' results are those of a stand-alone run."""
+    import orbx
+    S = 2
+    cam = orbx.make_camera()
+    imgs, Tt, Tp, maps = _map_setup(ork, S, 160)
+    ex = orbx.ORBextractor(ctx, max_batch=2 * S)
+    trk = orbx.Tracker(ctx, ex, S, cam)
+    ref = trk.step(imgs, Tt, Tp)
+    scen = [sc.lba_scenario(70 + i, K=6, M=300, n_fixed=2) for i in range(S)]
+    lba = orbx.LocalBABatch(ctx, scen, cam)
+    lba.run()
+    alone = lba.fetch()
+    trk.set_overlap(True)
+    trk.set_keyframe_work(None, lba, 2)
+    outs = [trk.step(imgs, Tt, Tp) for _ in range(5)]
+    trk.synchronize()
+    assert trk.keyframe_runs == 3          # the tracker had done 1 step before: steps 2, 4 and 6 carry keyframe work
+    for o in outs:
+        assert np.array_equal(o[0], ref[0]) and np.array_equal(o[1], ref[1])
+    beside = lba.fetch()
+    for q in range(S):
+        assert np.array_equal(beside[q][0], alone[q][0]) and np.array_equal(beside[q][3], alone[q][3])
+    trk.set_keyframe_work(None, None, 0)
+    trk.close()
+    lba.close()
+    ex.close()
