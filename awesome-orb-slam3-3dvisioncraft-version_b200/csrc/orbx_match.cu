@@ -1227,6 +1227,7 @@ int orbx_search_for_triangulation(orbx_ctx* ctx, const orbx_frame_desc* kf1, con
 // ------------------------------------------------------------------------------------------------------------------
 struct orbx_tri_batch {
   orbx_ctx* ctx = nullptr;
+  int device = 0;               // kept separately: destroy() must not dereference a context that may be gone already
   int Q = 0, maxTot1 = 0;
   uint8_t* pool = nullptr;
   FrameDev* dFrames = nullptr;
@@ -1282,7 +1283,7 @@ orbx_tri_batch* orbx_tri_batch_prepare(orbx_ctx* ctx, int Q, const orbx_tri_prob
   const size_t oMatch = B.reserve(sizeof(int) * (size_t)matchOfs[Q]), oNm = B.reserve(sizeof(int) * (size_t)Q);
   const size_t oFrames = B.reserve(sizeof(FrameDev) * 2 * (size_t)Q), oArgs = B.reserve(sizeof(TriArgs) * (size_t)Q);
   orbx_tri_batch* T = new orbx_tri_batch();
-  T->ctx = ctx; T->Q = Q; T->maxTot1 = maxTot1; T->matchOfs = matchOfs; T->n1 = n1; T->matchInts = (size_t)matchOfs[Q];
+  T->ctx = ctx; T->device = ctx->device; T->Q = Q; T->maxTot1 = maxTot1; T->matchOfs = matchOfs; T->n1 = n1; T->matchInts = (size_t)matchOfs[Q];
   if (cudaMalloc(&T->pool, B.size()) != cudaSuccess) {
     orbx_set_error("orbx_tri_batch_prepare: cudaMalloc(%zu) failed", B.size());
     cudaGetLastError();
@@ -1366,8 +1367,8 @@ int orbx_tri_batch_fetch(orbx_tri_batch* T, orbx_tri_problem* pr) {
 
 void orbx_tri_batch_destroy(orbx_tri_batch* T) {
   if (!T) return;
-  cudaSetDevice(T->ctx->device);
-  if (T->lastStream) cudaStreamSynchronize(T->lastStream);
+  cudaSetDevice(T->device);
+  cudaDeviceSynchronize();   // the stream of the last run may belong to an object that is gone already
   cudaFree(T->pool);
   delete T;
 }

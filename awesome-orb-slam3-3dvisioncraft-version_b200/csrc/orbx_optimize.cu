@@ -2824,6 +2824,7 @@ int orbx_local_ba(orbx_ctx* ctx, int n_kf, float* kf_Tcw, const uint8_t* kf_fixe
 // ------------------------------------------------------------------------------------------------------------------
 struct orbx_lba_batch {
   orbx_ctx* ctx = nullptr;
+  int device = 0;               // kept separately: destroy() must not dereference a context that may be gone already
   int P = 0;
   uint8_t* pool = nullptr;
   size_t poolBytes = 0;
@@ -2857,7 +2858,7 @@ orbx_lba_batch* orbx_lba_batch_prepare(orbx_ctx* ctx, int P, const orbx_lba_prob
   }
   if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
   orbx_lba_batch* L = new orbx_lba_batch();
-  L->ctx = ctx; L->P = P;
+  L->ctx = ctx; L->device = ctx->device; L->P = P;
   L->kfOfs.assign(P + 1, 0); L->mpOfs.assign(P + 1, 0); L->badOfs.assign(P + 1, 0);
   L->nKf.resize(P); L->nMp.resize(P); L->nE.resize(P);
   for (int p = 0; p < P; ++p) {
@@ -3021,8 +3022,8 @@ int orbx_lba_batch_fetch(orbx_lba_batch* L, orbx_lba_problem* pr) {
 
 void orbx_lba_batch_destroy(orbx_lba_batch* L) {
   if (!L) return;
-  cudaSetDevice(L->ctx->device);
-  if (L->lastStream) cudaStreamSynchronize(L->lastStream);
+  cudaSetDevice(L->device);
+  cudaDeviceSynchronize();   // the stream of the last run may belong to an object that is gone already
   cudaFree(L->pool);
   delete L;
 }

@@ -679,7 +679,7 @@ int orbx_tracker_set_chain(orbx_tracker* t, int enable, const float* d_Tcw_init)
   if (enable) {
     if (!t->d_Tlast) t->d_Tlast = talloc<float>(t, 16 * (size_t)t->S);
     if (!t->d_Tlast) return ORBX_ECUDA;
-    ORBX_CUDA(cudaMemcpy(t->d_Tlast, d_Tcw_init, sizeof(float) * 16 * t->S, cudaMemcpyDeviceToDevice));
+    ORBX_CUDA(cudaMemcpy(t->d_Tlast, d_Tcw_init, sizeof(float) * 16 * t->S, cudaMemcpyDefault));   // host or device pointer
   }
   t->chain = enable != 0;
   return ORBX_OK;

@@ -574,8 +574,8 @@ int orbx_tracker_upload_map(orbx_tracker *trk, const orbx_track_map *host_map);
 size_t orbx_tracker_map_bytes(const orbx_tracker *trk);
 /* Motion-model chaining (Tracking::TrackWithMotionModel, src/Tracking.cc:2354: SetPose(mVelocity * mLastFrame.mTcw)):
  * when enabled, the Tcw_prior argument of the step functions is the RELATIVE motion dT (last -> current, [S][16]) and
- * the prior used is dT * (pose the previous step produced), composed on the device; d_Tcw_init [S][16] (device) is
- * the pose before the first chained step. */
+ * the prior used is dT * (pose the previous step produced), composed on the device; d_Tcw_init [S][16] (a device OR
+ * host pointer) is the pose before the first chained step. */
 int orbx_tracker_set_chain(orbx_tracker *trk, int enable, const float *d_Tcw_init);
 /* Keyframe-rate work of the S streams (LocalMapping's share, which the reference runs in its own thread beside
  * Tracking, src/LocalMapping.cc:68-200): every `period`-th step the two prepared plans — the CreateNewMapPoints

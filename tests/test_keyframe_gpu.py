@@ -72,6 +72,7 @@ def test_triangulation_batch_handles_empty_feature_vectors(ctx, kf_frames):
     batch.run()
     got = batch.fetch()
     assert got[0][0] > 50 and got[1][0] == 0 and np.all(got[1][1] == -1)
+    batch.close()
 
 
 @pytest.mark.parametrize("shapes", [[(6, 300, 2), (8, 500, 2), (6, 300, 2), (5, 120, 1)], [(20, 3000, 3), (20, 3000, 3)]])

@@ -176,7 +176,6 @@ def test_tracker_given_map_matches_oracle_chain(ctx, ork):
 def test_tracker_chain_mode_composes_the_prior_on_the_device(ctx, ork):
     """Motion-model chaining: step t+1 starts from dT * (pose step t produced).  Equal to feeding that product from the host."""
     import orbx
-    import torch
     S = 2
     cam = orbx.make_camera()
     imgs, Tt, Tp, maps = _map_setup(ork, S, 150)
@@ -198,8 +197,8 @@ def test_tracker_chain_mode_composes_the_prior_on_the_device(ctx, ork):
                 prior[s, i, j] = acc
     trk.upload_map(host)
     want = trk.step(imgs, Tt, prior)                               # step 2 with the prior composed on the host
-    d_init = torch.from_numpy(T1.reshape(S, 16).copy()).cuda()
-    trk.set_chain(True, d_init.data_ptr())
+    init = np.ascontiguousarray(T1.reshape(S, 16))
+    trk.set_chain(True, init.ctypes.data)
     trk.upload_map(host)
     got = trk.step(imgs, Tt, dT)                                   # the same, composed on the device
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
