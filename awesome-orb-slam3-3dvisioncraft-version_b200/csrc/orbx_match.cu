@@ -851,6 +851,24 @@ __global__ void __launch_bounds__(256) tri_rot_filter_batch_kernel(const FrameDe
 // =====================================================================================
 // batched launchers
 // =====================================================================================
+// The ordered-replay kernels keep one byte per keypoint of the frame in dynamic shared memory.  Frames may hold up to
+// 65535 keypoints (the candidate records carry 16-bit indices), i.e. more than the 48 KB a kernel gets without opting in:
+// raise the limit once per device, and check every launch (a failed launch is not sticky -- without the check the entry
+// point would return ORBX_OK with untouched output buffers).
+static int resolve_smem_opt_in() {
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  ORBX_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (!done[dev & 63]) {
+    ORBX_CUDA(cudaFuncSetAttribute(sbp_frame_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 64));
+    ORBX_CUDA(cudaFuncSetAttribute(sbp_map_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 64));
+    done[dev & 63] = true;
+  }
+  return ORBX_OK;
+}
+
 int orbx_launch_stereo_batch(orbx_ctx* ctx, cudaStream_t st, const StereoArgs* dArgs, int S, int maxL) {
   stereo_match_kernel<<<dim3(div_up(maxL, (STEREO_NT / 32) * STEREO_KPW), S), STEREO_NT, 0, st>>>(dArgs);
   ORBX_LAUNCH(ctx);
@@ -861,6 +879,7 @@ int orbx_launch_stereo_batch(orbx_ctx* ctx, cudaStream_t st, const StereoArgs* d
 }
 int orbx_launch_sbp_frame_batch(orbx_ctx* ctx, cudaStream_t st, const FrameDev* dF, const SbpFrameArgs* dA, int S, int maxQ,
                                 int maxN) {
+  if (maxN + 16 > 48 * 1024) { int rc = resolve_smem_opt_in(); if (rc != ORBX_OK) return rc; }
   sbp_frame_score_kernel<<<dim3(div_up(maxQ * 32, 128), S), 128, 0, st>>>(dF, dA);
   ORBX_LAUNCH(ctx);
   sbp_frame_resolve_kernel<<<S, 32, align_up((size_t)maxN + 16, 16), st>>>(dF, dA);
@@ -870,6 +889,7 @@ int orbx_launch_sbp_frame_batch(orbx_ctx* ctx, cudaStream_t st, const FrameDev* 
 }
 int orbx_launch_sbp_map_batch(orbx_ctx* ctx, cudaStream_t st, const FrameDev* dF, const SbpMapArgs* dA, int S, int maxQ,
                               int maxN) {
+  if (maxN + 16 > 48 * 1024) { int rc = resolve_smem_opt_in(); if (rc != ORBX_OK) return rc; }
   sbp_map_score_kernel<<<dim3(div_up(maxQ * 32, 128), S), 128, 0, st>>>(dF, dA);
   ORBX_LAUNCH(ctx);
   sbp_map_resolve_kernel<<<S, 32, align_up((size_t)maxN + 16, 16), st>>>(dF, dA);
@@ -996,6 +1016,7 @@ int orbx_search_by_projection_map(orbx_ctx* ctx, const orbx_frame_desc* frame, c
   A.bestIdx = S.alloc<int>(nq);
   if (S.failed) return ORBX_ECUDA;
   ORBX_CUDA(cudaMemsetAsync(misc, 0, 4 * sizeof(int), st));
+  ORBX_CUDA(cudaMemsetAsync(A.bestIdx, 0xff, sizeof(int) * (size_t)std::max(nq, 1), st));   // -1: never hand back arena garbage
   rc = orbx_launch_grid_build(ctx, st, dF, 1);
   if (rc != ORBX_OK) return rc;
   A.nqDev = nullptr;
@@ -1005,8 +1026,10 @@ int orbx_search_by_projection_map(orbx_ctx* ctx, const orbx_frame_desc* frame, c
     sbp_map_score_kernel<<<dim3(div_up(nq * 32, 128), 1), 128, 0, st>>>(dF, dA);
     ORBX_LAUNCH(ctx);
   }
+  if (frame->n + 16 > 48 * 1024) { rc = resolve_smem_opt_in(); if (rc != ORBX_OK) return rc; }
   sbp_map_resolve_kernel<<<1, 32, align_up((size_t)frame->n + 16, 16), st>>>(dF, dA);
   ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
   int h[4];
   ORBX_CUDA(cudaMemcpyAsync(h, misc, sizeof h, cudaMemcpyDeviceToHost, st));
   if (nq > 0) ORBX_CUDA(cudaMemcpyAsync(best_idx, A.bestIdx, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
@@ -1073,6 +1096,10 @@ int orbx_search_by_projection_frame(orbx_ctx* ctx, const orbx_frame_desc* cur, c
   A.kept = S.alloc<uint8_t>(nq);
   A.curMatch = S.alloc<int>(cur->n);
   if (S.failed) return ORBX_ECUDA;
+  ORBX_CUDA(cudaMemsetAsync(A.matchIdx, 0xff, sizeof(int) * (size_t)std::max(nq, 1), st));   // -1 / 0: never hand back arena garbage
+  ORBX_CUDA(cudaMemsetAsync(A.kept, 0, (size_t)std::max(nq, 1), st));
+  ORBX_CUDA(cudaMemsetAsync(A.curMatch, 0xff, sizeof(int) * (size_t)std::max(cur->n, 1), st));
+  if (S.failed) return ORBX_ECUDA;
   ORBX_CUDA(cudaMemsetAsync(misc, 0, 4 * sizeof(int), st));
   rc = orbx_launch_grid_build(ctx, st, dF, 1);
   if (rc != ORBX_OK) return rc;
@@ -1084,8 +1111,10 @@ int orbx_search_by_projection_frame(orbx_ctx* ctx, const orbx_frame_desc* cur, c
     sbp_frame_score_kernel<<<dim3(div_up(nq * 32, 128), 1), 128, 0, st>>>(dF, dA);
     ORBX_LAUNCH(ctx);
   }
+  if (cur->n + 16 > 48 * 1024) { rc = resolve_smem_opt_in(); if (rc != ORBX_OK) return rc; }
   sbp_frame_resolve_kernel<<<1, 32, align_up((size_t)cur->n + 16, 16), st>>>(dF, dA);
   ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
   int h[4];
   ORBX_CUDA(cudaMemcpyAsync(h, misc, sizeof h, cudaMemcpyDeviceToHost, st));
   if (nq > 0) {
@@ -1212,6 +1241,7 @@ int orbx_search_for_triangulation(orbx_ctx* ctx, const orbx_frame_desc* kf1, con
   }
   tri_rot_filter_kernel<<<1, 256, 0, st>>>(dF, A);
   ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
   if (kf1->n > 0) ORBX_CUDA(cudaMemcpyAsync(match12, A.match12, sizeof(int) * kf1->n, cudaMemcpyDeviceToHost, st));
   ORBX_CUDA(cudaMemcpyAsync(nmatches, A.nmatches, sizeof(int), cudaMemcpyDeviceToHost, st));
   ORBX_CUDA(cudaStreamSynchronize(st));

@@ -244,16 +244,31 @@ void Optimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap
     }
   }
   num_fixedKF = (int)lFixedCameras.size() + num_fixedKF;
-  if (num_fixedKF < 2) {   // force two fixed keyframes: the two lowest ids of the window (:1901-1945)
-    for (int pass = 0; pass < 2 && num_fixedKF < 2; ++pass) {
-      KeyFrame* lowest = NULL;
-      for (KeyFrame* pKFi : lLocalKeyFrames) {
-        if (pKFi == pKF || pKFi->mnId == pMap->GetInitKFid()) continue;
-        if (!lowest || pKFi->mnId < lowest->mnId) lowest = pKFi;
+  if (num_fixedKF < 2) {
+    // Force two fixed keyframes exactly as the reference does (src/Optimizer.cc:1906-1945): ONE pass that keeps a
+    // running lowest id and, in the else-branch only, a running "second lowest" -- a keyframe displaced from the lowest
+    // slot is NOT demoted to second (ids visited as 4,3,5 fix {3,5}, not {3,4}).  The reference leaves both pointers
+    // uninitialised when no candidate qualifies and pushes them anyway; here a slot that was never assigned is skipped.
+    long unsigned int lowerId = pKF->mnId, secondLowerId = pKF->mnId;
+    KeyFrame *pLowerKf = NULL, *pSecondLowerKF = NULL;
+    for (KeyFrame* pKFi : lLocalKeyFrames) {
+      if (pKFi == pKF || pKFi->mnId == pMap->GetInitKFid()) continue;
+      if (pKFi->mnId < lowerId) {
+        lowerId = pKFi->mnId;
+        pLowerKf = pKFi;
+      } else if (pKFi->mnId < secondLowerId) {
+        secondLowerId = pKFi->mnId;
+        pSecondLowerKF = pKFi;
       }
-      if (!lowest) break;
-      lFixedCameras.push_back(lowest);
-      lLocalKeyFrames.remove(lowest);
+    }
+    if (pLowerKf) {
+      lFixedCameras.push_back(pLowerKf);
+      lLocalKeyFrames.remove(pLowerKf);
+      num_fixedKF++;
+    }
+    if (num_fixedKF < 2 && pSecondLowerKF) {
+      lFixedCameras.push_back(pSecondLowerKF);
+      lLocalKeyFrames.remove(pSecondLowerKF);
       num_fixedKF++;
     }
   }

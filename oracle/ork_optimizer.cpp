@@ -847,7 +847,48 @@ namespace ork {
 static void m3_mul(const double* A, const double* B, double* C) { mat3_mul(A, B, C); }
 static void m3_t(const double* A, double* T) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) T[i * 3 + j] = A[j * 3 + i]; }
 static void m3_v(const double* A, const double* v, double* o) { for (int i = 0; i < 3; ++i) o[i] = A[i * 3] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2]; }
+// ---- arithmetic variant (tests/test_oracle_inertial.py::test_reference_arithmetic_variant_stays_within_tolerance) ----
+// 0 (default, what the device implements): the conventions above.
+// 1: the reference's arithmetic where it can be restated without Eigen / OpenCV internals:
+//    * every NormalizeRotation is the polar factor U V^T of an SVD (here from the symmetric eigen-decomposition of R^T R,
+//      3 Newton-free Jacobi sweeps in double) instead of the quaternion round trip;
+//    * ExpSO3's result additionally passes through float32, like the cv::Mat(CV_32F) round trip of src/G2oTypes.cc:1012-1017;
+//    * the bias-corrected deltas GetDeltaRotation / Velocity / Position (src/ImuTypes.cc:373-394) are evaluated in float32
+//      on float32-rounded biases and Jacobians, as cv::Mat_<float> arithmetic does.
+//    NOT restated: this fork's Eigen NormalizeRotation returns svd.matrixU()*svd.matrixV() (V not transposed,
+//    src/G2oTypes.cc:1085-1089), whose value depends on which of the non-unique singular-vector pairs Eigen's JacobiSVD
+//    picks for a near-orthogonal matrix; the variant uses the intended U V^T.
+static int g_inertial_arith = 0;
+static void polar_orthonormalize(double* R) {
+  // R (R^T R)^(-1/2) via cyclic Jacobi on the symmetric 3x3 R^T R
+  double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A[i * 3 + j] = R[0 * 3 + i] * R[0 * 3 + j] + R[1 * 3 + i] * R[1 * 3 + j] + R[2 * 3 + i] * R[2 * 3 + j];
+  for (int sweep = 0; sweep < 12; ++sweep)
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = A[p * 3 + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double theta = (A[q * 3 + q] - A[p * 3 + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; ++k) { const double a = A[k * 3 + p], b = A[k * 3 + q]; A[k * 3 + p] = c * a - sn * b; A[k * 3 + q] = sn * a + c * b; }
+        for (int k = 0; k < 3; ++k) { const double a = A[p * 3 + k], b = A[q * 3 + k]; A[p * 3 + k] = c * a - sn * b; A[q * 3 + k] = sn * a + c * b; }
+        for (int k = 0; k < 3; ++k) { const double a = V[k * 3 + p], b = V[k * 3 + q]; V[k * 3 + p] = c * a - sn * b; V[k * 3 + q] = sn * a + c * b; }
+      }
+  double Mi[9];   // (R^T R)^(-1/2) = V diag(1/sqrt(lambda)) V^T
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double acc = 0;
+      for (int k = 0; k < 3; ++k) acc += V[i * 3 + k] * V[j * 3 + k] / std::sqrt(A[k * 3 + k]);
+      Mi[i * 3 + j] = acc;
+    }
+  double out[9];
+  mat3_mul(R, Mi, out);
+  for (int i = 0; i < 9; ++i) R[i] = out[i];
+}
 static void orthonormalize(double* R) {   // convention, see above
+  if (g_inertial_arith == 1) { polar_orthonormalize(R); return; }
   Quat q = quat_from_R(R);
   quat_normalize(q);
   quat_to_R(q, R);
@@ -861,6 +902,12 @@ static void exp_so3(const double* w, double* R) {   // ExpSO3 (src/G2oTypes.cc:1
   const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   if (d < 1e-5) { for (int i = 0; i < 9; ++i) R[i] = I[i] + W[i] + 0.5 * W2[i]; }
   else { const double a = std::sin(d) / d, b = (1.0 - std::cos(d)) / d2; for (int i = 0; i < 9; ++i) R[i] = I[i] + W[i] * a + W2[i] * b; }
+  if (g_inertial_arith == 1) {   // Converter::toCvMat (CV_32F) -> IMU::NormalizeRotation -> Converter::toMatrix3d
+    for (int i = 0; i < 9; ++i) R[i] = (double)(float)R[i];
+    polar_orthonormalize(R);
+    for (int i = 0; i < 9; ++i) R[i] = (double)(float)R[i];
+    return;
+  }
   orthonormalize(R);
 }
 static void log_so3(const double* R, double* w) {   // LogSO3 (:1021-1035)
@@ -1311,6 +1358,30 @@ struct InertialProblemLF {
   // (pose1 0-5, velocity1 6-8, gyro1 9-11, acc1 12-14, pose2 15-20, velocity2 21-23)
   void inertial(double* e9, double* J) const {
     double dbg[3], dba[3], w[3], Ew[9], dRc[9], dV[3], dP[3];
+    if (g_inertial_arith == 1) {
+      // src/ImuTypes.cc:373-394 in cv::Mat_<float> arithmetic: IMU::Bias holds floats, dbg/dba are float differences, the
+      // 3x3 * 3x1 products take cv::gemm's small-matrix fp32 path (a0*b0 + a1*b1 + a2*b2, left to right), sums in float
+      float fbg[3], fba[3];
+      for (int i = 0; i < 3; ++i) { fbg[i] = (float)prev.bg[i] - (float)bpre[i]; fba[i] = (float)prev.ba[i] - (float)bpre[3 + i]; }
+      auto mv = [](const double* A, const float* v, float* o) {
+        for (int i = 0; i < 3; ++i) o[i] = ((float)A[i * 3] * v[0] + (float)A[i * 3 + 1] * v[1]) + (float)A[i * 3 + 2] * v[2];
+      };
+      float fw[3], f1[3], f2[3];
+      mv(JRg, fbg, fw);
+      for (int i = 0; i < 3; ++i) w[i] = fw[i];
+      exp_so3(w, Ew);
+      float fR[9];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+          fR[i * 3 + j] = ((float)dR0[i * 3] * (float)Ew[j] + (float)dR0[i * 3 + 1] * (float)Ew[3 + j]) + (float)dR0[i * 3 + 2] * (float)Ew[6 + j];
+      for (int i = 0; i < 9; ++i) dRc[i] = fR[i];
+      polar_orthonormalize(dRc);
+      for (int i = 0; i < 9; ++i) dRc[i] = (double)(float)dRc[i];
+      mv(JVg, fbg, f1); mv(JVa, fba, f2);
+      for (int i = 0; i < 3; ++i) dV[i] = ((float)dV0[i] + f1[i]) + f2[i];
+      mv(JPg, fbg, f1); mv(JPa, fba, f2);
+      for (int i = 0; i < 3; ++i) dP[i] = ((float)dP0[i] + f1[i]) + f2[i];
+    } else {
     for (int i = 0; i < 3; ++i) { dbg[i] = prev.bg[i] - bpre[i]; dba[i] = prev.ba[i] - bpre[3 + i]; }
     m3_v(JRg, dbg, w);
     exp_so3(w, Ew);
@@ -1321,6 +1392,7 @@ struct InertialProblemLF {
     for (int i = 0; i < 3; ++i) dV[i] = dV0[i] + t1[i] + t2[i];
     m3_v(JPg, dbg, t1); m3_v(JPa, dba, t2);
     for (int i = 0; i < 3; ++i) dP[i] = dP0[i] + t1[i] + t2[i];
+    }
     const double g[3] = {0, 0, -9.81};
     double Rbw1[9], dRt[9], T1[9], eR[9], er[3];
     m3_t(prev.Rwb, Rbw1);
@@ -1578,6 +1650,13 @@ int ork_jacobi_eig(int n, double* A, double* V) { jacobi_eig(n, A, V); return OR
 int ork_marginalize_prev(const double* H30, double* H15) { marginalize_prev(H30, H15); return ORBX_OK; }
 
 // test hooks: the analytic Jacobians against the error functions (finite differences are taken by the test)
+// selects the arithmetic variant of the inertial section (0: conventions = device, 1: reference-like float32 / SVD); returns the old one
+int ork_inertial_set_arithmetic(int mode) {
+  const int old = g_inertial_arith;
+  g_inertial_arith = mode ? 1 : 0;
+  return old;
+}
+
 int ork_inertial_debug(const double* state, const double* kfState, const double* preint, double* e9, double* J81) {
   InertialProblem P;
   std::memcpy(P.Rwb, state, 72); std::memcpy(P.twb, state + 9, 24); std::memcpy(P.v, state + 12, 24);

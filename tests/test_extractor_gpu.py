@@ -186,3 +186,37 @@ def test_blur_plane_equals_oracle_on_every_level(ctx, ork):
             seen.add(lvl.shape[1] % 4)
         ex.close()
     assert seen  # (per-size coverage of w % 4 is by construction of the list above)
+
+
+def test_alternating_extractors_keep_their_shared_memory_opt_in(ctx, ork):
+    """The dynamic shared-memory opt-in of the FAST / quadtree kernels is process-wide per kernel: a later, smaller
+    extractor must not lower it under an earlier one that is still in use (monocular initialisation uses 5 x nFeatures
+    beside the regular extractor, src/Tracking.cc:593-599; a re-initialisation alternates between them)."""
+    import orbx
+    from orbx import synth
+    img = synth.scene_image(13, 752, 480)
+    big = orbx.ORBextractor(ctx, nfeatures=5000)
+    a = big(img)
+    small = orbx.ORBextractor(ctx, nfeatures=1000)
+    b = small(img)
+    for _ in range(2):
+        a2, b2 = big(img), small(img)            # cached geometry on both: no reconfiguration in between
+        assert np.array_equal(a2[1], a[1]) and np.array_equal(a2[2], a[2])
+        assert np.array_equal(b2[1], b[1]) and np.array_equal(b2[2], b[2])
+    _assert_same(ork.Extractor(5000)(img), a, "5000 after 1000")
+    big.close()
+    small.close()
+
+
+def test_failed_reconfiguration_does_not_leave_mixed_geometry(ctx, ork):
+    """A call with an unsupported size fails cleanly and the next call with the previous size still gives the right answer."""
+    import orbx
+    from orbx import synth
+    img = synth.scene_image(2, 640, 400)
+    ex = orbx.ORBextractor(ctx, max_w=640, max_h=400)
+    good = ex(img)
+    with pytest.raises(orbx.OrbxError):
+        ex(synth.scene_image(1, 200, 150))       # last level narrower than one FAST cell
+    again = ex(img)
+    assert np.array_equal(good[1], again[1]) and np.array_equal(good[2], again[2])
+    ex.close()

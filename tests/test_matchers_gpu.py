@@ -153,3 +153,17 @@ def test_matchers_handle_empty_inputs(ctx, ork):
                                               np.zeros(0, np.uint8), np.zeros((0, 3), np.float32),
                                               np.zeros(0, np.int32), z, np.zeros((0, 32), np.uint8), 7.0, False, sf)
     assert n == 0
+
+
+def test_projection_searches_on_a_frame_above_48k_keypoints(ctx, ork):
+    """The ordered-replay kernels keep one byte per keypoint in dynamic shared memory: above 49 136 keypoints that needs the
+    opt-in (and every launch is checked) — the result must still be the oracle's, not untouched output buffers."""
+    import orbx
+    n = 52000
+    kps, desc = sc.synthetic_keypoints(5, n)
+    F = orbx.Frame(kps, desc, None)
+    s = sc.sbp_map_scenario(77, kps[:1000], desc[:1000], None, nq=300)
+    args = (F, None, s["projX"], s["projY"], None, s["level"], s["viewCos"], s["mpDesc"], s["flags"], 3.0)
+    rn, rbest = ork.search_by_projection_map(*args, 0.8, s["scaleFactors"])
+    gn, gbest = orbx.ORBmatcher(ctx, 0.8).SearchByProjectionMap(*args, s["scaleFactors"])
+    assert rn > 20 and gn == rn and np.array_equal(gbest, rbest)

@@ -292,3 +292,38 @@ def test_pose_inertial_argument_errors(ctx):
     assert call(k["ofs"], prior_H=None) != 0                   # missing prior
     with pytest.raises(orbx.OrbxError):
         api._check(call(np.array([0, 50, 40], np.int32)), "orbx_pose_inertial_optimization_last_frame_batch")
+
+
+def test_local_ba_stop_flag_raised_during_the_run(ctx, ork):
+    """Tracking::InterruptBA sets mbAbortBA while LocalBundleAdjustment runs (g2o polls forceStopFlag between iterations,
+    sparse_optimizer.cpp:369-376; the reference then skips the second optimize(), src/Optimizer.cc:2201-2290).  The flag
+    is raised from another thread while the kernel is running: the call must come back early, consistently (status 0,
+    fewer iterations than an undisturbed run, poses written), and never later than the undisturbed run's count."""
+    import threading
+    import time
+    import orbx
+    cam = orbx.make_camera()
+    opt = orbx.Optimizer(ctx)
+    s = sc.lba_scenario(1, K=20, M=3000, n_fixed=3)
+    a = (s["kf_T"], s["kf_fixed"], s["mp_xyz"], s["e_kf"], s["e_mp"], s["e_obs"], s["e_inv_sigma2"], cam)
+    _, _, _, full_it, full_st = opt.LocalBundleAdjustment(*a)
+    assert full_st == 0 and full_it.sum() >= 6
+    early = 0
+    for delay in (0.0002, 0.0006, 0.0012, 0.002):
+        stop = np.zeros(1, np.uint8)
+
+        def raise_flag():
+            time.sleep(delay)
+            stop[0] = 1
+        th = threading.Thread(target=raise_flag)
+        th.start()
+        gT, gX, gbad, git, gst = opt.LocalBundleAdjustment(*a, stop=stop)
+        th.join()
+        assert gst in (0, 1)
+        assert git[0] <= full_it[0] and git[1] <= full_it[1]
+        if git.sum() < full_it.sum():
+            early += 1
+            assert np.isfinite(gT).all() and np.isfinite(gX).all()
+            if gst == 0 and git.sum() > 0:      # interrupted after some iterations: the partial result is written back
+                assert not np.array_equal(gT.reshape(-1, 16), s["kf_T"].reshape(-1, 16))
+    assert early >= 1, "the stop flag never took effect during a run"
