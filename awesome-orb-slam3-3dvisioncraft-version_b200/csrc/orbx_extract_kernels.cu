@@ -17,38 +17,90 @@ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9
 
 // =====================================================================================
 // K1  pyramid level l from level l-1: cv::resize(INTER_LINEAR) 8U fixed point.
-// grid (ceil(w/4/128), h, B), block 128; each thread produces 4 horizontally adjacent pixels.
+// grid (ceil(w/4/128), ceil(h/PYR_STRIP), B), block 128.  A thread owns 4 horizontally adjacent output pixels and walks
+// down a strip of PYR_STRIP output rows.  The horizontal pass of a SOURCE row (T = S[x0]*a0 + S[x0+1]*a1, kept as T >> 4)
+// is computed once and reused by every output row that blends it: with the 1.2 scale factor a source row feeds 1.67
+// output rows on average, and consecutive output rows usually share one of their two source rows, so the thread keeps
+// the two most recent horizontal rows in registers (tags rowA / rowB, warp-uniform control flow).  The vertical pass is
+//   ((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2
+// with each ">> 16" product taken as a high multiply by b << 16 (coefficients are in [0, 2048], so this is exact).
+// About 12 issued instructions per output pixel instead of 45 for the one-output-row-per-thread form it replaces.
 // Packed coefficient tables (int16 x 4 per destination column / row, one 8-byte load each):
 //   X[dx] = { xofs, a0, a1, 0 }     Y[dy] = { y0, y1, b0, b1 }
 // =====================================================================================
+#define PYR_STRIP 16
+
+struct PyrCols {            // per-thread constants of its 4 output columns
+  int x0[4];
+  int a0[4], a1[4];
+};
+
+__device__ __forceinline__ void pyr_hrow(const uint8_t* __restrict__ row, const PyrCols& C, int (&T)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    // x0 + 1 may be one past the last source pixel at the right edge: there a1 == 0 (OpenCV clamps fx to 0) and the
+    // byte read lies inside the row's pitch padding
+    const int v = (int)__ldg(row + C.x0[i]) * C.a0[i] + (int)__ldg(row + C.x0[i] + 1) * C.a1[i];
+    T[i] = v >> 4;
+  }
+}
+
 __global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__ ExtractParams p, int level) {
   const LevelParams& D = p.lv[level];
   const LevelParams& S = p.lv[level - 1];
   const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int dy = blockIdx.y;
   if (dx0 >= D.w) return;
-  const short4 ty = reinterpret_cast<const short4*>(p.tab + D.tabY)[dy];
-  const int b0 = ty.z, b1 = ty.w;
+  const int dyBeg = blockIdx.y * PYR_STRIP, dyEnd = min(dyBeg + PYR_STRIP, D.h);
   const uint8_t* src = S.pyr + (size_t)blockIdx.z * S.imgStride;
-  const uint8_t* S0 = src + (size_t)ty.x * S.pitch;
-  const uint8_t* S1 = src + (size_t)ty.y * S.pitch;
-  // the table is padded to a multiple of 4 entries, so the two 16-byte loads never leave it
-  const int4* tx4 = reinterpret_cast<const int4*>(p.tab + D.tabX) + (dx0 >> 1);
-  const int4 e01 = __ldg(tx4), e23 = __ldg(tx4 + 1);
-  const int ent[8] = {e01.x, e01.y, e01.z, e01.w, e23.x, e23.y, e23.z, e23.w};
-  const int xmax = S.w - 1;
-  uint32_t out = 0;
+  uint8_t* dst = D.pyr + (size_t)blockIdx.z * D.imgStride + dx0;
+  PyrCols C;
+  {
+    // the table is padded to a multiple of 4 entries, so the two 16-byte loads never leave it
+    const int4* tx4 = reinterpret_cast<const int4*>(p.tab + D.tabX) + (dx0 >> 1);
+    const int4 e01 = __ldg(tx4), e23 = __ldg(tx4 + 1);
+    const int ent[8] = {e01.x, e01.y, e01.z, e01.w, e23.x, e23.y, e23.z, e23.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int x0 = ent[2 * i] & 0xffff, a0 = ent[2 * i] >> 16, a1 = (short)(ent[2 * i + 1] & 0xffff);
-    const int x1 = min(x0 + 1, xmax);
-    const int T0 = __ldg(S0 + x0) * a0 + __ldg(S0 + x1) * a1;
-    const int T1 = __ldg(S1 + x0) * a0 + __ldg(S1 + x1) * a1;
-    const int v = (((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2;
-    out |= (uint32_t)(v & 0xff) << (8 * i);
+    for (int i = 0; i < 4; ++i) {
+      C.x0[i] = ent[2 * i] & 0xffff;
+      C.a0[i] = ent[2 * i] >> 16;
+      C.a1[i] = (short)(ent[2 * i + 1] & 0xffff);
+    }
   }
-  uint8_t* dst = D.pyr + (size_t)blockIdx.z * D.imgStride + (size_t)dy * D.pitch + dx0;
-  *reinterpret_cast<uint32_t*>(dst) = out;  // pitch is a multiple of 16 and padded: safe past w
+  const short4* tabY = reinterpret_cast<const short4*>(p.tab + D.tabY);
+  int TA[4], TB[4];
+  int rowA = -1, rowB = -1;
+#pragma unroll 1
+  for (int dy = dyBeg; dy < dyEnd; ++dy) {
+    const short4 ty = tabY[dy];                      // uniform across the block
+    const int y0 = ty.x, y1 = ty.y;
+    // bring the horizontal pass of source rows y0 -> TA, y1 -> TB (reusing what the previous output row left)
+    if (y0 != rowA) {
+      if (y0 == rowB) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) TA[i] = TB[i];
+      } else {
+        pyr_hrow(src + (size_t)y0 * S.pitch, C, TA);
+      }
+      rowA = y0;
+    }
+    if (y1 != rowB) {
+      if (y1 == y0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) TB[i] = TA[i];
+      } else {
+        pyr_hrow(src + (size_t)y1 * S.pitch, C, TB);
+      }
+      rowB = y1;
+    }
+    const int B0 = (int)ty.z << 16, B1 = (int)ty.w << 16;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = (__mulhi(B0, TA[i]) + __mulhi(B1, TB[i]) + 2) >> 2;
+      out |= (uint32_t)(v & 0xff) << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(dst + (size_t)dy * D.pitch) = out;  // pitch is a multiple of 16 and padded: safe past w
+  }
 }
 
 // =====================================================================================
@@ -457,50 +509,61 @@ __device__ __forceinline__ void blur_hrow(uint32_t a, uint32_t b, uint32_t c, in
   }
 }
 
-__global__ void __launch_bounds__(256) gauss7_kernel(const __grid_constant__ ExtractParams p) {
+__global__ void __launch_bounds__(256, 3) gauss7_kernel(const __grid_constant__ ExtractParams p) {
   const int tile = blockIdx.x;
   int level = 0;
 #pragma unroll 1
   for (int l = 1; l < p.nlevels; ++l)
     if (tile >= p.lv[l].blurTileStart) level = l;
-  const LevelParams& L = p.lv[level];
-  const int lt = tile - L.blurTileStart;
-  const int tyi = lt / L.blurTilesX, txi = lt - tyi * L.blurTilesX;
+  // everything the row loop needs from the (dynamically indexed) level record, once, in registers
+  const int w = p.lv[level].w, h = p.lv[level].h, pitch = p.lv[level].pitch, opitch = p.lv[level].blurPitch;
+  const int lt = tile - p.lv[level].blurTileStart, tilesX = p.lv[level].blurTilesX;
+  const int tyi = lt / tilesX, txi = lt - tyi * tilesX;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int c = txi * 32 + lane;                       // word column
   const int y0 = (tyi * 8 + wid) * BLUR_STRIP;         // first output row of this warp's strip
-  if (4 * c >= L.w || y0 >= L.h) return;
-  const uint8_t* img = L.pyr + (size_t)blockIdx.y * L.imgStride;
-  uint8_t* out = L.blur + (size_t)blockIdx.y * L.blurStride;
-  const int y1 = min(y0 + BLUR_STRIP, L.h);
-  const BlurCols q = blur_cols(c, L.w);
-  int h[7][4];   // horizontal sums of rows y-3..y+3 (statically indexed: the row loop is unrolled by 7)
+  if (4 * c >= w || y0 >= h) return;
+  const uint8_t* img = p.lv[level].pyr + (size_t)blockIdx.y * p.lv[level].imgStride;
+  uint8_t* out = p.lv[level].blur + (size_t)blockIdx.y * p.lv[level].blurStride + 4 * c;
+  const int y1 = min(y0 + BLUR_STRIP, h);
+  const BlurCols q = blur_cols(c, w);
+  // per-thread column pointers (the three clamped words of a row), advanced by whole rows
+  const uint32_t* colA = reinterpret_cast<const uint32_t*>(img) + q.ia;
+  const int dB = q.ib - q.ia, dC = q.ic - q.ia;        // 0 or 1 / 1 or 2 words to the right of colA
+  auto load_row = [&](int yy, uint32_t& wa, uint32_t& wb, uint32_t& wc) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(colA) + (size_t)yy * pitch);
+    const uint32_t a0 = __ldg(r), b0 = __ldg(r + dB), c0 = __ldg(r + dC);
+    wa = q.fixA ? __byte_perm(b0, c0, 0x1234) : a0;
+    wb = q.fixB ? __byte_perm(a0, b0, q.selB) : b0;
+    wc = q.fixCab ? __byte_perm(a0, b0, q.selC) : (q.fixCbc ? __byte_perm(b0, c0, q.selC) : c0);
+  };
+  int hs[7][4];   // horizontal sums of rows y-3..y+3 (statically indexed: the row loop is unrolled by 7)
   // prologue: rows y0-3 .. y0+2
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
-    const uint8_t* row = img + (size_t)reflect101(y0 - 3 + r, L.h) * L.pitch;
     uint32_t wa, wb, wc;
-    blur_words(row, q, wa, wb, wc);
-    blur_hrow(wa, wb, wc, h[r]);
+    load_row(reflect101(y0 - 3 + r, h), wa, wb, wc);
+    blur_hrow(wa, wb, wc, hs[r]);
   }
   for (int yb = y0; yb < y1; yb += 7) {
 #pragma unroll
     for (int u = 0; u < 7; ++u) {
       const int y = yb + u;
       if (y < y1) {
-        // newest row y+3 goes to slot (6+u)%7; rows y-3..y+3 sit in slots (u+j)%7, j = 0..6
-        const uint8_t* row = img + (size_t)reflect101(y + 3, L.h) * L.pitch;
+        // newest row y+3 goes to slot (6+u)%7; rows y-3..y+3 sit in slots (u+j)%7, j = 0..6.  y + 3 >= 3 is never above the
+        // image, so only the bottom border reflects here
+        int yy = y + 3;
+        if (yy >= h) yy = max(2 * (h - 1) - yy, 0);
         uint32_t wa, wb, wc;
-        blur_words(row, q, wa, wb, wc);
-        blur_hrow(wa, wb, wc, h[(6 + u) % 7]);
-        uint32_t o = 0;
+        load_row(yy, wa, wb, wc);
+        blur_hrow(wa, wb, wc, hs[(6 + u) % 7]);
+        unsigned acc[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const unsigned acc = 18u * (unsigned)(h[u % 7][k] + h[(u + 6) % 7][k]) + 34u * (unsigned)(h[(u + 1) % 7][k] + h[(u + 5) % 7][k]) +
-                               48u * (unsigned)(h[(u + 2) % 7][k] + h[(u + 4) % 7][k]) + 56u * (unsigned)h[(u + 3) % 7][k];
-          o |= ((acc + 32768u) >> 16) << (8 * k);
-        }
-        *reinterpret_cast<uint32_t*>(out + (size_t)y * L.blurPitch + 4 * c) = o;   // pitch padding absorbs the tail
+        for (int k = 0; k < 4; ++k)      // < 2^24; the rounded result is byte 2 of the accumulator
+          acc[k] = 18u * (unsigned)(hs[u % 7][k] + hs[(u + 6) % 7][k]) + 34u * (unsigned)(hs[(u + 1) % 7][k] + hs[(u + 5) % 7][k]) +
+                   48u * (unsigned)(hs[(u + 2) % 7][k] + hs[(u + 4) % 7][k]) + (56u * (unsigned)hs[(u + 3) % 7][k] + 32768u);
+        const uint32_t o = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
+        *reinterpret_cast<uint32_t*>(out + (size_t)y * opitch) = o;   // pitch padding absorbs the tail
       }
     }
   }
@@ -1026,7 +1089,7 @@ int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, 
 #define ORBX_EV(i) do { if (ev) ORBX_CUDA(cudaEventRecord(ev[i], st)); } while (0)
   ORBX_EV(0);
   for (int l = 1; l < p.nlevels; ++l) {
-    dim3 grid(div_up(div_up(p.lv[l].w, 4), 128), p.lv[l].h, B);
+    dim3 grid(div_up(div_up(p.lv[l].w, 4), 128), div_up(p.lv[l].h, PYR_STRIP), B);
     pyr_resize_kernel<<<grid, 128, 0, st>>>(p, l);
     ORBX_LAUNCH(ctx);
   }
