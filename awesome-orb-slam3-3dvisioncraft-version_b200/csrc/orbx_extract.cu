@@ -192,10 +192,10 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
     fastBytes = std::max(fastBytes, ORBX_FAST_TP * (L.hCell + 14));
     fastScore = std::max(fastScore, ORBX_FAST_TP * (L.hCell + 2));
     fastCand = std::max(fastCand, (int)align_up((size_t)(L.fastCells * L.wCell) * L.hCell, 64));
-    L.blurTilesX = div_up(L.w, ORBX_BLUR_TW);        // 128 columns per warp (32 lanes x 4 px)
-    L.blurTilesY = div_up(L.h, ORBX_BLUR_TH);        // 8 warps x 32-row strips per CTA
+    L.blurTilesX = div_up(L.w, ORBX_BLUR_TW);        // warp tiles per row: 128 columns per warp (32 lanes x 4 px)
+    L.blurTilesY = div_up(L.h, ORBX_BLUR_STRIP);     // warp tiles per column: 32-row strips
     L.blurTileStart = btile;
-    btile += L.blurTilesX * L.blurTilesY;
+    btile += div_up(L.blurTilesX * L.blurTilesY, 8); // a CTA takes 8 consecutive warp tiles (row-major)
     L.nFeat = e->nFeat[l];
     L.nIni = (int)std::round(width / height);
     L.hX = width / (float)L.nIni;

@@ -28,7 +28,7 @@ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9
 // Packed coefficient tables (int16 x 4 per destination column / row, one 8-byte load each):
 //   X[dx] = { xofs, a0, a1, 0 }     Y[dy] = { y0, y1, b0, b1 }
 // =====================================================================================
-#define PYR_STRIP 16
+#define PYR_STRIP 8
 
 struct PyrCols {            // per-thread constants of its 4 output columns
   int x0[4];
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
 // sums in registers, and emits one packed output word per row from the vertical 7-tap combination.
 // A warp covers 128 columns; global loads are one coalesced 128-byte row segment plus two halo words.
 // =====================================================================================
-#define BLUR_STRIP 32   // output rows per warp (6 extra rows are filtered horizontally per strip)
+#define BLUR_STRIP ORBX_BLUR_STRIP   // output rows per warp (6 extra rows are filtered horizontally per strip)
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (i < 0) i = -i;
@@ -517,11 +517,15 @@ __global__ void __launch_bounds__(256, 3) gauss7_kernel(const __grid_constant__ 
     if (tile >= p.lv[l].blurTileStart) level = l;
   // everything the row loop needs from the (dynamically indexed) level record, once, in registers
   const int w = p.lv[level].w, h = p.lv[level].h, pitch = p.lv[level].pitch, opitch = p.lv[level].blurPitch;
+  // warp tiles (128 columns x BLUR_STRIP rows) are numbered row-major and a CTA takes 8 consecutive ones: its warps sit
+  // side by side on the same rows, so the CTA streams whole contiguous image rows (DRAM-page friendly) instead of eight
+  // 128-byte columns with a stride of one pitch
   const int lt = tile - p.lv[level].blurTileStart, tilesX = p.lv[level].blurTilesX;
-  const int tyi = lt / tilesX, txi = lt - tyi * tilesX;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int wt = lt * 8 + wid;
+  const int tyi = wt / tilesX, txi = wt - tyi * tilesX;
   const int c = txi * 32 + lane;                       // word column
-  const int y0 = (tyi * 8 + wid) * BLUR_STRIP;         // first output row of this warp's strip
+  const int y0 = tyi * BLUR_STRIP;                     // first output row of this warp's strip
   if (4 * c >= w || y0 >= h) return;
   const uint8_t* img = p.lv[level].pyr + (size_t)blockIdx.y * p.lv[level].imgStride;
   uint8_t* out = p.lv[level].blur + (size_t)blockIdx.y * p.lv[level].blurStride + 4 * c;
@@ -530,32 +534,43 @@ __global__ void __launch_bounds__(256, 3) gauss7_kernel(const __grid_constant__ 
   // per-thread column pointers (the three clamped words of a row), advanced by whole rows
   const uint32_t* colA = reinterpret_cast<const uint32_t*>(img) + q.ia;
   const int dB = q.ib - q.ia, dC = q.ic - q.ia;        // 0 or 1 / 1 or 2 words to the right of colA
-  auto load_row = [&](int yy, uint32_t& wa, uint32_t& wb, uint32_t& wc) {
+  // raw loads and border fix-up are separate so that the loads of the NEXT row can be issued before the arithmetic of the
+  // current one (the kernel is bound by load latency, not by issue slots: one row in flight per warp was 46 % issue
+  // utilisation with "long scoreboard" as the top stall)
+  auto load_raw = [&](int yy, uint32_t& a0, uint32_t& b0, uint32_t& c0) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(colA) + (size_t)yy * pitch);
-    const uint32_t a0 = __ldg(r), b0 = __ldg(r + dB), c0 = __ldg(r + dC);
+    a0 = __ldg(r); b0 = __ldg(r + dB); c0 = __ldg(r + dC);
+  };
+  auto fix_row = [&](uint32_t a0, uint32_t b0, uint32_t c0, uint32_t& wa, uint32_t& wb, uint32_t& wc) {
     wa = q.fixA ? __byte_perm(b0, c0, 0x1234) : a0;
     wb = q.fixB ? __byte_perm(a0, b0, q.selB) : b0;
     wc = q.fixCab ? __byte_perm(a0, b0, q.selC) : (q.fixCbc ? __byte_perm(b0, c0, q.selC) : c0);
   };
+  auto bottom = [&](int yy) { return yy >= h ? max(2 * (h - 1) - yy, 0) : yy; };   // rows below the image reflect
   int hs[7][4];   // horizontal sums of rows y-3..y+3 (statically indexed: the row loop is unrolled by 7)
-  // prologue: rows y0-3 .. y0+2
+  // prologue: rows y0-3 .. y0+2 (six independent rows: all 18 loads are issued before the first use)
+  {
+    uint32_t ra[6], rb[6], rc[6];
 #pragma unroll
-  for (int r = 0; r < 6; ++r) {
-    uint32_t wa, wb, wc;
-    load_row(reflect101(y0 - 3 + r, h), wa, wb, wc);
-    blur_hrow(wa, wb, wc, hs[r]);
+    for (int r = 0; r < 6; ++r) load_raw(reflect101(y0 - 3 + r, h), ra[r], rb[r], rc[r]);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      uint32_t wa, wb, wc;
+      fix_row(ra[r], rb[r], rc[r], wa, wb, wc);
+      blur_hrow(wa, wb, wc, hs[r]);
+    }
   }
+  uint32_t na, nb, nc;                                   // row y+3 of the next output row, already on its way
+  load_raw(bottom(y0 + 3), na, nb, nc);
   for (int yb = y0; yb < y1; yb += 7) {
 #pragma unroll
     for (int u = 0; u < 7; ++u) {
       const int y = yb + u;
       if (y < y1) {
-        // newest row y+3 goes to slot (6+u)%7; rows y-3..y+3 sit in slots (u+j)%7, j = 0..6.  y + 3 >= 3 is never above the
-        // image, so only the bottom border reflects here
-        int yy = y + 3;
-        if (yy >= h) yy = max(2 * (h - 1) - yy, 0);
+        // newest row y+3 goes to slot (6+u)%7; rows y-3..y+3 sit in slots (u+j)%7, j = 0..6
         uint32_t wa, wb, wc;
-        load_row(yy, wa, wb, wc);
+        fix_row(na, nb, nc, wa, wb, wc);
+        if (y + 1 < y1) load_raw(bottom(y + 4), na, nb, nc);   // prefetch for the next output row
         blur_hrow(wa, wb, wc, hs[(6 + u) % 7]);
         unsigned acc[4];
 #pragma unroll
