@@ -6,6 +6,7 @@
 #include <string>
 #include <atomic>
 #include <mutex>
+#include <vector>
 #include "../../include/orbx.h"
 
 void orbx_set_error(const char* fmt, ...);
@@ -32,6 +33,9 @@ struct orbx_ctx {
   uint8_t* arenaDev = nullptr;
   uint8_t* arenaHost = nullptr;
   size_t arenaCap = 0;
+  // Device-resident frames (orbx_frame_upload): looked up by the matcher entry points under apiMutex, keyed by the host
+  // arrays of the descriptor they were uploaded from.
+  std::vector<struct orbx_frame*> residentFrames;
 };
 
 #define ORBX_LAUNCH(ctx) ((ctx)->launches.fetch_add(1, std::memory_order_relaxed))

@@ -162,6 +162,13 @@ int orbx_upload_frame(DevScope& S, const orbx_frame_desc* f, FrameDev* out) {
     orbx_set_error("orbx: invalid frame descriptor");
     return ORBX_EINVAL;
   }
+  // a frame that was made device-resident with orbx_frame_upload: nothing to copy, grid already built
+  for (orbx_frame* R : S.ctx->residentFrames)
+    if (R->keyKps == (const void*)f->kps && R->keyDesc == (const void*)f->desc && R->keyUright == (const void*)f->uright && R->n == f->n &&
+        R->bounds[0] == f->min_x && R->bounds[1] == f->min_y && R->bounds[2] == f->max_x && R->bounds[3] == f->max_y) {
+      *out = R->F;
+      return ORBX_OK;
+    }
   out->n = f->n;
   out->nDev = nullptr;
   out->kps = S.upload(f->kps, f->n);
@@ -175,6 +182,7 @@ int orbx_upload_frame(DevScope& S, const orbx_frame_desc* f, FrameDev* out) {
   out->hInv = (float)ORBX_GRID_ROWS / (f->max_y - f->min_y);
   out->cellStart = S.alloc<int>(ORBX_NCELLS + 1);
   out->cellIdx = S.alloc<int>(f->n);
+  out->gridBuilt = 0;
   return S.failed ? ORBX_ECUDA : ORBX_OK;
 }
 
@@ -962,8 +970,10 @@ int orbx_features_in_area(orbx_ctx* ctx, const orbx_frame_desc* frame, int nq, c
   int* dout = S.alloc<int>((size_t)nq * cap);
   int* dn = S.alloc<int>(nq);
   if (S.failed) return ORBX_ECUDA;
-  rc = orbx_launch_grid_build(ctx, st, dF, 1);
-  if (rc != ORBX_OK) return rc;
+  if (!F.gridBuilt) {
+    rc = orbx_launch_grid_build(ctx, st, dF, 1);
+    if (rc != ORBX_OK) return rc;
+  }
   if (nq > 0) {
     features_in_area_kernel<<<div_up(nq * 32, 128), 128, 0, st>>>(dF, nq, dx, dy, dr, dmin, dmax, dout, cap, dn);
     ORBX_LAUNCH(ctx);
@@ -1017,8 +1027,10 @@ int orbx_search_by_projection_map(orbx_ctx* ctx, const orbx_frame_desc* frame, c
   if (S.failed) return ORBX_ECUDA;
   ORBX_CUDA(cudaMemsetAsync(misc, 0, 4 * sizeof(int), st));
   ORBX_CUDA(cudaMemsetAsync(A.bestIdx, 0xff, sizeof(int) * (size_t)std::max(nq, 1), st));   // -1: never hand back arena garbage
-  rc = orbx_launch_grid_build(ctx, st, dF, 1);
-  if (rc != ORBX_OK) return rc;
+  if (!F.gridBuilt) {
+    rc = orbx_launch_grid_build(ctx, st, dF, 1);
+    if (rc != ORBX_OK) return rc;
+  }
   A.nqDev = nullptr;
   SbpMapArgs* dA = S.upload(&A, 1);
   if (S.failed) return ORBX_ECUDA;
@@ -1101,8 +1113,10 @@ int orbx_search_by_projection_frame(orbx_ctx* ctx, const orbx_frame_desc* cur, c
   ORBX_CUDA(cudaMemsetAsync(A.curMatch, 0xff, sizeof(int) * (size_t)std::max(cur->n, 1), st));
   if (S.failed) return ORBX_ECUDA;
   ORBX_CUDA(cudaMemsetAsync(misc, 0, 4 * sizeof(int), st));
-  rc = orbx_launch_grid_build(ctx, st, dF, 1);
-  if (rc != ORBX_OK) return rc;
+  if (!F.gridBuilt) {
+    rc = orbx_launch_grid_build(ctx, st, dF, 1);
+    if (rc != ORBX_OK) return rc;
+  }
   A.nqDev = nullptr;
   A.TcDev = nullptr;
   SbpFrameArgs* dA = S.upload(&A, 1);
@@ -1402,5 +1416,81 @@ void orbx_tri_batch_destroy(orbx_tri_batch* T) {
   cudaFree(T->pool);
   delete T;
 }
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Device-resident Frame / KeyFrame.  A Frame crosses the boundary ONCE: keypoints, descriptors and
+// mvuRight are copied to the device and the 64x48 grid (Frame::AssignFeaturesToGrid) is built; every later matcher call
+// that is handed a descriptor over the same host arrays (SearchByProjection x2, SearchForTriangulation, Fuse,
+// GetFeaturesInArea) finds the resident copy and skips its uploads and the grid build.  The caller keeps the host arrays
+// unchanged while the handle lives (the reference's Frame is immutable in these fields after its constructor) and
+// releases the handle when the Frame dies.
+// ------------------------------------------------------------------------------------------------------------------
+orbx_frame* orbx_frame_upload(orbx_ctx* ctx, const orbx_frame_desc* f) {
+  if (!ctx || !f || f->n < 0 || (f->n > 0 && (!f->kps || !f->desc)) || !(f->max_x > f->min_x) || !(f->max_y > f->min_y) || f->n > 65535) {
+    orbx_set_error("orbx_frame_upload: invalid frame descriptor");
+    return nullptr;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+  PoolBuilder B;
+  const size_t n = (size_t)f->n;
+  const size_t oK = B.add(f->kps, sizeof(orbx_keypoint) * n), oD = B.add(f->desc, 32 * n);
+  const size_t oU = f->uright ? B.add(f->uright, sizeof(float) * n) : (size_t)-1;
+  const size_t oCs = B.reserve(sizeof(int) * (ORBX_NCELLS + 1)), oCi = B.reserve(sizeof(int) * n), oF = B.reserve(sizeof(FrameDev));
+  orbx_frame* R = new orbx_frame();
+  R->ctx = ctx;
+  R->keyKps = f->kps; R->keyDesc = f->desc; R->keyUright = f->uright;
+  R->n = f->n;
+  R->bounds[0] = f->min_x; R->bounds[1] = f->min_y; R->bounds[2] = f->max_x; R->bounds[3] = f->max_y;
+  if (cudaMalloc(&R->pool, B.size()) != cudaSuccess) {
+    orbx_set_error("orbx_frame_upload: cudaMalloc(%zu) failed", B.size());
+    cudaGetLastError();
+    delete R;
+    return nullptr;
+  }
+  uint8_t* base = R->pool;
+  FrameDev& F = R->F;
+  memset(&F, 0, sizeof F);
+  F.n = f->n;
+  F.kps = (const orbx_keypoint*)(base + oK);
+  F.desc = base + oD;
+  F.uright = oU == (size_t)-1 ? nullptr : (const float*)(base + oU);
+  F.minX = f->min_x; F.minY = f->min_y; F.maxX = f->max_x; F.maxY = f->max_y;
+  F.wInv = (float)ORBX_GRID_COLS / (f->max_x - f->min_x);
+  F.hInv = (float)ORBX_GRID_ROWS / (f->max_y - f->min_y);
+  F.cellStart = (int*)(base + oCs);
+  F.cellIdx = (int*)(base + oCi);
+  F.gridBuilt = 1;
+  memcpy(B.h.data() + oF, &F, sizeof F);
+  std::lock_guard<std::mutex> lock(ctx->apiMutex);
+  bool ok = cudaMemcpyAsync(base, B.h.data(), B.h.size(), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+  ok = ok && orbx_launch_grid_build(ctx, ctx->stream, (const FrameDev*)(base + oF), 1) == ORBX_OK;
+  ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;   // B.h is a local
+  if (!ok) {
+    orbx_set_error("orbx_frame_upload: upload failed");
+    cudaGetLastError();
+    cudaFree(R->pool);
+    delete R;
+    return nullptr;
+  }
+  ctx->residentFrames.push_back(R);
+  return R;
+}
+
+void orbx_frame_release(orbx_frame* R) {
+  if (!R) return;
+  orbx_ctx* ctx = R->ctx;
+  {
+    std::lock_guard<std::mutex> lock(ctx->apiMutex);
+    auto& v = ctx->residentFrames;
+    v.erase(std::remove(v.begin(), v.end(), R), v.end());
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(R->pool);
+  }
+  delete R;
+}
+
+int orbx_frame_count(const orbx_ctx* ctx) { return ctx ? (int)ctx->residentFrames.size() : ORBX_EINVAL; }
 
 }  // extern "C"

@@ -18,6 +18,17 @@ struct FrameDev {
   float minX, minY, maxX, maxY, wInv, hInv;
   int* cellStart;          // [ORBX_NCELLS + 1]  CSR of the 64x48 grid, cell id = ix * 48 + iy
   int* cellIdx;            // [n] keypoint indices, ascending inside a cell
+  int gridBuilt;           // host-side hint: the grid of this (device-resident) frame is already built
+};
+
+// A Frame / KeyFrame kept on the device between calls (include/orbx.h: orbx_frame_upload).
+struct orbx_frame {
+  orbx_ctx* ctx;
+  const void *keyKps, *keyDesc, *keyUright;   // host arrays of the descriptor it was uploaded from
+  int n;
+  float bounds[4];
+  uint8_t* pool;
+  FrameDev F;              // device view (grid built)
 };
 
 // Temporaries of one host-buffer API call.  Small requests are carved out of the context's staging arena (device

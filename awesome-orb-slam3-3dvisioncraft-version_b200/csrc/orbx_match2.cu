@@ -317,8 +317,10 @@ int orbx_fuse(orbx_ctx* ctx, const orbx_frame_desc* kf, const orbx_camera* cam, 
   A.nfused = S.alloc<int>(1);
   if (S.failed) return ORBX_ECUDA;
   ORBX_CUDA(cudaMemsetAsync(A.nfused, 0, sizeof(int), st));
-  rc = orbx_launch_grid_build(ctx, st, dF, 1);
-  if (rc != ORBX_OK) return rc;
+  if (!F.gridBuilt) {
+    rc = orbx_launch_grid_build(ctx, st, dF, 1);
+    if (rc != ORBX_OK) return rc;
+  }
   fuse_kernel<<<div_up(nmp * 32, 128), 128, 0, st>>>(dF, A);
   ORBX_LAUNCH(ctx);
   ORBX_CUDA(cudaGetLastError());

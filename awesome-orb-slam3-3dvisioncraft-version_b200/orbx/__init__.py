@@ -8,4 +8,4 @@ library or without a CUDA device raises.
 from .api import (Context, host_array, ORBextractor, KP_DTYPE, OrbxError, lib_path, load_library,
                   build_library, declared_symbols, ORBmatcher, Optimizer, Tracker, features_in_area, stereo_match, Frame,
                   Camera, make_camera, ORBVocabulary, search_by_bow, fuse, prepare_images, is_in_frustum, undistort_keypoints,
-                  TriangulationBatch, LocalBABatch)  # noqa: F401
+                  TriangulationBatch, LocalBABatch, ResidentFrame)  # noqa: F401

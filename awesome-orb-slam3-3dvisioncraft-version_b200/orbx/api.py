@@ -86,6 +86,10 @@ def load_library():
     L.orbx_pose_optimization.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_pose_optimization_batch_device.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbx_local_ba.argtypes = [vp, i, vp, vp, i, vp, i, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp, vp]
+    L.orbx_frame_upload.restype = vp
+    L.orbx_frame_upload.argtypes = [vp, vp]
+    L.orbx_frame_release.argtypes = [vp]
+    L.orbx_frame_count.argtypes = [vp]
     L.orbx_tri_batch_prepare.restype = vp
     L.orbx_tri_batch_prepare.argtypes = [vp, i, vp, vp, vp, i, i]
     L.orbx_tri_batch_run.argtypes = [vp, vp]
@@ -416,6 +420,24 @@ def stereo_match(ctx, extL, bL, extR, bR, kpL, descL, kpR, descR, bf, b):
                                             _p(descR), len(kpR), float(bf), float(b), _p(ur), _p(dp)),
            "orbx_stereo_match")
     return ur, dp
+
+
+class ResidentFrame:
+    """A Frame / KeyFrame kept on the device between calls (orbx_frame_upload): keypoints, descriptors, mvuRight and the
+    64x48 grid cross the boundary once; later matcher calls that receive the same `Frame` object use the resident copy."""
+
+    def __init__(self, ctx, frame):
+        self.ctx, self.frame = ctx, frame            # keeps the host arrays (the lookup key) alive
+        self.h = load_library().orbx_frame_upload(ctx.h, frame.ref())
+        if not self.h:
+            raise OrbxError("orbx_frame_upload: " + load_library().orbx_last_error().decode(errors="replace"))
+
+    def release(self):
+        if getattr(self, "h", None):
+            load_library().orbx_frame_release(self.h)
+            self.h = None
+
+    __del__ = release
 
 
 class TriangulationBatch:

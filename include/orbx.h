@@ -161,6 +161,17 @@ typedef struct orbx_camera {
   float bf, b;          /* Frame::mbf, Frame::mb = mbf/fx (src/Frame.cc:166) */
 } orbx_camera;
 
+/* Device-resident Frame / KeyFrame (Frame::Frame + AssignFeaturesToGrid, src/Frame.cc:90-170,444-478).
+ * orbx_frame_upload copies the descriptor's arrays to the device ONCE and builds the 64x48 grid there; afterwards every
+ * entry point below that is handed a descriptor over the SAME host arrays (same kps / desc / uright pointers, n and
+ * bounds) uses the resident copy: no per-call upload of the frame, no per-call grid build.  The host arrays must stay
+ * unchanged while the handle lives (the reference's Frame does not change these members after its constructor and
+ * ComputeStereoMatches); release the handle when the Frame dies.  Signatures of the matcher calls are unchanged. */
+typedef struct orbx_frame orbx_frame;
+orbx_frame *orbx_frame_upload(orbx_ctx *ctx, const orbx_frame_desc *frame);
+void orbx_frame_release(orbx_frame *frame);
+int orbx_frame_count(const orbx_ctx *ctx);
+
 /* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2700-2716): Hamming distance of two
  * 256-bit descriptors.  A static CPU helper in the reference (also called from Frame.cc,
  * MapPoint.cc, LoopClosing.cc); provided here for the shim, computed on the host. */

@@ -167,3 +167,42 @@ def test_projection_searches_on_a_frame_above_48k_keypoints(ctx, ork):
     rn, rbest = ork.search_by_projection_map(*args, 0.8, s["scaleFactors"])
     gn, gbest = orbx.ORBmatcher(ctx, 0.8).SearchByProjectionMap(*args, s["scaleFactors"])
     assert rn > 20 and gn == rn and np.array_equal(gbest, rbest)
+
+
+def test_resident_frame_gives_identical_results_without_reuploading(ctx, ork, stereo_frames):
+    """orbx_frame_upload: a Frame made device-resident once is found by every later matcher call over the same host
+    arrays (no signature change); results are identical to the per-call upload path, before and after release."""
+    import orbx
+    cam = orbx.make_camera()
+    f = stereo_frames[0]
+    F = orbx.Frame(f["kL"], f["dL"], f["ur"])
+    s1 = sc.sbp_map_scenario(10, f["kL"], f["dL"], f["ur"])
+    s2 = sc.sbp_frame_scenario(20, f["kL"], f["dL"], f["ur"], f["dp"])
+    m = orbx.ORBmatcher(ctx, 0.8)
+
+    def run():
+        a = m.SearchByProjectionMap(F, s1["kp_blocked"], s1["projX"], s1["projY"], s1["projXR"], s1["level"], s1["viewCos"], s1["mpDesc"],
+                                    s1["flags"], 3.0, s1["scaleFactors"])
+        b = orbx.ORBmatcher(ctx, 0.9, True).SearchByProjectionFrame(F, s2["cur_blocked"], cam, s2["Tcw_cur"], s2["Tcw_last"], s2["flags"],
+                                                                     s2["xw"], s2["octave"], s2["angle"], s2["mpDesc"], 7.0, False,
+                                                                     s2["scaleFactors"])
+        x = np.array([100.0, 400.0, 700.0], np.float32)
+        c = orbx.features_in_area(ctx, F, x, x * 0.5, np.full(3, 30.0, np.float32), np.zeros(3, np.int32), np.full(3, 7, np.int32))
+        return a, b, c
+
+    before = run()
+    n0 = orbx.load_library().orbx_frame_count(ctx.h)
+    R = orbx.ResidentFrame(ctx, F)
+    assert orbx.load_library().orbx_frame_count(ctx.h) == n0 + 1
+    launches0 = ctx.launches
+    during = run()
+    used = ctx.launches - launches0
+    R.release()
+    assert orbx.load_library().orbx_frame_count(ctx.h) == n0
+    launches0 = ctx.launches
+    after = run()
+    assert used == (ctx.launches - launches0) - 3          # three grid builds saved
+    for x, y in ((before, during), (before, after)):
+        assert x[0][0] == y[0][0] and np.array_equal(x[0][1], y[0][1])
+        assert x[1][0] == y[1][0] and all(np.array_equal(p, q) for p, q in zip(x[1][1:], y[1][1:]))
+        assert np.array_equal(x[2][0], y[2][0]) and np.array_equal(x[2][1], y[2][1])

@@ -79,6 +79,31 @@ def main():
     add("ORBmatcher::SearchByProjection(Cur, Last, th=7)", "src/ORBmatcher.cc:2244",
         lambda: m9.SearchByProjectionFrame(*a2, f["scaleFactors"]),
         lambda: oracle.search_by_projection_frame(*a2, True, f["scaleFactors"]))
+    # the same two searches on a device-resident Frame (orbx_frame_upload once per Frame: no per-call frame upload, no grid build)
+    RF = orbx.ResidentFrame(ctx, F)
+    add("  ... SearchByProjection(F, MapPoints) on a resident Frame", "orbx_frame_upload", lambda: m.SearchByProjectionMap(*a, s["scaleFactors"]),
+        lambda: oracle.search_by_projection_map(*a, 0.8, s["scaleFactors"]))
+    add("  ... SearchByProjection(Cur, Last) on a resident Frame", "orbx_frame_upload", lambda: m9.SearchByProjectionFrame(*a2, f["scaleFactors"]),
+        lambda: oracle.search_by_projection_frame(*a2, True, f["scaleFactors"]))
+    RF.release()
+    # one stereo frame through the whole per-frame chain in ONE call (S = 1 tracker, 8(d) map uploaded with the call)
+    from replay_reference import track_frame_map
+    ex1 = orbx.ORBextractor(ctx, max_batch=2)
+    trk1 = orbx.Tracker(ctx, ex1, 1, cam)
+    Tt1 = np.eye(4, dtype=np.float32)[None]
+    Tp1 = Tt1.copy()
+    Tp1[0, :3, 3] = (0.01, -0.01, 0.005)
+    mp1 = sc.track_map_scenario(5, kL, dL, ur, dp, Tt1[0])
+    host1 = sc.stack_track_maps([mp1])
+    oex = (oracle.Extractor(), oracle.Extractor())
+
+    def chain_gpu():
+        trk1.upload_map(host1)
+        return trk1.step([L, R], Tt1, Tp1)
+    add("whole per-frame chain of ONE stereo frame (extract L+R .. PoseOptimization #2), 1500-point map",
+        "src/Tracking.cc:1793-2480", chain_gpu, lambda: track_frame_map(oracle, cam, L, R, mp1, Tp1[0], extractors=oex), 30, 5)
+    trk1.close()
+    ex1.close()
     q = sc.tri_scenario(3, kL, dL, ur)
     K1, K2 = orbx.Frame(q["k1"], q["d1"], q["ur1"]), orbx.Frame(q["k2"], q["d2"], q["ur2"])
     a3 = (K1, K2, q["has1"], q["has2"], q["fv1"], q["fv2"], cam, cam, q["R1w"], q["t1w"], q["R2w"], q["t2w"], q["sigma2"], q["scaleFactors"])
