@@ -33,6 +33,7 @@ int orbx_launch_pose_opt_slices(orbx_ctx* ctx, cudaStream_t st, int P, const int
 
 struct TrackDev {
   int S, cap;
+  int ips;                    // images per stream: 2 = stereo (left, right), 1 = monocular
   int mcap;                   // stride of the map-indexed arrays (== cap in self-map mode)
   int useMap;                 // 1: map given by the caller (orbx_tracker_set_map)
   const int* nMap;            // [S] map points per stream (given map) or null
@@ -74,10 +75,10 @@ __global__ void __launch_bounds__(128) backproject_kernel(const TrackDev D) {
   const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= D.cap) return;
   const size_t o = (size_t)s * D.mcap + i;           // map-indexed arrays (keypoint i is map point i in this mode)
-  const int n = D.n[2 * s];
+  const int n = D.n[D.ips * s];
   uint8_t fl = 0, lfl = 0;
   if (i < n) {
-    const orbx_keypoint kp = D.kps[(size_t)(2 * s) * D.cap + i];
+    const orbx_keypoint kp = D.kps[(size_t)(D.ips * s) * D.cap + i];
     const float z = D.depth[(size_t)s * D.cap + i];
     D.octave[o] = kp.octave;
     D.angle[o] = kp.angle;
@@ -97,11 +98,20 @@ __global__ void __launch_bounds__(128) backproject_kernel(const TrackDev D) {
   D.lastFlags[o] = lfl;
 }
 
+// K-glue 1b (monocular): no ComputeStereoMatches -- mvuRight = mvDepth = -1 for every keypoint (src/Frame.cc:330-331)
+__global__ void __launch_bounds__(128) mono_fill_kernel(const TrackDev D) {
+  const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.cap) return;
+  const size_t o = (size_t)s * D.cap + i;
+  D.uright[o] = -1.0f;
+  D.depth[o] = -1.0f;
+}
+
 // K-glue 2: PoseOptimization's edge list: keypoints i (ascending) that hold a MapPoint (src/Optimizer.cc:961-1130)
 // mode 0: MapPoint of keypoint i = curMatch[i]; mode 1: kpMp[i]
 __global__ void __launch_bounds__(256) gather_edges_kernel(const TrackDev D, int mode) {
   const int s = blockIdx.x, tid = threadIdx.x;
-  const int n = D.n[2 * s];
+  const int n = D.n[D.ips * s];
   const size_t base = (size_t)s * D.cap, mb = (size_t)s * D.mcap;
   const int* src = (mode == 0 ? D.curMatch : D.kpMp) + base;
   __shared__ int s_warp[9];
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(256) gather_edges_kernel(const TrackDev D, int
     const int slot = before + __popc(m & ((1u << lane) - 1));
     if (i < n) D.kpEdge[base + i] = has ? slot : -1;
     if (has) {
-      const orbx_keypoint kp = D.kps[(size_t)(2 * s) * D.cap + i];
+      const orbx_keypoint kp = D.kps[(size_t)(D.ips * s) * D.cap + i];
       const size_t e = base + slot;
       D.exw[3 * e] = D.xw[3 * (mb + q)];
       D.exw[3 * e + 1] = D.xw[3 * (mb + q) + 1];
@@ -145,7 +155,7 @@ __global__ void __launch_bounds__(128) after_pose1_kernel(const TrackDev D) {
   const int s = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= D.cap) return;
   const size_t o = (size_t)s * D.cap + i;
-  if (i >= D.n[2 * s]) { D.blocked[o] = 0; return; }
+  if (i >= D.n[D.ips * s]) { D.blocked[o] = 0; return; }
   const int q = D.curMatch[o];
   uint8_t blk = 0;
   if (q >= 0) {
@@ -162,7 +172,7 @@ __global__ void __launch_bounds__(128) project_map_kernel(const TrackDev D, floa
   if (q >= D.cap) return;
   const size_t o = (size_t)s * D.mcap + q;
   uint8_t fl = 0;
-  if (q < D.n[2 * s] && (D.mpFlags[o] & 1) && !D.mpTaken[o]) {
+  if (q < D.n[D.ips * s] && (D.mpFlags[o] & 1) && !D.mpTaken[o]) {
     const float* T = D.T1 + 16 * s;
     const float X = D.xw[3 * o], Y = D.xw[3 * o + 1], Z = D.xw[3 * o + 2];
     const float xc = T[0] * X + T[1] * Y + T[2] * Z + T[3];
@@ -245,7 +255,7 @@ __global__ void chain_prior_kernel(const float* dT, const float* Tlast, float* p
 // K-glue 5: MapPoint of each keypoint after the local-map search, then per-stream stats
 __global__ void __launch_bounds__(256) merge_matches_kernel(const TrackDev D) {
   const int s = blockIdx.x, tid = threadIdx.x;
-  const int n = D.n[2 * s];
+  const int n = D.n[D.ips * s];
   const size_t base = (size_t)s * D.cap, mb = (size_t)s * D.mcap;
   for (int i = tid; i < n; i += 256) D.kpMp[base + i] = D.curMatch[base + i];
   __syncthreads();
@@ -260,7 +270,7 @@ __global__ void __launch_bounds__(256) merge_matches_kernel(const TrackDev D) {
 
 __global__ void __launch_bounds__(256) stats_kernel(const TrackDev D) {
   const int s = blockIdx.x, tid = threadIdx.x;
-  const int n = D.n[2 * s];
+  const int n = D.n[D.ips * s];
   const size_t base = (size_t)s * D.cap;
   __shared__ int s_st;
   if (tid == 0) s_st = 0;
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(256) stats_kernel(const TrackDev D) {
   if (tid == 0) {
     int* st = D.stats + ORBX_TRACK_STATS * s;
     st[0] = n;
-    st[1] = D.n[2 * s + 1];
+    st[1] = (D.ips == 2 ? D.n[2 * s + 1] : 0);
     st[2] = s_st;
     st[3] = D.nm1[s];
     st[4] = D.ninl[s];
@@ -317,6 +327,7 @@ struct orbx_tracker {
   cudaStream_t stA = nullptr, stB = nullptr;   // stB == stA unless overlap mode is on
   cudaStream_t ownB = nullptr;
   int S = 0, cap = 0, nlevels = 0;
+  int ips = 2;                 // images per stream (1: monocular tracker)
   orbx_camera cam{};
   float thFrame = 7.f, thMap = 1.f, nnMap = 0.8f;
   TrackSlot slot[2];
@@ -376,6 +387,7 @@ static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float th
   TrackDev& D = K.D;
   D.S = S;
   D.cap = cap;
+  D.ips = t->ips;
   D.mcap = mcap;
   D.useMap = 0;
   D.nMap = nullptr;
@@ -427,15 +439,15 @@ static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float th
   for (int s = 0; s < S; ++s) {
     const size_t o = (size_t)s * cap, m = (size_t)s * mcap;
     F[s].n = 0;
-    F[s].nDev = K.d_n + 2 * s;
-    F[s].kps = K.d_kps + (size_t)(2 * s) * cap;
-    F[s].desc = K.d_desc + (size_t)(2 * s) * cap * 32;
+    F[s].nDev = K.d_n + t->ips * s;
+    F[s].kps = K.d_kps + (size_t)(t->ips * s) * cap;
+    F[s].desc = K.d_desc + (size_t)(t->ips * s) * cap * 32;
     F[s].uright = D.uright + o;
     F[s].cellStart = cellStart + (size_t)s * (ORBX_NCELLS + 1);
     F[s].cellIdx = cellIdx + o;
     F[s].minX = F[s].minY = 0; F[s].maxX = F[s].maxY = 1; F[s].wInv = F[s].hInv = 1;   // set per image size
     SbpFrameArgs& a = AF[s];
-    a.nq = 0; a.nqDev = K.d_n + 2 * s; a.TcDev = D.Tprior + 16 * s;
+    a.nq = 0; a.nqDev = K.d_n + t->ips * s; a.TcDev = D.Tprior + 16 * s;
     a.flags = D.lastFlags + m; a.xw = D.xwOwn + 3 * m; a.octave = D.octave + m; a.angle = D.angle + m;
     a.mpDesc = F[s].desc;
     a.fx = cam->fx; a.fy = cam->fy; a.cx = cam->cx; a.cy = cam->cy; a.bf = cam->bf;
@@ -444,7 +456,7 @@ static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float th
     a.total = K.d_misc + 8 * s; a.err = K.d_misc + 8 * s + 1;
     a.curBlocked = nullptr; a.matchIdx = D.matchIdx + m; a.kept = D.kept + m; a.curMatch = D.curMatch + o; a.nmatches = D.nm1 + s;
     SbpMapArgs& g = AM[s];
-    g.nq = 0; g.nqDev = K.d_n + 2 * s;
+    g.nq = 0; g.nqDev = K.d_n + t->ips * s;
     g.projX = D.projX + m; g.projY = D.projY + m; g.projXR = D.projXR + m; g.viewCos = D.viewCos + m; g.level = D.level + m;
     g.mpDesc = F[s].desc; g.flags = D.mapFlags + m; g.th = thMap; g.nnratio = nnMap; g.scaleFactors = t->d_scale;
     g.candOfs = candOfs + m; g.candCnt = candCnt + m; g.cand = cand + (size_t)s * candCap; g.candCap = candCap;
@@ -498,14 +510,15 @@ void orbx_tracker_destroy(orbx_tracker* t) {
   delete t;
 }
 
-orbx_tracker* orbx_tracker_create(orbx_ctx* ctx, orbx_ext* ext, int S, const orbx_camera* cam, float th_frame, float th_map,
-                                  float nnratio_map) {
-  if (!ctx || !ext || S < 1 || !cam || !(cam->b > 0)) {
+static orbx_tracker* tracker_create(orbx_ctx* ctx, orbx_ext* ext, int S, const orbx_camera* cam, float th_frame, float th_map,
+                                    float nnratio_map, int ips) {
+  if (!ctx || !ext || S < 1 || !cam || (ips == 2 && !(cam->b > 0))) {
     orbx_set_error("orbx_tracker_create: invalid argument");
     return nullptr;
   }
   if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
   orbx_tracker* t = new orbx_tracker();
+  t->ips = ips;
   t->ctx = ctx;
   t->ext = ext;
   t->stA = t->stB = (cudaStream_t)orbx_extractor_stream(ext);
@@ -530,6 +543,20 @@ orbx_tracker* orbx_tracker_create(orbx_ctx* ctx, orbx_ext* ext, int S, const orb
   }
   return t;
 }
+
+orbx_tracker* orbx_tracker_create(orbx_ctx* ctx, orbx_ext* ext, int S, const orbx_camera* cam, float th_frame, float th_map,
+                                  float nnratio_map) {
+  return tracker_create(ctx, ext, S, cam, th_frame, th_map, nnratio_map, 2);
+}
+
+// Monocular tracker (BASELINE config 1; Frame::Frame(mono) src/Frame.cc:308-349, Tracking::TrackWithMotionModel with bMono,
+// th = 15, src/Tracking.cc:2364-2378; monocular edges of PoseOptimization src/Optimizer.cc:961-1010): ONE image per stream,
+// no ComputeStereoMatches (mvuRight = mvDepth = -1), the map must be given (orbx_tracker_set_map / _upload_map).
+orbx_tracker* orbx_tracker_create_mono(orbx_ctx* ctx, orbx_ext* ext, int S, const orbx_camera* cam, float th_frame, float th_map,
+                                       float nnratio_map) {
+  return tracker_create(ctx, ext, S, cam, th_frame, th_map, nnratio_map, 1);
+}
+int orbx_tracker_images_per_stream(const orbx_tracker* t) { return t ? t->ips : ORBX_EINVAL; }
 
 int orbx_tracker_set_overlap(orbx_tracker* t, int enable) {
   if (!t) return ORBX_EINVAL;
@@ -699,6 +726,10 @@ static int tracker_bind_geometry(orbx_tracker* t, int w, int h) {
     std::vector<FrameDev> F(S);
     ORBX_CUDA(cudaMemcpy(F.data(), K.d_frames, sizeof(FrameDev) * S, cudaMemcpyDeviceToHost));
     for (int s = 0; s < S; ++s) {
+      F[s].minX = 0.f; F[s].minY = 0.f; F[s].maxX = (float)w; F[s].maxY = (float)h;   // undistorted image bounds (src/Frame.cc:147-152)
+      F[s].wInv = (float)ORBX_GRID_COLS / (F[s].maxX - F[s].minX);
+      F[s].hInv = (float)ORBX_GRID_ROWS / (F[s].maxY - F[s].minY);
+      if (t->ips != 2) continue;
       StereoArgs& a = A[s];
       int nl = 0, nl2 = 0, w2[ORBX_MAX_LEVELS], h2[ORBX_MAX_LEVELS];
       float sc2[ORBX_MAX_LEVELS], isc2[ORBX_MAX_LEVELS];
@@ -761,8 +792,8 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
       const size_t m = (size_t)s * t->mcap;
       SbpFrameArgs& a = K.hF[s];
       SbpMapArgs& g = K.hM[s];
-      const uint8_t* ownDesc = K.d_desc + (size_t)(2 * s) * cap * 32;
-      a.nqDev = gm ? M.n_map + s : K.d_n + 2 * s;
+      const uint8_t* ownDesc = K.d_desc + (size_t)(t->ips * s) * cap * 32;
+      a.nqDev = gm ? M.n_map + s : K.d_n + t->ips * s;
       a.flags = gm ? M.last_flags + m : D.lastFlags + m;
       a.xw = D.xw + 3 * m;
       a.octave = gm ? M.last_octave + m : D.octave + m;
@@ -777,7 +808,11 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
   }
   TRK_EV(0, sa);
   // 1. Frame::Frame(stereo): ORB extraction of the 2*S images (src/Frame.cc:111-114)
-  int rc = orbx_extract_batch_device(t->ext, 2 * S, d_imgs, w, h, stride, 0, 0, K.d_kps, K.d_desc, cap, K.d_n, K.d_mono);
+  if (t->ips == 1 && !t->haveMap) {
+    orbx_set_error("orbx_tracker: the monocular tracker has no self-map harness (no depth): set a map first");
+    return ORBX_EINVAL;
+  }
+  int rc = orbx_extract_batch_device(t->ext, t->ips * S, d_imgs, w, h, stride, 0, 0, K.d_kps, K.d_desc, cap, K.d_n, K.d_mono);
   if (rc != ORBX_OK) return rc;
   if (w != t->argW || h != t->argH || stride != t->argStride || d_imgs != t->argImgs) {   // level 0 aliases the input
     rc = tracker_bind_geometry(t, w, h);
@@ -796,8 +831,13 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
   ORBX_CUDA(cudaMemsetAsync(K.d_misc, 0, sizeof(int) * 8 * S, sa));
   ORBX_CUDA(cudaMemsetAsync(D.mpTaken, 0, (size_t)S * t->mcap, sa));
   // 2. ComputeStereoMatches (src/Frame.cc:132)
-  rc = orbx_launch_stereo_batch(t->ctx, sa, K.d_stereo, S, cap);
-  if (rc != ORBX_OK) return rc;
+  if (t->ips == 2) {
+    rc = orbx_launch_stereo_batch(t->ctx, sa, K.d_stereo, S, cap);
+    if (rc != ORBX_OK) return rc;
+  } else {
+    mono_fill_kernel<<<dim3(div_up(cap, 128), S), 128, 0, sa>>>(D);
+    ORBX_LAUNCH(t->ctx);
+  }
   if (overlap) {
     ORBX_CUDA(cudaEventRecord(K.evA, sa));
     ORBX_CUDA(cudaStreamWaitEvent(sb, K.evA, 0));
@@ -875,10 +915,10 @@ int orbx_tracker_step(orbx_tracker* t, const uint8_t* const* imgs, int w, int h,
   const int S = t->S;
   const size_t img = (size_t)w * h;
   if (!t->h_imgs) {
-    ORBX_CUDA(cudaMallocHost(&t->h_imgs, 2 * S * img));
+    ORBX_CUDA(cudaMallocHost(&t->h_imgs, (size_t)t->ips * S * img));
     ORBX_CUDA(cudaMallocHost(&t->h_pose, sizeof(float) * 16 * S * 3));
     ORBX_CUDA(cudaMallocHost(&t->h_stats, sizeof(int) * ORBX_TRACK_STATS * S));
-    t->d_imgs = talloc<uint8_t>(t, 2 * S * img);
+    t->d_imgs = talloc<uint8_t>(t, (size_t)t->ips * S * img);
     t->d_hposeIn = talloc<float>(t, 32 * S);
     t->d_hposeOut = talloc<float>(t, 16 * S);
     t->d_hstats = talloc<int>(t, ORBX_TRACK_STATS * S);
@@ -888,21 +928,21 @@ int orbx_tracker_step(orbx_tracker* t, const uint8_t* const* imgs, int w, int h,
   // page-locked caller memory is DMA'd directly (one copy when the images are also contiguous); anything else is
   // staged through the tracker's own pinned buffer first
   bool pinned = true, contiguous = stride == w;
-  for (int b = 0; b < 2 * S && pinned; ++b) {
+  for (int b = 0; b < t->ips * S && pinned; ++b) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, imgs[b]) != cudaSuccess || at.type != cudaMemoryTypeHost) pinned = false;
     if (b > 0 && imgs[b] != imgs[b - 1] + img) contiguous = false;
   }
   cudaGetLastError();   // a failed attribute query on pageable memory leaves a sticky-free error behind
   if (pinned && contiguous) {
-    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, imgs[0], 2 * S * img, cudaMemcpyHostToDevice, sa));
+    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, imgs[0], (size_t)t->ips * S * img, cudaMemcpyHostToDevice, sa));
   } else if (pinned) {
-    for (int b = 0; b < 2 * S; ++b)
+    for (int b = 0; b < t->ips * S; ++b)
       ORBX_CUDA(cudaMemcpy2DAsync(t->d_imgs + b * img, w, imgs[b], stride, w, h, cudaMemcpyHostToDevice, sa));
   } else {
-    for (int b = 0; b < 2 * S; ++b)
+    for (int b = 0; b < t->ips * S; ++b)
       for (int y = 0; y < h; ++y) memcpy(t->h_imgs + b * img + (size_t)y * w, imgs[b] + (size_t)y * stride, w);
-    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, t->h_imgs, 2 * S * img, cudaMemcpyHostToDevice, sa));
+    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, t->h_imgs, (size_t)t->ips * S * img, cudaMemcpyHostToDevice, sa));
   }
   memcpy(t->h_pose, Tcw_true, sizeof(float) * 16 * S);
   memcpy(t->h_pose + 16 * S, Tcw_prior, sizeof(float) * 16 * S);
@@ -953,10 +993,10 @@ int orbx_tracker_submit(orbx_tracker* t, const uint8_t* const* imgs, int w, int 
     }
   }
   if (!t->h_imgs) {
-    ORBX_CUDA(cudaMallocHost(&t->h_imgs, 2 * S * img));
+    ORBX_CUDA(cudaMallocHost(&t->h_imgs, (size_t)t->ips * S * img));
     ORBX_CUDA(cudaMallocHost(&t->h_pose, sizeof(float) * 16 * S * 3));
     ORBX_CUDA(cudaMallocHost(&t->h_stats, sizeof(int) * ORBX_TRACK_STATS * S));
-    t->d_imgs = talloc<uint8_t>(t, 2 * S * img);
+    t->d_imgs = talloc<uint8_t>(t, (size_t)t->ips * S * img);
     t->d_hposeIn = talloc<float>(t, 32 * S);
     t->d_hposeOut = talloc<float>(t, 16 * S);
     t->d_hstats = talloc<int>(t, ORBX_TRACK_STATS * S);
@@ -964,8 +1004,8 @@ int orbx_tracker_submit(orbx_tracker* t, const uint8_t* const* imgs, int w, int 
   }
   size_t l0bytes = 0;
   uint8_t* level0 = orbx_ext_level0_storage(t->ext, &l0bytes);
-  if (!level0 || l0bytes < 2 * S * img) {
-    orbx_set_error("orbx_tracker_submit: extractor level-0 storage too small for %d images of %dx%d", 2 * S, w, h);
+  if (!level0 || l0bytes < (size_t)t->ips * S * img) {
+    orbx_set_error("orbx_tracker_submit: extractor level-0 storage too small for %d images of %dx%d", t->ips * S, w, h);
     return ORBX_ECAP;
   }
   const int k = (int)(t->stepCount & 1);            // the slot orbx_tracker_step_device is about to use
@@ -973,22 +1013,22 @@ int orbx_tracker_submit(orbx_tracker* t, const uint8_t* const* imgs, int w, int 
   // ---- copy stream: inputs of this step ----
   if (t->stagedUsed) ORBX_CUDA(cudaStreamWaitEvent(sc, t->evStaged, 0));   // staging buffer consumed by the previous step
   bool pinned = true, contiguous = stride == w;
-  for (int b = 0; b < 2 * S && pinned; ++b) {
+  for (int b = 0; b < t->ips * S && pinned; ++b) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, imgs[b]) != cudaSuccess || at.type != cudaMemoryTypeHost) pinned = false;
     if (b > 0 && imgs[b] != imgs[b - 1] + img) contiguous = false;
   }
   cudaGetLastError();
   if (pinned && contiguous) {
-    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, imgs[0], 2 * S * img, cudaMemcpyHostToDevice, sc));
+    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, imgs[0], (size_t)t->ips * S * img, cudaMemcpyHostToDevice, sc));
   } else if (pinned) {
-    for (int b = 0; b < 2 * S; ++b)
+    for (int b = 0; b < t->ips * S; ++b)
       ORBX_CUDA(cudaMemcpy2DAsync(t->d_imgs + b * img, w, imgs[b], stride, w, h, cudaMemcpyHostToDevice, sc));
   } else {
     if (t->submitted) ORBX_CUDA(cudaEventSynchronize(t->evH2D));          // the pinned bounce buffer is free again
-    for (int b = 0; b < 2 * S; ++b)
+    for (int b = 0; b < t->ips * S; ++b)
       for (int y = 0; y < h; ++y) memcpy(t->h_imgs + b * img + (size_t)y * w, imgs[b] + (size_t)y * stride, w);
-    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, t->h_imgs, 2 * S * img, cudaMemcpyHostToDevice, sc));
+    ORBX_CUDA(cudaMemcpyAsync(t->d_imgs, t->h_imgs, (size_t)t->ips * S * img, cudaMemcpyHostToDevice, sc));
   }
   memcpy(t->h_aPoseIn[k], Tcw_true, sizeof(float) * 16 * S);
   memcpy(t->h_aPoseIn[k] + 16 * S, Tcw_prior, sizeof(float) * 16 * S);
@@ -996,7 +1036,7 @@ int orbx_tracker_submit(orbx_tracker* t, const uint8_t* const* imgs, int w, int 
   ORBX_CUDA(cudaEventRecord(t->evH2D, sc));
   // ---- stage A stream: staging -> level 0, then the step ----
   ORBX_CUDA(cudaStreamWaitEvent(sa, t->evH2D, 0));
-  ORBX_CUDA(cudaMemcpyAsync(level0, t->d_imgs, 2 * S * img, cudaMemcpyDeviceToDevice, sa));
+  ORBX_CUDA(cudaMemcpyAsync(level0, t->d_imgs, (size_t)t->ips * S * img, cudaMemcpyDeviceToDevice, sa));
   ORBX_CUDA(cudaEventRecord(t->evStaged, sa));
   t->stagedUsed = true;
   int rc = orbx_tracker_step_device(t, level0, w, h, w, t->d_aPoseIn[k], t->d_aPoseIn[k] + 16 * S, t->d_aPoseOut[k], t->d_aStats[k]);

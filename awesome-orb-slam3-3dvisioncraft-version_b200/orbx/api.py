@@ -108,6 +108,9 @@ def load_library():
     L.orbx_pose_inertial_optimization_last_keyframe_batch.argtypes = [vp, i] + [vp] * 15 + [i] + [vp] * 4
     L.orbx_tracker_create.restype = vp
     L.orbx_tracker_create.argtypes = [vp, vp, i, vp, f, f, f]
+    L.orbx_tracker_create_mono.restype = vp
+    L.orbx_tracker_create_mono.argtypes = [vp, vp, i, vp, f, f, f]
+    L.orbx_tracker_images_per_stream.argtypes = [vp]
     L.orbx_tracker_destroy.argtypes = [vp]
     L.orbx_tracker_step_device.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
     L.orbx_tracker_step.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
@@ -704,9 +707,15 @@ class Tracker:
     STAGES = ("extract", "stereo_match", "search_last_frame", "pose_opt_1", "search_local_map", "pose_opt_2")
     STATS = ("nL", "nR", "nStereo", "matches_frame", "inliers_1", "matches_map", "inliers_2", "lm_iters")
 
-    def __init__(self, ctx, ext, S, cam, th_frame=7.0, th_map=1.0, nnratio_map=0.8):
+    def __init__(self, ctx, ext, S, cam, th_frame=None, th_map=1.0, nnratio_map=0.8, mono=False):
+        """mono=True: one image per stream, no stereo matching, th_frame defaults to 15 (src/Tracking.cc:2364-2368) and
+        the map must be given (set_map / upload_map) before the first step."""
         self.ctx, self.ext, self.S, self.cam = ctx, ext, S, cam
-        self.h = load_library().orbx_tracker_create(ctx.h, ext.h, S, C.byref(cam), th_frame, th_map, nnratio_map)
+        self.ips = 1 if mono else 2
+        if th_frame is None:
+            th_frame = 15.0 if mono else 7.0
+        create = load_library().orbx_tracker_create_mono if mono else load_library().orbx_tracker_create
+        self.h = create(ctx.h, ext.h, S, C.byref(cam), th_frame, th_map, nnratio_map)
         if not self.h:
             raise OrbxError("orbx_tracker_create: " + load_library().orbx_last_error().decode(errors="replace"))
 
@@ -722,9 +731,10 @@ class Tracker:
             pass
 
     def step(self, images, Tcw_true, Tcw_prior):
-        """images: [L0, R0, L1, R1, ...] equally sized uint8 arrays (host) -> (Tcw_out[S,4,4], stats[S,8])"""
+        """images: [L0, R0, L1, R1, ...] (monocular tracker: [I0, I1, ...]) equally sized uint8 arrays (host)
+        -> (Tcw_out[S,4,4], stats[S,8])"""
         imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
-        assert len(imgs) == 2 * self.S
+        assert len(imgs) == self.ips * self.S
         h, w = imgs[0].shape
         ptrs = (C.c_void_p * len(imgs))(*[im.ctypes.data for im in imgs])
         Tt = np.ascontiguousarray(Tcw_true, np.float32).reshape(self.S, 16)
@@ -739,7 +749,7 @@ class Tracker:
         """Asynchronous step(): enqueue only (orbx_tracker_submit).  `images` must stay alive until collect()."""
         if not isinstance(images, _PreparedImages):
             images = _PreparedImages(images)
-        assert images.n == 2 * self.S
+        assert images.n == self.ips * self.S
         Tt = np.ascontiguousarray(Tcw_true, np.float32).reshape(self.S, 16)
         Tp = np.ascontiguousarray(Tcw_prior, np.float32).reshape(self.S, 16)
         _check(load_library().orbx_tracker_submit(self.h, images.ptrs, images.w, images.h, images.w, _p(Tt), _p(Tp)),

@@ -36,10 +36,15 @@ import numpy as np  # noqa: E402
 W, H, NFEAT, NLEVELS = 752, 480, 1000, 8
 METRIC = "tracking frames/sec (extract+match+poseopt) EuRoC 752x480"
 UNIT = "stereo frames/s"
+MONO = False
+CHAIN_MONO = ("ORB extraction (one image), SearchByProjection(last frame, th 15), PoseOptimization (monocular edges), "
+              "isInFrustum + SearchByProjection(local map), PoseOptimization")
 CHAIN = ("ORB extraction L+R, ComputeStereoMatches, SearchByProjection(last frame), PoseOptimization, "
          "isInFrustum + SearchByProjection(local map), PoseOptimization")
 # BASELINE.json configs[1] (the configuration the metric is quoted on) and configs[3]
 CONFIGS = {
+    "c1": dict(w=752, h=480, nfeat=1000, streams=512, n_map=1500, mono=True,
+               name="EuRoC MH01-shaped monocular 752x480, 1000 feat, 8 levels (BASELINE config 1)"),
     "c2": dict(w=752, h=480, nfeat=1000, streams=256, n_map=1500,
                name="EuRoC MH01-shaped stereo 752x480, 1000 feat, 8 levels"),
     "c4": dict(w=1920, h=1080, nfeat=2000, streams=32, n_map=3000,
@@ -54,10 +59,12 @@ MAP_NOTE = ("SURVEY 8(d) map per stream: every keypoint as a MapPoint (descripto
 
 def set_config(name):
     """Select the image geometry / feature budget the module-level helpers below work on."""
-    global W, H, NFEAT, WORKLOAD
+    global W, H, NFEAT, WORKLOAD, MONO, UNIT
     c = CONFIGS[name]
     W, H, NFEAT = c["w"], c["h"], c["nfeat"]
-    WORKLOAD = c["name"] + ": " + CHAIN
+    MONO = bool(c.get("mono"))
+    UNIT = "monocular frames/s" if MONO else "stereo frames/s"
+    WORKLOAD = c["name"] + ": " + (CHAIN_MONO if MONO else CHAIN)
     return c
 
 
@@ -264,7 +271,7 @@ class _CpuStreams:
         from replay_reference import track_frame_map
         j %= self.n
         return track_frame_map(self.oracle, self.cam, self.imgs[2 * j], self.imgs[2 * j + 1], self.maps[j], self.Tp[j],
-                               nfeatures=NFEAT, extractors=extractors)
+                               nfeatures=NFEAT, extractors=extractors, mono=MONO)
 
 
 def cpu_baseline(n_frames, warm=20):
@@ -301,10 +308,12 @@ def cpu_baseline(n_frames, warm=20):
         fl.result(), fr.result()
     two_thread_ext = (time.perf_counter() - t0) / m
     one_thread_ext = 2 * ext_ms * 1e-3
+    if MONO:                                   # one image per frame: nothing to run side by side
+        two_thread_ext = one_thread_ext = 0.0
     med = float(np.median(lat))
     pool.shutdown()
     return {"value": 1.0 / med, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "%d stereo frames of the same chain and 8(d) map workload after %d warm-up frames, %.1f s, 1 thread "
+            "sample": "%d frames of the same chain and 8(d) map workload after %d warm-up frames, %.1f s, 1 thread "
                       "(host has %d cores); value = 1 / median frame time" % (n_frames, warm, total, os.cpu_count() or 0),
             "frame_ms": {"median": 1e3 * med, "p95": 1e3 * float(np.percentile(lat, 95)), "mean": 1e3 * float(lat.mean())},
             "oracle_extraction_ms_per_image": ext_ms,
@@ -408,7 +417,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="c2: EuRoC 752x480 stereo (the metric's configuration); "
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="c1: EuRoC 752x480 monocular (BASELINE config 1); "
+                    "c2: EuRoC 752x480 stereo (the metric's configuration); "
                     "c4: 1920x1080 stereo, 2000 features (BASELINE config 4)")
     ap.add_argument("--streams", type=int, default=0, help="independent stereo streams per GPU per step (0: the config's default)")
     ap.add_argument("--workload", default="sec8d", choices=["sec8d", "selfmap"],
@@ -428,6 +438,8 @@ def main():
     cfg = set_config(args.config)
     if not args.streams:
         args.streams = cfg["streams"]
+    if MONO and args.workload == "selfmap":
+        raise SystemExit("bench.py: the monocular tracker has no self-map harness (no stereo depth); use --workload sec8d")
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -468,12 +480,13 @@ def main():
         sampler.start()
 
     S = args.streams
-    B = 2 * S
+    IPS = 1 if MONO else 2
+    B = IPS * S
     RING = max(1, args.ring) if args.workload == "sec8d" else 1
     cam = orbx.make_camera()
     ctx = orbx.Context(local)
-    ex = orbx.ORBextractor(ctx, NFEAT, 1.2, NLEVELS, 20, 7, max_w=W, max_h=H, max_batch=B)
-    trk = orbx.Tracker(ctx, ex, S, cam, th_frame=7.0, th_map=1.0, nnratio_map=0.8)
+    ex = orbx.ORBextractor(ctx, NFEAT, 1.2, NLEVELS, 20, 7, max_w=W, max_h=H, max_batch=2 * S)
+    trk = orbx.Tracker(ctx, ex, S, cam, th_frame=None, th_map=1.0, nnratio_map=0.8, mono=MONO)
     mcap = trk.map_capacity
     Tt, dT, T_init = make_sequence(S, RING, seed=7 + rank)
     Tt_abs, Tp_abs = make_poses(S, seed=7 + rank)     # the self-map harness: one true pose and one absolute prior per stream
@@ -482,7 +495,7 @@ def main():
     for r in range(RING):
         imgs = make_streams(S, seed0=100 + 1000 * rank + 37 * r)
         pin = orbx.host_array((B, H, W), np.uint8)          # page-locked inputs for the e2e arm
-        pin[:] = np.stack(imgs)
+        pin[:] = np.stack(imgs[0::2] if MONO else imgs)     # monocular: the left images only (the right ones only build the map)
         entry = dict(pin=pin, imgs=[pin[i] for i in range(B)], d_img=torch.from_numpy(pin).cuda(),
                      Tt=Tt[r], dT=dT[r], d_true=torch.from_numpy(Tt[r].reshape(S, 16)).cuda(),
                      d_dT=torch.from_numpy(dT[r].reshape(S, 16)).cuda())
@@ -634,7 +647,7 @@ def main():
 
     # ---------------- continuity with round 1: the best-case self-map harness, resident ----------------
     self_ms = None
-    if args.workload == "sec8d":
+    if args.workload == "sec8d" and not MONO:
         trk.synchronize()
         trk.set_chain(False)
         trk.set_map(None)
@@ -775,15 +788,15 @@ def main():
                                 "bytes_per_image": alg["total"], "ms": ext_total_ms}}
 
     cpu = None
-    if not args.no_cpu and world == 1 and args.config == "c2":
+    if not args.no_cpu and world == 1 and args.config in ("c1", "c2"):
         cpu = cpu_baseline(args.cpu_frames)
 
     mean_stats = {n: float(v) for n, v in zip(trk.STATS, stats.mean(0))}
     mean_stats["outliers_1"] = mean_stats["matches_frame"] - mean_stats["inliers_1"]
     cfg_out = {"workload": WORKLOAD, "config": args.config, "streams_per_gpu": S, "images_per_step_per_gpu": B,
                "parallelism": "replicas x%d" % world,
-               "l2": "inputs larger than L2: each step streams 2*S fresh images (%d MB) and rebuilds %d MB of pyramid; a ring of %d "
-                     "different image sets" % (B * W * H >> 20, int(B * sum(w * h for w, h in level_sizes()) * 2) >> 20, RING),
+               "l2": "inputs larger than L2: each step streams %d*S fresh images (%d MB) and rebuilds %d MB of pyramid; a ring of %d "
+                     "different image sets" % (IPS, B * W * H >> 20, int(B * sum(w * h for w, h in level_sizes()) * 2) >> 20, RING),
                "overlap_steps": bool(args.overlap), "ms_per_step_serial_flushed": serial_ms / args.steps,
                "mean_per_stream": mean_stats, "max_translation_error_m": pose_err}
     if args.workload == "sec8d":

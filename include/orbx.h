@@ -525,6 +525,17 @@ int orbx_pose_inertial_optimization_last_frame_batch(
 typedef struct orbx_tracker orbx_tracker;
 #define ORBX_TRACK_STATS 8 /* nL, nR, nStereo, matches(last frame), inliers, matches(local map), inliers, LM its */
 
+/* Monocular tracker (BASELINE config 1).  Replaces Frame::Frame(mono) src/Frame.cc:308-349 ->
+ * Tracking::TrackWithMotionModel with bMono (th = 15, src/Tracking.cc:2364-2378) -> PoseOptimization's monocular edges
+ * (src/Optimizer.cc:961-1010) -> TrackLocalMap.  ONE image per stream ([I0, I1, ...] wherever the stereo tracker takes
+ * [L0, R0, L1, R1, ...]); ext max_batch >= S; mvuRight = mvDepth = -1 for every keypoint, so there is no back-projection
+ * harness: the map must be given with orbx_tracker_set_map / _upload_map before the first step (ORBX_EINVAL otherwise).
+ * cam->b / cam->bf may be 0.  stats[1] (nR) and stats[2] (nStereo) are 0.  Everything else as orbx_tracker_create. */
+orbx_tracker *orbx_tracker_create_mono(orbx_ctx *ctx, orbx_ext *ext /* max_batch >= S */, int S, const orbx_camera *cam,
+                                       float th_frame, float th_map, float nnratio_map);
+/* 2 (stereo tracker) or 1 (monocular tracker) */
+int orbx_tracker_images_per_stream(const orbx_tracker *trk);
+
 orbx_tracker *orbx_tracker_create(orbx_ctx *ctx, orbx_ext *ext /* max_batch >= 2*S */, int S,
                                   const orbx_camera *cam, float th_frame, float th_map,
                                   float nnratio_map);

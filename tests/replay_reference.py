@@ -82,20 +82,27 @@ def track_frame(ork, cam, L, R, Tcw_true, Tcw_prior, th_frame=7.0, th_map=1.0, n
     return T2, stats
 
 
-def track_frame_map(ork, cam, L, R, mp, Tcw_prior, th_frame=7.0, th_map=1.0, nn_map=0.8, nfeatures=1000, extractors=None,
-                    log_sf=None):
+def track_frame_map(ork, cam, L, R, mp, Tcw_prior, th_frame=None, th_map=1.0, nn_map=0.8, nfeatures=1000, extractors=None,
+                    log_sf=None, mono=False):
     """The chain of orbx_tracker_step with a GIVEN map (orbx_tracker_set_map; mp = one stream's arrays as produced by
     scenarios.track_map_scenario), composed from the oracle's functions: extract L+R, ComputeStereoMatches,
     SearchByProjection(Cur, Last) over the last-frame entries, PoseOptimization, outliers dropped, isInFrustum over the
     unmatched local map, SearchByProjection(F, local map), PoseOptimization."""
     from orbx import abi
+    if th_frame is None:
+        th_frame = 15.0 if mono else 7.0                  # src/Tracking.cc:2364-2368
     exL, exR = extractors if extractors else (ork.Extractor(nfeatures), ork.Extractor(nfeatures))
     _, kL, dL, _ = exL(L)
-    _, kR, dR, _ = exR(R)
     scale, inv_scale, isg = exL.scale, exL.inv_scale, exL.inv_sigma2
-    pyrL = [exL.pyramid_level(l) for l in range(exL.nlevels)]
-    pyrR = [exR.pyramid_level(l) for l in range(exR.nlevels)]
-    ur, dp = ork.stereo_match(pyrL, pyrR, kL, dL, kR, dR, scale, inv_scale, float(F32(cam.bf)), float(F32(cam.b)))
+    if mono:
+        # Frame::Frame(mono): one image, mvuRight = mvDepth = -1 (src/Frame.cc:330-331); R is ignored
+        kR = ()
+        ur = np.full(len(kL), -1, F32)
+    else:
+        _, kR, dR, _ = exR(R)
+        pyrL = [exL.pyramid_level(l) for l in range(exL.nlevels)]
+        pyrR = [exR.pyramid_level(l) for l in range(exR.nlevels)]
+        ur, dp = ork.stereo_match(pyrL, pyrR, kL, dL, kR, dR, scale, inv_scale, float(F32(cam.bf)), float(F32(cam.b)))
     n, M = len(kL), int(mp["n_map"])
     H, W = L.shape
     Fr = abi.Frame(kL, dL, ur, bounds=(0, 0, W, H))
@@ -105,7 +112,7 @@ def track_frame_map(ork, cam, L, R, mp, Tcw_prior, th_frame=7.0, th_map=1.0, nn_
     #  frame's pose is taken equal to the prior here, so tlc = 0)
     nm1, match, kept, cur = ork.search_by_projection_frame(Fr, None, cam, Tp, Tp, mp["last_flags"][:M], xw,
                                                            mp["last_octave"][:M], mp["last_angle"][:M], mp["desc"][:M], th_frame,
-                                                           False, True, scale)
+                                                           mono, True, scale)
 
     def edges(assign):
         idx = np.flatnonzero(assign >= 0)

@@ -173,6 +173,38 @@ def test_tracker_given_map_matches_oracle_chain(ctx, ork):
     ex.close()
 
 
+def test_monocular_tracker_matches_oracle_chain(ctx, ork):
+    """BASELINE config 1: ONE image per stream, no stereo matching, monocular edges only (chi2 5.991), th = 15."""
+    import orbx
+    from replay_reference import track_frame_map
+    S = 3
+    cam = orbx.make_camera()
+    imgs, Tt, Tp, maps = _map_setup(ork, S, 170)
+    left = imgs[0::2]
+    ex = orbx.ORBextractor(ctx, max_batch=S)
+    trk = orbx.Tracker(ctx, ex, S, cam, mono=True)
+    assert trk.ips == 1
+    with pytest.raises(orbx.OrbxError):                             # no depth -> no self-map harness
+        trk.step(left, Tt, Tp)
+    host = sc.stack_track_maps(maps)
+    for rep in range(2):
+        trk.upload_map(host)
+        Tout, stats = trk.step(left, Tt, Tp)
+        for s in range(S):
+            T2, st = track_frame_map(ork, cam, left[s], None, maps[s], Tp[s], mono=True)
+            assert st[1] == 0 and st[2] == 0
+            assert np.array_equal(stats[s], st), (s, stats[s], st)
+            assert np.abs(Tout[s] - T2).max() < 2e-6, (s, np.abs(Tout[s] - T2).max())
+            assert st[6] > 100 and np.abs(Tout[s][:3, 3] - Tt[s][:3, 3]).max() < 3e-2, st
+    # the asynchronous host path carries one image per stream as well
+    trk.upload_map(host)
+    trk.submit(left, Tt, Tp)
+    got = trk.collect()
+    assert np.array_equal(got[0], Tout) and np.array_equal(got[1], stats)
+    trk.close()
+    ex.close()
+
+
 def test_tracker_chain_mode_composes_the_prior_on_the_device(ctx, ork):
     """Motion-model chaining: step t+1 starts from dT * (pose step t produced).  Equal to feeding that product from the host."""
     import orbx
