@@ -241,6 +241,11 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
       tx[4 * dx + 1] = (int16_t)cv_round_f((1.f - fx) * 2048.f);
       tx[4 * dx + 2] = (int16_t)cv_round_f(fx * 2048.f);
     }
+    L.pyrSpan = 0;
+    for (int dx = 0; dx < L.w; dx += 4) {
+      const int lastCol = std::min(dx + 3, L.w - 1);
+      L.pyrSpan = std::max(L.pyrSpan, (int)tx[4 * lastCol] + 1 - (int)tx[4 * dx] + 1);
+    }
     L.tabY = (int)htab.size();
     htab.resize(htab.size() + 4 * (size_t)L.h);
     int16_t* ty = htab.data() + L.tabY;

@@ -27,6 +27,7 @@ struct LevelParams {
   int blurTileStart, blurTilesX, blurTilesY;
   // resize tables (level l from l-1): offsets into ExtractParams::tab (int16 units)
   int tabX, tabY;
+  int pyrSpan;                     // max source bytes (x0[3] + 1 - x0[0] + 1) any aligned group of 4 output columns reads
   // quadtree
   int nFeat, nIni;
   float hX;

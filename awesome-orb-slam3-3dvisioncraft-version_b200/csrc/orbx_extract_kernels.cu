@@ -17,89 +17,163 @@ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9
 
 // =====================================================================================
 // K1  pyramid level l from level l-1: cv::resize(INTER_LINEAR) 8U fixed point.
-// grid (ceil(w/4/128), ceil(h/PYR_STRIP), B), block 128.  A thread owns 4 horizontally adjacent output pixels and walks
-// down a strip of PYR_STRIP output rows.  The horizontal pass of a SOURCE row (T = S[x0]*a0 + S[x0+1]*a1, kept as T >> 4)
-// is computed once and reused by every output row that blends it: with the 1.2 scale factor a source row feeds 1.67
-// output rows on average, and consecutive output rows usually share one of their two source rows, so the thread keeps
-// the two most recent horizontal rows in registers (tags rowA / rowB, warp-uniform control flow).  The vertical pass is
+// grid (nbx, ceil(h/PYR_STRIP), B); the block covers one strip of PYR_STRIP output rows with one thread per 4-pixel word
+// (block width = the row's words split evenly over nbx blocks, rounded to whole warps).  The horizontal pass of a SOURCE
+// row (T = S[x0]*a0 + S[x0+1]*a1, kept as T >> 4) is computed once and reused by every output row that blends it (with
+// the 1.2 scale factor a source row feeds 1.67 output rows on average): the thread streams down the source rows of its
+// strip, keeps the previous and the current horizontal pass in registers and has the raw bytes of the next row in flight.
+// The vertical pass is
 //   ((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2
 // with each ">> 16" product taken as a high multiply by b << 16 (coefficients are in [0, 2048], so this is exact).
-// About 12 issued instructions per output pixel instead of 45 for the one-output-row-per-thread form it replaces.
 // Packed coefficient tables (int16 x 4 per destination column / row, one 8-byte load each):
 //   X[dx] = { xofs, a0, a1, 0 }     Y[dy] = { y0, y1, b0, b1 }
 // =====================================================================================
 #define PYR_STRIP 8
 
-struct PyrCols {            // per-thread constants of its 4 output columns
+// Per-thread constants of its 4 output columns.
+// WORDS path (every level whose source rows are 4-byte aligned and whose 4 columns span <= 8 source bytes, i.e. scale
+// factors up to 2): the 4 x 2 source bytes of a row are cut out of three aligned 32-bit loads -- two funnel shifts bring
+// the 8-byte window that starts at x0[0] into (u0, u1), two PRMTs with per-thread selectors line the pixel pairs up as
+// (S[x0], S[x0+1]) byte pairs, and one DP2A per pixel forms S[x0]*a0 + S[x0+1]*a1 against the packed coefficient pair
+// (a0 | a1 << 16): 3 loads + 12 ALU instructions per 4 pixels instead of 8 byte loads with 64-bit address arithmetic.
+// Where a1 == 0 (left / right clamp) the selector repeats byte x0, so nothing right of the last source pixel is touched.
+template <bool WORDS>
+struct PyrCols;
+template <>
+struct PyrCols<false> {
   int x0[4];
   int a0[4], a1[4];
 };
+template <>
+struct PyrCols<true> {
+  int base;                  // byte offset of the first aligned word (x0[0] & ~3)
+  unsigned shift;            // 8 * (x0[0] & 3)
+  unsigned sel01, sel23;     // PRMT selectors of the pixel pairs (0,1) and (2,3) inside (u0, u1)
+  unsigned coef[4];          // a0 | a1 << 16
+  bool need1, need2;         // the window reaches into the 2nd / 3rd word
+};
 
-__device__ __forceinline__ void pyr_hrow(const uint8_t* __restrict__ row, const PyrCols& C, int (&T)[4]) {
+__device__ __forceinline__ void pyr_cols_init(PyrCols<false>& C, const int (&ent)[8], int, int) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    // x0 + 1 may be one past the last source pixel at the right edge: there a1 == 0 (OpenCV clamps fx to 0) and the
-    // byte read lies inside the row's pitch padding
-    const int v = (int)__ldg(row + C.x0[i]) * C.a0[i] + (int)__ldg(row + C.x0[i] + 1) * C.a1[i];
-    T[i] = v >> 4;
+    C.x0[i] = ent[2 * i] & 0xffff;
+    C.a0[i] = ent[2 * i] >> 16;
+    C.a1[i] = (short)(ent[2 * i + 1] & 0xffff);
   }
 }
+__device__ __forceinline__ void pyr_cols_init(PyrCols<true>& C, const int (&ent)[8], int dx0, int dw) {
+  const int x00 = ent[0] & 0xffff;
+  C.base = x00 & ~3;
+  const int mis = x00 & 3;
+  C.shift = 8u * (unsigned)mis;
+  unsigned sel[4];
+  int last = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool live = dx0 + i < dw;                       // table padding past the last column: weight 0, byte x0[0]
+    const int a0 = live ? (ent[2 * i] >> 16) : 0, a1 = live ? (int)(short)(ent[2 * i + 1] & 0xffff) : 0;
+    const int o = live ? (ent[2 * i] & 0xffff) - x00 : 0;
+    const int o1 = o + (a1 != 0 ? 1 : 0);
+    sel[i] = (unsigned)o | ((unsigned)o1 << 4);
+    C.coef[i] = (unsigned)a0 | ((unsigned)a1 << 16);
+    last = max(last, o1);
+  }
+  C.sel01 = sel[0] | (sel[1] << 8);
+  C.sel23 = sel[2] | (sel[3] << 8);
+  C.need1 = mis + last >= 4;
+  C.need2 = mis + last >= 8;
+}
 
-__global__ void __launch_bounds__(128) pyr_resize_kernel(const __grid_constant__ ExtractParams p, int level) {
+// raw source bytes of one row for the thread's 4 columns (loaded one source row ahead of their use)
+template <bool WORDS>
+struct PyrRaw;
+template <>
+struct PyrRaw<false> { uint32_t s0, s1; };       // bytes S[x0[i]] and S[x0[i] + 1], packed
+template <>
+struct PyrRaw<true> { uint32_t w0, w1, w2; };    // the aligned words around x0[0]
+
+__device__ __forceinline__ void pyr_load(const uint8_t* __restrict__ row, const PyrCols<false>& C, PyrRaw<false>& R) {
+  // x0 + 1 may be one past the last source pixel at the right edge: there a1 == 0 (OpenCV clamps fx to 0) and the
+  // byte read lies inside the row's pitch padding
+  R.s0 = R.s1 = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    R.s0 |= (uint32_t)__ldg(row + C.x0[i]) << (8 * i);
+    R.s1 |= (uint32_t)__ldg(row + C.x0[i] + 1) << (8 * i);
+  }
+}
+__device__ __forceinline__ void pyr_load(const uint8_t* __restrict__ row, const PyrCols<true>& C, PyrRaw<true>& R) {
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(row + C.base);
+  R.w0 = __ldg(wp);
+  R.w1 = C.need1 ? __ldg(wp + 1) : 0u;
+  R.w2 = C.need2 ? __ldg(wp + 2) : 0u;
+}
+__device__ __forceinline__ void pyr_finish(const PyrRaw<false>& R, const PyrCols<false>& C, int (&T)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    T[i] = ((int)((R.s0 >> (8 * i)) & 0xff) * C.a0[i] + (int)((R.s1 >> (8 * i)) & 0xff) * C.a1[i]) >> 4;
+}
+__device__ __forceinline__ void pyr_finish(const PyrRaw<true>& R, const PyrCols<true>& C, int (&T)[4]) {
+  const uint32_t u0 = __funnelshift_r(R.w0, R.w1, C.shift), u1 = __funnelshift_r(R.w1, R.w2, C.shift);
+  const uint32_t p01 = __byte_perm(u0, u1, C.sel01), p23 = __byte_perm(u0, u1, C.sel23);
+  T[0] = (int)(__dp2a_lo(C.coef[0], p01, 0u) >> 4);
+  T[1] = (int)(__dp2a_hi(C.coef[1], p01, 0u) >> 4);
+  T[2] = (int)(__dp2a_lo(C.coef[2], p23, 0u) >> 4);
+  T[3] = (int)(__dp2a_hi(C.coef[3], p23, 0u) >> 4);
+}
+
+// The thread walks down the SOURCE rows its strip of output rows blends (y0 of the first .. y1 of the last; with scale
+// factors below 2 every one of them is used): the raw bytes of row sy + 1 are requested before row sy is reduced, and an
+// output row is emitted as soon as its lower source row y1 is there (its upper one, y0 = y1 - 1 or y1 at the clamped
+// border, is the previous / the same horizontal pass).  All control flow is uniform across the block.
+template <bool WORDS>
+__global__ void __launch_bounds__(256) pyr_resize_kernel(const __grid_constant__ ExtractParams p, int level) {
   const LevelParams& D = p.lv[level];
   const LevelParams& S = p.lv[level - 1];
   const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (dx0 >= D.w) return;
   const int dyBeg = blockIdx.y * PYR_STRIP, dyEnd = min(dyBeg + PYR_STRIP, D.h);
   const uint8_t* src = S.pyr + (size_t)blockIdx.z * S.imgStride;
-  uint8_t* dst = D.pyr + (size_t)blockIdx.z * D.imgStride + dx0;
-  PyrCols C;
+  uint8_t* drow = D.pyr + (size_t)blockIdx.z * D.imgStride + dx0 + (size_t)dyBeg * D.pitch;
+  const int dpitch = D.pitch, spitch = S.pitch;
+  PyrCols<WORDS> C;
   {
     // the table is padded to a multiple of 4 entries, so the two 16-byte loads never leave it
     const int4* tx4 = reinterpret_cast<const int4*>(p.tab + D.tabX) + (dx0 >> 1);
     const int4 e01 = __ldg(tx4), e23 = __ldg(tx4 + 1);
     const int ent[8] = {e01.x, e01.y, e01.z, e01.w, e23.x, e23.y, e23.z, e23.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      C.x0[i] = ent[2 * i] & 0xffff;
-      C.a0[i] = ent[2 * i] >> 16;
-      C.a1[i] = (short)(ent[2 * i + 1] & 0xffff);
-    }
+    pyr_cols_init(C, ent, dx0, D.w);
   }
   const short4* tabY = reinterpret_cast<const short4*>(p.tab + D.tabY);
-  int TA[4], TB[4];
-  int rowA = -1, rowB = -1;
+  const int syBeg = tabY[dyBeg].x, syEnd = tabY[dyEnd - 1].y;
+  int dy = dyBeg;
+  short4 ty = tabY[dy];                             // uniform across the block
+  const uint8_t* srow = src + (size_t)syBeg * spitch;
+  PyrRaw<WORDS> R;
+  pyr_load(srow, C, R);
+  int TP[4] = {0, 0, 0, 0}, TC[4];
 #pragma unroll 1
-  for (int dy = dyBeg; dy < dyEnd; ++dy) {
-    const short4 ty = tabY[dy];                      // uniform across the block
-    const int y0 = ty.x, y1 = ty.y;
-    // bring the horizontal pass of source rows y0 -> TA, y1 -> TB (reusing what the previous output row left)
-    if (y0 != rowA) {
-      if (y0 == rowB) {
+  for (int sy = syBeg; sy <= syEnd; ++sy) {
+    srow += spitch;
+    PyrRaw<WORDS> N = R;
+    if (sy < syEnd) pyr_load(srow, C, N);          // next source row, in flight while this one is reduced
+    pyr_finish(R, C, TC);
+    R = N;
+    while (dy < dyEnd && ty.y == sy) {
+      const int B0 = (int)ty.z << 16, B1 = (int)ty.w << 16;
+      const bool same = ty.x == sy;                 // y0 == y1 (clamped border)
+      int v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) TA[i] = TB[i];
-      } else {
-        pyr_hrow(src + (size_t)y0 * S.pitch, C, TA);
-      }
-      rowA = y0;
+      for (int i = 0; i < 4; ++i)
+        v[i] = (__mulhi(B0, same ? TC[i] : TP[i]) + __mulhi(B1, TC[i]) + 2) >> 2;   // <= 255: the weights sum to 2048 twice
+      const uint32_t out = __byte_perm(__byte_perm((uint32_t)v[0], (uint32_t)v[1], 0x0040),
+                                       __byte_perm((uint32_t)v[2], (uint32_t)v[3], 0x0040), 0x5410);
+      *reinterpret_cast<uint32_t*>(drow) = out;     // pitch is a multiple of 16 and padded: safe past w
+      drow += dpitch;
+      if (++dy < dyEnd) ty = tabY[dy];
     }
-    if (y1 != rowB) {
-      if (y1 == y0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) TB[i] = TA[i];
-      } else {
-        pyr_hrow(src + (size_t)y1 * S.pitch, C, TB);
-      }
-      rowB = y1;
-    }
-    const int B0 = (int)ty.z << 16, B1 = (int)ty.w << 16;
-    uint32_t out = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int v = (__mulhi(B0, TA[i]) + __mulhi(B1, TB[i]) + 2) >> 2;
-      out |= (uint32_t)(v & 0xff) << (8 * i);
-    }
-    *reinterpret_cast<uint32_t*>(dst + (size_t)dy * D.pitch) = out;  // pitch is a multiple of 16 and padded: safe past w
+    for (int i = 0; i < 4; ++i) TP[i] = TC[i];
   }
 }
 
@@ -936,7 +1010,17 @@ __device__ __forceinline__ int dp4a_us(unsigned a, unsigned b_s8, int c) {   // 
   return d;
 }
 
-__global__ void __launch_bounds__(DESC_NT) describe_kernel(const __grid_constant__ ExtractParams p, orbx_keypoint* kps,
+#define DESC_KPW 4                        // keypoints a warp processes one after the other
+#define DESC_OW 9                         // words per staged row of the un-blurred 31x31 patch (31 + <=3 bytes of misalignment)
+#define DESC_BW 10                        // words per staged row of the blurred 37x37 patch (the rotated pattern reaches +-18)
+#define DESC_OWORDS (31 * DESC_OW + 1)
+#define DESC_BWORDS (37 * DESC_BW + 2)
+
+// The kernel used to be bound by the L1 data pipe (87 % of its wavefront peak, profiles/r02m): a warp's 9 patch-row loads
+// touched 31 cache lines each and its 16 byte gathers ~25.  Both patches are now brought in by row-major word loads (a
+// request covers 3-4 rows) into per-warp shared memory, and the orientation sums and the 512 pattern samples are read from
+// there.
+__global__ void __launch_bounds__(DESC_NT, 5) describe_kernel(const __grid_constant__ ExtractParams p, orbx_keypoint* kps,
                                                            uint8_t* desc, int cap, int* nOut, int* monoOut) {
   // lanes of a warp read 32 different pattern rows: stage the table in shared memory (constant
   // memory would serialise the divergent addresses)
@@ -946,6 +1030,8 @@ __global__ void __launch_bounds__(DESC_NT) describe_kernel(const __grid_constant
   // s_icw[v*17 + 8 + j] the 0/1 membership mask (stride 17: rows of different lanes fall into different banks)
   __shared__ unsigned s_icw[16 * 17];
   __shared__ int s_cnt[2 * ORBX_MAX_LEVELS];
+  __shared__ uint32_t s_org[DESC_NT / 32][DESC_OWORDS];
+  __shared__ uint32_t s_blr[DESC_NT / 32][DESC_BWORDS];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 256; i += blockDim.x)   // transposed: word (byte row r, pair k) at [k*32 + r]
     s_pat[(i & 7) * 32 + (i >> 3)] = reinterpret_cast<const int*>(c_pattern)[i];
@@ -965,104 +1051,151 @@ __global__ void __launch_bounds__(DESC_NT) describe_kernel(const __grid_constant
     s_cnt[threadIdx.x] = (threadIdx.x & 1) ? p.selLap[b * p.nlevels + l] : p.selN[b * p.nlevels + l];
   }
   __syncthreads();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  // locate (level, i) of this warp's keypoint and the counts it needs for its output slot
-  int level = -1, idx = 0, base = 0, lapBefore = 0, total = 0, totalLap = 0;
-  {
-    int acc = 0, lapAcc = 0;
-    for (int l = 0; l < p.nlevels; ++l) {
-      const int nl = s_cnt[2 * l];
-      if (level < 0 && warp < acc + nl) {
-        level = l;
-        idx = warp - acc;
-        base = acc;
-        lapBefore = lapAcc;
-      }
-      acc += nl;
-      lapAcc += s_cnt[2 * l + 1];
-    }
-    total = acc;
-    totalLap = lapAcc;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int total = 0, totalLap = 0;
+  for (int l = 0; l < p.nlevels; ++l) {
+    total += s_cnt[2 * l];
+    totalLap += s_cnt[2 * l + 1];
   }
-  if (warp == 0 && lane == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     nOut[b] = min(total, cap);
     monoOut[b] = total - totalLap;
     if (total > cap) atomicExch(p.err, 4);
   }
-  if (level < 0) return;
-  const LevelParams& L = p.lv[level];
-  const uint2 rec = p.sel[(size_t)b * p.selPerImage + L.selOfs + idx];
-  const int px = rec.x & 0xffff, py = rec.x >> 16;
-  const int score = rec.y & 0xff, lap = (rec.y >> 8) & 1, lapPrefix = rec.y >> 16;
+  // lane -> (row, word) of the first staging round of either patch; every further round advances by 32 words
+  const int oRow0 = lane / DESC_OW, oCol0 = lane - oRow0 * DESC_OW;
+  const int bRow0 = lane / DESC_BW, bCol0 = lane - bRow0 * DESC_BW;
+  uint32_t* so = s_org[wid];
+  uint32_t* sb = s_blr[wid];
+  const uint8_t* sbBytes = reinterpret_cast<const uint8_t*>(sb);
 
-  // --- IC_Angle on the un-blurred level: lane = patch row.  The 31 pixels of the row are fetched as nine aligned
-  //     32-bit words (the keypoint sits >= 19 px inside the image, so they never leave it), re-aligned with funnel
-  //     shifts and reduced with DP4A against the disc weights: m10 = sum u*I, row sum = sum I (exact integers) ---
-  const uint8_t* img = L.pyr + (size_t)b * L.imgStride;
-  int m10 = 0, m01 = 0;
-  if (lane < 31) {
-    const int dy = lane - 15;
-    const int v = dy < 0 ? -dy : dy;
-    const uint8_t* rowp = img + (size_t)(py + dy) * L.pitch + (px - 15);
-    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(rowp) & 3);
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp - mis);
-    uint32_t w[9];
-#pragma unroll
-    for (int j = 0; j < 9; ++j) w[j] = __ldg(wp + j);
-    const unsigned* wt = s_icw + v * 17;
-    int rs = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t pix = __funnelshift_r(w[j], w[j + 1], 8 * mis);   // bytes u = 4j-15 .. 4j-12
-      m10 = dp4a_us(pix, wt[j], m10);
-      rs = (int)__dp4a(pix, wt[8 + j], (unsigned)rs);
+#pragma unroll 1
+  for (int it = 0; it < DESC_KPW; ++it) {
+    const int kp = blockIdx.x * ((DESC_NT / 32) * DESC_KPW) + it * (DESC_NT / 32) + wid;   // warp-uniform
+    if (kp >= total) break;
+    // locate (level, i) of this keypoint and the counts it needs for its output slot
+    int level = 0, idx = 0, base = 0, lapBefore = 0;
+    {
+      int acc = 0, lapAcc = 0;
+      bool found = false;
+      for (int l = 0; l < p.nlevels; ++l) {
+        const int nl = s_cnt[2 * l];
+        if (!found && kp < acc + nl) {
+          found = true;
+          level = l;
+          idx = kp - acc;
+          base = acc;
+          lapBefore = lapAcc;
+        }
+        acc += nl;
+        lapAcc += s_cnt[2 * l + 1];
+      }
     }
-    m01 = dy * rs;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-  }
-  const float angle = fast_atan2_deg((float)m01, (float)m10);
+    const LevelParams& L = p.lv[level];
+    const uint2 rec = p.sel[(size_t)b * p.selPerImage + L.selOfs + idx];
+    const int px = rec.x & 0xffff, py = rec.x >> 16;
+    const int score = rec.y & 0xff, lap = (rec.y >> 8) & 1, lapPrefix = rec.y >> 16;
 
-  // --- steered BRIEF on the blurred level: lane = descriptor byte ---
-  const float factorPI = (float)(3.14159265358979323846 / 180.0);
-  const float ang = __fmul_rn(angle, factorPI);
-  double sd, cd;
-  sincos((double)ang, &sd, &cd);            // (float)cos((double)angle), (float)sin((double)angle): DESIGN.md §3
-  const float a = (float)cd, bsn = (float)sd;
-  const uint8_t* bl = L.blur + (size_t)b * L.blurStride + (size_t)py * L.blurPitch + px;
-  int val = 0;
+    // --- stage both patches: word q = row * W + col of the patch goes to shared word q.  The un-blurred level may be
+    //     caller memory with any stride, so each row is aligned on its own; the blurred plane has a 64-byte pitch ---
+    const uint8_t* img = L.pyr + (size_t)b * L.imgStride + (size_t)(py - 15) * L.pitch + (px - 15);
+    const uint8_t* blb = L.blur + (size_t)b * L.blurStride + (size_t)(py - 18) * L.blurPitch + (px - 18);
+    const unsigned bmis = (unsigned)(reinterpret_cast<uintptr_t>(blb) & 3);
+    blb -= bmis;
+    const unsigned imgLo = (unsigned)reinterpret_cast<uintptr_t>(img);
+    __syncwarp();                                 // the previous keypoint's readers are done with so / sb
+    {
+      int r = oRow0, c = oCol0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int pw = s_pat[k * 32 + lane];   // (x0,y0,x1,y1) packed int8
-    const float x0 = (float)(int8_t)(pw & 0xff), y0 = (float)(int8_t)((pw >> 8) & 0xff);
-    const float x1 = (float)(int8_t)((pw >> 16) & 0xff), y1 = (float)(int8_t)((pw >> 24) & 0xff);
-    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, bsn), __fmul_rn(y0, a)));
-    const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bsn)));
-    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bsn), __fmul_rn(y1, a)));
-    const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, bsn)));
-    const int t0 = __ldg(bl + r0 * L.blurPitch + c0), t1 = __ldg(bl + r1 * L.blurPitch + c1);
-    val |= (t0 < t1) << k;
-  }
-  // --- output slot: non-lapping keypoints fill from the front, lapping ones from the back ---
-  const int slot = lap ? (total - 1 - (lapBefore + lapPrefix)) : (base - lapBefore + idx - lapPrefix);
-  if (slot < 0 || slot >= cap) return;
-  desc[((size_t)b * cap + slot) * 32 + lane] = (uint8_t)val;
-  if (lane == 0) {
-    orbx_keypoint kp;
-    kp.x = (float)px;
-    kp.y = (float)py;
-    if (level != 0) {
-      kp.x = __fmul_rn(kp.x, L.scale);
-      kp.y = __fmul_rn(kp.y, L.scale);
+      for (int t = 0; t < (31 * DESC_OW + 31) / 32; ++t) {
+        if (r < 31) {
+          const unsigned ro = (unsigned)r * (unsigned)L.pitch;
+          const int off = (int)ro - (int)((imgLo + ro) & 3u) + 4 * c;      // may be negative (-3..) in row 0
+          so[r * DESC_OW + c] = __ldg(reinterpret_cast<const uint32_t*>(img + off));
+        }
+        c += 32 % DESC_OW;
+        r += 32 / DESC_OW;
+        if (c >= DESC_OW) { c -= DESC_OW; ++r; }
+      }
+      r = bRow0;
+      c = bCol0;
+#pragma unroll
+      for (int t = 0; t < (37 * DESC_BW + 31) / 32; ++t) {
+        if (r < 37) sb[r * DESC_BW + c] = __ldg(reinterpret_cast<const uint32_t*>(blb + ((unsigned)r * (unsigned)L.blurPitch + 4u * (unsigned)c)));
+        c += 32 % DESC_BW;
+        r += 32 / DESC_BW;
+        if (c >= DESC_BW) { c -= DESC_BW; ++r; }
+      }
     }
-    kp.size = L.kpSize;
-    kp.angle = angle;
-    kp.response = (float)score;
-    kp.octave = level;
-    kps[(size_t)b * cap + slot] = kp;
+    __syncwarp();
+
+    // --- IC_Angle on the un-blurred level: lane = patch row.  The 31 pixels of the row sit in nine aligned words
+    //     (the keypoint lies >= 19 px inside the image, so they never leave it), re-aligned with funnel shifts and
+    //     reduced with DP4A against the disc weights: m10 = sum u*I, row sum = sum I (exact integers) ---
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+      const int dy = lane - 15;
+      const int v = dy < 0 ? -dy : dy;
+      const unsigned mis = (imgLo + (unsigned)lane * (unsigned)L.pitch) & 3u;
+      const uint32_t* wrow = so + lane * DESC_OW;
+      uint32_t w[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) w[j] = wrow[j];
+      const unsigned* wt = s_icw + v * 17;
+      int rs = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t pix = __funnelshift_r(w[j], w[j + 1], 8 * mis);   // bytes u = 4j-15 .. 4j-12
+        m10 = dp4a_us(pix, wt[j], m10);
+        rs = (int)__dp4a(pix, wt[8 + j], (unsigned)rs);
+      }
+      m01 = dy * rs;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+      m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // --- steered BRIEF on the blurred level: lane = descriptor byte ---
+    const float factorPI = (float)(3.14159265358979323846 / 180.0);
+    const float ang = __fmul_rn(angle, factorPI);
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);            // (float)cos((double)angle), (float)sin((double)angle): DESIGN.md §3
+    const float a = (float)cd, bsn = (float)sd;
+    const uint8_t* bl = sbBytes + 18 * (DESC_BW * 4) + 18 + bmis;   // the keypoint inside the staged patch
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int pw = s_pat[k * 32 + lane];   // (x0,y0,x1,y1) packed int8
+      const float x0 = (float)(int8_t)(pw & 0xff), y0 = (float)(int8_t)((pw >> 8) & 0xff);
+      const float x1 = (float)(int8_t)((pw >> 16) & 0xff), y1 = (float)(int8_t)((pw >> 24) & 0xff);
+      const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, bsn), __fmul_rn(y0, a)));
+      const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bsn)));
+      const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bsn), __fmul_rn(y1, a)));
+      const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, bsn)));
+      const int t0 = bl[r0 * (DESC_BW * 4) + c0], t1 = bl[r1 * (DESC_BW * 4) + c1];
+      val |= (t0 < t1) << k;
+    }
+    // --- output slot: non-lapping keypoints fill from the front, lapping ones from the back ---
+    const int slot = lap ? (total - 1 - (lapBefore + lapPrefix)) : (base - lapBefore + idx - lapPrefix);
+    if (slot < 0 || slot >= cap) continue;
+    desc[((size_t)b * cap + slot) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+      orbx_keypoint kpo;
+      kpo.x = (float)px;
+      kpo.y = (float)py;
+      if (level != 0) {
+        kpo.x = __fmul_rn(kpo.x, L.scale);
+        kpo.y = __fmul_rn(kpo.y, L.scale);
+      }
+      kpo.size = L.kpSize;
+      kpo.angle = angle;
+      kpo.response = (float)score;
+      kpo.octave = level;
+      kps[(size_t)b * cap + slot] = kpo;
+    }
   }
 }
 
@@ -1104,8 +1237,15 @@ int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, 
 #define ORBX_EV(i) do { if (ev) ORBX_CUDA(cudaEventRecord(ev[i], st)); } while (0)
   ORBX_EV(0);
   for (int l = 1; l < p.nlevels; ++l) {
-    dim3 grid(div_up(div_up(p.lv[l].w, 4), 128), div_up(p.lv[l].h, PYR_STRIP), B);
-    pyr_resize_kernel<<<grid, 128, 0, st>>>(p, l);
+    // block width: the row's 4-pixel words split evenly over as few blocks of <= 256 threads as possible, rounded up to
+    // whole warps (752 -> 627 px: one block of 160 threads instead of two of 128 with 99 idle lanes)
+    const int words = div_up(p.lv[l].w, 4), nbx = div_up(words, 256), nt = div_up(div_up(words, nbx), 32) * 32;
+    dim3 grid(nbx, div_up(p.lv[l].h, PYR_STRIP), B);
+    // word path: source rows 4-byte aligned (level 0 may be the caller's buffer) and <= 8 source bytes per 4 columns
+    const bool wordPath = p.lv[l].pyrSpan <= 8 && (p.lv[l - 1].pitch & 3) == 0 && (p.lv[l - 1].imgStride & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(p.lv[l - 1].pyr) & 3) == 0;
+    if (wordPath) pyr_resize_kernel<true><<<grid, nt, 0, st>>>(p, l);
+    else pyr_resize_kernel<false><<<grid, nt, 0, st>>>(p, l);
     ORBX_LAUNCH(ctx);
   }
   ORBX_EV(1);
@@ -1119,7 +1259,7 @@ int orbx_extract_launch(orbx_ctx* ctx, cudaStream_t st, const ExtractParams& p, 
   ORBX_LAUNCH(ctx);
   ORBX_EV(4);
   const int warpsPerImage = p.selPerImage;
-  describe_kernel<<<dim3(div_up(warpsPerImage * 32, DESC_NT), B), DESC_NT, 0, st>>>(p, d_kps, d_desc, cap, d_n, d_mono);
+  describe_kernel<<<dim3(div_up(warpsPerImage, (DESC_NT / 32) * DESC_KPW), B), DESC_NT, 0, st>>>(p, d_kps, d_desc, cap, d_n, d_mono);
   ORBX_LAUNCH(ctx);
   ORBX_EV(5);
   ORBX_CUDA(cudaGetLastError());

@@ -534,7 +534,27 @@ __device__ bool ldlt_solve_smem(double* A, const double* b, double* x) {
 // =====================================================================================
 // K11  PoseOptimization: one CTA per frame
 // =====================================================================================
+// PO_VT "virtual threads" fix the summation order of every reduction (edge e belongs to virtual thread e % PO_VT; lane
+// butterfly inside each virtual warp, then the virtual warps in index order), PO_NT real threads execute them: with
+// PO_NT = 128 a CTA holds half the registers of the SM's two resident problems, so that the extractor's CTAs of the next
+// step (other stream) find room beside them.
+#define PO_VT 256
+#ifndef PO_NT
 #define PO_NT 256
+#endif
+static_assert(PO_VT % PO_NT == 0 && PO_NT % 32 == 0 && PO_NT >= 64, "pose_opt_kernel thread mapping");
+
+// lane butterfly of NV doubles, then lane 0 stores the virtual warp's partials (no barriers: the caller places them)
+template <int NV>
+__device__ __forceinline__ void warp_partials(double* v, double* s_red, int vwarp) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < NV; ++k) s_red[vwarp * NV + k] = v[k];
+}
 
 struct PoseOptArgs {
   const int* edgeOfs;     // [P+1] contiguous slices ...
@@ -549,14 +569,24 @@ struct PoseOptArgs {
   int* nInliers;          // [P]
   int* iters;             // [P][4]
   double* err;            // [Etot][3] scratch: residual of the last evaluated state
+  int profile;            // 1: accumulate per-phase SM cycles into g_po_prof (orbx_debug_pose_opt_profile)
 };
 
-__global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A) {
+// per-phase cycle totals over all CTAs (thread 0 of each): 0 build pass, 1 reduction + unpack, 2 solve + exp (warp 0),
+// 3 trial residual pass, 4 trial reduction, 5 accept/reject logic incl. replayed trials, 6 chi2 classification,
+// 7 whole kernel; counts: 8 builds, 9 solved trials, 10 replayed trials, 11 CTAs
+__device__ unsigned long long g_po_prof[16];
+#define PO_TICK(k) do { if (A.profile && tid == 0) { const long long t1_ = clock64(); atomicAdd(&g_po_prof[k], (unsigned long long)(t1_ - t0)); t0 = t1_; } } while (0)
+#define PO_COUNT(k) do { if (A.profile && tid == 0) atomicAdd(&g_po_prof[k], 1ull); } while (0)
+
+__global__ void __launch_bounds__(PO_NT, 512 / PO_NT) pose_opt_kernel(const PoseOptArgs A) {
   const int prob = blockIdx.x, tid = threadIdx.x;
+  long long t0 = A.profile ? clock64() : 0ll;
+  const long long tStart = t0;
   const int e0 = A.edgeStart ? A.edgeStart[prob] : A.edgeOfs[prob];
   const int E = A.edgeStart ? A.edgeCount[prob] : A.edgeOfs[prob + 1] - e0;
   __shared__ SE3d s_est, s_trial, s_init;
-  __shared__ double s_red[(PO_NT / 32) * 28];
+  __shared__ double s_red[(PO_VT / 32) * 28];
   __shared__ double s_H[36], s_b[6], s_x[6], s_A[36], s_tot[28];
   __shared__ int s_ok;
   const float* xw = A.xw + 3 * (size_t)e0;
@@ -589,10 +619,13 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
     for (int it = 0; it < 10 && ok; ++it) {
       // computeActiveErrors + activeRobustChi2 + buildSystem in one pass over the active edges
       double acc[28];
+      const SE3d est = s_est;
+      PO_TICK(5);
+      __syncthreads();                            // s_red is free (previous reduction read by everyone)
+      for (int v = tid; v < PO_VT; v += PO_NT) {
 #pragma unroll
       for (int k = 0; k < 28; ++k) acc[k] = 0;
-      const SE3d est = s_est;
-      for (int e = tid; e < E; e += PO_NT) {
+      for (int e = v; e < E; e += PO_VT) {
         if (outlier[e]) continue;                 // level-1 edges are not active
         const double X[3] = {(double)xw[3 * e], (double)xw[3 * e + 1], (double)xw[3 * e + 2]};
         double p[3], r[3], J[18];
@@ -619,12 +652,16 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
           }
         }
       }
-      // same fixed-shape tree as block_sum (lane butterfly, then warps in index order), but the cross-warp stage is
-      // done once by 28 threads instead of redundantly by all 256
-      block_partials<28>(acc, s_red);
+      // fixed-shape tree: lane butterfly per virtual warp, then the virtual warps in index order, the cross-warp stage
+      // done once by 28 threads
+      warp_partials<28>(acc, s_red, v >> 5);
+      }
+      PO_TICK(0);
+      PO_COUNT(8);
+      __syncthreads();
       if (tid < 28) {
         double s = 0;
-        for (int w = 0; w < PO_NT / 32; ++w) s += s_red[w * 28 + tid];
+        for (int w = 0; w < PO_VT / 32; ++w) s += s_red[w * 28 + tid];
         s_tot[tid] = s;
       }
       __syncthreads();
@@ -645,6 +682,7 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
         nBad = 0;
       }
       __syncthreads();
+      PO_TICK(1);
       double rho = 0;
       int qmax = 0;
       // The reference's damping policy (tau = 1e-50, up to 100 trials, optimization_algorithm_levenberg.cpp:47-51)
@@ -661,6 +699,8 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
           for (int i = 0; i < 6; ++i) same = same && (s_H[7 * i] + lambda == s_H[7 * i] + lastLambda);
         }
         if (!same) {
+          PO_TICK(5);
+          PO_COUNT(9);
           __syncthreads();                        // every thread is done with s_x / s_ok of the previous trial
           if (tid < 32) {                         // warp 0: 6x6 solve cooperatively, then lane 0 applies the update
             for (int i = tid; i < 36; i += 32) s_A[i] = s_H[i] + ((i % 7 == 0) ? lambda : 0.0);
@@ -675,9 +715,12 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
             }
           }
           __syncthreads();
+          PO_TICK(2);
           const SE3d trial = s_trial;
-          double chi[1] = {0};
-          for (int e = tid; e < E; e += PO_NT) {
+          double chi[1];
+          for (int v = tid; v < PO_VT; v += PO_NT) {
+          chi[0] = 0;
+          for (int e = v; e < E; e += PO_VT) {
             if (outlier[e]) continue;
             const double X[3] = {(double)xw[3 * e], (double)xw[3 * e + 1], (double)xw[3 * e + 2]};
             double p[3], r[3];
@@ -690,10 +733,21 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
             double w;
             chi[0] += robust ? huber_rho(st ? hStereo : hMono, c, w) : c;
           }
-          block_sum<1>(chi, s_red);
+          warp_partials<1>(chi, s_red, v >> 5);
+          }
+          PO_TICK(3);
+          __syncthreads();
+          {
+            double t = 0;
+            for (int w = 0; w < PO_VT / 32; ++w) t += s_red[w];
+            chi[0] = t;
+          }
+          PO_TICK(4);
           trialChi = chi[0];
           lastLambda = lambda;
           haveTrial = true;
+        } else {
+          PO_COUNT(10);
         }
         double tempChi = trialChi;
         if (!s_ok) tempChi = 1.7976931348623157e308;
@@ -725,6 +779,7 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
       if (nBad >= 3) ok = false;
     }
     if (tid == 0) iters[round] = cj;
+    PO_TICK(5);
     // ---------------- chi2 classification (src/Optimizer.cc:1157-1255) ----------------
     const SE3d est = s_est;
     double bad[1] = {0};
@@ -746,14 +801,21 @@ __global__ void __launch_bounds__(PO_NT, 2) pose_opt_kernel(const PoseOptArgs A)
     }
     block_sum<1>(bad, s_red);
     nBadFinal = (int)bad[0];
+    PO_TICK(6);
     if (round == 2) robust = false;               // e->setRobustKernel(0)
     if (E < 10) break;                            // optimizer.edges().size()<10
   }
   if (tid == 0) {
     se3_to_Tcw(s_est, A.Tcw + 16 * prob);
     A.nInliers[prob] = E - nBadFinal;
+    if (A.profile) {
+      atomicAdd(&g_po_prof[7], (unsigned long long)(clock64() - tStart));
+      atomicAdd(&g_po_prof[11], 1ull);
+    }
   }
 }
+
+static int g_po_profile = 0;   // test / tuning hook, off in production
 
 // =====================================================================================
 // K12  LocalBundleAdjustment: one CTA (1024 threads) per problem; all state in global/L2 scratch
@@ -1674,6 +1736,7 @@ int orbx_launch_pose_opt_slices(orbx_ctx* ctx, cudaStream_t st, int P, const int
   A.nInliers = d_ninl;
   A.iters = d_iters;
   A.err = d_scratch;
+  A.profile = g_po_profile;
   pose_opt_kernel<<<P, PO_NT, 0, st>>>(A);
   ORBX_LAUNCH(ctx);
   ORBX_CUDA(cudaGetLastError());
@@ -2571,6 +2634,21 @@ __global__ void __launch_bounds__(PLF_NT, 2) pose_inertial_lf_kernel(const PlfAr
 // =====================================================================================
 extern "C" {
 
+// Tuning hook: enable = 1 switches the per-phase cycle counters of pose_opt_kernel on (and clears them), 0 off;
+// out (may be null) receives the 16 totals accumulated so far (layout: g_po_prof above).
+int orbx_debug_pose_opt_profile(orbx_ctx* ctx, int enable, unsigned long long* out) {
+  if (!ctx) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(ctx->device));
+  ORBX_CUDA(cudaDeviceSynchronize());
+  if (out) ORBX_CUDA(cudaMemcpyFromSymbol(out, g_po_prof, sizeof(unsigned long long) * 16));
+  if (enable) {
+    unsigned long long z[16] = {0};
+    ORBX_CUDA(cudaMemcpyToSymbol(g_po_prof, z, sizeof z));
+  }
+  g_po_profile = enable ? 1 : 0;
+  return ORBX_OK;
+}
+
 int orbx_pose_optimization_batch_device(orbx_ctx* ctx, int P, const int32_t* d_edge_ofs, const float* d_xw,
                                         const float* d_obs, const float* d_inv_sigma2, const orbx_camera* cam,
                                         float* d_Tcw, uint8_t* d_outlier, int32_t* d_n_inliers, int32_t* d_iters,
@@ -2592,6 +2670,7 @@ int orbx_pose_optimization_batch_device(orbx_ctx* ctx, int P, const int32_t* d_e
   A.nInliers = d_n_inliers;
   A.iters = d_iters;
   A.err = d_scratch;
+  A.profile = g_po_profile;
   pose_opt_kernel<<<P, PO_NT, 0, ctx->stream>>>(A);
   ORBX_LAUNCH(ctx);
   ORBX_CUDA(cudaGetLastError());

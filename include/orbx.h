@@ -142,6 +142,12 @@ int orbx_debug_blur_level(orbx_ext *ext, int b, int level, uint8_t *dst, int dst
 int orbx_debug_candidates(orbx_ext *ext, int b, int level, int16_t *xy, uint8_t *score,
                           int cap, int *n_out);
 
+/* Tuning hook: per-phase SM-cycle totals of the PoseOptimization kernel (0 build pass, 1 reduction, 2 solve + exp,
+ * 3 trial residual pass, 4 trial reduction, 5 accept/reject logic, 6 chi2 classification, 7 whole kernel; counts:
+ * 8 builds, 9 solved trials, 10 replayed trials, 11 CTAs).  enable = 1 clears and starts, 0 stops; `out` (16 values,
+ * may be NULL) receives the totals accumulated so far.  Synchronises the device. */
+int orbx_debug_pose_opt_profile(orbx_ctx *ctx, int enable, unsigned long long *out);
+
 /* ====================================================================================
  * Matchers.  A Frame / KeyFrame crosses the boundary as flat arrays (the shim flattens the
  * reference's pointer graph once per call, under the same mutexes the reference takes).
