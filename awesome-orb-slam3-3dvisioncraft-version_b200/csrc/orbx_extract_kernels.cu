@@ -1012,9 +1012,11 @@ __device__ __forceinline__ int dp4a_us(unsigned a, unsigned b_s8, int c) {   // 
 
 #define DESC_KPW 4                        // keypoints a warp processes one after the other
 #define DESC_OW 9                         // words per staged row of the un-blurred 31x31 patch (31 + <=3 bytes of misalignment)
-#define DESC_BW 10                        // words per staged row of the blurred 37x37 patch (the rotated pattern reaches +-18)
+#define DESC_BW 20                        // words per staged row of the blurred 37x37 patch (the rotated pattern reaches +-18):
+                                          // four 16-byte quads from the 16-byte aligned column at or left of px - 18 (<= 15 + 37
+                                          // bytes), padded to 20 words so that the rows spread over the banks
 #define DESC_OWORDS (31 * DESC_OW + 1)
-#define DESC_BWORDS (37 * DESC_BW + 2)
+#define DESC_BWORDS (37 * DESC_BW)
 
 // The kernel used to be bound by the L1 data pipe (87 % of its wavefront peak, profiles/r02m): a warp's 9 patch-row loads
 // touched 31 cache lines each and its 16 byte gathers ~25.  Both patches are now brought in by row-major word loads (a
@@ -1024,17 +1026,21 @@ __global__ void __launch_bounds__(DESC_NT, 5) describe_kernel(const __grid_const
                                                            uint8_t* desc, int cap, int* nOut, int* monoOut) {
   // lanes of a warp read 32 different pattern rows: stage the table in shared memory (constant
   // memory would serialise the divergent addresses)
-  __shared__ int s_pat[256];
+  __shared__ float4 s_pat[256];
   // IC_Angle weights: row |v| of the r=15 disc covers u in [-umax[v], umax[v]].  For the 32 bytes u = -15..16 of a
   // patch row, s_icw[v*17 + j] packs the signed weights u (0 outside the disc) of bytes 4j..4j+3 and
   // s_icw[v*17 + 8 + j] the 0/1 membership mask (stride 17: rows of different lanes fall into different banks)
   __shared__ unsigned s_icw[16 * 17];
   __shared__ int s_cnt[2 * ORBX_MAX_LEVELS];
+  __shared__ int s_pre[2 * (ORBX_MAX_LEVELS + 1)];     // exclusive prefix sums of s_cnt: keypoints / lapping keypoints before level l
   __shared__ uint32_t s_org[DESC_NT / 32][DESC_OWORDS];
-  __shared__ uint32_t s_blr[DESC_NT / 32][DESC_BWORDS];
+  __shared__ __align__(16) uint32_t s_blr[DESC_NT / 32][DESC_BWORDS];
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x)   // transposed: word (byte row r, pair k) at [k*32 + r]
-    s_pat[(i & 7) * 32 + (i >> 3)] = reinterpret_cast<const int*>(c_pattern)[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {  // transposed: pair (byte row r, pair k) at [k*32 + r], as floats
+    const int pw = reinterpret_cast<const int*>(c_pattern)[i];
+    s_pat[(i & 7) * 32 + (i >> 3)] = make_float4((float)(int8_t)(pw & 0xff), (float)(int8_t)((pw >> 8) & 0xff),
+                                                  (float)(int8_t)((pw >> 16) & 0xff), (float)(int8_t)((pw >> 24) & 0xff));
+  }
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     const int v = i >> 4, j = i & 7, isMask = (i >> 3) & 1;
     const int d = c_umax[v];
@@ -1052,11 +1058,15 @@ __global__ void __launch_bounds__(DESC_NT, 5) describe_kernel(const __grid_const
   }
   __syncthreads();
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int total = 0, totalLap = 0;
-  for (int l = 0; l < p.nlevels; ++l) {
-    total += s_cnt[2 * l];
-    totalLap += s_cnt[2 * l + 1];
+  if (threadIdx.x < 2) {
+    int acc = 0;
+    for (int l = 0; l <= ORBX_MAX_LEVELS; ++l) {
+      s_pre[2 * l + threadIdx.x] = acc;
+      if (l < p.nlevels) acc += s_cnt[2 * l + threadIdx.x];
+    }
   }
+  __syncthreads();
+  const int total = s_pre[2 * ORBX_MAX_LEVELS], totalLap = s_pre[2 * ORBX_MAX_LEVELS + 1];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     nOut[b] = min(total, cap);
     monoOut[b] = total - totalLap;
@@ -1064,7 +1074,6 @@ __global__ void __launch_bounds__(DESC_NT, 5) describe_kernel(const __grid_const
   }
   // lane -> (row, word) of the first staging round of either patch; every further round advances by 32 words
   const int oRow0 = lane / DESC_OW, oCol0 = lane - oRow0 * DESC_OW;
-  const int bRow0 = lane / DESC_BW, bCol0 = lane - bRow0 * DESC_BW;
   uint32_t* so = s_org[wid];
   uint32_t* sb = s_blr[wid];
   const uint8_t* sbBytes = reinterpret_cast<const uint8_t*>(sb);
@@ -1074,23 +1083,11 @@ __global__ void __launch_bounds__(DESC_NT, 5) describe_kernel(const __grid_const
     const int kp = blockIdx.x * ((DESC_NT / 32) * DESC_KPW) + it * (DESC_NT / 32) + wid;   // warp-uniform
     if (kp >= total) break;
     // locate (level, i) of this keypoint and the counts it needs for its output slot
-    int level = 0, idx = 0, base = 0, lapBefore = 0;
-    {
-      int acc = 0, lapAcc = 0;
-      bool found = false;
-      for (int l = 0; l < p.nlevels; ++l) {
-        const int nl = s_cnt[2 * l];
-        if (!found && kp < acc + nl) {
-          found = true;
-          level = l;
-          idx = kp - acc;
-          base = acc;
-          lapBefore = lapAcc;
-        }
-        acc += nl;
-        lapAcc += s_cnt[2 * l + 1];
-      }
-    }
+    int level = 0;
+#pragma unroll
+    for (int l = 1; l < ORBX_MAX_LEVELS; ++l) level += (kp >= s_pre[2 * l]) ? 1 : 0;   // prefix entries past nlevels equal total > kp
+    const int base = s_pre[2 * level], lapBefore = s_pre[2 * level + 1];
+    const int idx = kp - base;
     const LevelParams& L = p.lv[level];
     const uint2 rec = p.sel[(size_t)b * p.selPerImage + L.selOfs + idx];
     const int px = rec.x & 0xffff, py = rec.x >> 16;
@@ -1100,7 +1097,7 @@ __global__ void __launch_bounds__(DESC_NT, 5) describe_kernel(const __grid_const
     //     caller memory with any stride, so each row is aligned on its own; the blurred plane has a 64-byte pitch ---
     const uint8_t* img = L.pyr + (size_t)b * L.imgStride + (size_t)(py - 15) * L.pitch + (px - 15);
     const uint8_t* blb = L.blur + (size_t)b * L.blurStride + (size_t)(py - 18) * L.blurPitch + (px - 18);
-    const unsigned bmis = (unsigned)(reinterpret_cast<uintptr_t>(blb) & 3);
+    const unsigned bmis = (unsigned)(reinterpret_cast<uintptr_t>(blb) & 15);    // the blurred plane is 64-byte aligned
     blb -= bmis;
     const unsigned imgLo = (unsigned)reinterpret_cast<uintptr_t>(img);
     __syncwarp();                                 // the previous keypoint's readers are done with so / sb
@@ -1117,14 +1114,12 @@ __global__ void __launch_bounds__(DESC_NT, 5) describe_kernel(const __grid_const
         r += 32 / DESC_OW;
         if (c >= DESC_OW) { c -= DESC_OW; ++r; }
       }
-      r = bRow0;
-      c = bCol0;
 #pragma unroll
-      for (int t = 0; t < (37 * DESC_BW + 31) / 32; ++t) {
-        if (r < 37) sb[r * DESC_BW + c] = __ldg(reinterpret_cast<const uint32_t*>(blb + ((unsigned)r * (unsigned)L.blurPitch + 4u * (unsigned)c)));
-        c += 32 % DESC_BW;
-        r += 32 / DESC_BW;
-        if (c >= DESC_BW) { c -= DESC_BW; ++r; }
+      for (int t = 0; t < (37 * 4 + 31) / 32; ++t) {
+        const int q = t * 32 + lane, br = q >> 2, bc = q & 3;           // quad bc of patch row br
+        if (br < 37)
+          *reinterpret_cast<uint4*>(sb + br * DESC_BW + 4 * bc) =
+              __ldg(reinterpret_cast<const uint4*>(blb + ((unsigned)br * (unsigned)L.blurPitch + 16u * (unsigned)bc)));
       }
     }
     __syncwarp();
@@ -1168,9 +1163,8 @@ __global__ void __launch_bounds__(DESC_NT, 5) describe_kernel(const __grid_const
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int pw = s_pat[k * 32 + lane];   // (x0,y0,x1,y1) packed int8
-      const float x0 = (float)(int8_t)(pw & 0xff), y0 = (float)(int8_t)((pw >> 8) & 0xff);
-      const float x1 = (float)(int8_t)((pw >> 16) & 0xff), y1 = (float)(int8_t)((pw >> 24) & 0xff);
+      const float4 pw = s_pat[k * 32 + lane];   // (x0,y0,x1,y1)
+      const float x0 = pw.x, y0 = pw.y, x1 = pw.z, y1 = pw.w;
       const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, bsn), __fmul_rn(y0, a)));
       const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bsn)));
       const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bsn), __fmul_rn(y1, a)));
