@@ -38,6 +38,27 @@ struct orbx_ctx {
   std::vector<struct orbx_frame*> residentFrames;
 };
 
+// Device-resident arguments of the visual-inertial pose optimisers when the tracker drives them (orbx_optimize.cu:
+// orbx_launch_pose_inertial_slices).  Every pointer is device memory; per-stream arrays carry a leading [S] dimension.
+struct OrbxInertialSlices {
+  int mode;                 // 1: PoseInertialOptimizationLastKeyFrame, 2: PoseInertialOptimizationLastFrame
+  int S, recInit;
+  float fx, fy, cx, cy, bf;
+  const int *estart, *ecount;               // edge slices
+  const float *exw, *eobs, *eisg;
+  const uint8_t* eclose;
+  uint8_t* eoutlier;
+  double* err;                              // [3 * edges] scratch
+  const float* T1;                          // [S][16] frame pose before the optimisation (pFrame->mTcw)
+  const float *Tcb, *Tbc;                   // [16]
+  const float* vel;                         // [S][3] pFrame->mVw
+  const float* bias;                        // [S][6] pFrame->mImuBias, gyro xyz then acc xyz
+  const double *ref, *preint, *preintJac, *preintBias, *infoI, *infoG, *infoA, *priorState, *priorH;
+  double *stateOut, *H15;                   // [S][21], [S][225]
+  int *nRet, *iters;                        // [S], [S][4]
+  float* T2;                                // [S][16] pose after Frame::SetImuPoseVelocity
+};
+
 #define ORBX_LAUNCH(ctx) ((ctx)->launches.fetch_add(1, std::memory_order_relaxed))
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }

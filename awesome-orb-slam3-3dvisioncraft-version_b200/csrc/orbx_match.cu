@@ -925,7 +925,8 @@ static void tri_epipolar_geometry(const orbx_camera* cam1, const orbx_camera* ca
   A.epy = cam2->fy * C2[1] / C2[2] + cam2->cy;
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j)
-      R12[i * 3 + j] = R1w[i * 3 + 0] * R2w[j * 3 + 0] + R1w[i * 3 + 1] * R2w[j * 3 + 1] + R1w[i * 3 + 2] * R2w[j * 3 + 2];
+      R12[i * 3 + j] = (float)((double)R1w[i * 3 + 0] * (double)R2w[j * 3 + 0] + (double)R1w[i * 3 + 1] * (double)R2w[j * 3 + 1] +
+                               (double)R1w[i * 3 + 2] * (double)R2w[j * 3 + 2]);   // R1w*R2w.t(): gemm general path (double accumulation)
   for (int i = 0; i < 3; ++i) t12[i] = -(R12[i * 3 + 0] * t2w[0] + R12[i * 3 + 1] * t2w[1] + R12[i * 3 + 2] * t2w[2]) + t1w[i];
   const float tx[9] = {0, -t12[2], t12[1], t12[2], 0, -t12[0], -t12[1], t12[0], 0};
   for (int i = 0; i < 3; ++i)
@@ -1088,7 +1089,8 @@ int orbx_search_by_projection_frame(orbx_ctx* ctx, const orbx_frame_desc* cur, c
     const float* Tc = Tcw_cur;
     const float* Tl = Tcw_last;
     float twc[3];
-    for (int i = 0; i < 3; ++i) twc[i] = -(Tc[0 * 4 + i] * Tc[3] + Tc[1 * 4 + i] * Tc[7] + Tc[2 * 4 + i] * Tc[11]);
+    for (int i = 0; i < 3; ++i)   // -Rcw.t()*tcw: cv::gemm's general path (transposed operand): double accumulation, one rounding
+      twc[i] = (float)(-((double)Tc[0 * 4 + i] * (double)Tc[3] + (double)Tc[1 * 4 + i] * (double)Tc[7] + (double)Tc[2 * 4 + i] * (double)Tc[11]));
     const float tlcz = Tl[8] * twc[0] + Tl[9] * twc[1] + Tl[10] * twc[2] + Tl[11];
     const bool fwd = tlcz > cam->b && !bMono, bwd = -tlcz > cam->b && !bMono;
     A.mode = fwd ? 1 : (bwd ? 2 : 0);

@@ -2630,6 +2630,125 @@ __global__ void __launch_bounds__(PLF_NT, 2) pose_inertial_lf_kernel(const PlfAr
 }
 
 // =====================================================================================
+// K20/K21 driven from the tracker (SURVEY.md §8 f3 + e; src/Tracking.cc:2974-2990): the per-problem argument blocks are
+// filled ON THE DEVICE from the tracker's buffers -- the frame's body state is derived from the pose the first
+// PoseOptimization left (Frame::GetImuRotation / GetImuPosition, src/Frame.cc:534-554, float cv::Mat arithmetic:
+// ((a0*b0 + a1*b1) + a2*b2) for plain products, double accumulation where an operand is a lazy transpose) -- and the optimised state is written back as the
+// frame's Tcw the way Frame::SetImuPoseVelocity does it (src/Frame.cc:520-530: double -> float, Tbw, Tcb * Tbw).
+// =====================================================================================
+template <class ARGS>
+__device__ void inertial_fill_common(ARGS& A, const OrbxInertialSlices& I, int s) {
+  const int o = I.estart[s];
+  A.E = I.ecount[s];
+  A.xw = I.exw + 3 * (size_t)o; A.obs = I.eobs + 3 * (size_t)o; A.invSigma2 = I.eisg + o; A.closePt = I.eclose + o;
+  A.fx = I.fx; A.fy = I.fy; A.cx = I.cx; A.cy = I.cy; A.bf = I.bf;
+  const float* T = I.T1 + 16 * (size_t)s;
+  const float* Tcb = I.Tcb;
+  float Rwc[9], tcw[3], Ow[3];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      A.Rcb[i * 3 + j] = Tcb[i * 4 + j]; A.Rbc[j * 3 + i] = Tcb[i * 4 + j]; A.Rcw0[i * 3 + j] = T[i * 4 + j];
+      Rwc[j * 3 + i] = T[i * 4 + j];
+    }
+    A.tcb[i] = Tcb[i * 4 + 3]; A.tbc[i] = I.Tbc[i * 4 + 3]; A.tcw0[i] = T[i * 4 + 3];
+    tcw[i] = T[i * 4 + 3];
+  }
+  for (int i = 0; i < 3; ++i)   // mOw = -mRcw.t()*mtcw: gemm's general path (transposed operand), double accumulation
+    Ow[i] = (float)(-((double)Rwc[i * 3] * (double)tcw[0] + (double)Rwc[i * 3 + 1] * (double)tcw[1] + (double)Rwc[i * 3 + 2] * (double)tcw[2]));
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)                                  // GetImuRotation: mRwc * Rcb
+      A.state[i * 3 + j] = (double)((Rwc[i * 3] * Tcb[j] + Rwc[i * 3 + 1] * Tcb[4 + j]) + Rwc[i * 3 + 2] * Tcb[8 + j]);
+    // GetImuPosition: mRwc * tcb + mOw
+    A.state[9 + i] = (double)(((Rwc[i * 3] * Tcb[3] + Rwc[i * 3 + 1] * Tcb[7]) + Rwc[i * 3 + 2] * Tcb[11]) + Ow[i]);
+    A.state[12 + i] = (double)I.vel[3 * (size_t)s + i];
+  }
+  for (int i = 0; i < 6; ++i) A.state[15 + i] = (double)I.bias[6 * (size_t)s + i];
+  for (int i = 0; i < 81; ++i) A.infoI[i] = I.infoI[81 * (size_t)s + i];
+  for (int i = 0; i < 9; ++i) { A.infoG[i] = I.infoG[9 * (size_t)s + i]; A.infoA[i] = I.infoA[9 * (size_t)s + i]; }
+  A.recInit = I.recInit;
+  A.outlier = I.eoutlier + o;
+  A.err = I.err + 3 * (size_t)o;
+  A.outState = I.stateOut + 21 * (size_t)s;
+  A.H15 = I.H15 + 225 * (size_t)s;
+  A.nRet = I.nRet + s;
+  A.iters = I.iters + 4 * (size_t)s;
+}
+
+__global__ void inertial_fill_kf_kernel(const OrbxInertialSlices I, PioArgs* args) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= I.S) return;
+  PioArgs& A = args[s];
+  inertial_fill_common(A, I, s);
+  const double* pr = I.preint + 16 * (size_t)s;
+  for (int i = 0; i < 21; ++i) A.kf[i] = I.ref[21 * (size_t)s + i];
+  for (int i = 0; i < 9; ++i) A.dR[i] = pr[i];
+  for (int i = 0; i < 3; ++i) { A.dV[i] = pr[9 + i]; A.dP[i] = pr[12 + i]; }
+  A.dt = pr[15];
+}
+
+__global__ void inertial_fill_lf_kernel(const OrbxInertialSlices I, PlfArgs* args) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= I.S) return;
+  PlfArgs& A = args[s];
+  inertial_fill_common(A, I, s);
+  const double* pr = I.preint + 16 * (size_t)s;
+  const double* pj = I.preintJac + 45 * (size_t)s;
+  for (int i = 0; i < 21; ++i) { A.prev[i] = I.ref[21 * (size_t)s + i]; A.prior[i] = I.priorState[21 * (size_t)s + i]; }
+  for (int i = 0; i < 9; ++i) {
+    A.dR0[i] = pr[i];
+    A.JRg[i] = pj[i]; A.JVg[i] = pj[9 + i]; A.JVa[i] = pj[18 + i]; A.JPg[i] = pj[27 + i]; A.JPa[i] = pj[36 + i];
+  }
+  for (int i = 0; i < 3; ++i) { A.dV0[i] = pr[9 + i]; A.dP0[i] = pr[12 + i]; }
+  A.dt = pr[15];
+  for (int i = 0; i < 6; ++i) A.bpre[i] = I.preintBias[6 * (size_t)s + i];
+  for (int i = 0; i < 225; ++i) A.Hp[i] = I.priorH[225 * (size_t)s + i];
+  A.prof = nullptr;
+}
+
+// Frame::SetImuPoseVelocity (src/Frame.cc:520-530) on the optimised state: Tcw = Tcb * [Rwb^T | -Rwb^T twb] in float
+__global__ void inertial_finish_kernel(const OrbxInertialSlices I) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= I.S) return;
+  const double* st = I.stateOut + 21 * (size_t)s;
+  float Tbw[16];
+  float twb[3];
+  for (int i = 0; i < 3; ++i) twb[i] = (float)st[9 + i];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Tbw[i * 4 + j] = (float)st[j * 3 + i];                  // Rbw = Rwb.t()
+  for (int i = 0; i < 3; ++i) Tbw[i * 4 + 3] = -((Tbw[i * 4] * twb[0] + Tbw[i * 4 + 1] * twb[1]) + Tbw[i * 4 + 2] * twb[2]);
+  Tbw[12] = Tbw[13] = Tbw[14] = 0.f;
+  Tbw[15] = 1.f;
+  float* T = I.T2 + 16 * (size_t)s;
+  const float* Tcb = I.Tcb;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      T[i * 4 + j] = ((Tcb[i * 4] * Tbw[j] + Tcb[i * 4 + 1] * Tbw[4 + j]) + Tcb[i * 4 + 2] * Tbw[8 + j]) + Tcb[i * 4 + 3] * Tbw[12 + j];
+}
+
+size_t orbx_inertial_args_bytes(int S) { return (size_t)S * (sizeof(PioArgs) > sizeof(PlfArgs) ? sizeof(PioArgs) : sizeof(PlfArgs)); }
+
+// internal (orbx_track.cu): S problems on fixed-capacity edge slices, everything device-resident
+int orbx_launch_pose_inertial_slices(orbx_ctx* ctx, cudaStream_t st, const OrbxInertialSlices& I, void* d_args) {
+  if (I.mode != 1 && I.mode != 2) return ORBX_EINVAL;
+  const int nb = (I.S + 63) / 64;
+  if (I.mode == 1) {
+    inertial_fill_kf_kernel<<<nb, 64, 0, st>>>(I, (PioArgs*)d_args);
+    ORBX_LAUNCH(ctx);
+    pose_inertial_kernel<<<I.S, PIO_NT, 0, st>>>((const PioArgs*)d_args);
+    ORBX_LAUNCH(ctx);
+  } else {
+    inertial_fill_lf_kernel<<<nb, 64, 0, st>>>(I, (PlfArgs*)d_args);
+    ORBX_LAUNCH(ctx);
+    pose_inertial_lf_kernel<<<I.S, PLF_NT, 0, st>>>((const PlfArgs*)d_args);
+    ORBX_LAUNCH(ctx);
+  }
+  inertial_finish_kernel<<<nb, 64, 0, st>>>(I);
+  ORBX_LAUNCH(ctx);
+  ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+// =====================================================================================
 // host entry points
 // =====================================================================================
 extern "C" {

@@ -30,6 +30,8 @@ int orbx_ext_pyramid_view(orbx_ext* e, int b, int* nlevels, const uint8_t** ptr,
 int orbx_launch_pose_opt_slices(orbx_ctx* ctx, cudaStream_t st, int P, const int* d_start, const int* d_count, const float* d_xw,
                                 const float* d_obs, const float* d_isg, const orbx_camera* cam, float* d_Tcw, uint8_t* d_outlier,
                                 int* d_ninl, int* d_iters, double* d_scratch);
+size_t orbx_inertial_args_bytes(int S);                          // orbx_optimize.cu
+int orbx_launch_pose_inertial_slices(orbx_ctx* ctx, cudaStream_t st, const OrbxInertialSlices& I, void* d_args);
 
 struct TrackDev {
   int S, cap;
@@ -61,6 +63,7 @@ struct TrackDev {
   float *exw, *eobs, *eisg;
   int *ekp, *ecount, *estart, *kpEdge;
   uint8_t* eoutlier;
+  uint8_t* eclose;            // pMP->mTrackDepth < 10 (given map: bit 2 of map_flags), read by the inertial optimisers
   int *ninl, *iters;
   // local-map search
   uint8_t *blocked, *mpTaken, *mapFlags;
@@ -140,6 +143,7 @@ __global__ void __launch_bounds__(256) gather_edges_kernel(const TrackDev D, int
       D.eobs[3 * e + 1] = kp.y;
       D.eobs[3 * e + 2] = D.uright[base + i];
       D.eisg[e] = D.invSigma2[kp.octave];
+      D.eclose[e] = D.useMap ? ((D.gMapFlags[mb + q] >> 2) & 1) : 0;
       D.ekp[e] = i;
     }
     __syncthreads();
@@ -204,8 +208,11 @@ __global__ void __launch_bounds__(128) frustum_map_kernel(const TrackDev D, floa
   uint8_t fl = 0;
   if (q < D.nMap[s] && (D.gMapFlags[o] & 1) && !D.mpTaken[o]) {
     const float* T = D.T1 + 16 * s;
-    const float Ow0 = -(T[0] * T[3] + T[4] * T[7] + T[8] * T[11]), Ow1 = -(T[1] * T[3] + T[5] * T[7] + T[9] * T[11]),
-                Ow2 = -(T[2] * T[3] + T[6] * T[7] + T[10] * T[11]);
+    // Frame::UpdatePoseMatrices: mOw = -mRcw.t()*mtcw (src/Frame.cc:543) -- the transposed operand sends cv::gemm down its
+    // general path: products and sum in double, rounded to float once
+    const float Ow0 = (float)(-((double)T[0] * (double)T[3] + (double)T[4] * (double)T[7] + (double)T[8] * (double)T[11])),
+                Ow1 = (float)(-((double)T[1] * (double)T[3] + (double)T[5] * (double)T[7] + (double)T[9] * (double)T[11])),
+                Ow2 = (float)(-((double)T[2] * (double)T[3] + (double)T[6] * (double)T[7] + (double)T[10] * (double)T[11]));
     const float X = D.xw[3 * o], Y = D.xw[3 * o + 1], Z = D.xw[3 * o + 2];
     const float xc = T[0] * X + T[1] * Y + T[2] * Z + T[3];
     const float yc = T[4] * X + T[5] * Y + T[6] * Z + T[7];
@@ -319,6 +326,10 @@ struct TrackSlot {
   // of step t has finished, while step t+1's map is already being uploaded into the other slot
   uint8_t* mapBuf = nullptr;
   cudaEvent_t evMap = nullptr;
+  // device copy of host-side inertial inputs (orbx_tracker_upload_inertial), per slot like the map
+  uint8_t* imuBuf = nullptr;
+  cudaEvent_t evImu = nullptr;
+  bool imuPending = false;    // stream B has to wait for evImu before it reads imuBuf
 };
 
 struct orbx_tracker {
@@ -362,6 +373,10 @@ struct orbx_tracker {
   unsigned long long mapVersion = 0;
   bool chain = false;
   float* d_Tlast = nullptr;
+  // visual-inertial TrackLocalMap (src/Tracking.cc:2974-2990): mode 0 off, 1 LastKeyFrame, 2 LastFrame
+  orbx_track_imu imu{};
+  void* d_imuArgs = nullptr;                   // argument blocks of the inertial kernels
+  double *d_imuState = nullptr, *d_imuH = nullptr;   // [S][21], [S][225] results (also readable as the next step's prior)
   // keyframe-rate work (LocalMapping's share: CreateNewMapPoints searches + LocalBundleAdjustment of every stream),
   // enqueued every kfPeriod-th step on its own lowest-priority stream
   orbx_tri_batch* kfTri = nullptr;
@@ -411,6 +426,7 @@ static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float th
   D.exw = talloc<float>(t, 3 * SC); D.eobs = talloc<float>(t, 3 * SC); D.eisg = talloc<float>(t, SC);
   D.ekp = talloc<int>(t, SC); D.ecount = talloc<int>(t, S); D.estart = talloc<int>(t, S); D.kpEdge = talloc<int>(t, SC);
   D.eoutlier = talloc<uint8_t>(t, SC);
+  D.eclose = talloc<uint8_t>(t, SC);
   D.ninl = talloc<int>(t, 2 * S); D.iters = talloc<int>(t, 8 * S);
   D.blocked = talloc<uint8_t>(t, SC); D.mpTaken = talloc<uint8_t>(t, SM); D.mapFlags = talloc<uint8_t>(t, SM);
   D.projX = talloc<float>(t, SM); D.projY = talloc<float>(t, SM); D.projXR = talloc<float>(t, SM); D.viewCos = talloc<float>(t, SM);
@@ -625,6 +641,122 @@ int orbx_tracker_set_keyframe_work(orbx_tracker* t, orbx_tri_batch* tri, orbx_lb
   t->kfRuns = 0;
   return ORBX_OK;
 }
+
+// ---- visual-inertial TrackLocalMap ----
+static bool imu_complete(const orbx_track_imu* u) {
+  if (u->mode != 1 && u->mode != 2) return false;
+  if (!u->Tcb || !u->Tbc || !u->velocity || !u->bias || !u->ref_state || !u->preint || !u->info_inertial || !u->info_gyro || !u->info_acc)
+    return false;
+  if (u->mode == 2 && (!u->preint_jac || !u->preint_bias || !u->prior_state || !u->prior_H)) return false;
+  return true;
+}
+static int imu_ensure_buffers(orbx_tracker* t) {
+  if (t->d_imuArgs) return ORBX_OK;
+  t->d_imuArgs = talloc<uint8_t>(t, orbx_inertial_args_bytes(t->S));
+  t->d_imuState = talloc<double>(t, 21 * (size_t)t->S);
+  t->d_imuH = talloc<double>(t, 225 * (size_t)t->S);
+  if (!t->d_imuArgs || !t->d_imuState || !t->d_imuH) return ORBX_ECUDA;
+  ORBX_CUDA(cudaMemset(t->d_imuState, 0, sizeof(double) * 21 * t->S));
+  ORBX_CUDA(cudaMemset(t->d_imuH, 0, sizeof(double) * 225 * t->S));
+  return ORBX_OK;
+}
+
+// Bind DEVICE-resident inertial inputs for the following steps (NULL or mode 0: back to the visual PoseOptimization).
+// The arrays are read when the step's stage B runs; they must stay valid and unchanged until then.
+int orbx_tracker_set_inertial(orbx_tracker* t, const orbx_track_imu* imu) {
+  if (!t) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  if (!imu || imu->mode == 0) {
+    t->imu = orbx_track_imu{};
+    return ORBX_OK;
+  }
+  if (!imu_complete(imu)) {
+    orbx_set_error("orbx_tracker_set_inertial: mode must be 1 or 2 and every array of that mode non-null");
+    return ORBX_EINVAL;
+  }
+  int rc = imu_ensure_buffers(t);
+  if (rc != ORBX_OK) return rc;
+  t->imu = *imu;
+  return ORBX_OK;
+}
+
+// HOST-side inertial inputs -> the next step's slot (asynchronous, on the copy stream when the submit/collect pipeline is
+// in use), then bound like orbx_tracker_set_inertial.  prior_state / prior_H may be NULL in mode 2: the tracker then uses
+// the state and the marginalised Hessian the PREVIOUS step left on the device (the reference's pFp->mpcpi chain,
+// src/Optimizer.cc:8594-8599).
+int orbx_tracker_upload_inertial(orbx_tracker* t, const orbx_track_imu* h) {
+  if (!t || !h) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  int rc = imu_ensure_buffers(t);
+  if (rc != ORBX_OK) return rc;
+  orbx_track_imu probe = *h;
+  if (h->mode == 2 && !h->prior_state && !h->prior_H) { probe.prior_state = t->d_imuState; probe.prior_H = t->d_imuH; }
+  if (h->mode == 2 && !h->ref_state) probe.ref_state = t->d_imuState;
+  if (!imu_complete(&probe)) {
+    orbx_set_error("orbx_tracker_upload_inertial: mode must be 1 or 2 and every array of that mode non-null");
+    return ORBX_EINVAL;
+  }
+  const bool overlap = t->stB != t->stA;
+  TrackSlot& K = t->slot[overlap ? (int)(t->stepCount & 1) : 0];
+  const size_t S = (size_t)t->S;
+  // layout (bytes): Tcb, Tbc | vel | bias | ref | preint | jac | pbias | infoI | infoG | infoA | priorState | priorH
+  const size_t oT = 0, oV = 128, oB = align_up(oV + 12 * S, 256), oR = align_up(oB + 24 * S, 256), oP = oR + 8 * 21 * S,
+               oJ = oP + 8 * 16 * S, oPb = oJ + 8 * 45 * S, oI = oPb + 8 * 6 * S, oG = oI + 8 * 81 * S, oA = oG + 8 * 9 * S,
+               oPs = oA + 8 * 9 * S, oPh = oPs + 8 * 21 * S, total = oPh + 8 * 225 * S;
+  if (!K.imuBuf) {
+    K.imuBuf = talloc<uint8_t>(t, total);
+    if (!K.imuBuf || cudaEventCreateWithFlags(&K.evImu, cudaEventDisableTiming) != cudaSuccess) return ORBX_ECUDA;
+  }
+  cudaStream_t sc = t->stC ? t->stC : t->stA;
+  if (overlap && K.usedB) ORBX_CUDA(cudaStreamWaitEvent(sc, K.evB, 0));   // the slot's previous inputs are no longer read
+  uint8_t* b = K.imuBuf;
+  auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+    return src ? cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyHostToDevice, sc) : cudaSuccess;
+  };
+  ORBX_CUDA(up(oT, h->Tcb, 64));
+  ORBX_CUDA(up(oT + 64, h->Tbc, 64));
+  ORBX_CUDA(up(oV, h->velocity, 12 * S));
+  ORBX_CUDA(up(oB, h->bias, 24 * S));
+  ORBX_CUDA(up(oR, h->ref_state, 8 * 21 * S));
+  ORBX_CUDA(up(oP, h->preint, 8 * 16 * S));
+  ORBX_CUDA(up(oI, h->info_inertial, 8 * 81 * S));
+  ORBX_CUDA(up(oG, h->info_gyro, 8 * 9 * S));
+  ORBX_CUDA(up(oA, h->info_acc, 8 * 9 * S));
+  if (h->mode == 2) {
+    ORBX_CUDA(up(oJ, h->preint_jac, 8 * 45 * S));
+    ORBX_CUDA(up(oPb, h->preint_bias, 8 * 6 * S));
+    ORBX_CUDA(up(oPs, h->prior_state, 8 * 21 * S));
+    ORBX_CUDA(up(oPh, h->prior_H, 8 * 225 * S));
+  }
+  ORBX_CUDA(cudaEventRecord(K.evImu, sc));
+  K.imuPending = true;
+  orbx_track_imu d{};
+  d.mode = h->mode; d.rec_init = h->rec_init;
+  d.Tcb = (const float*)(b + oT); d.Tbc = (const float*)(b + oT + 64);
+  d.velocity = (const float*)(b + oV); d.bias = (const float*)(b + oB);
+  d.ref_state = (h->ref_state || h->mode != 2) ? (const double*)(b + oR) : t->d_imuState; d.preint = (const double*)(b + oP); d.preint_jac = (const double*)(b + oJ);
+  d.preint_bias = (const double*)(b + oPb); d.info_inertial = (const double*)(b + oI); d.info_gyro = (const double*)(b + oG);
+  d.info_acc = (const double*)(b + oA);
+  d.prior_state = h->prior_state ? (const double*)(b + oPs) : t->d_imuState;
+  d.prior_H = h->prior_H ? (const double*)(b + oPh) : t->d_imuH;
+  t->imu = d;
+  return ORBX_OK;
+}
+
+// Results of the last inertial step: the optimised body states [S][21] (Rwb, twb, v, bg, ba) and the 15x15 Hessians
+// [S][225] for the next ConstraintPoseImu; either pointer may be NULL.  Synchronises the tracker's streams.
+int orbx_tracker_inertial_result(orbx_tracker* t, double* state, double* H15) {
+  if (!t || !t->d_imuState) return ORBX_EINVAL;
+  int rc = orbx_tracker_synchronize(t);
+  if (rc != ORBX_OK) return rc;
+  if (state) ORBX_CUDA(cudaMemcpy(state, t->d_imuState, sizeof(double) * 21 * t->S, cudaMemcpyDeviceToHost));
+  if (H15) ORBX_CUDA(cudaMemcpy(H15, t->d_imuH, sizeof(double) * 225 * t->S, cudaMemcpyDeviceToHost));
+  return ORBX_OK;
+}
+// Device addresses of those two arrays (valid for the tracker's lifetime once an inertial mode was set): bind them as
+// prior_state / prior_H of the next LastFrame step to chain the prior on the device.
+const double* orbx_tracker_inertial_state_dev(orbx_tracker* t) { return (t && imu_ensure_buffers(t) == ORBX_OK) ? t->d_imuState : nullptr; }
+const double* orbx_tracker_inertial_hessian_dev(orbx_tracker* t) { return (t && imu_ensure_buffers(t) == ORBX_OK) ? t->d_imuH : nullptr; }
 
 int orbx_tracker_map_capacity(const orbx_tracker* t) { return t ? t->mcap : ORBX_EINVAL; }
 
@@ -880,10 +1012,30 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
   ORBX_LAUNCH(t->ctx);
   gather_edges_kernel<<<S, 256, 0, sb>>>(D, 1);
   ORBX_LAUNCH(t->ctx);
-  ORBX_CUDA(cudaMemcpyAsync(D.T2, D.T1, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sb));
   // inliers / iterations of the second optimisation land in the second halves of ninl / iters
-  rc = orbx_launch_pose_opt_slices(t->ctx, sb, S, D.estart, D.ecount, D.exw, D.eobs, D.eisg, &t->cam, D.T2, D.eoutlier,
-                                   D.ninl + S, D.iters + 4 * S, K.d_scratch);
+  if (t->imu.mode) {
+    // visual-inertial TrackLocalMap (src/Tracking.cc:2974-2990): PoseInertialOptimizationLastKeyFrame / LastFrame on the
+    // same edges; the frame's velocity, bias, the reference state and the pre-integration come from orbx_tracker_set_inertial
+    if (K.imuPending) {
+      ORBX_CUDA(cudaStreamWaitEvent(sb, K.evImu, 0));
+      K.imuPending = false;
+    }
+    const orbx_track_imu& U = t->imu;
+    OrbxInertialSlices I{};
+    I.mode = U.mode; I.S = S; I.recInit = U.rec_init;
+    I.fx = t->cam.fx; I.fy = t->cam.fy; I.cx = t->cam.cx; I.cy = t->cam.cy; I.bf = t->cam.bf;
+    I.estart = D.estart; I.ecount = D.ecount; I.exw = D.exw; I.eobs = D.eobs; I.eisg = D.eisg; I.eclose = D.eclose;
+    I.eoutlier = D.eoutlier; I.err = K.d_scratch;
+    I.T1 = D.T1; I.Tcb = U.Tcb; I.Tbc = U.Tbc; I.vel = U.velocity; I.bias = U.bias;
+    I.ref = U.ref_state; I.preint = U.preint; I.preintJac = U.preint_jac; I.preintBias = U.preint_bias;
+    I.infoI = U.info_inertial; I.infoG = U.info_gyro; I.infoA = U.info_acc; I.priorState = U.prior_state; I.priorH = U.prior_H;
+    I.stateOut = t->d_imuState; I.H15 = t->d_imuH; I.nRet = D.ninl + S; I.iters = D.iters + 4 * S; I.T2 = D.T2;
+    rc = orbx_launch_pose_inertial_slices(t->ctx, sb, I, t->d_imuArgs);
+  } else {
+    ORBX_CUDA(cudaMemcpyAsync(D.T2, D.T1, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sb));
+    rc = orbx_launch_pose_opt_slices(t->ctx, sb, S, D.estart, D.ecount, D.exw, D.eobs, D.eisg, &t->cam, D.T2, D.eoutlier,
+                                     D.ninl + S, D.iters + 4 * S, K.d_scratch);
+  }
   if (rc != ORBX_OK) return rc;
   TRK_EV(6, sb);
   ORBX_CUDA(cudaMemcpyAsync(d_Tcw_out, D.T2, sizeof(float) * 16 * S, cudaMemcpyDeviceToDevice, sb));

@@ -42,6 +42,20 @@ class TrackMap(C.Structure):
               ("normal", np.float32))
 
 
+class TrackImu(C.Structure):
+    """orbx_track_imu (include/orbx.h): inputs of the visual-inertial second pose optimisation of a tracker step."""
+    _fields_ = [("mode", C.c_int32), ("rec_init", C.c_int32), ("Tcb", C.c_void_p), ("Tbc", C.c_void_p), ("velocity", C.c_void_p),
+                ("bias", C.c_void_p), ("ref_state", C.c_void_p), ("preint", C.c_void_p), ("preint_jac", C.c_void_p),
+                ("preint_bias", C.c_void_p), ("info_inertial", C.c_void_p), ("info_gyro", C.c_void_p), ("info_acc", C.c_void_p),
+                ("prior_state", C.c_void_p), ("prior_H", C.c_void_p)]
+
+    # (name, dtype, trailing shape after the leading [S]; None = shared by the rig)
+    FIELDS = (("Tcb", np.float32, None), ("Tbc", np.float32, None), ("velocity", np.float32, (3,)), ("bias", np.float32, (6,)),
+              ("ref_state", np.float64, (21,)), ("preint", np.float64, (16,)), ("preint_jac", np.float64, (45,)),
+              ("preint_bias", np.float64, (6,)), ("info_inertial", np.float64, (81,)), ("info_gyro", np.float64, (9,)),
+              ("info_acc", np.float64, (9,)), ("prior_state", np.float64, (21,)), ("prior_H", np.float64, (225,)))
+
+
 def ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

@@ -126,6 +126,13 @@ def load_library():
     L.orbx_tracker_map_bytes.argtypes = [vp]
     L.orbx_tracker_set_map.argtypes = [vp, vp]
     L.orbx_tracker_upload_map.argtypes = [vp, vp]
+    L.orbx_tracker_set_inertial.argtypes = [vp, vp]
+    L.orbx_tracker_upload_inertial.argtypes = [vp, vp]
+    L.orbx_tracker_inertial_result.argtypes = [vp, vp, vp]
+    L.orbx_tracker_inertial_state_dev.restype = vp
+    L.orbx_tracker_inertial_state_dev.argtypes = [vp]
+    L.orbx_tracker_inertial_hessian_dev.restype = vp
+    L.orbx_tracker_inertial_hessian_dev.argtypes = [vp]
     L.orbx_tracker_set_chain.argtypes = [vp, i, vp]
     L.orbx_tracker_keyframe_stream.restype = vp
     L.orbx_tracker_keyframe_stream.argtypes = [vp]
@@ -807,6 +814,54 @@ class Tracker:
         self._map_keep = host_arrays
         m = self._track_map(keep, log_scale_factor)
         _check(load_library().orbx_tracker_upload_map(self.h, C.byref(m)), "orbx_tracker_upload_map")
+
+    # ---- visual-inertial TrackLocalMap (orbx_track_imu) ----
+    def _track_imu(self, mode, ptrs, rec_init):
+        m = abi.TrackImu()
+        m.mode, m.rec_init = int(mode), int(bool(rec_init))
+        for name, _, _ in abi.TrackImu.FIELDS:
+            setattr(m, name, ptrs.get(name))
+        return m
+
+    def set_inertial(self, mode, device_ptrs=None, rec_init=False):
+        """mode 0 / None: back to the visual PoseOptimization; 1: PoseInertialOptimizationLastKeyFrame, 2: ...LastFrame.
+        device_ptrs: dict name -> device address (abi.TrackImu.FIELDS)."""
+        if not mode:
+            _check(load_library().orbx_tracker_set_inertial(self.h, None), "orbx_tracker_set_inertial")
+            return
+        m = self._track_imu(mode, device_ptrs, rec_init)
+        _check(load_library().orbx_tracker_set_inertial(self.h, C.byref(m)), "orbx_tracker_set_inertial")
+
+    def upload_inertial(self, mode, host_arrays, rec_init=False):
+        """host_arrays: dict name -> numpy array (abi.TrackImu.FIELDS; mode 2 may leave ref_state / prior_state / prior_H out
+        to chain on what the previous inertial step left on the device).  Copied for the NEXT step."""
+        keep, ptrs = {}, {}
+        for name, dt, shape in abi.TrackImu.FIELDS:
+            a = host_arrays.get(name)
+            if a is None:
+                continue
+            a = np.ascontiguousarray(a, dt)
+            assert a.size == (16 if shape is None else self.S * int(np.prod(shape))), (name, a.shape)
+            keep[name] = a
+            ptrs[name] = a.ctypes.data
+        self._imu_keep = keep
+        m = self._track_imu(mode, ptrs, rec_init)
+        _check(load_library().orbx_tracker_upload_inertial(self.h, C.byref(m)), "orbx_tracker_upload_inertial")
+
+    def inertial_result(self):
+        """-> (state[S,21], H15[S,15,15]) of the last inertial step"""
+        st = np.zeros((self.S, 21), np.float64)
+        H = np.zeros((self.S, 225), np.float64)
+        _check(load_library().orbx_tracker_inertial_result(self.h, _p(st), _p(H)), "orbx_tracker_inertial_result")
+        return st, H.reshape(self.S, 15, 15)
+
+    @property
+    def inertial_state_dev(self):
+        return load_library().orbx_tracker_inertial_state_dev(self.h)
+
+    @property
+    def inertial_hessian_dev(self):
+        return load_library().orbx_tracker_inertial_hessian_dev(self.h)
 
     def set_chain(self, enable, d_Tcw_init=None):
         """Motion-model chaining: Tcw_prior of the following steps is the relative motion; d_Tcw_init = device [S,16]."""

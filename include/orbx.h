@@ -542,6 +542,43 @@ orbx_tracker *orbx_tracker_create_mono(orbx_ctx *ctx, orbx_ext *ext /* max_batch
 /* 2 (stereo tracker) or 1 (monocular tracker) */
 int orbx_tracker_images_per_stream(const orbx_tracker *trk);
 
+/* Visual-inertial TrackLocalMap (BASELINE config 3; src/Tracking.cc:2974-2990): with an inertial mode bound, the SECOND
+ * pose optimisation of a step is Optimizer::PoseInertialOptimizationLastKeyFrame (mode 1, src/Optimizer.cc:7665-8066)
+ * or PoseInertialOptimizationLastFrame (mode 2, :8068-8603) instead of PoseOptimization, on the same edges (close_pt =
+ * bit 2 of orbx_track_map::map_flags, i.e. pMP->mTrackDepth < 10).  The frame's ImuCamPose is built on the device from
+ * the pose the first PoseOptimization left, exactly as Frame::GetImuRotation / GetImuPosition do (src/Frame.cc:534-554,
+ * float cv::Mat arithmetic), with the velocity and bias given here (pFrame->mVw, mImuBias after PredictStateIMU); the
+ * optimised state goes back into the step's Tcw_out through Frame::SetImuPoseVelocity's arithmetic (src/Frame.cc:520-530).
+ * Array layouts are those of orbx_pose_inertial_optimization_last_{keyframe,frame}_batch with P = S:
+ *   Tcb, Tbc [16];  velocity [S][3];  bias [S][6] (gyro xyz, acc xyz);
+ *   ref_state [S][21]: the last keyframe (mode 1) / the previous frame (mode 2);  preint [S][16];
+ *   preint_jac [S][45], preint_bias [S][6], prior_state [S][21], prior_H [S][225]: mode 2 only;
+ *   info_inertial [S][81], info_gyro [S][9], info_acc [S][9].
+ * stats[6] (inliers_2) = nInitialCorrespondences - nBad, stats[7] counts the Gauss-Newton iterations. */
+typedef struct orbx_track_imu {
+  int mode;    /* 0 off, 1 LastKeyFrame, 2 LastFrame */
+  int rec_init;
+  const float *Tcb, *Tbc;
+  const float *velocity, *bias;
+  const double *ref_state, *preint, *preint_jac, *preint_bias;
+  const double *info_inertial, *info_gyro, *info_acc;
+  const double *prior_state, *prior_H;
+} orbx_track_imu;
+/* Bind DEVICE-resident inputs for the following steps (NULL / mode 0: back to the visual PoseOptimization); they are read
+ * when the step runs and must stay valid until then. */
+int orbx_tracker_set_inertial(orbx_tracker *trk, const orbx_track_imu *imu);
+/* HOST-side inputs -> the next step's slot (asynchronous), then bound.  In mode 2, ref_state and (prior_state, prior_H)
+ * may be NULL: the state and marginalised Hessian the PREVIOUS inertial step left on the device are used (the
+ * reference's pFp->mpcpi chain, src/Optimizer.cc:8594-8599). */
+int orbx_tracker_upload_inertial(orbx_tracker *trk, const orbx_track_imu *imu);
+/* Results of the last inertial step: body states [S][21] (Rwb, twb, v, bg, ba) and the 15x15 Hessians [S][225] for the
+ * next ConstraintPoseImu; either may be NULL.  Synchronises the tracker. */
+int orbx_tracker_inertial_result(orbx_tracker *trk, double *state, double *H15);
+/* Device addresses of those two arrays, for chaining them as ref_state / prior_state / prior_H with
+ * orbx_tracker_set_inertial. */
+const double *orbx_tracker_inertial_state_dev(orbx_tracker *trk);
+const double *orbx_tracker_inertial_hessian_dev(orbx_tracker *trk);
+
 orbx_tracker *orbx_tracker_create(orbx_ctx *ctx, orbx_ext *ext /* max_batch >= 2*S */, int S,
                                   const orbx_camera *cam, float th_frame, float th_map,
                                   float nnratio_map);
@@ -587,7 +624,8 @@ typedef struct orbx_track_map {
   const uint8_t *last_flags;  /* [S][m_cap] bit0: mLastFrame.mvpMapPoints holds it && !mvbOutlier, bit1: Observations() > 0 */
   const int32_t *last_octave; /* [S][m_cap] octave / angle of the last frame's keypoint that observed it */
   const float *last_angle;
-  const uint8_t *map_flags;   /* [S][m_cap] bit0: in mvpLocalMapPoints && !isBad(), bit1: Observations() > 0 */
+  const uint8_t *map_flags;   /* [S][m_cap] bit0: in mvpLocalMapPoints && !isBad(), bit1: Observations() > 0,
+                                 bit2: mTrackDepth < 10 (read by the inertial optimisers only) */
   const float *max_dist, *min_dist; /* [S][m_cap] mfMaxDistance / mfMinDistance */
   const float *normal;        /* [S][m_cap][3] GetNormal() */
   float log_scale_factor;     /* Frame::mfLogScaleFactor; <= 0: log of the extractor's scale factor */

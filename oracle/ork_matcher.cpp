@@ -287,9 +287,11 @@ int ork_search_by_projection_frame(const orbx_frame_desc* C, const uint8_t* cur_
   std::vector<uint8_t> blocked(cur_blocked, cur_blocked + C->n);
   for (int i = 0; i < C->n; ++i) cur_match[i] = -1;
   std::vector<int> rotHist[HISTO_LENGTH];
-  // twc = -Rcw^T tcw ; tlc = Rlw twc + tlw   (fp32, fixed order)
+  // twc = -Rcw.t()*tcw: a transposed operand sends cv::gemm down its general path (products and sum in double, rounded to
+  // float once; tests/test_ref_stub.py); tlc = Rlw*twc + tlw: the small-matrix fp32 path, fixed order
   float twc[3], tlc[3];
-  for (int i = 0; i < 3; ++i) twc[i] = -(Tc[0 * 4 + i] * Tc[3] + Tc[1 * 4 + i] * Tc[7] + Tc[2 * 4 + i] * Tc[11]);
+  for (int i = 0; i < 3; ++i)
+    twc[i] = (float)(-((double)Tc[0 * 4 + i] * (double)Tc[3] + (double)Tc[1 * 4 + i] * (double)Tc[7] + (double)Tc[2 * 4 + i] * (double)Tc[11]));
   for (int i = 0; i < 3; ++i) tlc[i] = Tl[i * 4 + 0] * twc[0] + Tl[i * 4 + 1] * twc[1] + Tl[i * 4 + 2] * twc[2] + Tl[i * 4 + 3];
   const bool bForward = tlc[2] > cam->b && !bMono;
   const bool bBackward = -tlc[2] > cam->b && !bMono;
@@ -367,7 +369,9 @@ int ork_search_for_triangulation(const orbx_frame_desc* K1, const orbx_frame_des
   // R12 = R1w R2w^T ; t12 = -R12 t2w + t1w
   float R12[9], t12[3];
   for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) R12[i * 3 + j] = R1w[i * 3 + 0] * R2w[j * 3 + 0] + R1w[i * 3 + 1] * R2w[j * 3 + 1] + R1w[i * 3 + 2] * R2w[j * 3 + 2];
+    for (int j = 0; j < 3; ++j)   // R1w*R2w.t(): gemm's general path (double accumulation) because of the transposed operand
+      R12[i * 3 + j] = (float)((double)R1w[i * 3 + 0] * (double)R2w[j * 3 + 0] + (double)R1w[i * 3 + 1] * (double)R2w[j * 3 + 1] +
+                               (double)R1w[i * 3 + 2] * (double)R2w[j * 3 + 2]);
   for (int i = 0; i < 3; ++i) t12[i] = -(R12[i * 3 + 0] * t2w[0] + R12[i * 3 + 1] * t2w[1] + R12[i * 3 + 2] * t2w[2]) + t1w[i];
   // F12 = K1^-T [t12]x R12 K2^-1   (Pinhole::epipolarConstrain, computed once instead of per pair)
   float A[9];   // [t12]x R12

@@ -172,7 +172,32 @@ Mat operator*(const Mat& a, double s) {
 Mat operator*(double s, const Mat& a) { return a * s; }
 Mat operator/(const Mat& a, double s) { return a * (1.0 / s); }
 
-Mat Mat::t() const {
+// Products with a lazily transposed operand: cv::gemm with GEMM_1_T / GEMM_2_T set skips the small-matrix path
+// (its condition starts with flags == 0) and runs GEMMSingleMul<float,double>: products and running sum in double, k
+// ascending, d = T(s * alpha).  Checked against cv2.gemm in tests/test_ref_stub.py.
+static Mat gemm_general(const Mat& a, bool ta, const Mat& b, bool tb, double alpha) {
+  const int ar = ta ? a.cols : a.rows, ac = ta ? a.rows : a.cols, br = tb ? b.cols : b.rows, bc = tb ? b.rows : b.cols;
+  assert(ac == br && a.type() == b.type() && (a.type() == CV_32F || a.type() == CV_64F));
+  (void)br;
+  Mat c(ar, bc, a.type());
+  for (int i = 0; i < ar; ++i)
+    for (int j = 0; j < bc; ++j) {
+      double s = 0;
+      for (int k = 0; k < ac; ++k) s += (ta ? get_elem(a, k, i) : get_elem(a, i, k)) * (tb ? get_elem(b, j, k) : get_elem(b, k, j));
+      set_elem(c, i, j, s * alpha);
+    }
+  return c;
+}
+MatT Mat::t() const { return MatT{*this, 1.0}; }
+MatT::operator Mat() const { return alpha == 1.0 ? m.transposed() : m.transposed() * alpha; }
+MatT operator-(const MatT& a) { return MatT{a.m, -a.alpha}; }
+MatT operator*(double s, const MatT& a) { return MatT{a.m, a.alpha * s}; }
+MatT operator*(const MatT& a, double s) { return MatT{a.m, a.alpha * s}; }
+Mat operator*(const MatT& a, const Mat& b) { return gemm_general(a.m, true, b, false, a.alpha); }
+Mat operator*(const Mat& a, const MatT& b) { return gemm_general(a, false, b.m, true, b.alpha); }
+Mat operator*(const MatT& a, const MatT& b) { return gemm_general(a.m, true, b.m, true, a.alpha * b.alpha); }
+
+Mat Mat::transposed() const {
   Mat c(cols, rows, flags_type);
   for (int i = 0; i < rows; ++i)
     for (int j = 0; j < cols; ++j) std::memcpy(c.data + (size_t)j * c.step.v + (size_t)i * elemSize(), data + (size_t)i * step.v + (size_t)j * elemSize(), elemSize());

@@ -156,6 +156,7 @@ inline size_t cvstub_elem_size(int type) {
 }
 
 // Single-channel 2-D matrix header over a ref-counted buffer: copying shares the data, ROI operators return views.
+struct MatT;
 class Mat {
  public:
   int flags_type, rows, cols;
@@ -215,8 +216,11 @@ class Mat {
   static Mat zeros(Size s, int type) { return zeros(s.height, s.width, type); }
   static Mat ones(int r, int c, int type);
   static Mat eye(int r, int c, int type);
-  // float / double algebra (eager; see cvstub.cpp for the evaluation order, pinned to cv2 by tests/test_ref_stub.py)
-  Mat t() const;
+  // float / double algebra (see cvstub.cpp for the evaluation order, pinned to cv2 by tests/test_ref_stub.py).  t() is
+  // the one lazy expression the stand-in keeps: cv::MatExpr turns A.t()*B and A*B.t() into cv::gemm calls with a
+  // GEMM_x_T flag, and those never take gemm's small-matrix fp32 path.
+  MatT t() const;
+  Mat transposed() const;
   Mat inv(int method = DECOMP_LU) const;
   double dot(const Mat& m) const;
   Mat mul(const Mat& m) const;
@@ -314,6 +318,19 @@ double determinant(InputArray a);
 void hconcat(InputArray a, InputArray b, OutputArray dst);
 void vconcat(InputArray a, InputArray b, OutputArray dst);
 
+// A.t() (optionally scaled: -A.t(), s*A.t()) as an operand; converts to the materialised (scaled) transpose anywhere else
+struct MatT {
+  Mat m;
+  double alpha;
+  operator Mat() const;
+  Mat inv(int method = DECOMP_LU) const { return Mat(*this).inv(method); }
+};
+MatT operator-(const MatT& a);
+MatT operator*(double s, const MatT& a);
+MatT operator*(const MatT& a, double s);
+Mat operator*(const MatT& a, const Mat& b);     // gemm(..., GEMM_1_T)
+Mat operator*(const Mat& a, const MatT& b);     // gemm(..., GEMM_2_T)
+Mat operator*(const MatT& a, const MatT& b);    // gemm(..., GEMM_1_T | GEMM_2_T)
 Mat operator*(const Mat& a, const Mat& b);
 Mat operator+(const Mat& a, const Mat& b);
 Mat operator-(const Mat& a, const Mat& b);

@@ -82,8 +82,49 @@ def track_frame(ork, cam, L, R, Tcw_true, Tcw_prior, th_frame=7.0, th_map=1.0, n
     return T2, stats
 
 
+def _f32_dot3(a0, b0, a1, b1, a2, b2):
+    """((a0*b0 + a1*b1) + a2*b2) in float32, the order of cv::gemm's small-matrix path"""
+    return F32(F32(F32(a0) * F32(b0)) + F32(F32(a1) * F32(b1))) + F32(F32(a2) * F32(b2))
+
+
+def camera_center(T):
+    """Frame::UpdatePoseMatrices: mOw = -mRcw.t()*mtcw (src/Frame.cc:543).  cv::MatExpr hands the transposed operand to
+    cv::gemm as GEMM_1_T, which takes the general path: products and sum in double, one rounding to float."""
+    T = np.asarray(T, F32).reshape(4, 4).astype(np.float64)
+    return np.array([-(T[0, i] * T[0, 3] + T[1, i] * T[1, 3] + T[2, i] * T[2, 3]) for i in range(3)]).astype(F32)
+
+
+def imu_state_from_pose(T1, Tcb, velocity, bias):
+    """ImuCamPose(Frame*) inputs: Frame::GetImuRotation / GetImuPosition on the pose T1 (src/Frame.cc:534-554), float32"""
+    T1 = np.asarray(T1, F32).reshape(4, 4)
+    Tcb = np.asarray(Tcb, F32).reshape(4, 4)
+    Rwc = T1[:3, :3].T
+    tcw = T1[:3, 3]
+    Ow = camera_center(T1)
+    Rwb = np.array([[_f32_dot3(Rwc[i, 0], Tcb[0, j], Rwc[i, 1], Tcb[1, j], Rwc[i, 2], Tcb[2, j]) for j in range(3)] for i in range(3)], F32)
+    twb = np.array([F32(_f32_dot3(Rwc[i, 0], Tcb[0, 3], Rwc[i, 1], Tcb[1, 3], Rwc[i, 2], Tcb[2, 3]) + Ow[i]) for i in range(3)], F32)
+    return np.concatenate([Rwb.astype(np.float64).ravel(), twb.astype(np.float64), np.asarray(velocity, F32).astype(np.float64),
+                           np.asarray(bias, F32).astype(np.float64)])
+
+
+def pose_from_imu_state(state, Tcb):
+    """Frame::SetImuPoseVelocity (src/Frame.cc:520-530): Tcw = Tcb * [Rwb^T | -Rwb^T twb], float32"""
+    Tcb = np.asarray(Tcb, F32).reshape(4, 4)
+    Rbw = np.asarray(state[:9], np.float64).reshape(3, 3).astype(F32).T
+    twb = np.asarray(state[9:12], np.float64).astype(F32)
+    Tbw = np.eye(4, dtype=F32)
+    Tbw[:3, :3] = Rbw
+    for i in range(3):
+        Tbw[i, 3] = -_f32_dot3(Rbw[i, 0], twb[0], Rbw[i, 1], twb[1], Rbw[i, 2], twb[2])
+    T = np.zeros((4, 4), F32)
+    for i in range(4):
+        for j in range(4):
+            T[i, j] = F32(_f32_dot3(Tcb[i, 0], Tbw[0, j], Tcb[i, 1], Tbw[1, j], Tcb[i, 2], Tbw[2, j]) + F32(Tcb[i, 3] * Tbw[3, j]))
+    return T
+
+
 def track_frame_map(ork, cam, L, R, mp, Tcw_prior, th_frame=None, th_map=1.0, nn_map=0.8, nfeatures=1000, extractors=None,
-                    log_sf=None, mono=False):
+                    log_sf=None, mono=False, imu=None, imu_mode=0, want_inertial=False):
     """The chain of orbx_tracker_step with a GIVEN map (orbx_tracker_set_map; mp = one stream's arrays as produced by
     scenarios.track_map_scenario), composed from the oracle's functions: extract L+R, ComputeStereoMatches,
     SearchByProjection(Cur, Last) over the last-frame entries, PoseOptimization, outliers dropped, isInFrustum over the
@@ -127,8 +168,7 @@ def track_frame_map(ork, cam, L, R, mp, Tcw_prior, th_frame=None, th_map=1.0, nn
     blocked = (cur2 >= 0).astype(np.uint8)
     taken = np.zeros(M, bool)
     taken[cur2[cur2 >= 0]] = True
-    # Ow = -Rcw^T tcw in the kernel's fp32 expression order
-    Ow = np.array([-(T1[0, i] * T1[0, 3] + T1[1, i] * T1[1, 3] + T1[2, i] * T1[2, 3]) for i in range(3)], F32)
+    Ow = camera_center(T1)
     if log_sf is None:
         log_sf = float(F32(np.log(np.float64(scale[1]))))
     fr = ork.is_in_frustum(cam, T1[:3, :3], T1[:3, 3], Ow, (0.0, float(W), 0.0, float(H)), 0.5, exL.nlevels, log_sf, xw,
@@ -142,6 +182,25 @@ def track_frame_map(ork, cam, L, R, mp, Tcw_prior, th_frame=None, th_map=1.0, nn
         if best[q] >= 0:
             kpmp[best[q]] = q
     idx2, exw2, eobs2, eisg2 = edges(kpmp)
-    T2, out2, nin2, it2 = ork.pose_optimization(exw2, eobs2, eisg2, cam, T1)
+    inertial = None
+    if imu_mode:
+        # visual-inertial TrackLocalMap (src/Tracking.cc:2974-2990) on the same edges
+        close = ((mp["map_flags"][:M][kpmp[idx2]] >> 2) & 1).astype(np.uint8)
+        sc_in = dict(xw=exw2, obs=eobs2, isg=eisg2, close=close, Tcw=T1, Tcb=imu["Tcb"], Tbc=imu["Tbc"],
+                     state=imu_state_from_pose(T1, imu["Tcb"], imu["velocity"], imu["bias"]), preint=imu["preint"],
+                     infoI=imu["info_inertial"], infoG=imu["info_gyro"], infoA=imu["info_acc"])
+        if imu_mode == 1:
+            sc_in["kf"] = imu["ref_state"]
+            res = ork.pose_inertial_optimization_last_keyframe(sc_in, cam)
+        else:
+            sc_in.update(prev=imu["ref_state"], preint_jac=imu["preint_jac"], preint_bias=imu["preint_bias"],
+                         prior_state=imu["prior_state"], prior_H=imu["prior_H"])
+            res = ork.pose_inertial_optimization_last_frame(sc_in, cam)
+        T2, nin2, it2 = pose_from_imu_state(res["state"], imu["Tcb"]), res["n"], res["iters"]
+        inertial = res
+    else:
+        T2, out2, nin2, it2 = ork.pose_optimization(exw2, eobs2, eisg2, cam, T1)
     stats = np.array([n, len(kR), int((ur >= 0).sum()), nm1, nin1, nm2, nin2, int(it1.sum() + it2.sum())], np.int32)
+    if want_inertial:
+        return T2, stats, inertial
     return T2, stats

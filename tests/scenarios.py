@@ -514,7 +514,7 @@ def track_map_scenario(seed, kps, desc, uright, depth, Tcw_true, m_cap=2048, n_m
     mdesc[:n] = tdesc
     mdesc[n:n_map] = ddesc
     last_flags, map_flags = np.zeros(m_cap, np.uint8), np.zeros(m_cap, np.uint8)
-    map_flags[:n_map] = 3
+    map_flags[:n_map] = 3 | np.where(dist < 10.0, 4, 0)              # bit 2: mTrackDepth < 10 (inertial optimisers)
     last_flags[:n_map] = np.where(np.concatenate([tlast, dlast]), 3, 0)
     last_octave, last_angle = np.zeros(m_cap, np.int32), np.zeros(m_cap, np.float32)
     last_octave[:n_map] = octv
@@ -538,4 +538,77 @@ def stack_track_maps(maps):
     for k in ("xw", "desc", "last_flags", "last_octave", "last_angle", "map_flags", "max_dist", "min_dist", "normal"):
         out[k] = np.ascontiguousarray(np.stack([m[k] for m in maps]))
     out["n_map"] = np.array([m["n_map"] for m in maps], np.int32)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Inertial inputs of one stream for the tracker's visual-inertial TrackLocalMap (orbx_track_imu): the frame's TRUE body
+# state follows from its true camera pose and the rig, the reference state (last keyframe, mode 1 / previous frame,
+# mode 2) lies dt seconds earlier, and the pre-integrated deltas are the exact relative motion, so the inertial residual
+# vanishes at the truth.  Velocity and bias handed to the tracker are the truth perturbed like PredictStateIMU would leave
+# them.  Mode 2 adds the raw pre-integration with bias Jacobians and the previous frame's ConstraintPoseImu.
+# ------------------------------------------------------------------------------------------------------------------
+def track_imu_scenario(seed, Tcw_true, mode, dt=None):
+    rng = np.random.default_rng(seed)
+    dt = dt if dt is not None else (0.25 if mode == 1 else 0.05)
+    g = np.array([0.0, 0.0, -9.81])
+    Rbc = _exp_so3(np.array([0.01, -0.02, 1.55]))
+    tbc = np.array([-0.02, -0.06, 0.01])
+    Tbc = np.eye(4); Tbc[:3, :3] = Rbc; Tbc[:3, 3] = tbc
+    Tcb = np.linalg.inv(Tbc)
+    T = np.asarray(Tcw_true, np.float64).reshape(4, 4)
+    Rwc = T[:3, :3].T
+    Ow = -Rwc @ T[:3, 3]
+    Rwb2 = Rwc @ Tcb[:3, :3]
+    twb2 = Rwc @ Tcb[:3, 3] + Ow
+    v2 = rng.normal(0, 0.5, 3)
+    bg, ba = rng.normal(0, 0.002, 3), rng.normal(0, 0.02, 3)
+    Rwb1 = Rwb2 @ _exp_so3(rng.normal(0, 0.08 if mode == 1 else 0.02, 3)).T
+    v1 = v2 - rng.normal(0, 0.3 if mode == 1 else 0.05, 3)
+    twb1 = twb2 - v1 * dt - rng.normal(0, 0.03 if mode == 1 else 0.003, 3)
+    dR = Rwb1.T @ Rwb2
+    dV = Rwb1.T @ (v2 - v1 - g * dt)
+    dP = Rwb1.T @ (twb2 - twb1 - v1 * dt - 0.5 * g * dt * dt)
+    ref_truth = np.concatenate([Rwb1.ravel(), twb1, v1, bg, ba])
+    A = rng.normal(0, 1, (9, 9))
+    out = dict(Tcb=Tcb.astype(np.float32), Tbc=Tbc.astype(np.float32),
+               velocity=(v2 + rng.normal(0, 0.05, 3)).astype(np.float32),
+               bias=np.concatenate([bg + rng.normal(0, 1e-4, 3), ba + rng.normal(0, 1e-3, 3)]).astype(np.float32),
+               info_inertial=(A @ A.T + np.diag([4e4] * 3 + [2e3] * 3 + [8e3] * 3)).ravel(),
+               info_gyro=(np.eye(3) * 1e7).ravel(), info_acc=(np.eye(3) * 1e4).ravel(),
+               truth=np.concatenate([Rwb2.ravel(), twb2, v2, bg, ba]))
+    if mode == 1:
+        out.update(ref_state=ref_truth, preint=np.concatenate([dR.ravel(), dV, dP, [dt]]))
+        return out
+    dg, da = rng.normal(0, 3e-4, 3), rng.normal(0, 3e-3, 3)                 # previous-frame bias - pre-integration bias
+    bpre = np.concatenate([bg - dg, ba - da])
+    JRg = -dt * (np.eye(3) + rng.normal(0, 0.02, (3, 3)))
+    JVg = rng.normal(0, 0.02, (3, 3))
+    JVa = -dt * (np.eye(3) + rng.normal(0, 0.05, (3, 3)))
+    JPg = rng.normal(0, 0.002, (3, 3))
+    JPa = -0.5 * dt * dt * (np.eye(3) + rng.normal(0, 0.05, (3, 3)))
+    dR0 = dR @ _exp_so3(JRg @ dg).T
+    dV0 = dV - JVg @ dg - JVa @ da
+    dP0 = dP - JPg @ dg - JPa @ da
+    R1 = Rwb1 @ _exp_so3(rng.normal(0, 0.002, 3))
+    prev = np.concatenate([R1.ravel(), twb1 + rng.normal(0, 0.005, 3), v1 + rng.normal(0, 0.01, 3), bg + rng.normal(0, 5e-5, 3),
+                           ba + rng.normal(0, 5e-4, 3)])
+    sc_ = np.sqrt(np.array([3e5] * 3 + [2e5] * 3 + [5e3] * 3 + [1e8] * 3 + [1e5] * 3))
+    Q = rng.normal(0, 1, (15, 15))
+    Hp = (sc_[:, None] * (np.eye(15) + 0.02 * (Q @ Q.T) / 15) * sc_[None, :])
+    Hp = 0.5 * (Hp + Hp.T)
+    out.update(ref_state=prev, preint=np.concatenate([dR0.ravel(), dV0, dP0, [dt]]),
+               preint_jac=np.concatenate([JRg.ravel(), JVg.ravel(), JVa.ravel(), JPg.ravel(), JPa.ravel()]), preint_bias=bpre,
+               prior_state=prev.copy(), prior_H=Hp.ravel())
+    return out
+
+
+def stack_track_imu(imus):
+    """list of per-stream track_imu_scenario dicts -> host arrays of orbx_track_imu ([S, ...]; Tcb / Tbc shared)"""
+    out = {"Tcb": np.ascontiguousarray(imus[0]["Tcb"], np.float32), "Tbc": np.ascontiguousarray(imus[0]["Tbc"], np.float32)}
+    for k in ("velocity", "bias"):
+        out[k] = np.ascontiguousarray(np.stack([m[k] for m in imus]), np.float32)
+    for k in ("ref_state", "preint", "preint_jac", "preint_bias", "info_inertial", "info_gyro", "info_acc", "prior_state", "prior_H"):
+        if k in imus[0]:
+            out[k] = np.ascontiguousarray(np.stack([np.asarray(m[k], np.float64).ravel() for m in imus]), np.float64)
     return out

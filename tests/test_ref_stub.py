@@ -17,6 +17,15 @@ extern "C" void stub_gemm(const float* a, int ar, int ac, const float* b, int bc
   cv::Mat Cm = A * B;
   for (int i = 0; i < ar; ++i) for (int j = 0; j < bc; ++j) c[i * bc + j] = Cm.at<float>(i, j);
 }
+// flags: 1 = A.t()*B, 2 = A*B.t(), 3 = A.t()*B.t(); neg: the transposed operand is negated first (-A.t()*B)
+extern "C" void stub_gemm_t(const float* a, int ar, int ac, const float* b, int br, int bc, int flags, int neg, float* c) {
+  cv::Mat A(ar, ac, CV_32F, (void*)a), B(br, bc, CV_32F, (void*)b);
+  cv::Mat Cm;
+  if (flags == 1) Cm = neg ? cv::Mat(-A.t() * B) : cv::Mat(A.t() * B);
+  else if (flags == 2) Cm = neg ? cv::Mat(A * (-B.t())) : cv::Mat(A * B.t());
+  else Cm = A.t() * B.t();
+  for (int i = 0; i < Cm.rows; ++i) for (int j = 0; j < Cm.cols; ++j) c[i * Cm.cols + j] = Cm.at<float>(i, j);
+}
 extern "C" void stub_inv3(const float* a, float* c) {
   cv::Mat A(3, 3, CV_32F, (void*)a);
   cv::Mat I = A.inv();
@@ -55,6 +64,31 @@ def test_gemm_equals_cv2(stub, shape):
         Cm = np.zeros((shape[0], shape[2]), np.float32)
         stub.stub_gemm(_p(A), shape[0], shape[1], _p(B), shape[2], _p(Cm))
         assert np.array_equal(Cm, cv2.gemm(A, B, 1, None, 0)), shape
+
+
+def test_transposed_products_equal_cv2(stub):
+    """A.t()*B, A*B.t() (cv::MatExpr -> gemm with GEMM_1_T / GEMM_2_T): never the small-matrix fp32 path, e.g.
+    Frame::UpdatePoseMatrices' mOw = -mRcw.t()*mtcw and SearchForTriangulation's R12 = R1w*R2w.t()."""
+    rng = np.random.default_rng(11)
+    differs_from_fp32 = 0
+    for _ in range(300):
+        A, B, v = (rng.normal(size=(3, 3)).astype(np.float32), rng.normal(size=(3, 3)).astype(np.float32),
+                   rng.normal(size=(3, 1)).astype(np.float32))
+        out = np.zeros((3, 3), np.float32)
+        stub.stub_gemm_t(_p(A), 3, 3, _p(B), 3, 3, 1, 0, _p(out))
+        assert np.array_equal(out, cv2.gemm(A, B, 1, None, 0, flags=cv2.GEMM_1_T))
+        stub.stub_gemm_t(_p(A), 3, 3, _p(B), 3, 3, 2, 0, _p(out))
+        want = cv2.gemm(A, B, 1, None, 0, flags=cv2.GEMM_2_T)
+        assert np.array_equal(out, want)
+        differs_from_fp32 += not np.array_equal(want, cv2.gemm(A, np.ascontiguousarray(B.T), 1, None, 0))
+        stub.stub_gemm_t(_p(A), 3, 3, _p(B), 3, 3, 3, 0, _p(out))
+        assert np.array_equal(out, cv2.gemm(A, B, 1, None, 0, flags=cv2.GEMM_1_T | cv2.GEMM_2_T))
+        o3 = np.zeros((3, 1), np.float32)
+        stub.stub_gemm_t(_p(A), 3, 3, _p(v), 3, 1, 1, 1, _p(o3))
+        assert np.array_equal(o3, cv2.gemm(A, v, -1, None, 0, flags=cv2.GEMM_1_T))
+        stub.stub_gemm_t(_p(A), 3, 3, _p(B), 3, 3, 2, 1, _p(out))
+        assert np.array_equal(out, cv2.gemm(A, B, -1, None, 0, flags=cv2.GEMM_2_T))
+    assert differs_from_fp32 > 100      # the distinction matters: most random 3x3 products differ in some element
 
 
 def test_invert_norm_dot_equal_cv2(stub):

@@ -205,6 +205,85 @@ def test_monocular_tracker_matches_oracle_chain(ctx, ork):
     ex.close()
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_inertial_tracker_matches_oracle_chain(ctx, ork, mode):
+    """BASELINE config 3: the second pose optimisation of the step is PoseInertialOptimizationLastKeyFrame (mode 1) /
+    LastFrame (mode 2), fed on the device from the pose the first PoseOptimization left (src/Tracking.cc:2974-2990)."""
+    import orbx
+    from replay_reference import track_frame_map
+    S = 2
+    cam = orbx.make_camera()
+    imgs, Tt, Tp, maps = _map_setup(ork, S, 180)
+    imus = [sc.track_imu_scenario(900 + s, Tt[s], mode) for s in range(S)]
+    ex = orbx.ORBextractor(ctx, max_batch=2 * S)
+    trk = orbx.Tracker(ctx, ex, S, cam)
+    host = sc.stack_track_maps(maps)
+    himu = sc.stack_track_imu(imus)
+    want = [track_frame_map(ork, cam, imgs[2 * s], imgs[2 * s + 1], maps[s], Tp[s], imu=imus[s], imu_mode=mode, want_inertial=True)
+            for s in range(S)]
+    for rep in range(2):
+        trk.upload_map(host)
+        trk.upload_inertial(mode, himu)
+        Tout, stats = trk.step(imgs, Tt, Tp)
+        state, H = trk.inertial_result()
+        for s in range(S):
+            T2, st, res = want[s]
+            assert np.array_equal(stats[s], st), (s, stats[s], st)
+            assert np.abs(state[s] - res["state"]).max() < 1e-9, (s, np.abs(state[s] - res["state"]).max())
+            assert np.abs(H[s] - res["H"]).max() <= 1e-9 * np.abs(res["H"]).max()
+            assert np.abs(Tout[s] - T2).max() < 2e-6, (s, np.abs(Tout[s] - T2).max())
+            assert st[6] > 500 and np.abs(state[s][9:12] - imus[s]["truth"][9:12]).max() < 2e-2
+    # the asynchronous host path carries the inertial inputs too
+    trk.upload_map(host)
+    trk.upload_inertial(mode, himu)
+    trk.submit(imgs, Tt, Tp)
+    got = trk.collect()
+    assert np.array_equal(got[0], Tout) and np.array_equal(got[1], stats)
+    # mode 0 detaches: the visual chain again
+    trk.set_inertial(0)
+    trk.upload_map(host)
+    Tv, sv = trk.step(imgs, Tt, Tp)
+    for s in range(S):
+        T2, st = track_frame_map(ork, cam, imgs[2 * s], imgs[2 * s + 1], maps[s], Tp[s])
+        assert np.array_equal(sv[s], st) and np.abs(Tv[s] - T2).max() < 2e-6
+    trk.close()
+    ex.close()
+
+
+def test_inertial_tracker_chains_the_prior_on_the_device(ctx, ork):
+    """Mode 2 without ref_state / prior: step t+1 reads the state and marginalised Hessian step t left on the device."""
+    import orbx
+    from replay_reference import track_frame_map
+    S = 2
+    cam = orbx.make_camera()
+    imgs, Tt, Tp, maps = _map_setup(ork, S, 190)
+    ex = orbx.ORBextractor(ctx, max_batch=2 * S)
+    trk = orbx.Tracker(ctx, ex, S, cam)
+    host = sc.stack_track_maps(maps)
+    # step 1: LastKeyFrame seeds state + H15
+    imu1 = [sc.track_imu_scenario(950 + s, Tt[s], 1) for s in range(S)]
+    trk.upload_map(host)
+    trk.upload_inertial(1, sc.stack_track_imu(imu1))
+    trk.step(imgs, Tt, Tp)
+    st1, H1 = trk.inertial_result()
+    # step 2: LastFrame on the same images, previous frame = step 1's result (a stationary rig: zero relative motion)
+    imu2 = [sc.track_imu_scenario(970 + s, Tt[s], 2) for s in range(S)]
+    h2 = sc.stack_track_imu(imu2)
+    chained = {k: v for k, v in h2.items() if k not in ("ref_state", "prior_state", "prior_H")}
+    trk.upload_map(host)
+    trk.upload_inertial(2, chained)
+    Tout, stats = trk.step(imgs, Tt, Tp)
+    st2, H2 = trk.inertial_result()
+    for s in range(S):
+        imu = dict(imu2[s], ref_state=st1[s], prior_state=st1[s], prior_H=H1[s].ravel())
+        T2, st, res = track_frame_map(ork, cam, imgs[2 * s], imgs[2 * s + 1], maps[s], Tp[s], imu=imu, imu_mode=2, want_inertial=True)
+        assert np.array_equal(stats[s], st), (s, stats[s], st)
+        assert np.abs(st2[s] - res["state"]).max() < 1e-9 and np.abs(H2[s] - res["H"]).max() <= 1e-9 * np.abs(res["H"]).max()
+        assert np.abs(Tout[s] - T2).max() < 2e-6
+    trk.close()
+    ex.close()
+
+
 def test_tracker_chain_mode_composes_the_prior_on_the_device(ctx, ork):
     """Motion-model chaining: step t+1 starts from dT * (pose step t produced).  Equal to feeding that product from the host."""
     import orbx
