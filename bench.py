@@ -37,12 +37,18 @@ W, H, NFEAT, NLEVELS = 752, 480, 1000, 8
 METRIC = "tracking frames/sec (extract+match+poseopt) EuRoC 752x480"
 UNIT = "stereo frames/s"
 MONO = False
+INERTIAL = False
+IMU_KF_PERIOD = 10          # c3: every 10th step optimises against the last keyframe (mbMapUpdated), the others against the last frame
+CHAIN_INERTIAL = ("ORB extraction L+R, ComputeStereoMatches, SearchByProjection(last frame), PoseOptimization, isInFrustum + "
+                  "SearchByProjection(local map), PoseInertialOptimizationLastFrame (LastKeyFrame every 10th step)")
 CHAIN_MONO = ("ORB extraction (one image), SearchByProjection(last frame, th 15), PoseOptimization (monocular edges), "
               "isInFrustum + SearchByProjection(local map), PoseOptimization")
 CHAIN = ("ORB extraction L+R, ComputeStereoMatches, SearchByProjection(last frame), PoseOptimization, "
          "isInFrustum + SearchByProjection(local map), PoseOptimization")
 # BASELINE.json configs[1] (the configuration the metric is quoted on) and configs[3]
 CONFIGS = {
+    "c3": dict(w=752, h=480, nfeat=1000, streams=256, n_map=1500, inertial=True,
+               name="EuRoC V1_02-shaped stereo-inertial 752x480, 1000 feat, 8 levels (BASELINE config 3)"),
     "c1": dict(w=752, h=480, nfeat=1000, streams=512, n_map=1500, mono=True,
                name="EuRoC MH01-shaped monocular 752x480, 1000 feat, 8 levels (BASELINE config 1)"),
     "c2": dict(w=752, h=480, nfeat=1000, streams=256, n_map=1500,
@@ -59,12 +65,13 @@ MAP_NOTE = ("SURVEY 8(d) map per stream: every keypoint as a MapPoint (descripto
 
 def set_config(name):
     """Select the image geometry / feature budget the module-level helpers below work on."""
-    global W, H, NFEAT, WORKLOAD, MONO, UNIT
+    global W, H, NFEAT, WORKLOAD, MONO, UNIT, INERTIAL
     c = CONFIGS[name]
     W, H, NFEAT = c["w"], c["h"], c["nfeat"]
     MONO = bool(c.get("mono"))
+    INERTIAL = bool(c.get("inertial"))
     UNIT = "monocular frames/s" if MONO else "stereo frames/s"
-    WORKLOAD = c["name"] + ": " + (CHAIN_MONO if MONO else CHAIN)
+    WORKLOAD = c["name"] + ": " + (CHAIN_MONO if MONO else CHAIN_INERTIAL if INERTIAL else CHAIN)
     return c
 
 
@@ -265,13 +272,18 @@ class _CpuStreams:
             ur, dp = oracle.stereo_match([ex[0].pyramid_level(l) for l in range(NLEVELS)], [ex[1].pyramid_level(l) for l in range(NLEVELS)],
                                          kL, dL, kR, dR, ex[0].scale, ex[0].inv_scale, sc.BF, sc.BF / sc.FX)
             self.maps.append(sc.track_map_scenario(900 + j, kL, dL, ur, dp, self.Tt[j], n_map=n_map, W=W, H=H))
+        self.imu = [[sc.track_imu_scenario(7000 + 10 * j + m, self.Tt[j], m) for m in (1, 2)] for j in range(npool)] if INERTIAL else None
         self.n = npool
 
     def frame(self, j, extractors, two_threads=None):
         from replay_reference import track_frame_map
-        j %= self.n
+        i, j = j, j % self.n
+        mode = 0
+        if INERTIAL:
+            mode = 1 if i % IMU_KF_PERIOD == 0 else 2
         return track_frame_map(self.oracle, self.cam, self.imgs[2 * j], self.imgs[2 * j + 1], self.maps[j], self.Tp[j],
-                               nfeatures=NFEAT, extractors=extractors, mono=MONO)
+                               nfeatures=NFEAT, extractors=extractors, mono=MONO, imu=self.imu[j][mode - 1] if mode else None,
+                               imu_mode=mode)
 
 
 def cpu_baseline(n_frames, warm=20):
@@ -418,7 +430,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="c1: EuRoC 752x480 monocular (BASELINE config 1); "
-                    "c2: EuRoC 752x480 stereo (the metric's configuration); "
+                    "c2: EuRoC 752x480 stereo (the metric's configuration); c3: stereo-inertial (BASELINE config 3); "
                     "c4: 1920x1080 stereo, 2000 features (BASELINE config 4)")
     ap.add_argument("--streams", type=int, default=0, help="independent stereo streams per GPU per step (0: the config's default)")
     ap.add_argument("--workload", default="sec8d", choices=["sec8d", "selfmap"],
@@ -517,6 +529,19 @@ def main():
             entry["map_host"] = pm
             entry["map_dev_t"] = {k: torch.from_numpy(v).cuda() for k, v in pm.items()}
             entry["map_dev"] = {k: v.data_ptr() for k, v in entry["map_dev_t"].items()}
+        if INERTIAL:
+            # inertial inputs of both optimisers for this frame of every stream (tests/scenarios.track_imu_scenario)
+            entry["imu_host"], entry["imu_dev_t"], entry["imu_dev"] = {}, {}, {}
+            for m in (1, 2):
+                himu = sc.stack_track_imu([sc.track_imu_scenario(90000 + 1000 * r + 10 * s + m + 100000 * rank, Tt[r][s], m) for s in range(S)])
+                pin_imu = {}
+                for k, v in himu.items():
+                    a = orbx.host_array(v.shape, v.dtype)
+                    a[...] = v
+                    pin_imu[k] = a
+                entry["imu_host"][m] = pin_imu
+                entry["imu_dev_t"][m] = {k: torch.from_numpy(v).cuda() for k, v in pin_imu.items()}
+                entry["imu_dev"][m] = {k: v.data_ptr() for k, v in entry["imu_dev_t"][m].items()}
         sets.append(entry)
     d_prior_abs = torch.from_numpy(Tp_abs.reshape(S, 16)).cuda()
     d_true_abs = torch.from_numpy(Tt_abs.reshape(S, 16)).cuda()
@@ -532,6 +557,9 @@ def main():
         E = sets[step_no[0] % RING]
         if args.workload == "sec8d":
             trk.set_map(E["map_dev"])
+            if INERTIAL:
+                m = 1 if step_no[0] % IMU_KF_PERIOD == 0 else 2
+                trk.set_inertial(m, E["imu_dev"][m])
             trk.step_device(E["d_img"].data_ptr(), W, H, W, E["d_true"].data_ptr(), E["d_dT"].data_ptr(), d_out.data_ptr(),
                             d_stats.data_ptr())
         else:
@@ -651,6 +679,7 @@ def main():
         trk.synchronize()
         trk.set_chain(False)
         trk.set_map(None)
+        trk.set_inertial(0)
         wl = args.workload
         args.workload = "selfmap"
         for _ in range(3):
@@ -686,6 +715,9 @@ def main():
                     trk.upload_map(E["map_host"])
                 else:
                     trk.set_map(E["map_dev"])
+                if INERTIAL:   # the IMU pre-integration of the frame crosses PCIe with it, every step
+                    m = 1 if eno[0] % IMU_KF_PERIOD == 0 else 2
+                    trk.upload_inertial(m, E["imu_host"][m])
                 trk.submit(E["prep"], E["Tt"], E["dT"])
             else:
                 trk.submit(E["prep"], Tt_abs, Tp_abs)
@@ -724,7 +756,8 @@ def main():
     map_period = max(1, args.kf_period) if args.kf_period > 0 else 10
     map_uploads = len([k for k in range(e2e_steps) if k % map_period == 0]) if args.workload == "sec8d" else 0
     map_bytes = trk.map_bytes * map_uploads // max(e2e_steps, 1)     # amortised over the timed steps
-    h2d = B * W * H + 2 * S * 64 + map_bytes
+    imu_bytes = S * (12 + 24 + 8 * (21 + 16 + 45 + 6 + 81 + 9 + 9 + 21 + 225)) + 128 if INERTIAL else 0   # mode-2 upload (the common step)
+    h2d = B * W * H + 2 * S * 64 + map_bytes + imu_bytes
     d2h = S * 64 + S * 8 * 4
     clocks = sampler.stop() if rank == 0 else None
 
@@ -788,7 +821,7 @@ def main():
                                 "bytes_per_image": alg["total"], "ms": ext_total_ms}}
 
     cpu = None
-    if not args.no_cpu and world == 1 and args.config in ("c1", "c2"):
+    if not args.no_cpu and world == 1 and args.config in ("c1", "c2", "c3"):
         cpu = cpu_baseline(args.cpu_frames)
 
     mean_stats = {n: float(v) for n, v in zip(trk.STATS, stats.mean(0))}
