@@ -47,11 +47,13 @@ CHAIN = ("ORB extraction L+R, ComputeStereoMatches, SearchByProjection(last fram
          "isInFrustum + SearchByProjection(local map), PoseOptimization")
 # BASELINE.json configs[1] (the configuration the metric is quoted on) and configs[3]
 CONFIGS = {
-    "c3": dict(w=752, h=480, nfeat=1000, streams=256, n_map=1500, inertial=True,
+    "c3": dict(w=752, h=480, nfeat=1000, streams=444, n_map=1500, inertial=True,
                name="EuRoC V1_02-shaped stereo-inertial 752x480, 1000 feat, 8 levels (BASELINE config 3)"),
-    "c1": dict(w=752, h=480, nfeat=1000, streams=512, n_map=1500, mono=True,
+    "c1": dict(w=752, h=480, nfeat=1000, streams=888, n_map=1500, mono=True,
                name="EuRoC MH01-shaped monocular 752x480, 1000 feat, 8 levels (BASELINE config 1)"),
-    "c2": dict(w=752, h=480, nfeat=1000, streams=256, n_map=1500,
+    # streams per GPU: a multiple of the 148 SMs (one PoseOptimization CTA per stream, two resident per SM); measured
+    # 256 -> 42.0 k, 296 -> 43.8 k, 444 -> 44.8 k, 592 -> 44.3 k frames/s (profiles/r02v_streams_sweep.md)
+    "c2": dict(w=752, h=480, nfeat=1000, streams=444, n_map=1500,
                name="EuRoC MH01-shaped stereo 752x480, 1000 feat, 8 levels"),
     "c4": dict(w=1920, h=1080, nfeat=2000, streams=32, n_map=3000,
                name="synthetic 1920x1080 stereo, 2000 feat, 8 levels (BASELINE config 4)"),
