@@ -539,6 +539,13 @@ __device__ bool ldlt_solve_smem(double* A, const double* b, double* x) {
 // PO_NT = 128 a CTA holds half the registers of the SM's two resident problems, so that the extractor's CTAs of the next
 // step (other stream) find room beside them.
 #define PO_VT 256
+// Speculative damping trials.  When a trial is rejected, g2o multiplies lambda by ni and doubles ni
+// (optimization_algorithm_levenberg.cpp:120-128): the lambdas of the NEXT rejections are known in advance.  Every round
+// ends with a chain of ~5 rejected trials whose matrices all differ (lambda crosses 40 orders of magnitude in five steps),
+// each costing a serial 6x6 solve + exp on one warp while seven wait.  From the second solved trial of an iteration on,
+// warps 0..PO_NSPEC-1 therefore solve the next PO_NSPEC lambdas of the chain side by side; a later trial whose lambda is
+// found among them (exact comparison) skips its solve.  Same arithmetic, same decisions, fewer serial phases.
+#define PO_NSPEC 5
 #ifndef PO_NT
 #define PO_NT 256
 #endif
@@ -585,10 +592,13 @@ __global__ void __launch_bounds__(PO_NT, 512 / PO_NT) pose_opt_kernel(const Pose
   const long long tStart = t0;
   const int e0 = A.edgeStart ? A.edgeStart[prob] : A.edgeOfs[prob];
   const int E = A.edgeStart ? A.edgeCount[prob] : A.edgeOfs[prob + 1] - e0;
-  __shared__ SE3d s_est, s_trial, s_init;
+  __shared__ SE3d s_est, s_init;
   __shared__ double s_red[(PO_VT / 32) * 28];
-  __shared__ double s_H[36], s_b[6], s_x[6], s_A[36], s_tot[28];
-  __shared__ int s_ok;
+  __shared__ double s_H[36], s_b[6], s_tot[28];
+  // damping-trial candidates: slot w holds the solve for the lambda reached after w further rejections (PO_NSPEC below)
+  __shared__ SE3d s_cTrial[PO_NSPEC];
+  __shared__ double s_cA[PO_NSPEC][36], s_cX[PO_NSPEC][6], s_cLambda[PO_NSPEC];
+  __shared__ int s_cOk[PO_NSPEC];
   const float* xw = A.xw + 3 * (size_t)e0;
   const float* obs = A.obs + 3 * (size_t)e0;
   const float* isg = A.invSigma2 + e0;
@@ -690,8 +700,9 @@ __global__ void __launch_bounds__(PO_NT, 512 / PO_NT) pose_opt_kernel(const Pose
       // whose damped matrix H + lambda*I is bit-identical to the last SOLVED trial's reproduces that trial exactly
       // (same update, same estimate, same residuals, same chi2), so it is replayed from the saved results instead of
       // being solved again; only rho's denominator, which depends on lambda itself, is recomputed.
-      bool haveTrial = false;
+      bool haveTrial = false, lastScalePos = false;
       double lastLambda = 0, trialChi = 0;
+      int nCand = 0, cur = 0;
       do {
         bool same = haveTrial;
         if (same) {
@@ -700,23 +711,38 @@ __global__ void __launch_bounds__(PO_NT, 512 / PO_NT) pose_opt_kernel(const Pose
         }
         if (!same) {
           PO_TICK(5);
-          PO_COUNT(9);
-          __syncthreads();                        // every thread is done with s_x / s_ok of the previous trial
-          if (tid < 32) {                         // warp 0: 6x6 solve cooperatively, then lane 0 applies the update
-            for (int i = tid; i < 36; i += 32) s_A[i] = s_H[i] + ((i % 7 == 0) ? lambda : 0.0);
-            if (tid < 6) s_x[tid] = 0;
-            __syncwarp();
-            const bool okSolve = ldlt6_solve_shfl(s_A, s_b, s_x);
-            if (tid == 0) {
-              s_ok = okSolve ? 1 : 0;
-              double x[6];
-              for (int i = 0; i < 6; ++i) x[i] = s_x[i];
-              s_trial = se3_mul(se3_exp(x), s_est);   // push(); oplus: exp(update) * estimate
+          int hit = -1;
+          for (int c = 0; c < nCand; ++c)
+            if (s_cLambda[c] == lambda) hit = c;
+          if (hit < 0) {
+            PO_COUNT(9);
+            __syncthreads();                      // every thread is done with the previous candidates
+            const int ns = haveTrial ? PO_NSPEC : 1;   // the first trial of an iteration is usually accepted: no speculation
+            const int wid = tid >> 5, lane = tid & 31;
+            if (wid < ns) {                       // warp w: 6x6 solve for the lambda after w more rejections, then lane 0 applies the update
+              double lam = lambda, nn = ni;
+              for (int k = 0; k < wid; ++k) { lam *= nn; nn *= 2; }
+              double* cA = s_cA[wid];
+              double* cX = s_cX[wid];
+              for (int i = lane; i < 36; i += 32) cA[i] = s_H[i] + ((i % 7 == 0) ? lam : 0.0);
+              if (lane < 6) cX[lane] = 0;
+              __syncwarp();
+              const bool okSolve = ldlt6_solve_shfl(cA, s_b, cX);
+              if (lane == 0) {
+                s_cOk[wid] = okSolve ? 1 : 0;
+                s_cLambda[wid] = lam;
+                double x[6];
+                for (int i = 0; i < 6; ++i) x[i] = cX[i];
+                s_cTrial[wid] = se3_mul(se3_exp(x), s_est);   // push(); oplus: exp(update) * estimate
+              }
             }
+            __syncthreads();
+            nCand = ns;
+            hit = 0;
           }
-          __syncthreads();
+          cur = hit;
           PO_TICK(2);
-          const SE3d trial = s_trial;
+          const SE3d trial = s_cTrial[cur];
           double chi[1];
           for (int v = tid; v < PO_VT; v += PO_NT) {
           chi[0] = 0;
@@ -750,11 +776,21 @@ __global__ void __launch_bounds__(PO_NT, 512 / PO_NT) pose_opt_kernel(const Pose
           PO_COUNT(10);
         }
         double tempChi = trialChi;
-        if (!s_ok) tempChi = 1.7976931348623157e308;
+        if (!s_cOk[cur]) tempChi = 1.7976931348623157e308;
         rho = currentChi - tempChi;
+        if (same && rho < 0 && lastScalePos) {
+          // replayed trial that made things worse: rho's denominator sum_j x_j (lambda x_j + b_j) + 1e-3 was positive for the
+          // smaller lambda of the solved trial and only grows with lambda (x, b unchanged, x.b = x^T (H + lambda I) x > 0), so
+          // rho stays negative: reject without the sum and the division
+          lambda *= ni;
+          ni *= 2;
+          ++qmax;
+          continue;
+        }
         double scale = 0;
-        for (int j = 0; j < 6; ++j) scale += s_x[j] * (lambda * s_x[j] + s_b[j]);
+        for (int j = 0; j < 6; ++j) scale += s_cX[cur][j] * (lambda * s_cX[cur][j] + s_b[j]);
         scale += 1e-3;
+        lastScalePos = scale > 0;
         rho /= scale;
         if (rho > 0 && isfinite(tempChi)) {
           const double tr = 2 * rho - 1;
@@ -765,7 +801,7 @@ __global__ void __launch_bounds__(PO_NT, 512 / PO_NT) pose_opt_kernel(const Pose
           ni = 2;
           currentChi = tempChi;
           __syncthreads();                        // every thread has read s_est / s_trial of this trial
-          if (tid == 0) s_est = s_trial;          // keep the update (discardTop)
+          if (tid == 0) s_est = s_cTrial[cur];    // keep the update (discardTop)
           __syncthreads();
         } else {
           lambda *= ni;                           // pop(): s_est was never overwritten

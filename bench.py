@@ -697,7 +697,7 @@ def main():
     # its poses + statistics back, all inside the timed region, through orbx_tracker_upload_map + orbx_tracker_submit /
     # orbx_tracker_collect: the H2D of step t+1 runs on a copy stream under the kernels of step t, and matching + pose
     # optimisation of step t overlap the extraction of step t+1, so two steps are in flight.
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 40))      # >= 2 map uploads at the default 20 steps; 10-step samples were too noisy
     e2e_ms, e2e_same = 0.0, None
     if not args.no_e2e:
         trk.set_overlap(True)
