@@ -536,8 +536,7 @@ __device__ bool ldlt_solve_smem(double* A, const double* b, double* x) {
 // =====================================================================================
 // PO_VT "virtual threads" fix the summation order of every reduction (edge e belongs to virtual thread e % PO_VT; lane
 // butterfly inside each virtual warp, then the virtual warps in index order), PO_NT real threads execute them: with
-// PO_NT = 128 a CTA holds half the registers of the SM's two resident problems, so that the extractor's CTAs of the next
-// step (other stream) find room beside them.
+// PO_NT = 128 a CTA would hold half the registers (measured: slower overall, profiles/r02x_pose_footprint.md; 256 is used).
 #define PO_VT 256
 // Speculative damping trials.  When a trial is rejected, g2o multiplies lambda by ni and doubles ni
 // (optimization_algorithm_levenberg.cpp:120-128): the lambdas of the NEXT rejections are known in advance.  Every round
@@ -545,11 +544,7 @@ __device__ bool ldlt_solve_smem(double* A, const double* b, double* x) {
 // each costing a serial 6x6 solve + exp on one warp while seven wait.  From the second solved trial of an iteration on,
 // warps 0..PO_NSPEC-1 therefore solve the next PO_NSPEC lambdas of the chain side by side; a later trial whose lambda is
 // found among them (exact comparison) skips its solve.  Same arithmetic, same decisions, fewer serial phases.
-#define PO_NSPEC 5
-#ifndef PO_NT
-#define PO_NT 256
-#endif
-static_assert(PO_VT % PO_NT == 0 && PO_NT % 32 == 0 && PO_NT >= 64, "pose_opt_kernel thread mapping");
+#define PO_NSPEC_MAX 5
 
 // lane butterfly of NV doubles, then lane 0 stores the virtual warp's partials (no barriers: the caller places them)
 template <int NV>
@@ -586,7 +581,10 @@ __device__ unsigned long long g_po_prof[16];
 #define PO_TICK(k) do { if (A.profile && tid == 0) { const long long t1_ = clock64(); atomicAdd(&g_po_prof[k], (unsigned long long)(t1_ - t0)); t0 = t1_; } } while (0)
 #define PO_COUNT(k) do { if (A.profile && tid == 0) atomicAdd(&g_po_prof[k], 1ull); } while (0)
 
+template <int PO_NT>
 __global__ void __launch_bounds__(PO_NT, 512 / PO_NT) pose_opt_kernel(const PoseOptArgs A) {
+  constexpr int PO_NSPEC = PO_NT / 32 < PO_NSPEC_MAX ? PO_NT / 32 : PO_NSPEC_MAX;
+  static_assert(PO_VT % PO_NT == 0 && PO_NT % 32 == 0 && PO_NT >= 64, "pose_opt_kernel thread mapping");
   const int prob = blockIdx.x, tid = threadIdx.x;
   long long t0 = A.profile ? clock64() : 0ll;
   const long long tStart = t0;
@@ -596,9 +594,9 @@ __global__ void __launch_bounds__(PO_NT, 512 / PO_NT) pose_opt_kernel(const Pose
   __shared__ double s_red[(PO_VT / 32) * 28];
   __shared__ double s_H[36], s_b[6], s_tot[28];
   // damping-trial candidates: slot w holds the solve for the lambda reached after w further rejections (PO_NSPEC below)
-  __shared__ SE3d s_cTrial[PO_NSPEC];
-  __shared__ double s_cA[PO_NSPEC][36], s_cX[PO_NSPEC][6], s_cLambda[PO_NSPEC];
-  __shared__ int s_cOk[PO_NSPEC];
+  __shared__ SE3d s_cTrial[PO_NSPEC_MAX];
+  __shared__ double s_cA[PO_NSPEC_MAX][36], s_cX[PO_NSPEC_MAX][6], s_cLambda[PO_NSPEC_MAX];
+  __shared__ int s_cOk[PO_NSPEC_MAX];
   const float* xw = A.xw + 3 * (size_t)e0;
   const float* obs = A.obs + 3 * (size_t)e0;
   const float* isg = A.invSigma2 + e0;
@@ -1773,7 +1771,10 @@ int orbx_launch_pose_opt_slices(orbx_ctx* ctx, cudaStream_t st, int P, const int
   A.iters = d_iters;
   A.err = d_scratch;
   A.profile = g_po_profile;
-  pose_opt_kernel<<<P, PO_NT, 0, st>>>(A);
+  // Many-stream tracker: a problem's CTA holds 32 K registers for ~0.4 ms while most of its warps wait, and the extractor's
+  // CTAs of the next step (other stream) only get what is left.  Both ways of shrinking that footprint were measured and
+  // lost (profiles/r02x_pose_footprint.md): 128 threads per problem, and one problem per SM.
+  pose_opt_kernel<256><<<P, 256, 0, st>>>(A);
   ORBX_LAUNCH(ctx);
   ORBX_CUDA(cudaGetLastError());
   return ORBX_OK;
@@ -2826,7 +2827,7 @@ int orbx_pose_optimization_batch_device(orbx_ctx* ctx, int P, const int32_t* d_e
   A.iters = d_iters;
   A.err = d_scratch;
   A.profile = g_po_profile;
-  pose_opt_kernel<<<P, PO_NT, 0, ctx->stream>>>(A);
+  pose_opt_kernel<256><<<P, 256, 0, ctx->stream>>>(A);
   ORBX_LAUNCH(ctx);
   ORBX_CUDA(cudaGetLastError());
   return ORBX_OK;
