@@ -192,7 +192,7 @@ static int configure_geometry(orbx_ext* e, int w, int h, int B) {
     fastBytes = std::max(fastBytes, ORBX_FAST_TP * (L.hCell + 14));
     fastScore = std::max(fastScore, ORBX_FAST_TP * (L.hCell + 2));
     fastCand = std::max(fastCand, (int)align_up((size_t)(L.fastCells * L.wCell) * L.hCell, 64));
-    L.blurTilesX = div_up(L.w, ORBX_BLUR_TW);        // warp tiles per row: 128 columns per warp (32 lanes x 4 px)
+    L.blurTilesX = div_up(L.w, ORBX_BLUR_TW);        // warp tiles per row: 120 columns per warp (30 output words + 2 halo lanes)
     L.blurTilesY = div_up(L.h, ORBX_BLUR_STRIP);     // warp tiles per column: 32-row strips
     L.blurTileStart = btile;
     btile += div_up(L.blurTilesX * L.blurTilesY, 8); // a CTA takes 8 consecutive warp tiles (row-major)

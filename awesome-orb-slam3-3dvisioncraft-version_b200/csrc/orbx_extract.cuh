@@ -7,7 +7,7 @@
 #define ORBX_MINB 16          // minBorderX = EDGE_THRESHOLD-3, src/ORBextractor.cc:771
 #define ORBX_FAST_CELLS 8     // cells per FAST tile (one cell row x up to 8 cells)
 #define ORBX_FAST_TP 240      // row pitch in bytes of the FAST shared-memory planes = TMA box width (compile-time: immediate offsets; a multiple of 16 for TMA; 60 words = -4 banks per row, so the 8 rows of a strip column hit 8 different banks: 256 B measured 5x the bank conflicts and 2.4 ms instead of 1.75)
-#define ORBX_BLUR_TW 128
+#define ORBX_BLUR_TW 120   // output columns per warp tile of the blur kernel (30 words; 2 lanes carry the halo)
 #define ORBX_BLUR_STRIP 32    // output rows per warp tile of the blur kernel
 
 // One pyramid level of a batch of B equally sized images.

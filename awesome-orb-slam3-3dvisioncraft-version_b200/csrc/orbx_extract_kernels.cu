@@ -519,13 +519,21 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
 // =====================================================================================
 // K5  7x7 sigma-2 Gaussian, OpenCV 4.x fixed point: [18,34,48,56,48,34,18]/256 per pass,
 //     (sum + 2^15) >> 16, BORDER_REFLECT_101.
-// Register-sliding separable filter, no shared memory: a thread owns 4 adjacent columns (one 32-bit word)
-// and walks down a strip of rows.  Per row it forms the 4 horizontal 7-tap sums with DP4A (u8 pixels x
-// s8 weights, two 4-byte windows per output built by funnel shifts), keeps the last 7 rows of those
-// sums in registers, and emits one packed output word per row from the vertical 7-tap combination.
-// A warp covers 128 columns; global loads are one coalesced 128-byte row segment plus two halo words.
+// Register-sliding separable filter, no shared memory, VERTICAL PASS FIRST.  Both passes are exact integer sums, so their
+// order is free: out = (sum_i wh_i * V(x+i-3, y) + 2^15) >> 16 with V(x, y) = sum_j wv_j * p(x, y+j-3) <= 255 * 256.
+// A thread owns one 32-bit word (4 adjacent columns) and walks down a strip of rows keeping the last 7 rows of ITS word
+// unpacked to 16-bit lanes (14 registers; the horizontal-first form kept 28 horizontal sums and three words per row):
+//   * vertical: the symmetric taps are added as packed 16-bit lanes and scaled by 4 packed multiply-adds per register
+//     (no lane overflows: V < 2^16): 16 instructions give V of the 4 columns as two u16x2 registers;
+//   * horizontal: the neighbours' V registers come by 4 warp shuffles, and every output column is 4 DP2A (u16 x u8)
+//     against weight words whose unused lane is 0 -- the register pairs (-4,-3) (-2,-1) (0,1) (2,3) (4,5) (6,7) line up
+//     with every window without any re-alignment;
+//   * borders: a lane's word is "virtual": columns outside [0, w) are reflected when the ROW IS LOADED (two words + one
+//     PRMT with a thread-invariant selector), so V of a reflected column is right by construction.  Lanes 0 and 31 of a
+//     warp only carry the halo words; a warp tile is 30 output words wide.
 // =====================================================================================
-#define BLUR_STRIP ORBX_BLUR_STRIP   // output rows per warp (6 extra rows are filtered horizontally per strip)
+#define BLUR_STRIP ORBX_BLUR_STRIP   // output rows per warp
+#define BLUR_OW (ORBX_BLUR_TW / 4)   // output words per warp tile
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (i < 0) i = -i;
@@ -533,57 +541,8 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return min(max(i, 0), n - 1);
 }
 
-// The three words (columns 4c-4 .. 4c+7) a thread needs from a row, with BORDER_REFLECT_101 outside [0, w), branch-free:
-// the words are loaded at clamped indices and the reflected bytes are patched in with byte permutes whose selectors
-// depend only on the thread's column (computed once per strip).  Reflected pixels always lie within the two words next
-// to the border, so every patch is one PRMT of an adjacent word pair.
-struct BlurCols {
-  int ia, ib, ic;              // clamped word indices
-  unsigned selB, selC;         // PRMT selectors
-  bool fixA, fixB, fixCab, fixCbc;
-};
-__device__ __forceinline__ BlurCols blur_cols(int c, int w) {
-  BlurCols q;
-  const int E = (w - 1) >> 2, m = (w - 1) & 3;   // last word, byte of the last valid pixel in it
-  q.ia = max(c - 1, 0); q.ib = c; q.ic = min(c + 1, E);
-  q.fixA = c == 0;                               // pixels -4..-1 = pixels 4,3,2,1 = PRMT(word0, word1, 0x1234)
-  q.fixB = c == E && m < 3;
-  q.fixCab = c == E;                             // word E+1 mirrors into (word E-1, word E)
-  q.fixCbc = c == E - 1 && m < 3;                // word E holds invalid bytes k > m: mirror from (word E-1, word E)
-  unsigned sb = 0, sc = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    // selectors index the pair (lo word: 0-3, hi word: 4-7); for fixB / fixCbc the hi word is word E, for fixCab too
-    sb |= (unsigned)(k <= m ? 4 + k : 4 + 2 * m - k) << (4 * k);
-    const int nc = (c == E) ? max(2 * m - k, 0)   // word E+1, byte k -> pixel 4E + 2m - 4 - k (only k < m is ever used)
-                            : (k <= m ? 4 + k : 4 + 2 * m - k);
-    sc |= (unsigned)nc << (4 * k);
-  }
-  q.selB = sb; q.selC = sc;
-  return q;
-}
-__device__ __forceinline__ void blur_words(const uint8_t* __restrict__ row, const BlurCols& q, uint32_t& a, uint32_t& b, uint32_t& c) {
-  const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row);
-  const uint32_t a0 = __ldg(r32 + q.ia), b0 = __ldg(r32 + q.ib), c0 = __ldg(r32 + q.ic);
-  a = q.fixA ? __byte_perm(b0, c0, 0x1234) : a0;
-  b = q.fixB ? __byte_perm(a0, b0, q.selB) : b0;
-  c = q.fixCab ? __byte_perm(a0, b0, q.selC) : (q.fixCbc ? __byte_perm(b0, c0, q.selC) : c0);
-}
-
-// horizontal 7-tap sums of the 4 pixels of word `b`, given its left/right neighbours
-__device__ __forceinline__ void blur_hrow(uint32_t a, uint32_t b, uint32_t c, int (&h)[4]) {
-  const unsigned W0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);   // taps -3..0
-  const unsigned W1 = 48u | (34u << 8) | (18u << 16);                 // taps +1..+3
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    // window A = pixels p-3..p, window B = pixels p+1..p+4 (p = 4c+k)
-    const uint32_t wa = k == 3 ? b : __funnelshift_r(a, b, 8 * (k + 1));
-    const uint32_t wb = __funnelshift_rc(b, c, 8 * (k + 1));   // clamp mode: a shift of 32 yields `c`
-    h[k] = (int)__dp4a(wb, W1, __dp4a(wa, W0, 0u));
-  }
-}
-
-__global__ void __launch_bounds__(256, 3) gauss7_kernel(const __grid_constant__ ExtractParams p) {
+__global__ void __launch_bounds__(256, 4) gauss7_kernel(const __grid_constant__ ExtractParams p) {
+  static_assert(BLUR_OW == 30, "a warp tile is 30 output words + 2 halo lanes");
   const int tile = blockIdx.x;
   int level = 0;
 #pragma unroll 1
@@ -591,68 +550,86 @@ __global__ void __launch_bounds__(256, 3) gauss7_kernel(const __grid_constant__ 
     if (tile >= p.lv[l].blurTileStart) level = l;
   // everything the row loop needs from the (dynamically indexed) level record, once, in registers
   const int w = p.lv[level].w, h = p.lv[level].h, pitch = p.lv[level].pitch, opitch = p.lv[level].blurPitch;
-  // warp tiles (128 columns x BLUR_STRIP rows) are numbered row-major and a CTA takes 8 consecutive ones: its warps sit
-  // side by side on the same rows, so the CTA streams whole contiguous image rows (DRAM-page friendly) instead of eight
-  // 128-byte columns with a stride of one pitch
+  // warp tiles (120 columns x BLUR_STRIP rows) are numbered row-major and a CTA takes 8 consecutive ones: its warps sit
+  // side by side on the same rows, so the CTA streams whole contiguous image rows (DRAM-page friendly)
   const int lt = tile - p.lv[level].blurTileStart, tilesX = p.lv[level].blurTilesX;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wt = lt * 8 + wid;
   const int tyi = wt / tilesX, txi = wt - tyi * tilesX;
-  const int c = txi * 32 + lane;                       // word column
   const int y0 = tyi * BLUR_STRIP;                     // first output row of this warp's strip
-  if (4 * c >= w || y0 >= h) return;
+  const int E = (w - 1) >> 2;                          // last word of a row
+  if (txi * BLUR_OW > E || y0 >= h) return;            // warp-uniform
+  const int cv = txi * BLUR_OW + lane - 1;             // this lane's (virtual) word: -1 and E+1 are the reflected halos
+  const bool writes = lane >= 1 && lane <= BLUR_OW && cv <= E;
   const uint8_t* img = p.lv[level].pyr + (size_t)blockIdx.y * p.lv[level].imgStride;
-  uint8_t* out = p.lv[level].blur + (size_t)blockIdx.y * p.lv[level].blurStride + 4 * c;
+  uint8_t* out = p.lv[level].blur + (size_t)blockIdx.y * p.lv[level].blurStride + 4 * max(cv, 0);
   const int y1 = min(y0 + BLUR_STRIP, h);
-  const BlurCols q = blur_cols(c, w);
-  // per-thread column pointers (the three clamped words of a row), advanced by whole rows
-  const uint32_t* colA = reinterpret_cast<const uint32_t*>(img) + q.ia;
-  const int dB = q.ib - q.ia, dC = q.ic - q.ia;        // 0 or 1 / 1 or 2 words to the right of colA
-  // raw loads and border fix-up are separate so that the loads of the NEXT row can be issued before the arithmetic of the
-  // current one (the kernel is bound by load latency, not by issue slots: one row in flight per warp was 46 % issue
-  // utilisation with "long scoreboard" as the top stall)
-  auto load_raw = [&](int yy, uint32_t& a0, uint32_t& b0, uint32_t& c0) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(colA) + (size_t)yy * pitch);
-    a0 = __ldg(r); b0 = __ldg(r + dB); c0 = __ldg(r + dC);
+  // source of the virtual word: its 4 reflected columns lie within two adjacent words
+  int base;
+  unsigned sel = 0;
+  {
+    int sc[4], lo = w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sc[k] = reflect101(4 * cv + k, w); lo = min(lo, sc[k]); }
+    base = lo >> 2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sel |= (unsigned)(sc[k] - 4 * base) << (4 * k);
+  }
+  const bool fix = sel != 0x3210u;
+  const int second = min(base + 1, E) - base;          // 0 or 1 words to the right
+  const uint32_t* col = reinterpret_cast<const uint32_t*>(img) + base;
+  // raw loads and border fix-up are separate so that the loads of the NEXT row are issued before the arithmetic of the
+  // current one
+  auto load_raw = [&](int yy, uint32_t& a0, uint32_t& b0) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(col) + (size_t)yy * pitch);
+    a0 = __ldg(r);
+    b0 = fix ? __ldg(r + second) : 0u;
   };
-  auto fix_row = [&](uint32_t a0, uint32_t b0, uint32_t c0, uint32_t& wa, uint32_t& wb, uint32_t& wc) {
-    wa = q.fixA ? __byte_perm(b0, c0, 0x1234) : a0;
-    wb = q.fixB ? __byte_perm(a0, b0, q.selB) : b0;
-    wc = q.fixCab ? __byte_perm(a0, b0, q.selC) : (q.fixCbc ? __byte_perm(b0, c0, q.selC) : c0);
+  auto unpack = [&](uint32_t a0, uint32_t b0, uint32_t (&u)[2]) {
+    const uint32_t v = fix ? __byte_perm(a0, b0, sel) : a0;
+    u[0] = __byte_perm(v, 0u, 0x4140);                 // columns 0,1 as 16-bit lanes
+    u[1] = __byte_perm(v, 0u, 0x4342);                 // columns 2,3
   };
   auto bottom = [&](int yy) { return yy >= h ? max(2 * (h - 1) - yy, 0) : yy; };   // rows below the image reflect
-  int hs[7][4];   // horizontal sums of rows y-3..y+3 (statically indexed: the row loop is unrolled by 7)
-  // prologue: rows y0-3 .. y0+2 (six independent rows: all 18 loads are issued before the first use)
+  uint32_t U[7][2];   // rows y-3..y+3 of this lane's word (statically indexed: the row loop is unrolled by 7)
+  // prologue: rows y0-3 .. y0+2 (six independent rows: all loads are issued before the first use)
   {
-    uint32_t ra[6], rb[6], rc[6];
+    uint32_t ra[6], rb[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) load_raw(reflect101(y0 - 3 + r, h), ra[r], rb[r], rc[r]);
+    for (int r = 0; r < 6; ++r) load_raw(reflect101(y0 - 3 + r, h), ra[r], rb[r]);
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      uint32_t wa, wb, wc;
-      fix_row(ra[r], rb[r], rc[r], wa, wb, wc);
-      blur_hrow(wa, wb, wc, hs[r]);
-    }
+    for (int r = 0; r < 6; ++r) unpack(ra[r], rb[r], U[r]);
   }
-  uint32_t na, nb, nc;                                   // row y+3 of the next output row, already on its way
-  load_raw(bottom(y0 + 3), na, nb, nc);
+  uint32_t na, nb;                                       // row y+3 of the next output row, already on its way
+  load_raw(bottom(y0 + 3), na, nb);
+  const unsigned WA = 0u | (18u << 8) | (34u << 16) | (48u << 24);     // lane weights (0,18 | 34,48)
+  const unsigned WB = 56u | (48u << 8) | (34u << 16) | (18u << 24);    // (56,48 | 34,18)
+  const unsigned WC = 18u | (34u << 8) | (48u << 16) | (56u << 24);    // (18,34 | 48,56)
+  const unsigned WD = 48u | (34u << 8) | (18u << 16) | (0u << 24);     // (48,34 | 18,0)
   for (int yb = y0; yb < y1; yb += 7) {
 #pragma unroll
     for (int u = 0; u < 7; ++u) {
       const int y = yb + u;
-      if (y < y1) {
+      if (y < y1) {                                      // warp-uniform
         // newest row y+3 goes to slot (6+u)%7; rows y-3..y+3 sit in slots (u+j)%7, j = 0..6
-        uint32_t wa, wb, wc;
-        fix_row(na, nb, nc, wa, wb, wc);
-        if (y + 1 < y1) load_raw(bottom(y + 4), na, nb, nc);   // prefetch for the next output row
-        blur_hrow(wa, wb, wc, hs[(6 + u) % 7]);
-        unsigned acc[4];
+        unpack(na, nb, U[(6 + u) % 7]);
+        if (y + 1 < y1) load_raw(bottom(y + 4), na, nb);   // prefetch for the next output row
+        uint32_t V[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)      // < 2^24; the rounded result is byte 2 of the accumulator
-          acc[k] = 18u * (unsigned)(hs[u % 7][k] + hs[(u + 6) % 7][k]) + 34u * (unsigned)(hs[(u + 1) % 7][k] + hs[(u + 5) % 7][k]) +
-                   48u * (unsigned)(hs[(u + 2) % 7][k] + hs[(u + 4) % 7][k]) + (56u * (unsigned)hs[(u + 3) % 7][k] + 32768u);
-        const uint32_t o = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
-        *reinterpret_cast<uint32_t*>(out + (size_t)y * opitch) = o;   // pitch padding absorbs the tail
+        for (int q = 0; q < 2; ++q)                      // packed 16-bit lanes, every partial result < 2^16
+          V[q] = 18u * (U[u % 7][q] + U[(u + 6) % 7][q]) + 34u * (U[(u + 1) % 7][q] + U[(u + 5) % 7][q]) +
+                 48u * (U[(u + 2) % 7][q] + U[(u + 4) % 7][q]) + 56u * U[(u + 3) % 7][q];
+        const uint32_t A = __shfl_up_sync(0xffffffffu, V[0], 1), B = __shfl_up_sync(0xffffffffu, V[1], 1);
+        const uint32_t Eo = __shfl_down_sync(0xffffffffu, V[0], 1), F = __shfl_down_sync(0xffffffffu, V[1], 1);
+        const uint32_t C = V[0], D = V[1];
+        // column k: window k-3..k+3 over the pairs (-4,-3)=A (-2,-1)=B (0,1)=C (2,3)=D (4,5)=Eo (6,7)=F
+        const unsigned acc0 = __dp2a_hi(D, WB, __dp2a_lo(C, WB, __dp2a_hi(B, WA, __dp2a_lo(A, WA, 32768u))));
+        const unsigned acc1 = __dp2a_hi(Eo, WD, __dp2a_lo(D, WD, __dp2a_hi(C, WC, __dp2a_lo(B, WC, 32768u))));
+        const unsigned acc2 = __dp2a_hi(Eo, WB, __dp2a_lo(D, WB, __dp2a_hi(C, WA, __dp2a_lo(B, WA, 32768u))));
+        const unsigned acc3 = __dp2a_hi(F, WD, __dp2a_lo(Eo, WD, __dp2a_hi(D, WC, __dp2a_lo(C, WC, 32768u))));
+        // < 2^24; the rounded result is byte 2 of the accumulator
+        const uint32_t o = __byte_perm(__byte_perm(acc0, acc1, 0x0062), __byte_perm(acc2, acc3, 0x0062), 0x5410);
+        if (writes) *reinterpret_cast<uint32_t*>(out + (size_t)y * opitch) = o;   // pitch padding absorbs the tail
       }
     }
   }
