@@ -768,9 +768,18 @@ int orbx_tracker_set_map(orbx_tracker* t, const orbx_track_map* map) {
       orbx_set_error("orbx_tracker_set_map: incomplete map, or m_cap != orbx_tracker_map_capacity() = %d", t->mcap);
       return ORBX_EINVAL;
     }
+    // the same arrays as the binding in place (e.g. orbx_tracker_upload_map refilling its slot buffer): the argument blocks
+    // already point there, nothing to rebind
+    const orbx_track_map& c = t->map;
+    if (t->haveMap && c.m_cap == map->m_cap && c.n_map == map->n_map && c.xw == map->xw && c.desc == map->desc &&
+        c.last_flags == map->last_flags && c.last_octave == map->last_octave && c.last_angle == map->last_angle &&
+        c.map_flags == map->map_flags && c.max_dist == map->max_dist && c.min_dist == map->min_dist && c.normal == map->normal &&
+        c.log_scale_factor == map->log_scale_factor)
+      return ORBX_OK;
     t->map = *map;
     t->haveMap = true;
   } else {
+    if (!t->haveMap) return ORBX_OK;
     t->haveMap = false;
   }
   t->mapVersion++;

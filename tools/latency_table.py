@@ -102,6 +102,21 @@ def main():
         return trk1.step([L, R], Tt1, Tp1)
     add("whole per-frame chain of ONE stereo frame (extract L+R .. PoseOptimization #2), 1500-point map",
         "src/Tracking.cc:1793-2480", chain_gpu, lambda: track_frame_map(oracle, cam, L, R, mp1, Tp1[0], extractors=oex), 30, 5)
+    # the same with the caller's frame buffers and map arrays in page-locked memory (what a capture pipeline that feeds a
+    # GPU keeps them in): the images are DMA'd in place instead of being staged, the ten map arrays are true async copies
+    pin = orbx.host_array((2,) + L.shape, np.uint8)
+    pin[0], pin[1] = L, R
+    host1p = {}
+    for k, v in host1.items():
+        host1p[k] = orbx.host_array(v.shape, v.dtype)
+        host1p[k][...] = v
+
+    def chain_gpu_pinned():
+        trk1.upload_map(host1p)
+        return trk1.step([pin[0], pin[1]], Tt1, Tp1)
+    assert np.array_equal(chain_gpu()[1], chain_gpu_pinned()[1])
+    add("  ... the same, frame buffers and map arrays page-locked", "orbx_host_alloc", chain_gpu_pinned,
+        lambda: track_frame_map(oracle, cam, L, R, mp1, Tp1[0], extractors=oex), 30, 5)
     trk1.close()
     ex1.close()
     q = sc.tri_scenario(3, kL, dL, ur)
