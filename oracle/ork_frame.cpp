@@ -62,12 +62,19 @@ int ork_is_in_frustum(const orbx_camera* cam, const float* Rcw, const float* tcw
 
 // cv::undistortPoints(src, dst, K, D, noArray(), P = K) on n points; dist = (k1, k2, p1, p2[, k3]); ndist = 4 or 5.
 // The reference skips the call when k1 == 0 (src/Frame.cc:877-881): then the keypoints are copied.
+int ork_cv_undistort_points(const float* xy, int n, const orbx_camera* cam, const float* dist, int ndist, float* out_xy);
 int ork_undistort_points(const float* xy, int n, const orbx_camera* cam, const float* dist, int ndist, float* out_xy) {
   if (ndist < 4) return ORBX_EINVAL;
   if (dist[0] == 0.0f) {
     for (int i = 0; i < 2 * n; ++i) out_xy[i] = xy[i];
     return ORBX_OK;
   }
+  return ork_cv_undistort_points(xy, n, cam, dist, ndist, out_xy);
+}
+
+// cv::undistortPoints itself (no shortcut): what oracle/ref_stub's stand-in calls when the reference's Frame.cc does
+int ork_cv_undistort_points(const float* xy, int n, const orbx_camera* cam, const float* dist, int ndist, float* out_xy) {
+  if (ndist < 4) return ORBX_EINVAL;
   double k[5] = {dist[0], dist[1], dist[2], dist[3], ndist > 4 ? (double)dist[4] : 0.0};
   const double fx = cam->fx, fy = cam->fy, cx = cam->cx, cy = cam->cy;
   const double ifx = 1. / fx, ify = 1. / fy;

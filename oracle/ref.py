@@ -267,3 +267,112 @@ def fuse(kf, cam, Rcw, tcw, Ow, flags, xw, max_dist, min_dist, normal, mp_desc, 
     f(kf.ref(), C.byref(cam), _p(Rcw), _p(tcw), _p(Ow), n, _p(flags), _p(xw), _p(max_dist), _p(min_dist), _p(normal), _p(mp_desc), th,
       _p(sf), _p(isg), len(sf), log_scale_factor, _p(out), C.byref(nf))
     return nf.value, out[:n]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ORB_SLAM3::Frame of the reference (src/Frame.cc + include/Frame.h, unmodified; oracle/ref_stub/frame_prelude.h)
+# ------------------------------------------------------------------------------------------------------------------
+_KP = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.float32), ("angle", np.float32), ("response", np.float32),
+                ("octave", np.int32)])
+
+
+class Frame:
+    """A real reference Frame built by its stereo (imgR given) or monocular constructor: extraction by the reference's
+    ORBextractor on two threads, UndistortKeyPoints, ComputeStereoMatches, AssignFeaturesToGrid."""
+
+    def __init__(self, imgL, imgR, cam, bf, th_depth=40.0, dist=(0, 0, 0, 0), nfeatures=1000, scale=1.2, nlevels=8, ini_th=20,
+                 min_th=7, Tcb=None, fma=False):
+        """fma=True: the TU built with the reference's own Release flags (-O3, -ffp-contract=fast) instead of one rounding
+        per operation"""
+        L = self.L = _lib("libref_frame_fma.so" if fma else "libref_frame.so")
+        _ml()                                             # make sure libref_matcher.so is built
+        L.ref_frame_init.argtypes = [C.c_char_p]
+        assert L.ref_frame_init(os.path.join(_HERE, "_ref", "libref_matcher.so").encode()) == 0
+        L.ref_frame_create.restype = C.c_void_p
+        L.ref_frame_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                       C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        for f in ("ref_frame_destroy", "ref_frame_n", "ref_frame_n_right"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.ref_frame_mb.restype = C.c_float
+        L.ref_frame_mb.argtypes = [C.c_void_p]
+        L.ref_frame_log_scale_factor.restype = C.c_float
+        L.ref_frame_log_scale_factor.argtypes = [C.c_void_p]
+        L.ref_frame_bounds.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_frame_keys.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_frame_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_frame_features_in_area.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.ref_frame_set_pose.argtypes = [C.c_void_p] * 5
+        L.ref_frame_set_imu_pose.argtypes = [C.c_void_p] * 4
+        L.ref_frame_is_in_frustum.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_float] + [C.c_void_p] * 7
+        imgL = np.ascontiguousarray(imgL, np.uint8)
+        imgR = None if imgR is None else np.ascontiguousarray(imgR, np.uint8)
+        h, w = imgL.shape
+        d = np.ascontiguousarray(dist, np.float32)
+        T = None if Tcb is None else np.ascontiguousarray(Tcb, np.float32)
+        self.h = L.ref_frame_create(_p(imgL), None if imgR is None else _p(imgR), w, h, w, nfeatures, scale, nlevels, ini_th, min_th,
+                                    cam.fx, cam.fy, cam.cx, cam.cy, _p(d), bf, th_depth, None if T is None else _p(T))
+        self.n, self.n_right = L.ref_frame_n(self.h), L.ref_frame_n_right(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ref_frame_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def mb(self):
+        return float(self.L.ref_frame_mb(self.h))
+
+    @property
+    def log_scale_factor(self):
+        return float(self.L.ref_frame_log_scale_factor(self.h))
+
+    @property
+    def bounds(self):
+        b = np.zeros(4, np.float32)
+        self.L.ref_frame_bounds(self.h, _p(b))
+        return b                                          # minX, minY, maxX, maxY
+
+    def keys(self, which=0):
+        """which: 0 mvKeys (+ mDescriptors), 1 mvKeysRight (+ mDescriptorsRight), 2 mvKeysUn"""
+        n = self.n_right if which == 1 else self.n
+        k = np.zeros(max(n, 1), _KP)
+        d = np.zeros((max(n, 1), 32), np.uint8)
+        self.L.ref_frame_keys(self.h, which, _p(k), _p(d) if which != 2 else None)
+        return k[:n], d[:n]
+
+    def stereo_matches(self):
+        ur, dp = np.zeros(max(self.n, 1), np.float32), np.zeros(max(self.n, 1), np.float32)
+        self.L.ref_frame_stereo_matches(self.h, _p(ur), _p(dp))
+        return ur[:self.n], dp[:self.n]
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1, cap=4096):
+        out = np.zeros(cap, np.int32)
+        n = self.L.ref_frame_features_in_area(self.h, float(x), float(y), float(r), int(min_level), int(max_level), _p(out), cap)
+        assert n <= cap
+        return out[:n]
+
+    def set_pose(self, Tcw):
+        T = np.ascontiguousarray(Tcw, np.float32)
+        Ow, R, t = np.zeros(3, np.float32), np.zeros(9, np.float32), np.zeros(3, np.float32)
+        self.L.ref_frame_set_pose(self.h, _p(T), _p(Ow), _p(R), _p(t))
+        return Ow, R.reshape(3, 3), t
+
+    def set_imu_pose(self, Rwb, twb):
+        R, t = np.ascontiguousarray(Rwb, np.float32), np.ascontiguousarray(twb, np.float32)
+        T = np.zeros(16, np.float32)
+        self.L.ref_frame_set_imu_pose(self.h, _p(R), _p(t), _p(T))
+        return T.reshape(4, 4)
+
+    def is_in_frustum(self, xw, max_dist, min_dist, normal, cos_limit=0.5):
+        n = len(max_dist)
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)   # noqa: E731
+        xw, max_dist, min_dist, normal = map(f32, (xw, max_dist, min_dist, normal))
+        out = dict(in_view=np.zeros(n, np.uint8), proj_x=np.zeros(n, np.float32), proj_y=np.zeros(n, np.float32),
+                   proj_xr=np.zeros(n, np.float32), depth=np.zeros(n, np.float32), level=np.zeros(n, np.int32),
+                   view_cos=np.zeros(n, np.float32))
+        out["n"] = self.L.ref_frame_is_in_frustum(self.h, n, _p(xw), _p(max_dist), _p(min_dist), _p(normal), cos_limit,
+                                                  _p(out["in_view"]), _p(out["proj_x"]), _p(out["proj_y"]), _p(out["proj_xr"]),
+                                                  _p(out["depth"]), _p(out["level"]), _p(out["view_cos"]))
+        return out

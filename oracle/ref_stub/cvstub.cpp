@@ -28,6 +28,8 @@ void Mat::copyTo(OutputArray dst) const {
 static double get_elem(const Mat& m, int y, int x) {
   switch (m.type()) {
     case CV_8U: return m.at<uchar>(y, x);
+    case CV_16S: return m.at<short>(y, x);
+    case CV_16U: return m.at<unsigned short>(y, x);
     case CV_32S: return m.at<int>(y, x);
     case CV_32F: return m.at<float>(y, x);
     default: return m.at<double>(y, x);
@@ -36,6 +38,8 @@ static double get_elem(const Mat& m, int y, int x) {
 static void set_elem(Mat& m, int y, int x, double v) {
   switch (m.type()) {
     case CV_8U: m.at<uchar>(y, x) = saturate_cast<uchar>(v); break;
+    case CV_16S: m.at<short>(y, x) = (short)std::min(32767.0, std::max(-32768.0, std::nearbyint(v))); break;
+    case CV_16U: m.at<unsigned short>(y, x) = (unsigned short)std::min(65535.0, std::max(0.0, std::nearbyint(v))); break;
     case CV_32S: m.at<int>(y, x) = cvRound(v); break;
     case CV_32F: m.at<float>(y, x) = (float)v; break;
     default: m.at<double>(y, x) = v;
@@ -220,6 +224,46 @@ double norm(InputArray a_) {
   return std::sqrt(s);
 }
 double norm(InputArray a, InputArray b) { return norm(a.getMat() - b.getMat()); }
+double norm(InputArray a_, InputArray b_, int normType) {
+  if (normType == NORM_L2) return norm(a_, b_);
+  assert(normType == NORM_L1);
+  const Mat a = a_.getMat(), b = b_.getMat();
+  assert(a.rows == b.rows && a.cols == b.cols && a.type() == b.type());
+  double s = 0;      // integer inputs: exact; cv::norm accumulates 16S differences in int and returns the sum as double
+  for (int i = 0; i < a.rows; ++i)
+    for (int j = 0; j < a.cols; ++j) s += std::fabs(get_elem(a, i, j) - get_elem(b, i, j));
+  return s;
+}
+Mat operator-(const Mat& a, double sc) {
+  Mat c(a.rows, a.cols, a.type());
+  for (int i = 0; i < a.rows; ++i)
+    for (int j = 0; j < a.cols; ++j) {
+      double v = get_elem(a, i, j) - sc;
+      if (a.type() == CV_16S) v = std::min(32767.0, std::max(-32768.0, std::nearbyint(v)));
+      else if (a.type() == CV_8U) v = std::min(255.0, std::max(0.0, std::nearbyint(v)));
+      set_elem(c, i, j, v);
+    }
+  return c;
+}
+extern "C" int ork_cv_undistort_points(const float* xy, int n, const orbx_camera* cam, const float* dist, int ndist, float* out_xy);
+void undistortPoints(InputArray src_, OutputArray dst_, InputArray K_, InputArray D_, InputArray R_, InputArray P_) {
+  const Mat src = src_.getMat(), K = K_.getMat(), D = D_.getMat(), P = P_.getMat();
+  assert(src.type() == CV_32F && src.cols == 2 && R_.getMat().empty());
+  // the oracle's restatement of cv::undistortPoints (K -> iterate -> P), pinned to cv2 4.13 by tests/test_oracle_frame.py;
+  // the reference passes P = mK, the same intrinsics
+  orbx_camera cam{};
+  cam.fx = K.at<float>(0, 0); cam.fy = K.at<float>(1, 1); cam.cx = K.at<float>(0, 2); cam.cy = K.at<float>(1, 2);
+  assert(P.empty() || (P.at<float>(0, 0) == cam.fx && P.at<float>(1, 1) == cam.fy && P.at<float>(0, 2) == cam.cx && P.at<float>(1, 2) == cam.cy));
+  float d[5] = {0, 0, 0, 0, 0};
+  const int nd = (int)D.total();
+  for (int i = 0; i < std::min(nd, 5); ++i) d[i] = D.at<float>(i);
+  std::vector<float> in((size_t)2 * src.rows), out((size_t)2 * src.rows);
+  for (int i = 0; i < src.rows; ++i) { in[2 * i] = src.at<float>(i, 0); in[2 * i + 1] = src.at<float>(i, 1); }
+  ork_cv_undistort_points(in.data(), src.rows, &cam, d, nd < 5 ? 4 : 5, out.data());
+  Mat dst(src.rows, 2, CV_32F);
+  for (int i = 0; i < src.rows; ++i) { dst.at<float>(i, 0) = out[2 * i]; dst.at<float>(i, 1) = out[2 * i + 1]; }
+  dst_.getMatRef() = dst;
+}
 
 double determinant(InputArray a_) {
   Mat a = a_.getMat();

@@ -66,7 +66,7 @@ enum { INTER_NEAREST = 0, INTER_LINEAR = 1 };
 enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_WRAP = 3, BORDER_REFLECT_101 = 4,
        BORDER_DEFAULT = 4, BORDER_ISOLATED = 16 };
 enum { DECOMP_LU = 0, DECOMP_SVD = 1 };
-enum { NORM_L2 = 4 };
+enum { NORM_L1 = 2, NORM_L2 = 4, NORM_HAMMING = 6 };
 
 template <typename T> static inline T saturate_cast(double v) { return (T)v; }
 template <> inline uchar saturate_cast<uchar>(double v) { int i = cvRound(v); return (uchar)(i < 0 ? 0 : i > 255 ? 255 : i); }
@@ -221,6 +221,7 @@ class Mat {
   // GEMM_x_T flag, and those never take gemm's small-matrix fp32 path.
   MatT t() const;
   Mat transposed() const;
+  Mat reshape(int /*cn*/, int /*rows*/ = 0) const { return *this; }   // single-channel stand-in: N x 2 floats stay N x 2
   Mat inv(int method = DECOMP_LU) const;
   double dot(const Mat& m) const;
   Mat mul(const Mat& m) const;
@@ -314,6 +315,15 @@ void GaussianBlur(InputArray src, OutputArray dst, Size ksize, double sigmaX, do
 float fastAtan2(float y, float x);
 double norm(InputArray a);
 double norm(InputArray a, InputArray b);
+double norm(InputArray a, InputArray b, int normType);   // NORM_L1 / NORM_L2 of a - b
+// N x 2 CV_32F points (the reference reshapes to 2 channels and back around the call: reshape() is the identity here)
+void undistortPoints(InputArray src, OutputArray dst, InputArray K, InputArray distCoeffs, InputArray R, InputArray P);
+struct DMatch { int queryIdx = -1, trainIdx = -1, imgIdx = -1; float distance = 0; };
+class BFMatcher {   // Frame::BFmatcher: only ComputeStereoFishEyeMatches (KannalaBrandt8 rigs, out of scope) calls it
+ public:
+  BFMatcher(int = NORM_L2, bool = false) {}
+  void knnMatch(InputArray, InputArray, std::vector<std::vector<DMatch>>&, int) const { std::abort(); }
+};
 double determinant(InputArray a);
 void hconcat(InputArray a, InputArray b, OutputArray dst);
 void vconcat(InputArray a, InputArray b, OutputArray dst);
@@ -335,6 +345,7 @@ Mat operator*(const Mat& a, const Mat& b);
 Mat operator+(const Mat& a, const Mat& b);
 Mat operator-(const Mat& a, const Mat& b);
 Mat operator-(const Mat& a);
+Mat operator-(const Mat& a, double s);           // Mat - Scalar, saturating for the integer types
 Mat operator*(const Mat& a, double s);
 Mat operator*(double s, const Mat& a);
 Mat operator/(const Mat& a, double s);

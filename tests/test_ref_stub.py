@@ -43,7 +43,8 @@ def stub(tmp_path_factory):
     so = str(d / "libstubtest.so")
     st = os.path.join(ROOT, "oracle", "ref_stub")
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++14", "-fPIC", "-shared", "-I", st, "-o", so, str(d / "t.cpp"),
-                           os.path.join(st, "cvstub.cpp"), os.path.join(ROOT, "oracle", "ork_primitives.cpp")])
+                           os.path.join(st, "cvstub.cpp"), os.path.join(ROOT, "oracle", "ork_primitives.cpp"),
+                           os.path.join(ROOT, "oracle", "ork_frame.cpp")])
     L = C.CDLL(so)
     L.stub_norm.restype = C.c_double
     L.stub_dot.restype = C.c_double
