@@ -748,6 +748,8 @@ __global__ void __launch_bounds__(PO_NT, 512 / PO_NT) pose_opt_kernel(const Pose
             __syncthreads();
             nCand = ns;
             hit = 0;
+          } else {
+            __syncthreads();                      // the previous trial's readers are done with s_red (compute-sanitizer racecheck)
           }
           cur = hit;
           PO_TICK(2);
