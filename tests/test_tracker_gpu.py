@@ -284,6 +284,56 @@ def test_inertial_tracker_chains_the_prior_on_the_device(ctx, ork):
     ex.close()
 
 
+def test_tracker_blank_images_in_every_mode(ctx, ork):
+    """A stream whose images hold no corner beside a normal one: no keypoints, no matches, PoseOptimization returns the
+    prior untouched (nInitialCorrespondences < 3, src/Optimizer.cc:1134); the inertial optimiser runs on the IMU edge alone."""
+    import orbx
+    from replay_reference import track_frame_map
+    S = 2
+    cam = orbx.make_camera()
+    imgs, Tt, Tp, maps = _map_setup(ork, S, 210)
+    blank = np.full_like(imgs[0], 127)
+    imgs = [blank, blank, imgs[2], imgs[3]]
+    host = sc.stack_track_maps(maps)
+    ex = orbx.ORBextractor(ctx, max_batch=2 * S)
+    # stereo
+    trk = orbx.Tracker(ctx, ex, S, cam)
+    trk.upload_map(host)
+    Tout, stats = trk.step(imgs, Tt, Tp)
+    for s in range(S):
+        T2, st = track_frame_map(ork, cam, imgs[2 * s], imgs[2 * s + 1], maps[s], Tp[s])
+        assert np.array_equal(stats[s], st) and np.abs(Tout[s] - T2).max() < 2e-6
+    assert not stats[0].any() and np.array_equal(Tout[0], Tp[0]) and stats[1][6] > 100
+    # stereo-inertial, both optimisers
+    for mode in (1, 2):
+        imus = [sc.track_imu_scenario(990 + s, Tt[s], mode) for s in range(S)]
+        trk.upload_map(host)
+        trk.upload_inertial(mode, sc.stack_track_imu(imus))
+        Tout, stats = trk.step(imgs, Tt, Tp)
+        state, H = trk.inertial_result()
+        for s in range(S):
+            T2, st, res = track_frame_map(ork, cam, imgs[2 * s], imgs[2 * s + 1], maps[s], Tp[s], imu=imus[s], imu_mode=mode,
+                                          want_inertial=True)
+            assert np.array_equal(stats[s], st), (mode, s, stats[s], st)
+            assert np.abs(state[s] - res["state"]).max() < 1e-9 and np.abs(Tout[s] - T2).max() < 2e-6
+            assert np.abs(H[s] - res["H"]).max() <= 1e-9 * max(np.abs(res["H"]).max(), 1.0)
+        assert stats[0][0] == 0 and stats[0][6] == 0
+    trk.close()
+    ex.close()
+    # monocular
+    ex1 = orbx.ORBextractor(ctx, max_batch=S)
+    trk = orbx.Tracker(ctx, ex1, S, cam, mono=True)
+    left = imgs[0::2]
+    trk.upload_map(host)
+    Tout, stats = trk.step(left, Tt, Tp)
+    for s in range(S):
+        T2, st = track_frame_map(ork, cam, left[s], None, maps[s], Tp[s], mono=True)
+        assert np.array_equal(stats[s], st) and np.abs(Tout[s] - T2).max() < 2e-6
+    assert not stats[0].any() and np.array_equal(Tout[0], Tp[0])
+    trk.close()
+    ex1.close()
+
+
 def test_tracker_chain_mode_composes_the_prior_on_the_device(ctx, ork):
     """Motion-model chaining: step t+1 starts from dT * (pose step t produced).  Equal to feeding that product from the host."""
     import orbx
