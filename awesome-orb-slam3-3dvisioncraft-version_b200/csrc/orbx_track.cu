@@ -373,6 +373,22 @@ struct orbx_tracker {
   unsigned long long mapVersion = 0;
   bool chain = false;
   float* d_Tlast = nullptr;
+  // CUDA graph of one step (orbx_tracker_set_graph): the ~45 launches of a step replayed as ONE graph launch when the
+  // step's arguments repeat (single-frame latency path)
+  bool graphMode = false;
+  struct GraphKey {
+    const void *imgs, *Ttrue, *Tprior, *Tout, *stats;
+    int w, h, stride;
+    unsigned long long mapVersion;
+    bool chain;
+    bool operator==(const GraphKey& o) const {
+      return imgs == o.imgs && Ttrue == o.Ttrue && Tprior == o.Tprior && Tout == o.Tout && stats == o.stats && w == o.w && h == o.h &&
+             stride == o.stride && mapVersion == o.mapVersion && chain == o.chain;
+    }
+  } graphKey{}, graphSeen{};
+  cudaGraphExec_t graphExec = nullptr;
+  size_t graphKernels = 0;
+  unsigned long long graphLaunches = 0;
   // visual-inertial TrackLocalMap (src/Tracking.cc:2974-2990): mode 0 off, 1 LastKeyFrame, 2 LastFrame
   orbx_track_imu imu{};
   void* d_imuArgs = nullptr;                   // argument blocks of the inertial kernels
@@ -494,6 +510,7 @@ void orbx_tracker_destroy(orbx_tracker* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
   cudaStreamSynchronize(t->stA);
+  if (t->graphExec) cudaGraphExecDestroy(t->graphExec);
   if (t->ownB) cudaStreamSynchronize(t->ownB);
   for (void* p : t->allocs) cudaFree(p);
   if (t->h_imgs) cudaFreeHost(t->h_imgs);
@@ -904,10 +921,8 @@ static int tracker_bind_geometry(orbx_tracker* t, int w, int h) {
   return ORBX_OK;
 }
 
-int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int h, int stride, const float* d_Tcw_true,
+static int tracker_step_body(orbx_tracker* t, const uint8_t* d_imgs, int w, int h, int stride, const float* d_Tcw_true,
                              const float* d_Tcw_prior, float* d_Tcw_out, int32_t* d_stats) {
-  if (!t || !d_imgs || !d_Tcw_true || !d_Tcw_prior || !d_Tcw_out) return ORBX_EINVAL;
-  ORBX_CUDA(cudaSetDevice(t->ctx->device));
   cudaStream_t sa = t->stA, sb = t->stB;
   const bool overlap = sb != sa;
   const int S = t->S, cap = t->cap;
@@ -1066,6 +1081,81 @@ int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
   t->stepCount++;
   t->profiled = t->profiling;
   ORBX_CUDA(cudaGetLastError());
+  return ORBX_OK;
+}
+
+static void tracker_drop_graph(orbx_tracker* t) {
+  if (t->graphExec) cudaGraphExecDestroy(t->graphExec);
+  t->graphExec = nullptr;
+  t->graphSeen = orbx_tracker::GraphKey{};
+}
+
+// One CUDA graph for the whole step.  A step whose arguments (device pointers, geometry, map binding) equal those of the
+// previous call is captured once with stream capture of the very same code path and replayed with ONE cudaGraphLaunch from
+// then on: the ~45 launches of a single frame's chain are mostly a few microseconds long, so the host's launch rate is what
+// separates them.  Only the plain single-stream configuration is captured (no overlap mode, profiling, keyframe work or
+// inertial upload events); anything else, and any change of the arguments, runs eagerly and drops the graph.
+int orbx_tracker_set_graph(orbx_tracker* t, int enable) {
+  if (!t) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  int rc = orbx_tracker_synchronize(t);
+  if (rc != ORBX_OK) return rc;
+  tracker_drop_graph(t);
+  t->graphMode = enable != 0;
+  return ORBX_OK;
+}
+long long orbx_tracker_graph_launches(const orbx_tracker* t) { return t ? (long long)t->graphLaunches : -1; }
+
+int orbx_tracker_step_device(orbx_tracker* t, const uint8_t* d_imgs, int w, int h, int stride, const float* d_Tcw_true,
+                             const float* d_Tcw_prior, float* d_Tcw_out, int32_t* d_stats) {
+  if (!t || !d_imgs || !d_Tcw_true || !d_Tcw_prior || !d_Tcw_out) return ORBX_EINVAL;
+  ORBX_CUDA(cudaSetDevice(t->ctx->device));
+  const bool plain = t->graphMode && t->stB == t->stA && !t->profiling && t->kfPeriod == 0 && !t->imu.mode;
+  if (!plain) {
+    if (t->graphExec) tracker_drop_graph(t);
+    return tracker_step_body(t, d_imgs, w, h, stride, d_Tcw_true, d_Tcw_prior, d_Tcw_out, d_stats);
+  }
+  const orbx_tracker::GraphKey key{d_imgs, d_Tcw_true, d_Tcw_prior, d_Tcw_out, d_stats, w, h, stride, t->mapVersion, t->chain};
+  if (t->graphExec && key == t->graphKey) {
+    ORBX_CUDA(cudaGraphLaunch(t->graphExec, t->stA));
+    t->ctx->launches.fetch_add(t->graphKernels, std::memory_order_relaxed);
+    t->graphLaunches++;
+    t->stepCount++;
+    return ORBX_OK;
+  }
+  if (t->graphExec) tracker_drop_graph(t);
+  // capture only a step that would not rebind anything: same arguments as the previous (eager) call, map already bound
+  const bool bound = t->slot[0].mapVersion == t->mapVersion && w == t->argW && h == t->argH && stride == t->argStride && d_imgs == t->argImgs;
+  if (!(key == t->graphSeen) || !bound) {
+    t->graphSeen = key;
+    return tracker_step_body(t, d_imgs, w, h, stride, d_Tcw_true, d_Tcw_prior, d_Tcw_out, d_stats);
+  }
+  cudaGraph_t graph = nullptr;
+  const unsigned long long launches0 = t->ctx->launches.load(std::memory_order_relaxed), step0 = t->stepCount;
+  if (cudaStreamBeginCapture(t->stA, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return tracker_step_body(t, d_imgs, w, h, stride, d_Tcw_true, d_Tcw_prior, d_Tcw_out, d_stats);
+  }
+  const int rc = tracker_step_body(t, d_imgs, w, h, stride, d_Tcw_true, d_Tcw_prior, d_Tcw_out, d_stats);
+  const cudaError_t ce = cudaStreamEndCapture(t->stA, &graph);
+  t->stepCount = step0;                                  // nothing has run yet
+  const size_t nk = (size_t)(t->ctx->launches.load(std::memory_order_relaxed) - launches0);
+  t->ctx->launches.store(launches0, std::memory_order_relaxed);
+  if (rc != ORBX_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&t->graphExec, graph, 0) != cudaSuccess) {
+    // not capturable after all (or the step failed): forget the graph path for these arguments and run eagerly
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    t->graphExec = nullptr;
+    t->graphMode = false;
+    return tracker_step_body(t, d_imgs, w, h, stride, d_Tcw_true, d_Tcw_prior, d_Tcw_out, d_stats);
+  }
+  cudaGraphDestroy(graph);
+  t->graphKey = key;
+  t->graphKernels = nk;
+  ORBX_CUDA(cudaGraphLaunch(t->graphExec, t->stA));
+  t->ctx->launches.fetch_add(nk, std::memory_order_relaxed);
+  t->graphLaunches++;
+  t->stepCount++;
   return ORBX_OK;
 }
 

@@ -126,6 +126,9 @@ def load_library():
     L.orbx_tracker_map_bytes.argtypes = [vp]
     L.orbx_tracker_set_map.argtypes = [vp, vp]
     L.orbx_tracker_upload_map.argtypes = [vp, vp]
+    L.orbx_tracker_set_graph.argtypes = [vp, i]
+    L.orbx_tracker_graph_launches.restype = C.c_longlong
+    L.orbx_tracker_graph_launches.argtypes = [vp]
     L.orbx_tracker_set_inertial.argtypes = [vp, vp]
     L.orbx_tracker_upload_inertial.argtypes = [vp, vp]
     L.orbx_tracker_inertial_result.argtypes = [vp, vp, vp]
@@ -814,6 +817,14 @@ class Tracker:
         self._map_keep = host_arrays
         m = self._track_map(keep, log_scale_factor)
         _check(load_library().orbx_tracker_upload_map(self.h, C.byref(m)), "orbx_tracker_upload_map")
+
+    def set_graph(self, on=True):
+        """Replay a step whose arguments repeat as ONE CUDA graph launch (single-frame latency path)."""
+        _check(load_library().orbx_tracker_set_graph(self.h, int(bool(on))), "orbx_tracker_set_graph")
+
+    @property
+    def graph_launches(self):
+        return int(load_library().orbx_tracker_graph_launches(self.h))
 
     # ---- visual-inertial TrackLocalMap (orbx_track_imu) ----
     def _track_imu(self, mode, ptrs, rec_init):

@@ -600,6 +600,13 @@ int orbx_tracker_step(orbx_tracker *trk, const uint8_t *const *imgs, int w, int 
 int orbx_tracker_submit(orbx_tracker *trk, const uint8_t *const *imgs, int w, int h, int stride,
                         const float *Tcw_true, const float *Tcw_prior);
 int orbx_tracker_collect(orbx_tracker *trk, float *Tcw_out, int32_t *stats);
+/* CUDA graph of one step (single-frame latency path): with enable = 1, a step whose arguments (device pointers, image
+ * geometry, map binding) repeat those of the previous call is captured once by stream capture of the same code path and
+ * replayed with ONE graph launch from then on; any change of the arguments, overlap mode, profiling, keyframe work or an
+ * inertial mode run eagerly.  Results are identical.  orbx_tracker_graph_launches counts the replays. */
+int orbx_tracker_set_graph(orbx_tracker *trk, int enable);
+long long orbx_tracker_graph_launches(const orbx_tracker *trk);
+
 /* Overlap mode: step t's extraction + stereo matching run on the extractor's stream and its matching +
  * pose stages on a second stream, double-buffered, so the latency-bound fp64 optimisation of step t
  * overlaps the throughput-bound extraction of step t+1 (frames of different steps are independent

@@ -284,6 +284,48 @@ def test_inertial_tracker_chains_the_prior_on_the_device(ctx, ork):
     ex.close()
 
 
+def test_tracker_graph_replay_equals_eager(ctx, ork):
+    """orbx_tracker_set_graph: the step captured as one CUDA graph gives the results of the eager launches, follows new
+    image CONTENT (same buffers) and falls back to eager launches when an argument changes."""
+    import orbx
+    S = 2
+    cam = orbx.make_camera()
+    imgs, Tt, Tp, maps = _map_setup(ork, S, 220)
+    imgs2, _, _, _ = _map_setup(ork, S, 230)
+    host = sc.stack_track_maps(maps)
+    ex = orbx.ORBextractor(ctx, max_batch=2 * S)
+    ref = orbx.Tracker(ctx, ex, S, cam)
+    want = []
+    for im in (imgs, imgs2, imgs):
+        ref.upload_map(host)
+        want.append(ref.step(im, Tt, Tp))
+    ref.close()
+    trk = orbx.Tracker(ctx, ex, S, cam)
+    trk.set_graph(True)
+    got = []
+    for im in (imgs, imgs, imgs2, imgs):               # eager (binds), capture + launch, replay, replay
+        trk.upload_map(host)
+        got.append(trk.step(im, Tt, Tp))
+    assert trk.graph_launches == 3
+    for g, w in zip(got, (want[0], want[0], want[1], want[2])):
+        assert np.array_equal(g[0], w[0]) and np.array_equal(g[1], w[1])
+    assert got[0][1][0][6] > 100
+    # a different prior array of the same content is the same staging buffer: still a replay; a different image size is not
+    trk.upload_map(host)
+    a = trk.step(imgs, Tt, Tp.copy())
+    assert trk.graph_launches == 4 and np.array_equal(a[0], want[0][0])
+    small = [np.ascontiguousarray(im[:400, :640]) for im in imgs]
+    trk.upload_map(host)
+    trk.step(small, Tt, Tp)
+    assert trk.graph_launches == 4
+    trk.set_graph(False)
+    trk.upload_map(host)
+    b = trk.step(imgs, Tt, Tp)
+    assert np.array_equal(b[0], want[0][0]) and np.array_equal(b[1], want[0][1]) and trk.graph_launches == 4
+    trk.close()
+    ex.close()
+
+
 def test_tracker_blank_images_in_every_mode(ctx, ork):
     """A stream whose images hold no corner beside a normal one: no keypoints, no matches, PoseOptimization returns the
     prior untouched (nInitialCorrespondences < 3, src/Optimizer.cc:1134); the inertial optimiser runs on the IMU edge alone."""

@@ -117,6 +117,12 @@ def main():
     assert np.array_equal(chain_gpu()[1], chain_gpu_pinned()[1])
     add("  ... the same, frame buffers and map arrays page-locked", "orbx_host_alloc", chain_gpu_pinned,
         lambda: track_frame_map(oracle, cam, L, R, mp1, Tp1[0], extractors=oex), 30, 5)
+    trk1.set_graph(True)
+    assert np.array_equal(chain_gpu_pinned()[1], chain_gpu()[1])
+    add("  ... the same, replayed as ONE CUDA graph (orbx_tracker_set_graph)", "orbx_tracker_set_graph", chain_gpu_pinned,
+        lambda: track_frame_map(oracle, cam, L, R, mp1, Tp1[0], extractors=oex), 30, 5)
+    assert trk1.graph_launches > 20
+    trk1.set_graph(False)
     trk1.close()
     ex1.close()
     q = sc.tri_scenario(3, kL, dL, ur)
