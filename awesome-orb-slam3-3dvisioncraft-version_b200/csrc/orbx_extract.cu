@@ -380,6 +380,9 @@ orbx_ext* orbx_extractor_create(orbx_ctx* ctx, int nfeatures, float scaleFactor,
   e->tabElems = tab + 64;
   bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_pyr, e->pyrBytes) == cudaSuccess;
+  // the kernels read whole aligned words / quads that may include a row's pitch padding (never used, never written): give
+  // those bytes a defined value once, so that initcheck stays quiet and a leaked padding byte could not go unnoticed
+  ok = ok && cudaMemset(e->d_pyr, 0, e->pyrBytes) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_tab, e->tabElems * sizeof(int16_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_cand, e->candElems * sizeof(uint32_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_keyNode, e->candElems * sizeof(uint16_t)) == cudaSuccess;
@@ -394,6 +397,7 @@ orbx_ext* orbx_extractor_create(orbx_ctx* ctx, int nfeatures, float scaleFactor,
   ok = ok && cudaMallocHost(&e->h_desc, (size_t)max_batch * sel * 32) == cudaSuccess;
   ok = ok && cudaMallocHost(&e->h_nOut, (2 * (size_t)max_batch + 4) * sizeof(int)) == cudaSuccess;
   if (ok) ok = cudaMemset(e->d_counts, 0, (3 * (size_t)max_batch * nlevels + 16) * sizeof(int)) == cudaSuccess;
+  if (ok) ok = cudaStreamSynchronize(0) == cudaSuccess;   // the memsets ran on the legacy stream; e->stream is non-blocking
   if (!ok) {
     orbx_set_error("orbx_extractor_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     orbx_extractor_destroy(e);

@@ -618,6 +618,61 @@ __device__ __forceinline__ void stereo_refine(const StereoArgs& A, int iL, const
   }
 }
 
+// Row index of the right keypoints: a counting sort of their ids by floor(y) (one CTA per frame).  The reference buckets
+// every right keypoint into all rows of its band (vRowIndices, src/Frame.cc:965-982) and scans the bucket of the left
+// keypoint's row; the band is at most +-(2 * scale[nlevels-1] + 1) rows wide, so scanning the rows v-W .. v+W of this index
+// and re-testing the band visits a superset of that bucket.  The order inside a bucket does not matter: the minimum is
+// taken over (distance << 16 | iR), i.e. the first minimum in ascending iR like the reference's strict "<".
+__global__ void __launch_bounds__(256) stereo_rows_kernel(const StereoArgs* __restrict__ args) {
+  __shared__ int s_cnt[ORBX_STEREO_MAX_ROWS + 1];
+  __shared__ int s_warp[9];
+  const StereoArgs& A = args[blockIdx.x];
+  if (!A.sortIdx || !A.rowStart) return;
+  const int nR = A.nRDev ? *A.nRDev : A.nR, nRows = A.lh[0], tid = threadIdx.x;
+  if (nRows > ORBX_STEREO_MAX_ROWS) {
+    if (tid == 0) A.rowStart[0] = -1;                 // not built: the matcher scans every right keypoint
+    return;
+  }
+  for (int r = tid; r <= nRows; r += 256) s_cnt[r] = 0;
+  __syncthreads();
+  for (int i = tid; i < nR; i += 256) {
+    const int r = min(max((int)floorf(A.kpR[i].y), 0), nRows - 1);
+    atomicAdd(&s_cnt[r], 1);
+  }
+  __syncthreads();
+  // exclusive scan of s_cnt[0..nRows) by 256 threads
+  const int per = (nRows + 255) / 256, beg = min(tid * per, nRows), end = min(beg + per, nRows);
+  int sum = 0;
+  for (int r = beg; r < end; ++r) sum += s_cnt[r];
+  int incl = sum;
+  const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int w = 0; w < 8; ++w) { const int t = s_warp[w]; s_warp[w] = run; run += t; }
+  }
+  __syncthreads();
+  int run = s_warp[wid] + incl - sum;
+  for (int r = beg; r < end; ++r) {
+    const int c = s_cnt[r];
+    s_cnt[r] = run;
+    A.rowStart[r] = run;
+    run += c;
+  }
+  if (tid == 0) A.rowStart[nRows] = nR;
+  __syncthreads();
+  for (int i = tid; i < nR; i += 256) {
+    const int r = min(max((int)floorf(A.kpR[i].y), 0), nRows - 1);
+    A.sortIdx[atomicAdd(&s_cnt[r], 1)] = (uint16_t)i;
+  }
+}
+
 __global__ void __launch_bounds__(STEREO_NT) stereo_match_kernel(const StereoArgs* __restrict__ args) {
   __shared__ float s_x[STEREO_CHUNK];
   __shared__ int s_rows[STEREO_CHUNK];      // minr (low 16, signed) | maxr << 16
@@ -651,7 +706,29 @@ __global__ void __launch_bounds__(STEREO_NT) stereo_match_kernel(const StereoArg
     }
     if (!valid[k]) row[k] = -32768;
   }
-  for (int c0 = 0; c0 < nR; c0 += STEREO_CHUNK) {
+  const bool indexed = A.sortIdx && A.rowStart && A.rowStart[0] >= 0;
+  if (indexed) {
+    // candidates of a left keypoint in row v: the right keypoints of rows v-W .. v+W of the index, band re-tested
+    const int W = (int)ceilf(__fmul_rn(2.0f, A.scale[A.nlevels - 1])) + 1;
+#pragma unroll
+    for (int k = 0; k < STEREO_KPW; ++k) {
+      if (!valid[k]) continue;                          // warp-uniform
+      const int lo = A.rowStart[max(row[k] - W, 0)], hi = A.rowStart[min(row[k] + W + 1, nRows)];
+      for (int i = lo + lane; i < hi; i += 32) {
+        const int iR = A.sortIdx[i];
+        const orbx_keypoint kr = A.kpR[iR];
+        const float r = __fmul_rn(2.0f, A.scale[kr.octave]);
+        const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));
+        if (row[k] >= minr && row[k] <= maxr && kr.octave >= octL[k] - 1 && kr.octave <= octL[k] + 1 && kr.x >= minU[k] &&
+            kr.x <= maxU[k]) {
+          const int d = hamming256(reinterpret_cast<const uint4*>(A.descL + 32 * (size_t)(iL0 + k)),
+                                   reinterpret_cast<const uint4*>(A.descR + 32 * (size_t)iR));
+          key[k] = min(key[k], ((unsigned)d << 16) | (unsigned)iR);
+        }
+      }
+    }
+  }
+  for (int c0 = 0; c0 < (indexed ? 0 : nR); c0 += STEREO_CHUNK) {
     const int n = min(STEREO_CHUNK, nR - c0);
     __syncthreads();                                  // the previous chunk has been consumed
     for (int i = tid; i < n; i += STEREO_NT) {
@@ -878,6 +955,8 @@ static int resolve_smem_opt_in() {
 }
 
 int orbx_launch_stereo_batch(orbx_ctx* ctx, cudaStream_t st, const StereoArgs* dArgs, int S, int maxL) {
+  stereo_rows_kernel<<<S, 256, 0, st>>>(dArgs);
+  ORBX_LAUNCH(ctx);
   stereo_match_kernel<<<dim3(div_up(maxL, (STEREO_NT / 32) * STEREO_KPW), S), STEREO_NT, 0, st>>>(dArgs);
   ORBX_LAUNCH(ctx);
   stereo_median_kernel<<<S, 256, 0, st>>>(dArgs);
@@ -1188,11 +1267,15 @@ int orbx_stereo_match(orbx_ctx* ctx, orbx_ext* extL, int bL, orbx_ext* extR, int
   A.uright = S.alloc<float>(nL);
   A.depth = S.alloc<float>(nL);
   A.sad = S.alloc<int>(nL);
+  A.sortIdx = S.alloc<uint16_t>(std::max(nR, 1));
+  A.rowStart = S.alloc<int>(ORBX_STEREO_MAX_ROWS + 1);
   if (S.failed) return ORBX_ECUDA;
   A.nLDev = A.nRDev = nullptr;
   StereoArgs* dA = S.upload(&A, 1);
   if (S.failed) return ORBX_ECUDA;
   if (nL > 0) {
+    stereo_rows_kernel<<<1, 256, 0, st>>>(dA);
+    ORBX_LAUNCH(ctx);
     stereo_match_kernel<<<dim3(div_up(nL, (STEREO_NT / 32) * STEREO_KPW), 1), STEREO_NT, 0, st>>>(dA);
     ORBX_LAUNCH(ctx);
     stereo_median_kernel<<<1, 256, 0, st>>>(dA);
@@ -1366,7 +1449,8 @@ orbx_tri_batch* orbx_tri_batch_prepare(orbx_ctx* ctx, int Q, const orbx_tri_prob
   }
   memcpy(B.h.data() + oFrames, F.data(), sizeof(FrameDev) * F.size());
   memcpy(B.h.data() + oArgs, A.data(), sizeof(TriArgs) * A.size());
-  if (cudaMemcpy(T->pool, B.h.data(), B.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+  // (pageable H2D on the legacy stream returns once the data is staged: wait for the DMA, the plan runs on non-blocking streams)
+  if (cudaMemcpy(T->pool, B.h.data(), B.size(), cudaMemcpyHostToDevice) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) {
     orbx_set_error("orbx_tri_batch_prepare: upload failed");
     cudaGetLastError();
     cudaFree(T->pool);

@@ -225,7 +225,12 @@ struct StereoArgs {
   float* uright;
   float* depth;
   int* sad;      // [nL] best SAD of accepted matches, -1 otherwise
+  // row index of the right keypoints (stereo_rows_kernel): sortIdx = right keypoint ids bucketed by floor(y), rowStart[r] =
+  // first entry of row r (rowStart[rows] = nR); rowStart[-1 + 0] < 0 marks "not built" (image taller than the kernel's table)
+  uint16_t* sortIdx;   // [nR] or null: scan every right keypoint
+  int* rowStart;       // [ORBX_STEREO_MAX_ROWS + 1]
 };
+#define ORBX_STEREO_MAX_ROWS 2304
 
 // batched launchers (S frames; arg/frame arrays are device pointers)
 int orbx_launch_stereo_batch(orbx_ctx* ctx, cudaStream_t st, const StereoArgs* dArgs, int S, int maxL);

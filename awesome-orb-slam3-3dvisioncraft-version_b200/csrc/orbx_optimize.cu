@@ -3214,7 +3214,8 @@ orbx_lba_batch* orbx_lba_batch_prepare(orbx_ctx* ctx, int P, const orbx_lba_prob
     a.status = (int*)(base + oRes) + 3 * p + 2;
   }
   memcpy(B.h.data() + oArgs, A.data(), sizeof(LbaArgs) * (size_t)P);
-  if (cudaMemcpy(L->pool, B.h.data(), B.h.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+  // (pageable H2D on the legacy stream returns once the data is staged: wait for the DMA, the plan runs on non-blocking streams)
+  if (cudaMemcpy(L->pool, B.h.data(), B.h.size(), cudaMemcpyHostToDevice) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) {
     orbx_set_error("orbx_lba_batch_prepare: upload failed");
     cudaGetLastError();
     cudaFree(L->pool);

@@ -311,6 +311,8 @@ struct TrackSlot {
   int *d_n = nullptr, *d_mono = nullptr;
   FrameDev* d_frames = nullptr;
   StereoArgs* d_stereo = nullptr;
+  uint16_t* d_stereoIdx = nullptr;   // [S][cap] row-bucketed right keypoint ids (stereo_rows_kernel)
+  int* d_stereoRows = nullptr;       // [S][ORBX_STEREO_MAX_ROWS + 1]
   SbpFrameArgs* d_sbpf = nullptr;
   SbpMapArgs* d_sbpm = nullptr;
   double* d_scratch = nullptr;
@@ -406,7 +408,11 @@ template <typename T>
 static T* talloc(orbx_tracker* t, size_t count) {
   void* p = nullptr;
   if (cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+  // cudaMemset runs on the legacy default stream, which the tracker's NON-BLOCKING streams do not wait for: without the
+  // synchronisation a lazily allocated buffer (the map / inertial staging of the first upload) could be zeroed AFTER the
+  // copies that fill it had landed -- seen as a rare wrong result on a cold box and under compute-sanitizer
   cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T));
+  cudaStreamSynchronize(0);
   t->allocs.push_back(p);
   return (T*)p;
 }
@@ -451,6 +457,8 @@ static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float th
   D.stats = talloc<int>(t, ORBX_TRACK_STATS * S);
   K.d_frames = talloc<FrameDev>(t, S);
   K.d_stereo = talloc<StereoArgs>(t, S);
+  K.d_stereoIdx = talloc<uint16_t>(t, (size_t)S * cap);
+  K.d_stereoRows = talloc<int>(t, (size_t)S * (ORBX_STEREO_MAX_ROWS + 1));
   K.d_sbpf = talloc<SbpFrameArgs>(t, S);
   K.d_sbpm = talloc<SbpMapArgs>(t, S);
   K.d_scratch = talloc<double>(t, 3 * SC);
@@ -501,6 +509,7 @@ static bool slot_alloc(orbx_tracker* t, TrackSlot& K, const float* isg, float th
   cudaMemcpy(K.d_frames, F.data(), sizeof(FrameDev) * S, cudaMemcpyHostToDevice);
   cudaMemcpy(K.d_sbpf, AF.data(), sizeof(SbpFrameArgs) * S, cudaMemcpyHostToDevice);
   cudaMemcpy(K.d_sbpm, AM.data(), sizeof(SbpMapArgs) * S, cudaMemcpyHostToDevice);
+  cudaStreamSynchronize(0);   // pageable H2D on the legacy stream may still be in flight; the tracker's streams are non-blocking
   return cudaGetLastError() == cudaSuccess;
 }
 
@@ -675,6 +684,7 @@ static int imu_ensure_buffers(orbx_tracker* t) {
   if (!t->d_imuArgs || !t->d_imuState || !t->d_imuH) return ORBX_ECUDA;
   ORBX_CUDA(cudaMemset(t->d_imuState, 0, sizeof(double) * 21 * t->S));
   ORBX_CUDA(cudaMemset(t->d_imuH, 0, sizeof(double) * 225 * t->S));
+  ORBX_CUDA(cudaStreamSynchronize(0));
   return ORBX_OK;
 }
 
@@ -865,6 +875,7 @@ int orbx_tracker_set_chain(orbx_tracker* t, int enable, const float* d_Tcw_init)
     if (!t->d_Tlast) t->d_Tlast = talloc<float>(t, 16 * (size_t)t->S);
     if (!t->d_Tlast) return ORBX_ECUDA;
     ORBX_CUDA(cudaMemcpy(t->d_Tlast, d_Tcw_init, sizeof(float) * 16 * t->S, cudaMemcpyDefault));   // host or device pointer
+    ORBX_CUDA(cudaStreamSynchronize(0));
   }
   t->chain = enable != 0;
   return ORBX_OK;
@@ -909,6 +920,8 @@ static int tracker_bind_geometry(orbx_tracker* t, int w, int h) {
       a.uright = K.D.uright + (size_t)s * t->cap;
       a.depth = K.D.depth + (size_t)s * t->cap;
       a.sad = K.D.kpEdge + (size_t)s * t->cap;   // scratch reuse: kpEdge is rewritten later in the step
+      a.sortIdx = K.d_stereoIdx + (size_t)s * t->cap;
+      a.rowStart = K.d_stereoRows + (size_t)s * (ORBX_STEREO_MAX_ROWS + 1);
       F[s].minX = 0.f; F[s].minY = 0.f; F[s].maxX = (float)w; F[s].maxY = (float)h;   // rectified stereo: image bounds (src/Frame.cc:147-152)
       F[s].wInv = (float)ORBX_GRID_COLS / (F[s].maxX - F[s].minX);
       F[s].hInv = (float)ORBX_GRID_ROWS / (F[s].maxY - F[s].minY);
@@ -916,6 +929,7 @@ static int tracker_bind_geometry(orbx_tracker* t, int w, int h) {
     ORBX_CUDA(cudaMemcpy(K.d_stereo, A.data(), sizeof(StereoArgs) * S, cudaMemcpyHostToDevice));
     ORBX_CUDA(cudaMemcpy(K.d_frames, F.data(), sizeof(FrameDev) * S, cudaMemcpyHostToDevice));
   }
+  ORBX_CUDA(cudaStreamSynchronize(0));   // see slot_alloc
   t->argW = w;
   t->argH = h;
   return ORBX_OK;

@@ -303,6 +303,7 @@ orbx_voc* orbx_vocabulary_from_memory(orbx_ctx* ctx, const void* data, size_t by
   ok = ok && cudaMemcpy(v->d_childIdx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemcpy(v->d_wordId, wordId.data(), wordId.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemcpy(v->d_weight, weight.data(), weight.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaStreamSynchronize(0) == cudaSuccess;   // pageable H2D on the legacy stream: wait for the DMA (the context's stream is non-blocking)
   if (!ok) {
     orbx_set_error("orbx_vocabulary: device allocation/copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
     voc_free(v);
