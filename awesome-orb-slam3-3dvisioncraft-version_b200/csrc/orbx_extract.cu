@@ -397,6 +397,11 @@ orbx_ext* orbx_extractor_create(orbx_ctx* ctx, int nfeatures, float scaleFactor,
   ok = ok && cudaMallocHost(&e->h_desc, (size_t)max_batch * sel * 32) == cudaSuccess;
   ok = ok && cudaMallocHost(&e->h_nOut, (2 * (size_t)max_batch + 4) * sizeof(int)) == cudaSuccess;
   if (ok) ok = cudaMemset(e->d_counts, 0, (3 * (size_t)max_batch * nlevels + 16) * sizeof(int)) == cudaSuccess;
+  // the host-buffer entry points copy whole [B][cap] output blocks back and use the first n entries of each: defined bytes
+  if (ok) ok = cudaMemset(e->d_kps, 0, (size_t)max_batch * sel * sizeof(orbx_keypoint)) == cudaSuccess;
+  if (ok) ok = cudaMemset(e->d_desc, 0, (size_t)max_batch * sel * 32) == cudaSuccess;
+  if (ok) ok = cudaMemset(e->d_cand, 0, e->candElems * sizeof(uint32_t)) == cudaSuccess;
+  if (ok) ok = cudaMemset(e->d_sel, 0, e->selElems * sizeof(uint2)) == cudaSuccess;
   if (ok) ok = cudaStreamSynchronize(0) == cudaSuccess;   // the memsets ran on the legacy stream; e->stream is non-blocking
   if (!ok) {
     orbx_set_error("orbx_extractor_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));

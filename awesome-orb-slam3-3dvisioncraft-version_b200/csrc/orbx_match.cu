@@ -1055,6 +1055,7 @@ int orbx_features_in_area(orbx_ctx* ctx, const orbx_frame_desc* frame, int nq, c
     if (rc != ORBX_OK) return rc;
   }
   if (nq > 0) {
+    ORBX_CUDA(cudaMemsetAsync(dout, 0xff, sizeof(int) * (size_t)nq * cap, st));   // slots past out_n[q] read back as -1
     features_in_area_kernel<<<div_up(nq * 32, 128), 128, 0, st>>>(dF, nq, dx, dy, dr, dmin, dmax, dout, cap, dn);
     ORBX_LAUNCH(ctx);
     ORBX_CUDA(cudaMemcpyAsync(out_idx, dout, sizeof(int) * (size_t)nq * cap, cudaMemcpyDeviceToHost, st));
