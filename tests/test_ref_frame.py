@@ -50,6 +50,26 @@ def test_stereo_frame_constructor_and_compute_stereo_matches(env, seed):
     F.close()
 
 
+def test_stereo_frame_1080p_2000_features(env):
+    """BASELINE config 4 geometry: 1920x1080, 2000 features -- constructor, extraction and ComputeStereoMatches."""
+    ork, ref, orbx, synth = env
+    cam = orbx.make_camera()
+    L, R = synth.stereo_pair(21, 1920, 1080)
+    F = ref.Frame(L, R, cam, sc.BF, nfeatures=2000)
+    exL, exR = ork.Extractor(2000), ork.Extractor(2000)
+    _, kL, dL, _ = exL(L)
+    _, kR, dR, _ = exR(R)
+    rkL, rdL = F.keys(0)
+    rkR, rdR = F.keys(1)
+    assert _same_keys(rkL, kL) and np.array_equal(rdL, dL) and _same_keys(rkR, kR) and np.array_equal(rdR, dR)
+    ur, dp = F.stereo_matches()
+    our, odp = ork.stereo_match([exL.pyramid_level(l) for l in range(8)], [exR.pyramid_level(l) for l in range(8)], kL, dL, kR, dR,
+                                exL.scale, exL.inv_scale, sc.BF, F.mb)
+    assert (ur >= 0).sum() > 500 and np.array_equal(ur, our) and np.array_equal(dp, odp)
+    assert np.array_equal(F.bounds, np.array([0, 0, 1920, 1080], np.float32))
+    F.close()
+
+
 def test_features_in_area_equals_reference_grid(env):
     """AssignFeaturesToGrid :444-478 + GetFeaturesInArea :755-850: same indices in the same ORDER."""
     ork, ref, orbx, synth = env
