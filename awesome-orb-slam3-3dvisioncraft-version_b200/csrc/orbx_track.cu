@@ -531,6 +531,7 @@ void orbx_tracker_destroy(orbx_tracker* t) {
     if (t->slot[k].evA) cudaEventDestroy(t->slot[k].evA);
     if (t->slot[k].evB) cudaEventDestroy(t->slot[k].evB);
     if (t->slot[k].evMap) cudaEventDestroy(t->slot[k].evMap);
+    if (t->slot[k].evImu) cudaEventDestroy(t->slot[k].evImu);
   }
   if (t->ownB) cudaStreamDestroy(t->ownB);
   if (t->stK) {
