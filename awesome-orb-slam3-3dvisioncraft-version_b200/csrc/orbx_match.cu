@@ -93,6 +93,36 @@ __device__ __forceinline__ int walk_candidates(const FrameDev& F, float x, float
   return pos;
 }
 
+// walk_candidates for the two-phase score kernels: the gated candidate of every (column, chunk) iteration is remembered per
+// lane (idx, or -1), so that the fill phase -- which needs the query's total first, to reserve its slice of the candidate
+// list -- replays the iterations from this cache instead of walking the grid, the keypoints and the uRight gate a second
+// time.  nIt = -1 when the walk has more than SBP_CACHE iterations (the caller then walks again).
+#define SBP_CACHE 24
+template <typename Gate>
+__device__ __forceinline__ int walk_cached(const FrameDev& F, float x, float y, float r, int minLevel, int maxLevel, Gate gate,
+                                           int (&cache)[SBP_CACHE], int& nIt) {
+  const int lane = threadIdx.x & 31;
+  const CellRange c = cell_range(F, x, y, r);
+  nIt = 0;
+  if (c.empty) return 0;
+  int cnt = 0, it = 0;
+  for (int ix = c.x0; ix <= c.x1; ++ix) {
+    const int beg = F.cellStart[ix * ORBX_GRID_ROWS + c.y0], end = F.cellStart[ix * ORBX_GRID_ROWS + c.y1 + 1];
+    for (int base = beg; base < end; base += 32, ++it) {
+      const int i = base + lane;
+      int idx = -1;
+      if (i < end) {
+        idx = F.cellIdx[i];
+        if (!(in_window(F.kps[idx], x, y, r, minLevel, maxLevel) && gate(idx))) idx = -1;
+      }
+      if (it < SBP_CACHE) cache[it] = idx;
+      cnt += idx >= 0;
+    }
+  }
+  nIt = it <= SBP_CACHE ? it : -1;
+  return cnt;
+}
+
 // ------------------------------------------------------------------------------------
 // K7 grid build: one CTA per frame.  Counting sort by cell, ascending keypoint index in a cell.
 // ------------------------------------------------------------------------------------
@@ -229,8 +259,8 @@ __global__ void __launch_bounds__(128) sbp_map_score_kernel(const FrameDev* fram
     }
     return true;
   };
-  int cnt = 0;
-  walk_candidates(F, x, y, rs, lvl - 1, lvl, [&](int, int idx) { if (gate(idx)) ++cnt; });
+  int cache[SBP_CACHE], nIt;
+  int cnt = walk_cached(F, x, y, rs, lvl - 1, lvl, gate, cache, nIt);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (cnt == 0) return;
@@ -245,7 +275,18 @@ __global__ void __launch_bounds__(128) sbp_map_score_kernel(const FrameDev* fram
   const uint4* dq = reinterpret_cast<const uint4*>(A.mpDesc + 32 * (size_t)q);
   const CellRange c = cell_range(F, x, y, rs);
   int pos = 0;
-  for (int ix = c.x0; ix <= c.x1; ++ix) {
+  for (int it = 0; it < nIt; ++it) {                     // replay of the cached walk (nIt = -1: walk again below)
+    const int idx = cache[it];
+    const bool ok = idx >= 0;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int d = hamming256(dq, reinterpret_cast<const uint4*>(F.desc + 32 * (size_t)idx));
+      A.cand[base + pos + __popc(m & ((1u << lane) - 1))] =
+          (uint32_t)idx | ((uint32_t)d << 16) | ((uint32_t)(F.kps[idx].octave & 0xf) << 25);
+    }
+    pos += __popc(m);
+  }
+  for (int ix = c.x0; nIt < 0 && ix <= c.x1; ++ix) {
     const int beg = F.cellStart[ix * ORBX_GRID_ROWS + c.y0], end = F.cellStart[ix * ORBX_GRID_ROWS + c.y1 + 1];
     for (int b0 = beg; b0 < end; b0 += 32) {
       const int i = b0 + lane;
@@ -390,8 +431,8 @@ __global__ void __launch_bounds__(128) sbp_frame_score_kernel(const FrameDev* fr
     }
     return true;
   };
-  int cnt = 0;
-  walk_candidates(F, u, v, radius, minL, maxL, [&](int, int idx) { if (gate(idx)) ++cnt; });
+  int cache[SBP_CACHE], nIt;
+  int cnt = walk_cached(F, u, v, radius, minL, maxL, gate, cache, nIt);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (cnt == 0) return;
@@ -405,7 +446,17 @@ __global__ void __launch_bounds__(128) sbp_frame_score_kernel(const FrameDev* fr
   const uint4* dq = reinterpret_cast<const uint4*>(A.mpDesc + 32 * (size_t)q);
   const CellRange c = cell_range(F, u, v, radius);
   int pos = 0;
-  for (int ix = c.x0; ix <= c.x1; ++ix) {
+  for (int it = 0; it < nIt; ++it) {                     // replay of the cached walk (nIt = -1: walk again below)
+    const int idx = cache[it];
+    const bool ok = idx >= 0;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int d = hamming256(dq, reinterpret_cast<const uint4*>(F.desc + 32 * (size_t)idx));
+      A.cand[base + pos + __popc(m & ((1u << lane) - 1))] = (uint32_t)idx | ((uint32_t)d << 16);
+    }
+    pos += __popc(m);
+  }
+  for (int ix = c.x0; nIt < 0 && ix <= c.x1; ++ix) {
     const int beg = F.cellStart[ix * ORBX_GRID_ROWS + c.y0], end = F.cellStart[ix * ORBX_GRID_ROWS + c.y1 + 1];
     for (int b0 = beg; b0 < end; b0 += 32) {
       const int i = b0 + lane;
