@@ -1,3 +1,7 @@
+#!/usr/bin/env python3
+"""Repeat the inertial tracker parity check on freshly created trackers (80 trials) and print every mismatch.  Written while
+chasing a rare wrong result on a cold box (a lazily allocated staging buffer zeroed by a late legacy-stream cudaMemset,
+DESIGN.md section 7); kept as a regression probe.  GPU box: python tools/flaky_probe.py"""
 import sys, os
 ROOT = "/root/repo"
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "awesome-orb-slam3-3dvisioncraft-version_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
