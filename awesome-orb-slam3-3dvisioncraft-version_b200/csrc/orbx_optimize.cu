@@ -2680,7 +2680,7 @@ __global__ void __launch_bounds__(PLF_NT, 2) pose_inertial_lf_kernel(const PlfAr
 }
 
 // =====================================================================================
-// K20/K21 driven from the tracker (SURVEY.md §8 f3 + e; src/Tracking.cc:2974-2990): the per-problem argument blocks are
+// K20/K21 driven from the tracker (SURVEY.md §8 f3 + e; src/Tracking.cc:2466-2490): the per-problem argument blocks are
 // filled ON THE DEVICE from the tracker's buffers -- the frame's body state is derived from the pose the first
 // PoseOptimization left (Frame::GetImuRotation / GetImuPosition, src/Frame.cc:534-554, float cv::Mat arithmetic:
 // ((a0*b0 + a1*b1) + a2*b2) for plain products, double accumulation where an operand is a lazy transpose) -- and the optimised state is written back as the

@@ -391,7 +391,7 @@ struct orbx_tracker {
   cudaGraphExec_t graphExec = nullptr;
   size_t graphKernels = 0;
   unsigned long long graphLaunches = 0;
-  // visual-inertial TrackLocalMap (src/Tracking.cc:2974-2990): mode 0 off, 1 LastKeyFrame, 2 LastFrame
+  // visual-inertial TrackLocalMap (src/Tracking.cc:2466-2490): mode 0 off, 1 LastKeyFrame, 2 LastFrame
   orbx_track_imu imu{};
   void* d_imuArgs = nullptr;                   // argument blocks of the inertial kernels
   double *d_imuState = nullptr, *d_imuH = nullptr;   // [S][21], [S][225] results (also readable as the next step's prior)
@@ -1053,7 +1053,7 @@ static int tracker_step_body(orbx_tracker* t, const uint8_t* d_imgs, int w, int 
   ORBX_LAUNCH(t->ctx);
   // inliers / iterations of the second optimisation land in the second halves of ninl / iters
   if (t->imu.mode) {
-    // visual-inertial TrackLocalMap (src/Tracking.cc:2974-2990): PoseInertialOptimizationLastKeyFrame / LastFrame on the
+    // visual-inertial TrackLocalMap (src/Tracking.cc:2466-2490): PoseInertialOptimizationLastKeyFrame / LastFrame on the
     // same edges; the frame's velocity, bias, the reference state and the pre-integration come from orbx_tracker_set_inertial
     if (K.imuPending) {
       ORBX_CUDA(cudaStreamWaitEvent(sb, K.evImu, 0));

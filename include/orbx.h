@@ -452,7 +452,7 @@ size_t orbx_lba_batch_device_bytes(const orbx_lba_batch *batch);
 /* Optimizer::PoseInertialOptimizationLastKeyFrame(Frame*, bool bRecInit) (src/Optimizer.cc:7665-8066;
  * vertices/edges: include/G2oTypes.h:387-491, src/G2oTypes.cc:170-220,385-407,496-520,730-812) — the
  * visual-inertial replacement of PoseOptimization that Tracking::TrackLocalMap calls when the map was
- * updated (src/Tracking.cc:2974-2990).  15 free unknowns (pose, velocity, gyro bias, acc bias of the
+ * updated (src/Tracking.cc:2466-2490).  15 free unknowns (pose, velocity, gyro bias, acc bias of the
  * frame), the last keyframe's four vertices fixed, Gauss-Newton + dense LDL^T, 4 x 10 iterations.
  *   xw/obs/inv_sigma2 : as orbx_pose_optimization (inv_sigma2 already divided by uncertainty2)
  *   close_pt[e]       : pMP->mTrackDepth < 10.f
@@ -483,7 +483,7 @@ int orbx_pose_inertial_optimization_last_keyframe_batch(
     uint8_t *outlier, double *H15, int32_t *n_ret, int32_t *iters);
 
 /* Optimizer::PoseInertialOptimizationLastFrame(Frame*, bool bRecInit) (src/Optimizer.cc:8068-8603) — what
- * Tracking::TrackLocalMap calls on every other visual-inertial frame (src/Tracking.cc:2974-2990).  The previous
+ * Tracking::TrackLocalMap calls on every other visual-inertial frame (src/Tracking.cc:2466-2490).  The previous
  * frame's four vertices are free too (30 unknowns), tied down by EdgePriorPoseImu (src/G2oTypes.cc:941-981,
  * Huber delta 5) built from pFp->mpcpi; EdgeInertial is linearised with respect to all six vertices
  * (:752-812) with bias-corrected deltas (src/ImuTypes.cc:367-394); at the end the previous frame is
@@ -542,7 +542,7 @@ orbx_tracker *orbx_tracker_create_mono(orbx_ctx *ctx, orbx_ext *ext /* max_batch
 /* 2 (stereo tracker) or 1 (monocular tracker) */
 int orbx_tracker_images_per_stream(const orbx_tracker *trk);
 
-/* Visual-inertial TrackLocalMap (BASELINE config 3; src/Tracking.cc:2974-2990): with an inertial mode bound, the SECOND
+/* Visual-inertial TrackLocalMap (BASELINE config 3; src/Tracking.cc:2466-2490): with an inertial mode bound, the SECOND
  * pose optimisation of a step is Optimizer::PoseInertialOptimizationLastKeyFrame (mode 1, src/Optimizer.cc:7665-8066)
  * or PoseInertialOptimizationLastFrame (mode 2, :8068-8603) instead of PoseOptimization, on the same edges (close_pt =
  * bit 2 of orbx_track_map::map_flags, i.e. pMP->mTrackDepth < 10).  The frame's ImuCamPose is built on the device from

@@ -133,7 +133,7 @@ void ref_frame_keys(RefFrame* r, int which, RefKeyPoint* out, uint8_t* desc) {
   }
 }
 
-// Frame::ComputeStereoMatches (src/Frame.cc:955-1133).  The stereo constructor calls it BEFORE it assigns mb (:127 vs :173:
+// Frame::ComputeStereoMatches (src/Frame.cc:955-1133).  The stereo constructor calls it BEFORE it assigns mb (:132 vs :166:
 // minZ = mb is read uninitialised there); here it runs again on the finished Frame, where mb = mbf / fx holds.
 void ref_frame_stereo_matches(RefFrame* r, float* uRight, float* depth) {
   Frame& F = *r->F;

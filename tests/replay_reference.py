@@ -184,7 +184,7 @@ def track_frame_map(ork, cam, L, R, mp, Tcw_prior, th_frame=None, th_map=1.0, nn
     idx2, exw2, eobs2, eisg2 = edges(kpmp)
     inertial = None
     if imu_mode:
-        # visual-inertial TrackLocalMap (src/Tracking.cc:2974-2990) on the same edges
+        # visual-inertial TrackLocalMap (src/Tracking.cc:2466-2490) on the same edges
         close = ((mp["map_flags"][:M][kpmp[idx2]] >> 2) & 1).astype(np.uint8)
         sc_in = dict(xw=exw2, obs=eobs2, isg=eisg2, close=close, Tcw=T1, Tcb=imu["Tcb"], Tbc=imu["Tbc"],
                      state=imu_state_from_pose(T1, imu["Tcb"], imu["velocity"], imu["bias"]), preint=imu["preint"],

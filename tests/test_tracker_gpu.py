@@ -208,7 +208,7 @@ def test_monocular_tracker_matches_oracle_chain(ctx, ork):
 @pytest.mark.parametrize("mode", [1, 2])
 def test_inertial_tracker_matches_oracle_chain(ctx, ork, mode):
     """BASELINE config 3: the second pose optimisation of the step is PoseInertialOptimizationLastKeyFrame (mode 1) /
-    LastFrame (mode 2), fed on the device from the pose the first PoseOptimization left (src/Tracking.cc:2974-2990)."""
+    LastFrame (mode 2), fed on the device from the pose the first PoseOptimization left (src/Tracking.cc:2466-2490)."""
     import orbx
     from replay_reference import track_frame_map
     S = 2
