@@ -80,3 +80,27 @@ def test_function_starts_where_cited(rel, a, sig):
     text = _lines(rel, max(a - 12, 1), a + 12)
     norm = lambda t: "".join(t.split())   # noqa: E731
     assert norm(sig) in norm(text), (rel, a, sig)
+
+
+def test_every_cited_range_exists():
+    """Every `src/File.cc:a-b` / `include/File.h:a-b` citation in the C header and the docs lies inside that file."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"((?:src|include|Thirdparty)/[A-Za-z0-9_/\.]+\.(?:cc|cpp|h|hpp)):(\d+)(?:-(\d+))?")
+    nlines = {}
+    bad, total = [], 0
+    for doc in ("include/orbx.h", "DESIGN.md", "INTEGRATION.md", "README.md"):
+        text = open(os.path.join(root, doc), errors="replace").read()
+        for m in pat.finditer(text):
+            rel, a, b = m.group(1), int(m.group(2)), int(m.group(3) or m.group(2))
+            path = os.path.join(REF, rel)
+            if not os.path.exists(path):
+                bad.append((doc, m.group(0), "no such file"))
+                continue
+            if rel not in nlines:
+                with open(path, errors="replace") as f:
+                    nlines[rel] = sum(1 for _ in f)
+            total += 1
+            if not (1 <= a <= b <= nlines[rel]):
+                bad.append((doc, m.group(0), nlines[rel]))
+    assert total > 100 and not bad, bad[:10]
